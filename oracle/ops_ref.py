@@ -1,0 +1,224 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (torch fp32/fp64) restatement of the arithmetic of
+every hot-path operator, at exactly the operator boundary the C-ABI in
+include/univs_b200.h exposes.  Each function cites the reference file:line it
+restates (paths relative to the reference tree).
+
+Parity pin: every function here is checked against the reference's OWN source files
+(loaded by path through oracle/ref_shim.py) in tests/test_oracle_vs_reference.py, and
+against the committed golden vectors in tests/golden/ (generated from the reference by
+tests/golden/make_golden.py).  The reference ships no golden vectors of its own for
+this path except the MSDeformAttn shapes of ops/test.py:24-63, which
+tests/test_oracle_vs_reference.py::test_msda_reference_test_shapes replays.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ---------------------------------------------------------------------------
+# a7: MSDeformAttn core.  ops/src/cuda/ms_deform_im2col_cuda.cuh:38-89 (bilinear),
+# :242-304 (per-output accumulation), h_im = loc_h*H - 0.5 (:290-291), zero padding
+# outside (-1, H) x (-1, W) (:293).
+# ---------------------------------------------------------------------------
+def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    """value [N,S,M,D]; spatial_shapes [[H,W]..]; sampling_loc [N,Lq,M,L,P,2] (x,y in [0,1]);
+    attn_weight [N,Lq,M,L,P]  ->  [N,Lq,M*D]"""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    shapes = [(int(h), int(w)) for h, w in spatial_shapes]
+    starts = [int(s) for s in level_start_index]
+    out = value.new_zeros(N, Lq, M, D)
+    n_idx = torch.arange(N).view(N, 1, 1, 1)
+    m_idx = torch.arange(M).view(1, 1, M, 1)
+    for l, (H, W) in enumerate(shapes):
+        v = value[:, starts[l]:starts[l] + H * W]                  # [N,HW,M,D]
+        x = sampling_loc[:, :, :, l, :, 0] * W - 0.5                # [N,Lq,M,P]
+        y = sampling_loc[:, :, :, l, :, 1] * H - 0.5
+        inside = (y > -1) & (x > -1) & (y < H) & (x < W)
+        x0 = torch.floor(x); y0 = torch.floor(y)
+        lx = x - x0; ly = y - y0
+        acc = value.new_zeros(N, Lq, M, P, D)
+        for dy, wy in ((0, 1 - ly), (1, ly)):
+            for dx, wx in ((0, 1 - lx), (1, lx)):
+                xi = (x0 + dx).long(); yi = (y0 + dy).long()
+                ok = inside & (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+                lin = (yi.clamp(0, H - 1) * W + xi.clamp(0, W - 1))  # [N,Lq,M,P]
+                g = v[n_idx, lin, m_idx]                              # [N,Lq,M,P,D]
+                acc = acc + g * (wy * wx * ok).unsqueeze(-1)
+        out = out + (acc * attn_weight[:, :, :, l].unsqueeze(-1)).sum(3)
+    return out.reshape(N, Lq, M * D)
+
+
+def encoder_reference_points(spatial_shapes):
+    """msdeformattn.py:143-155 with valid_ratios == 1 (masks are all-False, :62):
+    pixel centres normalised by the level size; identical for every level -> [Len, 2] (x,y)."""
+    pts = []
+    for H, W in spatial_shapes:
+        H = int(H); W = int(W)
+        ys = (torch.arange(H, dtype=torch.float32) + 0.5) / H
+        xs = (torch.arange(W, dtype=torch.float32) + 0.5) / W
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        pts.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+    return torch.cat(pts, 0)
+
+
+def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offs_logits, M, L, P):
+    """Fused front end of MSDeformAttn.forward (ops/modules/ms_deform_attn.py:98-117) for the
+    encoder case (queries == pixels of the level pyramid, reference points = pixel centres):
+      offs_logits [N,Len,M*L*P*3] = concat(sampling_offsets(q) [M,L,P,2], attention_weights(q) [M,L*P])
+      softmax over L*P (:101-102); loc = ref + off / (W_l, H_l) (:105-108)."""
+    N, Len, _ = offs_logits.shape
+    n_off = M * L * P * 2
+    off = offs_logits[..., :n_off].reshape(N, Len, M, L, P, 2)
+    logit = offs_logits[..., n_off:].reshape(N, Len, M, L * P)
+    w = torch.softmax(logit, -1).reshape(N, Len, M, L, P)
+    ref = encoder_reference_points(spatial_shapes).to(value)            # [Len,2]
+    norm = torch.tensor([[int(w_), int(h_)] for h_, w_ in spatial_shapes], dtype=value.dtype)
+    loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
+    return ms_deform_attn(value, spatial_shapes, level_start_index, loc, w)
+
+
+# ---------------------------------------------------------------------------
+# a2/a3: Swin (shifted-)window attention with the partition/roll/pad addressing folded in.
+# swin.py:131-171 (attention), :247-289 (pad -> roll -> partition ... reverse -> roll -> crop),
+# :413-440 (shift mask on the padded grid, -100 not -inf).
+# ---------------------------------------------------------------------------
+def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shift):
+    """qkv [B,H,W,3C] = Linear(LN(x)) on the UNPADDED token grid; pad tokens are zeros after
+    norm1 in the reference (swin.py:247-255), so their qkv equals the qkv bias.
+    rel_bias_table [(2w-1)^2, nH].  Returns the attention output (pre-proj) [B,H,W,C]."""
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    ws = window
+    d = C // num_heads
+    Hp = (H + ws - 1) // ws * ws
+    Wp = (W + ws - 1) // ws * ws
+    full = qkv_bias.view(1, 1, 1, C3).expand(B, Hp, Wp, C3).clone()
+    full[:, :H, :W] = qkv
+    if shift > 0:
+        full = torch.roll(full, shifts=(-shift, -shift), dims=(1, 2))
+    nWh, nWw = Hp // ws, Wp // ws
+    win = full.view(B, nWh, ws, nWw, ws, 3, num_heads, d).permute(5, 0, 1, 3, 6, 2, 4, 7)
+    win = win.reshape(3, B, nWh * nWw, num_heads, ws * ws, d)
+    q, k, v = win[0] * (d ** -0.5), win[1], win[2]
+    attn = q @ k.transpose(-2, -1)                                    # [B,nW,nH,N,N]
+    # relative position bias (swin.py:108-121, 148-156)
+    ar = torch.arange(ws)
+    cy, cx = torch.meshgrid(ar, ar, indexing="ij")
+    cy = cy.reshape(-1); cx = cx.reshape(-1)
+    idx = (cy[:, None] - cy[None, :] + ws - 1) * (2 * ws - 1) + (cx[:, None] - cx[None, :] + ws - 1)
+    bias = rel_bias_table[idx.reshape(-1)].view(ws * ws, ws * ws, num_heads).permute(2, 0, 1)
+    attn = attn + bias[None, None]
+    if shift > 0:
+        lab = torch.zeros(Hp, Wp)
+        cnt = 0
+        for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+                lab[hs, wsl] = cnt
+                cnt += 1
+        lab = lab.view(nWh, ws, nWw, ws).permute(0, 2, 1, 3).reshape(nWh * nWw, ws * ws)
+        m = (lab[:, None, :] != lab[:, :, None]).to(attn.dtype) * -100.0   # [nW,N,N]
+        attn = attn + m[None, :, None]
+    attn = torch.softmax(attn, -1)
+    o = attn @ v                                                      # [B,nW,nH,N,d]
+    o = o.view(B, nWh, nWw, num_heads, ws, ws, d).permute(0, 1, 4, 2, 5, 3, 6).reshape(B, Hp, Wp, C)
+    if shift > 0:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    return o[:, :H, :W].contiguous()
+
+
+# ---------------------------------------------------------------------------
+# a11: mask einsum "btqc,btchw->btqhw" then transpose(1,2)
+# (video_mask2former_transformer_decoder_univs.py:527-528)
+# ---------------------------------------------------------------------------
+def mask_einsum(mask_embed, mask_features):
+    """mask_embed [T,Q,C], mask_features [T,C,HW] -> [Q,T,HW]"""
+    return torch.einsum("tqc,tcp->qtp", mask_embed, mask_features)
+
+
+def attn_mask_from_logits(mask_logits, hw, target_hw):
+    """..._univs.py:555-566: bilinear resize (align_corners=False) of the [Q,T,H,W] logits to the
+    next level's size, sigmoid < 0.5 -> True (= key blocked).  Returns uint8 [T,Q,h*w]
+    (shared by the 8 heads -- the reference repeats it per head)."""
+    Q, T, _ = mask_logits.shape
+    H, W = hw
+    m = F.interpolate(mask_logits.view(Q, T, H, W), size=target_hw, mode="bilinear", align_corners=False)
+    m = m.permute(1, 0, 2, 3).reshape(T, Q, -1)
+    return (m.sigmoid() < 0.5).to(torch.uint8)
+
+
+# ---------------------------------------------------------------------------
+# a12/a13: multi-head attention core of nn.MultiheadAttention (post in-projection,
+# pre out-projection): torch.nn.functional.multi_head_attention_forward, called from
+# transformer_layers.py:34-44 (self) and :95-115 (cross).  Boolean mask: True = blocked
+# (-inf before softmax).  Row rule of ..._univs.py:390: a query row that is blocked
+# everywhere is un-blocked everywhere.
+# ---------------------------------------------------------------------------
+def mha_core(q, k, v, num_heads, mask=None, unmask_full_rows=False):
+    """q [B,Lq,C], k,v [B,Lk,C] (already projected; q NOT yet scaled), mask uint8/bool
+    [B or 1, Lq, Lk] with 1 = blocked.  Returns [B,Lq,C]."""
+    B, Lq, C = q.shape
+    Lk = k.shape[1]
+    d = C // num_heads
+    qh = q.view(B, Lq, num_heads, d).transpose(1, 2) * (d ** -0.5)
+    kh = k.view(B, Lk, num_heads, d).transpose(1, 2)
+    vh = v.view(B, Lk, num_heads, d).transpose(1, 2)
+    s = qh @ kh.transpose(-2, -1)                                     # [B,h,Lq,Lk]
+    if mask is not None:
+        mb = mask.bool()
+        if unmask_full_rows:
+            mb = mb & ~mb.all(-1, keepdim=True)
+        s = s.masked_fill(mb[:, None], float("-inf"))
+    p = torch.softmax(s, -1)
+    return (p @ vh).transpose(1, 2).reshape(B, Lq, C)
+
+
+# ---------------------------------------------------------------------------
+# a14: ProCA attention core (..._univs.py:456-496): every prompt query (per frame)
+# attends to [its own token ; its L prompt-memory tokens]; q-len 1.
+# ---------------------------------------------------------------------------
+def proca_core(q, k_self, v_self, k_mem, v_mem, num_heads):
+    """q,k_self,v_self [P,T,C]; k_mem,v_mem [P,Tm,L,C] with Tm in {1,T}.  Returns [P,T,C]."""
+    P, T, C = q.shape
+    L = k_mem.shape[2]
+    km = k_mem.expand(P, T, L, C)
+    vm = v_mem.expand(P, T, L, C)
+    k = torch.cat([k_self.unsqueeze(2), km], 2).reshape(P * T, 1 + L, C)
+    v = torch.cat([v_self.unsqueeze(2), vm], 2).reshape(P * T, 1 + L, C)
+    return mha_core(q.reshape(P * T, 1, C), k, v, num_heads).view(P, T, C)
+
+
+# ---------------------------------------------------------------------------
+# a10: sine position encodings
+# ---------------------------------------------------------------------------
+def pos2d_sine(h, w, num_pos_feats=128, temperature=10000.0):
+    """mask2former/modeling/transformer_decoder/position_encoding.py:29-52, normalize=True -> [2*npf,h,w]"""
+    eps, scale = 1e-6, 2 * math.pi
+    y = torch.arange(1, h + 1, dtype=torch.float32).view(h, 1).expand(h, w)
+    x = torch.arange(1, w + 1, dtype=torch.float32).view(1, w).expand(h, w)
+    y = y / (h + eps) * scale
+    x = x / (w + eps) * scale
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    px = x[:, :, None] / dim_t
+    py = y[:, :, None] / dim_t
+    px = torch.stack((px[:, :, 0::2].sin(), px[:, :, 1::2].cos()), 3).flatten(2)
+    py = torch.stack((py[:, :, 0::2].sin(), py[:, :, 1::2].cos()), 3).flatten(2)
+    return torch.cat((py, px), 2).permute(2, 0, 1)
+
+
+def pos3d_sine_arbitrary_t(frame_indices, h, w, num_pos_feats=128, temperature=10000.0, num_max_frames=128):
+    """univs/modeling/transformer_decoder/position_encoding.py:142-169 -> [T, 2*npf, h, w]"""
+    base = pos2d_sine(h, w, num_pos_feats, temperature)              # [C,h,w] (same y/x terms)
+    z = frame_indices.to(torch.float32) / num_max_frames * (2 * math.pi)   # [T]
+    dim_z = torch.arange(num_pos_feats * 2, dtype=torch.float32)
+    dim_z = temperature ** (2 * torch.div(dim_z, 2, rounding_mode="trunc") / (num_pos_feats * 2))
+    pz = z[:, None] / dim_z
+    pz = torch.stack((pz[:, 0::2].sin(), pz[:, 1::2].cos()), 2).flatten(1)   # [T,C]
+    return base[None] + pz[:, :, None, None]
