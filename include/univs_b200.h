@@ -1,0 +1,104 @@
+/* univs_b200 -- C ABI of the B200 (sm_100a) hot-path kernels of the UniVS per-clip forward.
+ *
+ * Every entry point is stream-ordered (no internal synchronisation, no allocation), takes
+ * plain device pointers + sizes, borrows its inputs and writes into caller-owned outputs.
+ * Return value: 0 on success, a negative UNIVS_E_* code otherwise; univs_b200_last_error()
+ * returns a human-readable message for the last failure on the calling thread.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *
+ * Reference interfaces replaced (paths relative to the MinghanLi/UniVS tree):
+ *   mask2former/modeling/pixel_decoder/ops/src/ms_deform_attn.h:25-44      (ms_deform_attn_forward)
+ *   mask2former/modeling/pixel_decoder/ops/src/cuda/ms_deform_im2col_cuda.cuh:928-959
+ *   mask2former/modeling/backbone/swin.py:131-171, 247-289                  (window attention + addressing)
+ *   univs/modeling/transformer_decoder/video_mask2former_transformer_decoder_univs.py:527  (mask einsum)
+ *   ...:555-566 (attention-mask generation), :390 (fully-blocked-row rule)
+ *   univs/modeling/transformer_decoder/transformer_layers.py:34-44, 95-115  (MHA cores)
+ *   ...video_mask2former_transformer_decoder_univs.py:456-496                (ProCA)
+ */
+#ifndef UNIVS_B200_H_
+#define UNIVS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNIVS_OK 0
+#define UNIVS_E_BADARG (-1)   /* invalid size / null pointer / unsupported shape      */
+#define UNIVS_E_LAUNCH (-2)   /* cudaGetLastError() != cudaSuccess after the launch   */
+#define UNIVS_E_NOTIMPL (-3)  /* entry point exported for ABI parity, not implemented */
+
+/* precision of the tensor-core contractions inside the attention kernels */
+#define UNIVS_PREC_TF32X3 0   /* 3xTF32 split (fp32-equivalent products), default */
+#define UNIVS_PREC_TF32 1     /* single TF32 product, round-to-nearest operands   */
+
+const char* univs_b200_last_error(void);
+int univs_b200_abi_version(void);
+
+/* ---- MSDeformAttn forward (a7).  Mirrors ms_deformable_im2col_cuda (ms_deform_im2col_cuda.cuh:928-942):
+ * value [N,S,M,D] f32, spatial_shapes [L,2] i64 (H,W), level_start_index [L] i64,
+ * sampling_loc [N,Lq,M,L,P,2] f32 (x,y in [0,1]), attn_weight [N,Lq,M,L,P] f32 -> out [N,Lq,M*D] f32. */
+int univs_ms_deform_attn_forward_f32(void* stream, const float* value, const int64_t* spatial_shapes,
+                                     const int64_t* level_start_index, const float* sampling_loc,
+                                     const float* attn_weight, int batch, int spatial_size, int num_heads,
+                                     int channels, int num_levels, int num_query, int num_point, float* out);
+
+/* Exported for ABI parity with ms_deform_attn_backward (ms_deform_attn.h:46-66); training is out of scope. */
+int univs_ms_deform_attn_backward_f32(void);
+
+/* ---- MSDeformAttn forward with the encoder front end fused (ms_deform_attn.py:98-117): queries are the
+ * pixels of the level pyramid (Lq == S, reference point = pixel centre, msdeformattn.py:143-155);
+ * offs_logits [N,S,M*L*P*3] = [sampling_offsets(q) (M,L,P,2) | attention_weights(q) (M,L*P)] raw linear outputs;
+ * the kernel applies softmax over L*P and loc = ref + off/(W_l,H_l).  D must be 32. */
+int univs_ms_deform_attn_encoder_f32(void* stream, const float* value, const int64_t* spatial_shapes,
+                                     const int64_t* level_start_index, const float* offs_logits, int batch,
+                                     int spatial_size, int num_heads, int num_levels, int num_point, float* out);
+
+/* ---- Swin (shifted-)window attention, addressing folded in (a2,a3).
+ * qkv [B,H,W,3C] f32 = Linear(LN(x)) on the unpadded token grid; qkv_bias [3C] (value of pad tokens);
+ * rel_bias_table [(2*window-1)^2, num_heads]; head_dim = C/num_heads must be 32; window in {7,12} (or any <=12);
+ * shift = 0 or window/2.  out [B,H,W,C] f32 (pre output projection). */
+int univs_swin_window_attention_f32(void* stream, const float* qkv, const float* qkv_bias,
+                                    const float* rel_bias_table, int batch, int height, int width, int channels,
+                                    int num_heads, int window, int shift, int precision, float* out);
+
+/* ---- Mask einsum "btqc,btchw->btqhw" + transpose(1,2) (a11).
+ * mask_embed [T,Q,C] f32; mask_features channel-last [T,HW,C] f32; out [Q,T,HW] f32.  C % 32 == 0, Q <= 256.
+ * Operands are rounded to nearest TF32, products accumulate in fp32. */
+int univs_mask_einsum_f32(void* stream, const float* mask_embed, const float* mask_features_cl, int frames,
+                          int queries, int channels, int pixels, float* out);
+
+/* ---- Attention-mask bits from mask logits (a11, ..._univs.py:555-566 + :390).
+ * logits [Q,T,H,W] f32; target (h,w) with H % h == 0 and W % w == 0 and even ratios (bilinear
+ * align_corners=False then equals the mean of the 2x2 centre pixels of each cell);
+ * bits [T,Q,words] u32, words = ceil(h*w/32), bit k of word j set <=> key 32*j+k is BLOCKED (sigmoid<0.5);
+ * row_open [T,Q] i32 = 1 if at least one key of the row is allowed. */
+int univs_attn_mask_bits_f32(void* stream, const float* logits, int queries, int frames, int height, int width,
+                             int tgt_h, int tgt_w, uint32_t* bits, int32_t* row_open);
+
+/* ---- Multi-head attention core (a12 masked cross-attention, a13 spatio-temporal self-attention).
+ * q [B,Lq,C], k,v [B,Lk,C] f32, already in-projected (q unscaled), head_dim 32, heads = C/32.
+ * mask_bits (nullable) [Bm,Lq,ceil(Lk/32)] u32, Bm in {1,B}, bit set = blocked;
+ * row_open (nullable) [Bm,Lq] i32: rows with 0 ignore the mask (..._univs.py:390).
+ * workspace: >= univs_mha_workspace_bytes(...) bytes of device scratch (split-K partials).
+ * out [B,Lq,C] f32 (pre output projection). */
+int64_t univs_mha_workspace_bytes(int batch, int len_q, int len_k, int channels);
+int univs_mha_forward_f32(void* stream, const float* q, const float* k, const float* v, const uint32_t* mask_bits,
+                          const int32_t* row_open, int mask_batch, int batch, int len_q, int len_k, int channels,
+                          int precision, void* workspace, float* out);
+
+/* ---- ProCA attention core (a14): every (prompt p, frame t) query attends to its own token and its L
+ * prompt-memory tokens.  q,k_self,v_self [P,T,C]; k_mem,v_mem [P,Tm,L,C], Tm in {1,T}; out [P,T,C]. */
+int univs_proca_forward_f32(void* stream, const float* q, const float* k_self, const float* v_self,
+                            const float* k_mem, const float* v_mem, int prompts, int frames, int mem_frames,
+                            int mem_len, int channels, float* out);
+
+/* ---- helpers ---- */
+/* in-place/out-of-place round-to-nearest-even to TF32 (19-bit) of n floats */
+int univs_round_tf32_f32(void* stream, const float* in, float* out, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIVS_B200_H_ */

@@ -1,0 +1,194 @@
+"""Parity tests proper: every CUDA kernel, called through the C ABI, against the CPU oracle (oracle/ops_ref.py) on
+seeded inputs.  Tolerances: relative max-error  max|a-b| / max|b|  per tensor; 1e-3 is the north-star
+bound, the kernels are held to tighter bounds where their arithmetic allows it."""
+import pytest
+import torch
+
+from oracle import ops_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from univs_b200 import ops
+    return ops
+
+
+def _lsi(shapes):
+    out = [0]
+    for h, w in shapes[:-1]:
+        out.append(out[-1] + h * w)
+    return out
+
+
+# ------------------------------------------------------------------ MSDeformAttn
+@pytest.mark.parametrize("shapes,N,M,D,P,Lq", [
+    ([(6, 4), (3, 2)], 1, 2, 2, 2, 2),          # the reference's own test shapes (ops/test.py:24-31)
+    ([(5, 7), (10, 14), (20, 27)], 2, 8, 32, 4, None),
+    ([(23, 40), (46, 80), (92, 160)], 1, 8, 32, 4, 300),
+    ([(3, 3)], 2, 3, 5, 3, 7),                    # D not a multiple of 4 -> scalar kernel
+    ([(4, 4), (2, 2)], 1, 4, 64, 1, 5),
+])
+def test_msda_forward_reference_abi(ops, shapes, N, M, D, P, Lq):
+    torch.manual_seed(3)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    Lq = S if Lq is None else Lq
+    value = torch.randn(N, S, M, D)
+    loc = torch.rand(N, Lq, M, L, P, 2) * 1.5 - 0.25       # includes samples outside [0,1]
+    w = torch.rand(N, Lq, M, L, P) + 1e-5
+    w = w / w.sum((-1, -2), keepdim=True)
+    want = ops_ref.ms_deform_attn(value, shapes, _lsi(shapes), loc, w)
+    got = ops.ms_deform_attn_forward(value.cuda(), shapes, _lsi(shapes), loc.cuda(), w.cuda())
+    assert _rel(got, want) < 2e-6
+    # device-resident level tables (the reference passes CUDA int64 tensors)
+    sh_d = torch.as_tensor(shapes, dtype=torch.long).cuda()
+    ls_d = torch.as_tensor(_lsi(shapes), dtype=torch.long).cuda()
+    got2 = ops.ms_deform_attn_forward(value.cuda(), sh_d, ls_d, loc.cuda(), w.cuda())
+    assert torch.equal(got, got2)
+
+
+def test_msda_empty_and_bad_args(ops):
+    from univs_b200._cabi import UnivsB200Error
+    shapes = [(2, 2)]
+    v = torch.randn(1, 4, 8, 32).cuda()
+    out = ops.ms_deform_attn_forward(v, shapes, [0], torch.zeros(1, 0, 8, 1, 4, 2).cuda(), torch.zeros(1, 0, 8, 1, 4).cuda())
+    assert out.shape == (1, 0, 256)
+    with pytest.raises(UnivsB200Error):    # sum(H*W) != S
+        ops.ms_deform_attn_forward(v, [(3, 3)], [0], torch.zeros(1, 2, 8, 1, 4, 2).cuda(), torch.zeros(1, 2, 8, 1, 4).cuda())
+
+
+@pytest.mark.parametrize("shapes", [[(3, 5), (6, 10), (12, 20)], [(15, 27), (30, 54), (60, 108)]])
+def test_msda_encoder_fused(ops, shapes):
+    torch.manual_seed(5)
+    N, M = 2, 8
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(N, S, M, 32)
+    ol = torch.cat([torch.randn(N, S, M * 3 * 4 * 2) * 3.0, torch.randn(N, S, M * 12) * 2.0], -1).contiguous()
+    want = ops_ref.ms_deform_attn_fused(value, shapes, _lsi(shapes), ol, M, 3, 4)
+    got = ops.ms_deform_attn_encoder(value.cuda(), shapes, _lsi(shapes), ol.cuda())
+    assert _rel(got, want) < 5e-6
+
+
+# ------------------------------------------------------------------ Swin window attention
+@pytest.mark.parametrize("B,H,W,nH,ws,shift", [
+    (2, 8, 12, 2, 4, 0), (2, 8, 12, 2, 4, 2), (1, 7, 10, 3, 4, 2),
+    (2, 14, 21, 3, 7, 0), (2, 13, 9, 1, 7, 3), (1, 30, 54, 6, 7, 3),
+    (1, 24, 36, 2, 12, 0), (2, 24, 27, 4, 12, 6), (1, 46, 80, 6, 12, 6),
+])
+@pytest.mark.parametrize("prec,tol", [(0, 2e-5), (1, 2e-3)])
+def test_swin_window_attention(ops, B, H, W, nH, ws, shift, prec, tol):
+    torch.manual_seed(7)
+    C = 32 * nH
+    qkv = torch.randn(B, H, W, 3 * C)
+    bias = torch.randn(3 * C) * 0.3
+    table = torch.randn((2 * ws - 1) ** 2, nH) * 0.5
+    want = ops_ref.swin_window_attention(qkv, bias, table, nH, ws, shift)
+    got = ops.swin_window_attention(qkv.cuda(), bias.cuda(), table.cuda(), nH, ws, shift, precision=prec)
+    assert _rel(got, want) < tol
+
+
+# ------------------------------------------------------------------ mask einsum + attention-mask bits
+@pytest.mark.parametrize("T,Q,C,HW", [(1, 20, 256, 64 * 64), (2, 100, 256, 30 * 54), (3, 200, 256, 46 * 80),
+                                        (1, 232, 256, 130), (2, 7, 64, 66), (1, 256, 32, 2)])
+def test_mask_einsum(ops, T, Q, C, HW):
+    torch.manual_seed(11)
+    E = torch.randn(T, Q, C)
+    F = torch.randn(T, HW, C)
+    want = ops_ref.mask_einsum(E.double(), F.transpose(1, 2).double()).float()
+    got = ops.mask_einsum(E.cuda(), F.cuda())
+    assert got.shape == (Q, T, HW)
+    # operands rounded to nearest TF32 (2^-12 relative each), fp32 accumulation
+    assert _rel(got, want) < 4e-4
+
+
+def test_mask_einsum_linearity_full_size(ops):
+    """Size-independent property at the north-star size (T=5,Q=200,C=256,184x320): einsum(E1+E2,F) == einsum(E1,F)+einsum(E2,F)
+    up to TF32 rounding, and a column checksum against an fp64 reduction on the device."""
+    torch.manual_seed(12)
+    T, Q, C, HW = 5, 200, 256, 184 * 320
+    F = torch.randn(T, HW, C, device="cuda")
+    E1 = torch.randn(T, Q, C, device="cuda")
+    E2 = torch.randn(T, Q, C, device="cuda")
+    o1, o2, o12 = ops.mask_einsum(E1, F), ops.mask_einsum(E2, F), ops.mask_einsum(E1 + E2, F)
+    assert _rel(o12, o1 + o2) < 1e-3
+    # checksum of checksums: sum_p out[q,t,p] == E[t,q,:] . sum_p F[t,p,:]
+    colsum = F.double().sum(1)                                  # [T,C]
+    want = torch.einsum("tqc,tc->qt", E1.double(), colsum)
+    got = o1.double().sum(-1)
+    assert (got - want).abs().max().item() / want.abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("Q,T,H,W,tgt", [(5, 2, 16, 24, (8, 12)), (5, 2, 16, 24, (4, 6)), (7, 3, 16, 24, (2, 3)),
+                                           (20, 1, 64, 64, (32, 32)), (3, 1, 8, 8, (1, 1))])
+def test_attn_mask_bits(ops, Q, T, H, W, tgt):
+    torch.manual_seed(13)
+    logits = torch.randn(Q, T, H * W)
+    logits[1] = logits[1].abs() * -1 - 0.1          # a query blocked everywhere -> row_open == 0
+    want = ops_ref.attn_mask_from_logits(logits, (H, W), tgt)                 # [T,Q,S] uint8
+    bits, row_open = ops.attn_mask_bits(logits.cuda(), (H, W), tgt)
+    S = tgt[0] * tgt[1]
+    b = bits.cpu().to(torch.int64) & 0xFFFFFFFF
+    unpacked = ((b.unsqueeze(-1) >> torch.arange(32)) & 1).flatten(-2)[..., :S].to(torch.uint8)
+    assert torch.equal(unpacked, want)
+    assert torch.equal(row_open.cpu().bool(), ~(want.bool().all(-1)))
+    assert not row_open.cpu()[:, 1].any()
+
+
+# ------------------------------------------------------------------ MHA core / ProCA
+@pytest.mark.parametrize("B,Lq,Lk,masked", [(3, 11, 37, True), (5, 200, 920, True), (2, 100, 6480, True),
+                                             (1, 1000, 1000, True), (1, 300, 130, False), (2, 1, 65, True)])
+@pytest.mark.parametrize("prec,tol", [(0, 2e-5), (1, 2e-3)])
+def test_mha_core(ops, B, Lq, Lk, masked, prec, tol):
+    torch.manual_seed(17)
+    C = 256
+    q, k, v = torch.randn(B, Lq, C), torch.randn(B, Lk, C), torch.randn(B, Lk, C)
+    mask = None
+    if masked:
+        mask = torch.rand(B, Lq, Lk) < 0.7
+        mask[0, min(4, Lq - 1)] = True             # fully blocked row -> un-blocked (..._univs.py:390)
+        mask[-1, 0, : Lk // 2] = True
+    want = ops_ref.mha_core(q, k, v, 8, None if mask is None else mask.to(torch.uint8), unmask_full_rows=True)
+    if masked:
+        bits = ops.pack_mask_bits(mask.cuda())
+        row_open = (~mask.all(-1)).to(torch.int32).cuda()
+        got = ops.mha_core(q.cuda(), k.cuda(), v.cuda(), bits, row_open, precision=prec)
+    else:
+        got = ops.mha_core(q.cuda(), k.cuda(), v.cuda(), precision=prec)
+    assert _rel(got, want) < tol
+
+
+def test_mha_shared_mask_batch1(ops):
+    torch.manual_seed(18)
+    q, k, v = torch.randn(1, 50, 256), torch.randn(1, 50, 256), torch.randn(1, 50, 256)
+    mask = torch.ones(50, 50, dtype=torch.bool)
+    mask[:30, :30] = False
+    mask[30:, 30:] = False
+    want = ops_ref.mha_core(q, k, v, 8, mask[None].to(torch.uint8))
+    got = ops.mha_core(q.cuda(), k.cuda(), v.cuda(), ops.pack_mask_bits(mask[None].cuda()))
+    assert _rel(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("P,T,Tm,L", [(4, 3, 3, 6), (10, 5, 1, 1408), (40, 2, 1, 1), (32, 10, 10, 78), (3, 2, 1, 2)])
+def test_proca_core(ops, P, T, Tm, L):
+    torch.manual_seed(19)
+    C = 256
+    q, ks, vs = torch.randn(P, T, C), torch.randn(P, T, C), torch.randn(P, T, C)
+    km, vm = torch.randn(P, Tm, L, C), torch.randn(P, Tm, L, C)
+    want = ops_ref.proca_core(q, ks, vs, km, vm, 8)
+    got = ops.proca_core(q.cuda(), ks.cuda(), vs.cuda(), km.cuda(), vm.cuda())
+    assert _rel(got, want) < 1e-5
+
+
+def test_round_tf32(ops):
+    x = torch.randn(1000).cuda()
+    y = ops.round_tf32(x)
+    assert (y.view(torch.int32) & 0x1FFF).eq(0).all()
+    assert (y - x).abs().max() <= x.abs().max() * 2 ** -11

@@ -1,0 +1,56 @@
+"""ctypes binding of the C ABI declared in include/univs_b200.h (one symbol per kernel entry point)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libunivs_b200.so")
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+
+# name -> (restype, argtypes); must list every function declared in include/univs_b200.h
+SIGNATURES = {
+    "univs_b200_last_error": (C.c_char_p, []),
+    "univs_b200_abi_version": (_i, []),
+    "univs_ms_deform_attn_forward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "univs_ms_deform_attn_backward_f32": (_i, []),
+    "univs_ms_deform_attn_encoder_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "univs_swin_window_attention_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "univs_mask_einsum_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "univs_attn_mask_bits_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "univs_mha_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "univs_mha_forward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "univs_proca_forward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "univs_round_tf32_f32": (_i, [_vp, _vp, _vp, _i64]),
+}
+
+_lib = None
+
+
+class UnivsB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libunivs_b200.so (built by univs_b200/csrc/build.sh or __graft_entry__.build()).
+    Fails loudly if it is missing: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UnivsB200Error(
+                f"{LIB_PATH} not found: build it with `bash univs_b200/csrc/build.sh` "
+                "(there is no CPU / PyTorch fallback for the hot-path kernels)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().univs_b200_last_error().decode("utf-8", "replace")
+        raise UnivsB200Error(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,306 @@
+// Multi-scale deformable attention forward for sm_100a.
+//
+// Replaces ms_deformable_im2col_gpu_kernel (reference ops/src/cuda/ms_deform_im2col_cuda.cuh:242-304,
+// bilinear helper :38-89, launcher :928-959).  The op is a gather: per (query, head) 12 samples x 4 corners
+// x 128 B head vectors; it is bound by L2/HBM bandwidth, not FLOPs, so the design is:
+//   * 8 lanes x float4 cover the 32 channels of a head  -> every corner is one 128-bit load per lane and
+//     one fully-used 128 B line per (sample corner);
+//   * all 48 corner loads of a thread are unconditional (clamped index, zeroed weight) so they are issued
+//     back-to-back (memory-level parallelism instead of the reference's dependent branchy loads);
+//   * offsets / logits are read as 128-bit broadcast loads; softmax over L*P and the sampling-location
+//     arithmetic of MSDeformAttn.forward (ops/modules/ms_deform_attn.py:101-108) are fused in the
+//     encoder variant, so loc/weight tensors are never materialised.
+#include "common.cuh"
+
+namespace univs {
+
+constexpr int kMaxLevels = 8;
+struct LevelTable {
+  int H[kMaxLevels];
+  int W[kMaxLevels];
+  int start[kMaxLevels];
+};
+
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  acc.x = fmaf(w, v.x, acc.x);
+  acc.y = fmaf(w, v.y, acc.y);
+  acc.z = fmaf(w, v.z, acc.z);
+  acc.w = fmaf(w, v.w, acc.w);
+}
+
+// One bilinear sample of a 4-channel slice.  `base` points at channel slice of pixel (0,0) of the level;
+// pix_stride = M*D floats.  Semantics of ms_deform_attn_im2col_bilinear (:38-89) + the in-range test (:293).
+__device__ __forceinline__ void sample4(float4& acc, const float* __restrict__ base, int pix_stride, int H, int W,
+                                        float x, float y, float aw) {
+  const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+  const float xf = floorf(x), yf = floorf(y);
+  const int x0 = (int)xf, y0 = (int)yf;
+  const float lx = x - xf, ly = y - yf;
+  const float hx = 1.f - lx, hy = 1.f - ly;
+  const bool x0ok = x0 >= 0, x1ok = x0 + 1 <= W - 1, y0ok = y0 >= 0, y1ok = y0 + 1 <= H - 1;
+  const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+  const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+  const float w1 = (inside && y0ok && x0ok) ? hy * hx : 0.f;
+  const float w2 = (inside && y0ok && x1ok) ? hy * lx : 0.f;
+  const float w3 = (inside && y1ok && x0ok) ? ly * hx : 0.f;
+  const float w4 = (inside && y1ok && x1ok) ? ly * lx : 0.f;
+  const float4 v1 = ldg_f4(base + (size_t)(yc0 * W + xc0) * pix_stride);
+  const float4 v2 = ldg_f4(base + (size_t)(yc0 * W + xc1) * pix_stride);
+  const float4 v3 = ldg_f4(base + (size_t)(yc1 * W + xc0) * pix_stride);
+  const float4 v4 = ldg_f4(base + (size_t)(yc1 * W + xc1) * pix_stride);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  fma4(s, w1, v1);
+  fma4(s, w2, v2);
+  fma4(s, w3, v3);
+  fma4(s, w4, v4);
+  fma4(acc, aw, s);
+}
+
+__device__ __forceinline__ float sample1(const float* __restrict__ base, int pix_stride, int H, int W, float x,
+                                         float y) {
+  if (!((y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W))) return 0.f;
+  const float xf = floorf(x), yf = floorf(y);
+  const int x0 = (int)xf, y0 = (int)yf;
+  const float lx = x - xf, ly = y - yf, hx = 1.f - lx, hy = 1.f - ly;
+  float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+  if (y0 >= 0 && x0 >= 0) v1 = __ldg(base + (size_t)(y0 * W + x0) * pix_stride);
+  if (y0 >= 0 && x0 + 1 <= W - 1) v2 = __ldg(base + (size_t)(y0 * W + x0 + 1) * pix_stride);
+  if (y0 + 1 <= H - 1 && x0 >= 0) v3 = __ldg(base + (size_t)((y0 + 1) * W + x0) * pix_stride);
+  if (y0 + 1 <= H - 1 && x0 + 1 <= W - 1) v4 = __ldg(base + (size_t)((y0 + 1) * W + x0 + 1) * pix_stride);
+  return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+}
+
+// ---- reference-ABI kernel: explicit sampling_loc / attn_weight tensors, any L, P; D % 4 == 0 ------------
+__global__ void __launch_bounds__(256)
+msda_generic_vec4_kernel(const float* __restrict__ value, LevelTable lt, const float* __restrict__ loc,
+                         const float* __restrict__ aw, int N, int S, int M, int D, int L, int Lq, int P,
+                         float* __restrict__ out) {
+  const int groups = D >> 2;
+  const long long total = (long long)N * Lq * M * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % groups);
+    const long long pair = idx / groups;  // (n*Lq + q)*M + m
+    const int m = (int)(pair % M);
+    const int n = (int)(pair / ((long long)M * Lq));
+    const float* lp = loc + pair * (L * P * 2);
+    const float* wp = aw + pair * (L * P);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int pix_stride = M * D;
+    for (int l = 0; l < L; ++l) {
+      const int H = lt.H[l], W = lt.W[l];
+      const float* base = value + ((size_t)n * S + lt.start[l]) * pix_stride + m * D + cg * 4;
+      for (int p = 0; p < P; ++p) {
+        const float lx = __ldg(lp + (l * P + p) * 2), ly = __ldg(lp + (l * P + p) * 2 + 1);
+        const float w = __ldg(wp + l * P + p);
+        sample4(acc, base, pix_stride, H, W, lx * W - 0.5f, ly * H - 0.5f, w);
+      }
+    }
+    *reinterpret_cast<float4*>(out + pair * D + cg * 4) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+msda_generic_scalar_kernel(const float* __restrict__ value, LevelTable lt, const float* __restrict__ loc,
+                           const float* __restrict__ aw, int N, int S, int M, int D, int L, int Lq, int P,
+                           float* __restrict__ out) {
+  const long long total = (long long)N * Lq * M * D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % D);
+    const long long pair = idx / D;
+    const int m = (int)(pair % M);
+    const int n = (int)(pair / ((long long)M * Lq));
+    const float* lp = loc + pair * (L * P * 2);
+    const float* wp = aw + pair * (L * P);
+    float acc = 0.f;
+    const int pix_stride = M * D;
+    for (int l = 0; l < L; ++l) {
+      const int H = lt.H[l], W = lt.W[l];
+      const float* base = value + ((size_t)n * S + lt.start[l]) * pix_stride + m * D + c;
+      for (int p = 0; p < P; ++p) {
+        const float lx = __ldg(lp + (l * P + p) * 2), ly = __ldg(lp + (l * P + p) * 2 + 1);
+        acc += __ldg(wp + l * P + p) * sample1(base, pix_stride, H, W, lx * W - 0.5f, ly * H - 0.5f);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// ---- encoder kernel: D = 32, queries = pyramid pixels, softmax + location arithmetic fused ---------------
+// 8 lanes per (n, q, m); a 256-thread CTA covers 32 consecutive (q, m) pairs = 4 queries x 8 heads.
+template <int L, int P>
+__global__ void __launch_bounds__(256)
+msda_encoder_kernel(const float* __restrict__ value, LevelTable lt, const float* __restrict__ ol, int N, int S,
+                    int M, float* __restrict__ out) {
+  constexpr int LP = L * P;
+  static_assert((LP * 2) % 4 == 0 && LP % 4 == 0, "vector loads need L*P % 4 == 0");
+  const int lane8 = threadIdx.x & 7;
+  const long long pair = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (pair >= (long long)N * S * M) return;
+  const int m = (int)(pair % M);
+  const long long nq = pair / M;
+  const int q = (int)(nq % S);
+  const int n = (int)(nq / S);
+
+  int lq = 0;
+#pragma unroll
+  for (int l = 1; l < L; ++l)
+    if (q >= lt.start[l]) lq = l;
+  const int rel = q - lt.start[lq];
+  const int qy = rel / lt.W[lq], qx = rel - qy * lt.W[lq];
+  const float refx = ((float)qx + 0.5f) / (float)lt.W[lq];
+  const float refy = ((float)qy + 0.5f) / (float)lt.H[lq];
+
+  const float* row = ol + nq * (long long)(M * LP * 3);
+  float off[LP * 2], lg[LP];
+  {
+    const float4* po = reinterpret_cast<const float4*>(row + m * (LP * 2));
+#pragma unroll
+    for (int i = 0; i < LP * 2 / 4; ++i) {
+      const float4 t = __ldg(po + i);
+      off[4 * i] = t.x; off[4 * i + 1] = t.y; off[4 * i + 2] = t.z; off[4 * i + 3] = t.w;
+    }
+    const float4* pl = reinterpret_cast<const float4*>(row + M * LP * 2 + m * LP);
+#pragma unroll
+    for (int i = 0; i < LP / 4; ++i) {
+      const float4 t = __ldg(pl + i);
+      lg[4 * i] = t.x; lg[4 * i + 1] = t.y; lg[4 * i + 2] = t.z; lg[4 * i + 3] = t.w;
+    }
+  }
+  float mx = lg[0];
+#pragma unroll
+  for (int i = 1; i < LP; ++i) mx = fmaxf(mx, lg[i]);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LP; ++i) {
+    lg[i] = expf(lg[i] - mx);
+    sum += lg[i];
+  }
+  const float inv = 1.f / sum;
+
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int pix_stride = M * 32;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int H = lt.H[l], W = lt.W[l];
+    const float* base = value + ((size_t)n * S + lt.start[l]) * pix_stride + m * 32 + lane8 * 4;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float locx = refx + off[(l * P + p) * 2] / (float)W;
+      const float locy = refy + off[(l * P + p) * 2 + 1] / (float)H;
+      sample4(acc, base, pix_stride, H, W, locx * (float)W - 0.5f, locy * (float)H - 0.5f, lg[l * P + p] * inv);
+    }
+  }
+  *reinterpret_cast<float4*>(out + pair * 32 + lane8 * 4) = acc;
+}
+
+static int fill_levels(LevelTable& lt, const int64_t* shapes_h, const int64_t* lsi_h, int L) {
+  for (int l = 0; l < L; ++l) {
+    lt.H[l] = (int)shapes_h[2 * l];
+    lt.W[l] = (int)shapes_h[2 * l + 1];
+    lt.start[l] = (int)lsi_h[l];
+  }
+  return 0;
+}
+
+}  // namespace univs
+
+using namespace univs;
+
+// spatial_shapes / level_start_index are DEVICE pointers in the reference ABI (ms_deform_attn_cuda.cu:25-32
+// receives CUDA tensors).  They are tiny (L <= 8 rows); to stay stream-ordered without a device->host sync
+// we accept either kind of pointer and resolve it with cudaPointerGetAttributes: host memory is read
+// directly, device memory is copied with a blocking 64-byte cudaMemcpy only when it is not host-accessible.
+static int load_small_i64(const int64_t* p, int n, int64_t* dst) {
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    for (int i = 0; i < n; ++i) dst[i] = p[i];
+    return 0;
+  }
+  if (attr.type == cudaMemoryTypeDevice) {
+    e = cudaMemcpy(dst, p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      set_error("cudaMemcpy of level table failed: %s", cudaGetErrorString(e));
+      return UNIVS_E_LAUNCH;
+    }
+  } else {
+    for (int i = 0; i < n; ++i) dst[i] = p[i];
+  }
+  return 0;
+}
+
+extern "C" int univs_ms_deform_attn_forward_f32(void* stream, const float* value, const int64_t* spatial_shapes,
+                                                const int64_t* level_start_index, const float* sampling_loc,
+                                                const float* attn_weight, int batch, int spatial_size,
+                                                int num_heads, int channels, int num_levels, int num_query,
+                                                int num_point, float* out) {
+  UNIVS_REQUIRE(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
+                "ms_deform_attn_forward: null pointer");
+  UNIVS_REQUIRE(batch >= 0 && spatial_size >= 0 && num_query >= 0, "ms_deform_attn_forward: negative size");
+  UNIVS_REQUIRE(num_heads > 0 && channels > 0 && num_point > 0, "ms_deform_attn_forward: bad head/channel/point");
+  UNIVS_REQUIRE(num_levels > 0 && num_levels <= kMaxLevels, "ms_deform_attn_forward: num_levels must be 1..%d",
+                kMaxLevels);
+  if (batch == 0 || num_query == 0) return UNIVS_OK;
+  int64_t sh[2 * kMaxLevels], ls[kMaxLevels];
+  int rc = load_small_i64(spatial_shapes, 2 * num_levels, sh);
+  if (rc) return rc;
+  rc = load_small_i64(level_start_index, num_levels, ls);
+  if (rc) return rc;
+  LevelTable lt;
+  fill_levels(lt, sh, ls, num_levels);
+  long long tot = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    UNIVS_REQUIRE(lt.H[l] > 0 && lt.W[l] > 0, "ms_deform_attn_forward: empty level %d", l);
+    tot += (long long)lt.H[l] * lt.W[l];
+  }
+  UNIVS_REQUIRE(tot == spatial_size, "ms_deform_attn_forward: sum(H*W)=%lld != spatial_size=%d", tot, spatial_size);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (channels % 4 == 0) {
+    const long long total = (long long)batch * num_query * num_heads * (channels / 4);
+    const int grid = (int)min((total + 255) / 256, (long long)148 * 64);
+    msda_generic_vec4_kernel<<<grid, 256, 0, st>>>(value, lt, sampling_loc, attn_weight, batch, spatial_size,
+                                                   num_heads, channels, num_levels, num_query, num_point, out);
+  } else {
+    const long long total = (long long)batch * num_query * num_heads * channels;
+    const int grid = (int)min((total + 255) / 256, (long long)148 * 64);
+    msda_generic_scalar_kernel<<<grid, 256, 0, st>>>(value, lt, sampling_loc, attn_weight, batch, spatial_size,
+                                                     num_heads, channels, num_levels, num_query, num_point, out);
+  }
+  return check_launch("ms_deform_attn_forward");
+}
+
+extern "C" int univs_ms_deform_attn_backward_f32(void) {
+  set_error("ms_deform_attn_backward: training path is out of scope (inference-only build)");
+  return UNIVS_E_NOTIMPL;
+}
+
+extern "C" int univs_ms_deform_attn_encoder_f32(void* stream, const float* value, const int64_t* spatial_shapes,
+                                                const int64_t* level_start_index, const float* offs_logits,
+                                                int batch, int spatial_size, int num_heads, int num_levels,
+                                                int num_point, float* out) {
+  UNIVS_REQUIRE(value && spatial_shapes && level_start_index && offs_logits && out,
+                "ms_deform_attn_encoder: null pointer");
+  UNIVS_REQUIRE(num_levels == 3 && num_point == 4,
+                "ms_deform_attn_encoder: only L=3, P=4 is instantiated (got L=%d P=%d)", num_levels, num_point);
+  UNIVS_REQUIRE(num_heads > 0 && batch >= 0 && spatial_size >= 0, "ms_deform_attn_encoder: bad sizes");
+  if (batch == 0 || spatial_size == 0) return UNIVS_OK;
+  int64_t sh[2 * kMaxLevels], ls[kMaxLevels];
+  int rc = load_small_i64(spatial_shapes, 2 * num_levels, sh);
+  if (rc) return rc;
+  rc = load_small_i64(level_start_index, num_levels, ls);
+  if (rc) return rc;
+  LevelTable lt;
+  fill_levels(lt, sh, ls, num_levels);
+  long long tot = 0;
+  for (int l = 0; l < num_levels; ++l) tot += (long long)lt.H[l] * lt.W[l];
+  UNIVS_REQUIRE(tot == spatial_size, "ms_deform_attn_encoder: sum(H*W)=%lld != spatial_size=%d", tot, spatial_size);
+  const long long pairs = (long long)batch * spatial_size * num_heads;
+  const long long grid = (pairs + 31) / 32;
+  UNIVS_REQUIRE(grid < (1ll << 31), "ms_deform_attn_encoder: problem too large");
+  msda_encoder_kernel<3, 4><<<(int)grid, 256, 0, (cudaStream_t)stream>>>(value, lt, offs_logits, batch,
+                                                                         spatial_size, num_heads, out);
+  return check_launch("ms_deform_attn_encoder");
+}

@@ -1,0 +1,178 @@
+"""Tensor-level wrappers of the hot-path kernels.  Inputs must be contiguous fp32 CUDA tensors; each wrapper
+allocates the output with torch (device memory plumbing), passes raw pointers and torch's current CUDA stream
+through the C ABI and returns immediately (stream-ordered, no synchronisation).  No CPU path exists."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check, lib
+
+PREC_TF32X3 = 0
+PREC_TF32 = 1
+
+_default_precision = PREC_TF32X3
+
+
+def set_attention_precision(p: int):
+    global _default_precision
+    assert p in (PREC_TF32X3, PREC_TF32)
+    _default_precision = p
+
+
+def _stream():
+    if not torch.cuda.is_available():
+        raise _cabi.UnivsB200Error("no CUDA device: the hot-path operators have no CPU fallback")
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise _cabi.UnivsB200Error(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise _cabi.UnivsB200Error(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _cabi.UnivsB200Error(f"{name}: expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def _levels(spatial_shapes, level_start_index):
+    sh = np.ascontiguousarray(np.asarray(spatial_shapes, dtype=np.int64).reshape(-1, 2))
+    ls = np.ascontiguousarray(np.asarray(level_start_index, dtype=np.int64).reshape(-1))
+    return sh, ls
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    """value [N,S,M,D], sampling_loc [N,Lq,M,L,P,2], attn_weight [N,Lq,M,L,P] -> [N,Lq,M*D]
+    (MSDA.ms_deform_attn_forward, reference ops/src/vision.cpp:18-21).  spatial_shapes / level_start_index may
+    be CUDA int64 tensors (reference ABI) or host sequences."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    out = torch.empty((N, Lq, M * D), device=value.device, dtype=torch.float32)
+    if torch.is_tensor(spatial_shapes) and spatial_shapes.is_cuda:
+        shp, lsp = _chk(spatial_shapes, "spatial_shapes", torch.int64), _chk(level_start_index, "level_start_index", torch.int64)
+        keep = None
+    else:
+        sh, ls = _levels(torch.as_tensor(spatial_shapes).cpu().numpy() if torch.is_tensor(spatial_shapes) else spatial_shapes,
+                         torch.as_tensor(level_start_index).cpu().numpy() if torch.is_tensor(level_start_index) else level_start_index)
+        shp, lsp, keep = sh.ctypes.data, ls.ctypes.data, (sh, ls)
+    rc = lib().univs_ms_deform_attn_forward_f32(_stream(), _chk(value, "value"), shp, lsp, _chk(sampling_loc, "sampling_loc"),
+                                                _chk(attn_weight, "attn_weight"), N, S, M, D, L, Lq, P, out.data_ptr())
+    check(rc, "ms_deform_attn_forward")
+    del keep
+    return out
+
+
+def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits, num_levels=3, num_points=4):
+    """value [N,S,M,32]; offs_logits [N,S,M*L*P*3] raw linear outputs -> [N,S,M*32]"""
+    N, S, M, D = value.shape
+    assert D == 32 and offs_logits.shape == (N, S, M * num_levels * num_points * 3)
+    sh, ls = _levels(spatial_shapes, level_start_index)
+    out = torch.empty((N, S, M * D), device=value.device, dtype=torch.float32)
+    rc = lib().univs_ms_deform_attn_encoder_f32(_stream(), _chk(value, "value"), sh.ctypes.data, ls.ctypes.data,
+                                                _chk(offs_logits, "offs_logits"), N, S, M, num_levels, num_points,
+                                                out.data_ptr())
+    check(rc, "ms_deform_attn_encoder")
+    return out
+
+
+def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shift, precision=None):
+    """qkv [B,H,W,3C] -> [B,H,W,C] (see include/univs_b200.h)"""
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    out = torch.empty((B, H, W, C), device=qkv.device, dtype=torch.float32)
+    rc = lib().univs_swin_window_attention_f32(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
+                                               _chk(rel_bias_table, "rel_bias_table"), B, H, W, C, num_heads, window,
+                                               shift, _default_precision if precision is None else precision,
+                                               out.data_ptr())
+    check(rc, "swin_window_attention")
+    return out
+
+
+def mask_einsum(mask_embed, mask_features_cl, out=None):
+    """mask_embed [T,Q,C], mask_features_cl [T,HW,C] (channel-last) -> [Q,T,HW]"""
+    T, Q, Cc = mask_embed.shape
+    HW = mask_features_cl.shape[1]
+    if out is None:
+        out = torch.empty((Q, T, HW), device=mask_embed.device, dtype=torch.float32)
+    rc = lib().univs_mask_einsum_f32(_stream(), _chk(mask_embed, "mask_embed"), _chk(mask_features_cl, "mask_features"),
+                                     T, Q, Cc, HW, _chk(out, "out"))
+    check(rc, "mask_einsum")
+    return out
+
+
+def attn_mask_bits(mask_logits, hw, target_hw):
+    """mask_logits [Q,T,H*W] -> (bits uint32-as-int32 [T,Q,words], row_open int32 [T,Q])"""
+    Q, T, _ = mask_logits.shape
+    H, W = hw
+    h, w = target_hw
+    words = (h * w + 31) // 32
+    bits = torch.empty((T, Q, words), device=mask_logits.device, dtype=torch.int32)
+    row_open = torch.empty((T, Q), device=mask_logits.device, dtype=torch.int32)
+    rc = lib().univs_attn_mask_bits_f32(_stream(), _chk(mask_logits, "mask_logits"), Q, T, H, W, h, w,
+                                        bits.data_ptr(), row_open.data_ptr())
+    check(rc, "attn_mask_bits")
+    return bits, row_open
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
+        _ws_cache[key] = ws
+    return ws
+
+
+def mha_core(q, k, v, mask_bits=None, row_open=None, precision=None):
+    """q [B,Lq,C], k,v [B,Lk,C] (projected, q unscaled); mask_bits int32 [Bm,Lq,ceil(Lk/32)] (bit set = blocked)."""
+    B, Lq, Cc = q.shape
+    Lk = k.shape[1]
+    out = torch.empty_like(q)
+    nbytes = lib().univs_mha_workspace_bytes(B, Lq, Lk, Cc)
+    ws = _workspace(nbytes, q.device)
+    mb = 0 if mask_bits is None else mask_bits.shape[0]
+    rc = lib().univs_mha_forward_f32(
+        _stream(), _chk(q, "q"), _chk(k, "k"), _chk(v, "v"),
+        None if mask_bits is None else _chk(mask_bits, "mask_bits", torch.int32),
+        None if row_open is None else _chk(row_open, "row_open", torch.int32),
+        mb, B, Lq, Lk, Cc, _default_precision if precision is None else precision, ws.data_ptr(), out.data_ptr())
+    check(rc, "mha_forward")
+    return out
+
+
+def proca_core(q, k_self, v_self, k_mem, v_mem):
+    """q,k_self,v_self [P,T,C]; k_mem,v_mem [P,Tm,L,C] -> [P,T,C]"""
+    P, T, Cc = q.shape
+    Tm, L = k_mem.shape[1], k_mem.shape[2]
+    out = torch.empty_like(q)
+    rc = lib().univs_proca_forward_f32(_stream(), _chk(q, "q"), _chk(k_self, "k_self"), _chk(v_self, "v_self"),
+                                       _chk(k_mem, "k_mem"), _chk(v_mem, "v_mem"), P, T, Tm, L, Cc, out.data_ptr())
+    check(rc, "proca_forward")
+    return out
+
+
+def round_tf32(x, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    rc = lib().univs_round_tf32_f32(_stream(), _chk(x, "x"), _chk(out, "out"), x.numel())
+    check(rc, "round_tf32")
+    return out
+
+
+def pack_mask_bits(mask_bool):
+    """Host-side helper: bool [..., Lk] (True = blocked) -> int32 words [..., ceil(Lk/32)] (torch ops; used once per
+    clip for the static self-attention mask)."""
+    Lk = mask_bool.shape[-1]
+    words = (Lk + 31) // 32
+    pad = words * 32 - Lk
+    m = torch.nn.functional.pad(mask_bool.to(torch.int64), (0, pad), value=1)
+    m = m.view(*mask_bool.shape[:-1], words, 32)
+    weights = (1 << torch.arange(32, device=mask_bool.device, dtype=torch.int64))
+    packed = (m * weights).sum(-1)
+    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed)
+    return packed.to(torch.int32).contiguous()
