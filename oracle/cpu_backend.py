@@ -1,0 +1,70 @@
+"""TEST / BASELINE INFRASTRUCTURE (tests/, bench.py cpu_baseline and --impl reference legs only): runs the product's host-side model with every hot-path operator replaced by its CPU oracle
+(oracle/ops_ref.py), by monkeypatching `univs_b200.ops` for the duration of a `with` block.  This lets the host
+logic (addressing, layouts, prompt plumbing, state_dict mapping) be checked against the reference on a machine
+without a GPU.  The product package itself contains no such switch and no CPU code path."""
+import contextlib
+
+import torch
+
+from oracle import ops_ref
+from univs_b200 import ops
+
+
+def unpack_bits(bits, n):
+    b = bits.to(torch.int64) & 0xFFFFFFFF
+    return ((b.unsqueeze(-1) >> torch.arange(32, device=bits.device)) & 1).flatten(-2)[..., :n].to(torch.uint8)
+
+
+def _swin(qkv, qkv_bias, table, num_heads, window, shift, precision=None):
+    return ops_ref.swin_window_attention(qkv, qkv_bias, table, num_heads, window, shift)
+
+
+def _msda_enc(value, shapes, starts, offs_logits, num_levels=3, num_points=4):
+    return ops_ref.ms_deform_attn_fused(value, shapes, starts, offs_logits, value.shape[2], num_levels, num_points)
+
+
+def _msda_fwd(value, shapes, starts, loc, w):
+    sh = shapes.tolist() if torch.is_tensor(shapes) else shapes
+    st = starts.tolist() if torch.is_tensor(starts) else starts
+    return ops_ref.ms_deform_attn(value, sh, st, loc, w)
+
+
+def _einsum(mask_embed, feats_cl, out=None):
+    r = ops_ref.mask_einsum(mask_embed, feats_cl.transpose(1, 2))
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r.contiguous()
+
+
+def _bits(mask_logits, hw, target_hw):
+    m = ops_ref.attn_mask_from_logits(mask_logits, hw, target_hw)          # [T,Q,S] uint8
+    return ops.pack_mask_bits(m.bool()), (~m.bool().all(-1)).to(torch.int32)
+
+
+def _mha(q, k, v, mask_bits=None, row_open=None, precision=None):
+    mask = None
+    if mask_bits is not None:
+        mask = unpack_bits(mask_bits, k.shape[1])
+    return ops_ref.mha_core(q, k, v, q.shape[-1] // 32, mask, unmask_full_rows=row_open is not None)
+
+
+def _proca(q, ks, vs, km, vm):
+    return ops_ref.proca_core(q, ks, vs, km, vm, q.shape[-1] // 32)
+
+
+_PATCH = {"swin_window_attention": _swin, "ms_deform_attn_encoder": _msda_enc, "ms_deform_attn_forward": _msda_fwd,
+          "mask_einsum": _einsum, "attn_mask_bits": _bits, "mha_core": _mha, "proca_core": _proca,
+          "round_tf32": lambda x, out=None: x}
+
+
+@contextlib.contextmanager
+def oracle_ops():
+    saved = {k: getattr(ops, k) for k in _PATCH}
+    try:
+        for k, f in _PATCH.items():
+            setattr(ops, k, f)
+        yield
+    finally:
+        for k, f in saved.items():
+            setattr(ops, k, f)

@@ -1,0 +1,99 @@
+"""Host-logic parity on CPU: the product modules (operators swapped for their CPU oracles, tests/oracle_backend.py)
+against the reference's own modules executed by path, with identical key-seeded weights and inputs.
+Also checks state_dict key/shape compatibility."""
+import pytest
+import torch
+
+from oracle import ref_shim
+from tests import model_factory as mf
+from oracle.cpu_backend import oracle_ops
+
+pytestmark = pytest.mark.reference
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _build_pair(swin, T, Q, **kw):
+    clip = mf.make_clip_emb()
+    rbb, rpix, rdec = ref_shim.build_reference_model(swin, num_queries=Q, num_frames=T, clip_emb=clip, **kw)
+    pbb, ppix, pdec = mf.build_product_model(swin, num_queries=Q, num_frames=T, clip_emb=clip, **kw)
+    for r, p in ((rbb, pbb), (rpix, ppix), (rdec, pdec)):
+        rsd, psd = r.state_dict(), p.state_dict()
+        assert set(rsd) == set(psd), (sorted(set(rsd) - set(psd))[:5], sorted(set(psd) - set(rsd))[:5])
+        for k in rsd:
+            assert rsd[k].shape == psd[k].shape, k
+        sd = mf.keyed_state_dict(rsd)
+        r.load_state_dict(sd)
+        p.load_state_dict(sd)
+    return (rbb, rpix, rdec), (pbb, ppix, pdec)
+
+
+@pytest.mark.parametrize("swin,H,W", [(mf.TINY_SWIN, 64, 96), (mf.SMALL_SWIN7, 96, 160)])
+def test_detection_no_prompts(swin, H, W):
+    torch.manual_seed(0)
+    T, Q = 2, 10
+    ref, prod = _build_pair(swin, T, Q, enc_layers=2, dec_layers=4)
+    x = torch.randn(T, 3, H, W)
+    tg = lambda: [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual",
+                   "frame_indices": torch.tensor([3, 4])}]
+    rf, (rmf, rms), rout = ref_shim.reference_clip_forward(*ref, x, tg())
+    prod[2].return_aux_outputs = True
+    with oracle_ops():
+        pf, (pmf, pms), pout = mf.product_clip_forward(*prod, x, tg())
+    for k in rf:
+        assert pf[k].shape == rf[k].shape
+        assert _rel(pf[k], rf[k]) < 1e-4, k
+    assert _rel(pmf, rmf) < 1e-4
+    for a, b in zip(pms, rms):
+        assert _rel(a, b) < 1e-4
+    assert pout["pred_masks"].shape == rout["pred_masks"].shape
+    assert _rel(pout["pred_masks"], rout["pred_masks"]) < 1e-3
+    assert _rel(pout["pred_logits"], rout["pred_logits"]) < 1e-3
+    assert _rel(pout["pred_embds"], rout["pred_embds"]) < 1e-3
+    assert len(pout["aux_outputs"]) == len(rout["aux_outputs"])
+    for pa, ra in zip(pout["aux_outputs"], rout["aux_outputs"]):
+        assert _rel(pa["pred_masks"], ra["pred_masks"]) < 1e-3
+        assert _rel(pa["pred_logits"], ra["pred_logits"]) < 1e-3
+        assert _rel(pa["pred_embds"], ra["pred_embds"]) < 1e-3
+
+
+@pytest.mark.parametrize("l2v", [False, True])
+def test_detection_category_prompts_proca(l2v):
+    """task=detection, prompt_type=text: one prompt query per category of the dataset, ProCA with L=1."""
+    torch.manual_seed(1)
+    T, Q = 2, 6
+    ref, prod = _build_pair(mf.TINY_SWIN, T, Q, enc_layers=1, dec_layers=3, text_prompt_to_image_enable=l2v)
+    x = torch.randn(T, 3, 64, 64)
+    tg = lambda: [{"task": "detection", "dataset_name": "bdd_track", "prompt_type": "text",
+                   "frame_indices": torch.arange(T)}]
+    _, _, rout = ref_shim.reference_clip_forward(*ref, x, tg())
+    with oracle_ops():
+        _, _, pout = mf.product_clip_forward(*prod, x, tg())
+    assert pout["pred_masks"].shape == rout["pred_masks"].shape == (1, Q + 8, T, 16, 16)
+    assert _rel(pout["pred_masks"], rout["pred_masks"]) < 1e-3
+    assert _rel(pout["pred_logits"], rout["pred_logits"]) < 1e-3
+    assert _rel(pout["pred_embds"], rout["pred_embds"]) < 1e-3
+
+
+@pytest.mark.parametrize("l2v", [False, True])
+def test_grounding_text_prompts(l2v):
+    torch.manual_seed(2)
+    T, Q, P = 2, 6, 3
+    ref, prod = _build_pair(mf.TINY_SWIN, T, Q, enc_layers=1, dec_layers=3, text_prompt_to_image_enable=l2v,
+                            self_attn_mask_type="sep-blocked")
+    x = torch.randn(T, 3, 64, 64)
+    words, sent = torch.randn(P, 77, T, 640), torch.randn(P, T, 640)
+    tg = lambda: [{"task": "grounding", "dataset_name": "refytvos", "prompt_type": "text",
+                   "frame_indices": torch.arange(T), "exp_word_feats": words.clone(),
+                   "exp_sentence_feats": sent.clone(), "exp_word_len": torch.full((P,), 10)}]
+    _, _, rout = ref_shim.reference_clip_forward(*ref, x, tg())
+    with oracle_ops():
+        _, _, pout = mf.product_clip_forward(*prod, x, tg())
+    assert pout["pred_masks"].shape == rout["pred_masks"].shape == (1, Q + P, T, 16, 16)
+    assert pout["pred_logits"].shape == rout["pred_logits"].shape == (1, Q + P, P)
+    assert _rel(pout["pred_masks"], rout["pred_masks"]) < 1e-3
+    assert _rel(pout["pred_logits"], rout["pred_logits"]) < 1e-3
+    assert _rel(pout["pred_reid_logits"], rout["pred_reid_logits"]) < 1e-3
+    assert _rel(pout["pred_embds"], rout["pred_embds"]) < 1e-3

@@ -47,7 +47,7 @@ def test_msda_forward_reference_abi(ops, shapes, N, M, D, P, Lq):
     w = w / w.sum((-1, -2), keepdim=True)
     want = ops_ref.ms_deform_attn(value, shapes, _lsi(shapes), loc, w)
     got = ops.ms_deform_attn_forward(value.cuda(), shapes, _lsi(shapes), loc.cuda(), w.cuda())
-    assert _rel(got, want) < 2e-6
+    assert _rel(got, want) < 2e-5
     # device-resident level tables (the reference passes CUDA int64 tensors)
     sh_d = torch.as_tensor(shapes, dtype=torch.long).cuda()
     ls_d = torch.as_tensor(_lsi(shapes), dtype=torch.long).cuda()

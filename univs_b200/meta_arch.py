@@ -1,0 +1,108 @@
+"""UniVS_Prompt meta-architecture, inference side (univs/univs_prompt.py:66-490).
+
+Registered under the reference's name so `MODEL.META_ARCHITECTURE: UniVS_Prompt` resolves here.  It owns
+`backbone` and `sem_seg_head` (the two calls every task head makes, e.g. inference_video_vis_fast.py:232-236) and the
+non-persistent `pixel_mean` / `pixel_std` buffers (:169-170).  `forward(batched_inputs)` keeps the input contract
+(list of one dict with "image": list of T [3,H,W] tensors, "height", "width", "task", "dataset_name", ...) and runs
+ONE clip through normalise -> pad to a multiple of 32 (ImageList.from_tensors semantics) -> backbone -> sem_seg_head.
+The sliding-window task heads, trackers and result writers of univs/inference/* are callers of this path and out of
+scope this round; `forward` therefore returns the per-clip decoder output dict.
+
+Frame sharding (new capability): with a process group of n ranks, rank r runs backbone + pixel decoder
+on frames {f : f mod n == r}; one all-gather reassembles the three multi-scale maps and mask_features; the decoder
+then runs on every rank."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .registry import META_ARCH_REGISTRY, build_backbone, build_sem_seg_head
+from .sharding import FrameSharder
+
+
+@META_ARCH_REGISTRY.register()
+class UniVS_Prompt(nn.Module):
+    def __init__(self, cfg=None, *, backbone=None, sem_seg_head=None, pixel_mean=None, pixel_std=None,
+                 size_divisibility=32, num_frames=5, process_group=None):
+        super().__init__()
+        if cfg is not None:
+            backbone = build_backbone(cfg)
+            sem_seg_head = build_sem_seg_head(cfg, backbone.output_shape())
+            pixel_mean, pixel_std = cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD
+            size_divisibility = cfg.MODEL.MASK_FORMER.SIZE_DIVISIBILITY
+            num_frames = cfg.INPUT.SAMPLING_FRAME_NUM
+        self.backbone = backbone
+        self.sem_seg_head = sem_seg_head
+        if size_divisibility < 0:
+            size_divisibility = self.backbone.size_divisibility
+        self.size_divisibility = size_divisibility
+        self.num_frames = num_frames
+        self.register_buffer("pixel_mean", torch.tensor(pixel_mean, dtype=torch.float32).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.tensor(pixel_std, dtype=torch.float32).view(-1, 1, 1), False)
+        self.sharder = FrameSharder(process_group)
+        self.eval()
+
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    # ---- pre-processing: (x - mean) / std, right/bottom zero pad to a multiple of size_divisibility
+    def preprocess(self, frames):
+        """frames: [T,3,H,W] uint8/float (RGB) or a list of [3,H,W].  Returns ([T,3,Hp,Wp] float32, (H, W))."""
+        if isinstance(frames, (list, tuple)):
+            frames = torch.stack([f.to(self.device, non_blocking=True) for f in frames])
+        else:
+            frames = frames.to(self.device, non_blocking=True)
+        x = (frames.float() - self.pixel_mean) / self.pixel_std
+        H, W = x.shape[-2:]
+        d = self.size_divisibility
+        Hp, Wp = (H + d - 1) // d * d, (W + d - 1) // d * d
+        if (Hp, Wp) != (H, W):
+            x = F.pad(x, (0, Wp - W, 0, Hp - H), value=0.0)
+        return x, (H, W)
+
+    @torch.no_grad()
+    def clip_forward(self, frames, targets):
+        """One clip through the hot path.  frames [T,3,H,W] (any device / dtype), targets list[dict] (mutated in
+        place by the prompt sampler, as in the reference)."""
+        x, image_size = self.preprocess(frames)
+        targets[0].setdefault("inter_image_size", tuple(x.shape[-2:]))
+        targets[0].setdefault("image_size", image_size)
+        targets[0].setdefault("num_frames", x.shape[0])
+        if "frame_indices" in targets[0]:
+            targets[0]["frame_indices"] = targets[0]["frame_indices"].to(self.device)
+        if self.sharder.world_size == 1:
+            features = self.backbone(x)
+            return self.sem_seg_head(features, targets=targets)
+        # frame-sharded: local frames -> backbone -> pixel decoder -> all-gather -> decoder
+        local = self.sharder.local_frames(x)
+        features = self.backbone(local)
+        pd = self.sem_seg_head.pixel_decoder
+        mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(features)
+        # exchange in storage order (channel-last), hand NCHW views back to the decoder
+        gathered = self.sharder.all_gather_frames(
+            [t.permute(0, 2, 3, 1) for t in [mask_features] + list(multi_scale)], x.shape[0])
+        gathered = [t.permute(0, 3, 1, 2) for t in gathered]
+        mask_features, multi_scale = gathered[0], gathered[1:]
+        return self.sem_seg_head.predictor(multi_scale, mask_features, mask_features, None, targets)
+
+    def forward(self, batched_inputs):
+        if self.training:
+            raise NotImplementedError("training is out of scope for the B200 hot-path build")
+        assert len(batched_inputs) == 1, "inference processes one video at a time (univs_prompt.py:421)"
+        inp = batched_inputs[0]
+        frames = inp["image"]
+        T = len(frames)
+        task = inp.get("task", "detection")
+        prompt_type = "text" if task == "grounding" else ("visual" if task in ("detection", "sot") else "visual")
+        tg = {"task": task, "dataset_name": inp.get("dataset_name", "ytvis21"), "prompt_type": inp.get("prompt_type", prompt_type),
+              "frame_indices": inp.get("frame_indices", torch.arange(T)), "num_frames": T,
+              "video_len": inp.get("video_len", T), "file_names": inp.get("file_names", [""] * T)}
+        for k in ("masks", "boxes", "ids", "first_appear_frame_idxs", "first_frame_idx", "exp_word_feats",
+                  "exp_sentence_feats", "exp_word_len"):
+            if k in inp:
+                tg[k] = inp[k]
+        out = self.clip_forward(frames, [tg])
+        out.pop("aux_outputs", None)
+        return out

@@ -1,0 +1,212 @@
+"""MSDeformAttn pixel decoder, B200-native host side.
+
+Drop-in for mask2former/modeling/pixel_decoder/msdeformattn.py::MSDeformAttnPixelDecoder (:166-360): same ctor
+kwargs / from_config, same state_dict keys, `forward_features(features)` returns
+`(mask_features, out[-1], out[0], multi_scale_features)` with the reference's NCHW shapes.
+
+Underneath: the 6 encoder layers run on one token-major tensor [N, Len, 256]; per layer the `sampling_offsets` and
+`attention_weights` linears are one fused 256->288 GEMM whose raw output feeds `ms_deform_attn_encoder` (softmax over
+L*P, reference-point and sampling-location arithmetic fused into the gather kernel -- no loc/weight tensors);
+the FPN level runs channels-last so that `mask_features` is produced channel-last ([N,HW,C] storage) -- the layout
+the mask einsum consumes -- and is returned as an NCHW *view* of that storage.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..registry import SEM_SEG_HEADS_REGISTRY, is_cfg
+from . import position
+
+
+class _MSDeformAttnParams(nn.Module):
+    """Key names of ops/modules/ms_deform_attn.py:34-80; init per :63-80."""
+
+    def __init__(self, d_model, n_levels, n_heads, n_points):
+        super().__init__()
+        self.n_levels, self.n_heads, self.n_points = n_levels, n_heads, n_points
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        nn.init.zeros_(self.sampling_offsets.weight)
+        th = torch.arange(n_heads, dtype=torch.float32) * (2.0 * np.pi / n_heads)
+        grid = torch.stack([th.cos(), th.sin()], -1)
+        grid = (grid / grid.abs().max(-1, keepdim=True)[0]).view(n_heads, 1, 1, 2).repeat(1, n_levels, n_points, 1)
+        for i in range(n_points):
+            grid[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias.copy_(grid.view(-1))
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+        nn.init.xavier_uniform_(self.value_proj.weight)
+        nn.init.zeros_(self.value_proj.bias)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.zeros_(self.output_proj.bias)
+        self._fused = None
+
+    def fused_offs_logits(self):
+        """[sampling_offsets ; attention_weights] as one (288 x 256) GEMM; rebuilt if parameters were replaced."""
+        key = (self.sampling_offsets.weight.data_ptr(), self.attention_weights.weight.data_ptr(),
+               self.sampling_offsets.weight._version, self.attention_weights.weight._version)
+        if self._fused is None or self._fused[0] != key:
+            w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0).contiguous()
+            b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0).contiguous()
+            self._fused = (key, w, b)
+        return self._fused[1], self._fused[2]
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, d_model, d_ffn, n_levels, n_heads, n_points):
+        super().__init__()
+        self.self_attn = _MSDeformAttnParams(d_model, n_levels, n_heads, n_points)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward(self, src, pos, shapes, starts):
+        a = self.self_attn
+        N, S, C = src.shape
+        value = a.value_proj(src).view(N, S, a.n_heads, C // a.n_heads)
+        w, b = a.fused_offs_logits()
+        offs_logits = F.linear(src + pos, w, b)
+        y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points)
+        src = self.norm1(src + a.output_proj(y))
+        return self.norm2(src + self.linear2(F.relu(self.linear1(src))))
+
+
+class _Encoder(nn.Module):
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+
+
+class _EncoderOnly(nn.Module):
+    """Key names of MSDeformAttnTransformerEncoderOnly (msdeformattn.py:23-48): encoder.layers.{i}.*, level_embed."""
+
+    def __init__(self, d_model, nhead, num_layers, d_ffn, n_levels, n_points=4):
+        super().__init__()
+        self.encoder = _Encoder([_EncoderLayer(d_model, d_ffn, n_levels, nhead, n_points) for _ in range(num_layers)])
+        self.level_embed = nn.Parameter(torch.empty(n_levels, d_model))
+        for n_, p in self.named_parameters():
+            if p.dim() > 1 and "self_attn" not in n_:
+                nn.init.xavier_uniform_(p)
+        nn.init.normal_(self.level_embed)
+
+
+class _ConvNorm(nn.Conv2d):
+    """detectron2.layers.Conv2d key layout: weight[, bias], norm.{weight,bias}; forward = conv -> norm -> act."""
+
+    def __init__(self, cin, cout, k, padding=0, bias=True, norm=None, act=None):
+        super().__init__(cin, cout, k, padding=padding, bias=bias)
+        self.norm = norm
+        self.act = act
+
+    def forward(self, x):
+        x = F.conv2d(x, self.weight, self.bias, self.stride, self.padding)
+        if self.norm is not None:
+            x = self.norm(x)
+        return self.act(x) if self.act is not None else x
+
+
+@SEM_SEG_HEADS_REGISTRY.register()
+class MSDeformAttnPixelDecoder(nn.Module):
+    def __init__(self, input_shape, *args, **kwargs):
+        super().__init__()
+        if is_cfg(input_shape):                      # @configurable: (cfg, input_shape)
+            kwargs = self.from_config(input_shape, *args)
+            input_shape = kwargs.pop("input_shape")
+        self._build(input_shape, **kwargs)
+
+    @classmethod
+    def from_config(cls, cfg, input_shape):
+        """msdeformattn.py:296-314"""
+        h = cfg.MODEL.SEM_SEG_HEAD
+        return dict(input_shape={k: v for k, v in input_shape.items() if k in h.IN_FEATURES},
+                    conv_dim=h.CONVS_DIM, mask_dim=h.MASK_DIM, norm=h.NORM,
+                    transformer_dropout=cfg.MODEL.MASK_FORMER.DROPOUT, transformer_nheads=cfg.MODEL.MASK_FORMER.NHEADS,
+                    transformer_dim_feedforward=1024, transformer_enc_layers=h.TRANSFORMER_ENC_LAYERS,
+                    transformer_in_features=h.DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES, common_stride=h.COMMON_STRIDE)
+
+    def _build(self, input_shape, *, transformer_dropout, transformer_nheads, transformer_dim_feedforward,
+               transformer_enc_layers, conv_dim, mask_dim, norm=None, transformer_in_features, common_stride):
+        shapes = sorted(input_shape.items(), key=lambda kv: kv[1].stride)
+        self.in_features = [k for k, _ in shapes]
+        self.feature_channels = [v.channels for _, v in shapes]
+        tshapes = [(k, v) for k, v in shapes if k in transformer_in_features]
+        self.transformer_in_features = [k for k, _ in tshapes]
+        tstrides = [v.stride for _, v in tshapes]
+        self.transformer_num_feature_levels = len(tshapes)
+        if conv_dim != 32 * transformer_nheads:
+            raise ValueError("the B200 MSDeformAttn kernel requires head_dim == 32")
+        self.input_proj = nn.ModuleList(
+            nn.Sequential(nn.Conv2d(v.channels, conv_dim, kernel_size=1), nn.GroupNorm(32, conv_dim))
+            for _, v in tshapes[::-1])
+        for proj in self.input_proj:
+            nn.init.xavier_uniform_(proj[0].weight, gain=1)
+            nn.init.zeros_(proj[0].bias)
+        self.transformer = _EncoderOnly(conv_dim, transformer_nheads, transformer_enc_layers,
+                                        transformer_dim_feedforward, self.transformer_num_feature_levels)
+        self.mask_dim, self.conv_dim = mask_dim, conv_dim
+        self.mask_features = _ConvNorm(conv_dim, mask_dim, 1)
+        self.maskformer_num_feature_levels = 3
+        self.common_stride = common_stride
+        self.num_fpn_levels = int(np.log2(min(tstrides)) - np.log2(common_stride))
+        use_bias = norm == ""
+        mk_norm = (lambda: nn.GroupNorm(32, conv_dim)) if norm == "GN" else (lambda: None)
+        if norm not in ("", "GN", None):
+            raise ValueError(f"unsupported norm {norm!r}")
+        lateral, output = [], []
+        for idx, cin in enumerate(self.feature_channels[:self.num_fpn_levels]):
+            lat = _ConvNorm(cin, conv_dim, 1, bias=use_bias, norm=mk_norm())
+            outc = _ConvNorm(conv_dim, conv_dim, 3, padding=1, bias=use_bias, norm=mk_norm(), act=F.relu)
+            self.add_module(f"adapter_{idx + 1}", lat)
+            self.add_module(f"layer_{idx + 1}", outc)
+            lateral.append(lat)
+            output.append(outc)
+        for m in [self.mask_features] + lateral + output:
+            nn.init.kaiming_uniform_(m.weight, a=1)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        self.lateral_convs, self.output_convs = lateral[::-1], output[::-1]
+        self.eval()
+
+    @torch.no_grad()
+    def forward_features(self, features):
+        """msdeformattn.py:316-360.  Frames are the batch dim; nothing here mixes frames."""
+        tokens, poss, shapes = [], [], []
+        for idx, f in enumerate(self.transformer_in_features[::-1]):      # res5, res4, res3
+            x = features[f].float()
+            y = self.input_proj[idx](x)                                     # conv1x1 + GroupNorm, NCHW
+            n, c, h, w = y.shape
+            shapes.append((h, w))
+            tokens.append(y.flatten(2).transpose(1, 2))                     # [N,hw,C]
+            poss.append(position.sine_2d(h, w, y.device, c // 2) + self.transformer.level_embed[idx])
+        src = torch.cat(tokens, 1).contiguous()
+        pos = torch.cat(poss, 0).unsqueeze(0)                               # [1,Len,C] (frame-invariant)
+        starts = [0]
+        for h, w in shapes[:-1]:
+            starts.append(starts[-1] + h * w)
+        for layer in self.transformer.encoder.layers:
+            src = layer(src, pos, shapes, starts)
+        n = src.shape[0]
+        out = []
+        for i, (h, w) in enumerate(shapes):
+            z = src[:, starts[i]:starts[i] + h * w]                         # [N,hw,C] token-major
+            out.append(z.reshape(n, h, w, -1).permute(0, 3, 1, 2))          # NCHW view of channel-last storage
+        for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
+            x = features[f].float().contiguous(memory_format=torch.channels_last)
+            cur = self.lateral_convs[idx](x)
+            up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
+            y = self.output_convs[idx]((cur + up).contiguous(memory_format=torch.channels_last))
+            out.append(y)
+        multi_scale = out[:self.maskformer_num_feature_levels]
+        last = out[-1].contiguous(memory_format=torch.channels_last)
+        mask_features = self.mask_features(last)                             # channels-last storage, NCHW shape
+        if not mask_features.is_contiguous(memory_format=torch.channels_last):
+            mask_features = mask_features.contiguous(memory_format=torch.channels_last)
+        return mask_features, out[-1], out[0], multi_scale

@@ -1,0 +1,60 @@
+"""Frame sharding of a clip across the GPUs of one node (new capability, not in the reference).
+
+Backbone and pixel decoder treat frames as the batch dimension with no cross-frame operation, so rank r owns frames
+{f : f mod n == r}.  The only exchange step is one all-gather of the per-frame {mask_features, 3 multi-scale maps}
+before the decoder.  Ragged clips (T not a multiple of n) are padded to ceil(T/n) frames per rank for the collective;
+padding frames are zeros and are dropped after the gather.  Works with NCCL (GPU) and gloo (CPU tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def frame_plan(num_frames: int, world_size: int):
+    """-> list over ranks of the frame indices each rank owns (round robin)."""
+    return [list(range(r, num_frames, world_size)) for r in range(world_size)]
+
+
+class FrameSharder:
+    def __init__(self, process_group=None):
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group) if process_group is not None else 1
+        self.rank = dist.get_rank(process_group) if process_group is not None else 0
+
+    def local_frames(self, x):
+        idx = frame_plan(x.shape[0], self.world_size)[self.rank]
+        if not idx:                      # an idle rank still takes part in the collective with a padding frame
+            return x[:0]
+        return x[idx]
+
+    def all_gather_frames(self, tensors, num_frames):
+        """tensors: list of [T_local, ...] (same trailing shapes on every rank).  Returns the list of [T, ...]
+        tensors in global frame order.  One fused collective: all tensors are packed into one flat buffer."""
+        n = self.world_size
+        per_rank = (num_frames + n - 1) // n
+        plan = frame_plan(num_frames, n)
+        trailing = [t.shape[1:] for t in tensors]
+        numels = [int(torch.Size(s).numel()) for s in trailing]
+        frame_numel = sum(numels)
+        dev, dt = tensors[0].device, tensors[0].dtype
+        send = torch.zeros(per_rank * frame_numel, device=dev, dtype=dt)
+        t_local = tensors[0].shape[0]
+        if t_local:
+            view = send[: t_local * frame_numel].view(t_local, frame_numel)
+            off = 0
+            for t, ne in zip(tensors, numels):
+                view[:, off:off + ne] = t.reshape(t_local, ne)
+                off += ne
+        recv = torch.empty(n * per_rank * frame_numel, device=dev, dtype=dt)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        recv = recv.view(n, per_rank, frame_numel)
+        order = torch.empty(num_frames, dtype=torch.long)
+        for r, frames in enumerate(plan):
+            for j, f in enumerate(frames):
+                order[f] = r * per_rank + j
+        flat = recv.view(n * per_rank, frame_numel)[order.to(dev)]
+        outs, off = [], 0
+        for s, ne in zip(trailing, numels):
+            outs.append(flat[:, off:off + ne].reshape(num_frames, *s))
+            off += ne
+        return outs
