@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Benchmark of the UniVS per-clip forward hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ns|c2] [--precision fp32|tf32]
+
+One step = one per-clip forward (normalise+pad -> Swin backbone -> MSDeformAttn pixel decoder -> UniVS decoder ->
+mask logits) over one synthetic clip.  Default workload = the configuration BASELINE.json's metric is quoted on:
+Swin-L, T=5, 720x1280 (padded to 736x1280), Q=200, detection task without prompts.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (swin variant, T, H, W, Q)
+    "ns": ("large", 5, 720, 1280, 200),      # north-star / metric configuration
+    "c2": ("tiny", 5, 480, 864, 100),        # BASELINE.json configs[1]
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        clocks, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                clocks.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(clocks) if clocks else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(clocks)}
+
+
+def make_targets(T, device):
+    return [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual",
+             "frame_indices": torch.arange(T, device=device)}]
+
+
+def run_cpu_reference(args, workload, steps, warmup, as_line):
+    """The reference algorithm on the host cores: product host logic with every operator replaced by its CPU oracle
+    (oracle/ops_ref.py; the reference tree itself does not travel to the GPU box), fp32, all host threads.
+    Bounded sample: a clip of ONE frame of the workload (the full clip has T frames)."""
+    from oracle.cpu_backend import oracle_ops
+    from univs_b200.build import build_model, make_cfg
+    variant, T, H, W, Q = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    cfg = make_cfg(variant, Q, 1, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
+    model = build_model(cfg)
+    frames = torch.rand(1, 3, H, W, generator=g) * 255
+    times = []
+    with oracle_ops():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = model.clip_forward(frames, make_targets(1, "cpu"))
+            float(out["pred_masks"].sum())
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if i == 0 and dt * (warmup + steps) > 900:
+                raise SystemExit(f"cpu reference too slow for the requested step count ({dt:.1f}s/step)")
+    mean = sum(times) / len(times)
+    sample = f"1 clip of T=1 frame ({variant} {H}x{W}, Q={Q}) per step; full workload has T={T} frames/clip"
+    base = {"value": 1.0 / mean, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+    if not as_line:
+        return base
+    return {
+        "impl": "reference", "metric": "frames/sec (per-clip forward)", "value": 1.0 / mean, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{workload}: Swin-{variant} T={T} {H}x{W} Q={Q} detection", "sample": sample},
+        "cpu_baseline": base,
+        "e2e": {"value": 1.0 / mean, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ns", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("UNIVS_PRECISION", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling aid: after warm-up run ONE step between cudaProfilerStart/Stop and exit "
+                         "(use with `ncu --profile-from-start off`); prints no bench line")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_cpu_reference(args, args.workload, max(1, args.steps), max(0, args.warmup), True)))
+        return
+
+    import torch.distributed as dist
+    from univs_b200 import ops
+    from univs_b200.build import build_model, make_cfg
+    from univs_b200.precision import set_precision
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    set_precision(args.precision)
+
+    variant, T, H, W, Q = WORKLOADS[args.workload]
+    g = torch.Generator().manual_seed(0)
+    cfg = make_cfg(variant, Q, T, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
+    model = build_model(cfg, process_group=group).to(dev)
+    frames_host = (torch.rand(T, 3, H, W, generator=g) * 255).to(torch.uint8).pin_memory()
+    frames_dev = frames_host.to(dev)
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- device-resident throughput ------------------------------------------------------------------------
+    def step_resident():
+        return model.clip_forward(frames_dev, make_targets(T, dev))
+
+    for _ in range(warmup):
+        out = step_resident()
+    n_lp = out["pred_masks"].shape[1]
+    if args.ncu_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sink = ops.profile_events(True)
+    launches0 = ops.launch_count
+    ms_total = timed(step_resident, steps)
+    launches = (ops.launch_count - launches0) // steps
+    torch.cuda.synchronize()
+    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in sink.items()}
+    kernel_calls = {k: len(v) // steps for k, v in sink.items()}
+    ops.profile_events(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / steps
+    fps = T / (ms_per_step / 1e3)
+
+    # ---- end-to-end through the public API with host buffers ------------------------------------------------
+    d2h_pinned = {}
+
+    def step_e2e():
+        o = model.clip_forward(frames_host, make_targets(T, dev))      # H2D of the pinned uint8 frames inside
+        res = {"pred_logits": o["pred_logits"], "pred_embds": o["pred_embds"], "pred_masks_bin": o["pred_masks"] > 0}
+        for k, v in res.items():
+            if k not in d2h_pinned:
+                d2h_pinned[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+            d2h_pinned[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                       # the caller reads the result every step
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, steps) / steps
+    h2d = frames_host.numel() * frames_host.element_size()
+    d2h = sum(v.numel() * v.element_size() for v in d2h_pinned.values())
+
+    # ---- roofline of the mask einsum (the kernel BASELINE.json's metric names) -----------------------------
+    HW = out["pred_masks"].shape[-1] * out["pred_masks"].shape[-2]
+    C = 256
+    t_einsum = out["pred_masks"].shape[2]
+    alg_bytes = 4.0 * t_einsum * (n_lp * C + C * HW + n_lp * HW)        # per launch (all T frames), SURVEY 8(d)
+    peak, peak_kind = peaks()
+    roof = None
+    if "mask_einsum" in kernel_ms:
+        ach = alg_bytes / (kernel_ms["mask_einsum"] * 1e-3) / 1e9
+        roof = {"kernel": "mask_einsum", "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "launch_ms": kernel_ms["mask_einsum"],
+                "algorithmic_bytes_per_launch": alg_bytes}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = run_cpu_reference(args, args.workload, 1, 1, False)
+            except BaseException as e:  # noqa: BLE001
+                cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        line = {
+            "metric": "frames/sec (Swin-L 720p T=5 Q=200)" if args.workload == "ns" else "frames/sec (per-clip forward)",
+            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init",
+                       "precision": args.precision, "parallelism": f"frame-shard x{world}" if world > 1 else "single",
+                       "l2": "per-step working set (multi-GB activations) exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": T / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "kernels": {k: {"ms_per_launch": kernel_ms[k], "launches_per_step": kernel_calls[k]} for k in sorted(kernel_ms)},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,79 @@
+"""End-to-end parity on the GPU: the product model with the real CUDA kernels (through the C ABI) against the same
+host logic with CPU oracle operators (validated against the reference itself in tests/test_host_model_vs_reference.py
+and against the golden vectors), on seeded inputs, for both arithmetic policies."""
+import pytest
+import torch
+
+from oracle.cpu_backend import oracle_ops
+from tests import model_factory as mf
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _pair(swin, T, Q, H, W, tgt, seed=0, **kw):
+    clip = mf.make_clip_emb()
+    cpu = mf.build_product_model(swin, num_queries=Q, num_frames=T, clip_emb=clip, **kw)
+    mf.load_keyed(cpu, seed)
+    gpu = mf.build_product_model(swin, num_queries=Q, num_frames=T, clip_emb=clip, **kw)
+    mf.load_keyed(gpu, seed)
+    gpu = tuple(m.cuda() for m in gpu)
+    g = torch.Generator().manual_seed(seed + 5)
+    x = torch.randn(T, 3, H, W, generator=g)
+    with oracle_ops():
+        want = mf.product_clip_forward(*cpu, x, [dict(tgt)])
+    return gpu, x, want
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("tf32", 1e-3)])
+def test_swin_tiny_clip_detection(precision, tol):
+    """Swin-T (window 7, real depths), T=2, 224x320, Q=100 -- a reduced-resolution BASELINE config 2."""
+    from univs_b200.precision import set_precision
+    swin = dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7)
+    tgt = {"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual", "frame_indices": torch.tensor([0, 1])}
+    gpu, x, (wf, (wmf, wms), wout) = _pair(swin, 2, 100, 224, 320, tgt)
+    set_precision(precision)
+    try:
+        tg = [{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in tgt.items()}]
+        gf, (gmf, gms), gout = mf.product_clip_forward(*gpu, x.cuda(), tg)
+    finally:
+        set_precision("fp32")
+    assert _rel(gf["res5"], wf["res5"]) < tol
+    assert _rel(gmf, wmf) < tol
+    assert _rel(gout["pred_masks"], wout["pred_masks"]) < tol
+    assert _rel(gout["pred_logits"], wout["pred_logits"]) < tol
+    assert _rel(gout["pred_embds"], wout["pred_embds"]) < tol
+
+
+def test_swin_window12_grounding_proca():
+    """window 12 (Swin-B/L geometry, shallow), text prompts: ProCA with L=78 + lang2vision + sep-blocked mask."""
+    swin = dict(embed_dim=64, depths=[2, 2, 2, 2], num_heads=[2, 4, 8, 16], window_size=12)
+    g = torch.Generator().manual_seed(3)
+    P, T = 4, 3
+    tgt = {"task": "grounding", "dataset_name": "refytvos", "prompt_type": "text", "frame_indices": torch.arange(T),
+           "exp_word_feats": torch.randn(P, 77, T, 640, generator=g), "exp_sentence_feats": torch.randn(P, T, 640, generator=g),
+           "exp_word_len": torch.full((P,), 9)}
+    gpu, x, (wf, (wmf, wms), wout) = _pair(swin, T, 20, 192, 256, tgt, enc_layers=2, dec_layers=3,
+                                           text_prompt_to_image_enable=True, self_attn_mask_type="sep-blocked")
+    tg = [{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in tgt.items()}]
+    gf, (gmf, gms), gout = mf.product_clip_forward(*gpu, x.cuda(), tg)
+    assert _rel(gf["res3"], wf["res3"]) < 2e-4
+    assert _rel(gout["pred_masks"], wout["pred_masks"]) < 1e-3
+    assert _rel(gout["pred_logits"], wout["pred_logits"]) < 1e-3
+    assert _rel(gout["pred_reid_logits"], wout["pred_reid_logits"]) < 1e-3
+
+
+def test_no_cpu_fallback_and_library_loaded():
+    """The product path fails loudly without CUDA tensors, and the in-tree .so is what runs."""
+    from univs_b200 import _cabi, ops
+    assert _cabi.lib().univs_b200_abi_version() == 1
+    assert "univs_b200/lib/libunivs_b200.so" in _cabi.LIB_PATH
+    with pytest.raises(_cabi.UnivsB200Error):
+        ops.mha_core(torch.zeros(1, 4, 256), torch.zeros(1, 4, 256), torch.zeros(1, 4, 256))
+    before = ops.launch_count
+    ops.mask_einsum(torch.zeros(1, 4, 32, device="cuda"), torch.zeros(1, 8, 32, device="cuda"))
+    assert ops.launch_count == before + 1

@@ -14,6 +14,39 @@ PREC_TF32 = 1
 
 _default_precision = PREC_TF32X3
 
+# ---- optional instrumentation (bench.py): launch counter + per-kernel CUDA-event brackets --------------------
+launch_count = 0          # number of univs_b200 kernels launched through this module
+_event_sink = None        # None, or dict name -> list[(start_event, end_event)]
+
+
+def profile_events(enable: bool):
+    """When enabled every wrapper brackets its launch(es) with CUDA events on the current stream."""
+    global _event_sink
+    _event_sink = {} if enable else None
+    return _event_sink
+
+
+class _Bracket:
+    __slots__ = ("name", "n", "ev")
+
+    def __init__(self, name, n=1):
+        self.name, self.n = name, n
+
+    def __enter__(self):
+        global launch_count
+        launch_count += self.n
+        if _event_sink is not None:
+            self.ev = torch.cuda.Event(enable_timing=True)
+            self.ev.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _event_sink is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _event_sink.setdefault(self.name, []).append((self.ev, e1))
+        return False
+
 
 def set_attention_precision(p: int):
     global _default_precision
@@ -57,7 +90,8 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
         sh, ls = _levels(torch.as_tensor(spatial_shapes).cpu().numpy() if torch.is_tensor(spatial_shapes) else spatial_shapes,
                          torch.as_tensor(level_start_index).cpu().numpy() if torch.is_tensor(level_start_index) else level_start_index)
         shp, lsp, keep = sh.ctypes.data, ls.ctypes.data, (sh, ls)
-    rc = lib().univs_ms_deform_attn_forward_f32(_stream(), _chk(value, "value"), shp, lsp, _chk(sampling_loc, "sampling_loc"),
+    with _Bracket("ms_deform_attn_forward", 1):
+        rc = lib().univs_ms_deform_attn_forward_f32(_stream(), _chk(value, "value"), shp, lsp, _chk(sampling_loc, "sampling_loc"),
                                                 _chk(attn_weight, "attn_weight"), N, S, M, D, L, Lq, P, out.data_ptr())
     check(rc, "ms_deform_attn_forward")
     del keep
@@ -70,7 +104,8 @@ def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits
     assert D == 32 and offs_logits.shape == (N, S, M * num_levels * num_points * 3)
     sh, ls = _levels(spatial_shapes, level_start_index)
     out = torch.empty((N, S, M * D), device=value.device, dtype=torch.float32)
-    rc = lib().univs_ms_deform_attn_encoder_f32(_stream(), _chk(value, "value"), sh.ctypes.data, ls.ctypes.data,
+    with _Bracket("ms_deform_attn_encoder", 1):
+        rc = lib().univs_ms_deform_attn_encoder_f32(_stream(), _chk(value, "value"), sh.ctypes.data, ls.ctypes.data,
                                                 _chk(offs_logits, "offs_logits"), N, S, M, num_levels, num_points,
                                                 out.data_ptr())
     check(rc, "ms_deform_attn_encoder")
@@ -82,7 +117,8 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     out = torch.empty((B, H, W, C), device=qkv.device, dtype=torch.float32)
-    rc = lib().univs_swin_window_attention_f32(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
+    with _Bracket("swin_window_attention", 1):
+        rc = lib().univs_swin_window_attention_f32(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
                                                _chk(rel_bias_table, "rel_bias_table"), B, H, W, C, num_heads, window,
                                                shift, _default_precision if precision is None else precision,
                                                out.data_ptr())
@@ -96,7 +132,8 @@ def mask_einsum(mask_embed, mask_features_cl, out=None):
     HW = mask_features_cl.shape[1]
     if out is None:
         out = torch.empty((Q, T, HW), device=mask_embed.device, dtype=torch.float32)
-    rc = lib().univs_mask_einsum_f32(_stream(), _chk(mask_embed, "mask_embed"), _chk(mask_features_cl, "mask_features"),
+    with _Bracket("mask_einsum", 1):
+        rc = lib().univs_mask_einsum_f32(_stream(), _chk(mask_embed, "mask_embed"), _chk(mask_features_cl, "mask_features"),
                                      T, Q, Cc, HW, _chk(out, "out"))
     check(rc, "mask_einsum")
     return out
@@ -110,7 +147,8 @@ def attn_mask_bits(mask_logits, hw, target_hw):
     words = (h * w + 31) // 32
     bits = torch.empty((T, Q, words), device=mask_logits.device, dtype=torch.int32)
     row_open = torch.empty((T, Q), device=mask_logits.device, dtype=torch.int32)
-    rc = lib().univs_attn_mask_bits_f32(_stream(), _chk(mask_logits, "mask_logits"), Q, T, H, W, h, w,
+    with _Bracket("attn_mask_bits", 1):
+        rc = lib().univs_attn_mask_bits_f32(_stream(), _chk(mask_logits, "mask_logits"), Q, T, H, W, h, w,
                                         bits.data_ptr(), row_open.data_ptr())
     check(rc, "attn_mask_bits")
     return bits, row_open
@@ -136,11 +174,12 @@ def mha_core(q, k, v, mask_bits=None, row_open=None, precision=None):
     nbytes = lib().univs_mha_workspace_bytes(B, Lq, Lk, Cc)
     ws = _workspace(nbytes, q.device)
     mb = 0 if mask_bits is None else mask_bits.shape[0]
-    rc = lib().univs_mha_forward_f32(
-        _stream(), _chk(q, "q"), _chk(k, "k"), _chk(v, "v"),
-        None if mask_bits is None else _chk(mask_bits, "mask_bits", torch.int32),
-        None if row_open is None else _chk(row_open, "row_open", torch.int32),
-        mb, B, Lq, Lk, Cc, _default_precision if precision is None else precision, ws.data_ptr(), out.data_ptr())
+    with _Bracket("mha", 1 if nbytes <= 16 else 2):
+          rc = lib().univs_mha_forward_f32(
+            _stream(), _chk(q, "q"), _chk(k, "k"), _chk(v, "v"),
+            None if mask_bits is None else _chk(mask_bits, "mask_bits", torch.int32),
+            None if row_open is None else _chk(row_open, "row_open", torch.int32),
+            mb, B, Lq, Lk, Cc, _default_precision if precision is None else precision, ws.data_ptr(), out.data_ptr())
     check(rc, "mha_forward")
     return out
 
@@ -150,7 +189,8 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
     P, T, Cc = q.shape
     Tm, L = k_mem.shape[1], k_mem.shape[2]
     out = torch.empty_like(q)
-    rc = lib().univs_proca_forward_f32(_stream(), _chk(q, "q"), _chk(k_self, "k_self"), _chk(v_self, "v_self"),
+    with _Bracket("proca", 1):
+        rc = lib().univs_proca_forward_f32(_stream(), _chk(q, "q"), _chk(k_self, "k_self"), _chk(v_self, "v_self"),
                                        _chk(k_mem, "k_mem"), _chk(v_mem, "v_mem"), P, T, Tm, L, Cc, out.data_ptr())
     check(rc, "proca_forward")
     return out
@@ -159,7 +199,8 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
 def round_tf32(x, out=None):
     if out is None:
         out = torch.empty_like(x)
-    rc = lib().univs_round_tf32_f32(_stream(), _chk(x, "x"), _chk(out, "out"), x.numel())
+    with _Bracket("round_tf32", 1):
+        rc = lib().univs_round_tf32_f32(_stream(), _chk(x, "x"), _chk(out, "out"), x.numel())
     check(rc, "round_tf32")
     return out
 
