@@ -69,6 +69,12 @@ int univs_swin_window_attention_f32(void* stream, const float* qkv, const float*
 int univs_mask_einsum_f32(void* stream, const float* mask_embed, const float* mask_features_cl, int frames,
                           int queries, int channels, int pixels, float* out);
 
+/* Same contraction on the tcgen05 tensor cores (TMA -> smem -> tcgen05.mma kind::tf32 -> TMEM).  The tensor core
+ * reads the upper 19 bits of each fp32 operand (truncation): pass operands through univs_round_tf32_f32 first for
+ * round-to-nearest behaviour.  Operands must be 16-byte aligned. */
+int univs_mask_einsum_tc_f32(void* stream, const float* mask_embed, const float* mask_features_cl, int frames,
+                             int queries, int channels, int pixels, float* out);
+
 /* ---- Attention-mask bits from mask logits (a11, ..._univs.py:555-566 + :390).
  * logits [Q,T,H,W] f32; target (h,w) with H % h == 0 and W % w == 0 and even ratios (bilinear
  * align_corners=False then equals the mean of the 2x2 centre pixels of each cell);

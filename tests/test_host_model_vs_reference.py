@@ -97,3 +97,56 @@ def test_grounding_text_prompts(l2v):
     assert _rel(pout["pred_logits"], rout["pred_logits"]) < 1e-3
     assert _rel(pout["pred_reid_logits"], rout["pred_reid_logits"]) < 1e-3
     assert _rel(pout["pred_embds"], rout["pred_embds"]) < 1e-3
+
+
+def _rect_masks(P, n, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    masks = torch.zeros(P, n, H, W)
+    boxes = torch.zeros(P, n, 4)
+    for p in range(P):
+        for f in range(n):
+            bw, bh = int(W * (0.2 + 0.3 * torch.rand(1, generator=g))), int(H * (0.2 + 0.3 * torch.rand(1, generator=g)))
+            x0, y0 = int((W - bw) * torch.rand(1, generator=g)), int((H - bh) * torch.rand(1, generator=g))
+            masks[p, f, y0:y0 + bh, x0:x0 + bw] = 1.0
+            boxes[p, f] = torch.tensor([x0 / W, y0 / H, (x0 + bw) / W, (y0 + bh) / H])
+    return masks, boxes
+
+
+def test_sot_visual_prompts_two_clips():
+    """task=sot: VisualPromptSampler + memory pool + ProCA over two consecutive stride-1 clips (same RNG seed/order)."""
+    T, Q, P, H, W = 3, 6, 3, 64, 96
+    ref, prod = _build_pair(mf.TINY_SWIN, T, Q, enc_layers=1, dec_layers=3, num_dense_points=8,
+                            num_prev_frames_memory=4)
+    g = torch.Generator().manual_seed(11)
+    frames = torch.randn(T + 1, 3, H, W, generator=g)
+    masks, boxes = _rect_masks(P, T + 1, H, W, 5)
+    masks[2, 0] = 0        # object 2 is absent in the first frame (blank prompt)
+
+    def targets():
+        return [{"task": "sot", "dataset_name": "davis", "prompt_type": "visual", "ids": torch.arange(P),
+                 "first_appear_frame_idxs": torch.tensor([0, 0, 1])}]
+
+    def clip_inputs(tg, c):
+        tg[0]["first_frame_idx"] = c
+        tg[0]["frame_indices"] = torch.arange(c, c + T)
+        tg[0]["masks"] = masks[:, : c + T].clone()
+        tg[0]["boxes"] = boxes[:, : c + T].clone()
+        return frames[c: c + T]
+
+    rtg, ptg = targets(), targets()
+    for c in range(2):
+        x = clip_inputs(rtg, c)
+        torch.manual_seed(100 + c)
+        _, _, rout = ref_shim.reference_clip_forward(*ref, x, rtg)
+        x = clip_inputs(ptg, c)
+        torch.manual_seed(100 + c)
+        with oracle_ops():
+            _, _, pout = mf.product_clip_forward(*prod, x, ptg)
+        assert pout["pred_masks"].shape == rout["pred_masks"].shape == (1, Q + P, T, 16, 24)
+        assert _rel(pout["pred_masks"], rout["pred_masks"]) < 1e-3, c
+        assert _rel(pout["pred_logits"], rout["pred_logits"]) < 1e-3
+        assert _rel(pout["pred_embds"], rout["pred_embds"]) < 1e-3
+        for k in ("prompt_feats", "prompt_pe"):
+            assert ptg[0][k].shape == rtg[0][k].shape, (k, ptg[0][k].shape, rtg[0][k].shape)
+            assert _rel(ptg[0][k], rtg[0][k]) < 1e-4, k
+        assert torch.equal(ptg[0]["prompt_attn_masks"], rtg[0]["prompt_attn_masks"])

@@ -114,7 +114,22 @@ mask_einsum_kernel(const float* __restrict__ E, const float* __restrict__ F, int
 
 }  // namespace univs
 
+namespace univs {
+int launch_mask_einsum_tc(cudaStream_t st, const float* E, const float* F, int T, int Q, int C, int HW, float* out);
+}
 using namespace univs;
+
+extern "C" int univs_mask_einsum_tc_f32(void* stream, const float* mask_embed, const float* mask_features_cl,
+                                        int frames, int queries, int channels, int pixels, float* out) {
+  UNIVS_REQUIRE(mask_embed && mask_features_cl && out, "mask_einsum_tc: null pointer");
+  UNIVS_REQUIRE(frames >= 0 && queries >= 0 && pixels >= 0, "mask_einsum_tc: negative size");
+  UNIVS_REQUIRE(queries <= 256, "mask_einsum_tc: at most 256 queries per call (got %d)", queries);
+  UNIVS_REQUIRE(channels > 0 && channels % 32 == 0, "mask_einsum_tc: channels must be a multiple of 32");
+  UNIVS_REQUIRE(((uintptr_t)mask_embed & 15) == 0 && ((uintptr_t)mask_features_cl & 15) == 0,
+                "mask_einsum_tc: operands must be 16-byte aligned (TMA)");
+  if (frames == 0 || queries == 0 || pixels == 0) return UNIVS_OK;
+  return launch_mask_einsum_tc((cudaStream_t)stream, mask_embed, mask_features_cl, frames, queries, channels, pixels, out);
+}
 
 extern "C" int univs_mask_einsum_f32(void* stream, const float* mask_embed, const float* mask_features_cl,
                                      int frames, int queries, int channels, int pixels, float* out) {

@@ -139,6 +139,19 @@ def mask_einsum(mask_embed, mask_features_cl, out=None):
     return out
 
 
+def mask_einsum_tc(mask_embed, mask_features_cl, out=None):
+    """tcgen05 variant (operands are consumed as TF32 by truncation; pre-round with round_tf32)."""
+    T, Q, Cc = mask_embed.shape
+    HW = mask_features_cl.shape[1]
+    if out is None:
+        out = torch.empty((Q, T, HW), device=mask_embed.device, dtype=torch.float32)
+    with _Bracket("mask_einsum", 1):
+        rc = lib().univs_mask_einsum_tc_f32(_stream(), _chk(mask_embed, "mask_embed"), _chk(mask_features_cl, "mask_features"),
+                                            T, Q, Cc, HW, _chk(out, "out"))
+    check(rc, "mask_einsum_tc")
+    return out
+
+
 def attn_mask_bits(mask_logits, hw, target_hw):
     """mask_logits [Q,T,H*W] -> (bits uint32-as-int32 [T,Q,words], row_open int32 [T,Q])"""
     Q, T, _ = mask_logits.shape
