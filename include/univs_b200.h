@@ -63,17 +63,19 @@ int univs_swin_window_attention_f32(void* stream, const float* qkv, const float*
                                     const float* rel_bias_table, int batch, int height, int width, int channels,
                                     int num_heads, int window, int shift, int precision, float* out);
 
-/* ---- Mask einsum "btqc,btchw->btqhw" + transpose(1,2) (a11).
- * mask_embed [T,Q,C] f32; mask_features channel-last [T,HW,C] f32; out [Q,T,HW] f32.  C % 32 == 0, Q <= 256.
- * Operands are rounded to nearest TF32, products accumulate in fp32. */
+/* ---- Mask einsum "btqc,btchw->btqhw" + transpose(1,2) (a11), on the tcgen05 tensor cores
+ * (TMA -> smem -> tcgen05.mma kind::tf32 -> TMEM -> tcgen05.ld -> coalesced stores).
+ * mask_embed [T,Q,C] f32; mask_features channel-last [T,HW,C] f32; out [Q,T,HW] f32.  C % 32 == 0, Q <= 256,
+ * operands 16-byte aligned.  The tensor core consumes the upper 19 bits of each fp32 operand (truncation) and
+ * accumulates in fp32: pass operands through univs_round_tf32_f32 first for round-to-nearest behaviour. */
 int univs_mask_einsum_f32(void* stream, const float* mask_embed, const float* mask_features_cl, int frames,
                           int queries, int channels, int pixels, float* out);
 
-/* Same contraction on the tcgen05 tensor cores (TMA -> smem -> tcgen05.mma kind::tf32 -> TMEM).  The tensor core
- * reads the upper 19 bits of each fp32 operand (truncation): pass operands through univs_round_tf32_f32 first for
- * round-to-nearest behaviour.  Operands must be 16-byte aligned. */
-int univs_mask_einsum_tc_f32(void* stream, const float* mask_embed, const float* mask_features_cl, int frames,
-                             int queries, int channels, int pixels, float* out);
+/* Same contraction with register operands (mma.sync): precision UNIVS_PREC_TF32 rounds operands to nearest TF32
+ * in-kernel (bit-identical to the tcgen05 kernel on pre-rounded operands); UNIVS_PREC_TF32X3 uses the 3xTF32 split
+ * (fp32-equivalent products) -- the strict-parity policy and the on-device cross-check of the tcgen05 kernel. */
+int univs_mask_einsum_mma_f32(void* stream, const float* mask_embed, const float* mask_features_cl, int frames,
+                              int queries, int channels, int pixels, int precision, float* out);
 
 /* ---- Attention-mask bits from mask logits (a11, ..._univs.py:555-566 + :390).
  * logits [Q,T,H,W] f32; target (h,w) with H % h == 0 and W % w == 0 and even ratios (bilinear

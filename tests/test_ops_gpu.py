@@ -97,33 +97,48 @@ def test_swin_window_attention(ops, B, H, W, nH, ws, shift, prec, tol):
 
 # ------------------------------------------------------------------ mask einsum + attention-mask bits
 @pytest.mark.parametrize("T,Q,C,HW", [(1, 20, 256, 64 * 64), (2, 100, 256, 30 * 54), (3, 200, 256, 46 * 80),
-                                        (1, 232, 256, 130), (2, 7, 64, 66), (1, 256, 32, 2)])
+                                        (1, 232, 256, 130), (2, 7, 64, 66), (1, 256, 32, 2), (1, 16, 32, 128)])
 def test_mask_einsum(ops, T, Q, C, HW):
     torch.manual_seed(11)
     E = torch.randn(T, Q, C)
     F = torch.randn(T, HW, C)
     want = ops_ref.mask_einsum(E.double(), F.transpose(1, 2).double()).float()
-    got = ops.mask_einsum(E.cuda(), F.cuda())
+    # TF32 policy: tcgen05 kernel on round-to-nearest operands (2^-12 relative each), fp32 accumulation in TMEM
+    Fr = ops.round_tf32(F.cuda())
+    got = ops.mask_einsum(E.cuda(), Fr, precision=ops.PREC_TF32)
     assert got.shape == (Q, T, HW)
-    # operands rounded to nearest TF32 (2^-12 relative each), fp32 accumulation
     assert _rel(got, want) < 4e-4
+    # the register-operand kernel on the same rounded operands must agree with the tensor-memory kernel
+    chk = ops.mask_einsum_mma(ops.round_tf32(E.cuda()), Fr, ops.PREC_TF32)
+    assert _rel(got, chk) < 2e-6
+    # strict policy: 3xTF32 split, fp32-equivalent
+    strict = ops.mask_einsum(E.cuda(), F.cuda(), precision=ops.PREC_TF32X3)
+    assert _rel(strict, want) < 5e-6
+
+
+def test_mask_einsum_empty(ops):
+    out = ops.mask_einsum(torch.zeros(0, 4, 32, device="cuda"), torch.zeros(0, 8, 32, device="cuda"))
+    assert out.shape == (4, 0, 8)
 
 
 def test_mask_einsum_linearity_full_size(ops):
-    """Size-independent property at the north-star size (T=5,Q=200,C=256,184x320): einsum(E1+E2,F) == einsum(E1,F)+einsum(E2,F)
-    up to TF32 rounding, and a column checksum against an fp64 reduction on the device."""
+    """Size-independent properties at the north-star size (T=5,Q=200,C=256,184x320): linearity in E up to TF32
+    rounding, and a checksum of checksums against an fp64 reduction on the device."""
     torch.manual_seed(12)
     T, Q, C, HW = 5, 200, 256, 184 * 320
-    F = torch.randn(T, HW, C, device="cuda")
+    F = ops.round_tf32(torch.randn(T, HW, C, device="cuda"))
     E1 = torch.randn(T, Q, C, device="cuda")
     E2 = torch.randn(T, Q, C, device="cuda")
-    o1, o2, o12 = ops.mask_einsum(E1, F), ops.mask_einsum(E2, F), ops.mask_einsum(E1 + E2, F)
+    P = ops.PREC_TF32
+    o1, o2, o12 = ops.mask_einsum(E1, F, precision=P), ops.mask_einsum(E2, F, precision=P), ops.mask_einsum(E1 + E2, F, precision=P)
     assert _rel(o12, o1 + o2) < 1e-3
-    # checksum of checksums: sum_p out[q,t,p] == E[t,q,:] . sum_p F[t,p,:]
     colsum = F.double().sum(1)                                  # [T,C]
     want = torch.einsum("tqc,tc->qt", E1.double(), colsum)
     got = o1.double().sum(-1)
     assert (got - want).abs().max().item() / want.abs().max().item() < 1e-3
+    # the two kernels agree at full size too
+    chk = ops.mask_einsum_mma(ops.round_tf32(E1), F, P)
+    assert _rel(o1, chk) < 2e-6
 
 
 @pytest.mark.parametrize("Q,T,H,W,tgt", [(5, 2, 16, 24, (8, 12)), (5, 2, 16, 24, (4, 6)), (7, 3, 16, 24, (2, 3)),

@@ -18,6 +18,7 @@ constexpr int kPxTile = 64;
 constexpr int kKChunk = 32;
 constexpr int kEinThreads = 256;  // 8 warps, warp w owns query rows [32w, 32w+32)
 
+template <bool X3>
 __global__ void __launch_bounds__(kEinThreads)
 mask_einsum_kernel(const float* __restrict__ E, const float* __restrict__ F, int T, int Q, int C, int HW,
                    float* __restrict__ out) {
@@ -74,21 +75,33 @@ mask_einsum_kernel(const float* __restrict__ E, const float* __restrict__ F, int
     if (act0) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        uint32_t a[2][4];
+        uint32_t a[2][4], as[2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const int r = warp * 32 + mt * 16 + g;
-          a[mt][0] = f2tf32(Es[r * kEStride + ks * 8 + t4]);
-          a[mt][1] = f2tf32(Es[(r + 8) * kEStride + ks * 8 + t4]);
-          a[mt][2] = f2tf32(Es[r * kEStride + ks * 8 + t4 + 4]);
-          a[mt][3] = f2tf32(Es[(r + 8) * kEStride + ks * 8 + t4 + 4]);
+          const float e0 = Es[r * kEStride + ks * 8 + t4], e1 = Es[(r + 8) * kEStride + ks * 8 + t4];
+          const float e2 = Es[r * kEStride + ks * 8 + t4 + 4], e3 = Es[(r + 8) * kEStride + ks * 8 + t4 + 4];
+          if (X3) {
+            split_tf32(e0, a[mt][0], as[mt][0]); split_tf32(e1, a[mt][1], as[mt][1]);
+            split_tf32(e2, a[mt][2], as[mt][2]); split_tf32(e3, a[mt][3], as[mt][3]);
+          } else {
+            a[mt][0] = f2tf32(e0); a[mt][1] = f2tf32(e1); a[mt][2] = f2tf32(e2); a[mt][3] = f2tf32(e3);
+          }
         }
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-          const uint32_t b0 = f2tf32(Fs[(nt * 8 + g) * kEStride + ks * 8 + t4]);
-          const uint32_t b1 = f2tf32(Fs[(nt * 8 + g) * kEStride + ks * 8 + t4 + 4]);
-          mma_tf32(acc[0][nt], a[0], b0, b1);
-          if (act1) mma_tf32(acc[1][nt], a[1], b0, b1);
+          const float f0 = Fs[(nt * 8 + g) * kEStride + ks * 8 + t4], f1 = Fs[(nt * 8 + g) * kEStride + ks * 8 + t4 + 4];
+          if (X3) {
+            uint32_t b0, b1, s0, s1;
+            split_tf32(f0, b0, s0);
+            split_tf32(f1, b1, s1);
+            mma_tf32x3(acc[0][nt], a[0], as[0], b0, b1, s0, s1);
+            if (act1) mma_tf32x3(acc[1][nt], a[1], as[1], b0, b1, s0, s1);
+          } else {
+            const uint32_t b0 = f2tf32(f0), b1 = f2tf32(f1);
+            mma_tf32(acc[0][nt], a[0], b0, b1);
+            if (act1) mma_tf32(acc[1][nt], a[1], b0, b1);
+          }
         }
       }
     }
@@ -119,32 +132,43 @@ int launch_mask_einsum_tc(cudaStream_t st, const float* E, const float* F, int T
 }
 using namespace univs;
 
-extern "C" int univs_mask_einsum_tc_f32(void* stream, const float* mask_embed, const float* mask_features_cl,
-                                        int frames, int queries, int channels, int pixels, float* out) {
-  UNIVS_REQUIRE(mask_embed && mask_features_cl && out, "mask_einsum_tc: null pointer");
-  UNIVS_REQUIRE(frames >= 0 && queries >= 0 && pixels >= 0, "mask_einsum_tc: negative size");
-  UNIVS_REQUIRE(queries <= 256, "mask_einsum_tc: at most 256 queries per call (got %d)", queries);
-  UNIVS_REQUIRE(channels > 0 && channels % 32 == 0, "mask_einsum_tc: channels must be a multiple of 32");
-  UNIVS_REQUIRE(((uintptr_t)mask_embed & 15) == 0 && ((uintptr_t)mask_features_cl & 15) == 0,
-                "mask_einsum_tc: operands must be 16-byte aligned (TMA)");
-  if (frames == 0 || queries == 0 || pixels == 0) return UNIVS_OK;
-  return launch_mask_einsum_tc((cudaStream_t)stream, mask_embed, mask_features_cl, frames, queries, channels, pixels, out);
+static int check_einsum_args(const char* who, const float* e, const float* f, const float* out, int frames,
+                             int queries, int channels, int pixels) {
+  UNIVS_REQUIRE(frames >= 0 && queries >= 0 && pixels >= 0, "%s: negative size", who);
+  UNIVS_REQUIRE(queries <= 256, "%s: at most 256 queries per call (got %d)", who, queries);
+  UNIVS_REQUIRE(channels > 0 && channels % 32 == 0, "%s: channels must be a multiple of 32", who);
+  if (frames == 0 || queries == 0 || pixels == 0) return 1;
+  UNIVS_REQUIRE(e && f && out, "%s: null pointer", who);
+  return 0;
 }
 
 extern "C" int univs_mask_einsum_f32(void* stream, const float* mask_embed, const float* mask_features_cl,
                                      int frames, int queries, int channels, int pixels, float* out) {
-  UNIVS_REQUIRE(mask_embed && mask_features_cl && out, "mask_einsum: null pointer");
-  UNIVS_REQUIRE(frames >= 0 && queries >= 0 && pixels >= 0, "mask_einsum: negative size");
-  UNIVS_REQUIRE(queries <= 256, "mask_einsum: at most 256 queries per call (got %d)", queries);
-  UNIVS_REQUIRE(channels > 0 && channels % 32 == 0, "mask_einsum: channels must be a multiple of 32");
-  UNIVS_REQUIRE(pixels % 2 == 0, "mask_einsum: pixels must be even");
-  if (frames == 0 || queries == 0 || pixels == 0) return UNIVS_OK;
+  int rc = check_einsum_args("mask_einsum", mask_embed, mask_features_cl, out, frames, queries, channels, pixels);
+  if (rc) return rc < 0 ? rc : UNIVS_OK;
+  UNIVS_REQUIRE(((uintptr_t)mask_embed & 15) == 0 && ((uintptr_t)mask_features_cl & 15) == 0,
+                "mask_einsum: operands must be 16-byte aligned (TMA)");
+  return launch_mask_einsum_tc((cudaStream_t)stream, mask_embed, mask_features_cl, frames, queries, channels, pixels, out);
+}
+
+extern "C" int univs_mask_einsum_mma_f32(void* stream, const float* mask_embed, const float* mask_features_cl,
+                                         int frames, int queries, int channels, int pixels, int precision, float* out) {
+  int rc = check_einsum_args("mask_einsum_mma", mask_embed, mask_features_cl, out, frames, queries, channels, pixels);
+  if (rc) return rc < 0 ? rc : UNIVS_OK;
+  UNIVS_REQUIRE(pixels % 2 == 0, "mask_einsum_mma: pixels must be even");
+  UNIVS_REQUIRE(precision == UNIVS_PREC_TF32X3 || precision == UNIVS_PREC_TF32, "mask_einsum_mma: bad precision");
   const size_t smem = 2 * (256 + kPxTile) * kEStride * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(mask_einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("mask_einsum: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNIVS_E_LAUNCH; }
   const long long grid = (long long)frames * ((pixels + kPxTile - 1) / kPxTile);
-  UNIVS_REQUIRE(grid < (1ll << 31), "mask_einsum: problem too large");
-  mask_einsum_kernel<<<(unsigned)grid, kEinThreads, smem, (cudaStream_t)stream>>>(mask_embed, mask_features_cl, frames,
-                                                                                  queries, channels, pixels, out);
-  return check_launch("mask_einsum");
+  UNIVS_REQUIRE(grid < (1ll << 31), "mask_einsum_mma: problem too large");
+  cudaError_t e;
+  if (precision == UNIVS_PREC_TF32X3) {
+    e = cudaFuncSetAttribute(mask_einsum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("mask_einsum_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNIVS_E_LAUNCH; }
+    mask_einsum_kernel<true><<<(unsigned)grid, kEinThreads, smem, (cudaStream_t)stream>>>(mask_embed, mask_features_cl, frames, queries, channels, pixels, out);
+  } else {
+    e = cudaFuncSetAttribute(mask_einsum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("mask_einsum_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNIVS_E_LAUNCH; }
+    mask_einsum_kernel<false><<<(unsigned)grid, kEinThreads, smem, (cudaStream_t)stream>>>(mask_embed, mask_features_cl, frames, queries, channels, pixels, out);
+  }
+  return check_launch("mask_einsum_mma");
 }

@@ -237,9 +237,10 @@ extern "C" int univs_ms_deform_attn_forward_f32(void* stream, const float* value
                                                 const float* attn_weight, int batch, int spatial_size,
                                                 int num_heads, int channels, int num_levels, int num_query,
                                                 int num_point, float* out) {
+  UNIVS_REQUIRE(batch >= 0 && spatial_size >= 0 && num_query >= 0, "ms_deform_attn_forward: negative size");
+  if (batch == 0 || num_query == 0) return UNIVS_OK;   // empty output: nothing to do (pointers may be null)
   UNIVS_REQUIRE(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
                 "ms_deform_attn_forward: null pointer");
-  UNIVS_REQUIRE(batch >= 0 && spatial_size >= 0 && num_query >= 0, "ms_deform_attn_forward: negative size");
   UNIVS_REQUIRE(num_heads > 0 && channels > 0 && num_point > 0, "ms_deform_attn_forward: bad head/channel/point");
   UNIVS_REQUIRE(num_levels > 0 && num_levels <= kMaxLevels, "ms_deform_attn_forward: num_levels must be 1..%d",
                 kMaxLevels);

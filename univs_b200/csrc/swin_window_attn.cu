@@ -32,7 +32,7 @@ struct WinCfg {
 };
 
 template <int WS, bool X3>
-__global__ void __launch_bounds__(WinCfg<WS>::THREADS)
+__global__ void __launch_bounds__(WinCfg<WS>::THREADS, (WS >= 12 ? 2 : 4))
 swin_window_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
                         const float* __restrict__ table, int B, int H, int W, int C, int nH, int shift,
                         float scale, float* __restrict__ out) {

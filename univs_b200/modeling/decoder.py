@@ -401,7 +401,7 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         feats_cl = mask_features.permute(0, 2, 3, 1)                        # [T,H,W,C]
         if not feats_cl.is_contiguous():
             feats_cl = feats_cl.contiguous()
-        feats_cl = feats_cl.view(t, h_m * w_m, c_m)
+        feats_cl = ops.prepare_mask_features(feats_cl.view(t, h_m * w_m, c_m))
         if "frame_indices" in targets[0]:
             frame_indices = targets[0]["frame_indices"]
         else:

@@ -126,29 +126,48 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     return out
 
 
-def mask_einsum(mask_embed, mask_features_cl, out=None):
-    """mask_embed [T,Q,C], mask_features_cl [T,HW,C] (channel-last) -> [Q,T,HW]"""
+def prepare_mask_features(mask_features_cl):
+    """Once per clip: the operand layout/rounding the mask einsum of the active precision policy consumes.
+    TF32 policy: round-to-nearest TF32 copy (the tcgen05 kernel truncates, so pre-rounded operands make it
+    round-to-nearest overall).  TF32X3 policy: the tensor itself."""
+    if _default_precision == PREC_TF32:
+        return round_tf32(mask_features_cl)
+    return mask_features_cl
+
+
+def mask_einsum(mask_embed, mask_features_cl, out=None, precision=None):
+    """mask_embed [T,Q,C], mask_features_cl [T,HW,C] (channel-last, from prepare_mask_features) -> [Q,T,HW].
+    TF32 policy -> tcgen05 kernel (mask_embed is rounded to nearest here); TF32X3 -> 3xTF32 register kernel."""
     T, Q, Cc = mask_embed.shape
     HW = mask_features_cl.shape[1]
+    prec = _default_precision if precision is None else precision
     if out is None:
         out = torch.empty((Q, T, HW), device=mask_embed.device, dtype=torch.float32)
-    with _Bracket("mask_einsum", 1):
-        rc = lib().univs_mask_einsum_f32(_stream(), _chk(mask_embed, "mask_embed"), _chk(mask_features_cl, "mask_features"),
-                                     T, Q, Cc, HW, _chk(out, "out"))
+    if prec == PREC_TF32:
+        e = round_tf32(mask_embed)
+        with _Bracket("mask_einsum", 1):
+            rc = lib().univs_mask_einsum_f32(_stream(), _chk(e, "mask_embed"), _chk(mask_features_cl, "mask_features"),
+                                             T, Q, Cc, HW, _chk(out, "out"))
+    else:
+        with _Bracket("mask_einsum", 1):
+            rc = lib().univs_mask_einsum_mma_f32(_stream(), _chk(mask_embed, "mask_embed"),
+                                                 _chk(mask_features_cl, "mask_features"), T, Q, Cc, HW, prec,
+                                                 _chk(out, "out"))
     check(rc, "mask_einsum")
     return out
 
 
-def mask_einsum_tc(mask_embed, mask_features_cl, out=None):
-    """tcgen05 variant (operands are consumed as TF32 by truncation; pre-round with round_tf32)."""
+def mask_einsum_mma(mask_embed, mask_features_cl, precision, out=None):
+    """register-operand variant, explicit precision (cross-check of the tcgen05 kernel)."""
     T, Q, Cc = mask_embed.shape
     HW = mask_features_cl.shape[1]
     if out is None:
         out = torch.empty((Q, T, HW), device=mask_embed.device, dtype=torch.float32)
     with _Bracket("mask_einsum", 1):
-        rc = lib().univs_mask_einsum_tc_f32(_stream(), _chk(mask_embed, "mask_embed"), _chk(mask_features_cl, "mask_features"),
-                                            T, Q, Cc, HW, _chk(out, "out"))
-    check(rc, "mask_einsum_tc")
+        rc = lib().univs_mask_einsum_mma_f32(_stream(), _chk(mask_embed, "mask_embed"),
+                                             _chk(mask_features_cl, "mask_features"), T, Q, Cc, HW, precision,
+                                             _chk(out, "out"))
+    check(rc, "mask_einsum_mma")
     return out
 
 
