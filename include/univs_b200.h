@@ -102,6 +102,18 @@ int univs_proca_forward_f32(void* stream, const float* q, const float* k_self, c
                             const float* k_mem, const float* v_mem, int prompts, int frames, int mem_frames,
                             int mem_len, int channels, float* out);
 
+/* ---- fused row-wise kernels around the library GEMMs -------------------------------------------------------
+ * "split" outputs are [rows, 2*C] = [hi | lo] with hi = upper 19 bits of the value (exact in TF32) and lo = x - hi:
+ * the operand format of the 3xTF32 (fp32-equivalent) GEMM policy, X*W^T ~= [Xh|Xl]*[Wh|Wh]^T + Xh*Wl^T.
+ * layernorm: s = x (+ residual, nullable); sum_out (nullable) = s; out = LayerNorm(s)*gamma+beta (nn.LayerNorm,
+ *   e.g. swin.py:246,292).  channels % 4 == 0, <= 4096.
+ * gelu: exact erf GELU (nn.GELU default, swin.py:24-41). */
+int univs_layernorm_f32(void* stream, const float* x, const float* residual, const float* gamma, const float* beta,
+                        int64_t rows, int channels, float eps, float* sum_out, float* out, int split);
+int univs_gelu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split);
+int univs_relu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split);
+int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, float* out);
+
 /* ---- helpers ---- */
 /* in-place/out-of-place round-to-nearest-even to TF32 (19-bit) of n floats */
 int univs_round_tf32_f32(void* stream, const float* in, float* out, int64_t n);

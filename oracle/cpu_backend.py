@@ -53,7 +53,24 @@ def _proca(q, ks, vs, km, vm):
     return ops_ref.proca_core(q, ks, vs, km, vm, q.shape[-1] // 32)
 
 
-_PATCH = {"swin_window_attention": _swin, "ms_deform_attn_encoder": _msda_enc, "ms_deform_attn_forward": _msda_fwd,
+def _split(x):
+    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)     # 0xFFFFE000
+    return torch.cat([hi, x - hi], -1)
+
+
+def _maybe_split(y, split):
+    return _split(y) if split else y
+
+
+def _layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=False):
+    s = x if residual is None else x + residual
+    y = torch.nn.functional.layer_norm(s, (x.shape[-1],), weight, bias, eps)
+    return (s if want_sum else None), _maybe_split(y, split)
+
+
+_PATCH = {"layernorm": _layernorm, "gelu": lambda x, split=False: _maybe_split(torch.nn.functional.gelu(x), split),
+          "relu": lambda x, split=False: _maybe_split(torch.relu(x), split), "split_tf32": _split,
+          "swin_window_attention": _swin, "ms_deform_attn_encoder": _msda_enc, "ms_deform_attn_forward": _msda_fwd,
           "mask_einsum": _einsum, "attn_mask_bits": _bits, "mha_core": _mha, "proca_core": _proca,
           "round_tf32": lambda x, out=None: x, "prepare_mask_features": lambda x: x}
 

@@ -222,3 +222,23 @@ def pos3d_sine_arbitrary_t(frame_indices, h, w, num_pos_feats=128, temperature=1
     pz = z[:, None] / dim_z
     pz = torch.stack((pz[:, 0::2].sin(), pz[:, 1::2].cos()), 2).flatten(1)   # [T,C]
     return base[None] + pz[:, :, None, None]
+
+
+# ---------------------------------------------------------------------------
+# fused row-wise kernels around the GEMMs (csrc/elementwise.cu)
+# ---------------------------------------------------------------------------
+def split_tf32(x):
+    """[..., C] -> [..., 2C] = [hi | lo]: hi keeps the upper 19 bits (sign, 8 exponent, 10 mantissa), lo = x - hi."""
+    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return torch.cat([hi, x - hi], -1)
+
+
+def layernorm(x, weight, bias, eps=1e-5, residual=None):
+    """nn.LayerNorm over the last dim of (x + residual) (swin.py:246,292; transformer_layers.py:42)."""
+    s = x if residual is None else x + residual
+    return s, F.layer_norm(s.double(), (x.shape[-1],), weight.double(), bias.double(), eps).float()
+
+
+def gelu(x):
+    """nn.GELU() default = exact erf form (swin.py:24-41)."""
+    return F.gelu(x.double()).float()

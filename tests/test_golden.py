@@ -62,8 +62,14 @@ def test_oracle_msda_matches_golden_reference_test_vectors():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(CASES))
-def test_cuda_model_matches_golden(name):
-    r = _run(name, "cuda")
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_cuda_model_matches_golden(name, precision):
+    from univs_b200.precision import set_precision
+    set_precision(precision)
+    try:
+        r = _run(name, "cuda")
+    finally:
+        set_precision("fp32")
     _compare(*r, tol_feat=1e-3, tol_out=1e-3)
 
 

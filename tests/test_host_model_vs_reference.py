@@ -150,3 +150,26 @@ def test_sot_visual_prompts_two_clips():
             assert ptg[0][k].shape == rtg[0][k].shape, (k, ptg[0][k].shape, rtg[0][k].shape)
             assert _rel(ptg[0][k], rtg[0][k]) < 1e-4, k
         assert torch.equal(ptg[0]["prompt_attn_masks"], rtg[0]["prompt_attn_masks"])
+
+
+def test_split_operand_policy_plumbing_on_cpu():
+    """The tf32x3 policy's hi|lo operand plumbing (fused LN/GELU/ReLU split outputs, cached split weights, split
+    convolution) reproduces the reference when every GEMM is an exact fp32 GEMM (CPU)."""
+    from univs_b200 import nn_ops
+    torch.manual_seed(0)
+    T, Q = 2, 8
+    ref, prod = _build_pair(mf.SMALL_SWIN7, T, Q, enc_layers=1, dec_layers=2)
+    x = torch.randn(T, 3, 64, 96)
+    tg = lambda: [{"task": "detection", "dataset_name": "bdd_track", "prompt_type": "text",
+                   "frame_indices": torch.arange(T)}]
+    rf, (rmf, rms), rout = ref_shim.reference_clip_forward(*ref, x, tg())
+    nn_ops.set_policy("tf32x3")
+    try:
+        with oracle_ops():
+            pf, (pmf, pms), pout = mf.product_clip_forward(*prod, x, tg())
+    finally:
+        nn_ops.set_policy("fp32")
+    assert _rel(pf["res5"], rf["res5"]) < 1e-4
+    assert _rel(pmf, rmf) < 1e-4
+    assert _rel(pout["pred_masks"], rout["pred_masks"]) < 1e-3
+    assert _rel(pout["pred_logits"], rout["pred_logits"]) < 1e-3

@@ -207,3 +207,51 @@ def test_round_tf32(ops):
     y = ops.round_tf32(x)
     assert (y.view(torch.int32) & 0x1FFF).eq(0).all()
     assert (y - x).abs().max() <= x.abs().max() * 2 ** -11
+
+
+# ------------------------------------------------------------------ fused row-wise kernels
+@pytest.mark.parametrize("rows,C", [(7, 32), (1000, 192), (333, 256), (65, 768), (40, 1536), (9, 3072), (3, 640)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_layernorm_fused(ops, rows, C, with_res):
+    torch.manual_seed(21)
+    x = torch.randn(rows, C) * 3 + 0.5
+    r = torch.randn(rows, C) if with_res else None
+    w, b = torch.randn(C), torch.randn(C)
+    s_want, y_want = ops_ref.layernorm(x, w, b, 1e-5, r)
+    s, y = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), want_sum=True)
+    assert _rel(y, y_want) < 2e-6
+    assert torch.equal(s.cpu(), s_want)
+    _, ys = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), split=True)
+    assert ys.shape == (rows, 2 * C)
+    assert torch.equal(ys.cpu(), ops_ref.split_tf32(y.cpu()))            # split of exactly the plain output
+    assert torch.equal(ys[:, :C] + ys[:, C:], y)                           # hi + lo == value, bit-exact
+    assert (ys[:, :C].view(torch.int32) & 0x1FFF).eq(0).all()              # hi is TF32-representable
+
+
+def test_gelu_relu_split(ops):
+    torch.manual_seed(22)
+    x = torch.randn(257, 768) * 2
+    assert _rel(ops.gelu(x.cuda()), ops_ref.gelu(x)) < 1e-6
+    gs = ops.gelu(x.cuda(), split=True)
+    assert torch.equal(gs.cpu(), ops_ref.split_tf32(ops.gelu(x.cuda()).cpu()))
+    assert torch.equal(ops.relu(x.cuda()).cpu(), torch.relu(x))
+    assert torch.equal(ops.split_tf32(x.cuda()).cpu(), ops_ref.split_tf32(x))
+    assert ops.layernorm(torch.zeros(0, 64).cuda(), torch.ones(64).cuda(), torch.zeros(64).cuda())[1].shape == (0, 64)
+
+
+def test_split_gemm_reproduces_fp32(ops):
+    """The 3xTF32 operand split makes a TF32 tensor-core GEMM fp32-equivalent (nn_ops.linear under tf32x3)."""
+    from univs_b200 import nn_ops
+    from univs_b200.precision import set_precision
+    torch.manual_seed(23)
+    x, w, b = torch.randn(4096, 768).cuda(), (torch.randn(384, 768) * 0.05).cuda(), torch.randn(384).cuda()
+    want = (x.double() @ w.double().t() + b.double()).float()
+    try:
+        set_precision("tf32x3")
+        y3 = nn_ops.linear(x, w, b)
+        set_precision("tf32")
+        y1 = nn_ops.linear(x, w, b)
+    finally:
+        set_precision("fp32")
+    assert _rel(y3, want) < 2e-6
+    assert _rel(y1, want) > 1e-5          # plain TF32 is visibly worse: the split is doing the work

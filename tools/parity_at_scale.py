@@ -35,7 +35,7 @@ cpu_s = time.time() - t0
 res = {"geometry": f"Swin-{variant} T={T} {H}x{W} Q={Q}", "cpu_oracle_seconds": cpu_s, "modes": {}}
 gpu_model = build_model(cfg).cuda()
 gpu_model.load_state_dict(cpu_model.state_dict())
-for mode in ("fp32", "tf32"):
+for mode in ("tf32x3", "fp32", "tf32"):
     set_precision(mode)
     x, _ = gpu_model.preprocess(frames.cuda())
     gf = gpu_model.backbone(x)

@@ -1,0 +1,159 @@
+// Fused row-wise kernels around the library GEMMs: residual-add + LayerNorm, exact GELU, and the TF32 hi|lo operand
+// split that lets TF32 tensor-core GEMMs reproduce fp32 products (3xTF32: X*W ~= Xh*Wh + Xl*Wh + Xh*Wl with
+// hi = upper 19 bits (exactly representable in TF32, so the tensor core's truncation is lossless) and lo = x - hi).
+//
+//   layernorm : s = x (+ residual);  [sum_out = s];  out = LN(s) * gamma + beta, written plain [rows,C] or split
+//               [rows,2C] = [hi | lo]              (reference: nn.LayerNorm sites swin.py:246,292; msdeformattn.py:126-133;
+//                                                    transformer_layers.py:42,113,176; decoder_norm ..._univs.py:500)
+//   gelu      : out = 0.5*x*(1+erf(x/sqrt(2))) (nn.GELU default, swin.py:24-41), plain or split
+//   split     : out = [hi | lo]
+// One warp per row, 128-bit loads/stores, the row is held in registers (single read of x), two-pass mean/variance
+// with warp-shuffle reductions.  All three are pure HBM streams.
+#include "common.cuh"
+
+namespace univs {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__device__ __forceinline__ void store_maybe_split(float* __restrict__ out, size_t row, int C, int col, float4 v, bool split) {
+  if (!split) {
+    *reinterpret_cast<float4*>(out + row * C + col) = v;
+  } else {
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    *reinterpret_cast<float4*>(out + row * (2 * (size_t)C) + col) = h;
+    *reinterpret_cast<float4*>(out + row * (2 * (size_t)C) + C + col) = l;
+  }
+}
+
+template <int MAXV>  // float4 per lane; C <= MAXV*128
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, long long rows, int C, float eps, float* __restrict__ sum_out,
+                 float* __restrict__ out, int split) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = C >> 2;  // float4 per row
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      float4 a = *reinterpret_cast<const float4*>(x + row * C + idx * 4);
+      if (res != nullptr) {
+        const float4 b = *reinterpret_cast<const float4*>(res + row * C + idx * 4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (sum_out != nullptr) *reinterpret_cast<float4*>(sum_out + row * C + idx * 4) = a;
+      v[i] = a;
+      s += (a.x + a.y) + (a.z + a.w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float4 gm = ldg_f4(gamma + idx * 4), bt = ldg_f4(beta + idx * 4);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+      o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+      o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+      o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+      store_maybe_split(out, (size_t)row, C, idx * 4, o, split != 0);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gelu_split_kernel(const float* __restrict__ x, long long rows, int C, float* __restrict__ out, int do_gelu, int split) {
+  const int nv = C >> 2;
+  const long long total = rows * nv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nv;
+    const int col = (int)(i - row * nv) * 4;
+    float4 a = *reinterpret_cast<const float4*>(x + row * C + col);
+    if (do_gelu == 2) {
+      a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+    } else if (do_gelu == 1) {
+      a.x = 0.5f * a.x * (1.f + erff(a.x * 0.70710678118654752440f));
+      a.y = 0.5f * a.y * (1.f + erff(a.y * 0.70710678118654752440f));
+      a.z = 0.5f * a.z * (1.f + erff(a.z * 0.70710678118654752440f));
+      a.w = 0.5f * a.w * (1.f + erff(a.w * 0.70710678118654752440f));
+    }
+    store_maybe_split(out, (size_t)row, C, col, a, split != 0);
+  }
+}
+
+}  // namespace univs
+
+using namespace univs;
+
+extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* residual, const float* gamma,
+                                   const float* beta, int64_t rows, int channels, float eps, float* sum_out, float* out,
+                                   int split) {
+  UNIVS_REQUIRE(rows >= 0 && channels > 0, "layernorm: bad sizes");
+  if (rows == 0) return UNIVS_OK;
+  UNIVS_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
+  UNIVS_REQUIRE(channels % 4 == 0 && channels <= 4096, "layernorm: channels must be a multiple of 4 and <= 4096 (got %d)", channels);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LN_LAUNCH(MV) layernorm_kernel<MV><<<grid, 256, 0, st>>>(x, residual, gamma, beta, rows, channels, eps, sum_out, out, split)
+  if (channels <= 128) LN_LAUNCH(1);
+  else if (channels <= 256) LN_LAUNCH(2);
+  else if (channels <= 512) LN_LAUNCH(4);
+  else if (channels <= 1024) LN_LAUNCH(8);
+  else if (channels <= 2048) LN_LAUNCH(16);
+  else LN_LAUNCH(32);
+#undef LN_LAUNCH
+  return check_launch("layernorm");
+}
+
+extern "C" int univs_gelu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split) {
+  UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "gelu: bad sizes (channels %% 4 == 0)");
+  if (rows == 0) return UNIVS_OK;
+  UNIVS_REQUIRE(x && out, "gelu: null pointer");
+  long long blocks = (rows * (channels / 4) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, channels, out, 1, split);
+  return check_launch("gelu");
+}
+
+extern "C" int univs_relu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split) {
+  UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "relu: bad sizes (channels %% 4 == 0)");
+  if (rows == 0) return UNIVS_OK;
+  UNIVS_REQUIRE(x && out, "relu: null pointer");
+  long long blocks = (rows * (channels / 4) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, channels, out, 2, split);
+  return check_launch("relu");
+}
+
+extern "C" int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, float* out) {
+  UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "split_tf32: bad sizes (channels %% 4 == 0)");
+  if (rows == 0) return UNIVS_OK;
+  UNIVS_REQUIRE(x && out, "split_tf32: null pointer");
+  long long blocks = (rows * (channels / 4) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, channels, out, 0, 1);
+  return check_launch("split_tf32");
+}

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import nn_ops, ops
 from ..registry import BACKBONE_REGISTRY, ShapeSpec
 
 
@@ -55,13 +55,20 @@ class _Block(nn.Module):
         self.norm2 = nn.LayerNorm(dim)
         self.mlp = _Mlp(dim, int(dim * mlp_ratio))
 
-    def forward(self, x):                      # x: [N,H,W,C]
+    def forward(self, x, pending):
+        """x: residual stream [N,H,W,C]; pending: branch output still to be added to it (or None).  The residual add
+        is fused into the LayerNorm that follows it; LayerNorm / GELU outputs are emitted in the GEMM operand format
+        of the active policy (nn_ops)."""
         a = self.attn
-        qkv = a.qkv(self.norm1(x))
+        x, h = nn_ops.layernorm(x, self.norm1, residual=pending, want_sum=True)
+        qkv = nn_ops.linear_prepped(h, a.qkv.weight, a.qkv.bias)
         bias = a.qkv.bias if a.qkv.bias is not None else x.new_zeros(qkv.shape[-1])
         y = ops.swin_window_attention(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift)
-        x = x + a.proj(y)
-        return x + self.mlp.fc2(F.gelu(self.mlp.fc1(self.norm2(x))))
+        y = nn_ops.linear(y, a.proj.weight, a.proj.bias)
+        x, h = nn_ops.layernorm(x, self.norm2, residual=y, want_sum=True)
+        f = nn_ops.linear_prepped(h, self.mlp.fc1.weight, self.mlp.fc1.bias)
+        z = nn_ops.linear_prepped(nn_ops.gelu(f), self.mlp.fc2.weight, self.mlp.fc2.bias)
+        return x, z
 
 
 class _PatchMerging(nn.Module):
@@ -77,7 +84,8 @@ class _PatchMerging(nn.Module):
         if H % 2 or W % 2:
             x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
         x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
-        return self.reduction(self.norm(x))
+        _, h = nn_ops.layernorm(x, self.norm)
+        return nn_ops.linear_prepped(h, self.reduction.weight, None)
 
 
 class _Stage(nn.Module):
@@ -87,10 +95,17 @@ class _Stage(nn.Module):
             _Block(dim, heads, window, 0 if i % 2 == 0 else window // 2, mlp_ratio, qkv_bias) for i in range(depth))
         self.downsample = _PatchMerging(dim) if downsample else None
 
-    def forward(self, x):
+    def forward(self, x, out_norm=None):
+        """-> (norm_i(x_out) or None, x_out or downsample(x_out))"""
+        pending = None
         for blk in self.blocks:
-            x = blk(x)
-        return x, (self.downsample(x) if self.downsample is not None else x)
+            x, pending = blk(x, pending)
+        y = None
+        if out_norm is not None:
+            x, y = nn_ops.layernorm(x, out_norm, residual=pending, want_sum=True, for_gemm=False)
+        else:
+            x = x + pending
+        return y, (self.downsample(x) if self.downsample is not None else x)
 
 
 class _PatchEmbed(nn.Module):
@@ -107,8 +122,9 @@ class _PatchEmbed(nn.Module):
         _, _, H, W = x.shape
         if W % p or H % p:
             x = F.pad(x, (0, (p - W % p) % p, 0, (p - H % p) % p))
-        x = self.proj(x).permute(0, 2, 3, 1)
-        return self.norm(x) if self.norm is not None else x.contiguous()
+        with nn_ops.ieee_fp32():                      # 3->E 4x4 patch projection: tiny, kept in exact fp32
+            x = self.proj(x).permute(0, 2, 3, 1).contiguous()
+        return nn_ops.layernorm(x, self.norm, for_gemm=False)[1] if self.norm is not None else x
 
 
 class SwinTransformer(nn.Module):
@@ -139,10 +155,9 @@ class SwinTransformer(nn.Module):
         x = self.patch_embed(x)
         outs = {}
         for i, stage in enumerate(self.layers):
-            x_out, x = stage(x)
-            if i in self.out_indices:
-                y = getattr(self, f"norm{i}")(x_out)           # [N,H,W,C] contiguous
-                outs[f"res{i + 2}"] = y.permute(0, 3, 1, 2)   # NCHW view of channel-last storage
+            y, x = stage(x, getattr(self, f"norm{i}") if i in self.out_indices else None)
+            if y is not None:                                   # [N,H,W,C] contiguous
+                outs[f"res{i + 2}"] = y.permute(0, 3, 1, 2)    # NCHW view of channel-last storage
         return outs
 
 

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import nn_ops, ops
 from ..registry import TRANSFORMER_DECODER_REGISTRY, is_cfg
 from . import position
 from .prompt_sampler import VisualPromptSampler
@@ -88,7 +88,9 @@ class _FFNLayer(nn.Module):               # transformer_layers.py:151-191 (post-
         nn.init.xavier_uniform_(self.linear2.weight)
 
     def forward(self, x):
-        return self.norm(x + self.linear2(F.relu(self.linear1(x))))
+        f = nn_ops.linear(x, self.linear1.weight, self.linear1.bias)
+        z = nn_ops.linear_prepped(nn_ops.relu(f), self.linear2.weight, self.linear2.bias)
+        return nn_ops.layernorm(x, self.norm, residual=z, for_gemm=False)[1]
 
 
 class _MLP(nn.Module):                    # transformer_layers.py:205-217
@@ -97,12 +99,13 @@ class _MLP(nn.Module):                    # transformer_layers.py:205-217
         dims = [din] + [dh] * (n - 1) + [dout]
         self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
 
-    def forward(self, x):
+    def forward(self, x, prepped=False):
+        h = x if prepped else nn_ops.prep(x)
         for i, l in enumerate(self.layers):
-            x = l(x)
+            y = nn_ops.linear_prepped(h, l.weight, l.bias)
             if i < len(self.layers) - 1:
-                x = F.relu(x)
-        return x
+                h = nn_ops.relu(y)
+        return y
 
 
 @TRANSFORMER_DECODER_REGISTRY.register()
@@ -251,9 +254,10 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
     def _cross_attention(self, layer, x, qpos, k, v, bits, row_open):
         mha = layer.multihead_attn
         wq, bq = mha.wq()
-        q = F.linear(x + qpos, wq, bq)
+        q = nn_ops.linear(x + qpos, wq, bq)
         a = ops.mha_core(q, k, v, bits, row_open)
-        return layer.norm(x + mha.out_proj(a))
+        o = nn_ops.linear(a, mha.out_proj.weight, mha.out_proj.bias)
+        return nn_ops.layernorm(x, layer.norm, residual=o, for_gemm=False)[1]
 
     def _self_attention(self, layer, x, qpos, bits):
         """x, qpos: [T,Q,C] -> tokens (q*T + t) (..._univs.py:408-416)"""
@@ -262,11 +266,12 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         xs = x.transpose(0, 1).reshape(1, Q * T, C)
         ps = qpos.transpose(0, 1).reshape(1, Q * T, C)
         wqk, bqk = mha.wqk()
-        qk = F.linear(xs + ps, wqk, bqk)
+        qk = nn_ops.linear(xs + ps, wqk, bqk)
         wv, bv = mha.wv()
-        v = F.linear(xs, wv, bv)
+        v = nn_ops.linear(xs, wv, bv)
         a = ops.mha_core(qk[..., :C].contiguous(), qk[..., C:].contiguous(), v, bits, None)
-        y = layer.norm(xs + mha.out_proj(a))
+        o = nn_ops.linear(a, mha.out_proj.weight, mha.out_proj.bias)
+        y = nn_ops.layernorm(xs.contiguous(), layer.norm, residual=o, for_gemm=False)[1]
         return y.view(Q, T, C).transpose(0, 1).contiguous()
 
     def _proca(self, i, x, qpos, mem, mem_pe):
@@ -278,42 +283,46 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         mha = layer.multihead_attn
         tok = x[:, nq:].transpose(0, 1).contiguous()                      # [P,T,C]
         wq, bq = mha.wq(); wk, bk = mha.wk(); wv, bv = mha.wv()
+        lin = nn_ops.linear_prepped
+        tk = nn_ops.prep(tok)
+        mm = nn_ops.prep(mem)
         if mem_pe is not None:
-            qe = qpos[:, nq:].transpose(0, 1)
-            q = F.linear(tok + qe, wq, bq)
-            k_self = F.linear(tok + qe, wk, bk)
-            k_mem = F.linear(mem + mem_pe, wk, bk)
+            tq = nn_ops.prep(tok + qpos[:, nq:].transpose(0, 1))
+            q, k_self = lin(tq, wq, bq), lin(tq, wk, bk)
+            k_mem = nn_ops.linear(mem + mem_pe, wk, bk)
         else:
-            q = F.linear(tok, wq, bq)
-            k_self = F.linear(tok, wk, bk)
-            k_mem = F.linear(mem, wk, bk)
-        v_self = F.linear(tok, wv, bv)
-        v_mem = F.linear(mem, wv, bv)
+            q, k_self = lin(tk, wq, bq), lin(tk, wk, bk)
+            k_mem = lin(mm, wk, bk)
+        v_self = lin(tk, wv, bv)
+        v_mem = lin(mm, wv, bv)
         a = ops.proca_core(q.contiguous(), k_self.contiguous(), v_self.contiguous(), k_mem.contiguous(), v_mem.contiguous())
-        y = layer.norm(tok + mha.out_proj(a))                              # [P,T,C]
+        o = nn_ops.linear(a, mha.out_proj.weight, mha.out_proj.bias)
+        y = nn_ops.layernorm(tok, layer.norm, residual=o, for_gemm=False)[1]   # [P,T,C]
         return torch.cat([x[:, :nq], y.transpose(0, 1)], 1)
 
     def _heads(self, x, feats_cl, hw, next_hw, task, targets, t, need_class, need_attn, out_buf=None):
         """forward_prediction_heads (:498-567).  x [T,Q,C] -> (class logits | None, mask logits [Q,T,HW], bits, row_open, reid)"""
-        dec = self.decoder_norm(x)
+        dec, dec_g = nn_ops.layernorm(x, self.decoder_norm, want_sum=False, for_gemm=False)[1], None
+        dec_g = nn_ops.prep(dec)                                            # GEMM operand of decoder_norm(x)
         cls, reid = None, [None]
         if need_class or (task == "grounding" and self.prompt_as_queries):
-            oc = self.vis2text_projection(dec)                              # [T,Q,640]
+            oc = nn_ops.linear_prepped(dec_g, self.vis2text_projection.weight, self.vis2text_projection.bias)   # [T,Q,640]
             if task != "grounding":
                 if need_class:
                     clip = self._clip_normalized(x.device)
                     # mean over T commutes with the (linear) class einsum: average first, 1/T of the work
-                    cls = (F.normalize(oc, p=2, dim=-1).mean(0, keepdim=True) @ clip.t()) * self.cls_temp.weight.exp()
+                    cls = nn_ops.linear(F.normalize(oc, p=2, dim=-1).mean(0, keepdim=True), clip) * self.cls_temp.weight.exp()
             else:
                 exp = torch.stack([tg["exp_sentence_feats"][:, 0] for tg in targets]).to(oc)      # [1,P,640]
-                cls = torch.einsum("bqc,bkc->bqk", oc.mean(0, keepdim=True), exp)
-        emb = self.mask_embed(dec)                                          # [T,Q,C]
+                cls = nn_ops.linear(oc.mean(0, keepdim=True), exp[0].contiguous(), cache=False)
+        emb = self.mask_embed(dec_g, prepped=True)                          # [T,Q,C]
         logits = ops.mask_einsum(emb.contiguous(), feats_cl, out=out_buf)   # [Q,T,HW]
         if task == "grounding" and self.prompt_as_queries:
             # learnable-for-prompt mask fusion (:537-547)
             nq = self.num_queries
             on = F.normalize(dec, p=2, dim=-1)
-            reid = torch.einsum("tqc,tkc->tqk", on, on[:, nq:]).mean(0, keepdim=True)      # [1,Q,P]
+            with nn_ops.ieee_fp32():
+                reid = torch.einsum("tqc,tkc->tqk", on, on[:, nq:]).mean(0, keepdim=True)  # [1,Q,P]
             idx = reid[0, :nq].argmax(0)
             logits[nq:] = (logits[nq:] + logits[idx]) / 2.0
         bits = row_open = None
@@ -330,8 +339,10 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         mha = layer.multihead_attn
         mem = torch.cat(src, 1)
         wq, bq = mha.wq(); wk, bk = mha.wk(); wv, bv = mha.wv()
-        a = ops.mha_core(F.linear(feats, wq, bq), F.linear(mem, wk, bk), F.linear(mem, wv, bv))
-        return layer.norm(feats + mha.out_proj(a))
+        mm = nn_ops.prep(mem)
+        a = ops.mha_core(nn_ops.linear(feats, wq, bq), nn_ops.linear_prepped(mm, wk, bk), nn_ops.linear_prepped(mm, wv, bv))
+        o = nn_ops.linear(a, mha.out_proj.weight, mha.out_proj.bias)
+        return nn_ops.layernorm(feats.contiguous(), layer.norm, residual=o, for_gemm=False)[1]
 
     def _prompt_encoder(self, src, pos, size_list, targets, t):
         """forward_prompt_encoder (:599-758), inference branches.
@@ -365,7 +376,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
             n_cls, start = COMBINED_DATASETS_CATEGORY_INFO[name]
             emb = self.clip_cls_text_emb.to(device)[start:start + n_cls].float()
             assert len(emb) == n_cls, f"Dismatch numbers of class, {len(emb)} and {n_cls}"
-            f = self.text2vis_projection(self.text_norm(emb))               # [P,C]
+            f = nn_ops.linear_prepped(nn_ops.layernorm(emb, self.text_norm)[1], self.text2vis_projection.weight,
+                                      self.text2vis_projection.bias)            # [P,C]
             feats = f[None].expand(t, -1, -1).contiguous()                  # [T,P,C]
             if self.text_prompt_to_image_enable:
                 feats = self._lang_to_vision(feats, src)
@@ -379,7 +391,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
             sent = tg["exp_sentence_feats"][..., :t, :].to(device)          # [P,T,640]
             P, Lw = words.shape[:2]
             ef = torch.cat([sent[:, None], words], 1)                       # [P,78,T,640]
-            f = self.text2vis_projection(self.text_norm(ef.float()))        # [P,78,T,C]
+            f = nn_ops.linear_prepped(nn_ops.layernorm(ef.float(), self.text_norm)[1], self.text2vis_projection.weight,
+                                      self.text2vis_projection.bias)            # [P,78,T,C]
             feats = f.permute(2, 0, 1, 3).reshape(t, P * (Lw + 1), -1).contiguous()   # [T, P*78, C]
             if self.text_prompt_to_image_enable:
                 feats = self._lang_to_vision(feats, src)
@@ -430,7 +443,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
 
         def record(cls, logits, reid, emb):
             aux.append({"pred_logits": cls, "pred_masks": logits.view(1, n_lp, t, h_m, w_m).clone(),
-                        "pred_reid_logits": reid, "pred_embds": self.decoder_norm(emb.transpose(0, 1))[None]})
+                        "pred_reid_logits": reid,
+                        "pred_embds": nn_ops.layernorm(emb.transpose(0, 1), self.decoder_norm, for_gemm=False)[1][None]})
 
         hw = (h_m, w_m)
         cls, logits, bits, row_open, reid = self._heads(out, feats_cl, hw, size_list[0], task, targets, t, want_aux, True)
@@ -443,8 +457,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
             lvl = i % 3
             ca = self.transformer_cross_attention_layers[i].multihead_attn
             wk, bk = ca.wk(); wv, bv = ca.wv()
-            k = F.linear(src[lvl] + pos[lvl], wk, bk)
-            v = F.linear(src[lvl], wv, bv)
+            k = nn_ops.linear(src[lvl] + pos[lvl], wk, bk)
+            v = nn_ops.linear(src[lvl], wv, bv)
             out = self._cross_attention(self.transformer_cross_attention_layers[i], out, qpos, k, v, bits, row_open)
             out = self._self_attention(self.transformer_self_attention_layers[i], out, qpos, sa_bits)
             out = self.transformer_ffn_layers[i](out)
@@ -453,7 +467,7 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
                 out, feats_cl, hw, size_list[(i + 1) % 3], task, targets, t, want_aux or last, not last, out_buf=logits)
             if want_aux and not last:
                 record(cls, logits, reid, out)
-        embds = self.decoder_norm(out.transpose(0, 1))[None]                # [1,Q,T,C]
+        embds = nn_ops.layernorm(out.transpose(0, 1), self.decoder_norm, for_gemm=False)[1][None]   # [1,Q,T,C]
         result = {
             "pred_logits": cls,
             "pred_masks": logits.view(1, n_lp, t, h_m, w_m),

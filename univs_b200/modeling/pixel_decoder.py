@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import nn_ops, ops
 from ..registry import SEM_SEG_HEADS_REGISTRY, is_cfg
 from . import position
 
@@ -71,12 +71,15 @@ class _EncoderLayer(nn.Module):
     def forward(self, src, pos, shapes, starts):
         a = self.self_attn
         N, S, C = src.shape
-        value = a.value_proj(src).view(N, S, a.n_heads, C // a.n_heads)
+        value = nn_ops.linear(src, a.value_proj.weight, a.value_proj.bias).view(N, S, a.n_heads, C // a.n_heads)
         w, b = a.fused_offs_logits()
-        offs_logits = F.linear(src + pos, w, b)
+        offs_logits = nn_ops.linear(src + pos, w, b)
         y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points)
-        src = self.norm1(src + a.output_proj(y))
-        return self.norm2(src + self.linear2(F.relu(self.linear1(src))))
+        o = nn_ops.linear(y, a.output_proj.weight, a.output_proj.bias)
+        src = nn_ops.layernorm(src, self.norm1, residual=o, for_gemm=False)[1]
+        f = nn_ops.linear(src, self.linear1.weight, self.linear1.bias)
+        z = nn_ops.linear_prepped(nn_ops.relu(f), self.linear2.weight, self.linear2.bias)
+        return nn_ops.layernorm(src, self.norm2, residual=z, for_gemm=False)[1]
 
 
 class _Encoder(nn.Module):
@@ -106,11 +109,18 @@ class _ConvNorm(nn.Conv2d):
         self.norm = norm
         self.act = act
 
-    def forward(self, x):
-        x = F.conv2d(x, self.weight, self.bias, self.stride, self.padding)
+    def forward_cl(self, x_cl):
+        """x_cl [N,H,W,Cin] channel-last -> [N,H,W,Cout] channel-last (conv -> norm -> act)."""
+        N, H, W, Cin = x_cl.shape
+        if self.kernel_size == (1, 1):
+            y = nn_ops.linear(x_cl, self.weight.view(self.out_channels, Cin), self.bias)
+        else:
+            y = nn_ops.conv2d_cl(x_cl, self.weight, self.bias, padding=self.padding)
         if self.norm is not None:
-            x = self.norm(x)
-        return self.act(x) if self.act is not None else x
+            y = self.norm(y.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)        # GroupNorm on the NCHW view
+        if self.act is not None:
+            y = self.act(y)
+        return y if y.is_contiguous() else y.contiguous()
 
 
 @SEM_SEG_HEADS_REGISTRY.register()
@@ -181,11 +191,15 @@ class MSDeformAttnPixelDecoder(nn.Module):
         tokens, poss, shapes = [], [], []
         for idx, f in enumerate(self.transformer_in_features[::-1]):      # res5, res4, res3
             x = features[f].float()
-            y = self.input_proj[idx](x)                                     # conv1x1 + GroupNorm, NCHW
-            n, c, h, w = y.shape
+            n, cin, h, w = x.shape
+            xt = x.permute(0, 2, 3, 1)                                      # channel-last view (copy only if NCHW)
+            xt = (xt if xt.is_contiguous() else xt.contiguous()).view(n, h * w, cin)
+            conv, gn = self.input_proj[idx][0], self.input_proj[idx][1]
+            y = nn_ops.linear(xt, conv.weight.view(conv.out_channels, cin), conv.bias)     # 1x1 conv
+            y = gn(y.transpose(1, 2)).transpose(1, 2)                        # GroupNorm(32) per frame
             shapes.append((h, w))
-            tokens.append(y.flatten(2).transpose(1, 2))                     # [N,hw,C]
-            poss.append(position.sine_2d(h, w, y.device, c // 2) + self.transformer.level_embed[idx])
+            tokens.append(y)                                                 # [N,hw,C]
+            poss.append(position.sine_2d(h, w, y.device, y.shape[-1] // 2) + self.transformer.level_embed[idx])
         src = torch.cat(tokens, 1).contiguous()
         pos = torch.cat(poss, 0).unsqueeze(0)                               # [1,Len,C] (frame-invariant)
         starts = [0]
@@ -194,19 +208,16 @@ class MSDeformAttnPixelDecoder(nn.Module):
         for layer in self.transformer.encoder.layers:
             src = layer(src, pos, shapes, starts)
         n = src.shape[0]
-        out = []
+        out_cl = []
         for i, (h, w) in enumerate(shapes):
-            z = src[:, starts[i]:starts[i] + h * w]                         # [N,hw,C] token-major
-            out.append(z.reshape(n, h, w, -1).permute(0, 3, 1, 2))          # NCHW view of channel-last storage
+            out_cl.append(src[:, starts[i]:starts[i] + h * w].reshape(n, h, w, -1))     # channel-last [N,h,w,C]
         for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
-            x = features[f].float().contiguous(memory_format=torch.channels_last)
-            cur = self.lateral_convs[idx](x)
-            up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
-            y = self.output_convs[idx]((cur + up).contiguous(memory_format=torch.channels_last))
-            out.append(y)
+            x = features[f].float().permute(0, 2, 3, 1)
+            x = x if x.is_contiguous() else x.contiguous()
+            cur = self.lateral_convs[idx].forward_cl(x)
+            up = F.interpolate(out_cl[-1].permute(0, 3, 1, 2), size=cur.shape[1:3], mode="bilinear", align_corners=False)
+            out_cl.append(self.output_convs[idx].forward_cl(cur + up.permute(0, 2, 3, 1)))
+        out = [o.permute(0, 3, 1, 2) for o in out_cl]                       # NCHW views of channel-last storage
         multi_scale = out[:self.maskformer_num_feature_levels]
-        last = out[-1].contiguous(memory_format=torch.channels_last)
-        mask_features = self.mask_features(last)                             # channels-last storage, NCHW shape
-        if not mask_features.is_contiguous(memory_format=torch.channels_last):
-            mask_features = mask_features.contiguous(memory_format=torch.channels_last)
+        mask_features = self.mask_features.forward_cl(out_cl[-1]).permute(0, 3, 1, 2)
         return mask_features, out[-1], out[0], multi_scale

@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+from .. import nn_ops
 from . import position
 
 
@@ -84,7 +85,8 @@ def _mask_prompt(sampler, feat, pe, masks, boxes, key_fid, key_fid_original, T, 
     fm = F.interpolate(masks.float().unsqueeze(1), (h, w), mode="nearest").squeeze(1)          # [Q,h,w]
     fm_bin = fm >= min(0.5, float(fm.max()))
     wgt = (fm * fm_bin).flatten(1)
-    key_feat = (wgt @ feat) / wgt.sum(-1).clamp(min=0.5)[:, None]                               # [Q,C]
+    with nn_ops.ieee_fp32():
+        key_feat = (wgt @ feat) / wgt.sum(-1).clamp(min=0.5)[:, None]                           # [Q,C]
     q_feat = key_feat[:, None].repeat(1, T, 1)
     attn = torch.zeros((T, 1, Q, h * w), dtype=torch.bool, device=dev)
     attn[key_fid, 0] = ~box_to_mask(boxes, h, w).flatten(-2)

@@ -228,6 +228,51 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
     return out
 
 
+def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=False):
+    """Fused (residual add +) LayerNorm over the last dim.  Returns (sum_or_None, out); `out` is [..., C] or, with
+    split=True, [..., 2C] = [hi | lo] (operand format of the 3xTF32 GEMM policy)."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
+    s = torch.empty_like(x) if (want_sum and residual is not None) else None
+    with _Bracket("layernorm", 1):
+        rc = lib().univs_layernorm_f32(_stream(), _chk(x, "x"), None if residual is None else _chk(residual, "residual"),
+                                       _chk(weight, "weight"), _chk(bias, "bias"), rows, C, float(eps),
+                                       None if s is None else s.data_ptr(), out.data_ptr(), int(split))
+    check(rc, "layernorm")
+    if want_sum and residual is None:
+        s = x
+    return s, out
+
+
+def gelu(x, split=False):
+    C = x.shape[-1]
+    out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
+    with _Bracket("gelu", 1):
+        rc = lib().univs_gelu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), int(split))
+    check(rc, "gelu")
+    return out
+
+
+def relu(x, split=False):
+    C = x.shape[-1]
+    out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
+    with _Bracket("relu", 1):
+        rc = lib().univs_relu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), int(split))
+    check(rc, "relu")
+    return out
+
+
+def split_tf32(x):
+    """[..., C] -> [..., 2C] = [hi | lo]"""
+    C = x.shape[-1]
+    out = torch.empty((*x.shape[:-1], 2 * C), device=x.device, dtype=torch.float32)
+    with _Bracket("split_tf32", 1):
+        rc = lib().univs_split_tf32_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr())
+    check(rc, "split_tf32")
+    return out
+
+
 def round_tf32(x, out=None):
     if out is None:
         out = torch.empty_like(x)
