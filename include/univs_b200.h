@@ -103,8 +103,11 @@ int univs_proca_forward_f32(void* stream, const float* q, const float* k_self, c
                             int mem_len, int channels, float* out);
 
 /* ---- fused row-wise kernels around the library GEMMs -------------------------------------------------------
- * "split" outputs are [rows, 2*C] = [hi | lo] with hi = upper 19 bits of the value (exact in TF32) and lo = x - hi:
- * the operand format of the 3xTF32 (fp32-equivalent) GEMM policy, X*W^T ~= [Xh|Xl]*[Wh|Wh]^T + Xh*Wl^T.
+ * `split` = 0 writes plain [rows, C]; `split` = Kc > 0 (Kc | C, Kc % 4 == 0) writes [rows, 2*C] in K-chunks of Kc
+ * columns, chunk c = [hi_c | lo_c] with hi = the value rounded to nearest TF32 and lo = x - hi: the operand format
+ * of the 3xTF32 (fp32-equivalent) GEMM policy, X*W^T ~= sum_c ([Xh|Xl]_c*[Wh|Wh]_c^T + Xh_c*Wl_c^T).  K is chunked
+ * because the tensor cores accumulate with truncation: the bias grows linearly with the accumulation chain
+ * (tools/accum_probe.py), so chains are kept <= Kc/8 MMA steps and chunks are summed in the fp32 epilogue.
  * layernorm: s = x (+ residual, nullable); sum_out (nullable) = s; out = LayerNorm(s)*gamma+beta (nn.LayerNorm,
  *   e.g. swin.py:246,292).  channels % 4 == 0, <= 4096.
  * gelu: exact erf GELU (nn.GELU default, swin.py:24-41). */
@@ -112,7 +115,7 @@ int univs_layernorm_f32(void* stream, const float* x, const float* residual, con
                         int64_t rows, int channels, float eps, float* sum_out, float* out, int split);
 int univs_gelu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split);
 int univs_relu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split);
-int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, float* out);
+int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, int chunk, float* out);
 
 /* ---- helpers ---- */
 /* in-place/out-of-place round-to-nearest-even to TF32 (19-bit) of n floats */

@@ -53,9 +53,23 @@ def _proca(q, ks, vs, km, vm):
     return ops_ref.proca_core(q, ks, vs, km, vm, q.shape[-1] // 32)
 
 
-def _split(x):
-    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)     # 0xFFFFE000
-    return torch.cat([hi, x - hi], -1)
+def _chunk(K):
+    if K <= 256:
+        return K
+    for c in range(256, 31, -32):
+        if K % c == 0:
+            return c
+    return K
+
+
+def _split(x, chunk=None):
+    b = x.contiguous().view(torch.int32)
+    mag = ((b & 0x7FFFFFFF) + 0x1000) & -8192              # round-to-nearest (ties away), cvt.rna.tf32.f32
+    hi = (mag | (b & -2147483648)).view(torch.float32)
+    C = x.shape[-1]
+    kc = _chunk(C) if chunk is None else chunk
+    hl = torch.stack([hi.reshape(*x.shape[:-1], C // kc, kc), (x - hi).reshape(*x.shape[:-1], C // kc, kc)], -2)
+    return hl.reshape(*x.shape[:-1], 2 * C)
 
 
 def _maybe_split(y, split):

@@ -227,10 +227,24 @@ def pos3d_sine_arbitrary_t(frame_indices, h, w, num_pos_feats=128, temperature=1
 # ---------------------------------------------------------------------------
 # fused row-wise kernels around the GEMMs (csrc/elementwise.cu)
 # ---------------------------------------------------------------------------
-def split_tf32(x):
-    """[..., C] -> [..., 2C] = [hi | lo]: hi keeps the upper 19 bits (sign, 8 exponent, 10 mantissa), lo = x - hi."""
-    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
-    return torch.cat([hi, x - hi], -1)
+def _chunk(K):
+    if K <= 256:
+        return K
+    for c in range(256, 31, -32):
+        if K % c == 0:
+            return c
+    return K
+
+
+def split_tf32(x, chunk=None):
+    """[..., C] -> [..., 2C] in K-chunks [hi_c | lo_c]: hi = x rounded to nearest TF32 (cvt.rna.tf32.f32), lo = x - hi."""
+    b = x.contiguous().view(torch.int32)
+    mag = ((b & 0x7FFFFFFF) + 0x1000) & -8192              # round-to-nearest (ties away), cvt.rna.tf32.f32
+    hi = (mag | (b & -2147483648)).view(torch.float32)
+    C = x.shape[-1]
+    kc = _chunk(C) if chunk is None else chunk
+    hl = torch.stack([hi.reshape(*x.shape[:-1], C // kc, kc), (x - hi).reshape(*x.shape[:-1], C // kc, kc)], -2)
+    return hl.reshape(*x.shape[:-1], 2 * C)
 
 
 def layernorm(x, weight, bias, eps=1e-5, residual=None):

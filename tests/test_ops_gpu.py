@@ -224,8 +224,10 @@ def test_layernorm_fused(ops, rows, C, with_res):
     _, ys = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), split=True)
     assert ys.shape == (rows, 2 * C)
     assert torch.equal(ys.cpu(), ops_ref.split_tf32(y.cpu()))            # split of exactly the plain output
-    assert torch.equal(ys[:, :C] + ys[:, C:], y)                           # hi + lo == value, bit-exact
-    assert (ys[:, :C].view(torch.int32) & 0x1FFF).eq(0).all()              # hi is TF32-representable
+    kc = ops.split_chunk(C)
+    v = ys.view(rows, C // kc, 2, kc)
+    assert torch.equal((v[:, :, 0] + v[:, :, 1]).reshape(rows, C), y)      # hi + lo == value, bit-exact
+    assert (v[:, :, 0].contiguous().view(torch.int32) & 0x1FFF).eq(0).all()   # hi is TF32-representable
 
 
 def test_gelu_relu_split(ops):
@@ -253,5 +255,21 @@ def test_split_gemm_reproduces_fp32(ops):
         y1 = nn_ops.linear(x, w, b)
     finally:
         set_precision("fp32")
-    assert _rel(y3, want) < 2e-6
+    assert _rel(y3, want) < 1e-6
     assert _rel(y1, want) > 1e-5          # plain TF32 is visibly worse: the split is doing the work
+
+
+def test_split_conv3x3_reproduces_fp32(ops):
+    from univs_b200 import nn_ops
+    from univs_b200.precision import set_precision
+    torch.manual_seed(24)
+    x = torch.randn(2, 20, 27, 256).cuda()
+    w = (torch.randn(64, 256, 3, 3) * 0.02).cuda()
+    want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=1).permute(0, 2, 3, 1).float()
+    try:
+        set_precision("tf32x3")
+        y = nn_ops.conv2d_cl(x, w, None, padding=1)
+    finally:
+        set_precision("fp32")
+    assert y.shape == want.shape
+    assert _rel(y, want) < 1e-6

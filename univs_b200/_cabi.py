@@ -26,7 +26,7 @@ SIGNATURES = {
     "univs_layernorm_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, C.c_float, _vp, _vp, _i]),
     "univs_gelu_f32": (_i, [_vp, _vp, _i64, _i, _vp, _i]),
     "univs_relu_f32": (_i, [_vp, _vp, _i64, _i, _vp, _i]),
-    "univs_split_tf32_f32": (_i, [_vp, _vp, _i64, _i, _vp]),
+    "univs_split_tf32_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "univs_round_tf32_f32": (_i, [_vp, _vp, _vp, _i64]),
 }
 

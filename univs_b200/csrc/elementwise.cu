@@ -1,6 +1,6 @@
 // Fused row-wise kernels around the library GEMMs: residual-add + LayerNorm, exact GELU, and the TF32 hi|lo operand
 // split that lets TF32 tensor-core GEMMs reproduce fp32 products (3xTF32: X*W ~= Xh*Wh + Xl*Wh + Xh*Wl with
-// hi = upper 19 bits (exactly representable in TF32, so the tensor core's truncation is lossless) and lo = x - hi).
+// hi = x rounded to nearest TF32 (exactly representable, so the tensor core's truncation is lossless) and lo = x - hi).
 //
 //   layernorm : s = x (+ residual);  [sum_out = s];  out = LN(s) * gamma + beta, written plain [rows,C] or split
 //               [rows,2C] = [hi | lo]              (reference: nn.LayerNorm sites swin.py:246,292; msdeformattn.py:126-133;
@@ -18,16 +18,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// hi = x rounded to nearest TF32 (|lo| <= 2^-12 |x|, so the dropped lo*lo term is 2^-24 relative and unbiased)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(f2tf32(x)); }
 
-__device__ __forceinline__ void store_maybe_split(float* __restrict__ out, size_t row, int C, int col, float4 v, bool split) {
-  if (!split) {
+// split == 0: plain [rows,C].  split == Kc > 0: [rows,2C] in K-chunks of Kc columns, chunk c = [hi_c (Kc) | lo_c (Kc)]
+// (so a K-slice of the 3xTF32 GEMM is one contiguous 2*Kc-column block; Kc divides C, Kc % 4 == 0).
+__device__ __forceinline__ void store_maybe_split(float* __restrict__ out, size_t row, int C, int col, float4 v, int split) {
+  if (split == 0) {
     *reinterpret_cast<float4*>(out + row * C + col) = v;
   } else {
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-    *reinterpret_cast<float4*>(out + row * (2 * (size_t)C) + col) = h;
-    *reinterpret_cast<float4*>(out + row * (2 * (size_t)C) + C + col) = l;
+    const int chunk = col / split;
+    const size_t o = row * (2 * (size_t)C) + (size_t)chunk * (2 * split) + (col - chunk * split);
+    *reinterpret_cast<float4*>(out + o) = h;
+    *reinterpret_cast<float4*>(out + o + split) = l;
   }
 }
 
@@ -79,7 +84,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, con
       o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
       o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
       o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
-      store_maybe_split(out, (size_t)row, C, idx * 4, o, split != 0);
+      store_maybe_split(out, (size_t)row, C, idx * 4, o, split);
     }
   }
 }
@@ -100,7 +105,7 @@ gelu_split_kernel(const float* __restrict__ x, long long rows, int C, float* __r
       a.z = 0.5f * a.z * (1.f + erff(a.z * 0.70710678118654752440f));
       a.w = 0.5f * a.w * (1.f + erff(a.w * 0.70710678118654752440f));
     }
-    store_maybe_split(out, (size_t)row, C, col, a, split != 0);
+    store_maybe_split(out, (size_t)row, C, col, a, split);
   }
 }
 
@@ -115,6 +120,7 @@ extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* re
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
   UNIVS_REQUIRE(channels % 4 == 0 && channels <= 4096, "layernorm: channels must be a multiple of 4 and <= 4096 (got %d)", channels);
+  UNIVS_REQUIRE(split == 0 || (split % 4 == 0 && channels % split == 0), "layernorm: split chunk must divide channels");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
 #define LN_LAUNCH(MV) layernorm_kernel<MV><<<grid, 256, 0, st>>>(x, residual, gamma, beta, rows, channels, eps, sum_out, out, split)
@@ -148,12 +154,13 @@ extern "C" int univs_relu_f32(void* stream, const float* x, int64_t rows, int ch
   return check_launch("relu");
 }
 
-extern "C" int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, float* out) {
+extern "C" int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, int chunk, float* out) {
   UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "split_tf32: bad sizes (channels %% 4 == 0)");
+  UNIVS_REQUIRE(chunk > 0 && chunk % 4 == 0 && channels % chunk == 0, "split_tf32: chunk must divide channels and be a multiple of 4");
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && out, "split_tf32: null pointer");
   long long blocks = (rows * (channels / 4) + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, channels, out, 0, 1);
+  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, channels, out, 0, chunk);
   return check_launch("split_tf32");
 }

@@ -34,23 +34,27 @@ def splitting() -> bool:
     return _policy == "tf32x3"
 
 
-def _split_weight(w: torch.Tensor):
-    """-> (W2 = [Wh | Wh] [N,2K], Wl [N,K]) for a 2-D weight, cached per parameter version."""
+def _split_weight(w: torch.Tensor, cache=True):
+    """2-D weight [N,K] -> (W2 [N,2K] in K-chunks [Wh_c | Wh_c], Wl [N,K]); cached per parameter version."""
     key = id(w)
-    ent = _wcache.get(key)
-    if ent is None or ent[0] != (w.data_ptr(), w._version, tuple(w.shape)):
+    sig = (w.data_ptr(), w._version, tuple(w.shape))
+    ent = _wcache.get(key) if cache else None
+    if ent is None or ent[0] != sig:
         w2d = w.detach().reshape(w.shape[0], -1).contiguous()
-        hl = ops.split_tf32(w2d)                          # [N, 2K] = [hi | lo]
-        K = w2d.shape[1]
-        hi, lo = hl[:, :K], hl[:, K:].contiguous()
-        ent = ((w.data_ptr(), w._version, tuple(w.shape)), torch.cat([hi, hi], 1).contiguous(), lo)
-        _wcache[key] = ent
+        N, K = w2d.shape
+        kc = ops.split_chunk(K)
+        hl = ops.split_tf32(w2d, kc).view(N, K // kc, 2, kc)              # chunk c = [hi_c | lo_c]
+        hi, lo = hl[:, :, 0], hl[:, :, 1]
+        w2 = torch.stack([hi, hi], 2).reshape(N, 2 * K).contiguous()
+        ent = (sig, w2, lo.reshape(N, K).contiguous())
+        if cache:
+            _wcache[key] = ent
     return ent[1], ent[2]
 
 
 def prep(x):
     """activation -> GEMM operand format of the active policy"""
-    return ops.split_tf32(x.contiguous()) if splitting() else x
+    return ops.split_tf32(x if x.is_contiguous() else x.contiguous()) if splitting() else x
 
 
 def layernorm(x, norm, residual=None, want_sum=False, for_gemm=True):
@@ -68,18 +72,24 @@ def relu(x, for_gemm=True):
 
 
 def linear_prepped(h, weight, bias=None, cache=True):
-    """h: operand from prep()/layernorm()/gelu() ([..., 2K] when splitting, else [..., K])."""
+    """h: operand from prep()/layernorm()/gelu() ([..., 2K] chunked hi|lo when splitting, else [..., K]).
+    Splitting: per K-chunk c (<= 256 columns)   y += [Xh|Xl]_c [Wh|Wh]_c^T  +  Xh_c Wl_c^T ; the chunks are summed by
+    the GEMM epilogues (beta = 1, fp32 round-to-nearest), which keeps every tensor-core accumulation chain short."""
     if not splitting():
         return F.linear(h, weight, bias)
-    K = weight.shape[1]
-    if cache:
-        w2, wlo = _split_weight(weight)
-    else:
-        hl = ops.split_tf32(weight.contiguous())
-        w2, wlo = torch.cat([hl[:, :K], hl[:, :K]], 1), hl[:, K:]
-    y = F.linear(h, w2, bias)                                        # Xh*Wh + Xl*Wh (+ bias)
-    y.view(-1, y.shape[-1]).addmm_(h.reshape(-1, 2 * K)[:, :K], wlo.t())   # + Xh*Wl
-    return y
+    N, K = weight.shape
+    kc = ops.split_chunk(K)
+    w2, wlo = _split_weight(weight, cache)
+    h2 = h.reshape(-1, 2 * K)
+    y = None
+    for c in range(K // kc):
+        hs = h2[:, 2 * c * kc: 2 * (c + 1) * kc]
+        if y is None:
+            y = F.linear(hs, w2[:, 2 * c * kc: 2 * (c + 1) * kc], bias)
+        else:
+            y.addmm_(hs, w2[:, 2 * c * kc: 2 * (c + 1) * kc].t())
+        y.addmm_(hs[:, :kc], wlo[:, c * kc:(c + 1) * kc].t())
+    return y.view(*h.shape[:-1], N)
 
 
 def linear(x, weight, bias=None, cache=True):
@@ -87,26 +97,46 @@ def linear(x, weight, bias=None, cache=True):
 
 
 def conv2d_cl(x_cl, weight, bias=None, padding=0):
-    """Convolution on a channel-last activation [N,H,W,Cin] -> [N,H,W,Cout] (storage channel-last)."""
+    """Convolution on a channel-last activation [N,H,W,Cin] -> [N,H,W,Cout] (storage channel-last).
+    Splitting policy: a kxk "same" convolution is k*k shifted GEMMs over the zero-padded, split activation viewed
+    as one 2-D token matrix (row = padded pixel), accumulated by the GEMM epilogues -- every tensor-core chain is one
+    tap deep."""
     N, H, W, Cin = x_cl.shape
+    if isinstance(padding, (tuple, list)):
+        assert padding[0] == padding[1]
+        padding = int(padding[0])
     if not splitting():
         y = F.conv2d(x_cl.permute(0, 3, 1, 2), weight, bias, padding=padding)
         return y.permute(0, 2, 3, 1)
+    Cout, _, kh, kw = weight.shape
+    assert kh == kw and padding == kh // 2, "only 'same' square convolutions are used on this path"
     key = ("conv", id(weight))
+    sig = (weight.data_ptr(), weight._version)
     ent = _wcache.get(key)
-    if ent is None or ent[0] != (weight.data_ptr(), weight._version):
-        w = weight.detach()
-        hl = ops.split_tf32(w.permute(0, 2, 3, 1).contiguous())            # [Cout,kh,kw,2Cin]
-        hi, lo = hl[..., :Cin], hl[..., Cin:]
-        w2 = torch.cat([hi, hi], -1).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
-        wl = lo.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
-        ent = ((weight.data_ptr(), weight._version), w2, wl)
+    if ent is None or ent[0] != sig:
+        taps = [_split_weight(weight.detach()[:, :, dy, dx].contiguous(), cache=False) for dy in range(kh) for dx in range(kw)]
+        ent = (sig, taps)
         _wcache[key] = ent
-    xs = ops.split_tf32(x_cl.contiguous())                                   # [N,H,W,2Cin]
-    xs_nchw = xs.permute(0, 3, 1, 2)
-    y = F.conv2d(xs_nchw, ent[1], bias, padding=padding)
-    y = y + F.conv2d(xs_nchw[:, :Cin], ent[2], None, padding=padding)
-    return y.permute(0, 2, 3, 1)
+    p = padding
+    Hp, Wp = H + 2 * p, W + 2 * p
+    xs = F.pad(ops.split_tf32(x_cl.contiguous()), (0, 0, p, p, p, p))            # [N,Hp,Wp,2Cin], zeros split to zeros
+    x2 = xs.view(N * Hp * Wp, 2 * Cin)
+    R = N * Hp * Wp - ((kh - 1) * Wp + (kw - 1))                                  # rows every tap can address
+    y = torch.empty((N * Hp * Wp, Cout), device=x_cl.device, dtype=torch.float32)
+    kc = ops.split_chunk(Cin)
+    first = True
+    for t, (w2, wlo) in enumerate(ent[1]):
+        off = (t // kw) * Wp + (t % kw)
+        a = x2[off: off + R]
+        for c in range(Cin // kc):
+            hs = a[:, 2 * c * kc: 2 * (c + 1) * kc]
+            if first:
+                torch.addmm(bias if bias is not None else y.new_zeros(Cout), hs, w2[:, 2 * c * kc: 2 * (c + 1) * kc].t(), out=y[:R])
+                first = False
+            else:
+                y[:R].addmm_(hs, w2[:, 2 * c * kc: 2 * (c + 1) * kc].t())
+            y[:R].addmm_(hs[:, :kc], wlo[:, c * kc:(c + 1) * kc].t())
+    return y.view(N, Hp, Wp, Cout)[:, :H, :W]
 
 
 @contextlib.contextmanager

@@ -228,9 +228,20 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
     return out
 
 
+def split_chunk(K: int) -> int:
+    """K-chunk length of the split operand format: the largest divisor of K that is <= 256 and a multiple of 32
+    (bounds the tensor-core accumulation chain to 32 MMA steps per pass; see tools/accum_probe.py)."""
+    if K <= 256:
+        return K
+    for c in range(256, 31, -32):
+        if K % c == 0:
+            return c
+    return K
+
+
 def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=False):
     """Fused (residual add +) LayerNorm over the last dim.  Returns (sum_or_None, out); `out` is [..., C] or, with
-    split=True, [..., 2C] = [hi | lo] (operand format of the 3xTF32 GEMM policy)."""
+    split=True, [..., 2C] in K-chunks [hi_c | lo_c] (operand format of the 3xTF32 GEMM policy)."""
     C = x.shape[-1]
     rows = x.numel() // C
     out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
@@ -238,7 +249,7 @@ def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=Fa
     with _Bracket("layernorm", 1):
         rc = lib().univs_layernorm_f32(_stream(), _chk(x, "x"), None if residual is None else _chk(residual, "residual"),
                                        _chk(weight, "weight"), _chk(bias, "bias"), rows, C, float(eps),
-                                       None if s is None else s.data_ptr(), out.data_ptr(), int(split))
+                                       None if s is None else s.data_ptr(), out.data_ptr(), split_chunk(C) if split else 0)
     check(rc, "layernorm")
     if want_sum and residual is None:
         s = x
@@ -249,7 +260,7 @@ def gelu(x, split=False):
     C = x.shape[-1]
     out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
     with _Bracket("gelu", 1):
-        rc = lib().univs_gelu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), int(split))
+        rc = lib().univs_gelu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), split_chunk(C) if split else 0)
     check(rc, "gelu")
     return out
 
@@ -258,17 +269,18 @@ def relu(x, split=False):
     C = x.shape[-1]
     out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
     with _Bracket("relu", 1):
-        rc = lib().univs_relu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), int(split))
+        rc = lib().univs_relu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), split_chunk(C) if split else 0)
     check(rc, "relu")
     return out
 
 
-def split_tf32(x):
-    """[..., C] -> [..., 2C] = [hi | lo]"""
+def split_tf32(x, chunk=None):
+    """[..., C] -> [..., 2C] in K-chunks of `chunk` (default split_chunk(C)) columns: chunk c = [hi_c | lo_c]"""
     C = x.shape[-1]
     out = torch.empty((*x.shape[:-1], 2 * C), device=x.device, dtype=torch.float32)
     with _Bracket("split_tf32", 1):
-        rc = lib().univs_split_tf32_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr())
+        rc = lib().univs_split_tf32_f32(_stream(), _chk(x, "x"), x.numel() // C, C,
+                                        split_chunk(C) if chunk is None else chunk, out.data_ptr())
     check(rc, "split_tf32")
     return out
 
