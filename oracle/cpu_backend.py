@@ -54,11 +54,6 @@ def _proca(q, ks, vs, km, vm):
 
 
 def _chunk(K):
-    if K <= 256:
-        return K
-    for c in range(256, 31, -32):
-        if K % c == 0:
-            return c
     return K
 
 

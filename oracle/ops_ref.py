@@ -228,11 +228,6 @@ def pos3d_sine_arbitrary_t(frame_indices, h, w, num_pos_feats=128, temperature=1
 # fused row-wise kernels around the GEMMs (csrc/elementwise.cu)
 # ---------------------------------------------------------------------------
 def _chunk(K):
-    if K <= 256:
-        return K
-    for c in range(256, 31, -32):
-        if K % c == 0:
-            return c
     return K
 
 

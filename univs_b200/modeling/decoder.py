@@ -209,6 +209,10 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         self.enabled_prev_visual_prompts_for_grounding = enabled_prev_visual_prompts_for_grounding
         self.semantic_extraction_enable = semantic_extraction_enable
         self.return_aux_outputs = False
+        # diagnostic hook (tools/parity_at_scale.py): fn(call_index, bits, row_open) -> (bits, row_open); lets a parity
+        # run record the attention-mask decisions or replay another run's decisions.  None in normal operation.
+        self.attn_mask_hook = None
+        self._head_calls = 0
         self._clip_norm_cache = None
         self.eval()
 
@@ -328,6 +332,9 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         bits = row_open = None
         if need_attn:
             bits, row_open = ops.attn_mask_bits(logits, hw, next_hw)
+            if self.attn_mask_hook is not None:
+                bits, row_open = self.attn_mask_hook(self._head_calls, bits, row_open)
+        self._head_calls += 1
         return cls, logits, bits, row_open, reid
 
     # ------------------------------------------------------------------ prompts
@@ -447,6 +454,7 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
                         "pred_embds": nn_ops.layernorm(emb.transpose(0, 1), self.decoder_norm, for_gemm=False)[1][None]})
 
         hw = (h_m, w_m)
+        self._head_calls = 0
         cls, logits, bits, row_open, reid = self._heads(out, feats_cl, hw, size_list[0], task, targets, t, want_aux, True)
         if want_aux:
             record(cls, logits, reid, out)

@@ -34,19 +34,28 @@ def splitting() -> bool:
     return _policy == "tf32x3"
 
 
+def g1_chunk(K: int) -> int:
+    """K-slice of the hi*hi GEMM.  The tensor cores accumulate with truncation, a bias of ~ -1.65e-8 per MMA step
+    (tools/accum_probe.py); slicing K at <= 1024 keeps it <= 2.1e-6 per GEMM; slices are summed by fp32 epilogues."""
+    if K <= 1024:
+        return K
+    for c in range(1024, 255, -32):
+        if K % c == 0:
+            return c
+    return K
+
+
 def _split_weight(w: torch.Tensor, cache=True):
-    """2-D weight [N,K] -> (W2 [N,2K] in K-chunks [Wh_c | Wh_c], Wl [N,K]); cached per parameter version."""
+    """2-D weight [N,K] -> (Wh [N,K], Wlh [N,2K] = [Wl | Wh]); cached per parameter version."""
     key = id(w)
     sig = (w.data_ptr(), w._version, tuple(w.shape))
     ent = _wcache.get(key) if cache else None
     if ent is None or ent[0] != sig:
         w2d = w.detach().reshape(w.shape[0], -1).contiguous()
         N, K = w2d.shape
-        kc = ops.split_chunk(K)
-        hl = ops.split_tf32(w2d, kc).view(N, K // kc, 2, kc)              # chunk c = [hi_c | lo_c]
-        hi, lo = hl[:, :, 0], hl[:, :, 1]
-        w2 = torch.stack([hi, hi], 2).reshape(N, 2 * K).contiguous()
-        ent = (sig, w2, lo.reshape(N, K).contiguous())
+        hl = ops.split_tf32(w2d)                                        # [N,2K] = [hi | lo]
+        hi, lo = hl[:, :K], hl[:, K:]
+        ent = (sig, hi.contiguous(), torch.cat([lo, hi], 1).contiguous())
         if cache:
             _wcache[key] = ent
     return ent[1], ent[2]
@@ -72,23 +81,20 @@ def relu(x, for_gemm=True):
 
 
 def linear_prepped(h, weight, bias=None, cache=True):
-    """h: operand from prep()/layernorm()/gelu() ([..., 2K] chunked hi|lo when splitting, else [..., K]).
-    Splitting: per K-chunk c (<= 256 columns)   y += [Xh|Xl]_c [Wh|Wh]_c^T  +  Xh_c Wl_c^T ; the chunks are summed by
-    the GEMM epilogues (beta = 1, fp32 round-to-nearest), which keeps every tensor-core accumulation chain short."""
+    """h: operand from prep()/layernorm()/gelu() ([..., 2K] = [Xh | Xl] when splitting, else [..., K]).
+    Splitting:  y = Xh Wh^T (+ bias)            -- main term, K sliced at <= 1024 to bound the accumulation chain
+                  + [Xh | Xl] [Wl | Wh]^T       -- both correction terms in one 2K-wide GEMM with its own (small)
+                                                   accumulator, added by the GEMM epilogue (beta = 1, fp32 RN)."""
     if not splitting():
         return F.linear(h, weight, bias)
     N, K = weight.shape
-    kc = ops.split_chunk(K)
-    w2, wlo = _split_weight(weight, cache)
+    wh, wlh = _split_weight(weight, cache)
     h2 = h.reshape(-1, 2 * K)
-    y = None
-    for c in range(K // kc):
-        hs = h2[:, 2 * c * kc: 2 * (c + 1) * kc]
-        if y is None:
-            y = F.linear(hs, w2[:, 2 * c * kc: 2 * (c + 1) * kc], bias)
-        else:
-            y.addmm_(hs, w2[:, 2 * c * kc: 2 * (c + 1) * kc].t())
-        y.addmm_(hs[:, :kc], wlo[:, c * kc:(c + 1) * kc].t())
+    kc = g1_chunk(K)
+    y = F.linear(h2[:, :kc], wh[:, :kc], bias)
+    for k0 in range(kc, K, kc):
+        y.addmm_(h2[:, k0:k0 + kc], wh[:, k0:k0 + kc].t())
+    y.addmm_(h2, wlh.t())
     return y.view(*h.shape[:-1], N)
 
 
@@ -123,19 +129,15 @@ def conv2d_cl(x_cl, weight, bias=None, padding=0):
     x2 = xs.view(N * Hp * Wp, 2 * Cin)
     R = N * Hp * Wp - ((kh - 1) * Wp + (kw - 1))                                  # rows every tap can address
     y = torch.empty((N * Hp * Wp, Cout), device=x_cl.device, dtype=torch.float32)
-    kc = ops.split_chunk(Cin)
-    first = True
-    for t, (w2, wlo) in enumerate(ent[1]):
+    yr = y[:R]
+    for t, (wh, wlh) in enumerate(ent[1]):
         off = (t // kw) * Wp + (t % kw)
         a = x2[off: off + R]
-        for c in range(Cin // kc):
-            hs = a[:, 2 * c * kc: 2 * (c + 1) * kc]
-            if first:
-                torch.addmm(bias if bias is not None else y.new_zeros(Cout), hs, w2[:, 2 * c * kc: 2 * (c + 1) * kc].t(), out=y[:R])
-                first = False
-            else:
-                y[:R].addmm_(hs, w2[:, 2 * c * kc: 2 * (c + 1) * kc].t())
-            y[:R].addmm_(hs[:, :kc], wlo[:, c * kc:(c + 1) * kc].t())
+        if t == 0:
+            torch.addmm(bias if bias is not None else y.new_zeros(Cout), a[:, :Cin], wh.t(), out=yr)
+        else:
+            yr.addmm_(a[:, :Cin], wh.t())
+        yr.addmm_(a, wlh.t())
     return y.view(N, Hp, Wp, Cout)[:, :H, :W]
 
 

@@ -229,13 +229,7 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
 
 
 def split_chunk(K: int) -> int:
-    """K-chunk length of the split operand format: the largest divisor of K that is <= 256 and a multiple of 32
-    (bounds the tensor-core accumulation chain to 32 MMA steps per pass; see tools/accum_probe.py)."""
-    if K <= 256:
-        return K
-    for c in range(256, 31, -32):
-        if K % c == 0:
-            return c
+    """K-chunk length of the split operand layout.  The layout in use is plain halves [hi (K) | lo (K)]."""
     return K
 
 
