@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ns", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("UNIVS_PRECISION", "tf32x3"), choices=["tf32x3", "fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("UNIVS_PRECISION", "tf32x3"), choices=["fp16x3", "tf32x3", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: after warm-up run ONE step between cudaProfilerStart/Stop and exit "
@@ -254,7 +254,7 @@ def main():
             "metric": "frames/sec (Swin-L 720p T=5 Q=200)" if args.workload == "ns" else "frames/sec (per-clip forward)",
             "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"tf32x3": "tf32x3 (3-pass TF32 split, fp32-equivalent products, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "dtype": {"fp16x3": "fp16x3 (2-term fp16 split operands, fp32-equivalent products, fp32 accumulate)", "tf32x3": "tf32x3 (3-pass TF32 split, fp32-equivalent products, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init",
                        "precision": args.precision, "parallelism": f"frame-shard x{world}" if world > 1 else "single",
                        "l2": "per-step working set (multi-GB activations) exceeds the 126 MB L2; no explicit flush"},

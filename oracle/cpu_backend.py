@@ -67,18 +67,29 @@ def _split(x, chunk=None):
     return hl.reshape(*x.shape[:-1], 2 * C)
 
 
+def _split16(x, scaled):
+    hi = x.clamp(-65504, 65504).half()
+    lo = ((x - hi.float()) * (2048.0 if scaled else 1.0)).clamp(-65504, 65504).half()
+    return torch.cat([hi, lo], -1)
+
+
 def _maybe_split(y, split):
-    return _split(y) if split else y
+    if not split:
+        return y
+    if split in ("f16", "f16u"):
+        return _split16(y, split == "f16")
+    return _split(y)
 
 
-def _layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=False):
+def _layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=None):
     s = x if residual is None else x + residual
     y = torch.nn.functional.layer_norm(s, (x.shape[-1],), weight, bias, eps)
     return (s if want_sum else None), _maybe_split(y, split)
 
 
-_PATCH = {"layernorm": _layernorm, "gelu": lambda x, split=False: _maybe_split(torch.nn.functional.gelu(x), split),
-          "relu": lambda x, split=False: _maybe_split(torch.relu(x), split), "split_tf32": _split,
+_PATCH = {"layernorm": _layernorm, "gelu": lambda x, split=None: _maybe_split(torch.nn.functional.gelu(x), split),
+          "relu": lambda x, split=None: _maybe_split(torch.relu(x), split), "split_tf32": _split,
+          "split_operand": lambda x, split="tf32": _maybe_split(x, split),
           "swin_window_attention": _swin, "ms_deform_attn_encoder": _msda_enc, "ms_deform_attn_forward": _msda_fwd,
           "mask_einsum": _einsum, "attn_mask_bits": _bits, "mha_core": _mha, "proca_core": _proca,
           "round_tf32": lambda x, out=None: x, "prepare_mask_features": lambda x: x}

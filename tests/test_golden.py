@@ -62,7 +62,7 @@ def test_oracle_msda_matches_golden_reference_test_vectors():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+@pytest.mark.parametrize("precision", ["fp16x3", "tf32x3", "fp32"])
 def test_cuda_model_matches_golden(name, precision):
     from univs_b200.precision import set_precision
     set_precision(precision)

@@ -29,7 +29,7 @@ def _pair(swin, T, Q, H, W, tgt, seed=0, **kw):
     return gpu, x, want
 
 
-@pytest.mark.parametrize("precision,tol", [("tf32x3", 1e-3), ("fp32", 1e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp16x3", 1e-3), ("tf32x3", 1e-3), ("fp32", 1e-3)])
 def test_swin_tiny_clip_detection(precision, tol):
     """Swin-T (window 7, real depths), T=2, 224x320, Q=100 -- a reduced-resolution BASELINE config 2."""
     from univs_b200.precision import set_precision

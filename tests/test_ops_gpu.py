@@ -221,10 +221,10 @@ def test_layernorm_fused(ops, rows, C, with_res):
     s, y = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), want_sum=True)
     assert _rel(y, y_want) < 2e-6
     assert torch.equal(s.cpu(), s_want)
-    _, ys = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), split=True)
+    _, ys = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), split="tf32")
     assert ys.shape == (rows, 2 * C)
     assert torch.equal(ys.cpu(), ops_ref.split_tf32(y.cpu()))            # split of exactly the plain output
-    kc = ops.split_chunk(C)
+    kc = C
     v = ys.view(rows, C // kc, 2, kc)
     assert torch.equal((v[:, :, 0] + v[:, :, 1]).reshape(rows, C), y)      # hi + lo == value, bit-exact
     assert (v[:, :, 0].contiguous().view(torch.int32) & 0x1FFF).eq(0).all()   # hi is TF32-representable
@@ -234,7 +234,7 @@ def test_gelu_relu_split(ops):
     torch.manual_seed(22)
     x = torch.randn(257, 768) * 2
     assert _rel(ops.gelu(x.cuda()), ops_ref.gelu(x)) < 1e-6
-    gs = ops.gelu(x.cuda(), split=True)
+    gs = ops.gelu(x.cuda(), split="tf32")
     assert torch.equal(gs.cpu(), ops_ref.split_tf32(ops.gelu(x.cuda()).cpu()))
     assert torch.equal(ops.relu(x.cuda()).cpu(), torch.relu(x))
     assert torch.equal(ops.split_tf32(x.cuda()).cpu(), ops_ref.split_tf32(x))
@@ -273,3 +273,38 @@ def test_split_conv3x3_reproduces_fp32(ops):
         set_precision("fp32")
     assert y.shape == want.shape
     assert _rel(y, want) < 2.5e-6
+
+
+def test_fp16_split_formats(ops):
+    torch.manual_seed(25)
+    x = torch.randn(300, 384) * torch.logspace(-6, 2, 384)          # magnitudes from 1e-6 to 1e2
+    s16 = ops.split_operand(x.cuda(), "f16")
+    assert s16.dtype == torch.float16 and s16.shape == (300, 768)
+    rec = s16[:, :384].float() + s16[:, 384:].float() * 2.0 ** -11
+    assert ((rec.cpu() - x).abs() <= x.abs() * 2.0 ** -21 + 1e-12).all()       # ~22-bit reconstruction
+    u16 = ops.split_operand(x.cuda(), "f16u")
+    rec = u16[:, :384].float() + u16[:, 384:].float()
+    assert ((rec.cpu() - x).abs() <= x.abs() * 2.0 ** -21 + 4e-8).all()        # unscaled lo: fp16 subnormal floor
+    big = torch.tensor([[1e6, -1e6, 70000.0, 1.0]]).cuda()
+    sat = ops.split_operand(big, "f16")
+    assert torch.isfinite(sat.float()).all()                                     # saturating, never inf
+
+
+def test_fp16x3_gemm_reproduces_fp32(ops):
+    from univs_b200 import nn_ops
+    from univs_b200.precision import set_precision
+    torch.manual_seed(26)
+    x, w, b = torch.randn(4096, 768).cuda(), (torch.randn(384, 768) * 0.05).cuda(), torch.randn(384).cuda()
+    want = (x.double() @ w.double().t() + b.double()).float()
+    try:
+        set_precision("fp16x3")
+        y = nn_ops.linear(x, w, b)
+        yc = nn_ops.conv2d_cl(x[:540].view(2, 10, 27, 768)[..., :256].contiguous(), (w.view(384, 768)[:64, :2304 // 9 * 0 + 256].reshape(64, 256, 1, 1)).repeat(1, 1, 3, 3) * 0.1, None, padding=1)
+    finally:
+        set_precision("fp32")
+    assert y.dtype == torch.float32
+    assert _rel(y, want) < 2e-6
+    xc = x[:540].view(2, 10, 27, 768)[..., :256]
+    wc = (w[:64, :256].reshape(64, 256, 1, 1)).repeat(1, 1, 3, 3) * 0.1
+    wantc = torch.nn.functional.conv2d(xc.permute(0, 3, 1, 2).double(), wc.double(), padding=1).permute(0, 2, 3, 1).float()
+    assert _rel(yc, wantc) < 2e-6

@@ -15,7 +15,7 @@ from univs_b200.precision import set_precision
 
 T = int(os.environ.get("PARITY_T", "2"))
 variant = os.environ.get("PARITY_VARIANT", "large")
-modes = os.environ.get("PARITY_MODES", "tf32x3,fp32,tf32").split(",")
+modes = os.environ.get("PARITY_MODES", "fp16x3,tf32x3,fp32,tf32").split(",")
 H, W, Q = 720, 1280, 200
 g = torch.Generator().manual_seed(0)
 clip = torch.randn(3938, 640, generator=g)

@@ -9,6 +9,8 @@
 //   split     : out = [hi | lo]
 // One warp per row, 128-bit loads/stores, the row is held in registers (single read of x), two-pass mean/variance
 // with warp-shuffle reductions.  All three are pure HBM streams.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace univs {
@@ -21,18 +23,36 @@ __device__ __forceinline__ float warp_sum(float v) {
 // hi = x rounded to nearest TF32 (|lo| <= 2^-12 |x|, so the dropped lo*lo term is 2^-24 relative and unbiased)
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(f2tf32(x)); }
 
-// split == 0: plain [rows,C].  split == Kc > 0: [rows,2C] in K-chunks of Kc columns, chunk c = [hi_c (Kc) | lo_c (Kc)]
-// (so a K-slice of the 3xTF32 GEMM is one contiguous 2*Kc-column block; Kc divides C, Kc % 4 == 0).
+// Output formats of the row-wise kernels (`split` argument):
+//   0                plain fp32 [rows, C]
+//   Kc > 0           fp32 [rows, 2C] in K-chunks of Kc columns, chunk c = [hi_c | lo_c], hi = rna_tf32(x), lo = x - hi
+//   UNIVS_SPLIT_F16  (-1) fp16 [rows, 2C] = [hi | lo*2^11], hi = fp16(x) (round-to-nearest, saturating), lo = x - hi
+//   UNIVS_SPLIT_F16U (-2) fp16 [rows, 2C] = [hi | lo] (lo unscaled; operands of the fp16 mask einsum)
+// fp16 carries an 11-bit significand like TF32, so hi*hi products are exact in fp32 and two terms give 22 bits; the
+// 2^11 scale keeps lo out of the fp16 subnormal range (undone by alpha = 2^-11 in the correction GEMM).
+__device__ __forceinline__ __half sat_half(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
+
 __device__ __forceinline__ void store_maybe_split(float* __restrict__ out, size_t row, int C, int col, float4 v, int split) {
   if (split == 0) {
     *reinterpret_cast<float4*>(out + row * C + col) = v;
-  } else {
+  } else if (split > 0) {
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
     const int chunk = col / split;
     const size_t o = row * (2 * (size_t)C) + (size_t)chunk * (2 * split) + (col - chunk * split);
     *reinterpret_cast<float4*>(out + o) = h;
     *reinterpret_cast<float4*>(out + o + split) = l;
+  } else {
+    const float sc = (split == -1) ? 2048.f : 1.f;
+    __half* o16 = reinterpret_cast<__half*>(out);
+    const __half h0 = sat_half(v.x), h1 = sat_half(v.y), h2 = sat_half(v.z), h3 = sat_half(v.w);
+    const __half l0 = sat_half((v.x - __half2float(h0)) * sc), l1 = sat_half((v.y - __half2float(h1)) * sc);
+    const __half l2 = sat_half((v.z - __half2float(h2)) * sc), l3 = sat_half((v.w - __half2float(h3)) * sc);
+    const size_t o = row * (2 * (size_t)C) + col;
+    *reinterpret_cast<__half2*>(o16 + o) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(o16 + o + 2) = __halves2half2(h2, h3);
+    *reinterpret_cast<__half2*>(o16 + o + C) = __halves2half2(l0, l1);
+    *reinterpret_cast<__half2*>(o16 + o + C + 2) = __halves2half2(l2, l3);
   }
 }
 
@@ -120,7 +140,8 @@ extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* re
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
   UNIVS_REQUIRE(channels % 4 == 0 && channels <= 4096, "layernorm: channels must be a multiple of 4 and <= 4096 (got %d)", channels);
-  UNIVS_REQUIRE(split == 0 || (split % 4 == 0 && channels % split == 0), "layernorm: split chunk must divide channels");
+  UNIVS_REQUIRE(split == 0 || split == -1 || split == -2 || (split > 0 && split % 4 == 0 && channels % split == 0),
+                "layernorm: split chunk must divide channels");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
 #define LN_LAUNCH(MV) layernorm_kernel<MV><<<grid, 256, 0, st>>>(x, residual, gamma, beta, rows, channels, eps, sum_out, out, split)
@@ -156,7 +177,8 @@ extern "C" int univs_relu_f32(void* stream, const float* x, int64_t rows, int ch
 
 extern "C" int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, int chunk, float* out) {
   UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "split_tf32: bad sizes (channels %% 4 == 0)");
-  UNIVS_REQUIRE(chunk > 0 && chunk % 4 == 0 && channels % chunk == 0, "split_tf32: chunk must divide channels and be a multiple of 4");
+  UNIVS_REQUIRE(chunk == -1 || chunk == -2 || (chunk > 0 && chunk % 4 == 0 && channels % chunk == 0),
+                "split_tf32: chunk must divide channels and be a multiple of 4 (or -1/-2 for the fp16 formats)");
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && out, "split_tf32: null pointer");
   long long blocks = (rows * (channels / 4) + 255) / 256;

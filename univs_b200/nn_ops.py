@@ -21,7 +21,7 @@ _wcache = {}
 
 def set_policy(p: str):
     global _policy
-    assert p in ("fp32", "tf32", "tf32x3")
+    assert p in ("fp32", "tf32", "tf32x3", "fp16x3")
     _policy = p
     _wcache.clear()
 
@@ -31,7 +31,12 @@ def policy() -> str:
 
 
 def splitting() -> bool:
-    return _policy == "tf32x3"
+    return _policy in ("tf32x3", "fp16x3")
+
+
+def _fmt():
+    """operand format produced by the fused kernels for the active policy"""
+    return {"tf32x3": "tf32", "fp16x3": "f16"}.get(_policy)
 
 
 def g1_chunk(K: int) -> int:
@@ -51,9 +56,9 @@ def _split_weight(w: torch.Tensor, cache=True):
     sig = (w.data_ptr(), w._version, tuple(w.shape))
     ent = _wcache.get(key) if cache else None
     if ent is None or ent[0] != sig:
-        w2d = w.detach().reshape(w.shape[0], -1).contiguous()
+        w2d = w.detach().float().reshape(w.shape[0], -1).contiguous()
         N, K = w2d.shape
-        hl = ops.split_tf32(w2d)                                        # [N,2K] = [hi | lo]
+        hl = ops.split_operand(w2d, _fmt())                             # [N,2K] = [hi | lo]  (fp32 or fp16)
         hi, lo = hl[:, :K], hl[:, K:]
         ent = (sig, hi.contiguous(), torch.cat([lo, hi], 1).contiguous())
         if cache:
@@ -63,21 +68,21 @@ def _split_weight(w: torch.Tensor, cache=True):
 
 def prep(x):
     """activation -> GEMM operand format of the active policy"""
-    return ops.split_tf32(x if x.is_contiguous() else x.contiguous()) if splitting() else x
+    return ops.split_operand(x if x.is_contiguous() else x.contiguous(), _fmt()) if splitting() else x
 
 
 def layernorm(x, norm, residual=None, want_sum=False, for_gemm=True):
     """(sum | None, LN(x + residual)); the LN output is split iff it feeds a GEMM under the tf32x3 policy."""
     return ops.layernorm(x.contiguous(), norm.weight, norm.bias, norm.eps,
-                         None if residual is None else residual.contiguous(), want_sum, for_gemm and splitting())
+                         None if residual is None else residual.contiguous(), want_sum, _fmt() if for_gemm else None)
 
 
 def gelu(x, for_gemm=True):
-    return ops.gelu(x.contiguous(), for_gemm and splitting())
+    return ops.gelu(x.contiguous(), _fmt() if for_gemm else None)
 
 
 def relu(x, for_gemm=True):
-    return ops.relu(x.contiguous(), for_gemm and splitting())
+    return ops.relu(x.contiguous(), _fmt() if for_gemm else None)
 
 
 def linear_prepped(h, weight, bias=None, cache=True):
@@ -91,10 +96,20 @@ def linear_prepped(h, weight, bias=None, cache=True):
     wh, wlh = _split_weight(weight, cache)
     h2 = h.reshape(-1, 2 * K)
     kc = g1_chunk(K)
-    y = F.linear(h2[:, :kc], wh[:, :kc], bias)
-    for k0 in range(kc, K, kc):
-        y.addmm_(h2[:, k0:k0 + kc], wh[:, k0:k0 + kc].t())
-    y.addmm_(h2, wlh.t())
+    if _policy == "tf32x3":
+        y = F.linear(h2[:, :kc], wh[:, :kc], bias)
+        for k0 in range(kc, K, kc):
+            y.addmm_(h2[:, k0:k0 + kc], wh[:, k0:k0 + kc].t())
+        y.addmm_(h2, wlh.t())
+    else:  # fp16x3: fp16 operands, fp32 accumulate + fp32 output; lo terms carry a 2^11 scale -> alpha = 2^-11
+        f32 = torch.float32
+        if bias is not None:
+            y = torch.addmm(bias.float(), h2[:, :kc], wh[:, :kc].t(), out_dtype=f32)
+        else:
+            y = torch.mm(h2[:, :kc], wh[:, :kc].t(), out_dtype=f32)
+        for k0 in range(kc, K, kc):
+            y = torch.addmm(y, h2[:, k0:k0 + kc], wh[:, k0:k0 + kc].t(), out_dtype=f32)
+        y = torch.addmm(y, h2, wlh.t(), alpha=2.0 ** -11, out_dtype=f32)
     return y.view(*h.shape[:-1], N)
 
 
@@ -125,19 +140,29 @@ def conv2d_cl(x_cl, weight, bias=None, padding=0):
         _wcache[key] = ent
     p = padding
     Hp, Wp = H + 2 * p, W + 2 * p
-    xs = F.pad(ops.split_tf32(x_cl.contiguous()), (0, 0, p, p, p, p))            # [N,Hp,Wp,2Cin], zeros split to zeros
+    xs = F.pad(ops.split_operand(x_cl.contiguous(), _fmt()), (0, 0, p, p, p, p))  # [N,Hp,Wp,2Cin], zeros split to zeros
     x2 = xs.view(N * Hp * Wp, 2 * Cin)
     R = N * Hp * Wp - ((kh - 1) * Wp + (kw - 1))                                  # rows every tap can address
     y = torch.empty((N * Hp * Wp, Cout), device=x_cl.device, dtype=torch.float32)
     yr = y[:R]
+    f32 = torch.float32
     for t, (wh, wlh) in enumerate(ent[1]):
         off = (t // kw) * Wp + (t % kw)
         a = x2[off: off + R]
-        if t == 0:
-            torch.addmm(bias if bias is not None else y.new_zeros(Cout), a[:, :Cin], wh.t(), out=yr)
+        if _policy == "tf32x3":
+            if t == 0:
+                torch.addmm(bias if bias is not None else y.new_zeros(Cout), a[:, :Cin], wh.t(), out=yr)
+            else:
+                yr.addmm_(a[:, :Cin], wh.t())
+            yr.addmm_(a, wlh.t())
         else:
-            yr.addmm_(a[:, :Cin], wh.t())
-        yr.addmm_(a, wlh.t())
+            if t == 0:
+                yr = torch.addmm(bias.float() if bias is not None else y.new_zeros(Cout), a[:, :Cin], wh.t(), out_dtype=f32)
+            else:
+                yr = torch.addmm(yr, a[:, :Cin], wh.t(), out_dtype=f32)
+            yr = torch.addmm(yr, a, wlh.t(), alpha=2.0 ** -11, out_dtype=f32)
+    if _policy != "tf32x3":
+        y[:R] = yr
     return y.view(N, Hp, Wp, Cout)[:, :H, :W]
 
 

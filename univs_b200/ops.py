@@ -228,55 +228,71 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
     return out
 
 
-def split_chunk(K: int) -> int:
-    """K-chunk length of the split operand layout.  The layout in use is plain halves [hi (K) | lo (K)]."""
-    return K
+SPLIT_CODES = {None: 0, False: 0, "tf32": None, True: None, "f16": -1, "f16u": -2}
 
 
-def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=False):
-    """Fused (residual add +) LayerNorm over the last dim.  Returns (sum_or_None, out); `out` is [..., C] or, with
-    split=True, [..., 2C] in K-chunks [hi_c | lo_c] (operand format of the 3xTF32 GEMM policy)."""
+def _split_code(split, C):
+    """split: None/False plain | "tf32"/True fp32 [hi|lo] halves | "f16" fp16 [hi|lo*2^11] | "f16u" fp16 [hi|lo]"""
+    code = SPLIT_CODES[split]
+    return C if code is None else code
+
+
+def _split_out(x, split):
+    C = x.shape[-1]
+    code = _split_code(split, C)
+    if code == 0:
+        return torch.empty(x.shape, device=x.device, dtype=torch.float32), code
+    dt = torch.float32 if code > 0 else torch.float16
+    return torch.empty((*x.shape[:-1], 2 * C), device=x.device, dtype=dt), code
+
+
+def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=None):
+    """Fused (residual add +) LayerNorm over the last dim.  Returns (sum_or_None, out); `out` is fp32 [..., C] or a
+    split GEMM operand [..., 2C] (see _split_code)."""
     C = x.shape[-1]
     rows = x.numel() // C
-    out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
+    out, code = _split_out(x, split)
     s = torch.empty_like(x) if (want_sum and residual is not None) else None
     with _Bracket("layernorm", 1):
         rc = lib().univs_layernorm_f32(_stream(), _chk(x, "x"), None if residual is None else _chk(residual, "residual"),
                                        _chk(weight, "weight"), _chk(bias, "bias"), rows, C, float(eps),
-                                       None if s is None else s.data_ptr(), out.data_ptr(), split_chunk(C) if split else 0)
+                                       None if s is None else s.data_ptr(), out.data_ptr(), code)
     check(rc, "layernorm")
     if want_sum and residual is None:
         s = x
     return s, out
 
 
-def gelu(x, split=False):
+def gelu(x, split=None):
     C = x.shape[-1]
-    out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
+    out, code = _split_out(x, split)
     with _Bracket("gelu", 1):
-        rc = lib().univs_gelu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), split_chunk(C) if split else 0)
+        rc = lib().univs_gelu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), code)
     check(rc, "gelu")
     return out
 
 
-def relu(x, split=False):
+def relu(x, split=None):
     C = x.shape[-1]
-    out = torch.empty((*x.shape[:-1], 2 * C if split else C), device=x.device, dtype=torch.float32)
+    out, code = _split_out(x, split)
     with _Bracket("relu", 1):
-        rc = lib().univs_relu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), split_chunk(C) if split else 0)
+        rc = lib().univs_relu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), code)
     check(rc, "relu")
     return out
 
 
-def split_tf32(x, chunk=None):
-    """[..., C] -> [..., 2C] in K-chunks of `chunk` (default split_chunk(C)) columns: chunk c = [hi_c | lo_c]"""
+def split_operand(x, split="tf32"):
+    """[..., C] fp32 -> split GEMM operand [..., 2C] ("tf32": fp32 [hi|lo]; "f16": fp16 [hi|lo*2^11]; "f16u": fp16 [hi|lo])"""
     C = x.shape[-1]
-    out = torch.empty((*x.shape[:-1], 2 * C), device=x.device, dtype=torch.float32)
-    with _Bracket("split_tf32", 1):
-        rc = lib().univs_split_tf32_f32(_stream(), _chk(x, "x"), x.numel() // C, C,
-                                        split_chunk(C) if chunk is None else chunk, out.data_ptr())
-    check(rc, "split_tf32")
+    out, code = _split_out(x, split)
+    with _Bracket("split", 1):
+        rc = lib().univs_split_tf32_f32(_stream(), _chk(x, "x"), x.numel() // C, C, code, out.data_ptr())
+    check(rc, "split")
     return out
+
+
+def split_tf32(x, chunk=None):
+    return split_operand(x, "tf32")
 
 
 def round_tf32(x, out=None):

@@ -4,6 +4,9 @@
          hi|lo-split operands (nn_ops.py), the attention contractions and the mask einsum use the 3xTF32 split
          in-kernel; fp32 accumulation, softmax, LayerNorm, residuals.  Meets the 1e-3 mask-logit bound
          (profiles/parity_at_scale_*.json).
+"fp16x3": same construction with fp16 hi|lo*2^11 operands (fp16 has TF32's 11-bit significand, so hi*hi is exact in
+         fp32 and two terms give 22 bits) at twice the tensor-core rate and half the operand bytes; operands
+         saturate at +-65504 (LayerNorm / attention / activation outputs are far inside that range).
 "tf32":  single-pass TF32 everywhere (round-to-nearest operands); ~1e-3 feature error which the discontinuous
          masked-attention decoder amplifies -- fails the mask-logit bound on random-init models; kept as the
          throughput upper bound of the same kernels.
@@ -28,12 +31,12 @@ def set_precision(mode: str):
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
         ops.set_attention_precision(ops.PREC_TF32)
-    elif mode == "tf32x3":
+    elif mode in ("tf32x3", "fp16x3"):
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
         ops.set_attention_precision(ops.PREC_TF32X3)
     else:
-        raise ValueError(f"unknown precision mode {mode!r} (tf32x3 | tf32 | fp32)")
+        raise ValueError(f"unknown precision mode {mode!r} (fp16x3 | tf32x3 | tf32 | fp32)")
     nn_ops.set_policy(mode)
     _mode = mode
 
