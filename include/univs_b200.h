@@ -108,14 +108,15 @@ int univs_proca_forward_f32(void* stream, const float* q, const float* k_self, c
  * of the 3xTF32 (fp32-equivalent) GEMM policy, X*W^T ~= sum_c ([Xh|Xl]_c*[Wh|Wh]_c^T + Xh_c*Wl_c^T).  K is chunked
  * because the tensor cores accumulate with truncation: the bias grows linearly with the accumulation chain
  * (tools/accum_probe.py), so chains are kept <= Kc/8 MMA steps and chunks are summed in the fp32 epilogue.
- * `split` = UNIVS_SPLIT_F16 / UNIVS_SPLIT_F16U write fp16 [rows, 2*C] (hi = fp16(x) saturating, lo = x - hi, scaled
- * by 2^11 or not): fp16 has TF32's 11-bit significand at twice the tensor-core rate and half the bytes; `out` is then
- * a __half buffer of 2*C*rows elements.
+ * `split` = UNIVS_SPLIT_F16U writes fp16 [rows, 2*C] = [hi | lo]; `split` = -Kc writes fp16 [rows, 3*C] in K-chunks
+ * [lo*2^11 | hi*2^-11 | hi] (hi = fp16(x) saturating, lo = x - hi): fp16 has TF32's 11-bit significand at twice the
+ * tensor-core rate; X*W^T = [Xl' | Xh_s | Xh][Wh_s | Wl' | Wh]^T is ONE GEMM (correction terms first).  `out` is
+ * then a __half buffer.
  * layernorm: s = x (+ residual, nullable); sum_out (nullable) = s; out = LayerNorm(s)*gamma+beta (nn.LayerNorm,
  *   e.g. swin.py:246,292).  channels % 4 == 0, <= 4096.
  * gelu: exact erf GELU (nn.GELU default, swin.py:24-41). */
-#define UNIVS_SPLIT_F16 (-1)   /* fp16 [rows,2C] = [hi | lo*2^11]  (operand format of the fp16x3 GEMM policy) */
-#define UNIVS_SPLIT_F16U (-2)  /* fp16 [rows,2C] = [hi | lo]       (operands of the fp16 mask einsum)            */
+#define UNIVS_SPLIT_F16U (-2)  /* fp16 [rows,2C] = [hi | lo]  (operands of the fp16 mask einsum)                            */
+/* split = -Kc (Kc >= 4, Kc | C): fp16 [rows,3C] in K-chunks [lo*2^11 | hi*2^-11 | hi]  (A operand of the fp16x3 GEMM) */
 int univs_layernorm_f32(void* stream, const float* x, const float* residual, const float* gamma, const float* beta,
                         int64_t rows, int channels, float eps, float* sum_out, float* out, int split);
 int univs_gelu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split);

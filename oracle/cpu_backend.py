@@ -70,7 +70,14 @@ def _split(x, chunk=None):
 def _split16(x, scaled):
     hi = x.clamp(-65504, 65504).half()
     lo = ((x - hi.float()) * (2048.0 if scaled else 1.0)).clamp(-65504, 65504).half()
-    return torch.cat([hi, lo], -1)
+    if not scaled:
+        return torch.cat([hi, lo], -1)
+    from univs_b200.ops import f16_chunk
+    C = x.shape[-1]
+    kc = f16_chunk(C)
+    hs = (hi.float() / 2048.0).half()
+    parts = [t.reshape(*x.shape[:-1], C // kc, kc) for t in (lo, hs, hi)]
+    return torch.stack(parts, -2).reshape(*x.shape[:-1], 3 * C)
 
 
 def _maybe_split(y, split):

@@ -278,16 +278,20 @@ def test_split_conv3x3_reproduces_fp32(ops):
 def test_fp16_split_formats(ops):
     torch.manual_seed(25)
     x = torch.randn(300, 384) * torch.logspace(-6, 2, 384)          # magnitudes from 1e-6 to 1e2
-    s16 = ops.split_operand(x.cuda(), "f16")
-    assert s16.dtype == torch.float16 and s16.shape == (300, 768)
-    rec = s16[:, :384].float() + s16[:, 384:].float() * 2.0 ** -11
-    assert ((rec.cpu() - x).abs() <= x.abs() * 2.0 ** -21 + 1e-12).all()       # ~22-bit reconstruction
+    s16 = ops.split_operand(x.cuda(), "f16")                         # chunks [lo*2^11 | hi*2^-11 | hi]
+    assert s16.dtype == torch.float16 and s16.shape == (300, 3 * 384)
+    lo, hs, hi = s16[:, :384].float(), s16[:, 384:768].float(), s16[:, 768:].float()
+    rec = hi + lo * 2.0 ** -11
+    assert ((rec.cpu() - x).abs() <= x.abs() * 2.0 ** -21 + 3e-11).all()       # ~22-bit reconstruction
+    assert ((hs * 2048.0 - hi).abs() <= 2048 * 3.1e-8).all()                    # hi*2^-11 up to the fp16 subnormal floor
     u16 = ops.split_operand(x.cuda(), "f16u")
     rec = u16[:, :384].float() + u16[:, 384:].float()
     assert ((rec.cpu() - x).abs() <= x.abs() * 2.0 ** -21 + 4e-8).all()        # unscaled lo: fp16 subnormal floor
     big = torch.tensor([[1e6, -1e6, 70000.0, 1.0]]).cuda()
-    sat = ops.split_operand(big, "f16")
-    assert torch.isfinite(sat.float()).all()                                     # saturating, never inf
+    assert torch.isfinite(ops.split_operand(big, "f16").float()).all()          # saturating, never inf
+    wide = torch.randn(8, 3072).cuda()                                           # chunked layout (2 chunks of 1536)
+    w3 = ops.split_operand(wide, "f16").view(8, 2, 3, 1536).float()
+    assert torch.allclose((w3[:, :, 2] + w3[:, :, 0] * 2.0 ** -11).reshape(8, 3072), wide, rtol=1e-6, atol=1e-9)
 
 
 def test_fp16x3_gemm_reproduces_fp32(ops):

@@ -24,12 +24,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(f2tf32(x)); }
 
 // Output formats of the row-wise kernels (`split` argument):
-//   0                plain fp32 [rows, C]
-//   Kc > 0           fp32 [rows, 2C] in K-chunks of Kc columns, chunk c = [hi_c | lo_c], hi = rna_tf32(x), lo = x - hi
-//   UNIVS_SPLIT_F16  (-1) fp16 [rows, 2C] = [hi | lo*2^11], hi = fp16(x) (round-to-nearest, saturating), lo = x - hi
-//   UNIVS_SPLIT_F16U (-2) fp16 [rows, 2C] = [hi | lo] (lo unscaled; operands of the fp16 mask einsum)
+//   0          plain fp32 [rows, C]
+//   Kc > 0     fp32 [rows, 2C] in K-chunks of Kc columns, chunk c = [hi_c | lo_c], hi = rna_tf32(x), lo = x - hi
+//   -2         fp16 [rows, 2C] = [hi | lo], hi = fp16(x) (round-to-nearest, saturating), lo = x - hi   (einsum operands)
+//   -Kc <= -4  fp16 [rows, 3C] in K-chunks of Kc columns, chunk c = [lo_c * 2^11 | hi_c * 2^-11 | hi_c]: the A operand of
+//              the single-GEMM fp16x3 product  X W^T = [Xl' | Xh_s | Xh] [Wh_s | Wl' | Wh]^T  (correction terms first, so
+//              the tensor core's truncating accumulator is still small while they are added; main term last).
 // fp16 carries an 11-bit significand like TF32, so hi*hi products are exact in fp32 and two terms give 22 bits; the
-// 2^11 scale keeps lo out of the fp16 subnormal range (undone by alpha = 2^-11 in the correction GEMM).
+// 2^11 scale keeps lo out of the fp16 subnormal range.
 __device__ __forceinline__ __half sat_half(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
 
 __device__ __forceinline__ void store_maybe_split(float* __restrict__ out, size_t row, int C, int col, float4 v, int split) {
@@ -43,16 +45,34 @@ __device__ __forceinline__ void store_maybe_split(float* __restrict__ out, size_
     *reinterpret_cast<float4*>(out + o) = h;
     *reinterpret_cast<float4*>(out + o + split) = l;
   } else {
-    const float sc = (split == -1) ? 2048.f : 1.f;
     __half* o16 = reinterpret_cast<__half*>(out);
-    const __half h0 = sat_half(v.x), h1 = sat_half(v.y), h2 = sat_half(v.z), h3 = sat_half(v.w);
-    const __half l0 = sat_half((v.x - __half2float(h0)) * sc), l1 = sat_half((v.y - __half2float(h1)) * sc);
-    const __half l2 = sat_half((v.z - __half2float(h2)) * sc), l3 = sat_half((v.w - __half2float(h3)) * sc);
-    const size_t o = row * (2 * (size_t)C) + col;
-    *reinterpret_cast<__half2*>(o16 + o) = __halves2half2(h0, h1);
-    *reinterpret_cast<__half2*>(o16 + o + 2) = __halves2half2(h2, h3);
-    *reinterpret_cast<__half2*>(o16 + o + C) = __halves2half2(l0, l1);
-    *reinterpret_cast<__half2*>(o16 + o + C + 2) = __halves2half2(l2, l3);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    __half h[4], l[4], hs[4];
+    const float sc = (split == -2) ? 1.f : 2048.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = sat_half(vv[i]);
+      const float hf = __half2float(h[i]);
+      l[i] = sat_half((vv[i] - hf) * sc);
+      hs[i] = __float2half_rn(hf * (1.f / 2048.f));
+    }
+    if (split == -2) {
+      const size_t o = row * (2 * (size_t)C) + col;
+      *reinterpret_cast<__half2*>(o16 + o) = __halves2half2(h[0], h[1]);
+      *reinterpret_cast<__half2*>(o16 + o + 2) = __halves2half2(h[2], h[3]);
+      *reinterpret_cast<__half2*>(o16 + o + C) = __halves2half2(l[0], l[1]);
+      *reinterpret_cast<__half2*>(o16 + o + C + 2) = __halves2half2(l[2], l[3]);
+    } else {
+      const int kc = -split;
+      const int chunk = col / kc;
+      const size_t o = row * (3 * (size_t)C) + (size_t)chunk * (3 * kc) + (col - chunk * kc);
+      *reinterpret_cast<__half2*>(o16 + o) = __halves2half2(l[0], l[1]);
+      *reinterpret_cast<__half2*>(o16 + o + 2) = __halves2half2(l[2], l[3]);
+      *reinterpret_cast<__half2*>(o16 + o + kc) = __halves2half2(hs[0], hs[1]);
+      *reinterpret_cast<__half2*>(o16 + o + kc + 2) = __halves2half2(hs[2], hs[3]);
+      *reinterpret_cast<__half2*>(o16 + o + 2 * kc) = __halves2half2(h[0], h[1]);
+      *reinterpret_cast<__half2*>(o16 + o + 2 * kc + 2) = __halves2half2(h[2], h[3]);
+    }
   }
 }
 
@@ -140,7 +160,8 @@ extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* re
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
   UNIVS_REQUIRE(channels % 4 == 0 && channels <= 4096, "layernorm: channels must be a multiple of 4 and <= 4096 (got %d)", channels);
-  UNIVS_REQUIRE(split == 0 || split == -1 || split == -2 || (split > 0 && split % 4 == 0 && channels % split == 0),
+  UNIVS_REQUIRE(split == 0 || split == -2 || (split != -1 && split != -3 && (split > 0 ? split : -split) % 4 == 0 &&
+                                               channels % (split > 0 ? split : -split) == 0),
                 "layernorm: split chunk must divide channels");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
@@ -177,8 +198,9 @@ extern "C" int univs_relu_f32(void* stream, const float* x, int64_t rows, int ch
 
 extern "C" int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, int chunk, float* out) {
   UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "split_tf32: bad sizes (channels %% 4 == 0)");
-  UNIVS_REQUIRE(chunk == -1 || chunk == -2 || (chunk > 0 && chunk % 4 == 0 && channels % chunk == 0),
-                "split_tf32: chunk must divide channels and be a multiple of 4 (or -1/-2 for the fp16 formats)");
+  UNIVS_REQUIRE(chunk == -2 || (chunk != 0 && chunk != -1 && chunk != -3 && (chunk > 0 ? chunk : -chunk) % 4 == 0 &&
+                               channels % (chunk > 0 ? chunk : -chunk) == 0),
+                "split_tf32: |chunk| must divide channels and be a multiple of 4 (or -2 for the fp16 [hi|lo] format)");
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && out, "split_tf32: null pointer");
   long long blocks = (rows * (channels / 4) + 255) / 256;

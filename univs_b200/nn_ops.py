@@ -51,19 +51,48 @@ def g1_chunk(K: int) -> int:
 
 
 def _split_weight(w: torch.Tensor, cache=True):
-    """2-D weight [N,K] -> (Wh [N,K], Wlh [N,2K] = [Wl | Wh]); cached per parameter version."""
+    """2-D weight [N,K] -> policy-specific B operands, cached per parameter version.
+    tf32x3: (Wh [N,K], Wlh [N,2K] = [Wl | Wh]).
+    fp16x3: (B3 [N,3K] fp16 in K-chunks [Wh*2^-11 | Wl*2^11 | Wh] of W*2^s, alpha = 2^-s); s is a per-tensor power of
+            two that lifts the weights into fp16's normal range."""
     key = id(w)
-    sig = (w.data_ptr(), w._version, tuple(w.shape))
+    sig = (w.data_ptr(), w._version, tuple(w.shape), _policy)
     ent = _wcache.get(key) if cache else None
     if ent is None or ent[0] != sig:
         w2d = w.detach().float().reshape(w.shape[0], -1).contiguous()
         N, K = w2d.shape
-        hl = ops.split_operand(w2d, _fmt())                             # [N,2K] = [hi | lo]  (fp32 or fp16)
-        hi, lo = hl[:, :K], hl[:, K:]
-        ent = (sig, hi.contiguous(), torch.cat([lo, hi], 1).contiguous())
+        if _policy == "tf32x3":
+            hl = ops.split_operand(w2d, "tf32")                              # [N,2K] = [hi | lo]
+            hi, lo = hl[:, :K], hl[:, K:]
+            ent = (sig, hi.contiguous(), torch.cat([lo, hi], 1).contiguous())
+        else:
+            amax = float(w2d.abs().max())
+            s = 0 if amax == 0.0 else max(-24, min(24, int(torch.floor(torch.log2(torch.tensor(8192.0 / amax))))))
+            a3 = ops.split_operand(w2d * (2.0 ** s), "f16")                   # chunks [lo' | hi_s | hi]
+            kc = ops.f16_chunk(K)
+            v = a3.view(N, K // kc, 3, kc)
+            b3 = torch.stack([v[:, :, 1], v[:, :, 0], v[:, :, 2]], 2).reshape(N, 3 * K).contiguous()   # [hi_s | lo' | hi]
+            ent = (sig, b3, 2.0 ** -s)
         if cache:
             _wcache[key] = ent
     return ent[1], ent[2]
+
+
+_inplace16 = [None]     # whether torch.addmm(..., out_dtype=f32, out=acc) accepts acc as both input and output
+
+
+def _addmm16(acc, a, bt, alpha):
+    """acc (fp32) + alpha * a @ bt with fp16 operands and fp32 accumulate/output."""
+    if _inplace16[0] is not False:
+        try:
+            y = torch.addmm(acc, a, bt, alpha=alpha, out_dtype=torch.float32, out=acc)
+            _inplace16[0] = True
+            return y
+        except (RuntimeError, TypeError):
+            if _inplace16[0] is True:
+                raise
+            _inplace16[0] = False
+    return torch.addmm(acc, a, bt, alpha=alpha, out_dtype=torch.float32)
 
 
 def prep(x):
@@ -94,22 +123,26 @@ def linear_prepped(h, weight, bias=None, cache=True):
         return F.linear(h, weight, bias)
     N, K = weight.shape
     wh, wlh = _split_weight(weight, cache)
-    h2 = h.reshape(-1, 2 * K)
     kc = g1_chunk(K)
     if _policy == "tf32x3":
+        h2 = h.reshape(-1, 2 * K)
         y = F.linear(h2[:, :kc], wh[:, :kc], bias)
         for k0 in range(kc, K, kc):
             y.addmm_(h2[:, k0:k0 + kc], wh[:, k0:k0 + kc].t())
         y.addmm_(h2, wlh.t())
-    else:  # fp16x3: fp16 operands, fp32 accumulate + fp32 output; lo terms carry a 2^11 scale -> alpha = 2^-11
+    else:  # fp16x3: ONE fp16 GEMM per K-chunk over [Xl' | Xh_s | Xh] x [Wh_s | Wl' | Wh], fp32 accumulate and output
         f32 = torch.float32
+        b3, alpha = wh, wlh
+        kc3 = 3 * ops.f16_chunk(K)
+        h3 = h.reshape(-1, 3 * K)
         if bias is not None:
-            y = torch.addmm(bias.float(), h2[:, :kc], wh[:, :kc].t(), out_dtype=f32)
+            y = torch.addmm(bias.float(), h3[:, :kc3], b3[:, :kc3].t(), alpha=alpha, out_dtype=f32)
         else:
-            y = torch.mm(h2[:, :kc], wh[:, :kc].t(), out_dtype=f32)
-        for k0 in range(kc, K, kc):
-            y = torch.addmm(y, h2[:, k0:k0 + kc], wh[:, k0:k0 + kc].t(), out_dtype=f32)
-        y = torch.addmm(y, h2, wlh.t(), alpha=2.0 ** -11, out_dtype=f32)
+            y = torch.mm(h3[:, :kc3], b3[:, :kc3].t(), out_dtype=f32)
+            if alpha != 1.0:
+                y.mul_(alpha)
+        for k0 in range(kc3, 3 * K, kc3):
+            y = _addmm16(y, h3[:, k0:k0 + kc3], b3[:, k0:k0 + kc3].t(), alpha)
     return y.view(*h.shape[:-1], N)
 
 
@@ -141,11 +174,12 @@ def conv2d_cl(x_cl, weight, bias=None, padding=0):
     p = padding
     Hp, Wp = H + 2 * p, W + 2 * p
     xs = F.pad(ops.split_operand(x_cl.contiguous(), _fmt()), (0, 0, p, p, p, p))  # [N,Hp,Wp,2Cin], zeros split to zeros
-    x2 = xs.view(N * Hp * Wp, 2 * Cin)
+    x2 = xs.view(N * Hp * Wp, xs.shape[-1])
     R = N * Hp * Wp - ((kh - 1) * Wp + (kw - 1))                                  # rows every tap can address
     y = torch.empty((N * Hp * Wp, Cout), device=x_cl.device, dtype=torch.float32)
     yr = y[:R]
     f32 = torch.float32
+    mult = 2 if _policy == "tf32x3" else 3
     for t, (wh, wlh) in enumerate(ent[1]):
         off = (t // kw) * Wp + (t % kw)
         a = x2[off: off + R]
@@ -157,12 +191,11 @@ def conv2d_cl(x_cl, weight, bias=None, padding=0):
             yr.addmm_(a, wlh.t())
         else:
             if t == 0:
-                yr = torch.addmm(bias.float() if bias is not None else y.new_zeros(Cout), a[:, :Cin], wh.t(), out_dtype=f32)
+                yr = torch.addmm(bias.float() if bias is not None else y.new_zeros(Cout), a, wh.t(), alpha=wlh, out_dtype=f32)
             else:
-                yr = torch.addmm(yr, a[:, :Cin], wh.t(), out_dtype=f32)
-            yr = torch.addmm(yr, a, wlh.t(), alpha=2.0 ** -11, out_dtype=f32)
+                yr = _addmm16(yr, a, wh.t(), wlh)
     if _policy != "tf32x3":
-        y[:R] = yr
+        return torch.cat([yr, yr.new_zeros(N * Hp * Wp - R, Cout)], 0).view(N, Hp, Wp, Cout)[:, :H, :W]
     return y.view(N, Hp, Wp, Cout)[:, :H, :W]
 
 

@@ -228,22 +228,34 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
     return out
 
 
-SPLIT_CODES = {None: 0, False: 0, "tf32": None, True: None, "f16": -1, "f16u": -2}
+def f16_chunk(K: int) -> int:
+    """K-chunk of the fp16x3 operand layout: the largest divisor of K that is <= 1536 and a multiple of 32 (bounds the
+    main-term accumulation chain of one GEMM to 96 MMA steps; chunks are summed by fp32 GEMM epilogues)."""
+    if K <= 1536:
+        return K
+    for c in range(1536, 31, -32):
+        if K % c == 0:
+            return c
+    return K
 
 
 def _split_code(split, C):
-    """split: None/False plain | "tf32"/True fp32 [hi|lo] halves | "f16" fp16 [hi|lo*2^11] | "f16u" fp16 [hi|lo]"""
-    code = SPLIT_CODES[split]
-    return C if code is None else code
+    """split: None/False plain | "tf32"/True fp32 [hi|lo] | "f16" fp16 chunks [lo*2^11|hi*2^-11|hi] | "f16u" fp16 [hi|lo]"""
+    if not split:
+        return 0, 1, torch.float32
+    if split in ("tf32", True):
+        return C, 2, torch.float32
+    if split == "f16":
+        return -f16_chunk(C), 3, torch.float16
+    if split == "f16u":
+        return -2, 2, torch.float16
+    raise ValueError(split)
 
 
 def _split_out(x, split):
     C = x.shape[-1]
-    code = _split_code(split, C)
-    if code == 0:
-        return torch.empty(x.shape, device=x.device, dtype=torch.float32), code
-    dt = torch.float32 if code > 0 else torch.float16
-    return torch.empty((*x.shape[:-1], 2 * C), device=x.device, dtype=dt), code
+    code, mult, dt = _split_code(split, C)
+    return torch.empty((*x.shape[:-1], mult * C), device=x.device, dtype=dt), code
 
 
 def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=None):
@@ -282,7 +294,8 @@ def relu(x, split=None):
 
 
 def split_operand(x, split="tf32"):
-    """[..., C] fp32 -> split GEMM operand [..., 2C] ("tf32": fp32 [hi|lo]; "f16": fp16 [hi|lo*2^11]; "f16u": fp16 [hi|lo])"""
+    """[..., C] fp32 -> split GEMM operand ("tf32": fp32 [..,2C] = [hi|lo]; "f16": fp16 [..,3C] chunks [lo*2^11|hi*2^-11|hi];
+    "f16u": fp16 [..,2C] = [hi|lo])"""
     C = x.shape[-1]
     out, code = _split_out(x, split)
     with _Bracket("split", 1):
