@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--workload", default="ns", choices=list(WORKLOADS))
     ap.add_argument("--precision", default=os.environ.get("UNIVS_PRECISION", "tf32x3"), choices=["fp16x3", "tf32x3", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the clip eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: after warm-up run ONE step between cudaProfilerStart/Stop and exit "
                          "(use with `ncu --profile-from-start off`); prints no bench line")
@@ -183,39 +184,55 @@ def main():
         return ms.item()
 
     # ---- device-resident throughput ------------------------------------------------------------------------
-    def step_resident():
+    def step_eager():
         return model.clip_forward(frames_dev, make_targets(T, dev))
 
     for _ in range(warmup):
-        out = step_resident()
+        out = step_eager()
     n_lp = out["pred_masks"].shape[1]
     if args.ncu_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step_resident()
+        step_eager()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
+    use_graph = (world == 1) and not args.no_graph
+    graphed = None
+    if use_graph:
+        from univs_b200.runtime import GraphedClip
+        graphed = GraphedClip(model, frames_dev, lambda: make_targets(T, dev))
+        step_resident = lambda: graphed(frames_dev)
+    else:
+        step_resident = step_eager
+    for _ in range(2):
+        out = step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    ms_total = timed(step_resident, steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / steps
+    fps = T / (ms_per_step / 1e3)
+
+    # ---- per-kernel CUDA-event brackets (eager pass: events cannot be read back from inside a graph replay) ---
     sink = ops.profile_events(True)
     launches0 = ops.launch_count
-    ms_total = timed(step_resident, steps)
+    timed(step_eager, steps)
     launches = (ops.launch_count - launches0) // steps
     torch.cuda.synchronize()
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in sink.items()}
     kernel_calls = {k: len(v) // steps for k, v in sink.items()}
     ops.profile_events(False)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms_total / steps
-    fps = T / (ms_per_step / 1e3)
 
     # ---- end-to-end through the public API with host buffers ------------------------------------------------
     d2h_pinned = {}
 
     def step_e2e():
-        o = model.clip_forward(frames_host, make_targets(T, dev))      # H2D of the pinned uint8 frames inside
+        if graphed is not None:
+            o = graphed(frames_host)                                    # H2D of the pinned uint8 frames, then replay
+        else:
+            o = model.clip_forward(frames_host, make_targets(T, dev))
         res = {"pred_logits": o["pred_logits"], "pred_embds": o["pred_embds"], "pred_masks_bin": o["pred_masks"] > 0}
         for k, v in res.items():
             if k not in d2h_pinned:
@@ -257,6 +274,7 @@ def main():
             "dtype": {"fp16x3": "fp16x3 (2-term fp16 split operands, fp32-equivalent products, fp32 accumulate)", "tf32x3": "tf32x3 (3-pass TF32 split, fp32-equivalent products, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init",
                        "precision": args.precision, "parallelism": f"frame-shard x{world}" if world > 1 else "single",
+                       "execution": "CUDA graph replay" if use_graph else "eager",
                        "l2": "per-step working set (multi-GB activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": T / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

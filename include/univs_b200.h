@@ -56,7 +56,8 @@ int univs_ms_deform_attn_encoder_f32(void* stream, const float* value, const int
                                      int spatial_size, int num_heads, int num_levels, int num_point, float* out);
 
 /* ---- Swin (shifted-)window attention, addressing folded in (a2,a3).
- * qkv [B,H,W,3C] f32 = Linear(LN(x)) on the unpadded token grid; qkv_bias [3C] (value of pad tokens);
+ * qkv [B,H,W,3C] f32 = LN(x) * Wqkv^T on the unpadded token grid WITHOUT the bias; qkv_bias [3C] is added by the kernel
+ * to every token (and is the whole value of a pad token: zero-padded after norm1, swin.py:247-255);
  * rel_bias_table [(2*window-1)^2, num_heads]; head_dim = C/num_heads must be 32; window in {7,12} (or any <=12);
  * shift = 0 or window/2.  out [B,H,W,C] f32 (pre output projection). */
 int univs_swin_window_attention_f32(void* stream, const float* qkv, const float* qkv_bias,
@@ -112,15 +113,17 @@ int univs_proca_forward_f32(void* stream, const float* q, const float* k_self, c
  * [lo*2^11 | hi*2^-11 | hi] (hi = fp16(x) saturating, lo = x - hi): fp16 has TF32's 11-bit significand at twice the
  * tensor-core rate; X*W^T = [Xl' | Xh_s | Xh][Wh_s | Wl' | Wh]^T is ONE GEMM (correction terms first).  `out` is
  * then a __half buffer.
- * layernorm: s = x (+ residual, nullable); sum_out (nullable) = s; out = LayerNorm(s)*gamma+beta (nn.LayerNorm,
+ * layernorm: s = x (+ residual (+ residual_bias), nullable); sum_out (nullable) = s; out = LayerNorm(s)*gamma+beta (nn.LayerNorm,
  *   e.g. swin.py:246,292).  channels % 4 == 0, <= 4096.
  * gelu: exact erf GELU (nn.GELU default, swin.py:24-41). */
 #define UNIVS_SPLIT_F16U (-2)  /* fp16 [rows,2C] = [hi | lo]  (operands of the fp16 mask einsum)                            */
 /* split = -Kc (Kc >= 4, Kc | C): fp16 [rows,3C] in K-chunks [lo*2^11 | hi*2^-11 | hi]  (A operand of the fp16x3 GEMM) */
-int univs_layernorm_f32(void* stream, const float* x, const float* residual, const float* gamma, const float* beta,
-                        int64_t rows, int channels, float eps, float* sum_out, float* out, int split);
-int univs_gelu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split);
-int univs_relu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split);
+int univs_layernorm_f32(void* stream, const float* x, const float* residual, const float* residual_bias,
+                        const float* gamma, const float* beta, int64_t rows, int channels, float eps, float* sum_out,
+                        float* out, int split);
+/* bias (nullable, [channels]) = the bias of the GEMM that produced x (resp. `residual`), deferred into these kernels */
+int univs_gelu_f32(void* stream, const float* x, const float* bias, int64_t rows, int channels, float* out, int split);
+int univs_relu_f32(void* stream, const float* x, const float* bias, int64_t rows, int channels, float* out, int split);
 int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, int chunk, float* out);
 
 /* ---- helpers ---- */

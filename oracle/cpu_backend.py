@@ -88,14 +88,18 @@ def _maybe_split(y, split):
     return _split(y)
 
 
-def _layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=None):
+def _layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=None, residual_bias=None):
     s = x if residual is None else x + residual
+    if residual_bias is not None:
+        s = s + residual_bias
     y = torch.nn.functional.layer_norm(s, (x.shape[-1],), weight, bias, eps)
     return (s if want_sum else None), _maybe_split(y, split)
 
 
-_PATCH = {"layernorm": _layernorm, "gelu": lambda x, split=None: _maybe_split(torch.nn.functional.gelu(x), split),
-          "relu": lambda x, split=None: _maybe_split(torch.relu(x), split), "split_tf32": _split,
+_PATCH = {"layernorm": _layernorm,
+          "gelu": lambda x, split=None, bias=None: _maybe_split(torch.nn.functional.gelu(x if bias is None else x + bias), split),
+          "relu": lambda x, split=None, bias=None: _maybe_split(torch.relu(x if bias is None else x + bias), split),
+          "split_tf32": _split,
           "split_operand": lambda x, split="tf32": _maybe_split(x, split),
           "swin_window_attention": _swin, "ms_deform_attn_encoder": _msda_enc, "ms_deform_attn_forward": _msda_fwd,
           "mask_einsum": _einsum, "attn_mask_bits": _bits, "mha_core": _mha, "proca_core": _proca,

@@ -90,8 +90,9 @@ def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offs_logits, 
 # :413-440 (shift mask on the padded grid, -100 not -inf).
 # ---------------------------------------------------------------------------
 def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shift):
-    """qkv [B,H,W,3C] = Linear(LN(x)) on the UNPADDED token grid; pad tokens are zeros after
-    norm1 in the reference (swin.py:247-255), so their qkv equals the qkv bias.
+    """qkv [B,H,W,3C] = LN(x) @ Wqkv^T on the UNPADDED token grid WITHOUT the bias (the operator adds
+    qkv_bias to every token); pad tokens are zeros after norm1 in the reference (swin.py:247-255),
+    so their qkv equals the qkv bias.
     rel_bias_table [(2w-1)^2, nH].  Returns the attention output (pre-proj) [B,H,W,C]."""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
@@ -100,7 +101,7 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     Hp = (H + ws - 1) // ws * ws
     Wp = (W + ws - 1) // ws * ws
     full = qkv_bias.view(1, 1, 1, C3).expand(B, Hp, Wp, C3).clone()
-    full[:, :H, :W] = qkv
+    full[:, :H, :W] = qkv + qkv_bias
     if shift > 0:
         full = torch.roll(full, shifts=(-shift, -shift), dims=(1, 2))
     nWh, nWw = Hp // ws, Wp // ws
@@ -242,12 +243,14 @@ def split_tf32(x, chunk=None):
     return hl.reshape(*x.shape[:-1], 2 * C)
 
 
-def layernorm(x, weight, bias, eps=1e-5, residual=None):
-    """nn.LayerNorm over the last dim of (x + residual) (swin.py:246,292; transformer_layers.py:42)."""
+def layernorm(x, weight, bias, eps=1e-5, residual=None, residual_bias=None):
+    """nn.LayerNorm over the last dim of (x + residual + residual_bias) (swin.py:246,292; transformer_layers.py:42)."""
     s = x if residual is None else x + residual
+    if residual_bias is not None:
+        s = s + residual_bias
     return s, F.layer_norm(s.double(), (x.shape[-1],), weight.double(), bias.double(), eps).float()
 
 
-def gelu(x):
-    """nn.GELU() default = exact erf form (swin.py:24-41)."""
-    return F.gelu(x.double()).float()
+def gelu(x, bias=None):
+    """nn.GELU() default = exact erf form (swin.py:24-41), applied to x + bias."""
+    return F.gelu((x if bias is None else x + bias).double()).float()

@@ -217,11 +217,14 @@ def test_layernorm_fused(ops, rows, C, with_res):
     x = torch.randn(rows, C) * 3 + 0.5
     r = torch.randn(rows, C) if with_res else None
     w, b = torch.randn(C), torch.randn(C)
-    s_want, y_want = ops_ref.layernorm(x, w, b, 1e-5, r)
-    s, y = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), want_sum=True)
+    rb = torch.randn(C) if with_res else None
+    s_want, y_want = ops_ref.layernorm(x, w, b, 1e-5, r, rb)
+    s, y = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), want_sum=True,
+                         residual_bias=None if rb is None else rb.cuda())
     assert _rel(y, y_want) < 2e-6
-    assert torch.equal(s.cpu(), s_want)
-    _, ys = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), split="tf32")
+    assert _rel(s, s_want) < 1e-6
+    _, ys = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, None if r is None else r.cuda(), split="tf32",
+                          residual_bias=None if rb is None else rb.cuda())
     assert ys.shape == (rows, 2 * C)
     assert torch.equal(ys.cpu(), ops_ref.split_tf32(y.cpu()))            # split of exactly the plain output
     kc = C
@@ -234,6 +237,9 @@ def test_gelu_relu_split(ops):
     torch.manual_seed(22)
     x = torch.randn(257, 768) * 2
     assert _rel(ops.gelu(x.cuda()), ops_ref.gelu(x)) < 1e-6
+    bb = torch.randn(768)
+    assert _rel(ops.gelu(x.cuda(), bias=bb.cuda()), ops_ref.gelu(x, bb)) < 1e-6
+    assert torch.equal(ops.relu(x.cuda(), bias=bb.cuda()).cpu(), torch.relu(x + bb))
     gs = ops.gelu(x.cuda(), split="tf32")
     assert torch.equal(gs.cpu(), ops_ref.split_tf32(ops.gelu(x.cuda()).cpu()))
     assert torch.equal(ops.relu(x.cuda()).cpu(), torch.relu(x))

@@ -90,7 +90,7 @@ def test_swin_window_attention_vs_basic_layer(ref, H, W, ws, nH):
         want = layer(x, H, W)[0]
         y = x
         for i, blk in enumerate(layer.blocks):
-            qkv = blk.attn.qkv(blk.norm1(y)).view(2, H, W, 3 * C)
+            qkv = torch.nn.functional.linear(blk.norm1(y), blk.attn.qkv.weight).view(2, H, W, 3 * C)   # bias-free
             a = ops_ref.swin_window_attention(qkv, blk.attn.qkv.bias, blk.attn.relative_position_bias_table,
                                               nH, ws, 0 if i % 2 == 0 else ws // 2)
             y = y + blk.attn.proj(a.view(2, H * W, C))

@@ -78,9 +78,9 @@ __device__ __forceinline__ void store_maybe_split(float* __restrict__ out, size_
 
 template <int MAXV>  // float4 per lane; C <= MAXV*128
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, long long rows, int C, float eps, float* __restrict__ sum_out,
-                 float* __restrict__ out, int split) {
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ res_bias,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C, float eps,
+                 float* __restrict__ sum_out, float* __restrict__ out, int split) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -95,6 +95,10 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, con
       if (res != nullptr) {
         const float4 b = *reinterpret_cast<const float4*>(res + row * C + idx * 4);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        if (res_bias != nullptr) {   // bias of the GEMM that produced `res`, deferred into this kernel
+          const float4 rb = ldg_f4(res_bias + idx * 4);
+          a.x += rb.x; a.y += rb.y; a.z += rb.z; a.w += rb.w;
+        }
       }
       if (sum_out != nullptr) *reinterpret_cast<float4*>(sum_out + row * C + idx * 4) = a;
       v[i] = a;
@@ -130,13 +134,18 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, con
 }
 
 __global__ void __launch_bounds__(256)
-gelu_split_kernel(const float* __restrict__ x, long long rows, int C, float* __restrict__ out, int do_gelu, int split) {
+gelu_split_kernel(const float* __restrict__ x, const float* __restrict__ bias, long long rows, int C,
+                  float* __restrict__ out, int do_gelu, int split) {
   const int nv = C >> 2;
   const long long total = rows * nv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / nv;
     const int col = (int)(i - row * nv) * 4;
     float4 a = *reinterpret_cast<const float4*>(x + row * C + col);
+    if (bias != nullptr) {   // bias of the producing GEMM, deferred into this kernel
+      const float4 b = ldg_f4(bias + col);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
     if (do_gelu == 2) {
       a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
     } else if (do_gelu == 1) {
@@ -153,19 +162,20 @@ gelu_split_kernel(const float* __restrict__ x, long long rows, int C, float* __r
 
 using namespace univs;
 
-extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* residual, const float* gamma,
-                                   const float* beta, int64_t rows, int channels, float eps, float* sum_out, float* out,
-                                   int split) {
+extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* residual, const float* residual_bias,
+                                   const float* gamma, const float* beta, int64_t rows, int channels, float eps,
+                                   float* sum_out, float* out, int split) {
   UNIVS_REQUIRE(rows >= 0 && channels > 0, "layernorm: bad sizes");
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
+  UNIVS_REQUIRE(residual_bias == nullptr || residual != nullptr, "layernorm: residual_bias needs a residual");
   UNIVS_REQUIRE(channels % 4 == 0 && channels <= 4096, "layernorm: channels must be a multiple of 4 and <= 4096 (got %d)", channels);
   UNIVS_REQUIRE(split == 0 || split == -2 || (split != -1 && split != -3 && (split > 0 ? split : -split) % 4 == 0 &&
                                                channels % (split > 0 ? split : -split) == 0),
                 "layernorm: split chunk must divide channels");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_LAUNCH(MV) layernorm_kernel<MV><<<grid, 256, 0, st>>>(x, residual, gamma, beta, rows, channels, eps, sum_out, out, split)
+#define LN_LAUNCH(MV) layernorm_kernel<MV><<<grid, 256, 0, st>>>(x, residual, residual_bias, gamma, beta, rows, channels, eps, sum_out, out, split)
   if (channels <= 128) LN_LAUNCH(1);
   else if (channels <= 256) LN_LAUNCH(2);
   else if (channels <= 512) LN_LAUNCH(4);
@@ -176,23 +186,23 @@ extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* re
   return check_launch("layernorm");
 }
 
-extern "C" int univs_gelu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split) {
+extern "C" int univs_gelu_f32(void* stream, const float* x, const float* bias, int64_t rows, int channels, float* out, int split) {
   UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "gelu: bad sizes (channels %% 4 == 0)");
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && out, "gelu: null pointer");
   long long blocks = (rows * (channels / 4) + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, channels, out, 1, split);
+  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, bias, rows, channels, out, 1, split);
   return check_launch("gelu");
 }
 
-extern "C" int univs_relu_f32(void* stream, const float* x, int64_t rows, int channels, float* out, int split) {
+extern "C" int univs_relu_f32(void* stream, const float* x, const float* bias, int64_t rows, int channels, float* out, int split) {
   UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "relu: bad sizes (channels %% 4 == 0)");
   if (rows == 0) return UNIVS_OK;
   UNIVS_REQUIRE(x && out, "relu: null pointer");
   long long blocks = (rows * (channels / 4) + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, channels, out, 2, split);
+  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, bias, rows, channels, out, 2, split);
   return check_launch("relu");
 }
 
@@ -205,6 +215,6 @@ extern "C" int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, 
   UNIVS_REQUIRE(x && out, "split_tf32: null pointer");
   long long blocks = (rows * (channels / 4) + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, channels, out, 0, chunk);
+  gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, nullptr, rows, channels, out, 0, chunk);
   return check_launch("split_tf32");
 }

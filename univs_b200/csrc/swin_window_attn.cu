@@ -9,6 +9,7 @@
 // Reference semantics restated: swin.py:131-171 (attention), :108-121 (relative_position_index, computed
 // analytically here), :413-440 (shift mask = -100 between different regions of the PADDED, SHIFTED grid),
 // :247-255 (zero pad AFTER norm1 => qkv of a pad token == qkv bias; pad tokens are real keys).
+// The qkv input is the bias-free GEMM output; the kernel adds the bias while staging (one less pass over qkv).
 #include "common.cuh"
 
 namespace univs {
@@ -93,6 +94,9 @@ swin_window_attn_kernel(const float* __restrict__ qkv, const float* __restrict__
           q = ldg_f4(p);
           k = ldg_f4(p + C);
           v = ldg_f4(p + 2 * C);
+          q.x += bq.x; q.y += bq.y; q.z += bq.z; q.w += bq.w;   // qkv arrives without its bias
+          k.x += bk.x; k.y += bk.y; k.z += bk.z; k.w += bk.w;
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
         } else {
           q = bq; k = bk; v = bv;
         }

@@ -55,20 +55,21 @@ class _Block(nn.Module):
         self.norm2 = nn.LayerNorm(dim)
         self.mlp = _Mlp(dim, int(dim * mlp_ratio))
 
-    def forward(self, x, pending):
-        """x: residual stream [N,H,W,C]; pending: branch output still to be added to it (or None).  The residual add
-        is fused into the LayerNorm that follows it; LayerNorm / GELU outputs are emitted in the GEMM operand format
-        of the active policy (nn_ops)."""
+    def forward(self, x, pending, pending_bias=None):
+        """x: residual stream [N,H,W,C]; pending (+ pending_bias): branch output (and the deferred bias of the GEMM that
+        produced it) still to be added to the stream.  Residual adds and GEMM biases are folded into the fused kernels
+        that consume them (LayerNorm, GELU, window attention); LayerNorm / GELU outputs are emitted directly in the GEMM
+        operand format of the active policy (nn_ops)."""
         a = self.attn
-        x, h = nn_ops.layernorm(x, self.norm1, residual=pending, want_sum=True)
-        qkv = nn_ops.linear_prepped(h, a.qkv.weight, a.qkv.bias)
+        x, h = nn_ops.layernorm(x, self.norm1, residual=pending, want_sum=True, residual_bias=pending_bias)
+        qkv = nn_ops.linear_prepped(h, a.qkv.weight, None)                  # bias added inside the attention kernel
         bias = a.qkv.bias if a.qkv.bias is not None else x.new_zeros(qkv.shape[-1])
         y = ops.swin_window_attention(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift)
-        y = nn_ops.linear(y, a.proj.weight, a.proj.bias)
-        x, h = nn_ops.layernorm(x, self.norm2, residual=y, want_sum=True)
-        f = nn_ops.linear_prepped(h, self.mlp.fc1.weight, self.mlp.fc1.bias)
-        z = nn_ops.linear_prepped(nn_ops.gelu(f), self.mlp.fc2.weight, self.mlp.fc2.bias)
-        return x, z
+        y = nn_ops.linear(y, a.proj.weight, None)
+        x, h = nn_ops.layernorm(x, self.norm2, residual=y, want_sum=True, residual_bias=a.proj.bias)
+        f = nn_ops.linear_prepped(h, self.mlp.fc1.weight, None)
+        z = nn_ops.linear_prepped(nn_ops.gelu(f, bias=self.mlp.fc1.bias), self.mlp.fc2.weight, None)
+        return x, z, self.mlp.fc2.bias
 
 
 class _PatchMerging(nn.Module):
@@ -97,14 +98,14 @@ class _Stage(nn.Module):
 
     def forward(self, x, out_norm=None):
         """-> (norm_i(x_out) or None, x_out or downsample(x_out))"""
-        pending = None
+        pending = pbias = None
         for blk in self.blocks:
-            x, pending = blk(x, pending)
+            x, pending, pbias = blk(x, pending, pbias)
         y = None
         if out_norm is not None:
-            x, y = nn_ops.layernorm(x, out_norm, residual=pending, want_sum=True, for_gemm=False)
+            x, y = nn_ops.layernorm(x, out_norm, residual=pending, want_sum=True, for_gemm=False, residual_bias=pbias)
         else:
-            x = x + pending
+            x = x + pending + pbias
         return y, (self.downsample(x) if self.downsample is not None else x)
 
 

@@ -88,9 +88,9 @@ class _FFNLayer(nn.Module):               # transformer_layers.py:151-191 (post-
         nn.init.xavier_uniform_(self.linear2.weight)
 
     def forward(self, x):
-        f = nn_ops.linear(x, self.linear1.weight, self.linear1.bias)
-        z = nn_ops.linear_prepped(nn_ops.relu(f), self.linear2.weight, self.linear2.bias)
-        return nn_ops.layernorm(x, self.norm, residual=z, for_gemm=False)[1]
+        f = nn_ops.linear(x, self.linear1.weight, None)
+        z = nn_ops.linear_prepped(nn_ops.relu(f, bias=self.linear1.bias), self.linear2.weight, None)
+        return nn_ops.layernorm(x, self.norm, residual=z, for_gemm=False, residual_bias=self.linear2.bias)[1]
 
 
 class _MLP(nn.Module):                    # transformer_layers.py:205-217
@@ -102,9 +102,10 @@ class _MLP(nn.Module):                    # transformer_layers.py:205-217
     def forward(self, x, prepped=False):
         h = x if prepped else nn_ops.prep(x)
         for i, l in enumerate(self.layers):
-            y = nn_ops.linear_prepped(h, l.weight, l.bias)
-            if i < len(self.layers) - 1:
-                h = nn_ops.relu(y)
+            last = i == len(self.layers) - 1
+            y = nn_ops.linear_prepped(h, l.weight, l.bias if last else None)
+            if not last:
+                h = nn_ops.relu(y, bias=l.bias)
         return y
 
 
@@ -260,8 +261,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         wq, bq = mha.wq()
         q = nn_ops.linear(x + qpos, wq, bq)
         a = ops.mha_core(q, k, v, bits, row_open)
-        o = nn_ops.linear(a, mha.out_proj.weight, mha.out_proj.bias)
-        return nn_ops.layernorm(x, layer.norm, residual=o, for_gemm=False)[1]
+        o = nn_ops.linear(a, mha.out_proj.weight, None)
+        return nn_ops.layernorm(x, layer.norm, residual=o, for_gemm=False, residual_bias=mha.out_proj.bias)[1]
 
     def _self_attention(self, layer, x, qpos, bits):
         """x, qpos: [T,Q,C] -> tokens (q*T + t) (..._univs.py:408-416)"""
@@ -274,8 +275,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         wv, bv = mha.wv()
         v = nn_ops.linear(xs, wv, bv)
         a = ops.mha_core(qk[..., :C].contiguous(), qk[..., C:].contiguous(), v, bits, None)
-        o = nn_ops.linear(a, mha.out_proj.weight, mha.out_proj.bias)
-        y = nn_ops.layernorm(xs.contiguous(), layer.norm, residual=o, for_gemm=False)[1]
+        o = nn_ops.linear(a, mha.out_proj.weight, None)
+        y = nn_ops.layernorm(xs.contiguous(), layer.norm, residual=o, for_gemm=False, residual_bias=mha.out_proj.bias)[1]
         return y.view(Q, T, C).transpose(0, 1).contiguous()
 
     def _proca(self, i, x, qpos, mem, mem_pe):
@@ -300,8 +301,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         v_self = lin(tk, wv, bv)
         v_mem = lin(mm, wv, bv)
         a = ops.proca_core(q.contiguous(), k_self.contiguous(), v_self.contiguous(), k_mem.contiguous(), v_mem.contiguous())
-        o = nn_ops.linear(a, mha.out_proj.weight, mha.out_proj.bias)
-        y = nn_ops.layernorm(tok, layer.norm, residual=o, for_gemm=False)[1]   # [P,T,C]
+        o = nn_ops.linear(a, mha.out_proj.weight, None)
+        y = nn_ops.layernorm(tok, layer.norm, residual=o, for_gemm=False, residual_bias=mha.out_proj.bias)[1]   # [P,T,C]
         return torch.cat([x[:, :nq], y.transpose(0, 1)], 1)
 
     def _heads(self, x, feats_cl, hw, next_hw, task, targets, t, need_class, need_attn, out_buf=None):
@@ -348,8 +349,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         wq, bq = mha.wq(); wk, bk = mha.wk(); wv, bv = mha.wv()
         mm = nn_ops.prep(mem)
         a = ops.mha_core(nn_ops.linear(feats, wq, bq), nn_ops.linear_prepped(mm, wk, bk), nn_ops.linear_prepped(mm, wv, bv))
-        o = nn_ops.linear(a, mha.out_proj.weight, mha.out_proj.bias)
-        return nn_ops.layernorm(feats.contiguous(), layer.norm, residual=o, for_gemm=False)[1]
+        o = nn_ops.linear(a, mha.out_proj.weight, None)
+        return nn_ops.layernorm(feats.contiguous(), layer.norm, residual=o, for_gemm=False, residual_bias=mha.out_proj.bias)[1]
 
     def _prompt_encoder(self, src, pos, size_list, targets, t):
         """forward_prompt_encoder (:599-758), inference branches.

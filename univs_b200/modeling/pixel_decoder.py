@@ -75,11 +75,11 @@ class _EncoderLayer(nn.Module):
         w, b = a.fused_offs_logits()
         offs_logits = nn_ops.linear(src + pos, w, b)
         y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points)
-        o = nn_ops.linear(y, a.output_proj.weight, a.output_proj.bias)
-        src = nn_ops.layernorm(src, self.norm1, residual=o, for_gemm=False)[1]
-        f = nn_ops.linear(src, self.linear1.weight, self.linear1.bias)
-        z = nn_ops.linear_prepped(nn_ops.relu(f), self.linear2.weight, self.linear2.bias)
-        return nn_ops.layernorm(src, self.norm2, residual=z, for_gemm=False)[1]
+        o = nn_ops.linear(y, a.output_proj.weight, None)
+        src = nn_ops.layernorm(src, self.norm1, residual=o, for_gemm=False, residual_bias=a.output_proj.bias)[1]
+        f = nn_ops.linear(src, self.linear1.weight, None)
+        z = nn_ops.linear_prepped(nn_ops.relu(f, bias=self.linear1.bias), self.linear2.weight, None)
+        return nn_ops.layernorm(src, self.norm2, residual=z, for_gemm=False, residual_bias=self.linear2.bias)[1]
 
 
 class _Encoder(nn.Module):

@@ -78,6 +78,17 @@ def _split_weight(w: torch.Tensor, cache=True):
     return ent[1], ent[2]
 
 
+_zero_cache = {}
+
+
+def _zeros(n, device):
+    z = _zero_cache.get((n, device))
+    if z is None:
+        z = torch.zeros(n, device=device, dtype=torch.float32)
+        _zero_cache[(n, device)] = z
+    return z
+
+
 _inplace16 = [None]     # whether torch.addmm(..., out_dtype=f32, out=acc) accepts acc as both input and output
 
 
@@ -100,18 +111,20 @@ def prep(x):
     return ops.split_operand(x if x.is_contiguous() else x.contiguous(), _fmt()) if splitting() else x
 
 
-def layernorm(x, norm, residual=None, want_sum=False, for_gemm=True):
-    """(sum | None, LN(x + residual)); the LN output is split iff it feeds a GEMM under the tf32x3 policy."""
+def layernorm(x, norm, residual=None, want_sum=False, for_gemm=True, residual_bias=None):
+    """(sum | None, LN(x + residual + residual_bias)); the LN output is emitted in the GEMM operand format of the active
+    policy iff it feeds a GEMM.  `residual_bias` = the deferred bias of the GEMM that produced `residual`."""
     return ops.layernorm(x.contiguous(), norm.weight, norm.bias, norm.eps,
-                         None if residual is None else residual.contiguous(), want_sum, _fmt() if for_gemm else None)
+                         None if residual is None else residual.contiguous(), want_sum, _fmt() if for_gemm else None,
+                         residual_bias)
 
 
-def gelu(x, for_gemm=True):
-    return ops.gelu(x.contiguous(), _fmt() if for_gemm else None)
+def gelu(x, for_gemm=True, bias=None):
+    return ops.gelu(x.contiguous(), _fmt() if for_gemm else None, bias)
 
 
-def relu(x, for_gemm=True):
-    return ops.relu(x.contiguous(), _fmt() if for_gemm else None)
+def relu(x, for_gemm=True, bias=None):
+    return ops.relu(x.contiguous(), _fmt() if for_gemm else None, bias)
 
 
 def linear_prepped(h, weight, bias=None, cache=True):
@@ -135,12 +148,10 @@ def linear_prepped(h, weight, bias=None, cache=True):
         b3, alpha = wh, wlh
         kc3 = 3 * ops.f16_chunk(K)
         h3 = h.reshape(-1, 3 * K)
-        if bias is not None:
+        if bias is not None:                      # small GEMMs only: hot-path callers defer the bias into the consumer kernel
             y = torch.addmm(bias.float(), h3[:, :kc3], b3[:, :kc3].t(), alpha=alpha, out_dtype=f32)
-        else:
-            y = torch.mm(h3[:, :kc3], b3[:, :kc3].t(), out_dtype=f32)
-            if alpha != 1.0:
-                y.mul_(alpha)
+        else:                                     # beta = 0: `input` is ignored (no broadcast copy), alpha undoes the weight scale
+            y = torch.addmm(_zeros(N, h.device), h3[:, :kc3], b3[:, :kc3].t(), beta=0, alpha=alpha, out_dtype=f32)
         for k0 in range(kc3, 3 * K, kc3):
             y = _addmm16(y, h3[:, k0:k0 + kc3], b3[:, k0:k0 + kc3].t(), alpha)
     return y.view(*h.shape[:-1], N)

@@ -113,7 +113,7 @@ def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits
 
 
 def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shift, precision=None):
-    """qkv [B,H,W,3C] -> [B,H,W,C] (see include/univs_b200.h)"""
+    """qkv [B,H,W,3C] (bias-free GEMM output; the kernel adds qkv_bias) -> [B,H,W,C] (see include/univs_b200.h)"""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     out = torch.empty((B, H, W, C), device=qkv.device, dtype=torch.float32)
@@ -258,7 +258,7 @@ def _split_out(x, split):
     return torch.empty((*x.shape[:-1], mult * C), device=x.device, dtype=dt), code
 
 
-def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=None):
+def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=None, residual_bias=None):
     """Fused (residual add +) LayerNorm over the last dim.  Returns (sum_or_None, out); `out` is fp32 [..., C] or a
     split GEMM operand [..., 2C] (see _split_code)."""
     C = x.shape[-1]
@@ -267,6 +267,7 @@ def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=No
     s = torch.empty_like(x) if (want_sum and residual is not None) else None
     with _Bracket("layernorm", 1):
         rc = lib().univs_layernorm_f32(_stream(), _chk(x, "x"), None if residual is None else _chk(residual, "residual"),
+                                       None if residual_bias is None else _chk(residual_bias, "residual_bias"),
                                        _chk(weight, "weight"), _chk(bias, "bias"), rows, C, float(eps),
                                        None if s is None else s.data_ptr(), out.data_ptr(), code)
     check(rc, "layernorm")
@@ -275,20 +276,22 @@ def layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=No
     return s, out
 
 
-def gelu(x, split=None):
+def gelu(x, split=None, bias=None):
     C = x.shape[-1]
     out, code = _split_out(x, split)
     with _Bracket("gelu", 1):
-        rc = lib().univs_gelu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), code)
+        rc = lib().univs_gelu_f32(_stream(), _chk(x, "x"), None if bias is None else _chk(bias, "bias"),
+                                  x.numel() // C, C, out.data_ptr(), code)
     check(rc, "gelu")
     return out
 
 
-def relu(x, split=None):
+def relu(x, split=None, bias=None):
     C = x.shape[-1]
     out, code = _split_out(x, split)
     with _Bracket("relu", 1):
-        rc = lib().univs_relu_f32(_stream(), _chk(x, "x"), x.numel() // C, C, out.data_ptr(), code)
+        rc = lib().univs_relu_f32(_stream(), _chk(x, "x"), None if bias is None else _chk(bias, "bias"),
+                                  x.numel() // C, C, out.data_ptr(), code)
     check(rc, "relu")
     return out
 
