@@ -72,6 +72,12 @@ int univs_swin_window_attention_f32(void* stream, const float* qkv, const float*
 int univs_mask_einsum_f32(void* stream, const float* mask_embed, const float* mask_features_cl, int frames,
                           int queries, int channels, int pixels, float* out);
 
+/* fp32-equivalent variant on the tensor cores: operands are fp16 [hi | lo] pairs (univs_split_tf32_f32 with
+ * chunk = UNIVS_SPLIT_F16U): mask_embed16 [T,Q,2C], mask_features16 [T,HW,2C] (__half); three tcgen05.mma kind::f16 per
+ * k-step (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM).  Same bytes per element as the fp32 tensors.  C % 64 == 0. */
+int univs_mask_einsum_f16x3(void* stream, const void* mask_embed16, const void* mask_features16, int frames, int queries,
+                            int channels, int pixels, float* out);
+
 /* Same contraction with register operands (mma.sync): precision UNIVS_PREC_TF32 rounds operands to nearest TF32
  * in-kernel (bit-identical to the tcgen05 kernel on pre-rounded operands); UNIVS_PREC_TF32X3 uses the 3xTF32 split
  * (fp32-equivalent products) -- the strict-parity policy and the on-device cross-check of the tcgen05 kernel. */

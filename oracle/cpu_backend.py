@@ -29,7 +29,7 @@ def _msda_fwd(value, shapes, starts, loc, w):
     return ops_ref.ms_deform_attn(value, sh, st, loc, w)
 
 
-def _einsum(mask_embed, feats_cl, out=None, precision=None):
+def _einsum(mask_embed, feats_cl, out=None, mode=None):
     r = ops_ref.mask_einsum(mask_embed, feats_cl.transpose(1, 2))
     if out is not None:
         out.copy_(r)
@@ -103,7 +103,7 @@ _PATCH = {"layernorm": _layernorm,
           "split_operand": lambda x, split="tf32": _maybe_split(x, split),
           "swin_window_attention": _swin, "ms_deform_attn_encoder": _msda_enc, "ms_deform_attn_forward": _msda_fwd,
           "mask_einsum": _einsum, "attn_mask_bits": _bits, "mha_core": _mha, "proca_core": _proca,
-          "round_tf32": lambda x, out=None: x, "prepare_mask_features": lambda x: x}
+          "round_tf32": lambda x, out=None: x, "prepare_mask_features": lambda x, mode=None: x}
 
 
 @contextlib.contextmanager

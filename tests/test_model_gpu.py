@@ -80,7 +80,7 @@ def test_no_cpu_fallback_and_library_loaded():
     with pytest.raises(_cabi.UnivsB200Error):
         ops.mha_core(torch.zeros(1, 4, 256), torch.zeros(1, 4, 256), torch.zeros(1, 4, 256))
     before = ops.launch_count
-    ops.mask_einsum(torch.zeros(1, 4, 32, device="cuda"), torch.zeros(1, 8, 32, device="cuda"), precision=ops.PREC_TF32X3)
+    ops.mask_einsum(torch.zeros(1, 4, 32, device="cuda"), torch.zeros(1, 8, 32, device="cuda"), mode="mma3x")
     assert ops.launch_count == before + 1
 
 

@@ -103,42 +103,45 @@ def test_mask_einsum(ops, T, Q, C, HW):
     E = torch.randn(T, Q, C)
     F = torch.randn(T, HW, C)
     want = ops_ref.mask_einsum(E.double(), F.transpose(1, 2).double()).float()
-    # TF32 policy: tcgen05 kernel on round-to-nearest operands (2^-12 relative each), fp32 accumulation in TMEM
-    Fr = ops.round_tf32(F.cuda())
-    got = ops.mask_einsum(E.cuda(), Fr, precision=ops.PREC_TF32)
+    # 1-pass TF32 on the tcgen05 tensor cores: round-to-nearest operands (2^-12 relative each), fp32 accumulation in TMEM
+    Fr = ops.prepare_mask_features(F.cuda(), "tf32")
+    got = ops.mask_einsum(E.cuda(), Fr, mode="tf32")
     assert got.shape == (Q, T, HW)
     assert _rel(got, want) < 4e-4
     # the register-operand kernel on the same rounded operands must agree with the tensor-memory kernel
     chk = ops.mask_einsum_mma(ops.round_tf32(E.cuda()), Fr, ops.PREC_TF32)
     assert _rel(got, chk) < 2e-6
-    # strict policy: 3xTF32 split, fp32-equivalent
-    strict = ops.mask_einsum(E.cuda(), F.cuda(), precision=ops.PREC_TF32X3)
+    # strict: 3xTF32 register kernel, and (C % 64 == 0) the fp16x3 tcgen05 kernel -- both fp32-equivalent
+    strict = ops.mask_einsum(E.cuda(), F.cuda(), mode="mma3x")
     assert _rel(strict, want) < 5e-6
+    if C % 64 == 0:
+        f16 = ops.mask_einsum(E.cuda(), ops.prepare_mask_features(F.cuda(), "f16x3"), mode="f16x3")
+        assert _rel(f16, want) < 5e-6
 
 
 def test_mask_einsum_empty(ops):
-    out = ops.mask_einsum(torch.zeros(0, 4, 32, device="cuda"), torch.zeros(0, 8, 32, device="cuda"))
+    out = ops.mask_einsum(torch.zeros(0, 4, 32, device="cuda"), torch.zeros(0, 8, 32, device="cuda"), mode="mma3x")
     assert out.shape == (4, 0, 8)
 
 
 def test_mask_einsum_linearity_full_size(ops):
-    """Size-independent properties at the north-star size (T=5,Q=200,C=256,184x320): linearity in E up to TF32
-    rounding, and a checksum of checksums against an fp64 reduction on the device."""
+    """Size-independent properties at the north-star size (T=5,Q=200,C=256,184x320): linearity in E, a checksum of
+    checksums against an fp64 reduction on the device, and agreement of the kernels with each other."""
     torch.manual_seed(12)
     T, Q, C, HW = 5, 200, 256, 184 * 320
-    F = ops.round_tf32(torch.randn(T, HW, C, device="cuda"))
+    Fraw = torch.randn(T, HW, C, device="cuda")
     E1 = torch.randn(T, Q, C, device="cuda")
     E2 = torch.randn(T, Q, C, device="cuda")
-    P = ops.PREC_TF32
-    o1, o2, o12 = ops.mask_einsum(E1, F, precision=P), ops.mask_einsum(E2, F, precision=P), ops.mask_einsum(E1 + E2, F, precision=P)
-    assert _rel(o12, o1 + o2) < 1e-3
-    colsum = F.double().sum(1)                                  # [T,C]
-    want = torch.einsum("tqc,tc->qt", E1.double(), colsum)
-    got = o1.double().sum(-1)
-    assert (got - want).abs().max().item() / want.abs().max().item() < 1e-3
-    # the two kernels agree at full size too
-    chk = ops.mask_einsum_mma(ops.round_tf32(E1), F, P)
-    assert _rel(o1, chk) < 2e-6
+    for mode, tol in (("f16x3", 2e-5), ("tf32", 1e-3)):
+        F = ops.prepare_mask_features(Fraw, mode)
+        o1, o2, o12 = ops.mask_einsum(E1, F, mode=mode), ops.mask_einsum(E2, F, mode=mode), ops.mask_einsum(E1 + E2, F, mode=mode)
+        assert _rel(o12, o1 + o2) < tol
+        colsum = Fraw.double().sum(1)                               # [T,C]
+        want = torch.einsum("tqc,tc->qt", E1.double(), colsum)
+        got = o1.double().sum(-1)
+        assert (got - want).abs().max().item() / want.abs().max().item() < tol
+    strict = ops.mask_einsum(E1, Fraw, mode="mma3x")
+    assert _rel(ops.mask_einsum(E1, ops.prepare_mask_features(Fraw, "f16x3"), mode="f16x3"), strict) < 5e-6
 
 
 @pytest.mark.parametrize("Q,T,H,W,tgt", [(5, 2, 16, 24, (8, 12)), (5, 2, 16, 24, (4, 6)), (7, 3, 16, 24, (2, 3)),

@@ -9,7 +9,7 @@ ok = True
 for (T, Q, C, HW) in [(1, 16, 32, 128), (1, 20, 256, 4096), (2, 100, 256, 1620), (3, 200, 256, 3680), (1, 232, 256, 130), (2, 7, 64, 66), (5, 200, 256, 58880)]:
     E = ops.round_tf32(torch.randn(T, Q, C, device="cuda"))
     F = ops.round_tf32(torch.randn(T, HW, C, device="cuda"))
-    got = ops.mask_einsum(E, F, precision=ops.PREC_TF32)
+    got = ops.mask_einsum(E, F, mode="tf32")
     torch.cuda.synchronize()
     ref = ops.mask_einsum_mma(E, F, ops.PREC_TF32)
     want = torch.einsum("tqc,tpc->qtp", E.double(), F.double()) if HW < 10000 else None
@@ -22,7 +22,8 @@ T, Q, C, HW = 5, 200, 256, 58880
 E = ops.round_tf32(torch.randn(T, Q, C, device="cuda")); F = ops.round_tf32(torch.randn(T, HW, C, device="cuda"))
 out = torch.empty(Q, T, HW, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for name, fn in (("tc", lambda e, f, out: ops.mask_einsum(e, f, out=out, precision=ops.PREC_TF32)), ("mma", lambda e, f, out: ops.mask_einsum_mma(e, f, ops.PREC_TF32, out=out)), ("mma3x", lambda e, f, out: ops.mask_einsum_mma(e, f, ops.PREC_TF32X3, out=out))):
+F16 = ops.prepare_mask_features(F, "f16x3")
+for name, fn in (("tc_tf32", lambda e, f, out: ops.mask_einsum(e, f, out=out, mode="tf32")), ("tc_f16x3", lambda e, f, out: ops.mask_einsum(e, F16, out=out, mode="f16x3")), ("mma", lambda e, f, out: ops.mask_einsum_mma(e, f, ops.PREC_TF32, out=out)), ("mma3x", lambda e, f, out: ops.mask_einsum_mma(e, f, ops.PREC_TF32X3, out=out))):
     for _ in range(3): fn(E, F, out=out)
     ts = []
     for _ in range(10):

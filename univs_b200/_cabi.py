@@ -18,6 +18,7 @@ SIGNATURES = {
     "univs_ms_deform_attn_encoder_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "univs_swin_window_attention_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "univs_mask_einsum_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "univs_mask_einsum_f16x3": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "univs_mask_einsum_mma_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "univs_attn_mask_bits_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "univs_mha_workspace_bytes": (_i64, [_i, _i, _i, _i]),

@@ -129,6 +129,7 @@ mask_einsum_kernel(const float* __restrict__ E, const float* __restrict__ F, int
 
 namespace univs {
 int launch_mask_einsum_tc(cudaStream_t st, const float* E, const float* F, int T, int Q, int C, int HW, float* out);
+int launch_mask_einsum_tc_f16(cudaStream_t st, const void* E16, const void* F16, int T, int Q, int C, int HW, float* out);
 }
 using namespace univs;
 
@@ -149,6 +150,17 @@ extern "C" int univs_mask_einsum_f32(void* stream, const float* mask_embed, cons
   UNIVS_REQUIRE(((uintptr_t)mask_embed & 15) == 0 && ((uintptr_t)mask_features_cl & 15) == 0,
                 "mask_einsum: operands must be 16-byte aligned (TMA)");
   return launch_mask_einsum_tc((cudaStream_t)stream, mask_embed, mask_features_cl, frames, queries, channels, pixels, out);
+}
+
+extern "C" int univs_mask_einsum_f16x3(void* stream, const void* mask_embed16, const void* mask_features16, int frames,
+                                       int queries, int channels, int pixels, float* out) {
+  int rc = check_einsum_args("mask_einsum_f16x3", (const float*)mask_embed16, (const float*)mask_features16, out, frames,
+                             queries, channels, pixels);
+  if (rc) return rc < 0 ? rc : UNIVS_OK;
+  UNIVS_REQUIRE(channels % 64 == 0, "mask_einsum_f16x3: channels must be a multiple of 64");
+  UNIVS_REQUIRE(((uintptr_t)mask_embed16 & 15) == 0 && ((uintptr_t)mask_features16 & 15) == 0,
+                "mask_einsum_f16x3: operands must be 16-byte aligned (TMA)");
+  return launch_mask_einsum_tc_f16((cudaStream_t)stream, mask_embed16, mask_features16, frames, queries, channels, pixels, out);
 }
 
 extern "C" int univs_mask_einsum_mma_f32(void* stream, const float* mask_embed, const float* mask_features_cl,

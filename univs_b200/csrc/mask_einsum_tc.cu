@@ -26,7 +26,8 @@ namespace univs {
 
 constexpr int kTcTileM = 128;
 constexpr int kTcChunk = 32;  // fp32 channels per stage = 128 bytes = one SWIZZLE_128B row
-constexpr int kTcStages = 4;
+constexpr int kTcStagesTf32 = 4;
+constexpr int kTcStagesF16 = 2;
 constexpr int kTcThreads = 256;
 constexpr int kTcMaxN = 256;
 constexpr int kTcABytes = kTcTileM * 128;  // 16 KB
@@ -67,6 +68,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
@@ -104,11 +115,19 @@ __device__ __forceinline__ bool elect_one() {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                      \
       : "r"(taddr))
 
+// F16X3 == false: fp32 operands consumed as TF32 (one MMA per k-step, K-chunk = 32 floats).
+// F16X3 == true : fp16 operands [hi | lo] (lo unscaled), three MMAs per k-step  lo*hi + hi*lo + hi*hi  (fp32-equivalent
+//                 products, correction terms first), K-chunk = 64 halfs; `C` is the logical channel count, the tensors
+//                 are [.., 2C] wide with hi at columns [0,C) and lo at [C,2C).
+template <bool F16X3>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_e, int T, int Q,
                       int C, int HW, int npad, float* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int stage_bytes = kTcABytes + npad * 128;  // multiple of 1024 (npad % 16 == 0 -> npad*128 % 2048 == 0)
+  constexpr int kTcStages = F16X3 ? kTcStagesF16 : kTcStagesTf32;
+  constexpr int kChunkElems = F16X3 ? 64 : 32;      // 128-byte operand rows
+  const int b_bytes = npad * 128;                   // multiple of 2048 (npad % 16 == 0)
+  const int stage_bytes = (F16X3 ? 2 : 1) * (kTcABytes + b_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kTcStages * stage_bytes);
   uint64_t* full = bars;                   // [kTcStages]
   uint64_t* empty = bars + kTcStages;      // [kTcStages]
@@ -119,7 +138,7 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_frame = (HW + kTcTileM - 1) / kTcTileM;
   const int num_tiles = T * tiles_per_frame;
-  const int kchunks = C / kTcChunk;
+  const int kchunks = C / kChunkElems;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kTcStages; ++i) {
@@ -152,8 +171,12 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sA = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-          tma_load_3d(sA, &map_f, &full[stage], kc * kTcChunk, p0, t);
-          tma_load_3d(sA + kTcABytes, &map_e, &full[stage], kc * kTcChunk, 0, t);
+          tma_load_3d(sA, &map_f, &full[stage], kc * kChunkElems, p0, t);
+          tma_load_3d(sA + kTcABytes, &map_e, &full[stage], kc * kChunkElems, 0, t);
+          if (F16X3) {   // lo halves live C columns further right
+            tma_load_3d(sA + kTcABytes + b_bytes, &map_f, &full[stage], C + kc * kChunkElems, p0, t);
+            tma_load_3d(sA + 2 * kTcABytes + b_bytes, &map_e, &full[stage], C + kc * kChunkElems, 0, t);
+          }
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -161,7 +184,9 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2 at bits 7-9 / 10-12), K-major both, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kTcTileM >> 4) << 24);
+    // (kind::f16: A=B=f16 -> format code 0)
+    const uint32_t fmt = F16X3 ? 0u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kTcTileM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -178,9 +203,17 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
           const uint64_t adesc = make_sw128_desc(a_addr);
           const uint64_t bdesc = make_sw128_desc(a_addr + kTcABytes);
 #pragma unroll
-          for (int k = 0; k < kTcChunk / 8; ++k) {
-            // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // one k-step = 32 bytes (8 tf32 / 16 f16) inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            if (F16X3) {
+              const uint64_t adesc_lo = make_sw128_desc(a_addr + kTcABytes + b_bytes);
+              const uint64_t bdesc_lo = make_sw128_desc(a_addr + 2 * kTcABytes + b_bytes);
+              umma_f16(tmem_d, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);  // Fl*Eh
+              umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, 1u);                        // Fh*El
+              umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);                           // Fh*Eh
+            } else {
+              umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);                       // frees the smem stage when these MMAs retire
           if (kc == kchunks - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
@@ -246,41 +279,53 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 3-D fp32 tensor [d2][d1][d0 = C] (d0 contiguous), box [32][box_rows][1], SWIZZLE_128B
-static int make_map(CUtensorMap* m, const float* base, int d0, int d1, int d2, int box_rows) {
+// 3-D tensor [d2][d1][d0] (d0 contiguous) of fp32 (esize 4) or fp16 (esize 2), box [128 bytes][box_rows][1], SWIZZLE_128B
+static int make_map(CUtensorMap* m, const void* base, int d0, int d1, int d2, int box_rows, int esize) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("mask_einsum_tc: cuTensorMapEncodeTiled entry point unavailable"); return UNIVS_E_LAUNCH; }
   cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
-  cuuint64_t strides[2] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * (cuuint64_t)d1 * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kTcChunk, (cuuint32_t)box_rows, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)d0 * esize, (cuuint64_t)d0 * (cuuint64_t)d1 * esize};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("mask_einsum_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return UNIVS_E_LAUNCH; }
   return 0;
 }
 
-int launch_mask_einsum_tc(cudaStream_t st, const float* E, const float* F, int T, int Q, int C, int HW, float* out) {
+template <bool F16X3>
+static int launch_tc(cudaStream_t st, const void* E, const void* F, int T, int Q, int C, int HW, float* out) {
   const int npad = (Q + 15) & ~15;
+  const int esize = F16X3 ? 2 : 4;
+  const int width = F16X3 ? 2 * C : C;      // fp16 operands carry [hi | lo]
   CUtensorMap map_f, map_e;
-  int rc = make_map(&map_f, F, C, HW, T, kTcTileM);
+  int rc = make_map(&map_f, F, width, HW, T, kTcTileM, esize);
   if (rc) return rc;
-  rc = make_map(&map_e, E, C, Q, T, npad);
+  rc = make_map(&map_e, E, width, Q, T, npad, esize);
   if (rc) return rc;
-  const size_t smem = (size_t)kTcStages * (kTcABytes + npad * 128) + 256;
+  const int stages = F16X3 ? kTcStagesF16 : kTcStagesTf32;
+  const size_t smem = (size_t)stages * (F16X3 ? 2 : 1) * (kTcABytes + npad * 128) + 256;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  cudaError_t e = cudaFuncSetAttribute(mask_einsum_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(mask_einsum_tc_kernel<F16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("mask_einsum_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); return UNIVS_E_LAUNCH; }
   const int tiles = T * ((HW + kTcTileM - 1) / kTcTileM);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  mask_einsum_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_f, map_e, T, Q, C, HW, npad, out);
+  mask_einsum_tc_kernel<F16X3><<<grid, kTcThreads, smem, st>>>(map_f, map_e, T, Q, C, HW, npad, out);
   return check_launch("mask_einsum_tc");
+}
+
+int launch_mask_einsum_tc(cudaStream_t st, const float* E, const float* F, int T, int Q, int C, int HW, float* out) {
+  return launch_tc<false>(st, E, F, T, Q, C, HW, out);
+}
+int launch_mask_einsum_tc_f16(cudaStream_t st, const void* E16, const void* F16, int T, int Q, int C, int HW, float* out) {
+  return launch_tc<true>(st, E16, F16, T, Q, C, HW, out);
 }
 
 }  // namespace univs

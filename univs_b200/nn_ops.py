@@ -55,7 +55,7 @@ def _split_weight(w: torch.Tensor, cache=True):
     tf32x3: (Wh [N,K], Wlh [N,2K] = [Wl | Wh]).
     fp16x3: (B3 [N,3K] fp16 in K-chunks [Wh*2^-11 | Wl*2^11 | Wh] of W*2^s, alpha = 2^-s); s is a per-tensor power of
             two that lifts the weights into fp16's normal range."""
-    key = id(w)
+    key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()))        # views of packed parameters (in_proj slices) hit too
     sig = (w.data_ptr(), w._version, tuple(w.shape), _policy)
     ent = _wcache.get(key) if cache else None
     if ent is None or ent[0] != sig:
@@ -175,7 +175,7 @@ def conv2d_cl(x_cl, weight, bias=None, padding=0):
         return y.permute(0, 2, 3, 1)
     Cout, _, kh, kw = weight.shape
     assert kh == kw and padding == kh // 2, "only 'same' square convolutions are used on this path"
-    key = ("conv", id(weight))
+    key = ("conv", weight.data_ptr(), tuple(weight.shape))
     sig = (weight.data_ptr(), weight._version)
     ent = _wcache.get(key)
     if ent is None or ent[0] != sig:

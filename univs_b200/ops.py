@@ -48,6 +48,15 @@ class _Bracket:
         return False
 
 
+_einsum_mode = "mma3x"     # "f16x3" (tcgen05, fp16 hi|lo operands) | "tf32" (tcgen05, 1-pass) | "mma3x" (register 3xTF32)
+
+
+def set_einsum_mode(m: str):
+    global _einsum_mode
+    assert m in ("f16x3", "tf32", "mma3x")
+    _einsum_mode = m
+
+
 def set_attention_precision(p: int):
     global _default_precision
     assert p in (PREC_TF32X3, PREC_TF32)
@@ -126,32 +135,40 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     return out
 
 
-def prepare_mask_features(mask_features_cl):
-    """Once per clip: the operand layout/rounding the mask einsum of the active precision policy consumes.
-    TF32 policy: round-to-nearest TF32 copy (the tcgen05 kernel truncates, so pre-rounded operands make it
-    round-to-nearest overall).  TF32X3 policy: the tensor itself."""
-    if _default_precision == PREC_TF32:
+def prepare_mask_features(mask_features_cl, mode=None):
+    """Once per clip: mask features in the operand format the mask einsum of the active policy consumes.
+    "f16x3": fp16 [T,HW,2C] = [hi | lo] (same bytes as fp32);  "tf32": round-to-nearest TF32 copy (the tcgen05 kernel
+    truncates, pre-rounding makes it round-to-nearest overall);  "mma3x": the tensor itself."""
+    mode = _einsum_mode if mode is None else mode
+    if mode == "f16x3":
+        return split_operand(mask_features_cl, "f16u")
+    if mode == "tf32":
         return round_tf32(mask_features_cl)
     return mask_features_cl
 
 
-def mask_einsum(mask_embed, mask_features_cl, out=None, precision=None):
-    """mask_embed [T,Q,C], mask_features_cl [T,HW,C] (channel-last, from prepare_mask_features) -> [Q,T,HW].
-    TF32 policy -> tcgen05 kernel (mask_embed is rounded to nearest here); TF32X3 -> 3xTF32 register kernel."""
+def mask_einsum(mask_embed, mask_features_prepared, out=None, mode=None):
+    """mask_embed [T,Q,C] fp32, mask_features_prepared from prepare_mask_features (channel-last) -> [Q,T,HW] fp32."""
+    mode = _einsum_mode if mode is None else mode
     T, Q, Cc = mask_embed.shape
-    HW = mask_features_cl.shape[1]
-    prec = _default_precision if precision is None else precision
+    HW = mask_features_prepared.shape[1]
     if out is None:
         out = torch.empty((Q, T, HW), device=mask_embed.device, dtype=torch.float32)
-    if prec == PREC_TF32:
+    if mode == "f16x3":
+        e = split_operand(mask_embed if mask_embed.is_contiguous() else mask_embed.contiguous(), "f16u")
+        with _Bracket("mask_einsum", 1):
+            rc = lib().univs_mask_einsum_f16x3(_stream(), _chk(e, "mask_embed", torch.float16),
+                                               _chk(mask_features_prepared, "mask_features", torch.float16),
+                                               T, Q, Cc, HW, _chk(out, "out"))
+    elif mode == "tf32":
         e = round_tf32(mask_embed)
         with _Bracket("mask_einsum", 1):
-            rc = lib().univs_mask_einsum_f32(_stream(), _chk(e, "mask_embed"), _chk(mask_features_cl, "mask_features"),
+            rc = lib().univs_mask_einsum_f32(_stream(), _chk(e, "mask_embed"), _chk(mask_features_prepared, "mask_features"),
                                              T, Q, Cc, HW, _chk(out, "out"))
     else:
         with _Bracket("mask_einsum", 1):
             rc = lib().univs_mask_einsum_mma_f32(_stream(), _chk(mask_embed, "mask_embed"),
-                                                 _chk(mask_features_cl, "mask_features"), T, Q, Cc, HW, prec,
+                                                 _chk(mask_features_prepared, "mask_features"), T, Q, Cc, HW, PREC_TF32X3,
                                                  _chk(out, "out"))
     check(rc, "mask_einsum")
     return out

@@ -27,14 +27,17 @@ def set_precision(mode: str):
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
         ops.set_attention_precision(ops.PREC_TF32X3)
+        ops.set_einsum_mode("mma3x")
     elif mode == "tf32":
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
         ops.set_attention_precision(ops.PREC_TF32)
+        ops.set_einsum_mode("tf32")
     elif mode in ("tf32x3", "fp16x3"):
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
         ops.set_attention_precision(ops.PREC_TF32X3)
+        ops.set_einsum_mode("f16x3" if mode == "fp16x3" else "mma3x")
     else:
         raise ValueError(f"unknown precision mode {mode!r} (fp16x3 | tf32x3 | tf32 | fp32)")
     nn_ops.set_policy(mode)
