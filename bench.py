@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ns", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("UNIVS_PRECISION", "tf32x3"), choices=["fp16x3", "tf32x3", "fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("UNIVS_PRECISION", "fp16x3"), choices=["fp16x3", "tf32x3", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the clip eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ncu-step", action="store_true",
@@ -197,11 +197,21 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     graphed = None
     if use_graph:
         from univs_b200.runtime import GraphedClip
-        graphed = GraphedClip(model, frames_dev, lambda: make_targets(T, dev))
+        try:
+            graphed = GraphedClip(model, frames_dev, lambda: make_targets(T, dev))
+            ok = torch.ones(1, device=dev)
+        except Exception as e:  # noqa: BLE001  (e.g. a collective that refuses stream capture)
+            sys.stderr.write(f"[bench] CUDA-graph capture failed on rank {rank}: {e}\n")
+            graphed, ok = None, torch.zeros(1, device=dev)
+        if world > 1:                                   # all ranks must take the same path
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            graphed, use_graph = None, False
+    if graphed is not None:
         step_resident = lambda: graphed(frames_dev)
     else:
         step_resident = step_eager
