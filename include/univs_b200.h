@@ -59,10 +59,17 @@ int univs_ms_deform_attn_encoder_f32(void* stream, const float* value, const int
  * qkv [B,H,W,3C] f32 = LN(x) * Wqkv^T on the unpadded token grid WITHOUT the bias; qkv_bias [3C] is added by the kernel
  * to every token (and is the whole value of a pad token: zero-padded after norm1, swin.py:247-255);
  * rel_bias_table [(2*window-1)^2, num_heads]; head_dim = C/num_heads must be 32; window in {7,12} (or any <=12);
- * shift = 0 or window/2.  out [B,H,W,C] f32 (pre output projection). */
+ * shift = 0 or window/2.  out [B,H,W,C] f32 (pre output projection).  precision UNIVS_PREC_TF32X3 runs the fp16 hi|lo
+ * split kernel (m16n8k16, fp32-equivalent products), UNIVS_PREC_TF32 the single-pass TF32 kernel. */
 int univs_swin_window_attention_f32(void* stream, const float* qkv, const float* qkv_bias,
                                     const float* rel_bias_table, int batch, int height, int width, int channels,
                                     int num_heads, int window, int shift, int precision, float* out);
+
+/* Same operator (strict precision), writing its result directly as the A operand of the fp16x3 projection GEMM:
+ * out16 = __half [B,H,W,3C] = [lo*2^11 | hi*2^-11 | hi] (channels <= 1536). */
+int univs_swin_window_attention_f16x3out(void* stream, const float* qkv, const float* qkv_bias,
+                                         const float* rel_bias_table, int batch, int height, int width, int channels,
+                                         int num_heads, int window, int shift, void* out16);
 
 /* ---- Mask einsum "btqc,btchw->btqhw" + transpose(1,2) (a11), on the tcgen05 tensor cores
  * (TMA -> smem -> tcgen05.mma kind::tf32 -> TMEM -> tcgen05.ld -> coalesced stores).

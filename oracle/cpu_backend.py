@@ -97,6 +97,7 @@ def _layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=N
 
 
 _PATCH = {"layernorm": _layernorm,
+          "swin_window_attention_operand": lambda q, b, t, nh, ws, sh: _split16(_swin(q, b, t, nh, ws, sh), True),
           "gelu": lambda x, split=None, bias=None: _maybe_split(torch.nn.functional.gelu(x if bias is None else x + bias), split),
           "relu": lambda x, split=None, bias=None: _maybe_split(torch.relu(x if bias is None else x + bias), split),
           "split_tf32": _split,

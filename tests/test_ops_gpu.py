@@ -93,6 +93,11 @@ def test_swin_window_attention(ops, B, H, W, nH, ws, shift, prec, tol):
     want = ops_ref.swin_window_attention(qkv, bias, table, nH, ws, shift)
     got = ops.swin_window_attention(qkv.cuda(), bias.cuda(), table.cuda(), nH, ws, shift, precision=prec)
     assert _rel(got, want) < tol
+    if prec == 0:      # strict kernel can emit the fp16x3 GEMM operand [lo*2^11 | hi*2^-11 | hi] directly
+        op = ops.swin_window_attention_operand(qkv.cuda(), bias.cuda(), table.cuda(), nH, ws, shift).float()
+        rec = op[..., 2 * C:] + op[..., :C] * 2.0 ** -11
+        assert _rel(rec, want) < tol
+        assert torch.equal(op[..., 2 * C:].half(), got.half())
 
 
 # ------------------------------------------------------------------ mask einsum + attention-mask bits

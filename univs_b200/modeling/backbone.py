@@ -64,8 +64,13 @@ class _Block(nn.Module):
         x, h = nn_ops.layernorm(x, self.norm1, residual=pending, want_sum=True, residual_bias=pending_bias)
         qkv = nn_ops.linear_prepped(h, a.qkv.weight, None)                  # bias added inside the attention kernel
         bias = a.qkv.bias if a.qkv.bias is not None else x.new_zeros(qkv.shape[-1])
-        y = ops.swin_window_attention(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift)
-        y = nn_ops.linear(y, a.proj.weight, None)
+        if nn_ops.policy() == "fp16x3" and qkv.shape[-1] <= 3 * 1536:     # attention writes the GEMM operand itself
+            ys = ops.swin_window_attention_operand(qkv, bias, a.relative_position_bias_table, self.heads, self.window,
+                                                   self.shift)
+            y = nn_ops.linear_prepped(ys, a.proj.weight, None)
+        else:
+            y = ops.swin_window_attention(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift)
+            y = nn_ops.linear(y, a.proj.weight, None)
         x, h = nn_ops.layernorm(x, self.norm2, residual=y, want_sum=True, residual_bias=a.proj.bias)
         f = nn_ops.linear_prepped(h, self.mlp.fc1.weight, None)
         z = nn_ops.linear_prepped(nn_ops.gelu(f, bias=self.mlp.fc1.bias), self.mlp.fc2.weight, None)

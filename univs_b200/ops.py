@@ -135,6 +135,20 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     return out
 
 
+def swin_window_attention_operand(qkv, qkv_bias, rel_bias_table, num_heads, window, shift):
+    """Strict-precision window attention emitting the fp16x3 GEMM operand directly: fp16 [B,H,W,3C] =
+    [lo*2^11 | hi*2^-11 | hi] (the A operand of the projection GEMM; C <= 1536)."""
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    out = torch.empty((B, H, W, 3 * C), device=qkv.device, dtype=torch.float16)
+    with _Bracket("swin_window_attention", 1):
+        rc = lib().univs_swin_window_attention_f16x3out(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
+                                                        _chk(rel_bias_table, "rel_bias_table"), B, H, W, C, num_heads,
+                                                        window, shift, out.data_ptr())
+    check(rc, "swin_window_attention_f16x3out")
+    return out
+
+
 def prepare_mask_features(mask_features_cl, mode=None):
     """Once per clip: mask features in the operand format the mask einsum of the active policy consumes.
     "f16x3": fp16 [T,HW,2C] = [hi | lo] (same bytes as fp32);  "tf32": round-to-nearest TF32 copy (the tcgen05 kernel
