@@ -100,3 +100,53 @@ def test_tf32_policy_runs_and_is_close_on_features():
     assert _rel(gf["res5"], wf["res5"]) < 3e-3
     assert _rel(gmf, wmf) < 3e-3
     assert torch.isfinite(gout["pred_masks"]).all()
+
+
+def test_sot_visual_prompts_two_clips_cuda():
+    """task=sot on the GPU: visual-prompt sampler + memory pool + ProCA (T-invariant memory) over two stride-1 clips,
+    against the same host logic with CPU oracle operators (identical RNG seed / call order)."""
+    from tests.test_host_model_vs_reference import _rect_masks
+    from univs_b200.precision import set_precision
+    T, Q, P, H, W = 3, 10, 3, 96, 160
+    swin = dict(embed_dim=64, depths=[2, 2, 2, 2], num_heads=[2, 4, 8, 16], window_size=7)
+    clip = mf.make_clip_emb()
+    kw = dict(enc_layers=2, dec_layers=3, num_dense_points=16, num_prev_frames_memory=4)
+    cpu = mf.build_product_model(swin, num_queries=Q, num_frames=T, clip_emb=clip, **kw)
+    mf.load_keyed(cpu)
+    gpu = mf.build_product_model(swin, num_queries=Q, num_frames=T, clip_emb=clip, **kw)
+    mf.load_keyed(gpu)
+    gpu = tuple(m.cuda() for m in gpu)
+    g = torch.Generator().manual_seed(11)
+    frames = torch.randn(T + 1, 3, H, W, generator=g)
+    masks, boxes = _rect_masks(P, T + 1, H, W, 5)
+    masks[2, 0] = 0
+
+    def targets(dev):
+        return [{"task": "sot", "dataset_name": "davis", "prompt_type": "visual", "ids": torch.arange(P, device=dev),
+                 "first_appear_frame_idxs": torch.tensor([0, 0, 1], device=dev)}]
+
+    def clip_inputs(tg, c, dev):
+        tg[0]["first_frame_idx"] = c
+        tg[0]["frame_indices"] = torch.arange(c, c + T, device=dev)
+        tg[0]["masks"] = masks[:, : c + T].clone().to(dev)
+        tg[0]["boxes"] = boxes[:, : c + T].clone().to(dev)
+        return frames[c: c + T].to(dev)
+
+    ctg, gtg = targets("cpu"), targets("cuda")
+    set_precision("fp16x3")
+    try:
+        for c in range(2):
+            x = clip_inputs(ctg, c, "cpu")
+            torch.manual_seed(100 + c)
+            with oracle_ops():
+                _, _, wout = mf.product_clip_forward(*cpu, x, ctg)
+            x = clip_inputs(gtg, c, "cuda")
+            torch.manual_seed(100 + c)
+            _, _, gout = mf.product_clip_forward(*gpu, x, gtg)
+            assert gout["pred_masks"].shape == wout["pred_masks"].shape == (1, Q + P, T, H // 4, W // 4)
+            assert _rel(gout["pred_masks"], wout["pred_masks"]) < 1e-3, c
+            assert _rel(gout["pred_logits"], wout["pred_logits"]) < 1e-3
+            assert _rel(gtg[0]["prompt_feats"], ctg[0]["prompt_feats"]) < 1e-4
+            assert torch.equal(gtg[0]["prompt_attn_masks"].cpu(), ctg[0]["prompt_attn_masks"])
+    finally:
+        set_precision("fp32")

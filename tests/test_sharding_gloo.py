@@ -48,7 +48,7 @@ def test_all_gather_frames_gloo(T):
     assert all(ok for _, ok in res), res
 
 
-def _model_worker(rank, world, port, q):
+def _model_worker(rank, world, port, q, T=3):
     _init(rank, world, port)
     torch.set_num_threads(2)
     from oracle.cpu_backend import oracle_ops
@@ -56,7 +56,7 @@ def _model_worker(rank, world, port, q):
     from univs_b200.meta_arch import UniVS_Prompt
     from univs_b200.modeling.head import MaskFormerHead
     from univs_b200.registry import ShapeSpec
-    T, Q = 3, 6
+    Q = 6
     bb, pix, dec = mf.build_product_model(mf.TINY_SWIN, num_queries=Q, num_frames=T, clip_emb=mf.make_clip_emb(),
                                           enc_layers=1, dec_layers=2)
     mf.load_keyed((bb, pix, dec))
@@ -74,14 +74,15 @@ def _model_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_frame_sharded_clip_forward_gloo():
+@pytest.mark.parametrize("T", [3, 1])      # T=1 on 2 ranks: rank 1 owns no frame (the 8-GPU / T=5 situation)
+def test_frame_sharded_clip_forward_gloo(T):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29900 + (os.getpid() % 500)
-    procs = [ctx.Process(target=_model_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29900 + T + (os.getpid() % 500)
+    procs = [ctx.Process(target=_model_worker, args=(r, 2, port, q, T)) for r in range(2)]
     [p.start() for p in procs]
     res = [q.get(timeout=300) for _ in procs]
     [p.join(60) for p in procs]
     for rank, err, shape in res:
-        assert shape == (1, 6, 3, 16, 24)
+        assert shape == (1, 6, T, 16, 24)
         assert err < 1e-5, (rank, err)

@@ -77,12 +77,17 @@ class UniVS_Prompt(nn.Module):
             return self.sem_seg_head(features, targets=targets)
         # frame-sharded: local frames -> backbone -> pixel decoder -> all-gather -> decoder
         local = self.sharder.local_frames(x)
-        features = self.backbone(local)
         pd = self.sem_seg_head.pixel_decoder
-        mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(features)
+        if local.shape[0] > 0:
+            features = self.backbone(local)
+            mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(features)
+            parts = [t.permute(0, 2, 3, 1) for t in [mask_features] + list(multi_scale)]
+        else:   # more ranks than frames: this rank owns nothing and only takes part in the exchange
+            Hp, Wp = x.shape[-2:]
+            parts = [x.new_zeros((0, Hp // s, Wp // s, c)) for s, c in
+                     [(4, pd.mask_dim), (32, pd.conv_dim), (16, pd.conv_dim), (8, pd.conv_dim)]]
         # exchange in storage order (channel-last), hand NCHW views back to the decoder
-        gathered = self.sharder.all_gather_frames(
-            [t.permute(0, 2, 3, 1) for t in [mask_features] + list(multi_scale)], x.shape[0])
+        gathered = self.sharder.all_gather_frames(parts, x.shape[0])
         gathered = [t.permute(0, 3, 1, 2) for t in gathered]
         mask_features, multi_scale = gathered[0], gathered[1:]
         return self.sem_seg_head.predictor(multi_scale, mask_features, mask_features, None, targets)
