@@ -146,14 +146,23 @@ def linear_prepped(h, weight, bias=None, cache=True):
     else:  # fp16x3: ONE fp16 GEMM per K-chunk over [Xl' | Xh_s | Xh] x [Wh_s | Wl' | Wh], fp32 accumulate and output
         f32 = torch.float32
         b3, alpha = wh, wlh
-        kc3 = 3 * ops.f16_chunk(K)
+        kc = ops.f16_chunk(K)
+        kc3 = 3 * kc
         h3 = h.reshape(-1, 3 * K)
-        if bias is not None:                      # small GEMMs only: hot-path callers defer the bias into the consumer kernel
-            y = torch.addmm(bias.float(), h3[:, :kc3], b3[:, :kc3].t(), alpha=alpha, out_dtype=f32)
-        else:                                     # beta = 0: `input` is ignored (no broadcast copy), alpha undoes the weight scale
-            y = torch.addmm(_zeros(N, h.device), h3[:, :kc3], b3[:, :kc3].t(), beta=0, alpha=alpha, out_dtype=f32)
-        for k0 in range(kc3, 3 * K, kc3):
-            y = _addmm16(y, h3[:, k0:k0 + kc3], b3[:, k0:k0 + kc3].t(), alpha)
+        try:
+            if bias is not None:                  # small GEMMs only: hot-path callers defer the bias into the consumer kernel
+                y = torch.addmm(bias.float(), h3[:, :kc3], b3[:, :kc3].t(), alpha=alpha, out_dtype=f32)
+            else:                                 # beta = 0: `input` is ignored (no broadcast copy), alpha undoes the weight scale
+                y = torch.addmm(_zeros(N, h.device), h3[:, :kc3], b3[:, :kc3].t(), beta=0, alpha=alpha, out_dtype=f32)
+            for k0 in range(kc3, 3 * K, kc3):
+                y = _addmm16(y, h3[:, k0:k0 + kc3], b3[:, k0:k0 + kc3].t(), alpha)
+        except NotImplementedError:
+            # shapes the fp16->fp32 library GEMM does not cover (e.g. degenerate row counts): rebuild the fp32 operand
+            # from its split (hi + lo*2^-11, exact) and use an IEEE fp32 GEMM -- these are tiny prompt-side products
+            v = h3.view(-1, K // kc, 3, kc).float()
+            x = (v[:, :, 2] + v[:, :, 0] * 2.0 ** -11).reshape(-1, K)
+            with ieee_fp32():
+                y = F.linear(x, weight.float(), bias)
     return y.view(*h.shape[:-1], N)
 
 

@@ -20,6 +20,7 @@ class FrameSharder:
         self.group = process_group
         self.world_size = dist.get_world_size(process_group) if process_group is not None else 1
         self.rank = dist.get_rank(process_group) if process_group is not None else 0
+        self._order = {}
 
     def local_frames(self, x):
         idx = frame_plan(x.shape[0], self.world_size)[self.rank]
@@ -48,11 +49,16 @@ class FrameSharder:
         recv = torch.empty(n * per_rank * frame_numel, device=dev, dtype=dt)
         dist.all_gather_into_tensor(recv, send, group=self.group)
         recv = recv.view(n, per_rank, frame_numel)
-        order = torch.empty(num_frames, dtype=torch.long)
-        for r, frames in enumerate(plan):
-            for j, f in enumerate(frames):
-                order[f] = r * per_rank + j
-        flat = recv.view(n * per_rank, frame_numel)[order.to(dev)]
+        key = (num_frames, n, str(dev))
+        order = self._order.get(key)
+        if order is None:                      # cached on the device: no host->device copy in the (graph-captured) forward
+            idx = [0] * num_frames
+            for r, frames in enumerate(plan):
+                for j, f in enumerate(frames):
+                    idx[f] = r * per_rank + j
+            order = torch.tensor(idx, dtype=torch.long, device=dev)
+            self._order[key] = order
+        flat = recv.view(n * per_rank, frame_numel)[order]
         outs, off = [], 0
         for s, ne in zip(trailing, numels):
             outs.append(flat[:, off:off + ne].reshape(num_frames, *s))
