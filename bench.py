@@ -87,7 +87,9 @@ def run_cpu_reference(args, workload, steps, warmup, as_line):
     from oracle.cpu_backend import oracle_ops
     from univs_b200.build import build_model, make_cfg
     variant, T, H, W, Q = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
+    # the torch CPU path scales to ~32 threads on this workload and slows down beyond (measured on the 128-thread
+    # GPU-box host: 16 thr 8.7 s/frame, 32 thr 7.7 s, 64 thr 13.2 s, 128 thr 115 s) -- use what it can use
+    cores = min(os.cpu_count() or 1, int(os.environ.get("UNIVS_CPU_THREADS", "32")))
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
     cfg = make_cfg(variant, Q, 1, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
