@@ -10,6 +10,8 @@
 //     prompt memory is read with a frame stride of 0 instead of being repeated T times (:819-820).
 //   * univs_attn_mask_bits_f32 -- (..._univs.py:555-566) bilinear-downsample + sigmoid<0.5 threshold of the
 //     mask logits straight to bits + the row flag.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace univs {
@@ -243,6 +245,256 @@ mha_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
   }
 }
 
+// ---- strict-precision variant: fp16 hi|lo split operands, m16n8k16 MMAs (see swin_window_attn.cu) ----------------
+__device__ __forceinline__ void mha_mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mha_split_h(float x, __half& h, __half& l) {
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ uint32_t mha_pack(__half a, __half b) {
+  __half2 v = __halves2half2(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+constexpr int kKS16 = 40;            // halfs per K row (32 + 8)
+constexpr int kVS16 = kKeyBlk + 8;   // halfs per V^T row (64 keys + 8)
+
+__global__ void __launch_bounds__(kMhaThreads)
+mha_fwd_f16x3_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                     const uint32_t* __restrict__ mask_bits, const int32_t* __restrict__ row_open, int mask_batch, int B,
+                     int Lq, int Lk, int C, int heads, int nsplit, int blocks_per_split, float* __restrict__ out,
+                     float* __restrict__ part_o, float* __restrict__ part_ml) {
+  __shared__ __align__(16) __half Kh[kKeyBlk * kKS16], Kl[kKeyBlk * kKS16];
+  __shared__ __align__(16) __half Vth[32 * kVS16], Vtl[32 * kVS16];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int bh = blockIdx.y, b = bh / heads, h = bh - b * heads;
+  const int split = blockIdx.z;
+  const int r0 = blockIdx.x * kRowsPerCta + warp * 16 + g, r1 = r0 + 8;
+  const int nkb = (Lk + kKeyBlk - 1) / kKeyBlk;
+  const int kb_begin = split * blocks_per_split;
+  const int kb_end = min(nkb, kb_begin + blocks_per_split);
+  const float scale = 0.17677669529663687f;
+  const float* kbase = k + (size_t)b * Lk * C + h * 32;
+  const float* vbase = v + (size_t)b * Lk * C + h * 32;
+
+  // register prefetch of one 64-key block: thread -> (row = tid/8 + 32*it, 4 dims = (tid%8)*4), K and V
+  float4 pk[2], pv[2];
+  auto fetch = [&](int kb) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int key = kb * kKeyBlk + (tid >> 3) + 32 * it;
+      if (key < Lk) {
+        pk[it] = ldg_f4(kbase + (size_t)key * C + (tid & 7) * 4);
+        pv[it] = ldg_f4(vbase + (size_t)key * C + (tid & 7) * 4);
+      } else {
+        pk[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pv[it] = pk[it];
+      }
+    }
+  };
+  auto stash = [&]() {   // split to fp16 hi|lo; K row-major, V transposed
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int rr = (tid >> 3) + 32 * it, c4 = (tid & 7) * 4;
+      const float kk[4] = {pk[it].x, pk[it].y, pk[it].z, pk[it].w};
+      const float vv[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
+      __half hh[4], ll[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mha_split_h(kk[e], hh[e], ll[e]);
+      *reinterpret_cast<uint2*>(Kh + rr * kKS16 + c4) = make_uint2(mha_pack(hh[0], hh[1]), mha_pack(hh[2], hh[3]));
+      *reinterpret_cast<uint2*>(Kl + rr * kKS16 + c4) = make_uint2(mha_pack(ll[0], ll[1]), mha_pack(ll[2], ll[3]));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        mha_split_h(vv[e], hh[e], ll[e]);
+        Vth[(c4 + e) * kVS16 + rr] = hh[e];
+        Vtl[(c4 + e) * kVS16 + rr] = ll[e];
+      }
+    }
+  };
+
+  // Q fragments (scaled, split) straight from global
+  uint32_t qh[2][4], ql[2][4];
+  {
+    const float* q0 = q + ((size_t)b * Lq + min(r0, Lq - 1)) * C + h * 32;
+    const float* q1 = q + ((size_t)b * Lq + min(r1, Lq - 1)) * C + h * 32;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        const int c0 = ks * 16 + 2 * t + 8 * part;
+        const float2 x0 = r0 < Lq ? __ldg(reinterpret_cast<const float2*>(q0 + c0)) : make_float2(0.f, 0.f);
+        const float2 x1 = r1 < Lq ? __ldg(reinterpret_cast<const float2*>(q1 + c0)) : make_float2(0.f, 0.f);
+        __half a, bb, la, lb;
+        mha_split_h(x0.x * scale, a, la);
+        mha_split_h(x0.y * scale, bb, lb);
+        qh[ks][2 * part] = mha_pack(a, bb);
+        ql[ks][2 * part] = mha_pack(la, lb);
+        mha_split_h(x1.x * scale, a, la);
+        mha_split_h(x1.y * scale, bb, lb);
+        qh[ks][2 * part + 1] = mha_pack(a, bb);
+        ql[ks][2 * part + 1] = mha_pack(la, lb);
+      }
+    }
+  }
+  const int words = (Lk + 31) >> 5;
+  const int mb = (mask_batch == 1) ? 0 : b;
+  const uint32_t* mrow0 = nullptr;
+  const uint32_t* mrow1 = nullptr;
+  if (mask_bits != nullptr) {
+    bool use0 = r0 < Lq, use1 = r1 < Lq;
+    if (row_open != nullptr) {
+      if (use0) use0 = __ldg(row_open + (size_t)mb * Lq + r0) != 0;
+      if (use1) use1 = __ldg(row_open + (size_t)mb * Lq + r1) != 0;
+    }
+    if (use0) mrow0 = mask_bits + ((size_t)mb * Lq + r0) * words;
+    if (use1) mrow1 = mask_bits + ((size_t)mb * Lq + r1) * words;
+  }
+
+  float o[4][4];
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  if (kb_begin < kb_end) fetch(kb_begin);
+  for (int kb = kb_begin; kb < kb_end; ++kb) {
+    __syncthreads();            // previous block's fragments are no longer read
+    stash();
+    __syncthreads();
+    if (kb + 1 < kb_end) fetch(kb + 1);   // global loads of the next block fly during the MMAs below
+
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const int krow = nt * 8 + g;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int c0 = ks * 16 + 2 * t;
+        const uint32_t kh0 = *reinterpret_cast<const uint32_t*>(Kh + krow * kKS16 + c0);
+        const uint32_t kh1 = *reinterpret_cast<const uint32_t*>(Kh + krow * kKS16 + c0 + 8);
+        const uint32_t kl0 = *reinterpret_cast<const uint32_t*>(Kl + krow * kKS16 + c0);
+        const uint32_t kl1 = *reinterpret_cast<const uint32_t*>(Kl + krow * kKS16 + c0 + 8);
+        mha_mma_f16(s[nt], ql[ks], kh0, kh1);
+        mha_mma_f16(s[nt], qh[ks], kl0, kl1);
+        mha_mma_f16(s[nt], qh[ks], kh0, kh1);
+      }
+    }
+    uint32_t w00 = 0, w01 = 0, w10 = 0, w11 = 0;
+    const int wbase = kb * 2;
+    if (mrow0) {
+      w00 = __ldg(mrow0 + wbase);
+      if (wbase + 1 < words) w01 = __ldg(mrow0 + wbase + 1);
+    }
+    if (mrow1) {
+      w10 = __ldg(mrow1 + wbase);
+      if (wbase + 1 < words) w11 = __ldg(mrow1 + wbase + 1);
+    }
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int jj = nt * 8 + 2 * t + e;
+        const int key = kb * kKeyBlk + jj;
+        const uint32_t bit0 = ((jj < 32 ? w00 : w01) >> (jj & 31)) & 1u;
+        const uint32_t bit1 = ((jj < 32 ? w10 : w11) >> (jj & 31)) & 1u;
+        if (key >= Lk || bit0) s[nt][e] = -INFINITY;
+        if (key >= Lk || bit1) s[nt][2 + e] = -INFINITY;
+        bm0 = fmaxf(bm0, s[nt][e]);
+        bm1 = fmaxf(bm1, s[nt][2 + e]);
+      }
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+    const float e0 = (nm0 == -INFINITY) ? 0.f : nm0, e1 = (nm1 == -INFINITY) ? 0.f : nm1;
+    const float sc0 = safe_exp_diff(m0, e0), sc1 = safe_exp_diff(m1, e1);
+    m0 = nm0;
+    m1 = nm1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = expf(s[nt][0] - e0);
+      s[nt][1] = expf(s[nt][1] - e0);
+      s[nt][2] = expf(s[nt][2] - e1);
+      s[nt][3] = expf(s[nt][3] - e1);
+      ps0 += s[nt][0] + s[nt][1];
+      ps1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * sc0 + ps0;
+    l1 = l1 * sc1 + ps1;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      o[nb][0] *= sc0; o[nb][1] *= sc0; o[nb][2] *= sc1; o[nb][3] *= sc1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int nt = 2 * kk + half;
+        __half h0, h1, h2, h3, x0, x1, x2, x3;
+        mha_split_h(s[nt][0], h0, x0);
+        mha_split_h(s[nt][1], h1, x1);
+        mha_split_h(s[nt][2], h2, x2);
+        mha_split_h(s[nt][3], h3, x3);
+        ph[2 * half] = mha_pack(h0, h1);
+        ph[2 * half + 1] = mha_pack(h2, h3);
+        pl[2 * half] = mha_pack(x0, x1);
+        pl[2 * half + 1] = mha_pack(x2, x3);
+      }
+      const int key0 = kk * 16 + 2 * t;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const int d = nb * 8 + g;
+        const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(Vth + d * kVS16 + key0);
+        const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(Vth + d * kVS16 + key0 + 8);
+        const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(Vtl + d * kVS16 + key0);
+        const uint32_t vl1 = *reinterpret_cast<const uint32_t*>(Vtl + d * kVS16 + key0 + 8);
+        mha_mma_f16(o[nb], pl, vh0, vh1);
+        mha_mma_f16(o[nb], ph, vl0, vl1);
+        mha_mma_f16(o[nb], ph, vh0, vh1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+  if (nsplit == 1) {
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const int c = h * 32 + nb * 8 + 2 * t;
+      if (r0 < Lq) *reinterpret_cast<float2*>(out + ((size_t)b * Lq + r0) * C + c) = make_float2(o[nb][0] * i0, o[nb][1] * i0);
+      if (r1 < Lq) *reinterpret_cast<float2*>(out + ((size_t)b * Lq + r1) * C + c) = make_float2(o[nb][2] * i1, o[nb][3] * i1);
+    }
+  } else {
+    const size_t rows = (size_t)B * heads * Lq;
+    float* po = part_o + ((size_t)split * rows + (size_t)bh * Lq) * 32;
+    float* pm = part_ml + ((size_t)split * rows + (size_t)bh * Lq) * 2;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const int c = nb * 8 + 2 * t;
+      if (r0 < Lq) *reinterpret_cast<float2*>(po + (size_t)r0 * 32 + c) = make_float2(o[nb][0], o[nb][1]);
+      if (r1 < Lq) *reinterpret_cast<float2*>(po + (size_t)r1 * 32 + c) = make_float2(o[nb][2], o[nb][3]);
+    }
+    if (t == 0) {
+      if (r0 < Lq) *reinterpret_cast<float2*>(pm + (size_t)r0 * 2) = make_float2(m0, l0);
+      if (r1 < Lq) *reinterpret_cast<float2*>(pm + (size_t)r1 * 2) = make_float2(m1, l1);
+    }
+  }
+}
+
 // merge split-K partials: one warp per (b, h, q) row, lane = channel
 __global__ void __launch_bounds__(256)
 mha_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int B, int heads, int Lq,
@@ -416,8 +668,8 @@ extern "C" int univs_mha_forward_f32(void* stream, const float* q, const float* 
   float* part_ml = part_o ? part_o + (size_t)ns * batch * heads * len_q * 32 : nullptr;
   dim3 grid(qt, batch * heads, ns);
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == UNIVS_PREC_TF32X3)
-    mha_fwd_kernel<true><<<grid, kMhaThreads, 0, st>>>(q, k, v, mask_bits, row_open, mask_batch, batch, len_q, len_k,
+  if (precision == UNIVS_PREC_TF32X3)   // strict: fp16 hi|lo split kernel (fp32-equivalent products)
+    mha_fwd_f16x3_kernel<<<grid, kMhaThreads, 0, st>>>(q, k, v, mask_bits, row_open, mask_batch, batch, len_q, len_k,
                                                        channels, heads, ns, bps, out, part_o, part_ml);
   else
     mha_fwd_kernel<false><<<grid, kMhaThreads, 0, st>>>(q, k, v, mask_bits, row_open, mask_batch, batch, len_q, len_k,

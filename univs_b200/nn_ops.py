@@ -211,11 +211,15 @@ def conv2d_cl(x_cl, weight, bias=None, padding=0):
             yr.addmm_(a, wlh.t())
         else:
             if t == 0:
-                yr = torch.addmm(bias.float() if bias is not None else y.new_zeros(Cout), a, wh.t(), alpha=wlh, out_dtype=f32)
+                base = bias.float() if bias is not None else _zeros(Cout, y.device)
+                try:        # write straight into the padded output buffer (rows beyond R are never read)
+                    torch.addmm(base, a, wh.t(), beta=0 if bias is None else 1, alpha=wlh, out_dtype=f32, out=yr)
+                except (RuntimeError, TypeError):
+                    yr.copy_(torch.addmm(base, a, wh.t(), beta=0 if bias is None else 1, alpha=wlh, out_dtype=f32))
             else:
-                yr = _addmm16(yr, a, wh.t(), wlh)
-    if _policy != "tf32x3":
-        return torch.cat([yr, yr.new_zeros(N * Hp * Wp - R, Cout)], 0).view(N, Hp, Wp, Cout)[:, :H, :W]
+                res = _addmm16(yr, a, wh.t(), wlh)
+                if res.data_ptr() != yr.data_ptr():
+                    yr.copy_(res)
     return y.view(N, Hp, Wp, Cout)[:, :H, :W]
 
 
