@@ -278,7 +278,8 @@ def main():
             try:
                 cpu = run_cpu_reference(args, args.workload, 1, 1, False)
             except BaseException as e:  # noqa: BLE001
-                cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+                cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                       "sample": f"failed: {str(e)[:200]}"}
         line = {
             "metric": "frames/sec (Swin-L 720p T=5 Q=200)" if args.workload == "ns" else "frames/sec (per-clip forward)",
             "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,

@@ -108,12 +108,19 @@ _PATCH = {"layernorm": _layernorm,
 
 
 @contextlib.contextmanager
-def oracle_ops():
+def oracle_ops(policy="fp32"):
+    """`policy`: the nn_ops operand policy while the oracle is active.  "fp32" (default) = plain fp32 operands and
+    IEEE GEMMs, i.e. the reference arithmetic; "tf32x3" exercises the split-operand plumbing with exact CPU GEMMs
+    (the fp16 GEMM path has no CPU implementation)."""
+    from univs_b200 import nn_ops
     saved = {k: getattr(ops, k) for k in _PATCH}
+    saved_policy = nn_ops.policy()
     try:
         for k, f in _PATCH.items():
             setattr(ops, k, f)
+        nn_ops.set_policy(policy)
         yield
     finally:
         for k, f in saved.items():
             setattr(ops, k, f)
+        nn_ops.set_policy(saved_policy)

@@ -163,12 +163,9 @@ def test_split_operand_policy_plumbing_on_cpu():
     tg = lambda: [{"task": "detection", "dataset_name": "bdd_track", "prompt_type": "text",
                    "frame_indices": torch.arange(T)}]
     rf, (rmf, rms), rout = ref_shim.reference_clip_forward(*ref, x, tg())
-    nn_ops.set_policy("tf32x3")
-    try:
-        with oracle_ops():
-            pf, (pmf, pms), pout = mf.product_clip_forward(*prod, x, tg())
-    finally:
-        nn_ops.set_policy("fp32")
+    with oracle_ops(policy="tf32x3"):
+        pf, (pmf, pms), pout = mf.product_clip_forward(*prod, x, tg())
+    assert nn_ops.policy() == "fp32"
     assert _rel(pf["res5"], rf["res5"]) < 1e-4
     assert _rel(pmf, rmf) < 1e-4
     assert _rel(pout["pred_masks"], rout["pred_masks"]) < 1e-3
