@@ -157,7 +157,7 @@ extern "C" int univs_mask_einsum_f16x3(void* stream, const void* mask_embed16, c
   int rc = check_einsum_args("mask_einsum_f16x3", (const float*)mask_embed16, (const float*)mask_features16, out, frames,
                              queries, channels, pixels);
   if (rc) return rc < 0 ? rc : UNIVS_OK;
-  UNIVS_REQUIRE(channels % 64 == 0, "mask_einsum_f16x3: channels must be a multiple of 64");
+  UNIVS_REQUIRE(channels % 32 == 0, "mask_einsum_f16x3: channels must be a multiple of 32");
   UNIVS_REQUIRE(((uintptr_t)mask_embed16 & 15) == 0 && ((uintptr_t)mask_features16 & 15) == 0,
                 "mask_einsum_f16x3: operands must be 16-byte aligned (TMA)");
   return launch_mask_einsum_tc_f16((cudaStream_t)stream, mask_embed16, mask_features16, frames, queries, channels, pixels, out);

@@ -27,7 +27,7 @@ namespace univs {
 constexpr int kTcTileM = 128;
 constexpr int kTcChunk = 32;  // fp32 channels per stage = 128 bytes = one SWIZZLE_128B row
 constexpr int kTcStagesTf32 = 4;
-constexpr int kTcStagesF16 = 2;
+constexpr int kTcStagesF16 = 4;   // 64-byte operand rows (SWIZZLE_64B): four 42 KB stages instead of two 85 KB ones
 constexpr int kTcThreads = 256;
 constexpr int kTcMaxN = 256;
 constexpr int kTcABytes = kTcTileM * 128;  // 16 KB
@@ -88,10 +88,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (cute: ((8,n),2):((8,SBO),1), LBO=1)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
+// K-major swizzled operand tile: rows of ROW bytes (128 -> SWIZZLE_128B, layout code 2; 64 -> SWIZZLE_64B, code 4),
+// 8-row groups 8*ROW bytes apart (cute canonical K-major layouts ((8,n),2):((ROW/16,SBO),1), LBO = 1)
+template <int ROW>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((8 * ROW) >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)(ROW == 128 ? 2 : 4) << 61);
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -125,9 +127,12 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
                       int C, int HW, int npad, float* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int kTcStages = F16X3 ? kTcStagesF16 : kTcStagesTf32;
-  constexpr int kChunkElems = F16X3 ? 64 : 32;      // 128-byte operand rows
-  const int b_bytes = npad * 128;                   // multiple of 2048 (npad % 16 == 0)
-  const int stage_bytes = (F16X3 ? 2 : 1) * (kTcABytes + b_bytes);
+  constexpr int kRowBytes = F16X3 ? 64 : 128;       // operand row = one swizzle span
+  constexpr int kChunkElems = 32;                   // 32 halfs (64 B) or 32 floats (128 B) per stage
+  constexpr int kKSteps = F16X3 ? 2 : 4;            // MMA k-steps (32 B each) per stage
+  constexpr int kABytes = kTcTileM * kRowBytes;     // 8 KB / 16 KB
+  const int b_bytes = npad * kRowBytes;             // multiple of 1024 (npad % 16 == 0)
+  const int stage_bytes = (F16X3 ? 2 : 1) * (kABytes + b_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kTcStages * stage_bytes);
   uint64_t* full = bars;                   // [kTcStages]
   uint64_t* empty = bars + kTcStages;      // [kTcStages]
@@ -172,10 +177,10 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
           unsigned char* sA = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
           tma_load_3d(sA, &map_f, &full[stage], kc * kChunkElems, p0, t);
-          tma_load_3d(sA + kTcABytes, &map_e, &full[stage], kc * kChunkElems, 0, t);
+          tma_load_3d(sA + kABytes, &map_e, &full[stage], kc * kChunkElems, 0, t);
           if (F16X3) {   // lo halves live C columns further right
-            tma_load_3d(sA + kTcABytes + b_bytes, &map_f, &full[stage], C + kc * kChunkElems, p0, t);
-            tma_load_3d(sA + 2 * kTcABytes + b_bytes, &map_e, &full[stage], C + kc * kChunkElems, 0, t);
+            tma_load_3d(sA + kABytes + b_bytes, &map_f, &full[stage], C + kc * kChunkElems, p0, t);
+            tma_load_3d(sA + 2 * kABytes + b_bytes, &map_e, &full[stage], C + kc * kChunkElems, 0, t);
           }
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
@@ -200,14 +205,14 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + kTcABytes);
+          const uint64_t adesc = make_desc<kRowBytes>(a_addr);
+          const uint64_t bdesc = make_desc<kRowBytes>(a_addr + kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // one k-step = 32 bytes (8 tf32 / 16 f16) inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          for (int k = 0; k < kKSteps; ++k) {
+            // one k-step = 32 bytes (8 tf32 / 16 f16) inside the swizzle row: +2 in the (addr >> 4) field
             if (F16X3) {
-              const uint64_t adesc_lo = make_sw128_desc(a_addr + kTcABytes + b_bytes);
-              const uint64_t bdesc_lo = make_sw128_desc(a_addr + 2 * kTcABytes + b_bytes);
+              const uint64_t adesc_lo = make_desc<kRowBytes>(a_addr + kABytes + b_bytes);
+              const uint64_t bdesc_lo = make_desc<kRowBytes>(a_addr + 2 * kABytes + b_bytes);
               umma_f16(tmem_d, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);  // Fl*Eh
               umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, 1u);                        // Fh*El
               umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);                           // Fh*Eh
@@ -280,16 +285,17 @@ static EncodeTiledFn get_encode() {
 }
 
 // 3-D tensor [d2][d1][d0] (d0 contiguous) of fp32 (esize 4) or fp16 (esize 2), box [128 bytes][box_rows][1], SWIZZLE_128B
-static int make_map(CUtensorMap* m, const void* base, int d0, int d1, int d2, int box_rows, int esize) {
+static int make_map(CUtensorMap* m, const void* base, int d0, int d1, int d2, int box_rows, int esize, int row_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("mask_einsum_tc: cuTensorMapEncodeTiled entry point unavailable"); return UNIVS_E_LAUNCH; }
   cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
   cuuint64_t strides[2] = {(cuuint64_t)d0 * esize, (cuuint64_t)d0 * (cuuint64_t)d1 * esize};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)(row_bytes / esize), (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                    const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("mask_einsum_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return UNIVS_E_LAUNCH; }
   return 0;
@@ -301,12 +307,13 @@ static int launch_tc(cudaStream_t st, const void* E, const void* F, int T, int Q
   const int esize = F16X3 ? 2 : 4;
   const int width = F16X3 ? 2 * C : C;      // fp16 operands carry [hi | lo]
   CUtensorMap map_f, map_e;
-  int rc = make_map(&map_f, F, width, HW, T, kTcTileM, esize);
+  const int row_bytes = F16X3 ? 64 : 128;
+  int rc = make_map(&map_f, F, width, HW, T, kTcTileM, esize, row_bytes);
   if (rc) return rc;
-  rc = make_map(&map_e, E, width, Q, T, npad, esize);
+  rc = make_map(&map_e, E, width, Q, T, npad, esize, row_bytes);
   if (rc) return rc;
   const int stages = F16X3 ? kTcStagesF16 : kTcStagesTf32;
-  const size_t smem = (size_t)stages * (F16X3 ? 2 : 1) * (kTcABytes + npad * 128) + 256;
+  const size_t smem = (size_t)stages * (F16X3 ? 2 : 1) * ((size_t)kTcTileM * row_bytes + (size_t)npad * row_bytes) + 256;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

@@ -63,6 +63,18 @@ class _PackedMHA(nn.Module):
     def wqk(self):
         return self.in_proj_weight[: 2 * self.d], self.in_proj_bias[: 2 * self.d]
 
+    def folded_out_bias(self):
+        """out_proj.bias + out_proj.weight @ b_v : softmax rows sum to one, so the value bias passes through the
+        attention unchanged and can be added after the output projection (cached per parameter version)."""
+        key = (self.in_proj_bias._version, self.out_proj.weight._version, self.out_proj.bias._version,
+               self.in_proj_bias.data_ptr())
+        if getattr(self, "_fold", None) is None or self._fold[0] != key:
+            with torch.no_grad():
+                bv = self.in_proj_bias[2 * self.d:].double()
+                fb = (self.out_proj.bias.double() + self.out_proj.weight.double() @ bv).float().contiguous()
+            self._fold = (key, fb)
+        return self._fold[1]
+
 
 class _SelfAttnLayer(nn.Module):          # transformer_layers.py:11-66 (post-norm)
     def __init__(self, d):
@@ -262,7 +274,9 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         q = nn_ops.linear(x + qpos, wq, bq)
         a = ops.mha_core(q, k, v, bits, row_open)
         o = nn_ops.linear(a, mha.out_proj.weight, None)
-        return nn_ops.layernorm(x, layer.norm, residual=o, for_gemm=False, residual_bias=mha.out_proj.bias)[1]
+        # k, v arrive without their in-proj biases: the key bias shifts every score of a row by the same constant
+        # (softmax-invariant) and the value bias is folded into the output bias
+        return nn_ops.layernorm(x, layer.norm, residual=o, for_gemm=False, residual_bias=mha.folded_out_bias())[1]
 
     def _self_attention(self, layer, x, qpos, bits):
         """x, qpos: [T,Q,C] -> tokens (q*T + t) (..._univs.py:408-416)"""
@@ -466,8 +480,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
             lvl = i % 3
             ca = self.transformer_cross_attention_layers[i].multihead_attn
             wk, bk = ca.wk(); wv, bv = ca.wv()
-            k = nn_ops.linear(src[lvl] + pos[lvl], wk, bk)
-            v = nn_ops.linear(src[lvl], wv, bv)
+            k = nn_ops.linear(src[lvl] + pos[lvl], wk, None)      # biases handled in _cross_attention
+            v = nn_ops.linear(src[lvl], wv, None)
             out = self._cross_attention(self.transformer_cross_attention_layers[i], out, qpos, k, v, bits, row_open)
             out = self._self_attention(self.transformer_self_attention_layers[i], out, qpos, sa_bits)
             out = self.transformer_ffn_layers[i](out)
