@@ -12,7 +12,7 @@
 // HBM-bound by design (AI = 56 F/B): per 128-pixel tile the kernel streams 128 KB of F once and writes
 // Q*512 B of logits once; E (Q*C*4 B per frame) is re-read from L2 per tile.  Persistent CTAs (one per SM),
 // warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
-// warps 4-7 = epilogue.  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1;
+// warps 4-11 = epilogue.  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1;
 // a 4-stage smem ring (F 16 KB + E Npad*128 B per stage) keeps TMA ahead of the tensor core.
 //
 // Precision: kind::tf32 consumes the upper 19 bits of each fp32 operand (truncation).  Callers that need
@@ -28,7 +28,7 @@ constexpr int kTcTileM = 128;
 constexpr int kTcChunk = 32;  // fp32 channels per stage = 128 bytes = one SWIZZLE_128B row
 constexpr int kTcStagesTf32 = 4;
 constexpr int kTcStagesF16 = 4;   // 64-byte operand rows (SWIZZLE_64B): four 42 KB stages instead of two 85 KB ones
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kTcMaxN = 256;
 constexpr int kTcABytes = kTcTileM * 128;  // 16 KB
 
@@ -152,7 +152,7 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[i], 8);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -229,8 +229,12 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int wq = warp - 4;  // TMEM lane quarter this warp may access (== warp % 4)
+    // ===== epilogue: TMEM -> registers -> global.  8 warps: two per TMEM lane quarter, each taking every other
+    // 32-column chunk; branch-free stores (one pointer bump per query column) for all full chunks =====
+    const int ew = warp - 4;
+    const int wq = ew & 3;      // TMEM lane quarter this warp may access (== warp % 4)
+    const int half = ew >> 2;   // 0: chunks 0,2,4,..   1: chunks 1,3,5,..
+    const size_t plane = (size_t)T * HW;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -241,15 +245,24 @@ mask_einsum_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kTcMaxN);
       float* orow = out + (size_t)t * HW + p;
-      for (int c0 = 0; c0 < npad; c0 += 32) {
+      const bool row_ok = p < HW;
+      for (int c0 = half * 32; c0 < npad; c0 += 64) {
         uint32_t r[32];
         TMEM_LD_32x32b_X32(taddr + (uint32_t)c0, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (p < HW) {
+        if (row_ok) {
+          float* dst = orow + (size_t)c0 * plane;
+          if (c0 + 32 <= Q) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int q = c0 + j;
-            if (q < Q) __stcs(orow + (size_t)q * T * HW, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) {
+              __stcs(dst, __uint_as_float(r[j]));
+              dst += plane;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < Q) __stcs(dst + (size_t)j * plane, __uint_as_float(r[j]));
+            }
           }
         }
       }
