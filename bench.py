@@ -199,7 +199,9 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    use_graph = not args.no_graph
+    # frame-sharded runs replay a graph only when asked to (UNIVS_GRAPH_MULTI=1): capturing the NCCL all-gather is
+    # supported by torch but has been validated here on fewer configurations than the eager path
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("UNIVS_GRAPH_MULTI", "0") == "1")
     graphed = None
     if use_graph:
         from univs_b200.runtime import GraphedClip
@@ -267,8 +269,14 @@ def main():
     roof = None
     if "mask_einsum" in kernel_ms:
         ach = alg_bytes / (kernel_ms["mask_einsum"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_einsum_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == args.workload and tj.get("precision") == args.precision:
+                traffic = tj.get("dram_bytes_per_launch")     # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full
         roof = {"kernel": "mask_einsum", "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "launch_ms": kernel_ms["mask_einsum"],
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "launch_ms": kernel_ms["mask_einsum"],
                 "algorithmic_bytes_per_launch": alg_bytes}
 
     line = None
