@@ -238,7 +238,7 @@ def mha_core(q, k, v, mask_bits=None, row_open=None, precision=None):
     ws = _workspace(nbytes, q.device)
     mb = 0 if mask_bits is None else mask_bits.shape[0]
     with _Bracket("mha", 1 if nbytes <= 16 else 2):
-          rc = lib().univs_mha_forward_f32(
+        rc = lib().univs_mha_forward_f32(
             _stream(), _chk(q, "q"), _chk(k, "k"), _chk(v, "v"),
             None if mask_bits is None else _chk(mask_bits, "mask_bits", torch.int32),
             None if row_open is None else _chk(row_open, "row_open", torch.int32),
