@@ -124,6 +124,18 @@ def test_mask_einsum(ops, T, Q, C, HW):
         assert _rel(f16, want) < 5e-6
 
 
+def test_mask_einsum_more_than_256_queries(ops):
+    """Category prompts of a large vocabulary (e.g. lvis: 200 + 1203 queries) exceed one launch's 256 queries."""
+    torch.manual_seed(14)
+    T, Q, C, HW = 2, 600, 256, 500
+    E, F = torch.randn(T, Q, C), torch.randn(T, HW, C)
+    want = ops_ref.mask_einsum(E.double(), F.transpose(1, 2).double()).float()
+    for mode in ("f16x3", "mma3x"):
+        got = ops.mask_einsum(E.cuda(), ops.prepare_mask_features(F.cuda(), mode), mode=mode)
+        assert got.shape == (Q, T, HW)
+        assert _rel(got, want) < 5e-6
+
+
 def test_mask_einsum_empty(ops):
     out = ops.mask_einsum(torch.zeros(0, 4, 32, device="cuda"), torch.zeros(0, 8, 32, device="cuda"), mode="mma3x")
     assert out.shape == (4, 0, 8)

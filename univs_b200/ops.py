@@ -168,6 +168,10 @@ def mask_einsum(mask_embed, mask_features_prepared, out=None, mode=None):
     HW = mask_features_prepared.shape[1]
     if out is None:
         out = torch.empty((Q, T, HW), device=mask_embed.device, dtype=torch.float32)
+    if Q > 256:      # one launch covers <= 256 queries (TMEM columns); large prompt vocabularies run in query chunks
+        for q0 in range(0, Q, 256):
+            mask_einsum(mask_embed[:, q0:q0 + 256].contiguous(), mask_features_prepared, out=out[q0:q0 + 256], mode=mode)
+        return out
     if mode == "f16x3":
         e = split_operand(mask_embed if mask_embed.is_contiguous() else mask_embed.contiguous(), "f16u")
         with _Bracket("mask_einsum", 1):
