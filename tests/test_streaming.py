@@ -1,0 +1,35 @@
+"""Cross-clip reuse: per-frame cached pixel-decoder outputs + per-clip decoder equal the
+per-clip recomputation of the whole path (operators = CPU oracles)."""
+import torch
+
+from oracle.cpu_backend import oracle_ops
+from tests import model_factory as mf
+from univs_b200.meta_arch import UniVS_Prompt
+from univs_b200.modeling.head import MaskFormerHead
+from univs_b200.registry import ShapeSpec
+from univs_b200.streaming import ClipStream
+
+
+def test_clip_stream_equals_per_clip_recompute():
+    T, Q, V = 3, 6, 5
+    bb, pix, dec = mf.build_product_model(mf.TINY_SWIN, num_queries=Q, num_frames=T, clip_emb=mf.make_clip_emb(),
+                                          enc_layers=1, dec_layers=2)
+    mf.load_keyed((bb, pix, dec))
+    shapes = {f"res{i + 2}": ShapeSpec(channels=32 * 2 ** i, stride=4 * 2 ** i) for i in range(4)}
+    head = MaskFormerHead(shapes, num_classes=133, pixel_decoder=pix, transformer_predictor=dec)
+    model = UniVS_Prompt(backbone=bb, sem_seg_head=head, pixel_mean=[123.675, 116.28, 103.53],
+                         pixel_std=[58.395, 57.12, 57.375])
+    g = torch.Generator().manual_seed(3)
+    video = torch.rand(V, 3, 60, 90, generator=g) * 255
+    mk = lambda s: [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual",
+                     "frame_indices": torch.arange(s, s + T)}]
+    with oracle_ops():
+        stream = ClipStream(model, T)
+        got = {s: o["pred_masks"].clone() for s, o in stream.run(video, mk, stride=1, chunk=2)}
+        want = {s: model.clip_forward(video[s:s + T], mk(s))["pred_masks"] for s in range(V - T + 1)}
+    assert sorted(got) == [0, 1, 2]
+    assert stream.frames_encoded == V                       # every frame through backbone + pixel decoder exactly once
+    for s in want:
+        assert got[s].shape == want[s].shape
+        err = (got[s] - want[s]).abs().max().item() / want[s].abs().max().item()
+        assert err < 1e-4, (s, err)
