@@ -1,23 +1,28 @@
-// Mask-logit einsum on the 5th-gen tensor cores: TMA -> shared memory -> tcgen05.mma (kind::tf32) -> TMEM ->
-// tcgen05.ld -> coalesced global stores.  (reference op: ..._univs.py:527-528 "btqc,btchw->btqhw" + transpose)
+// Mask-logit einsum on the 5th-gen tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM -> tcgen05.ld -> coalesced
+// global stores.  (reference op: ..._univs.py:527-528 "btqc,btchw->btqhw" + transpose)
 //
-//   out[q, t, p] = sum_c E[t, q, c] * F[t, p, c]      E [T,Q,C], F channel-last [T,HW,C], out [Q,T,HW], all fp32
+//   out[q, t, p] = sum_c E[t, q, c] * F[t, p, c]      E [T,Q,C], F channel-last [T,HW,C], out [Q,T,HW] fp32
 //
 // Mapping onto UMMA (D = A * B^T, both operands K-major):
-//   A (M side) = F tile: 128 pixels x 32 channels   -> TMEM lane  = pixel
-//   B (N side) = E tile: Npad queries x 32 channels -> TMEM column = query        (Npad = ceil16(Q) <= 256)
+//   A (M side) = F tile: 128 pixels x one K-chunk   -> TMEM lane  = pixel
+//   B (N side) = E tile: Npad queries x one K-chunk -> TMEM column = query        (Npad = ceil16(Q) <= 256)
 // so that one TMEM column (= one query) is 128 consecutive pixels = 512 contiguous bytes of `out`: the epilogue's
 // 32x32b TMEM loads give every lane one pixel and the stores of a warp are one full 128-byte line per query.
 //
-// HBM-bound by design (AI = 56 F/B): per 128-pixel tile the kernel streams 128 KB of F once and writes
-// Q*512 B of logits once; E (Q*C*4 B per frame) is re-read from L2 per tile.  Persistent CTAs (one per SM),
-// warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
-// warps 4-11 = epilogue.  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1;
-// a 4-stage smem ring (F 16 KB + E Npad*128 B per stage) keeps TMA ahead of the tensor core.
+// Two instantiations:
+//   <false> fp32 operands consumed as TF32 (kind::tf32, truncation: callers pre-round with univs_round_tf32_f32),
+//           128-byte operand rows (32 floats), SWIZZLE_128B, 4-stage ring;
+//   <true>  fp16 [hi | lo] operands (univs_split_tf32_f32 chunk = UNIVS_SPLIT_F16U), three kind::f16 MMAs per k-step
+//           (lo*hi + hi*lo + hi*hi): fp32-equivalent products at the byte count of the fp32 tensors; 64-byte operand
+//           rows (32 halfs), SWIZZLE_64B, 4-stage ring of {F_hi, E_hi, F_lo, E_lo}.
+// Accumulation is fp32 in TMEM in both.
 //
-// Precision: kind::tf32 consumes the upper 19 bits of each fp32 operand (truncation).  Callers that need
-// round-to-nearest pre-round E and F with univs_round_tf32_f32 (the decoder does: F once per clip, E per call);
-// accumulation is fp32 in TMEM.
+// HBM-bound by design (AI = 56 F/B): per 128-pixel tile the kernel streams 128 KB of F once and writes Q*512 B of logits
+// once; E (Q*C*4 B per frame) is re-read from L2 per tile.  Persistent CTAs (one per SM), warp-specialised:
+// warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-11 = epilogue
+// (two per TMEM lane quarter, alternating 32-column chunks, branch-free pointer-bump stores -- the 4-warp predicated
+// epilogue of the first version was the bottleneck: 0.177 ms -> 0.109 ms at the north-star shape).  Two TMEM accumulator
+// stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -25,7 +30,6 @@
 namespace univs {
 
 constexpr int kTcTileM = 128;
-constexpr int kTcChunk = 32;  // fp32 channels per stage = 128 bytes = one SWIZZLE_128B row
 constexpr int kTcStagesTf32 = 4;
 constexpr int kTcStagesF16 = 4;   // 64-byte operand rows (SWIZZLE_64B): four 42 KB stages instead of two 85 KB ones
 constexpr int kTcThreads = 384;   // 4 control warps + 8 epilogue warps
