@@ -298,3 +298,59 @@ def reference_clip_forward(bb, pix, dec, frames, targets):
     mf, mf_bfe, _enc0, ms = pix.forward_features(feats)
     out = dec(ms, mf, mf_bfe, None, targets)
     return feats, (mf, ms), out
+
+
+# --------------------------------------------------------------------------
+# Sliding-window task heads (univs/inference/*), loaded by path for the head parity tests
+# --------------------------------------------------------------------------
+_HEADS = None
+
+
+class _RefModel:
+    """What a reference head touches on `model`: .backbone(x) and .sem_seg_head(features, targets=...)
+    (MaskFormerHead.layers glue, mask_former_head.py:148-154)."""
+
+    def __init__(self, bb, pix, dec):
+        self.backbone, self._pix, self._dec = bb, pix, dec
+
+    @torch.no_grad()
+    def sem_seg_head(self, features, targets=None):
+        mf, mf_bfe, _enc0, ms = self._pix.forward_features(features)
+        return self._dec(ms, mf, mf_bfe, None, targets)
+
+
+class _ImageList:
+    def __init__(self, tensor, image_sizes):
+        self.tensor, self.image_sizes = tensor, image_sizes
+
+
+def load_inference_heads():
+    """Imports the reference's inference heads with their heavy imports (kornia, pycocotools, detectron2 structures,
+    the training-side `univs` exports) stubbed; only the inference code paths are exercised."""
+    global _HEADS
+    if _HEADS is not None:
+        return _HEADS
+    load()
+    R = REF_ROOT
+    _mod("kornia", color=types.SimpleNamespace())
+    mu = _mod("pycocotools.mask")
+    _mod("pycocotools", mask=mu)
+    _mod("detectron2.data", MetadataCatalog=types.SimpleNamespace(get=lambda name: types.SimpleNamespace()))
+    _mod("detectron2.modeling.postprocessing", sem_seg_postprocess=None)
+    _mod("detectron2.structures", Boxes=object, ImageList=_ImageList, Instances=object, BitMasks=object)
+    _mod("detectron2.utils.memory", retry_if_cuda_oom=lambda f: f)
+    _pkg("mask2former.utils", f"{R}/mask2former/utils")
+    univs = sys.modules["univs"]
+    for name in ("VideoSetCriterionUni", "VideoHungarianMatcherUni", "BoxVISTeacherSetPseudoMask",
+                 "TextPromptEncoder", "build_clip_language_encoder", "Clips", "FastOverTracker_DET"):
+        setattr(univs, name, object)
+    _mod("univs.prepare_targets", PrepareTargets=object)
+    _pkg("univs.inference", f"{R}/univs/inference")
+    imp = importlib.import_module
+    comm = imp("univs.inference.comm")
+    ucomm = imp("univs.utils.comm")
+    vis_fast = imp("univs.inference.inference_video_vis_fast")
+    _HEADS = types.SimpleNamespace(comm=comm, utils_comm=ucomm, vis_fast=vis_fast,
+                                   InferenceVideoVISFast=vis_fast.InferenceVideoVISFast,
+                                   RefModel=_RefModel, ImageList=_ImageList)
+    return _HEADS

@@ -79,8 +79,11 @@ def get_cfg() -> CfgNode:
                             "ENC_LAYERS": 0, "PRE_NORM": False, "ENFORCE_INPUT_PROJ": False, "SIZE_DIVISIBILITY": 32,
                             "DEC_LAYERS": 10,
                             "TEST": {"SEMANTIC_ON": False, "INSTANCE_ON": True, "PANOPTIC_ON": False,
-                                     "OVERLAP_THRESHOLD": 0.8, "OBJECT_MASK_THRESHOLD": 0.05}},
-            "BoxVIS": {"TEST": {"NUM_FRAMES_WINDOW": 5, "CLIP_STRIDE": 1, "NUM_FRAMES": 3}},
+                                     "OVERLAP_THRESHOLD": 0.8, "OBJECT_MASK_THRESHOLD": 0.05,
+                                     "STABILITY_SCORE_THRESH": 0.0}},
+            "BoxVIS": {"TEST": {"NUM_FRAMES_WINDOW": 5, "CLIP_STRIDE": 1, "NUM_FRAMES": 3, "TRACKER_TYPE": "minvis",
+                                "ZERO_SHOT_INFERENCE": False, "MERGE_ON_CPU": False, "NUM_MAX_INST": 50,
+                                "APPLY_CLS_THRES": 0.05, "MULTI_CLS_ON": True, "WINDOW_INFERENCE": False}},
             "UniVS": {"CLIP_CLASS_EMBED_PATH": "datasets/concept_emb/combined_datasets_cls_emb_rn50x4.pth",
                       "VISUAL_PROMPT_ENCODER": True, "TEXT_PROMPT_ENCODER": True, "PROMPT_AS_QUERIES": True,
                       "TEXT_PROMPT_TO_IMAGE_ENABLE": True, "MASKDEC_SELF_ATTN_MASK_TYPE": "sep",
@@ -91,6 +94,7 @@ def get_cfg() -> CfgNode:
                                "SEMANTIC_EXTRACTION": {"ENABLE": False}}},
         },
         "INPUT": {"SAMPLING_FRAME_NUM": 5, "FORMAT": "RGB", "LSJ_AUG": {"IMAGE_SIZE": 1024, "SQUARE_ENABLED": False}},
+        "TEST": {"DETECTIONS_PER_IMAGE": 100},
     })
 
 

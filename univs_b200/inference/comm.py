@@ -1,0 +1,85 @@
+"""Tracking helpers shared by the sliding-window heads (univs/inference/comm.py:11-58, univs/utils/comm.py:85-88).
+
+Device-first restatements: similarities are one small GEMM on the device, the only host work is the Hungarian
+assignment itself (scipy, as in the reference, comm.py:53-54) on a [N, M] cost matrix copied once."""
+from __future__ import annotations
+
+import math
+
+import torch
+from scipy.optimize import linear_sum_assignment
+
+
+def calculate_mask_quality_scores(mask_logits: torch.Tensor, threshold: float = 1.0) -> torch.Tensor:
+    """Stability score per query (univs/utils/comm.py:85-88): #{logit > thr} / max(#{logit > -thr}, 1) over all
+    trailing dims."""
+    flat = mask_logits.flatten(1)
+    inner = (flat > threshold).sum(-1)
+    outer = (flat > -threshold).sum(-1).clamp(min=1)
+    return inner / outer
+
+
+def generate_temporal_weights(num_frames: int, weights: torch.Tensor | None = None, enable_softmax: bool = False,
+                              scaler: float = 5.0) -> torch.Tensor:
+    """Exponentially increasing weight for later frames, optionally gated per frame, normalised to sum 1
+    (inference/comm.py:11-26)."""
+    w = (torch.arange(1, num_frames + 1, dtype=torch.float32) / num_frames * scaler).exp()
+    if enable_softmax:          # NB: softmax OF the exponentials, as the reference does (:17-19)
+        w = w.softmax(-1)
+    if weights is not None:
+        if weights.shape[-1] != num_frames:
+            raise ValueError("weights must have one entry per frame")
+        w = w.to(weights) * weights
+    return w / w.sum(-1, keepdim=True).clamp(min=1e-3)
+
+
+def _unit(x: torch.Tensor) -> torch.Tensor:
+    return x / x.norm(dim=-1, keepdim=True).clamp(min=1e-3)
+
+
+def match_from_learnable_embds(tgt_embds, cur_embds, return_similarity=False, return_src_indices=False,
+                               use_norm=True, thresh=0):
+    """Hungarian assignment of the current clip's queries to the tracked ones (inference/comm.py:28-58).
+
+    tgt_embds [N, V, C] (memory of V past clips), cur_embds [M, T, C].  use_norm: cosine similarity averaged over the
+    clip frames, memory frames weighted by `generate_temporal_weights` (blank memory rows masked out); otherwise
+    bi-softmax of scaled dot products.  Returns the permutation of current queries aligned to the targets."""
+    V = tgt_embds.shape[1]
+    if use_norm:
+        tgt = _unit(tgt_embds)
+        # mean over the clip frames commutes with the dot product: sim[n,m,v] = <tgt[n,v], mean_t cur[m,t]>
+        cur = _unit(cur_embds).mean(1)
+        w = generate_temporal_weights(V, weights=(tgt != 0).any(-1).float())          # [N, V]
+        sim = torch.einsum("nvc,mc->nmv", tgt, cur)
+        sim = (sim * w.unsqueeze(1)).sum(-1)                                          # [N, M]
+    else:
+        sim = torch.einsum("nvc,mc->nmv", tgt_embds, cur_embds.mean(1)) / math.sqrt(tgt_embds.shape[-1])
+        sim = (sim.softmax(1) + sim.softmax(0)).mean(-1) / 2.0
+        if thresh > 0:
+            sim = sim.masked_fill(sim < thresh, 0.0)
+    rows, cols = linear_sum_assignment((1.0 - sim).cpu().numpy())
+    matched = sim[torch.as_tensor(rows, device=sim.device), torch.as_tensor(cols, device=sim.device)]
+    indices = (rows, cols) if return_src_indices else cols
+    return (indices, matched) if return_similarity else indices
+
+
+class TemporalMaskMean:
+    """Running per-frame mean of overlapping clip masks.
+
+    The reference keeps every clip's [Q, T, h, w] logits and averages at the end
+    (inference_video_vis_fast.py:273-281: frame v is the mean of out_masks[v - t][:, t] over the clips that contain
+    it).  Here the sum is accumulated in place into one [Q, V, h, w] buffer (T x less memory, no second pass)."""
+
+    def __init__(self, num_queries: int, video_len: int, size, device, dtype=torch.float32):
+        self.sum = torch.zeros((num_queries, video_len, *size), device=device, dtype=dtype)
+        self.count = torch.zeros(video_len, device=device, dtype=dtype)
+
+    def add(self, start: int, clip_masks: torch.Tensor):
+        """clip_masks [Q, T, h, w] for frames [start, start + T)."""
+        T = clip_masks.shape[1]
+        self.sum[:, start:start + T] += clip_masks
+        self.count[start:start + T] += 1
+
+    def mean(self, num_frames: int | None = None) -> torch.Tensor:
+        n = self.sum.shape[1] if num_frames is None else num_frames
+        return self.sum[:, :n] / self.count[:n].clamp(min=1).view(1, -1, 1, 1)

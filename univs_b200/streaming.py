@@ -30,6 +30,12 @@ class ClipStream:
     def push(self, first_index: int, frames):
         """Encode frames [first_index, first_index + k) (k >= 1; any k -- a chunk is one backbone / pixel-decoder batch)."""
         x, self.image_size = self.model.preprocess(frames)
+        self.push_preprocessed(first_index, x)
+
+    @torch.no_grad()
+    def push_preprocessed(self, first_index: int, x):
+        """Same for frames that are already normalised and padded ([k,3,Hp,Wp] float32 on the device) -- what the
+        task heads hold after ImageList.from_tensors (inference_video_vis_fast.py:198-207)."""
         feats = self.model.backbone(x)
         mf, _bfe, _enc, ms = self.model.sem_seg_head.pixel_decoder.forward_features(feats)
         for j in range(x.shape[0]):
