@@ -324,6 +324,38 @@ class _ImageList:
         self.tensor, self.image_sizes = tensor, image_sizes
 
 
+class _TensorBox:
+    """detectron2 Boxes / BitMasks: a tensor behind `.tensor`."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+    def to(self, device):
+        return _TensorBox(self.tensor.to(device))
+
+
+class _Instances:
+    """detectron2 Instances as the VOS head reads it (inference_video_vos.py:587-606): image_size, free fields,
+    len() = number of objects, .to(device)."""
+
+    def __init__(self, image_size, **fields):
+        self.image_size = image_size
+        self._fields = dict(fields)
+
+    def __getattr__(self, k):
+        try:
+            return self.__dict__["_fields"][k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __len__(self):
+        return len(self._fields.get("ori_ids", []))
+
+    def to(self, device):
+        return _Instances(self.image_size, **{k: (v.to(device) if hasattr(v, "to") else v)
+                                              for k, v in self._fields.items()})
+
+
 def load_inference_heads():
     """Imports the reference's inference heads with their heavy imports (kornia, pycocotools, detectron2 structures,
     the training-side `univs` exports) stubbed; only the inference code paths are exercised."""
@@ -337,12 +369,13 @@ def load_inference_heads():
     _mod("pycocotools", mask=mu)
     _mod("detectron2.data", MetadataCatalog=types.SimpleNamespace(get=lambda name: types.SimpleNamespace()))
     _mod("detectron2.modeling.postprocessing", sem_seg_postprocess=None)
-    _mod("detectron2.structures", Boxes=object, ImageList=_ImageList, Instances=object, BitMasks=object)
+    _mod("detectron2.structures", Boxes=_TensorBox, ImageList=_ImageList, Instances=_Instances, BitMasks=_TensorBox)
     _mod("detectron2.utils.memory", retry_if_cuda_oom=lambda f: f)
     _pkg("mask2former.utils", f"{R}/mask2former/utils")
     univs = sys.modules["univs"]
     for name in ("VideoSetCriterionUni", "VideoHungarianMatcherUni", "BoxVISTeacherSetPseudoMask",
-                 "TextPromptEncoder", "build_clip_language_encoder", "Clips", "FastOverTracker_DET"):
+                 "TextPromptEncoder", "build_clip_language_encoder", "Clips", "FastOverTracker_DET",
+                 "MDQE_OverTrackerEfficient"):
         setattr(univs, name, object)
     _mod("univs.prepare_targets", PrepareTargets=object)
     _pkg("univs.inference", f"{R}/univs/inference")
@@ -350,7 +383,13 @@ def load_inference_heads():
     comm = imp("univs.inference.comm")
     ucomm = imp("univs.utils.comm")
     vis_fast = imp("univs.inference.inference_video_vis_fast")
-    _HEADS = types.SimpleNamespace(comm=comm, utils_comm=ucomm, vis_fast=vis_fast,
+    _mod("matplotlib"); _mod("matplotlib.pyplot")
+    _mod("univs.inference.visualization", visualization_query_embds=lambda **kw: None)
+    _mod("univs.utils.visualizer", VisualizerFrame=object)
+    vos = imp("univs.inference.inference_video_vos")
+    _HEADS = types.SimpleNamespace(comm=comm, utils_comm=ucomm, vis_fast=vis_fast, vos=vos,
                                    InferenceVideoVISFast=vis_fast.InferenceVideoVISFast,
-                                   RefModel=_RefModel, ImageList=_ImageList)
+                                   InferenceVideoVOS=vos.InferenceVideoVOS,
+                                   RefModel=_RefModel, ImageList=_ImageList, Instances=_Instances,
+                                   BitMasks=_TensorBox, Boxes=_TensorBox)
     return _HEADS

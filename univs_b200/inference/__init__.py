@@ -1,8 +1,10 @@
 """Sliding-window task heads over the hot path (callers of `model.backbone` / `model.sem_seg_head`,
 univs/inference/*).  Built on `ClipStream`: every frame is encoded once."""
-from .comm import (calculate_mask_quality_scores, generate_temporal_weights, match_from_learnable_embds,
-                   TemporalMaskMean)
+from .comm import (TemporalMaskMean, calculate_mask_quality_scores, check_consistency_with_prev_frames,
+                   generate_temporal_weights, match_from_learnable_embds, pair_mask_iou, video_box_iou)
 from .video_vis_fast import InferenceVideoVISFast
+from .video_vos import FrameAnnotations, InferenceVideoVOS
 
-__all__ = ["InferenceVideoVISFast", "match_from_learnable_embds", "generate_temporal_weights",
-           "calculate_mask_quality_scores", "TemporalMaskMean"]
+__all__ = ["InferenceVideoVISFast", "InferenceVideoVOS", "FrameAnnotations", "match_from_learnable_embds",
+           "check_consistency_with_prev_frames", "generate_temporal_weights", "calculate_mask_quality_scores",
+           "video_box_iou", "pair_mask_iou", "TemporalMaskMean"]

@@ -83,3 +83,38 @@ class TemporalMaskMean:
     def mean(self, num_frames: int | None = None) -> torch.Tensor:
         n = self.sum.shape[1] if num_frames is None else num_frames
         return self.sum[:, :n] / self.count[:n].clamp(min=1).view(1, -1, 1, 1)
+
+
+def check_consistency_with_prev_frames(prev_embds, cur_embds, sim_threshold=0.5, return_similarity=False,
+                                       use_norm=True):
+    """Row-wise (object i against itself) temporal consistency of prompt-query embeddings (inference/comm.py:64-95).
+    prev_embds [N, V, C] memory, cur_embds [N, T, C] current clip."""
+    if use_norm:
+        prev = _unit(prev_embds)
+        cur = _unit(cur_embds).mean(1)                                    # mean over clip frames commutes
+        w = generate_temporal_weights(prev.shape[1], weights=(prev != 0).any(-1).float())
+        sim = ((prev * cur.unsqueeze(1)).sum(-1) * w).sum(-1)             # [N]
+        ok = sim > sim_threshold
+    else:
+        pair = prev_embds[:, -3:].mean(1) @ cur_embds.mean(1).t()
+        pair = 0.5 * (pair.softmax(0) + pair.softmax(1))
+        ok = pair.argmax(-1) == torch.arange(pair.shape[0], device=pair.device)
+        sim = pair.diagonal()
+        ok = ok | (sim > 0.25)
+    return (ok, sim) if return_similarity else ok
+
+
+def video_box_iou(boxes1, boxes2):
+    """Per-frame IoU of XYXY boxes: [N, T, 4] x [M, T, 4] -> [N, M, T] (univs/utils/comm.py:137-158)."""
+    area = lambda b: (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+    lt = torch.maximum(boxes1[:, None, :, :2], boxes2[None, :, :, :2])
+    rb = torch.minimum(boxes1[:, None, :, 2:], boxes2[None, :, :, 2:])
+    inter = (rb - lt).clamp(min=0).prod(-1)
+    union = (area(boxes1)[:, None] + area(boxes2)[None] - inter).clamp(min=1e-3)
+    return inter / union
+
+
+def pair_mask_iou(masks1, masks2):
+    """IoU of corresponding binary masks [..., H, W] -> [...] (univs/utils/comm.py:213-227)."""
+    a, b = masks1.flatten(-2) > 0.5, masks2.flatten(-2) > 0.5
+    return (a & b).sum(-1) / (a | b).sum(-1).clamp(min=1)

@@ -45,9 +45,11 @@ class ClipStream:
             self._cache.popitem(last=False)
 
     @torch.no_grad()
-    def clip(self, start: int, targets):
-        """Decoder output for frames [start, start + T); every frame must have been pushed."""
-        idx = range(start, start + self.T)
+    def clip(self, start: int, targets, length: int | None = None):
+        """Decoder output for frames [start, start + T) (or a shorter last clip of `length` frames); every frame must
+        have been pushed."""
+        n = self.T if length is None else length
+        idx = range(start, start + n)
         missing = [i for i in idx if i not in self._cache]
         if missing:
             raise KeyError(f"frames {missing} are not cached (push them first / raise max_cached_frames)")
@@ -56,7 +58,7 @@ class ClipStream:
         # keep the channel-last storage the decoder consumes without a copy
         mf = mf.contiguous(memory_format=torch.channels_last)
         tg = targets[0]
-        tg["frame_indices"] = torch.arange(start, start + self.T, device=mf.device)
+        tg["frame_indices"] = torch.arange(start, start + n, device=mf.device)
         tg.setdefault("num_frames", self.T)
         return self.model.sem_seg_head.predictor(ms, mf, mf, None, targets)
 
