@@ -139,6 +139,39 @@ int univs_gelu_f32(void* stream, const float* x, const float* bias, int64_t rows
 int univs_relu_f32(void* stream, const float* x, const float* bias, int64_t rows, int channels, float* out, int split);
 int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, int chunk, float* out);
 
+/* ---- channel-last GroupNorm fused with the FPN glue of the pixel decoder (detectron2 Conv2d = conv -> GroupNorm ->
+ * [ReLU], msdeformattn.py:218-221, :249-283; top-down add of the bilinearly upsampled coarser level, :345-354).
+ * x is addressed as x[n*img_stride + y*row_stride + xw*channels + c] (elements), so it may be the convolution output
+ * inside a spatially padded row buffer.  stats: mean_rstd [frames, groups, 2] f32 = (mean, 1/sqrt(var + eps)) per frame
+ * and group (biased variance, as nn.GroupNorm); workspace >= univs_groupnorm_workspace_bytes(...) bytes of device scratch.
+ * apply: y = (x - mean) * rstd * gamma + beta  [+ bilinear resize of lowres [frames, low_height, low_width, channels] (frame n at
+ * lowres + n*lowres_img_stride) to (height, width), align_corners = False]  [ReLU if relu != 0], written to out_f32 [frames, height, width, channels]
+ * (nullable) and / or to out_split (nullable) in the operand format `split` (see above) at the zero-padded position
+ * (y + pad, xw + pad) of a [frames, height + 2*pad, width + 2*pad, .] token matrix whose border the caller keeps zero.
+ * Requirements: channels % groups == 0, (channels / groups) % 4 == 0, 256 % (channels / 4) == 0. */
+int64_t univs_groupnorm_workspace_bytes(int frames, int height, int width, int groups);
+int univs_groupnorm_stats_f32(void* stream, const float* x, int frames, int height, int width, int channels,
+                              int64_t img_stride, int64_t row_stride, int groups, float eps, void* workspace,
+                              float* mean_rstd);
+int univs_groupnorm_apply_f32(void* stream, const float* x, int frames, int height, int width, int channels,
+                              int64_t img_stride, int64_t row_stride, const float* mean_rstd, const float* gamma,
+                              const float* beta, int groups, const float* lowres, int64_t lowres_img_stride, int low_height,
+                              int low_width, int relu, float* out_f32, void* out_split, int split, int pad);
+
+/* ---- gather-fused kernels at the edges of the Swin stages ------------------------------------------------------
+ * patchify_normalize: frames [num_frames, 3, height, width] (uint8 if is_uint8 else f32, values 0..255) -> the patch
+ *   matrix [num_frames * (padded_height/4) * (padded_width/4), 48] (column = c*16 + ky*4 + kx, the flattening of the
+ *   PatchEmbed.proj weight [E,3,4,4], swin.py:456-495) of the normalised ((x - mean[c]) / std[c], univs_prompt.py:165-168)
+ *   and zero-padded frames, plain f32 or in the operand format `split`.  mean3 / std3 are HOST arrays of 3 floats.
+ * layernorm_merge2x2: PatchMerging (swin.py:298-337) without the concatenated copy: x [num_frames, height, width,
+ *   channels] -> LayerNorm over [x(2i,2j) | x(2i+1,2j) | x(2i,2j+1) | x(2i+1,2j+1)] (zeros beyond odd borders),
+ *   out [num_frames * ceil(height/2) * ceil(width/2), 4*channels] plain or split.  4*channels <= 4096. */
+int univs_patchify_normalize(void* stream, const void* frames, int is_uint8, int num_frames, int height, int width,
+                             int padded_height, int padded_width, int patch, const float* mean3, const float* std3,
+                             float* out, int split);
+int univs_layernorm_merge2x2_f32(void* stream, const float* x, int num_frames, int height, int width, int channels,
+                                 const float* gamma, const float* beta, float eps, float* out, int split);
+
 /* ---- helpers ---- */
 /* in-place/out-of-place round-to-nearest-even to TF32 (19-bit) of n floats */
 int univs_round_tf32_f32(void* stream, const float* in, float* out, int64_t n);

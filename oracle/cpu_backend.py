@@ -96,7 +96,26 @@ def _layernorm(x, weight, bias, eps=1e-5, residual=None, want_sum=False, split=N
     return (s if want_sum else None), _maybe_split(y, split)
 
 
+def _groupnorm_cl(x, weight, bias, groups, eps=1e-5, lowres=None, relu=False, want_f32=True, split=None, pad=0,
+                  out_split=None):
+    y = ops_ref.groupnorm_cl(x, weight, bias, groups, eps, lowres, relu)
+    op = None
+    if split:
+        op = _maybe_split(y, split)
+        if pad:
+            op = torch.nn.functional.pad(op, (0, 0, pad, pad, pad, pad))
+        if out_split is not None:
+            out_split.copy_(op)
+            op = out_split
+    return (y if want_f32 else None), op
+
+
 _PATCH = {"layernorm": _layernorm,
+          "groupnorm_cl": _groupnorm_cl,
+          "patchify_normalize": lambda f, m, s, padded, patch=4, split=None: _maybe_split(
+              ops_ref.patchify_normalize(f, m, s, padded, patch), split),
+          "layernorm_merge2x2": lambda x, w, b, eps=1e-5, split=None: _maybe_split(
+              ops_ref.layernorm_merge2x2(x, w, b, eps), split),
           "swin_window_attention_operand": lambda q, b, t, nh, ws, sh: _split16(_swin(q, b, t, nh, ws, sh), True),
           "gelu": lambda x, split=None, bias=None: _maybe_split(torch.nn.functional.gelu(x if bias is None else x + bias), split),
           "relu": lambda x, split=None, bias=None: _maybe_split(torch.relu(x if bias is None else x + bias), split),

@@ -254,3 +254,43 @@ def layernorm(x, weight, bias, eps=1e-5, residual=None, residual_bias=None):
 def gelu(x, bias=None):
     """nn.GELU() default = exact erf form (swin.py:24-41), applied to x + bias."""
     return F.gelu((x if bias is None else x + bias).double()).float()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Fused glue around the library GEMMs (csrc/groupnorm.cu, csrc/swin_glue.cu): the reference's own op sequences
+# --------------------------------------------------------------------------------------------------------------
+def groupnorm_cl(x_cl, weight, bias, groups, eps=1e-5, lowres_cl=None, relu=False):
+    """detectron2 Conv2d tail on channel-last data: GroupNorm (msdeformattn.py:218-221, :249-283) [+ the top-down add
+    of the bilinearly upsampled coarser level, :345-354: F.interpolate(..., mode="bilinear", align_corners=False)]
+    [+ ReLU].  x_cl [N,H,W,C], lowres_cl [N,h2,w2,C] -> [N,H,W,C]."""
+    x = x_cl.permute(0, 3, 1, 2)
+    y = torch.nn.functional.group_norm(x, groups, weight, bias, eps)
+    if lowres_cl is not None:
+        y = y + torch.nn.functional.interpolate(lowres_cl.permute(0, 3, 1, 2), size=x.shape[-2:], mode="bilinear",
+                                                align_corners=False)
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def patchify_normalize(frames, pixel_mean, pixel_std, padded_size, patch=4):
+    """(x - mean) / std (univs_prompt.py:165-168), zero pad right / bottom (ImageList.from_tensors), then the im2col of
+    the stride-`patch` PatchEmbed convolution (swin.py:456-495): [N,3,H,W] -> [N, Hp/p, Wp/p, 3*p*p], column order
+    (c, ky, kx) = proj.weight.view(E, -1)."""
+    mean = torch.as_tensor(pixel_mean, dtype=torch.float32).view(1, 3, 1, 1)
+    std = torch.as_tensor(pixel_std, dtype=torch.float32).view(1, 3, 1, 1)
+    x = (frames.float() - mean) / std
+    N, _, H, W = x.shape
+    Hp, Wp = padded_size
+    x = torch.nn.functional.pad(x, (0, Wp - W, 0, Hp - H))
+    cols = torch.nn.functional.unfold(x, kernel_size=patch, stride=patch)          # [N, 3*p*p, L]
+    return cols.transpose(1, 2).reshape(N, Hp // patch, Wp // patch, 3 * patch * patch).contiguous()
+
+
+def layernorm_merge2x2(x_cl, weight, bias, eps=1e-5):
+    """PatchMerging up to the reduction linear (swin.py:312-335): pad odd sizes, concatenate the 2x2 neighbours in the
+    order x0, x1, x2, x3 = (0,0), (1,0), (0,1), (1,1), LayerNorm(4C)."""
+    N, H, W, C = x_cl.shape
+    x = torch.nn.functional.pad(x_cl, (0, 0, 0, W % 2, 0, H % 2))
+    x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
+    return torch.nn.functional.layer_norm(x, (4 * C,), weight, bias, eps)

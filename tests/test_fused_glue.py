@@ -1,0 +1,186 @@
+"""Opt-in fused glue path (nn_ops.set_fused_glue: channel-last GroupNorm + FPN add / ReLU / operand emission,
+PatchMerging gather-LayerNorm, fused frame ingest).  CPU: the host plumbing with oracle operators must reproduce the
+default path (which the reference-parity tests pin); GPU op tests are opt-in (UNIVS_GPU_GLUE=1) until validated."""
+import os
+
+import pytest
+import torch
+
+from oracle import ops_ref
+from oracle.cpu_backend import oracle_ops
+from tests import model_factory as mf
+from univs_b200 import nn_ops
+from univs_b200.meta_arch import UniVS_Prompt
+from univs_b200.modeling.head import MaskFormerHead
+from univs_b200.registry import ShapeSpec
+
+MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+
+
+def _model(T=2, Q=6):
+    parts = mf.build_product_model(mf.TINY_SWIN, num_queries=Q, num_frames=T, clip_emb=mf.make_clip_emb(),
+                                   enc_layers=1, dec_layers=2)
+    mf.load_keyed(parts)
+    shapes = {f"res{i + 2}": ShapeSpec(channels=32 * 2 ** i, stride=4 * 2 ** i) for i in range(4)}
+    head = MaskFormerHead(shapes, num_classes=133, pixel_decoder=parts[1], transformer_predictor=parts[2])
+    return UniVS_Prompt(backbone=parts[0], sem_seg_head=head, pixel_mean=MEAN, pixel_std=STD)
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("policy", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("size", [(60, 90), (64, 96), (50, 70)])
+def test_fused_glue_host_path_equals_default(policy, size):
+    T = 2
+    model = _model(T)
+    g = torch.Generator().manual_seed(4)
+    frames = (torch.rand(T, 3, *size, generator=g) * 255).round()
+    tg = lambda: [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual"}]
+    outs = {}
+    for fused in (False, True):
+        nn_ops.set_fused_glue(fused)
+        try:
+            with oracle_ops(policy):
+                x, _ = model.preprocess(frames)
+                feats = model.backbone(x) if not fused else model.backbone_from_frames(frames)
+                mfeat, _bfe, _enc, ms = model.sem_seg_head.pixel_decoder.forward_features(feats)
+                out = model.clip_forward(frames, tg())
+            outs[fused] = (feats, mfeat, ms, out)
+        finally:
+            nn_ops.set_fused_glue(False)
+    (f0, m0, s0, o0), (f1, m1, s1, o1) = outs[False], outs[True]
+    for k in f0:
+        assert f1[k].shape == f0[k].shape and _rel(f1[k], f0[k]) < 2e-5, k
+    assert m1.shape == m0.shape and _rel(m1, m0) < 2e-5
+    for a, b in zip(s1, s0):
+        assert _rel(a, b) < 2e-5
+    for k in ("pred_masks", "pred_logits", "pred_embds"):
+        assert _rel(o1[k], o0[k]) < 1e-4, k
+
+
+def test_clip_stream_with_fused_glue():
+    from univs_b200.streaming import ClipStream
+    T, V = 2, 3
+    model = _model(T)
+    g = torch.Generator().manual_seed(8)
+    video = (torch.rand(V, 3, 60, 90, generator=g) * 255).round()
+    mk = lambda s: [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual"}]
+    res = {}
+    for fused in (False, True):
+        nn_ops.set_fused_glue(fused)
+        try:
+            with oracle_ops():
+                res[fused] = {s: o["pred_masks"].clone() for s, o in ClipStream(model, T).run(video, mk)}
+        finally:
+            nn_ops.set_fused_glue(False)
+    for s in res[False]:
+        assert _rel(res[True][s], res[False][s]) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA kernels against the oracle (opt-in until validated on a B200: UNIVS_GPU_GLUE=1)
+# ---------------------------------------------------------------------------------------------------------------
+_gpu_glue = pytest.mark.skipif(os.environ.get("UNIVS_GPU_GLUE") != "1",
+                               reason="fused glue kernels on CUDA: opt-in until validated on a B200 (UNIVS_GPU_GLUE=1)")
+
+
+def _unsplit(op, fmt, C):
+    """GEMM operand -> the fp32 value it represents (hi + lo)."""
+    from univs_b200.ops import f16_chunk
+    if fmt == "tf32":
+        v = op.float().view(*op.shape[:-1], 1, 2, C)
+        return (v[..., 0, 0, :] + v[..., 0, 1, :])
+    if fmt == "f16u":
+        return op[..., :C].float() + op[..., C:].float()
+    kc = f16_chunk(C)
+    v = op.float().view(*op.shape[:-1], C // kc, 3, kc)
+    return (v[..., 2, :] + v[..., 0, :] * 2.0 ** -11).reshape(*op.shape[:-1], C)
+
+
+@pytest.mark.gpu
+@_gpu_glue
+@pytest.mark.parametrize("N,H,W,C,groups", [(2, 23, 37, 256, 32), (1, 184, 320, 256, 32), (3, 8, 12, 64, 8)])
+@pytest.mark.parametrize("fmt", [None, "tf32", "f16", "f16u"])
+def test_groupnorm_cl_cuda(N, H, W, C, groups, fmt):
+    from univs_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    pad = 1
+    # x as a [:, :H, :W] view of a padded convolution output buffer; lowres as a level slice of a token matrix
+    buf = torch.randn(N, H + 2, W + 2, C, generator=g) * 2 + 0.5
+    h2, w2 = (H + 1) // 2, (W + 1) // 2
+    tokens = torch.randn(N, 7 + h2 * w2, C, generator=g)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    want = ops_ref.groupnorm_cl(buf[:, :H, :W], gamma, beta, groups, 1e-5, tokens[:, 7:].reshape(N, h2, w2, C), relu=True)
+    d = "cuda"
+    bufd, tokd = buf.to(d), tokens.to(d)
+    y, op = ops.groupnorm_cl(bufd[:, :H, :W], gamma.to(d), beta.to(d), groups, 1e-5,
+                             lowres=tokd[:, 7:].reshape(N, h2, w2, C), relu=True, want_f32=True, split=fmt,
+                             pad=pad if fmt else 0)
+    assert _rel(y.cpu(), want) < 2e-5
+    if fmt:
+        assert op.shape[1:3] == (H + 2 * pad, W + 2 * pad)
+        border = op.clone()
+        border[:, pad:-pad, pad:-pad] = 0
+        assert not border.any()                                   # the zero border is never written
+        got = _unsplit(op[:, pad:-pad, pad:-pad], fmt, C).cpu()
+        assert _rel(got, want) < (2e-5 if fmt != "f16u" else 1e-4)
+    # plain GroupNorm (no top-down add, no ReLU), contiguous input
+    y2, _ = ops.groupnorm_cl(bufd[:, :H, :W].contiguous(), gamma.to(d), beta.to(d), groups)
+    assert _rel(y2.cpu(), ops_ref.groupnorm_cl(buf[:, :H, :W], gamma, beta, groups)) < 2e-5
+
+
+@pytest.mark.gpu
+@_gpu_glue
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+@pytest.mark.parametrize("H,W", [(720, 1280), (61, 95), (64, 96)])
+def test_patchify_normalize_cuda(dtype, H, W):
+    from univs_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    frames = (torch.rand(2, 3, H, W, generator=g) * 255).round().to(dtype)
+    padded = ((H + 31) // 32 * 32, (W + 31) // 32 * 32)
+    want = ops_ref.patchify_normalize(frames, MEAN, STD, padded)
+    got = ops.patchify_normalize(frames.cuda(), MEAN, STD, padded)
+    assert got.shape == want.shape
+    assert (got.cpu() - want).abs().max().item() <= 1e-6
+    op = ops.patchify_normalize(frames.cuda(), MEAN, STD, padded, split="f16")
+    assert _rel(_unsplit(op, "f16", 48).cpu(), want) < 1e-6
+
+
+@pytest.mark.gpu
+@_gpu_glue
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 24, 32), (1, 23, 41, 192), (5, 46, 80, 768)])
+@pytest.mark.parametrize("fmt", [None, "f16"])
+def test_layernorm_merge2x2_cuda(N, H, W, C, fmt):
+    from univs_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(N, H, W, C, generator=g) * 3 + 1
+    gamma, beta = torch.randn(4 * C, generator=g), torch.randn(4 * C, generator=g)
+    want = ops_ref.layernorm_merge2x2(x, gamma, beta)
+    got = ops.layernorm_merge2x2(x.cuda(), gamma.cuda(), beta.cuda(), split=fmt)
+    got = _unsplit(got, fmt, 4 * C) if fmt else got
+    assert got.shape == want.shape and _rel(got.cpu(), want) < 2e-5
+
+
+@pytest.mark.gpu
+@_gpu_glue
+@pytest.mark.parametrize("policy", ["fp16x3", "tf32x3", "fp32"])
+def test_fused_glue_model_cuda_equals_default(policy):
+    from univs_b200 import precision
+    T = 2
+    model = _model(T).cuda()
+    g = torch.Generator().manual_seed(4)
+    frames = (torch.rand(T, 3, 60, 90, generator=g) * 255).round()
+    tg = lambda: [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual"}]
+    precision.set_precision(policy)
+    try:
+        outs = {}
+        for fused in (False, True):
+            nn_ops.set_fused_glue(fused)
+            outs[fused] = model.clip_forward(frames.to(torch.uint8 if fused else torch.float32).cuda(), tg())
+        for k in ("pred_masks", "pred_logits", "pred_embds"):
+            assert _rel(outs[True][k].cpu(), outs[False][k].cpu()) < 1e-3, k
+    finally:
+        nn_ops.set_fused_glue(False)
+        precision.set_precision("fp32")

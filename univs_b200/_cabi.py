@@ -30,6 +30,13 @@ SIGNATURES = {
     "univs_relu_f32": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i]),
     "univs_split_tf32_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "univs_round_tf32_f32": (_i, [_vp, _vp, _vp, _i64]),
+    "univs_groupnorm_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "univs_groupnorm_stats_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _i, C.c_float, _vp, _vp]),
+    "univs_groupnorm_apply_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp, _vp, _vp, _i, _vp, _i64, _i, _i, _i, _vp,
+                                       _vp, _i, _i]),
+    "univs_patchify_normalize": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      _vp, _i]),
+    "univs_layernorm_merge2x2_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_float, _vp, _i]),
 }
 
 _lib = None

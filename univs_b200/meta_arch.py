@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import nn_ops
 from .registry import META_ARCH_REGISTRY, build_backbone, build_sem_seg_head
 from .sharding import FrameSharder
 
@@ -62,32 +63,58 @@ class UniVS_Prompt(nn.Module):
             x = F.pad(x, (0, Wp - W, 0, Hp - H), value=0.0)
         return x, (H, W)
 
+    def _padded_size(self, H, W):
+        d = self.size_divisibility
+        return (H + d - 1) // d * d, (W + d - 1) // d * d
+
+    @torch.no_grad()
+    def backbone_from_frames(self, frames):
+        """backbone(preprocess(frames)) with the ingest fused into the patch embedding (nn_ops.fused_glue() path)."""
+        if isinstance(frames, (list, tuple)):
+            frames = torch.stack([f.to(self.device, non_blocking=True) for f in frames])
+        else:
+            frames = frames.to(self.device, non_blocking=True)
+        if frames.dtype not in (torch.uint8, torch.float32):
+            frames = frames.float()
+        H, W = frames.shape[-2:]
+        return self.backbone.forward_frames(frames.contiguous(), self.pixel_mean.flatten().tolist(),
+                                            self.pixel_std.flatten().tolist(), self._padded_size(H, W))
+
     @torch.no_grad()
     def clip_forward(self, frames, targets):
         """One clip through the hot path.  frames [T,3,H,W] (any device / dtype), targets list[dict] (mutated in
         place by the prompt sampler, as in the reference)."""
-        x, image_size = self.preprocess(frames)
-        targets[0].setdefault("inter_image_size", tuple(x.shape[-2:]))
+        fused = nn_ops.fused_glue() and hasattr(self.backbone, "forward_frames")
+        if fused:       # ingest (cast, normalise, pad, patchify) happens inside the patch embedding
+            if isinstance(frames, (list, tuple)):
+                frames = torch.stack([f.to(self.device, non_blocking=True) for f in frames])
+            x = None
+            T, image_size = frames.shape[0], tuple(frames.shape[-2:])
+            padded = self._padded_size(*image_size)
+        else:
+            x, image_size = self.preprocess(frames)
+            T, padded = x.shape[0], tuple(x.shape[-2:])
+        targets[0].setdefault("inter_image_size", padded)
         targets[0].setdefault("image_size", image_size)
-        targets[0].setdefault("num_frames", x.shape[0])
+        targets[0].setdefault("num_frames", T)
         if "frame_indices" in targets[0]:
             targets[0]["frame_indices"] = targets[0]["frame_indices"].to(self.device)
         if self.sharder.world_size == 1:
-            features = self.backbone(x)
+            features = self.backbone_from_frames(frames) if fused else self.backbone(x)
             return self.sem_seg_head(features, targets=targets)
         # frame-sharded: local frames -> backbone -> pixel decoder -> all-gather -> decoder
-        local = self.sharder.local_frames(x)
+        local = self.sharder.local_frames(frames if fused else x)
         pd = self.sem_seg_head.pixel_decoder
         if local.shape[0] > 0:
-            features = self.backbone(local)
+            features = self.backbone_from_frames(local) if fused else self.backbone(local)
             mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(features)
             parts = [t.permute(0, 2, 3, 1) for t in [mask_features] + list(multi_scale)]
         else:   # more ranks than frames: this rank owns nothing and only takes part in the exchange
-            Hp, Wp = x.shape[-2:]
-            parts = [x.new_zeros((0, Hp // s, Wp // s, c)) for s, c in
+            Hp, Wp = padded
+            parts = [torch.zeros((0, Hp // s, Wp // s, c), device=self.device) for s, c in
                      [(4, pd.mask_dim), (32, pd.conv_dim), (16, pd.conv_dim), (8, pd.conv_dim)]]
         # exchange in storage order (channel-last), hand NCHW views back to the decoder
-        gathered = self.sharder.all_gather_frames(parts, x.shape[0])
+        gathered = self.sharder.all_gather_frames(parts, T)
         gathered = [t.permute(0, 3, 1, 2) for t in gathered]
         mask_features, multi_scale = gathered[0], gathered[1:]
         return self.sem_seg_head.predictor(multi_scale, mask_features, mask_features, None, targets)

@@ -87,6 +87,8 @@ class _PatchMerging(nn.Module):
 
     def forward(self, x):                      # [N,H,W,C] -> [N,ceil(H/2),ceil(W/2),2C]
         N, H, W, C = x.shape
+        if nn_ops.fused_glue() and 4 * C <= 4096:       # gather + LayerNorm in one kernel, no concatenated copy
+            return nn_ops.linear_prepped(nn_ops.layernorm_merge2x2(x, self.norm), self.reduction.weight, None)
         if H % 2 or W % 2:
             x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
         x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
@@ -132,6 +134,16 @@ class _PatchEmbed(nn.Module):
             x = self.proj(x).permute(0, 2, 3, 1).contiguous()
         return nn_ops.layernorm(x, self.norm, for_gemm=False)[1] if self.norm is not None else x
 
+    def forward_frames(self, frames, pixel_mean, pixel_std, padded_size):
+        """Fused ingest (csrc/swin_glue.cu): raw frames [N,3,H,W] uint8 / float32 -> normalise, zero-pad to
+        `padded_size` and gather 4x4 patches in one pass; the patch projection is then one GEMM (weight.view(E, 48))."""
+        p = self.patch
+        Hp, Wp = padded_size
+        padded = ((Hp + p - 1) // p * p, (Wp + p - 1) // p * p)
+        rows = nn_ops.patchify(frames, pixel_mean, pixel_std, padded, p)
+        x = nn_ops.linear_prepped(rows, self.proj.weight.view(self.proj.out_channels, -1), self.proj.bias)
+        return nn_ops.layernorm(x, self.norm, for_gemm=False)[1] if self.norm is not None else x
+
 
 class SwinTransformer(nn.Module):
     def __init__(self, pretrain_img_size=224, patch_size=4, in_chans=3, embed_dim=96, depths=(2, 2, 6, 2),
@@ -157,8 +169,17 @@ class SwinTransformer(nn.Module):
         self.eval()
 
     @torch.no_grad()
+    def forward_frames(self, frames, pixel_mean, pixel_std, padded_size):
+        """Same as forward((frames - mean) / std zero-padded to padded_size) without materialising that tensor."""
+        if self.patch_embed.patch != 4:
+            raise NotImplementedError("fused ingest is built for the 4x4 patch embedding")
+        return self._stages(self.patch_embed.forward_frames(frames, pixel_mean, pixel_std, padded_size))
+
+    @torch.no_grad()
     def forward(self, x):
-        x = self.patch_embed(x)
+        return self._stages(self.patch_embed(x))
+
+    def _stages(self, x):
         outs = {}
         for i, stage in enumerate(self.layers):
             y, x = stage(x, getattr(self, f"norm{i}") if i in self.out_indices else None)

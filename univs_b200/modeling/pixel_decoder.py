@@ -196,7 +196,10 @@ class MSDeformAttnPixelDecoder(nn.Module):
             xt = (xt if xt.is_contiguous() else xt.contiguous()).view(n, h * w, cin)
             conv, gn = self.input_proj[idx][0], self.input_proj[idx][1]
             y = nn_ops.linear(xt, conv.weight.view(conv.out_channels, cin), conv.bias)     # 1x1 conv
-            y = gn(y.transpose(1, 2)).transpose(1, 2)                        # GroupNorm(32) per frame
+            if nn_ops.fused_glue():                                          # channel-last GroupNorm, one pass
+                y = nn_ops.groupnorm_cl(y.view(n, h, w, -1), gn)[0].view(n, h * w, -1)
+            else:
+                y = gn(y.transpose(1, 2)).transpose(1, 2)                    # GroupNorm(32) per frame
             shapes.append((h, w))
             tokens.append(y)                                                 # [N,hw,C]
             poss.append(position.sine_2d(h, w, y.device, y.shape[-1] // 2) + self.transformer.level_embed[idx])
@@ -211,13 +214,41 @@ class MSDeformAttnPixelDecoder(nn.Module):
         out_cl = []
         for i, (h, w) in enumerate(shapes):
             out_cl.append(src[:, starts[i]:starts[i] + h * w].reshape(n, h, w, -1))     # channel-last [N,h,w,C]
+        fused = nn_ops.fused_glue() and all(c.norm is not None for c in self.lateral_convs + self.output_convs)
+        last_operand = None
         for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
             x = features[f].float().permute(0, 2, 3, 1)
             x = x if x.is_contiguous() else x.contiguous()
+            if fused:
+                y, last_operand = self._fpn_level_fused(idx, x, out_cl[-1], idx == self.num_fpn_levels - 1)
+                out_cl.append(y)
+                continue
             cur = self.lateral_convs[idx].forward_cl(x)
             up = F.interpolate(out_cl[-1].permute(0, 3, 1, 2), size=cur.shape[1:3], mode="bilinear", align_corners=False)
             out_cl.append(self.output_convs[idx].forward_cl(cur + up.permute(0, 2, 3, 1)))
         out = [o.permute(0, 3, 1, 2) for o in out_cl]                       # NCHW views of channel-last storage
         multi_scale = out[:self.maskformer_num_feature_levels]
-        mask_features = self.mask_features.forward_cl(out_cl[-1]).permute(0, 3, 1, 2)
+        if last_operand is not None:      # the last GroupNorm already emitted the operand of the 1x1 mask-feature conv
+            mf = self.mask_features
+            mask_features = nn_ops.linear_prepped(last_operand, mf.weight.view(mf.out_channels, -1), mf.bias)
+            mask_features = mask_features.permute(0, 3, 1, 2)
+        else:
+            mask_features = self.mask_features.forward_cl(out_cl[-1]).permute(0, 3, 1, 2)
         return mask_features, out[-1], out[0], multi_scale
+
+    def _fpn_level_fused(self, idx, x_cl, coarser_cl, emit_operand):
+        """One top-down FPN level (msdeformattn.py:345-354) with the GroupNorm glue fused (csrc/groupnorm.cu):
+        lateral 1x1 GEMM -> [stats] -> GN + bilinear(coarser) add, written straight as the zero-padded operand of the 3x3
+        convolution -> nine tap GEMMs -> [stats] -> GN + ReLU -> fp32 level output (+ the operand of the mask-feature conv)."""
+        lat, outc = self.lateral_convs[idx], self.output_convs[idx]
+        N, H, W, Cin = x_cl.shape
+        cur = nn_ops.linear(x_cl, lat.weight.view(lat.out_channels, Cin), lat.bias)          # [N,H,W,C] fp32
+        if nn_ops.splitting():
+            _, operand = nn_ops.groupnorm_cl(cur, lat.norm, lowres=coarser_cl, want_f32=False, for_gemm=True,
+                                             pad=outc.padding[0])
+            y = nn_ops.conv2d_cl_operand(operand, H, W, outc.weight, outc.bias)               # view of the padded rows
+        else:
+            summed, _ = nn_ops.groupnorm_cl(cur, lat.norm, lowres=coarser_cl)
+            y = nn_ops.conv2d_cl(summed, outc.weight, outc.bias, padding=outc.padding)
+            y = y if (y.stride(3) == 1 and y.stride(2) == y.shape[3]) else y.contiguous()
+        return nn_ops.groupnorm_cl(y, outc.norm, relu=True, for_gemm=emit_operand)

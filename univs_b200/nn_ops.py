@@ -9,6 +9,7 @@ Policy "tf32": plain operands, single TF32 GEMM.  Policy "fp32": plain operands,
 from __future__ import annotations
 
 import contextlib
+import os
 
 import torch
 import torch.nn.functional as F
@@ -17,6 +18,19 @@ from . import ops
 
 _policy = "fp32"
 _wcache = {}
+# Fused glue kernels (channel-last GroupNorm + FPN add / ReLU / operand emission, PatchMerging gather-LayerNorm, fused
+# frame ingest; csrc/groupnorm.cu, csrc/swin_glue.cu).  Written at the end of round 1 without GPU time left to validate
+# them, hence opt-in (UNIVS_FUSED_GLUE=1 or set_fused_glue(True)); the default path is the one measured in round 1.
+_fused_glue = os.environ.get("UNIVS_FUSED_GLUE", "0") == "1"
+
+
+def set_fused_glue(on: bool):
+    global _fused_glue
+    _fused_glue = bool(on)
+
+
+def fused_glue() -> bool:
+    return _fused_glue
 
 
 def set_policy(p: str):
@@ -119,6 +133,17 @@ def layernorm(x, norm, residual=None, want_sum=False, for_gemm=True, residual_bi
                          residual_bias)
 
 
+def layernorm_merge2x2(x_cl, norm):
+    """PatchMerging gather + LayerNorm (ops.layernorm_merge2x2), emitted as the operand of the reduction GEMM."""
+    return ops.layernorm_merge2x2(x_cl if x_cl.is_contiguous() else x_cl.contiguous(), norm.weight, norm.bias, norm.eps,
+                                  _fmt())
+
+
+def patchify(frames, pixel_mean, pixel_std, padded_size, patch):
+    """Frame ingest: normalise + zero-pad + 4x4 patch gather in one pass, emitted as the operand of the patch-embedding GEMM."""
+    return ops.patchify_normalize(frames, pixel_mean, pixel_std, padded_size, patch, _fmt())
+
+
 def gelu(x, for_gemm=True, bias=None):
     return ops.gelu(x.contiguous(), _fmt() if for_gemm else None, bias)
 
@@ -170,6 +195,32 @@ def linear(x, weight, bias=None, cache=True):
     return linear_prepped(prep(x), weight, bias, cache)
 
 
+_pad_cache = {}
+
+
+def padded_operand_buffer(N, H, W, C, pad, device):
+    """Zeroed [N, H+2p, W+2p, width] buffer in the operand format of the active policy, cached per shape: producers
+    only ever write its interior, so the zero border survives from call to call (and across CUDA-graph replays)."""
+    _code, mult, dt = ops._split_code(_fmt(), C)
+    key = (N, H, W, C, pad, str(device), dt)
+    buf = _pad_cache.get(key)
+    if buf is None:
+        buf = torch.zeros((N, H + 2 * pad, W + 2 * pad, mult * C), device=device, dtype=dt)
+        _pad_cache[key] = buf
+    return buf
+
+
+def groupnorm_cl(x_cl, gn, lowres=None, relu=False, want_f32=True, for_gemm=False, pad=0):
+    """GroupNorm module `gn` on a channel-last activation [N,H,W,C] (rows / frames may be strided) + optional bilinear
+    top-down add + ReLU, in one pass (ops.groupnorm_cl).  Returns (fp32 [N,H,W,C] or None, GEMM operand or None);
+    with pad > 0 the operand sits in the interior of a cached zero-bordered buffer for conv2d_cl_operand."""
+    split = _fmt() if (for_gemm and splitting()) else None
+    N, H, W, C = x_cl.shape
+    buf = padded_operand_buffer(N, H, W, C, pad, x_cl.device) if (split and pad) else None
+    return ops.groupnorm_cl(x_cl, gn.weight, gn.bias, gn.num_groups, gn.eps, lowres, relu,
+                            want_f32 or not split, split, pad if split else 0, buf)
+
+
 def conv2d_cl(x_cl, weight, bias=None, padding=0):
     """Convolution on a channel-last activation [N,H,W,Cin] -> [N,H,W,Cout] (storage channel-last).
     Splitting policy: a kxk "same" convolution is k*k shifted GEMMs over the zero-padded, split activation viewed
@@ -184,6 +235,22 @@ def conv2d_cl(x_cl, weight, bias=None, padding=0):
         return y.permute(0, 2, 3, 1)
     Cout, _, kh, kw = weight.shape
     assert kh == kw and padding == kh // 2, "only 'same' square convolutions are used on this path"
+    p = padding
+    xs = F.pad(ops.split_operand(x_cl.contiguous(), _fmt()), (0, 0, p, p, p, p))  # [N,Hp,Wp,2Cin], zeros split to zeros
+    return _conv_taps(xs, H, W, weight, bias, _conv_weight_taps(weight))
+
+
+def conv2d_cl_operand(xs_padded, H, W, weight, bias=None):
+    """conv2d_cl on an activation that already is a spatially zero-padded split operand [N,H+2p,W+2p,width]
+    (groupnorm_cl(..., for_gemm=True, pad=p)).  Splitting policies only."""
+    assert splitting()
+    Cout, _, kh, kw = weight.shape
+    assert kh == kw and xs_padded.shape[1] == H + 2 * (kh // 2)
+    return _conv_taps(xs_padded, H, W, weight, bias, _conv_weight_taps(weight))
+
+
+def _conv_weight_taps(weight):
+    Cout, _, kh, kw = weight.shape
     key = ("conv", weight.data_ptr(), tuple(weight.shape))
     sig = (weight.data_ptr(), weight._version)
     ent = _wcache.get(key)
@@ -191,16 +258,19 @@ def conv2d_cl(x_cl, weight, bias=None, padding=0):
         taps = [_split_weight(weight.detach()[:, :, dy, dx].contiguous(), cache=False) for dy in range(kh) for dx in range(kw)]
         ent = (sig, taps)
         _wcache[key] = ent
-    p = padding
-    Hp, Wp = H + 2 * p, W + 2 * p
-    xs = F.pad(ops.split_operand(x_cl.contiguous(), _fmt()), (0, 0, p, p, p, p))  # [N,Hp,Wp,2Cin], zeros split to zeros
+    return ent[1]
+
+
+def _conv_taps(xs, H, W, weight, bias, taps):
+    """k*k shifted GEMMs over the padded split activation xs [N,Hp,Wp,width] viewed as one token matrix."""
+    Cout, Cin, kh, kw = weight.shape
+    N, Hp, Wp = xs.shape[0], xs.shape[1], xs.shape[2]
     x2 = xs.view(N * Hp * Wp, xs.shape[-1])
     R = N * Hp * Wp - ((kh - 1) * Wp + (kw - 1))                                  # rows every tap can address
-    y = torch.empty((N * Hp * Wp, Cout), device=x_cl.device, dtype=torch.float32)
+    y = torch.empty((N * Hp * Wp, Cout), device=xs.device, dtype=torch.float32)
     yr = y[:R]
     f32 = torch.float32
-    mult = 2 if _policy == "tf32x3" else 3
-    for t, (wh, wlh) in enumerate(ent[1]):
+    for t, (wh, wlh) in enumerate(taps):
         off = (t // kw) * Wp + (t % kw)
         a = x2[off: off + R]
         if _policy == "tf32x3":

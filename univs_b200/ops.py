@@ -79,6 +79,11 @@ def _chk(t: torch.Tensor, name: str, dtype=torch.float32):
     return t.data_ptr()
 
 
+def _chk_t(t: torch.Tensor, name: str, dtype=torch.float32):
+    _chk(t, name, dtype)
+    return t
+
+
 def _levels(spatial_shapes, level_start_index):
     sh = np.ascontiguousarray(np.asarray(spatial_shapes, dtype=np.int64).reshape(-1, 2))
     ls = np.ascontiguousarray(np.asarray(level_start_index, dtype=np.int64).reshape(-1))
@@ -339,6 +344,108 @@ def split_operand(x, split="tf32"):
     with _Bracket("split", 1):
         rc = lib().univs_split_tf32_f32(_stream(), _chk(x, "x"), x.numel() // C, C, code, out.data_ptr())
     check(rc, "split")
+    return out
+
+
+# ---- channel-last GroupNorm fused with the FPN glue (csrc/groupnorm.cu) ------------------------------------------
+_gn_ws = {}
+
+
+def _gn_workspace(device, nbytes):
+    buf = _gn_ws.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), device=device, dtype=torch.uint8)
+        _gn_ws[device] = buf
+    return buf
+
+
+def _strided_image(x):
+    """x [N,H,W,C] fp32 with contiguous pixels (stride(3) == 1, stride(2) == C); rows / images may be strided (a
+    [:, :H, :W] view of a padded buffer).  Returns (img_stride, row_stride) in elements."""
+    N, H, W, C = x.shape
+    if x.stride(3) != 1 or x.stride(2) != C:
+        raise _cabi.UnivsB200Error("groupnorm_cl: pixels must be contiguous channel-last rows")
+    return x.stride(0), x.stride(1)
+
+
+def groupnorm_cl(x, weight, bias, groups, eps=1e-5, lowres=None, relu=False, want_f32=True, split=None, pad=0,
+                 out_split=None):
+    """GroupNorm over a channel-last activation x [N,H,W,C] (+ bilinear-upsampled `lowres` [N,h2,w2,C]) (+ ReLU).
+    Returns (y_f32 or None, operand or None): y_f32 [N,H,W,C]; operand = the result in the GEMM operand format `split`
+    ("tf32" | "f16" | "f16u") written at the interior of a spatially zero-padded [N,H+2*pad,W+2*pad,width] buffer
+    (`out_split`, allocated zeroed if not given -- only the interior is ever written, so a cached buffer stays valid)."""
+    N, H, W, C = x.shape
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise _cabi.UnivsB200Error("groupnorm_cl: x must be a CUDA float32 tensor")
+    img_stride, row_stride = _strided_image(x)
+    dev = x.device
+    ws = _gn_workspace(dev, int(lib().univs_groupnorm_workspace_bytes(N, H, W, groups)))
+    stats = torch.empty((N, groups, 2), device=dev, dtype=torch.float32)
+    with _Bracket("groupnorm_stats", 2):
+        rc = lib().univs_groupnorm_stats_f32(_stream(), x.data_ptr(), N, H, W, C, img_stride, row_stride, groups, float(eps),
+                                             ws.data_ptr(), stats.data_ptr())
+    check(rc, "groupnorm_stats")
+    y = torch.empty((N, H, W, C), device=dev, dtype=torch.float32) if want_f32 else None
+    code = 0
+    if split:
+        code, mult, dt = _split_code(split, C)
+        shape = (N, H + 2 * pad, W + 2 * pad, mult * C)
+        if out_split is None:
+            out_split = torch.zeros(shape, device=dev, dtype=dt) if pad else torch.empty(shape, device=dev, dtype=dt)
+        elif tuple(out_split.shape) != shape or out_split.dtype != dt or not out_split.is_contiguous():
+            raise _cabi.UnivsB200Error(f"groupnorm_cl: out_split must be a contiguous {dt} tensor of shape {shape}")
+    else:
+        out_split = None
+    low_stride = 0
+    if lowres is not None:
+        if lowres.dtype != torch.float32 or not lowres.is_cuda or lowres.shape[0] != N or lowres.shape[3] != C:
+            raise _cabi.UnivsB200Error("groupnorm_cl: lowres must be a CUDA float32 [N,h2,w2,C] tensor")
+        if lowres.stride(3) != 1 or lowres.stride(2) != C or lowres.stride(1) != C * lowres.shape[2]:
+            lowres = lowres.contiguous()        # frames may be strided (a level slice of the token matrix), pixels not
+        low_stride = lowres.stride(0) if N > 1 else lowres.shape[1] * lowres.shape[2] * C
+    with _Bracket("groupnorm_apply", 1):
+        rc = lib().univs_groupnorm_apply_f32(
+            _stream(), x.data_ptr(), N, H, W, C, img_stride, row_stride, stats.data_ptr(), _chk(weight, "weight"),
+            _chk(bias, "bias"), groups, None if lowres is None else lowres.data_ptr(), low_stride,
+            0 if lowres is None else lowres.shape[1], 0 if lowres is None else lowres.shape[2], 1 if relu else 0,
+            None if y is None else y.data_ptr(), None if out_split is None else out_split.data_ptr(), code, pad)
+    check(rc, "groupnorm_apply")
+    return y, out_split
+
+
+# ---- gather-fused kernels at the edges of the Swin stages (csrc/swin_glue.cu) ------------------------------------
+def patchify_normalize(frames, pixel_mean, pixel_std, padded_size, patch=4, split=None):
+    """frames [N,3,H,W] uint8 / float32 (0..255) on the device -> [N, Hp/4, Wp/4, 48 (* split width)]: normalised,
+    zero-padded 4x4 patches, column = c*16 + ky*4 + kx (PatchEmbed.proj weight.view(E, 48))."""
+    if frames.dtype not in (torch.uint8, torch.float32) or not frames.is_cuda or not frames.is_contiguous():
+        raise _cabi.UnivsB200Error("patchify_normalize: frames must be a contiguous CUDA uint8 / float32 tensor")
+    N, c3, H, W = frames.shape
+    Hp, Wp = padded_size
+    if c3 != 3:
+        raise _cabi.UnivsB200Error("patchify_normalize: frames must be [N,3,H,W]")
+    import ctypes
+    K = 3 * patch * patch
+    code, mult, dt = _split_code(split, K)
+    out = torch.empty((N, Hp // patch, Wp // patch, mult * K), device=frames.device, dtype=dt)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in pixel_mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in pixel_std])
+    with _Bracket("patchify", 1):
+        rc = lib().univs_patchify_normalize(_stream(), frames.data_ptr(), 1 if frames.dtype == torch.uint8 else 0, N, H, W,
+                                            Hp, Wp, patch, m3, s3, out.data_ptr(), code)
+    check(rc, "patchify_normalize")
+    return out
+
+
+def layernorm_merge2x2(x, weight, bias, eps=1e-5, split=None):
+    """PatchMerging gather + LayerNorm: x [N,H,W,C] -> [N, ceil(H/2), ceil(W/2), 4C (* split width)]."""
+    x = _chk_t(x, "x")
+    N, H, W, C = x.shape
+    code, mult, dt = _split_code(split, 4 * C)
+    out = torch.empty((N, (H + 1) // 2, (W + 1) // 2, mult * 4 * C), device=x.device, dtype=dt)
+    with _Bracket("layernorm_merge2x2", 1):
+        rc = lib().univs_layernorm_merge2x2_f32(_stream(), x.data_ptr(), N, H, W, C, _chk(weight, "weight"),
+                                                _chk(bias, "bias"), float(eps), out.data_ptr(), code)
+    check(rc, "layernorm_merge2x2")
     return out
 
 

@@ -29,6 +29,13 @@ class ClipStream:
     @torch.no_grad()
     def push(self, first_index: int, frames):
         """Encode frames [first_index, first_index + k) (k >= 1; any k -- a chunk is one backbone / pixel-decoder batch)."""
+        from . import nn_ops
+        if nn_ops.fused_glue() and hasattr(self.model, "backbone_from_frames"):      # ingest fused into the patch embedding
+            if isinstance(frames, (list, tuple)):
+                frames = torch.stack([f.to(self.model.device) for f in frames])
+            self.image_size = tuple(frames.shape[-2:])
+            self._store(first_index, self.model.backbone_from_frames(frames))
+            return
         x, self.image_size = self.model.preprocess(frames)
         self.push_preprocessed(first_index, x)
 
@@ -36,9 +43,11 @@ class ClipStream:
     def push_preprocessed(self, first_index: int, x):
         """Same for frames that are already normalised and padded ([k,3,Hp,Wp] float32 on the device) -- what the
         task heads hold after ImageList.from_tensors (inference_video_vis_fast.py:198-207)."""
-        feats = self.model.backbone(x)
+        self._store(first_index, self.model.backbone(x))
+
+    def _store(self, first_index: int, feats):
         mf, _bfe, _enc, ms = self.model.sem_seg_head.pixel_decoder.forward_features(feats)
-        for j in range(x.shape[0]):
+        for j in range(mf.shape[0]):
             self._cache[first_index + j] = (mf[j:j + 1], [m[j:j + 1] for m in ms])
             self.frames_encoded += 1
         while len(self._cache) > self.capacity:
