@@ -19,7 +19,7 @@ def _swin(qkv, qkv_bias, table, num_heads, window, shift, precision=None):
     return ops_ref.swin_window_attention(qkv, qkv_bias, table, num_heads, window, shift)
 
 
-def _msda_enc(value, shapes, starts, offs_logits, num_levels=3, num_points=4):
+def _msda_enc(value, shapes, starts, offs_logits, num_levels=3, num_points=4, tile=None):
     return ops_ref.ms_deform_attn_fused(value, shapes, starts, offs_logits, value.shape[2], num_levels, num_points)
 
 

@@ -184,3 +184,25 @@ def test_fused_glue_model_cuda_equals_default(policy):
     finally:
         nn_ops.set_fused_glue(False)
         precision.set_precision("fp32")
+
+
+@pytest.mark.gpu
+@_gpu_glue
+@pytest.mark.parametrize("shapes", [[(23, 40), (46, 80), (92, 160)], [(3, 5), (6, 9), (11, 18)]])
+@pytest.mark.parametrize("tile", [1, 4, 8, 16, 32])
+def test_msda_encoder_tiled_is_bit_identical(shapes, tile):
+    """Only the work distribution differs: every (frame, query, head) runs the same instruction sequence."""
+    from univs_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    N, M = 2, 8
+    shapes = shapes[::-1]                                   # coarse to fine, as the pixel decoder orders them
+    S = sum(h * w for h, w in shapes)
+    starts = [0]
+    for h, w in shapes[:-1]:
+        starts.append(starts[-1] + h * w)
+    value = torch.randn(N, S, M, 32, generator=g).cuda()
+    ol = torch.randn(N, S, M * 3 * 4 * 3, generator=g).cuda()
+    ol[..., : M * 24] *= 3.0                                # offsets reaching across pixels and past the borders
+    base = ops.ms_deform_attn_encoder(value, shapes, starts, ol, tile=0)
+    tiled = ops.ms_deform_attn_encoder(value, shapes, starts, ol, tile=tile)
+    assert torch.equal(base, tiled)

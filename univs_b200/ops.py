@@ -3,6 +3,8 @@ allocates the output with torch (device memory plumbing), passes raw pointers an
 through the C ABI and returns immediately (stream-ordered, no synchronisation).  No CPU path exists."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -112,12 +114,31 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
-def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits, num_levels=3, num_points=4):
+# Work distribution of the encoder MSDeformAttn kernel: 0 = 4 consecutive queries x 8 heads per CTA (validated in round 1),
+# w in {1,..,32} = w x (32/w) query tiles of one head per CTA (bit-identical results, better L1 reuse; opt-in until it
+# has been run on a B200).
+_msda_tile = int(os.environ.get("UNIVS_MSDA_TILE", "0"))
+
+
+def set_msda_tile(width: int):
+    global _msda_tile
+    _msda_tile = int(width)
+
+
+def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits, num_levels=3, num_points=4, tile=None):
     """value [N,S,M,32]; offs_logits [N,S,M*L*P*3] raw linear outputs -> [N,S,M*32]"""
     N, S, M, D = value.shape
     assert D == 32 and offs_logits.shape == (N, S, M * num_levels * num_points * 3)
     sh, ls = _levels(spatial_shapes, level_start_index)
     out = torch.empty((N, S, M * D), device=value.device, dtype=torch.float32)
+    tile = _msda_tile if tile is None else tile
+    if tile:
+        with _Bracket("ms_deform_attn_encoder", 1):
+            rc = lib().univs_ms_deform_attn_encoder_tiled_f32(_stream(), _chk(value, "value"), sh.ctypes.data,
+                                                              ls.ctypes.data, _chk(offs_logits, "offs_logits"), N, S, M,
+                                                              num_levels, num_points, tile, out.data_ptr())
+        check(rc, "ms_deform_attn_encoder_tiled")
+        return out
     with _Bracket("ms_deform_attn_encoder", 1):
         rc = lib().univs_ms_deform_attn_encoder_f32(_stream(), _chk(value, "value"), sh.ctypes.data, ls.ctypes.data,
                                                 _chk(offs_logits, "offs_logits"), N, S, M, num_levels, num_points,
