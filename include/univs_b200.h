@@ -56,11 +56,15 @@ int univs_ms_deform_attn_encoder_f32(void* stream, const float* value, const int
                                      int spatial_size, int num_heads, int num_levels, int num_point, float* out);
 /* Same operation, same arithmetic per (frame, query, head) -- results are bit-identical -- with a different work
  * distribution: one CTA = a tile_width x (32 / tile_width) block of neighbouring queries of one head, so that the
- * overlapping sampling footprints are served from L1 (tile_width: power of two <= 32). */
+ * overlapping sampling footprints are served from L1 (tile_width: power of two <= 32).
+ * Optional fusions (all nullable / 0): value_bias [heads*32] = bias of value_proj, applied to the in-bounds samples as
+ * the reference's zero padding requires, so that GEMM runs bias-free; offs_logits_bias [heads*L*P*3] = biases of the
+ * sampling_offsets / attention_weights linears; split != 0 writes `out` as a GEMM operand (see the row-wise kernels). */
 int univs_ms_deform_attn_encoder_tiled_f32(void* stream, const float* value, const int64_t* spatial_shapes,
                                            const int64_t* level_start_index, const float* offs_logits, int batch,
                                            int spatial_size, int num_heads, int num_levels, int num_point,
-                                           int tile_width, float* out);
+                                           int tile_width, const float* value_bias, const float* offs_logits_bias,
+                                           int split, float* out);
 
 /* ---- Swin (shifted-)window attention, addressing folded in (a2,a3).
  * qkv [B,H,W,3C] f32 = LN(x) * Wqkv^T on the unpadded token grid WITHOUT the bias; qkv_bias [3C] is added by the kernel

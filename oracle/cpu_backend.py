@@ -19,8 +19,15 @@ def _swin(qkv, qkv_bias, table, num_heads, window, shift, precision=None):
     return ops_ref.swin_window_attention(qkv, qkv_bias, table, num_heads, window, shift)
 
 
-def _msda_enc(value, shapes, starts, offs_logits, num_levels=3, num_points=4, tile=None):
-    return ops_ref.ms_deform_attn_fused(value, shapes, starts, offs_logits, value.shape[2], num_levels, num_points)
+def _msda_enc(value, shapes, starts, offs_logits, num_levels=3, num_points=4, tile=None, value_bias=None,
+              offs_logits_bias=None, split=None):
+    # the reference adds the biases in the producing linears (ms_deform_attn.py:98-105)
+    if value_bias is not None:
+        value = value + value_bias.view(1, 1, value.shape[2], value.shape[3])
+    if offs_logits_bias is not None:
+        offs_logits = offs_logits + offs_logits_bias
+    y = ops_ref.ms_deform_attn_fused(value, shapes, starts, offs_logits, value.shape[2], num_levels, num_points)
+    return _maybe_split(y, split) if split else y
 
 
 def _msda_fwd(value, shapes, starts, loc, w):

@@ -206,3 +206,25 @@ def test_msda_encoder_tiled_is_bit_identical(shapes, tile):
     base = ops.ms_deform_attn_encoder(value, shapes, starts, ol, tile=0)
     tiled = ops.ms_deform_attn_encoder(value, shapes, starts, ol, tile=tile)
     assert torch.equal(base, tiled)
+
+
+@pytest.mark.gpu
+@_gpu_glue
+@pytest.mark.parametrize("fmt", [None, "f16", "tf32"])
+def test_msda_encoder_fused_biases_and_operand_cuda(fmt):
+    """value_proj / offsets / logits biases folded into the kernel (in-bounds samples only) + operand emission."""
+    from univs_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    N, M = 2, 8
+    shapes = [(5, 9), (10, 18), (20, 36)]
+    S = sum(h * w for h, w in shapes)
+    starts = [0, 45, 45 + 180]
+    value = torch.randn(N, S, M, 32, generator=g)
+    ol = torch.randn(N, S, M * 36, generator=g)
+    ol[..., : M * 24] *= 4.0                       # plenty of samples beyond the borders: bias must not leak into them
+    vb, ob = torch.randn(M * 32, generator=g), torch.randn(M * 36, generator=g) * 0.5
+    want = ops_ref.ms_deform_attn_fused(value + vb.view(1, 1, M, 32), shapes, starts, ol + ob, M, 3, 4)
+    got = ops.ms_deform_attn_encoder(value.cuda(), shapes, starts, ol.cuda(), value_bias=vb.cuda(),
+                                     offs_logits_bias=ob.cuda(), split=fmt)
+    got = _unsplit(got, fmt, M * 32) if fmt else got
+    assert _rel(got.cpu(), want) < 2e-5

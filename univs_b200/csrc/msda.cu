@@ -10,7 +10,7 @@
 //   * offsets / logits are read as 128-bit broadcast loads; softmax over L*P and the sampling-location
 //     arithmetic of MSDeformAttn.forward (ops/modules/ms_deform_attn.py:101-108) are fused in the
 //     encoder variant, so loc/weight tensors are never materialised.
-#include "common.cuh"
+#include "rowwise.cuh"
 
 namespace univs {
 
@@ -197,10 +197,43 @@ msda_encoder_kernel(const float* __restrict__ value, LevelTable lt, const float*
 
 // The work of one (frame n, query q, head m) triple for one 8-lane group (lane8 owns channels [4*lane8, 4*lane8+4)):
 // a verbatim restatement of the body of msda_encoder_kernel above, which is left untouched (validated SASS).
-template <int L, int P>
+// FUSED adds what surrounds the operator in the encoder layer (ops/modules/ms_deform_attn.py:98-120): the biases of the
+// value_proj / sampling_offsets / attention_weights linears (so those GEMMs run bias-free, without the broadcast copy a
+// library GEMM needs for a bias), and emission of the result in the GEMM operand format of output_proj.
+//   value bias: sum_i w_i (v_i + b) = sum_i w_i v_i + b * sum_i w_i over the IN-BOUNDS corners i (out-of-range corners
+//   read zero in the reference, not b: ms_deform_im2col_cuda.cuh:38-89), so b is scaled by the surviving corner weights.
+__device__ __forceinline__ void sample4_biased(float4& acc, const float* __restrict__ base, int pix_stride, int H, int W,
+                                               float x, float y, float aw, const float4& vb) {
+  const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+  const float xf = floorf(x), yf = floorf(y);
+  const int x0 = (int)xf, y0 = (int)yf;
+  const float lx = x - xf, ly = y - yf;
+  const float hx = 1.f - lx, hy = 1.f - ly;
+  const bool x0ok = x0 >= 0, x1ok = x0 + 1 <= W - 1, y0ok = y0 >= 0, y1ok = y0 + 1 <= H - 1;
+  const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+  const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+  const float w1 = (inside && y0ok && x0ok) ? hy * hx : 0.f;
+  const float w2 = (inside && y0ok && x1ok) ? hy * lx : 0.f;
+  const float w3 = (inside && y1ok && x0ok) ? ly * hx : 0.f;
+  const float w4 = (inside && y1ok && x1ok) ? ly * lx : 0.f;
+  const float4 v1 = ldg_f4(base + (size_t)(yc0 * W + xc0) * pix_stride);
+  const float4 v2 = ldg_f4(base + (size_t)(yc0 * W + xc1) * pix_stride);
+  const float4 v3 = ldg_f4(base + (size_t)(yc1 * W + xc0) * pix_stride);
+  const float4 v4 = ldg_f4(base + (size_t)(yc1 * W + xc1) * pix_stride);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  fma4(s, w1, v1);
+  fma4(s, w2, v2);
+  fma4(s, w3, v3);
+  fma4(s, w4, v4);
+  fma4(s, (w1 + w2) + (w3 + w4), vb);
+  fma4(acc, aw, s);
+}
+
+template <int L, int P, bool FUSED>
 __device__ __forceinline__ void msda_encoder_pair(const float* __restrict__ value, const LevelTable& lt,
                                                   const float* __restrict__ ol, int n, int q, int m, int lane8, int S,
-                                                  int M, float* __restrict__ out) {
+                                                  int M, float* __restrict__ out, const float* __restrict__ value_bias,
+                                                  const float* __restrict__ ol_bias, int split) {
   constexpr int LP = L * P;
   static_assert((LP * 2) % 4 == 0 && LP % 4 == 0, "vector loads need L*P % 4 == 0");
   const long long nq = (long long)n * S + q;
@@ -231,6 +264,12 @@ __device__ __forceinline__ void msda_encoder_pair(const float* __restrict__ valu
       lg[4 * i] = t.x; lg[4 * i + 1] = t.y; lg[4 * i + 2] = t.z; lg[4 * i + 3] = t.w;
     }
   }
+  if (FUSED && ol_bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < LP * 2; ++i) off[i] += __ldg(ol_bias + m * (LP * 2) + i);
+#pragma unroll
+    for (int i = 0; i < LP; ++i) lg[i] += __ldg(ol_bias + M * LP * 2 + m * LP + i);
+  }
   float mx = lg[0];
 #pragma unroll
   for (int i = 1; i < LP; ++i) mx = fmaxf(mx, lg[i]);
@@ -244,6 +283,8 @@ __device__ __forceinline__ void msda_encoder_pair(const float* __restrict__ valu
 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int pix_stride = M * 32;
+  float4 vb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (FUSED && value_bias != nullptr) vb = ldg_f4(value_bias + m * 32 + lane8 * 4);
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     const int H = lt.H[l], W = lt.W[l];
@@ -252,10 +293,16 @@ __device__ __forceinline__ void msda_encoder_pair(const float* __restrict__ valu
     for (int p = 0; p < P; ++p) {
       const float locx = refx + off[(l * P + p) * 2] / (float)W;
       const float locy = refy + off[(l * P + p) * 2 + 1] / (float)H;
-      sample4(acc, base, pix_stride, H, W, locx * (float)W - 0.5f, locy * (float)H - 0.5f, lg[l * P + p] * inv);
+      if (FUSED)
+        sample4_biased(acc, base, pix_stride, H, W, locx * (float)W - 0.5f, locy * (float)H - 0.5f, lg[l * P + p] * inv, vb);
+      else
+        sample4(acc, base, pix_stride, H, W, locx * (float)W - 0.5f, locy * (float)H - 0.5f, lg[l * P + p] * inv);
     }
   }
-  *reinterpret_cast<float4*>(out + pair * 32 + lane8 * 4) = acc;
+  if (FUSED)
+    store_maybe_split(out, (size_t)nq, M * 32, m * 32 + lane8 * 4, acc, split);
+  else
+    *reinterpret_cast<float4*>(out + pair * 32 + lane8 * 4) = acc;
 }
 
 // Tiled variant (opt-in, results bit-identical to msda_encoder_kernel: same per-(n,q,m) arithmetic): a CTA covers a
@@ -268,10 +315,11 @@ struct TileTable {
   int tiles_x[kMaxLevels];
 };
 
-template <int L, int P>
+template <int L, int P, bool FUSED>
 __global__ void __launch_bounds__(256)
 msda_encoder_tiled_kernel(const float* __restrict__ value, LevelTable lt, TileTable tt, const float* __restrict__ ol,
-                          int S, int M, int tile_w_log2, float* __restrict__ out) {
+                          int S, int M, int tile_w_log2, float* __restrict__ out, const float* __restrict__ value_bias,
+                          const float* __restrict__ ol_bias, int split) {
   const int lane8 = threadIdx.x & 7;
   const int tq = threadIdx.x >> 3;                 // query inside the tile
   const int tile = blockIdx.x, m = blockIdx.y, n = blockIdx.z;
@@ -285,7 +333,7 @@ msda_encoder_tiled_kernel(const float* __restrict__ value, LevelTable lt, TileTa
   const int qx = tx * tile_w + (tq & (tile_w - 1));
   const int qy = ty * tile_h + (tq >> tile_w_log2);
   if (qx >= lt.W[l] || qy >= lt.H[l]) return;
-  msda_encoder_pair<L, P>(value, lt, ol, n, lt.start[l] + qy * lt.W[l] + qx, m, lane8, S, M, out);
+  msda_encoder_pair<L, P, FUSED>(value, lt, ol, n, lt.start[l] + qy * lt.W[l] + qx, m, lane8, S, M, out, value_bias, ol_bias, split);
 }
 
 static int fill_levels(LevelTable& lt, const int64_t* shapes_h, const int64_t* lsi_h, int L) {
@@ -402,7 +450,8 @@ extern "C" int univs_ms_deform_attn_encoder_f32(void* stream, const float* value
 extern "C" int univs_ms_deform_attn_encoder_tiled_f32(void* stream, const float* value, const int64_t* spatial_shapes,
                                                       const int64_t* level_start_index, const float* offs_logits,
                                                       int batch, int spatial_size, int num_heads, int num_levels,
-                                                      int num_point, int tile_width, float* out) {
+                                                      int num_point, int tile_width, const float* value_bias,
+                                                      const float* offs_logits_bias, int split, float* out) {
   UNIVS_REQUIRE(value && spatial_shapes && level_start_index && offs_logits && out,
                 "ms_deform_attn_encoder_tiled: null pointer");
   UNIVS_REQUIRE(num_levels == 3 && num_point == 4,
@@ -434,7 +483,18 @@ extern "C" int univs_ms_deform_attn_encoder_tiled_f32(void* stream, const float*
   tt.first[num_levels] = (int)tiles;
   UNIVS_REQUIRE(tot == spatial_size, "ms_deform_attn_encoder_tiled: sum(H*W)=%lld != spatial_size=%d", tot, spatial_size);
   UNIVS_REQUIRE(tiles < (1ll << 31), "ms_deform_attn_encoder_tiled: problem too large");
-  msda_encoder_tiled_kernel<3, 4><<<dim3((unsigned)tiles, (unsigned)num_heads, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(
-      value, lt, tt, offs_logits, spatial_size, num_heads, log2w, out);
+  const dim3 grid((unsigned)tiles, (unsigned)num_heads, (unsigned)batch);
+  if (value_bias == nullptr && offs_logits_bias == nullptr && split == 0) {
+    msda_encoder_tiled_kernel<3, 4, false><<<grid, 256, 0, (cudaStream_t)stream>>>(value, lt, tt, offs_logits, spatial_size,
+                                                                                 num_heads, log2w, out, nullptr, nullptr, 0);
+  } else {
+    const int C = num_heads * 32;
+    UNIVS_REQUIRE(split == 0 || split == UNIVS_SPLIT_F16U ||
+                      (split != -1 && split != -3 && (split > 0 ? split : -split) % 4 == 0 && C % (split > 0 ? split : -split) == 0),
+                  "ms_deform_attn_encoder_tiled: split chunk must divide heads*32");
+    msda_encoder_tiled_kernel<3, 4, true><<<grid, 256, 0, (cudaStream_t)stream>>>(value, lt, tt, offs_logits, spatial_size,
+                                                                                num_heads, log2w, out, value_bias,
+                                                                                offs_logits_bias, split);
+  }
   return check_launch("ms_deform_attn_encoder_tiled");
 }

@@ -71,11 +71,21 @@ class _EncoderLayer(nn.Module):
     def forward(self, src, pos, shapes, starts):
         a = self.self_attn
         N, S, C = src.shape
-        value = nn_ops.linear(src, a.value_proj.weight, a.value_proj.bias).view(N, S, a.n_heads, C // a.n_heads)
         w, b = a.fused_offs_logits()
-        offs_logits = nn_ops.linear(src + pos, w, b)
-        y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points)
-        o = nn_ops.linear(y, a.output_proj.weight, None)
+        if nn_ops.fused_glue():
+            # the three linear biases move into the MSDeformAttn kernel (no bias-broadcast copies for the GEMMs) and the
+            # kernel emits the operand of output_proj directly
+            value = nn_ops.linear(src, a.value_proj.weight, None).view(N, S, a.n_heads, C // a.n_heads)
+            offs_logits = nn_ops.linear(src + pos, w, None)
+            y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points,
+                                           value_bias=a.value_proj.bias, offs_logits_bias=b,
+                                           split=nn_ops._fmt() if nn_ops.splitting() else None)
+            o = nn_ops.linear_prepped(y, a.output_proj.weight, None)
+        else:
+            value = nn_ops.linear(src, a.value_proj.weight, a.value_proj.bias).view(N, S, a.n_heads, C // a.n_heads)
+            offs_logits = nn_ops.linear(src + pos, w, b)
+            y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points)
+            o = nn_ops.linear(y, a.output_proj.weight, None)
         src = nn_ops.layernorm(src, self.norm1, residual=o, for_gemm=False, residual_bias=a.output_proj.bias)[1]
         f = nn_ops.linear(src, self.linear1.weight, None)
         z = nn_ops.linear_prepped(nn_ops.relu(f, bias=self.linear1.bias), self.linear2.weight, None)

@@ -125,20 +125,28 @@ def set_msda_tile(width: int):
     _msda_tile = int(width)
 
 
-def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits, num_levels=3, num_points=4, tile=None):
-    """value [N,S,M,32]; offs_logits [N,S,M*L*P*3] raw linear outputs -> [N,S,M*32]"""
+def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits, num_levels=3, num_points=4, tile=None,
+                           value_bias=None, offs_logits_bias=None, split=None):
+    """value [N,S,M,32]; offs_logits [N,S,M*L*P*3] raw linear outputs -> [N,S,M*32] (fp32, or a GEMM operand if `split`).
+    value_bias / offs_logits_bias: biases of the producing linears, folded into the kernel (tiled variant only)."""
     N, S, M, D = value.shape
     assert D == 32 and offs_logits.shape == (N, S, M * num_levels * num_points * 3)
     sh, ls = _levels(spatial_shapes, level_start_index)
-    out = torch.empty((N, S, M * D), device=value.device, dtype=torch.float32)
     tile = _msda_tile if tile is None else tile
+    fused = value_bias is not None or offs_logits_bias is not None or bool(split)
+    if fused and not tile:
+        tile = 8
     if tile:
+        code, mult, dt = _split_code(split, M * D)
+        out = torch.empty((N, S, mult * M * D), device=value.device, dtype=dt)
         with _Bracket("ms_deform_attn_encoder", 1):
-            rc = lib().univs_ms_deform_attn_encoder_tiled_f32(_stream(), _chk(value, "value"), sh.ctypes.data,
-                                                              ls.ctypes.data, _chk(offs_logits, "offs_logits"), N, S, M,
-                                                              num_levels, num_points, tile, out.data_ptr())
+            rc = lib().univs_ms_deform_attn_encoder_tiled_f32(
+                _stream(), _chk(value, "value"), sh.ctypes.data, ls.ctypes.data, _chk(offs_logits, "offs_logits"), N, S, M,
+                num_levels, num_points, tile, None if value_bias is None else _chk(value_bias, "value_bias"),
+                None if offs_logits_bias is None else _chk(offs_logits_bias, "offs_logits_bias"), code, out.data_ptr())
         check(rc, "ms_deform_attn_encoder_tiled")
         return out
+    out = torch.empty((N, S, M * D), device=value.device, dtype=torch.float32)
     with _Bracket("ms_deform_attn_encoder", 1):
         rc = lib().univs_ms_deform_attn_encoder_f32(_stream(), _chk(value, "value"), sh.ctypes.data, ls.ctypes.data,
                                                 _chk(offs_logits, "offs_logits"), N, S, M, num_levels, num_points,
