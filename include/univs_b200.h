@@ -182,6 +182,12 @@ int univs_patchify_normalize(void* stream, const void* frames, int is_uint8, int
                              float* out, int split);
 int univs_layernorm_merge2x2_f32(void* stream, const float* x, int num_frames, int height, int width, int channels,
                                  const float* gamma, const float* beta, float eps, float* out, int split);
+/* LayerNorm with several consumers (post-norm layers, msdeformattn.py:126-133): y = LN(x (+ residual (+ residual_bias)));
+ * out_f32 (nullable) = y; out_split (nullable) = y as a GEMM operand (`split`); out_split_pos (nullable) = (y +
+ * pos[row % pos_rows]) as a GEMM operand -- the query of the next deformable attention (src + pos, ms_deform_attn.py). */
+int univs_layernorm_multi_f32(void* stream, const float* x, const float* residual, const float* residual_bias,
+                              const float* gamma, const float* beta, int64_t rows, int channels, float eps, float* out_f32,
+                              void* out_split, int split, const float* pos, int64_t pos_rows, void* out_split_pos);
 
 /* ---- helpers ---- */
 /* in-place/out-of-place round-to-nearest-even to TF32 (19-bit) of n floats */

@@ -117,7 +117,21 @@ def _groupnorm_cl(x, weight, bias, groups, eps=1e-5, lowres=None, relu=False, wa
     return (y if want_f32 else None), op
 
 
+def _layernorm_multi(x, weight, bias, eps=1e-5, residual=None, residual_bias=None, want_f32=True, split=None, pos=None,
+                     want_operand=True):
+    _, y = _layernorm(x, weight, bias, eps, residual, False, None, residual_bias)
+    op = _maybe_split(y, split) if (split and want_operand) else None
+    op_pos = None
+    if pos is not None:
+        C = x.shape[-1]
+        p = pos.reshape(-1, C)
+        yp = (y.reshape(-1, p.shape[0], C) + p).reshape(y.shape)
+        op_pos = _maybe_split(yp, split)
+    return (y if want_f32 else None), op, op_pos
+
+
 _PATCH = {"layernorm": _layernorm,
+          "layernorm_multi": _layernorm_multi,
           "groupnorm_cl": _groupnorm_cl,
           "patchify_normalize": lambda f, m, s, padded, patch=4, split=None: _maybe_split(
               ops_ref.patchify_normalize(f, m, s, padded, patch), split),

@@ -19,7 +19,7 @@ MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
 
 def _model(T=2, Q=6):
     parts = mf.build_product_model(mf.TINY_SWIN, num_queries=Q, num_frames=T, clip_emb=mf.make_clip_emb(),
-                                   enc_layers=1, dec_layers=2)
+                                   enc_layers=2, dec_layers=2)      # two encoder layers: operands carried between them
     mf.load_keyed(parts)
     shapes = {f"res{i + 2}": ShapeSpec(channels=32 * 2 ** i, stride=4 * 2 ** i) for i in range(4)}
     head = MaskFormerHead(shapes, num_classes=133, pixel_decoder=parts[1], transformer_predictor=parts[2])
@@ -228,3 +228,25 @@ def test_msda_encoder_fused_biases_and_operand_cuda(fmt):
                                      offs_logits_bias=ob.cuda(), split=fmt)
     got = _unsplit(got, fmt, M * 32) if fmt else got
     assert _rel(got.cpu(), want) < 2e-5
+
+
+@pytest.mark.gpu
+@_gpu_glue
+@pytest.mark.parametrize("C,fmt", [(256, "f16"), (256, "tf32"), (192, "f16"), (1024, "f16u")])
+def test_layernorm_multi_cuda(C, fmt):
+    from univs_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    N, S = 3, 37
+    x, r = torch.randn(N, S, C, generator=g) * 2, torch.randn(N, S, C, generator=g)
+    rb, gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g), torch.randn(C, generator=g)
+    pos = torch.randn(1, S, C, generator=g)
+    want = torch.nn.functional.layer_norm(x + r + rb, (C,), gamma, beta, 1e-5)
+    d = "cuda"
+    y, op, opp = ops.layernorm_multi(x.to(d), gamma.to(d), beta.to(d), 1e-5, r.to(d), rb.to(d), True, fmt, pos.to(d))
+    tol = 2e-5 if fmt != "f16u" else 1e-4
+    assert _rel(y.cpu(), want) < 2e-5
+    assert _rel(_unsplit(op, fmt, C).cpu(), want) < tol
+    assert _rel(_unsplit(opp, fmt, C).cpu(), want + pos) < tol
+    y2, op2, opp2 = ops.layernorm_multi(x.to(d), gamma.to(d), beta.to(d), want_f32=False, split=fmt)
+    assert y2 is None and opp2 is None
+    assert _rel(_unsplit(op2, fmt, C).cpu(), torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5)) < tol

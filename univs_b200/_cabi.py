@@ -37,6 +37,7 @@ SIGNATURES = {
                                        _vp, _i, _i]),
     "univs_patchify_normalize": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       _vp, _i]),
+    "univs_layernorm_multi_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, C.c_float, _vp, _vp, _i, _vp, _i64, _vp]),
     "univs_layernorm_merge2x2_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_float, _vp, _i]),
 }
 

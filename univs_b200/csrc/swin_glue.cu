@@ -114,6 +114,72 @@ layernorm_merge_kernel(const float* __restrict__ x, int N, int H, int W, int C, 
   }
 }
 
+// LayerNorm with several consumers (post-norm transformer layers, msdeformattn.py:126-133: the normalised tokens are the
+// residual stream AND the input of the next GEMMs, one of them after adding the positional embedding):
+//   s = x (+ residual (+ residual_bias));  y = LN(s) * gamma + beta
+//   out_f32 (nullable) = y;  out_split (nullable) = operand(y);  out_split_pos (nullable) = operand(y + pos[row % pos_rows])
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_multi_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ res_bias,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C, float eps,
+                       float* __restrict__ out_f32, float* __restrict__ out_split, int split, const float* __restrict__ pos,
+                       long long pos_rows, float* __restrict__ out_split_pos) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = C >> 2;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < nv) {
+      float4 a = *reinterpret_cast<const float4*>(x + row * C + idx * 4);
+      if (res != nullptr) {
+        const float4 b = *reinterpret_cast<const float4*>(res + row * C + idx * 4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        if (res_bias != nullptr) {
+          const float4 rb = ldg_f4(res_bias + idx * 4);
+          a.x += rb.x; a.y += rb.y; a.z += rb.z; a.w += rb.w;
+        }
+      }
+      v[i] = a;
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const long long prow = pos != nullptr ? row % pos_rows : 0;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float4 gm = ldg_f4(gamma + idx * 4), bt = ldg_f4(beta + idx * 4);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+      o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+      o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+      o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+      if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + row * C + idx * 4) = o;
+      if (out_split != nullptr) store_maybe_split(out_split, (size_t)row, C, idx * 4, o, split);
+      if (out_split_pos != nullptr) {
+        const float4 pe = ldg_f4(pos + prow * C + idx * 4);
+        store_maybe_split(out_split_pos, (size_t)row, C, idx * 4, make_float4(o.x + pe.x, o.y + pe.y, o.z + pe.z, o.w + pe.w), split);
+      }
+    }
+  }
+}
+
 }  // namespace univs
 
 using namespace univs;
@@ -170,4 +236,34 @@ extern "C" int univs_layernorm_merge2x2_f32(void* stream, const float* x, int nu
   else LNM_LAUNCH(32);
 #undef LNM_LAUNCH
   return check_launch("layernorm_merge2x2");
+}
+
+extern "C" int univs_layernorm_multi_f32(void* stream, const float* x, const float* residual, const float* residual_bias,
+                                         const float* gamma, const float* beta, int64_t rows, int channels, float eps,
+                                         float* out_f32, void* out_split, int split, const float* pos, int64_t pos_rows,
+                                         void* out_split_pos) {
+  UNIVS_REQUIRE(rows >= 0 && channels > 0, "layernorm_multi: bad sizes");
+  if (rows == 0) return UNIVS_OK;
+  UNIVS_REQUIRE(x && gamma && beta, "layernorm_multi: null pointer");
+  UNIVS_REQUIRE(out_f32 || out_split || out_split_pos, "layernorm_multi: no output requested");
+  UNIVS_REQUIRE(residual_bias == nullptr || residual != nullptr, "layernorm_multi: residual_bias needs a residual");
+  UNIVS_REQUIRE(channels % 4 == 0 && channels <= 4096, "layernorm_multi: channels must be a multiple of 4 and <= 4096 (got %d)", channels);
+  UNIVS_REQUIRE((out_split == nullptr && out_split_pos == nullptr) || (split != 0 && split_ok(split, channels)),
+                "layernorm_multi: operand outputs need a valid split code");
+  UNIVS_REQUIRE(out_split_pos == nullptr || (pos != nullptr && pos_rows > 0 && rows % pos_rows == 0),
+                "layernorm_multi: pos [pos_rows, channels] must tile the rows");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LNX_LAUNCH(MV)                                                                                                    \
+  layernorm_multi_kernel<MV><<<grid, 256, 0, st>>>(x, residual, residual_bias, gamma, beta, rows, channels, eps, out_f32,      \
+                                                   reinterpret_cast<float*>(out_split), split, pos, pos_rows,                  \
+                                                   reinterpret_cast<float*>(out_split_pos))
+  if (channels <= 128) LNX_LAUNCH(1);
+  else if (channels <= 256) LNX_LAUNCH(2);
+  else if (channels <= 512) LNX_LAUNCH(4);
+  else if (channels <= 1024) LNX_LAUNCH(8);
+  else if (channels <= 2048) LNX_LAUNCH(16);
+  else LNX_LAUNCH(32);
+#undef LNX_LAUNCH
+  return check_launch("layernorm_multi");
 }

@@ -68,28 +68,36 @@ class _EncoderLayer(nn.Module):
         self.linear2 = nn.Linear(d_ffn, d_model)
         self.norm2 = nn.LayerNorm(d_model)
 
-    def forward(self, src, pos, shapes, starts):
+    def forward(self, src, pos, shapes, starts, carry=None, emit_next=False):
+        """-> (src_out, carry_out).  `carry` = (operand(src), operand(src + pos)) emitted by the previous layer's last
+        LayerNorm under the fused-glue path (None otherwise / for the first layer)."""
         a = self.self_attn
         N, S, C = src.shape
         w, b = a.fused_offs_logits()
         if nn_ops.fused_glue():
-            # the three linear biases move into the MSDeformAttn kernel (no bias-broadcast copies for the GEMMs) and the
-            # kernel emits the operand of output_proj directly
-            value = nn_ops.linear(src, a.value_proj.weight, None).view(N, S, a.n_heads, C // a.n_heads)
-            offs_logits = nn_ops.linear(src + pos, w, None)
+            # the three linear biases move into the MSDeformAttn kernel (no bias-broadcast copies for the GEMMs), the kernel
+            # emits the operand of output_proj, and each LayerNorm emits the operands of the GEMMs that consume it
+            h_src, h_q = carry if carry is not None else (nn_ops.prep(src), nn_ops.prep(src + pos))
+            value = nn_ops.linear_prepped(h_src, a.value_proj.weight, None).view(N, S, a.n_heads, C // a.n_heads)
+            offs_logits = nn_ops.linear_prepped(h_q, w, None)
             y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points,
                                            value_bias=a.value_proj.bias, offs_logits_bias=b,
                                            split=nn_ops._fmt() if nn_ops.splitting() else None)
             o = nn_ops.linear_prepped(y, a.output_proj.weight, None)
-        else:
-            value = nn_ops.linear(src, a.value_proj.weight, a.value_proj.bias).view(N, S, a.n_heads, C // a.n_heads)
-            offs_logits = nn_ops.linear(src + pos, w, b)
-            y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points)
-            o = nn_ops.linear(y, a.output_proj.weight, None)
+            src, h1, _ = nn_ops.layernorm_multi(src, self.norm1, residual=o, residual_bias=a.output_proj.bias)
+            f = nn_ops.linear_prepped(h1, self.linear1.weight, None)
+            z = nn_ops.linear_prepped(nn_ops.relu(f, bias=self.linear1.bias), self.linear2.weight, None)
+            src, h2, hq2 = nn_ops.layernorm_multi(src, self.norm2, residual=z, residual_bias=self.linear2.bias,
+                                                  pos=pos if emit_next else None, want_operand=emit_next)
+            return src, ((h2, hq2) if emit_next else None)
+        value = nn_ops.linear(src, a.value_proj.weight, a.value_proj.bias).view(N, S, a.n_heads, C // a.n_heads)
+        offs_logits = nn_ops.linear(src + pos, w, b)
+        y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points)
+        o = nn_ops.linear(y, a.output_proj.weight, None)
         src = nn_ops.layernorm(src, self.norm1, residual=o, for_gemm=False, residual_bias=a.output_proj.bias)[1]
         f = nn_ops.linear(src, self.linear1.weight, None)
         z = nn_ops.linear_prepped(nn_ops.relu(f, bias=self.linear1.bias), self.linear2.weight, None)
-        return nn_ops.layernorm(src, self.norm2, residual=z, for_gemm=False, residual_bias=self.linear2.bias)[1]
+        return nn_ops.layernorm(src, self.norm2, residual=z, for_gemm=False, residual_bias=self.linear2.bias)[1], None
 
 
 class _Encoder(nn.Module):
@@ -218,8 +226,10 @@ class MSDeformAttnPixelDecoder(nn.Module):
         starts = [0]
         for h, w in shapes[:-1]:
             starts.append(starts[-1] + h * w)
-        for layer in self.transformer.encoder.layers:
-            src = layer(src, pos, shapes, starts)
+        layers = self.transformer.encoder.layers
+        carry = None
+        for i, layer in enumerate(layers):
+            src, carry = layer(src, pos, shapes, starts, carry, emit_next=i + 1 < len(layers))
         n = src.shape[0]
         out_cl = []
         for i, (h, w) in enumerate(shapes):

@@ -133,6 +133,19 @@ def layernorm(x, norm, residual=None, want_sum=False, for_gemm=True, residual_bi
                          residual_bias)
 
 
+def layernorm_multi(x, norm, residual=None, residual_bias=None, pos=None, want_operand=True):
+    """Post-norm LayerNorm whose result is both the residual stream and GEMM input(s).  Returns
+    (y fp32, operand(y), operand(y + pos) or None); under non-splitting policies the operands are plain fp32 tensors."""
+    if splitting():
+        return ops.layernorm_multi(x.contiguous(), norm.weight, norm.bias, norm.eps,
+                                   None if residual is None else residual.contiguous(), residual_bias, True, _fmt(),
+                                   pos, want_operand)
+    y = ops.layernorm(x.contiguous(), norm.weight, norm.bias, norm.eps,
+                      None if residual is None else residual.contiguous(), False, None, residual_bias)[1]
+    return y, (y if want_operand else None), (None if pos is None else y + pos.view(1, -1, y.shape[-1]).expand(
+        y.numel() // pos.numel(), -1, -1).reshape(y.shape))
+
+
 def layernorm_merge2x2(x_cl, norm):
     """PatchMerging gather + LayerNorm (ops.layernorm_merge2x2), emitted as the operand of the reduction GEMM."""
     return ops.layernorm_merge2x2(x_cl if x_cl.is_contiguous() else x_cl.contiguous(), norm.weight, norm.bias, norm.eps,

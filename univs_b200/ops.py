@@ -465,6 +465,35 @@ def patchify_normalize(frames, pixel_mean, pixel_std, padded_size, patch=4, spli
     return out
 
 
+def layernorm_multi(x, weight, bias, eps=1e-5, residual=None, residual_bias=None, want_f32=True, split=None, pos=None,
+                    want_operand=True):
+    """LayerNorm(x + residual + residual_bias) with several consumers.  Returns (y fp32 or None, operand(y) or None,
+    operand(y + pos[row % pos_rows]) or None); operands in format `split` ("tf32" | "f16" | "f16u")."""
+    x = _chk_t(x, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty_like(x) if want_f32 else None
+    code, mult, dt = _split_code(split, C)
+    op = torch.empty((*x.shape[:-1], mult * C), device=x.device, dtype=dt) if (split and want_operand) else None
+    op_pos = None
+    pos_rows = 0
+    if pos is not None:
+        if not split:
+            raise _cabi.UnivsB200Error("layernorm_multi: pos needs an operand format")
+        pos = _chk_t(pos, "pos")
+        pos_rows = pos.numel() // C
+        op_pos = torch.empty((*x.shape[:-1], mult * C), device=x.device, dtype=dt)
+    with _Bracket("layernorm_multi", 1):
+        rc = lib().univs_layernorm_multi_f32(
+            _stream(), x.data_ptr(), None if residual is None else _chk(residual, "residual"),
+            None if residual_bias is None else _chk(residual_bias, "residual_bias"), _chk(weight, "weight"),
+            _chk(bias, "bias"), rows, C, float(eps), None if y is None else y.data_ptr(),
+            None if op is None else op.data_ptr(), code, None if pos is None else pos.data_ptr(), pos_rows,
+            None if op_pos is None else op_pos.data_ptr())
+    check(rc, "layernorm_multi")
+    return y, op, op_pos
+
+
 def layernorm_merge2x2(x, weight, bias, eps=1e-5, split=None):
     """PatchMerging gather + LayerNorm: x [N,H,W,C] -> [N, ceil(H/2), ceil(W/2), 4C (* split width)]."""
     x = _chk_t(x, "x")
