@@ -82,6 +82,16 @@ int univs_swin_window_attention_f16x3out(void* stream, const float* qkv, const f
                                          const float* rel_bias_table, int batch, int height, int width, int channels,
                                          int num_heads, int window, int shift, void* out16);
 
+/* Same operator for 12x12 windows (Swin-B / Swin-L) with both contractions on the tcgen05 tensor cores: one persistent
+ * CTA per SM, fp16 hi|lo operand tiles in shared memory, S and O accumulated in TMEM, softmax on rows read back with
+ * tcgen05.ld (swin_window_attn_tc.cu).  Strict precision only (same arithmetic contract as UNIVS_PREC_TF32X3 above).
+ * out (f32 [B,H,W,C]) and out16 (__half [B,H,W,3C] operand layout as above, channels <= 1536) are both optional, at
+ * least one must be given.  flags bit 0: stage V transposed and use the K-major B descriptor instead of the MN-major
+ * one.  debug_scores: NULL, or f32 [B*windows*heads, 144, 144] receiving the biased, masked scores before the softmax. */
+int univs_swin_window_attention_tc(void* stream, const float* qkv, const float* qkv_bias, const float* rel_bias_table,
+                                   int batch, int height, int width, int channels, int num_heads, int window, int shift,
+                                   int flags, float* out, void* out16, float* debug_scores);
+
 /* ---- Mask einsum "btqc,btchw->btqhw" + transpose(1,2) (a11), on the tcgen05 tensor cores
  * (TMA -> smem -> tcgen05.mma kind::tf32 -> TMEM -> tcgen05.ld -> coalesced stores).
  * mask_embed [T,Q,C] f32; mask_features channel-last [T,HW,C] f32; out [Q,T,HW] f32.  C % 32 == 0, Q <= 256,

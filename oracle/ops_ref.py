@@ -89,11 +89,12 @@ def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offs_logits, 
 # swin.py:131-171 (attention), :247-289 (pad -> roll -> partition ... reverse -> roll -> crop),
 # :413-440 (shift mask on the padded grid, -100 not -inf).
 # ---------------------------------------------------------------------------
-def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shift):
+def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shift, return_scores=False):
     """qkv [B,H,W,3C] = LN(x) @ Wqkv^T on the UNPADDED token grid WITHOUT the bias (the operator adds
     qkv_bias to every token); pad tokens are zeros after norm1 in the reference (swin.py:247-255),
     so their qkv equals the qkv bias.
-    rel_bias_table [(2w-1)^2, nH].  Returns the attention output (pre-proj) [B,H,W,C]."""
+    rel_bias_table [(2w-1)^2, nH].  Returns the attention output (pre-proj) [B,H,W,C]
+    (with return_scores also the biased, masked pre-softmax scores [B, nW, nH, N, N])."""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     ws = window
@@ -126,12 +127,14 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
         lab = lab.view(nWh, ws, nWw, ws).permute(0, 2, 1, 3).reshape(nWh * nWw, ws * ws)
         m = (lab[:, None, :] != lab[:, :, None]).to(attn.dtype) * -100.0   # [nW,N,N]
         attn = attn + m[None, :, None]
+    scores = attn
     attn = torch.softmax(attn, -1)
     o = attn @ v                                                      # [B,nW,nH,N,d]
     o = o.view(B, nWh, nWw, num_heads, ws, ws, d).permute(0, 1, 4, 2, 5, 3, 6).reshape(B, Hp, Wp, C)
     if shift > 0:
         o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
-    return o[:, :H, :W].contiguous()
+    o = o[:, :H, :W].contiguous()
+    return (o, scores) if return_scores else o
 
 
 # ---------------------------------------------------------------------------

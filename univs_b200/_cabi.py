@@ -19,6 +19,7 @@ SIGNATURES = {
     "univs_ms_deform_attn_encoder_tiled_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "univs_swin_window_attention_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "univs_swin_window_attention_f16x3out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "univs_swin_window_attention_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "univs_mask_einsum_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "univs_mask_einsum_f16x3": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "univs_mask_einsum_mma_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

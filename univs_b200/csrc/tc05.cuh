@@ -1,0 +1,175 @@
+// tcgen05 / TMEM / mbarrier building blocks shared by the tensor-core kernels written after mask_einsum_tc.cu
+// (which keeps its own validated copies).  Encodings follow the PTX ISA tables restated in CuTe's
+// cute/arch/mma_sm100_desc.hpp (instruction descriptor, shared-memory matrix descriptor) and the canonical layouts
+// documented in cute/atom/mma_traits_sm100.hpp; the K-major SWIZZLE_64B / SWIZZLE_128B forms are the ones
+// mask_einsum_tc.cu runs on hardware.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace univs {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void mbar_timeout(int id, uint32_t parity) {
+  printf("univs tc: mbarrier timeout id=%d block=%d thread=%d parity=%u\n", id, (int)blockIdx.x, (int)threadIdx.x, parity);
+  __trap();
+}
+// Phase-parity wait with a wall-clock bound: a protocol bug becomes a trapped launch (reported through
+// cudaGetLastError by the next C-ABI call) instead of a hung GPU.  `id` names the barrier in the message.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int id = 0) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 0xfffu) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > 4000000000ull) {   // 4 s
+        mbar_timeout(id, parity);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma / TMA reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a swizzled operand tile whose rows are ROW bytes (= one swizzle span: 128 ->
+// SWIZZLE_128B, 64 -> SWIZZLE_64B, 32 -> SWIZZLE_32B), consecutive rows ROW bytes apart, 8-row groups 8*ROW bytes apart.
+//   K-major operand : row = M/N index, the ROW bytes are consecutive K elements   ((8,n),(T,2)):((ROW/16,SBO),(1,T))
+//   MN-major operand: row = K index,  the ROW bytes are consecutive M/N elements  ((T,ROW/16,1),(8,k)):((1,T,-),(ROW/16,SBO))
+// Both read SBO (bits 32-45) as the byte distance between 8-row groups; LBO is unused for one swizzle span (set to 1);
+// bit 46 = descriptor version 1 (Blackwell).  Which of the two the MMA assumes is the a_major / b_major bit of the
+// instruction descriptor.  The tile base must be 1024-byte aligned; advancing the start address by 32 bytes inside a row
+// selects the next 16-element K step of a K-major f16 operand.
+template <int ROW>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  static_assert(ROW == 128 || ROW == 64 || ROW == 32, "one swizzle span per row");
+  constexpr uint64_t layout = ROW == 128 ? 2 : (ROW == 64 ? 4 : 6);
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((8 * ROW) >> 4) << 32) |
+         ((uint64_t)1 << 46) | (layout << 61);
+}
+// Instruction descriptor, kind::f16 with fp16 operands and fp32 accumulation.
+//   bits 4-5 D format (1 = f32), 7-9 / 10-12 A / B format (0 = f16), 15 / 16 A / B major (1 = MN-major),
+//   17-22 N >> 3, 24-28 M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int Nn, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u) | ((uint32_t)(Nn >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of the 16-byte chunk `chunk` of row `row` in a swizzled tile with ROW-byte rows (Swizzle<log2(ROW/16),4,3>
+// on the byte address: the chunk index is XORed with the row bits that sit log2(ROW) .. above it)
+template <int ROW>
+__host__ __device__ constexpr uint32_t swz_off(int row, int chunk) {
+  return ROW == 128 ? (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4))
+                    : (ROW == 64 ? (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4))
+                                 : (uint32_t)(row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4)));
+}
+
+#define UNIVS_TMEM_LD_X8(taddr, r)                                                                              \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                        \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
+               : "r"(taddr))
+#define UNIVS_TMEM_LD_X16(taddr, r)                                                                                  \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                     \
+      : "r"(taddr))
+#define UNIVS_TMEM_LD_X32(taddr, r)                                                                                    \
+  asm volatile(                                                                                                        \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19," \
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                       \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),    \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),         \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),        \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                      \
+      : "r"(taddr))
+
+// fp32 -> fp16 hi + fp16 lo (hi + lo carries ~22 significand bits), two values at a time
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+
+}  // namespace tc
+}  // namespace univs

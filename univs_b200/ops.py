@@ -155,10 +155,37 @@ def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits
     return out
 
 
+_win_tc = int(os.environ.get("UNIVS_WIN_TC", "0"))   # opt-in: 1 = tcgen05 kernel for 12x12 windows, 3 = with transposed V
+
+
+def swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, want_f32=True, want_operand=False,
+                             flags=0, debug_scores=False):
+    """12x12-window attention on the tcgen05 tensor cores (univs_swin_window_attention_tc).  Returns
+    (out f32 [B,H,W,C] | None, operand f16 [B,H,W,3C] | None[, scores f32 [units,144,144]])."""
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    out = torch.empty((B, H, W, C), device=qkv.device, dtype=torch.float32) if want_f32 else None
+    op = torch.empty((B, H, W, 3 * C), device=qkv.device, dtype=torch.float16) if want_operand else None
+    dbg = None
+    if debug_scores:
+        units = B * (-(-H // 12)) * (-(-W // 12)) * num_heads
+        dbg = torch.zeros((units, 144, 144), device=qkv.device, dtype=torch.float32)
+    with _Bracket("swin_window_attention", 1):
+        rc = lib().univs_swin_window_attention_tc(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
+                                                  _chk(rel_bias_table, "rel_bias_table"), B, H, W, C, num_heads, 12,
+                                                  shift, flags, None if out is None else out.data_ptr(),
+                                                  None if op is None else op.data_ptr(),
+                                                  None if dbg is None else dbg.data_ptr())
+    check(rc, "swin_window_attention_tc")
+    return (out, op, dbg) if debug_scores else (out, op)
+
+
 def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shift, precision=None):
     """qkv [B,H,W,3C] (bias-free GEMM output; the kernel adds qkv_bias) -> [B,H,W,C] (see include/univs_b200.h)"""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
+    if _win_tc and window == 12 and (_default_precision if precision is None else precision) == PREC_TF32X3:
+        return swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, flags=_win_tc >> 1)[0]
     out = torch.empty((B, H, W, C), device=qkv.device, dtype=torch.float32)
     with _Bracket("swin_window_attention", 1):
         rc = lib().univs_swin_window_attention_f32(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
@@ -174,6 +201,9 @@ def swin_window_attention_operand(qkv, qkv_bias, rel_bias_table, num_heads, wind
     [lo*2^11 | hi*2^-11 | hi] (the A operand of the projection GEMM; C <= 1536)."""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
+    if _win_tc and window == 12:
+        return swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, want_f32=False,
+                                        want_operand=True, flags=_win_tc >> 1)[1]
     out = torch.empty((B, H, W, 3 * C), device=qkv.device, dtype=torch.float16)
     with _Bracket("swin_window_attention", 1):
         rc = lib().univs_swin_window_attention_f16x3out(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
