@@ -134,6 +134,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("UNIVS_PRECISION", "fp16x3"), choices=["fp16x3", "tf32x3", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the clip eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--shard-decoder", action="store_true",
+                    help="N>1: keep the decoder frame-sharded and exchange query tokens per layer instead of all-gathering "
+                         "the pixel features (also UNIVS_SHARD_DECODER=1)")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: after warm-up run ONE step between cudaProfilerStart/Stop and exit "
                          "(use with `ncu --profile-from-start off`); prints no bench line")
@@ -166,6 +169,8 @@ def main():
     g = torch.Generator().manual_seed(0)
     cfg = make_cfg(variant, Q, T, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
     model = build_model(cfg, process_group=group).to(dev)
+    if args.shard_decoder:
+        model.shard_decoder = True
     frames_host = (torch.rand(T, 3, H, W, generator=g) * 255).to(torch.uint8).pin_memory()
     frames_dev = frames_host.to(dev)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
@@ -297,7 +302,9 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"fp16x3": "fp16x3 (2-term fp16 split operands, fp32-equivalent products, fp32 accumulate)", "tf32x3": "tf32x3 (3-pass TF32 split, fp32-equivalent products, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init",
-                       "precision": args.precision, "parallelism": f"frame-shard x{world}" if world > 1 else "single",
+                       "precision": args.precision, "parallelism": (f"frame-shard x{world}" + (", frame-sharded decoder (token all-gather per layer)"
+                                                                  if model.shard_decoder else ", feature all-gather"))
+                       if world > 1 else "single",
                        "execution": "CUDA graph replay" if use_graph else "eager",
                        "l2": "per-step working set (multi-GB activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,

@@ -17,15 +17,17 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
 from . import nn_ops
 from .registry import META_ARCH_REGISTRY, build_backbone, build_sem_seg_head
-from .sharding import FrameSharder
+from .sharding import FrameSharder, TokenExchange
 
 
 @META_ARCH_REGISTRY.register()
 class UniVS_Prompt(nn.Module):
     def __init__(self, cfg=None, *, backbone=None, sem_seg_head=None, pixel_mean=None, pixel_std=None,
-                 size_divisibility=32, num_frames=5, process_group=None):
+                 size_divisibility=32, num_frames=5, process_group=None, shard_decoder=None):
         super().__init__()
         if cfg is not None:
             backbone = build_backbone(cfg)
@@ -42,6 +44,8 @@ class UniVS_Prompt(nn.Module):
         self.register_buffer("pixel_mean", torch.tensor(pixel_mean, dtype=torch.float32).view(-1, 1, 1), False)
         self.register_buffer("pixel_std", torch.tensor(pixel_std, dtype=torch.float32).view(-1, 1, 1), False)
         self.sharder = FrameSharder(process_group)
+        # frame-sharded decoder with per-layer token exchange instead of the feature all-gather (opt-in)
+        self.shard_decoder = (os.environ.get("UNIVS_SHARD_DECODER", "0") == "1") if shard_decoder is None else shard_decoder
         self.eval()
 
     @property
@@ -102,9 +106,17 @@ class UniVS_Prompt(nn.Module):
         if self.sharder.world_size == 1:
             features = self.backbone_from_frames(frames) if fused else self.backbone(x)
             return self.sem_seg_head(features, targets=targets)
+        pd = self.sem_seg_head.pixel_decoder
+        dec = self.sem_seg_head.predictor
+        if self.shard_decoder and dec.supports_exchange(targets):
+            # frames stay on their rank through the decoder; only query tokens are exchanged (sharding.TokenExchange)
+            ex = TokenExchange(self.sharder, T)
+            local = (frames if fused else x)[ex.frames]
+            features = self.backbone_from_frames(local) if fused else self.backbone(local)
+            mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(features)
+            return dec(multi_scale, mask_features, mf_bfe, None, targets, exchange=ex)
         # frame-sharded: local frames -> backbone -> pixel decoder -> all-gather -> decoder
         local = self.sharder.local_frames(frames if fused else x)
-        pd = self.sem_seg_head.pixel_decoder
         if local.shape[0] > 0:
             features = self.backbone_from_frames(local) if fused else self.backbone(local)
             mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(features)

@@ -319,7 +319,7 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         y = nn_ops.layernorm(tok, layer.norm, residual=o, for_gemm=False, residual_bias=mha.out_proj.bias)[1]   # [P,T,C]
         return torch.cat([x[:, :nq], y.transpose(0, 1)], 1)
 
-    def _heads(self, x, feats_cl, hw, next_hw, task, targets, t, need_class, need_attn, out_buf=None):
+    def _heads(self, x, feats_cl, hw, next_hw, task, targets, t, need_class, need_attn, out_buf=None, exchange=None):
         """forward_prediction_heads (:498-567).  x [T,Q,C] -> (class logits | None, mask logits [Q,T,HW], bits, row_open, reid)"""
         dec, dec_g = nn_ops.layernorm(x, self.decoder_norm, want_sum=False, for_gemm=False)[1], None
         dec_g = nn_ops.prep(dec)                                            # GEMM operand of decoder_norm(x)
@@ -330,7 +330,10 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
                 if need_class:
                     clip = self._clip_normalized(x.device)
                     # mean over T commutes with the (linear) class einsum: average first, 1/T of the work
-                    cls = nn_ops.linear(F.normalize(oc, p=2, dim=-1).mean(0, keepdim=True), clip) * self.cls_temp.weight.exp()
+                    ocn = F.normalize(oc, p=2, dim=-1)
+                    if exchange is not None:                                # frame-sharded decoder: the mean needs all frames
+                        ocn = exchange.gather(ocn)
+                    cls = nn_ops.linear(ocn.mean(0, keepdim=True), clip) * self.cls_temp.weight.exp()
             else:
                 exp = torch.stack([tg["exp_sentence_feats"][:, 0] for tg in targets]).to(oc)      # [1,P,640]
                 cls = nn_ops.linear(oc.mean(0, keepdim=True), exp[0].contiguous(), cache=False)
@@ -425,14 +428,31 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         raise ValueError(task)
 
     # ------------------------------------------------------------------ forward
+    def supports_exchange(self, targets):
+        """The frame-sharded (token-exchange) decoder covers the clip paths whose prompt handling is per-frame:
+        detection with learnable queries and with category prompts.  Visual prompts (memory pool across frames) and
+        grounding (cross-frame reid fusion) go through the feature all-gather instead."""
+        tg = targets[0]
+        has_masks = "masks" in tg and torch.is_tensor(tg["masks"]) and tg["masks"].nelement() > 0
+        return (tg["task"] == "detection" and not has_masks and "prompt_feats" not in tg
+                and not self.return_aux_outputs and not self.semantic_extraction_enable)
+
     @torch.no_grad()
-    def forward(self, x, mask_features, mask_features_bfe_conv=None, mask=None, targets=None):
+    def forward(self, x, mask_features, mask_features_bfe_conv=None, mask=None, targets=None, exchange=None):
+        """exchange: None, or a sharding.TokenExchange -- x / mask_features then hold only this rank's frames and the
+        decoder stays frame-sharded (SURVEY.md 8e "cheaper alternative"); every rank returns the full-clip outputs."""
         if self.training:
             raise NotImplementedError("the B200 decoder implements the inference path only")
         assert len(x) == self.num_feature_levels
         t, c_m, h_m, w_m = mask_features.shape                              # bs = 1 at inference (:309-311)
         device = mask_features.device
         task = targets[0]["task"]
+        t_all = t
+        if exchange is not None:
+            if not self.supports_exchange(targets):
+                raise NotImplementedError("token-exchange decoder: detection clips without visual prompts only")
+            t_all = exchange.num_frames
+            assert t == len(exchange.frames)
         feats_cl = mask_features.permute(0, 2, 3, 1)                        # [T,H,W,C]
         if not feats_cl.is_contiguous():
             feats_cl = feats_cl.contiguous()
@@ -440,7 +460,9 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         if "frame_indices" in targets[0]:
             frame_indices = targets[0]["frame_indices"]
         else:
-            frame_indices = torch.arange(t, device=device)
+            frame_indices = torch.arange(t_all, device=device)
+        if exchange is not None:
+            frame_indices = frame_indices.to(device).index_select(0, exchange.frames_tensor(device))
         src, pos, size_list = [], [], []
         for i in range(3):
             n, c, h, w = x[i].shape
@@ -470,10 +492,12 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
 
         hw = (h_m, w_m)
         self._head_calls = 0
-        cls, logits, bits, row_open, reid = self._heads(out, feats_cl, hw, size_list[0], task, targets, t, want_aux, True)
+        cls, logits, bits, row_open, reid = self._heads(out, feats_cl, hw, size_list[0], task, targets, t, want_aux, True,
+                                                        exchange=exchange)
         if want_aux:
             record(cls, logits, reid, out)
-        sa_bits = self._self_attn_mask_bits(t, n_lp, device, task)
+        sa_bits = self._self_attn_mask_bits(t_all, n_lp, device, task)
+        qpos_all = exchange.gather(qpos) if exchange is not None else None   # constant over the layers
         for i in range(self.num_layers):
             if self.prompt_as_queries and 0 < i < self.prompt_self_attn_layers:
                 out = self._proca(i, out, qpos, mem, mem_pe)
@@ -483,17 +507,25 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
             k = nn_ops.linear(src[lvl] + pos[lvl], wk, None)      # biases handled in _cross_attention
             v = nn_ops.linear(src[lvl], wv, None)
             out = self._cross_attention(self.transformer_cross_attention_layers[i], out, qpos, k, v, bits, row_open)
-            out = self._self_attention(self.transformer_self_attention_layers[i], out, qpos, sa_bits)
+            if exchange is None:
+                out = self._self_attention(self.transformer_self_attention_layers[i], out, qpos, sa_bits)
+            else:       # the Q*T self-attention is the one step that sees all frames: tokens travel, features stay
+                out = exchange.local(self._self_attention(self.transformer_self_attention_layers[i],
+                                                          exchange.gather(out), qpos_all, sa_bits))
             out = self.transformer_ffn_layers[i](out)
             last = i == self.num_layers - 1
             cls, logits, bits, row_open, reid = self._heads(
-                out, feats_cl, hw, size_list[(i + 1) % 3], task, targets, t, want_aux or last, not last, out_buf=logits)
+                out, feats_cl, hw, size_list[(i + 1) % 3], task, targets, t, want_aux or last, not last, out_buf=logits,
+                exchange=exchange)
             if want_aux and not last:
                 record(cls, logits, reid, out)
         embds = nn_ops.layernorm(out.transpose(0, 1), self.decoder_norm, for_gemm=False)[1][None]   # [1,Q,T,C]
+        if exchange is not None:        # full-clip outputs on every rank
+            embds = exchange.gather(embds[0].transpose(0, 1)).transpose(0, 1).contiguous()[None]
+            logits = exchange.gather(logits.transpose(0, 1)).transpose(0, 1).contiguous()
         result = {
             "pred_logits": cls,
-            "pred_masks": logits.view(1, n_lp, t, h_m, w_m),
+            "pred_masks": logits.view(1, n_lp, t_all, h_m, w_m),
             "aux_outputs": aux,
             "pred_embds": embds,
             "pred_reid_logits": reid,

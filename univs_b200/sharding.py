@@ -3,7 +3,12 @@
 Backbone and pixel decoder treat frames as the batch dimension with no cross-frame operation, so rank r owns frames
 {f : f mod n == r}.  The only exchange step is one all-gather of the per-frame {mask_features, 3 multi-scale maps}
 before the decoder.  Ragged clips (T not a multiple of n) are padded to ceil(T/n) frames per rank for the collective;
-padding frames are zeros and are dropped after the gather.  Works with NCCL (GPU) and gloo (CPU tests)."""
+padding frames are zeros and are dropped after the gather.  Works with NCCL (GPU) and gloo (CPU tests).
+
+`TokenExchange` is the cheaper alternative of SURVEY.md 8e: cross-attention, mask einsum and attention-mask generation
+are per-frame too, so the decoder can stay frame-sharded and only the [Q,256] query tokens of each frame travel (one
+small all-gather per decoder layer for the Q*T self-attention, one for the T-mean of the class logits, one for the final
+mask logits) instead of 80 MB of features per frame."""
 from __future__ import annotations
 
 import torch
@@ -64,3 +69,30 @@ class FrameSharder:
             outs.append(flat[:, off:off + ne].reshape(num_frames, *s))
             off += ne
         return outs
+
+
+class TokenExchange:
+    """Frame-sharded decoder plumbing.  Rank r keeps frames {f : f mod n == r} through the decoder; `gather` reassembles a
+    per-frame tensor [T_local, ...] to [T, ...] in global frame order on every rank, `local` selects this rank's frames
+    again.  With more ranks than frames a rank without a frame shadows frame (rank mod T): it computes like its owner
+    (so every rank runs the same program and reaches every collective) but contributes nothing to the gathers."""
+
+    def __init__(self, sharder: FrameSharder, num_frames: int):
+        own = frame_plan(num_frames, sharder.world_size)[sharder.rank]
+        self.sharder = sharder
+        self.num_frames = num_frames
+        self.shadow = not own
+        self.frames = own if own else [sharder.rank % num_frames]
+        self._idx = {}
+
+    def frames_tensor(self, device):
+        key = str(device)
+        if key not in self._idx:
+            self._idx[key] = torch.tensor(self.frames, dtype=torch.long, device=device)
+        return self._idx[key]
+
+    def gather(self, x):
+        return self.sharder.all_gather_frames([x[:0] if self.shadow else x], self.num_frames)[0]
+
+    def local(self, x):
+        return x.index_select(0, self.frames_tensor(x.device))
