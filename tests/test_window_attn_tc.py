@@ -5,7 +5,7 @@ compile-time constant, shift-mask region bits, roll/pad source addressing); the 
 Python and checked against the oracle's explicit construction (oracle/ops_ref.py::swin_window_attention, which follows
 swin.py:108-121, 247-289, 413-440).
 GPU part (opt-in until it has run on a B200: UNIVS_GPU_WINTC=1): parity of scores, output and GEMM-operand output
-against the oracle, both V staging modes."""
+against the oracle and the mma.sync kernel."""
 import os
 
 import pytest
@@ -109,14 +109,13 @@ def _rel(a, b):
 
 @pytest.mark.gpu
 @_gpu_wintc
-@pytest.mark.parametrize("flags", [0, 1])
 @pytest.mark.parametrize("B,H,W,nH,shift", [
     (1, 12, 12, 1, 0),          # one unit
     (1, 24, 36, 2, 0), (2, 24, 27, 4, 6), (1, 46, 80, 6, 6),
     (3, 23, 40, 24, 6),         # more units than SMs: persistent loop, both ring stages, stage reuse
     (1, 92, 160, 12, 6),
 ])
-def test_window_attention_tc(B, H, W, nH, shift, flags):
+def test_window_attention_tc(B, H, W, nH, shift):
     from univs_b200 import ops
     torch.manual_seed(7)
     C = 32 * nH
@@ -125,7 +124,7 @@ def test_window_attention_tc(B, H, W, nH, shift, flags):
     table = torch.randn(23 * 23, nH) * 0.5
     want, scores = ops_ref.swin_window_attention(qkv, bias, table, nH, 12, shift, return_scores=True)
     out, op, dbg = ops.swin_window_attention_tc(qkv.cuda(), bias.cuda(), table.cuda(), nH, shift, want_f32=True,
-                                                want_operand=True, flags=flags, debug_scores=True)
+                                                want_operand=True, debug_scores=True)
     torch.cuda.synchronize()
     assert _rel(dbg.view(scores.shape), scores) < 2e-5, "QK^T + bias + mask"
     assert _rel(out, want) < 2e-5, "softmax / PV / store"

@@ -10,22 +10,25 @@
 //   warps 12-15  loaders : gather q/k/v rows through the roll/pad addressing (128-bit loads, 9 in flight per thread), add
 //                          the qkv bias, scale q, split fp32 -> fp16 hi + lo once, store K-major SWIZZLE_64B operand
 //                          tiles (64-byte rows = 32 dims) + the head's relative-position table; 2-stage ring
-//   warp 9       MMA     : one elected lane issues  S = Ql Kh^T + Qh Kl^T + Qh Kh^T  (M=128, N=144, K=32: 6 MMAs) and
-//                          O = Pl Vh + Ph Vl + Ph Vh  (M=128, N=32, K=144: 27 MMAs) per row tile; V is consumed as stored
-//                          ([key][dim] rows) through the MN-major B descriptor (flag 1: transposed-V K-major fallback)
-//   warps 0-7    softmax of row tile 0 (rows 0-127): warp = (TMEM lane quarter, column half); a thread owns 72 scores of
-//                          one row; the halves exchange max / sum through shared memory (64-thread named barrier)
-//   warp 8       softmax of the tail tile (rows 128-143): the loader stores those 16 Q rows twice, so TMEM lanes 0-15
-//                          and 16-31 hold the same rows; lanes 0-15 take columns 0-71, lanes 16-31 columns 72-143 and
-//                          zero the other half of their P row, so the PV MMA leaves two partial sums that the epilogue
-//                          adds with one shuffle -- every softmax thread does the same 72-column job.
+//   warp 9       MMA     : one elected lane issues  S = Ql Kh^T + Qh Kl^T + Qh Kh^T  and  O = Pl Vh + Ph Vl + Ph Vh;
+//                          V is consumed as stored ([key][dim] rows) through the MN-major B descriptor
+//   warps 0-7    softmax of row tile 0 (query rows 0-127; M=128, N=144): warp = (TMEM lane quarter, column half); a thread
+//                          owns 72 scores of one row; the halves exchange max / sum through shared memory
+//   warp 8       softmax of the tail tile (query rows 128-143).  tcgen05.ld addresses are warp-uniform, so the two lane
+//                          halves cannot read different columns; instead the MMA puts different KEYS under the same
+//                          columns: the 16 tail rows of Q sit between two blocks of 16 zero rows ("Z Q Z"), the A tile
+//                          starting at Z (rows = [0 | Q]) multiplies keys 64-143 (N=80, overwrite), the A tile starting
+//                          at Q (rows = [Q | 0]) multiplies keys 0-63 (N=64, accumulate): TMEM lanes 0-15 end up with
+//                          keys 0-63 of the 16 rows, lanes 16-31 with keys 64-143 of the same rows, both in columns
+//                          0-79.  Each lane writes its part of its P row and zeros elsewhere, the PV MMA leaves two
+//                          partial sums per row and the epilogue adds them with one shuffle.
 //   warp 10      TMEM allocator; warp 11 idle.
 // Softmax warps run  softmax(n+1) -> epilogue(n), the MMA lane  S(n+1) -> PV(n), so the tensor pipe works on the next
 // unit's scores while the softmax of the current one is in flight, and no softmax warp waits for a PV it just enabled.
-// TMEM columns: S tile0 [0,144)  S tail [160,304)  O tile0 [320,352)  O tail [352,384).
+// TMEM columns: S tile0 [0,144)  S tail [160,240)  O tile0 [320,352)  O tail [352,384).
 //
 // HBM-bound by design: per unit 55.3 KB of qkv in, 18.4 KB (fp32) or 27.6 KB (fp16x3 operand) out; tensor work per unit
-// is 33 MMAs (~1.7k tensor cycles), the issue-slot budget is dominated by the softmax (~9 instructions per score).
+// is 45 MMAs (~1.5k tensor cycles), the issue-slot budget is dominated by the softmax (~9 instructions per score).
 #include "tc05.cuh"
 
 namespace univs {
@@ -41,29 +44,34 @@ constexpr int kAllocWarp = 10;
 constexpr int kLoaderWarp0 = 12;
 constexpr int kLoaderThreads = 128;
 constexpr int kTable = 23 * 23;
+constexpr int kTailKeys0 = 64;                 // keys of the tail rows handled by TMEM lanes 0-15 (lanes 16-31: the other 80)
 
 // ---- shared memory map (bytes); every operand tile base is a multiple of 1024 --------------------------------------
 constexpr int kRow = 64;                       // operand row: 32 halfs = one SWIZZLE_64B span
-constexpr int kQBytes = 160 * kRow;            // 144 rows + the 16 tail rows once more (MMA of the tail tile reads
-                                               // 128 rows from row 128 on: whatever follows is garbage in unused lanes)
+constexpr int kQTailOff = 128 * kRow;          // "Z Q Z": 16 zero rows, the 16 tail rows, 16 zero rows
+constexpr int kQBytes = kQTailOff + 48 * kRow; // 11264 (an MMA reads 128 rows from its start: what follows is garbage in
+                                               // TMEM lanes nobody reads)
 constexpr int kKBytes = kN * kRow;             // 9216
-constexpr int kVBytes = 10 * 1024;             // [key][dim]: 9216 used; transposed fallback: 5 atoms x 32 dims x 64 B
+constexpr int kVBytes = kN * kRow;             // [key][dim] rows, MN-major B operand
 constexpr int kOffQh = 0, kOffQl = kQBytes, kOffKh = 2 * kQBytes, kOffKl = kOffKh + kKBytes;
 constexpr int kOffVh = kOffKl + kKBytes, kOffVl = kOffVh + kVBytes;
 constexpr int kStageBytes = kOffVl + kVBytes;  // 59392
 constexpr int kP1Atom = 32 * kRow;             // tail tile: 32 valid rows per 32-key atom
 constexpr int kP0Atom = 128 * kRow;            // 8192
-constexpr int kP1Bytes = 5 * kP1Atom;          // 10240 (MMA reads up to 6 KB past it: lands in the P0 buffers)
+constexpr int kP1Bytes = 5 * kP1Atom;          // 10240 (the MMA reads up to 6 KB past it: lands in the P0 buffers)
 constexpr int kP0Bytes = 5 * kP0Atom;          // 40960
 constexpr int kOffP1h = 2 * kStageBytes, kOffP1l = kOffP1h + kP1Bytes;
 constexpr int kOffP0h = kOffP1l + kP1Bytes, kOffP0l = kOffP0h + kP0Bytes;
 constexpr int kOffBias = kOffP0l + kP0Bytes;   // 2 x 544 floats
 constexpr int kBiasStride = 544;
 constexpr int kOffXch = kOffBias + 2 * kBiasStride * 4;   // max[2 parity][2 half][128] + sum[2][2][128] floats
-constexpr int kOffBars = kOffXch + 2 * 2 * 2 * 128 * 4;
+constexpr int kOffKidx = kOffXch + 2 * 2 * 2 * 128 * 4;   // int[144]: key -> ky * 23 + kx
+constexpr int kOffBars = kOffKidx + kN * 4;
 constexpr int kNumBars = 16;
 constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
-static_assert(kStageBytes % 1024 == 0 && kOffP1h % 1024 == 0 && kOffP0h % 1024 == 0 && kOffP0l % 1024 == 0, "tile alignment");
+static_assert(kQBytes % 1024 == 0 && kStageBytes % 1024 == 0 && kOffP1h % 1024 == 0 && kOffP0h % 1024 == 0 &&
+                  kOffP0l % 1024 == 0 && kOffBars % 8 == 0,
+              "tile alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 constexpr uint32_t kColS0 = 0, kColS1 = 160, kColO0 = 320, kColO1 = 352;
@@ -96,51 +104,39 @@ __device__ __forceinline__ int source_token(const Geo& g, const Unit& un, int i)
 }
 
 // ---- loader ----------------------------------------------------------------------------------------------------------
-template <bool VT>
 __device__ __forceinline__ void store_token(unsigned char* st, int i, int lane8, float4 q, float4 k, float4 v) {
   uint32_t h0, h1, l0, l1;
-  const uint32_t off = swz_off<kRow>(i, lane8 >> 1) + (lane8 & 1) * 8;
+  const uint32_t sub = (uint32_t)(lane8 & 1) * 8u;
+  const uint32_t off = swz_off<kRow>(i, lane8 >> 1) + sub;
+  // query rows 0-127: tile 0; rows 128-143: rows 16-31 of the "Z Q Z" block behind it
+  const uint32_t qoff = i < 128 ? off : (uint32_t)kQTailOff + swz_off<kRow>(16 + (i - 128), lane8 >> 1) + sub;
   split_h2(q.x, q.y, h0, l0);
   split_h2(q.z, q.w, h1, l1);
-  sts_v2(smem_u32(st + kOffQh) + off, h0, h1);
-  sts_v2(smem_u32(st + kOffQl) + off, l0, l1);
-  if (i >= 128) {   // tail rows once more, 16 rows further down
-    const uint32_t off2 = swz_off<kRow>(i + 16, lane8 >> 1) + (lane8 & 1) * 8;
-    sts_v2(smem_u32(st + kOffQh) + off2, h0, h1);
-    sts_v2(smem_u32(st + kOffQl) + off2, l0, l1);
-  }
+  sts_v2(smem_u32(st + kOffQh) + qoff, h0, h1);
+  sts_v2(smem_u32(st + kOffQl) + qoff, l0, l1);
   split_h2(k.x, k.y, h0, l0);
   split_h2(k.z, k.w, h1, l1);
   sts_v2(smem_u32(st + kOffKh) + off, h0, h1);
   sts_v2(smem_u32(st + kOffKl) + off, l0, l1);
   split_h2(v.x, v.y, h0, l0);
   split_h2(v.z, v.w, h1, l1);
-  if (!VT) {
-    sts_v2(smem_u32(st + kOffVh) + off, h0, h1);
-    sts_v2(smem_u32(st + kOffVl) + off, l0, l1);
-  } else {
-    // transposed: row = dim, 32-key atoms of 32 rows x 64 B
-    const uint32_t hv[2] = {h0, h1}, lv[2] = {l0, l1};
-    __half* vh = reinterpret_cast<__half*>(st + kOffVh);
-    __half* vl = reinterpret_cast<__half*>(st + kOffVl);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = lane8 * 4 + e;
-      const uint32_t o = (uint32_t)(i >> 5) * 2048u + swz_off<kRow>(d, (i & 31) >> 3) + (uint32_t)(i & 7) * 2u;
-      const uint32_t hw = hv[e >> 1], lw = lv[e >> 1];
-      vh[o >> 1] = __ushort_as_half((unsigned short)((e & 1) ? (hw >> 16) : (hw & 0xffffu)));
-      vl[o >> 1] = __ushort_as_half((unsigned short)((e & 1) ? (lw >> 16) : (lw & 0xffffu)));
-    }
-  }
+  sts_v2(smem_u32(st + kOffVh) + off, h0, h1);
+  sts_v2(smem_u32(st + kOffVl) + off, l0, l1);
 }
 
-template <bool VT>
 __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const float* __restrict__ qkv,
                             const float* __restrict__ qkv_bias, const float* __restrict__ table, const Geo g,
                             long long units, float scale) {
   const int lt = threadIdx.x - kLoaderWarp0 * 32;
   const int lane8 = lt & 7, slot = lt >> 3;
   const int C = g.C;
+  // the zero rows of the "Z Q Z" blocks (both stages, hi and lo) are written once; token stores never touch them
+  for (int i = lt; i < 2 * 2 * 2 * 16 * 4; i += kLoaderThreads) {     // stage x {hi,lo} x {first,last Z} x 16 rows x 4 chunks
+    const int chunk = i & 3, row = (i >> 2) & 15, z = (i >> 6) & 1, hl = (i >> 7) & 1, s = i >> 8;
+    sts_v4(smem_u32(smem + (size_t)s * kStageBytes + (hl ? kOffQl : kOffQh) + kQTailOff) + (uint32_t)(z * 32 + row) * kRow +
+               (uint32_t)chunk * 16u,
+           0u, 0u, 0u, 0u);
+  }
   int it = 0;
   for (long long u = blockIdx.x; u < units; u += gridDim.x, ++it) {
     const int s = it & 1;
@@ -173,7 +169,7 @@ __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const float* __
         qq.x = (qq.x + bq.x) * scale; qq.y = (qq.y + bq.y) * scale; qq.z = (qq.z + bq.z) * scale; qq.w = (qq.w + bq.w) * scale;
         kk.x += bk.x; kk.y += bk.y; kk.z += bk.z; kk.w += bk.w;
         vv.x += bv.x; vv.y += bv.y; vv.z += bv.z; vv.w += bv.w;
-        store_token<VT>(st, i, lane8, qq, kk, vv);
+        store_token(st, i, lane8, qq, kk, vv);
       }
     }
     fence_proxy_async_smem();
@@ -182,38 +178,47 @@ __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const float* __
 }
 
 // ---- MMA issuer --------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void issue_scores(uint32_t stage_addr, int tile, uint32_t tmem_base) {
-  constexpr uint32_t idesc = make_idesc_f16(128, kN, false, false);
-  const uint32_t qoff = (uint32_t)tile * 128u * kRow;
-  const uint64_t ah = make_desc<kRow>(stage_addr + kOffQh + qoff), al = make_desc<kRow>(stage_addr + kOffQl + qoff);
-  const uint64_t bh = make_desc<kRow>(stage_addr + kOffKh), bl = make_desc<kRow>(stage_addr + kOffKl);
-  const uint32_t d = tmem_base + (tile ? kColS1 : kColS0);
+// three MMAs per 16-dim k-step: lo*hi + hi*lo + hi*hi (correction terms first)
+__device__ __forceinline__ void issue_qk(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+                                         bool accumulate) {
+  const uint64_t ah = make_desc<kRow>(a_hi), al = make_desc<kRow>(a_lo);
+  const uint64_t bh = make_desc<kRow>(b_hi), bl = make_desc<kRow>(b_lo);
 #pragma unroll
   for (int k = 0; k < 2; ++k) {   // 16 dims = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-    umma_f16(d, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, k ? 1u : 0u);   // lo * hi
-    umma_f16(d, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);            // hi * lo
-    umma_f16(d, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);            // hi * hi
+    umma_f16(d, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, (accumulate || k) ? 1u : 0u);
+    umma_f16(d, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
+    umma_f16(d, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
   }
 }
-template <bool VT>
-__device__ __forceinline__ void issue_pv(uint32_t smem_base, uint32_t stage_addr, int tile, uint32_t tmem_base) {
-  constexpr uint32_t idesc = make_idesc_f16(128, 32, false, !VT);
+__device__ __forceinline__ void issue_scores(uint32_t st, int tile, uint32_t tmem_base) {
+  if (tile == 0) {
+    issue_qk(tmem_base + kColS0, st + kOffQh, st + kOffQl, st + kOffKh, st + kOffKl, make_idesc_f16(128, kN, false, false), false);
+  } else {
+    // A = [0 | Q_tail] x keys 64..143 (overwrites columns 0-79), then A = [Q_tail | 0] x keys 0..63 (accumulates into 0-63)
+    constexpr uint32_t k1 = (uint32_t)kTailKeys0 * kRow;
+    issue_qk(tmem_base + kColS1, st + kOffQh + kQTailOff, st + kOffQl + kQTailOff, st + kOffKh + k1, st + kOffKl + k1,
+             make_idesc_f16(128, kN - kTailKeys0, false, false), false);
+    issue_qk(tmem_base + kColS1, st + kOffQh + kQTailOff + 16 * kRow, st + kOffQl + kQTailOff + 16 * kRow, st + kOffKh,
+             st + kOffKl, make_idesc_f16(128, kTailKeys0, false, false), true);
+  }
+}
+__device__ __forceinline__ void issue_pv(uint32_t smem_base, uint32_t st, int tile, uint32_t tmem_base) {
+  constexpr uint32_t idesc = make_idesc_f16(128, 32, false, true);   // B = V [key][dim]: MN-major
   const uint32_t ph = smem_base + (tile ? kOffP1h : kOffP0h), pl = smem_base + (tile ? kOffP1l : kOffP0l);
   const uint32_t atom = tile ? kP1Atom : kP0Atom;
   const uint32_t d = tmem_base + (tile ? kColO1 : kColO0);
 #pragma unroll
   for (int s = 0; s < 9; ++s) {   // 16 keys per step
     const uint32_t aoff = (uint32_t)(s >> 1) * atom + (uint32_t)(s & 1) * 32u;
-    const uint32_t boff = VT ? (uint32_t)(s >> 1) * 2048u + (uint32_t)(s & 1) * 32u : (uint32_t)s * 16u * kRow;
+    const uint32_t boff = (uint32_t)s * 16u * kRow;
     const uint64_t ah = make_desc<kRow>(ph + aoff), al = make_desc<kRow>(pl + aoff);
-    const uint64_t bh = make_desc<kRow>(stage_addr + kOffVh + boff), bl = make_desc<kRow>(stage_addr + kOffVl + boff);
+    const uint64_t bh = make_desc<kRow>(st + kOffVh + boff), bl = make_desc<kRow>(st + kOffVl + boff);
     umma_f16(d, al, bh, idesc, s ? 1u : 0u);
     umma_f16(d, ah, bl, idesc, 1u);
     umma_f16(d, ah, bh, idesc, 1u);
   }
 }
 
-template <bool VT>
 __device__ void mma_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_base, int count) {
   const uint32_t smem_base = smem_u32(smem);
   for (int n = -1; n < count; ++n) {
@@ -239,7 +244,7 @@ __device__ void mma_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_base
       if (n > 0) mbar_wait(&bars[O_FREE + tile], (uint32_t)((n - 1) & 1), O_FREE + tile);
       fence_after();
       if (elect_one()) {
-        issue_pv<VT>(smem_base, smem_base + (uint32_t)s * kStageBytes, tile, tmem_base);
+        issue_pv(smem_base, smem_base + (uint32_t)s * kStageBytes, tile, tmem_base);
         umma_commit(&bars[O_FULL + tile]);
         umma_commit(&bars[P_FREE + tile]);
         if (tile == 1) umma_commit(&bars[QKV_EMPTY + s]);   // last reader of this stage's operand tiles
@@ -250,9 +255,10 @@ __device__ void mma_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_base
 }
 
 // ---- softmax + epilogue ------------------------------------------------------------------------------------------------
-// One thread = 72 consecutive score columns [72*half, 72*half + 72) of one query row.
-//   TAIL == false: row = 32*quarter + lane of tile 0; partner = same row, other half, in warp (quarter, half^1)
-//   TAIL == true : row = 128 + (lane & 15), half = lane >> 4; partner = lane ^ 16
+// One thread = NCOL consecutive score columns of one query row.
+//   TAIL == false: row = 32*quarter + lane of tile 0, keys [72*half, 72*half + 72); partner = same row in warp (quarter, half^1)
+//   TAIL == true : row = 128 + (lane & 15), half = lane >> 4: keys [0,64) (half 0; columns 64-79 are not its keys) or
+//                  [64,144) (half 1); partner = lane ^ 16
 struct RowCtx {
   int quarter, half, lane;
   int row;       // token slot in the window, 0..143
@@ -263,31 +269,51 @@ template <bool TAIL>
 __device__ __forceinline__ float softmax_unit(unsigned char* smem, uint64_t* bars, uint32_t tmem_base, const RowCtx& rc,
                                               const Geo& g, const Unit& un, int n, long long u, float* __restrict__ dbg) {
   constexpr float kLog2e = 1.4426950408889634f;
-  uint32_t sr[72];
-  mbar_wait(&bars[S_FULL + (TAIL ? 1 : 0)], (uint32_t)(n & 1), S_FULL + (TAIL ? 1 : 0));
+  constexpr int NCOL = TAIL ? (kN - kTailKeys0) : 72;
+  constexpr int TB = TAIL ? 1 : 0;
+  uint32_t sr[NCOL];
+  mbar_wait(&bars[S_FULL + TB], (uint32_t)(n & 1), S_FULL + TB);
   fence_after();
   {
-    const uint32_t taddr = tmem_base + ((uint32_t)(TAIL ? 0 : rc.quarter * 32) << 16) + (TAIL ? kColS1 : kColS0) +
-                           (uint32_t)rc.half * 72u;
+    // warp-uniform address: lane quarter and (tile 0) column half are per-warp values
+    const uint32_t taddr = TAIL ? tmem_base + kColS1
+                                : tmem_base + ((uint32_t)(rc.quarter * 32) << 16) + kColS0 + (uint32_t)rc.half * 72u;
     uint32_t* r0 = sr;
     uint32_t* r1 = sr + 32;
     uint32_t* r2 = sr + 64;
     UNIVS_TMEM_LD_X32(taddr, r0);
     UNIVS_TMEM_LD_X32(taddr + 32u, r1);
-    UNIVS_TMEM_LD_X8(taddr + 64u, r2);
+    if (TAIL) {
+      UNIVS_TMEM_LD_X16(taddr + 64u, r2);
+    } else {
+      UNIVS_TMEM_LD_X8(taddr + 64u, r2);
+    }
     tmem_wait_ld();
   }
   fence_before();
   __syncwarp();
-  if (rc.lane == 0) mbar_arrive(&bars[S_FREE + (TAIL ? 1 : 0)]);   // the MMA lane may overwrite S with the next unit
+  if (rc.lane == 0) mbar_arrive(&bars[S_FREE + TB]);   // the MMA lane may overwrite S with the next unit
 
   // relative-position bias (swin.py:108-121: index = (qy-ky+11)*23 + (qx-kx+11)) and the shift mask
   const int qy = rc.row / kWS, qx = rc.row - qy * kWS;
-  const float* bp = reinterpret_cast<const float*>(smem + kOffBias) + (n & 1) * kBiasStride + (qy + 11) * 23 + (qx + 11) -
-                    rc.half * 6 * 23;
-  float sc[72];
+  const float* sbias = reinterpret_cast<const float*>(smem + kOffBias) + (n & 1) * kBiasStride + (qy + 11) * 23 + (qx + 11);
+  const int* kidx = reinterpret_cast<const int*>(smem + kOffKidx);
+  const int key0 = TAIL ? rc.half * kTailKeys0 : rc.half * 72;
+  float sc[NCOL];
+  if (!TAIL) {
+    const float* bp = sbias - rc.half * 6 * 23;     // 72 keys = 6 key rows: the per-column part is a compile-time constant
 #pragma unroll
-  for (int j = 0; j < 72; ++j) sc[j] = __uint_as_float(sr[j]) + bp[-((j / kWS) * 23 + (j % kWS))];
+    for (int j = 0; j < NCOL; ++j) sc[j] = __uint_as_float(sr[j]) + bp[-((j / kWS) * 23 + (j % kWS))];
+  } else {
+    // key -> table offset through the LUT (64 keys are not a whole number of key rows); in blocks of 16 columns with a
+    // scheduling barrier in between, so that the 160 dependent loads are not all hoisted (register pressure)
+#pragma unroll
+    for (int jb = 0; jb < NCOL; jb += 16) {
+#pragma unroll
+      for (int j = jb; j < jb + 16; ++j) sc[j] = __uint_as_float(sr[j]) + sbias[-kidx[key0 + j]];
+      asm volatile("" ::: "memory");
+    }
+  }
   // shift mask (swin.py:413-440): -100 between tokens of different regions; only windows in the last window row /
   // column of the padded grid contain more than one region: rows (cols) >= 12 - shift belong to the wrapped part
   const bool mh = g.shift > 0 && un.wy == g.nWh - 1, mw = g.shift > 0 && un.wx == g.nWw - 1;
@@ -296,21 +322,37 @@ __device__ __forceinline__ float softmax_unit(unsigned char* smem, uint64_t* bar
     uint32_t dh = 0, dw = 0;   // bit y: key row y (key col x) lies in another region than this query
     if (mh) dh = (qy >= thr) ? ((1u << thr) - 1u) : (0xfffu & ~((1u << thr) - 1u));
     if (mw) dw = (qx >= thr) ? ((1u << thr) - 1u) : (0xfffu & ~((1u << thr) - 1u));
-    dh >>= rc.half * 6;
+    if (!TAIL) {
+      dh >>= rc.half * 6;
 #pragma unroll
-    for (int j = 0; j < 72; ++j)
-      if (((dh >> (j / kWS)) | (dw >> (j % kWS))) & 1u) sc[j] += -100.f;
+      for (int j = 0; j < NCOL; ++j)
+        if (((dh >> (j / kWS)) | (dw >> (j % kWS))) & 1u) sc[j] += -100.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) {
+        const int c = kidx[key0 + j];
+        const int ky = c / 23, kx = c - ky * 23;
+        if (((dh >> ky) | (dw >> kx)) & 1u) sc[j] += -100.f;
+      }
+    }
+  }
+  if (TAIL) {      // lanes 0-15 own 64 keys only: the other 16 columns hold nothing of theirs
+#pragma unroll
+    for (int j = kTailKeys0; j < NCOL; ++j)
+      if (rc.half == 0) sc[j] = -INFINITY;
   }
   if (dbg != nullptr) {
-    float* drow = dbg + ((size_t)u * kN + rc.row) * kN + rc.half * 72;
+    float* drow = dbg + ((size_t)u * kN + rc.row) * kN + key0;
 #pragma unroll
-    for (int j = 0; j < 72; ++j) drow[j] = sc[j];
+    for (int j = 0; j < NCOL; ++j)
+      if (!TAIL || rc.half == 1 || j < kTailKeys0) drow[j] = sc[j];
   }
   float mx = sc[0];
 #pragma unroll
-  for (int j = 1; j < 72; ++j) mx = fmaxf(mx, sc[j]);
-  float* xmax = reinterpret_cast<float*>(smem + kOffXch) + (n & 1) * 256;
+  for (int j = 1; j < NCOL; ++j) mx = fmaxf(mx, sc[j]);
+  float* xch = reinterpret_cast<float*>(smem + kOffXch);
   if (!TAIL) {
+    float* xmax = xch + (n & 1) * 256;
     xmax[rc.half * 128 + rc.row] = mx;
     named_bar_sync(1 + rc.quarter, 64);
     mx = fmaxf(mx, xmax[(rc.half ^ 1) * 128 + rc.row]);
@@ -320,36 +362,43 @@ __device__ __forceinline__ float softmax_unit(unsigned char* smem, uint64_t* bar
   const float mneg = -mx * kLog2e;
 
   // P = exp(s - max) as fp16 hi + lo into the K-major SWIZZLE_64B A tile of the PV MMA (32-key atoms)
-  if (n > 0) mbar_wait(&bars[P_FREE + (TAIL ? 1 : 0)], (uint32_t)((n - 1) & 1), P_FREE + (TAIL ? 1 : 0));
+  if (n > 0) mbar_wait(&bars[P_FREE + TB], (uint32_t)((n - 1) & 1), P_FREE + TB);
   const uint32_t ph = smem_u32(smem + (TAIL ? kOffP1h : kOffP0h)), pl = smem_u32(smem + (TAIL ? kOffP1l : kOffP0l));
   constexpr uint32_t atom = TAIL ? kP1Atom : kP0Atom;
   const uint32_t rowoff = (uint32_t)rc.prow * kRow;
   const uint32_t sw = (uint32_t)(rc.prow >> 1) & 3u;
+  const uint32_t chunk0 = (uint32_t)key0 >> 3;                               // first 16-byte chunk (8 keys) of this thread
   float sum = 0.f;
 #pragma unroll
-  for (int cc = 0; cc < 9; ++cc) {
+  for (int cc = 0; cc < NCOL / 8; ++cc) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float p0 = ex2_approx(fmaf(sc[cc * 8 + 2 * e], kLog2e, mneg));
+      const float p0 = ex2_approx(fmaf(sc[cc * 8 + 2 * e], kLog2e, mneg));        // exp2(-inf) = 0 in the unowned columns
       const float p1 = ex2_approx(fmaf(sc[cc * 8 + 2 * e + 1], kLog2e, mneg));
       sum += p0 + p1;
       split_h2(p0, p1, hi[e], lo[e]);
     }
-    const uint32_t gch = (uint32_t)(rc.half * 9 + cc);                       // 16-byte chunk index along the key axis
+    const uint32_t gch = chunk0 + (uint32_t)cc;
     const uint32_t off = (gch >> 2) * atom + rowoff + (((gch & 3u) ^ sw) << 4);
     sts_v4(ph + off, hi[0], hi[1], hi[2], hi[3]);
     sts_v4(pl + off, lo[0], lo[1], lo[2], lo[3]);
-    if (TAIL) {   // the other column half of this (duplicated) row contributes nothing
-      const uint32_t gz = (uint32_t)((rc.half ^ 1) * 9 + cc);
+  }
+  if (TAIL) {
+    // the rest of this lane's P row is zero (its keys belong to the partner lane's copy of the row):
+    // half 0 wrote chunks 0-9 (8, 9 as zeros) -> zero 10-17;  half 1 wrote chunks 8-17 -> zero 0-7
+#pragma unroll
+    for (int cz = 0; cz < 8; ++cz) {
+      const uint32_t gz = (rc.half ? 0u : 10u) + (uint32_t)cz;
       const uint32_t offz = (gz >> 2) * atom + rowoff + (((gz & 3u) ^ sw) << 4);
       sts_v4(ph + offz, 0u, 0u, 0u, 0u);
       sts_v4(pl + offz, 0u, 0u, 0u, 0u);
     }
+  } else {
+    xch[512 + (n & 1) * 256 + rc.half * 128 + rc.row] = sum;
   }
-  if (!TAIL) reinterpret_cast<float*>(smem + kOffXch)[512 + (n & 1) * 256 + rc.half * 128 + rc.row] = sum;
   fence_proxy_async_smem();
-  mbar_arrive(&bars[P_FULL + (TAIL ? 1 : 0)]);
+  mbar_arrive(&bars[P_FULL + TB]);
   return sum;
 }
 
@@ -357,7 +406,8 @@ template <bool TAIL>
 __device__ __forceinline__ void epilogue_unit(unsigned char* smem, uint64_t* bars, uint32_t tmem_base, const RowCtx& rc,
                                               const Geo& g, const Unit& un, int n, float sum, float* __restrict__ out,
                                               __half* __restrict__ out16) {
-  mbar_wait(&bars[O_FULL + (TAIL ? 1 : 0)], (uint32_t)(n & 1), O_FULL + (TAIL ? 1 : 0));
+  constexpr int TB = TAIL ? 1 : 0;
+  mbar_wait(&bars[O_FULL + TB], (uint32_t)(n & 1), O_FULL + TB);
   fence_after();
   float o[16];
   float total;
@@ -375,7 +425,7 @@ __device__ __forceinline__ void epilogue_unit(unsigned char* smem, uint64_t* bar
     UNIVS_TMEM_LD_X32(taddr, r);
     tmem_wait_ld();
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {   // lanes l and l^16 hold the two key-half partial sums of the same row
+    for (int e = 0; e < 16; ++e) {   // lanes l and l^16 hold the two key-range partial sums of the same row
       const float a = __uint_as_float(r[e]), b = __uint_as_float(r[16 + e]);
       const float a2 = a + __shfl_xor_sync(0xffffffffu, a, 16), b2 = b + __shfl_xor_sync(0xffffffffu, b, 16);
       o[e] = rc.half ? b2 : a2;      // lanes 0-15 store dims 0-15, lanes 16-31 dims 16-31
@@ -384,7 +434,7 @@ __device__ __forceinline__ void epilogue_unit(unsigned char* smem, uint64_t* bar
   }
   fence_before();
   __syncwarp();
-  if (rc.lane == 0) mbar_arrive(&bars[O_FREE + (TAIL ? 1 : 0)]);
+  if (rc.lane == 0) mbar_arrive(&bars[O_FREE + TB]);
 
   const int src = source_token(g, un, rc.row);     // window_reverse + roll(+shift) + crop: pad rows are dropped
   if (src < 0) return;
@@ -423,9 +473,8 @@ __device__ __forceinline__ void epilogue_unit(unsigned char* smem, uint64_t* bar
 }
 
 template <bool TAIL>
-__device__ void softmax_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_base, const RowCtx rc, const Geo g,
-                             long long units, int count, float* __restrict__ out, __half* __restrict__ out16,
-                             float* __restrict__ dbg) {
+__device__ void softmax_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_base, const RowCtx rc, const Geo g, int count,
+                             float* __restrict__ out, __half* __restrict__ out16, float* __restrict__ dbg) {
   if (count <= 0) return;
   long long u = blockIdx.x;
   Unit cur = decode(u, g);
@@ -443,10 +492,8 @@ __device__ void softmax_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_
     sum_cur = sum_nxt;
     u += gridDim.x;
   }
-  (void)units;
 }
 
-template <bool VT>
 __global__ void __launch_bounds__(kThreads, 1)
 swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
                              const float* __restrict__ table, const Geo g, long long units, float scale,
@@ -477,6 +524,9 @@ swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restr
     mbar_init_fence();
   } else if (warp == kAllocWarp) {
     tmem_alloc(tmem_slot, 512);
+  } else if (warp == kAllocWarp + 1) {
+    int* kidx = reinterpret_cast<int*>(smem + kOffKidx);
+    for (int k = lane; k < kN; k += 32) kidx[k] = (k / kWS) * 23 + (k % kWS);
   }
   fence_before();
   __syncthreads();
@@ -484,9 +534,9 @@ swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restr
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= kLoaderWarp0) {
-    loader_loop<VT>(smem, bars, qkv, qkv_bias, table, g, units, scale);
+    loader_loop(smem, bars, qkv, qkv_bias, table, g, units, scale);
   } else if (warp == kMmaWarp) {
-    mma_loop<VT>(smem, bars, tmem_base, count);
+    mma_loop(smem, bars, tmem_base, count);
   } else if (warp < 8) {
     RowCtx rc;
     rc.quarter = warp & 3;
@@ -494,7 +544,7 @@ swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restr
     rc.lane = lane;
     rc.row = rc.quarter * 32 + lane;
     rc.prow = rc.row;
-    softmax_loop<false>(smem, bars, tmem_base, rc, g, units, count, out, out16, dbg);
+    softmax_loop<false>(smem, bars, tmem_base, rc, g, count, out, out16, dbg);
   } else if (warp == 8) {
     RowCtx rc;
     rc.quarter = 0;
@@ -502,7 +552,7 @@ swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restr
     rc.lane = lane;
     rc.row = 128 + (lane & 15);
     rc.prow = lane;
-    softmax_loop<true>(smem, bars, tmem_base, rc, g, units, count, out, out16, dbg);
+    softmax_loop<true>(smem, bars, tmem_base, rc, g, count, out, out16, dbg);
   }
   fence_before();
   __syncthreads();
@@ -512,7 +562,6 @@ swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restr
   }
 }
 
-template <bool VT>
 static int launch(cudaStream_t st, const float* qkv, const float* bias, const float* table, const Geo& g, float* out,
                   __half* out16, float* dbg) {
   const long long units = (long long)g.B * g.nWh * g.nWw * g.nH;
@@ -523,14 +572,14 @@ static int launch(cudaStream_t st, const float* qkv, const float* bias, const fl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  cudaError_t e = cudaFuncSetAttribute(swin_window_attn_tc12_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(swin_window_attn_tc12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) {
     set_error("swin_window_attention_tc: cudaFuncSetAttribute(%d): %s", kSmemBytes, cudaGetErrorString(e));
     return UNIVS_E_LAUNCH;
   }
   const int grid = (int)(units < num_sms ? units : num_sms);
   const float scale = 0.17677669529663687f;   // 32^-0.5 (swin.py:96)
-  swin_window_attn_tc12_kernel<VT><<<grid, kThreads, kSmemBytes, st>>>(qkv, bias, table, g, units, scale, out, out16, dbg);
+  swin_window_attn_tc12_kernel<<<grid, kThreads, kSmemBytes, st>>>(qkv, bias, table, g, units, scale, out, out16, dbg);
   return check_launch("swin_window_attention_tc");
 }
 
@@ -550,6 +599,7 @@ extern "C" int univs_swin_window_attention_tc(void* stream, const float* qkv, co
                 channels, num_heads);
   UNIVS_REQUIRE(shift >= 0 && shift < window, "swin_window_attention_tc: shift must be in [0, window)");
   UNIVS_REQUIRE(out16 == nullptr || channels <= 1536, "swin_window_attention_tc: the operand output needs channels <= 1536");
+  UNIVS_REQUIRE(flags == 0, "swin_window_attention_tc: no flags are defined yet (got %d)", flags);
   if (batch == 0) return UNIVS_OK;
   wintc::Geo g;
   g.B = batch; g.H = height; g.W = width; g.C = channels; g.nH = num_heads; g.shift = shift;
@@ -557,8 +607,5 @@ extern "C" int univs_swin_window_attention_tc(void* stream, const float* qkv, co
   g.Wp = (width + window - 1) / window * window;
   g.nWh = g.Hp / window;
   g.nWw = g.Wp / window;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (flags & 1)
-    return wintc::launch<true>(st, qkv, qkv_bias, rel_bias_table, g, out, reinterpret_cast<__half*>(out16), debug_scores);
-  return wintc::launch<false>(st, qkv, qkv_bias, rel_bias_table, g, out, reinterpret_cast<__half*>(out16), debug_scores);
+  return wintc::launch((cudaStream_t)stream, qkv, qkv_bias, rel_bias_table, g, out, reinterpret_cast<__half*>(out16), debug_scores);
 }

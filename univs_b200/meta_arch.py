@@ -111,7 +111,8 @@ class UniVS_Prompt(nn.Module):
         if self.shard_decoder and dec.supports_exchange(targets):
             # frames stay on their rank through the decoder; only query tokens are exchanged (sharding.TokenExchange)
             ex = TokenExchange(self.sharder, T)
-            local = (frames if fused else x)[ex.frames]
+            whole = frames if fused else x
+            local = whole.index_select(0, ex.frames_tensor(whole.device))
             features = self.backbone_from_frames(local) if fused else self.backbone(local)
             mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(features)
             return dec(multi_scale, mask_features, mf_bfe, None, targets, exchange=ex)

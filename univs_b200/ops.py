@@ -155,7 +155,7 @@ def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits
     return out
 
 
-_win_tc = int(os.environ.get("UNIVS_WIN_TC", "0"))   # opt-in: 1 = tcgen05 kernel for 12x12 windows, 3 = with transposed V
+_win_tc = int(os.environ.get("UNIVS_WIN_TC", "0"))   # opt-in: 1 = tcgen05 kernel for 12x12 windows
 
 
 def swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, want_f32=True, want_operand=False,
@@ -185,7 +185,7 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     if _win_tc and window == 12 and (_default_precision if precision is None else precision) == PREC_TF32X3:
-        return swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, flags=_win_tc >> 1)[0]
+        return swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, flags=0)[0]
     out = torch.empty((B, H, W, C), device=qkv.device, dtype=torch.float32)
     with _Bracket("swin_window_attention", 1):
         rc = lib().univs_swin_window_attention_f32(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
@@ -203,7 +203,7 @@ def swin_window_attention_operand(qkv, qkv_bias, rel_bias_table, num_heads, wind
     C = C3 // 3
     if _win_tc and window == 12:
         return swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, want_f32=False,
-                                        want_operand=True, flags=_win_tc >> 1)[1]
+                                        want_operand=True, flags=0)[1]
     out = torch.empty((B, H, W, 3 * C), device=qkv.device, dtype=torch.float16)
     with _Bracket("swin_window_attention", 1):
         rc = lib().univs_swin_window_attention_f16x3out(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
