@@ -172,8 +172,8 @@ def _split16(x):
 
 
 class _Smem:
-    def __init__(self, rng):
-        self.h = rng.standard_normal(SMEM // 2).astype(np.float16)      # garbage everywhere a store does not reach
+    def __init__(self, rng, nbytes=SMEM):
+        self.h = rng.standard_normal(nbytes // 2).astype(np.float16)    # garbage everywhere a store does not reach
 
     def st(self, byte_addr, v16):
         assert byte_addr % 2 == 0

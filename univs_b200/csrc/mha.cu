@@ -638,6 +638,14 @@ static void mha_plan(int B, int heads, int Lq, int Lk, int& qtiles, int& nsplit,
   if (nsplit < 1) nsplit = 1;
 }
 
+// split-K merge for the tensor-core kernel of mha_tc.cu (same partial format)
+int launch_mha_combine(cudaStream_t st, const float* part_o, const float* part_ml, int B, int heads, int Lq, int C, int nsplit,
+                       float* out) {
+  const size_t rows = (size_t)B * heads * Lq;
+  mha_combine_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(part_o, part_ml, B, heads, Lq, C, nsplit, out);
+  return check_launch("mha_combine");
+}
+
 }  // namespace univs
 
 using namespace univs;

@@ -297,10 +297,35 @@ def _workspace(nbytes, device):
     return ws
 
 
+_mha_tc = int(os.environ.get("UNIVS_MHA_TC", "0"))   # opt-in: tcgen05 kernel for the cross-attention shape (Lq <= 256)
+MHA_TC_MIN_KEYS = 512
+
+
+def mha_core_tc(q, k, v, mask_bits=None, row_open=None):
+    """Strict-precision attention core on the tcgen05 tensor cores (univs_mha_tc_forward_f32): Lq <= 256."""
+    B, Lq, Cc = q.shape
+    Lk = k.shape[1]
+    out = torch.empty_like(q)
+    nbytes = lib().univs_mha_tc_workspace_bytes(B, Lq, Lk, Cc)
+    ws = _workspace(nbytes, q.device)
+    mb = 0 if mask_bits is None else mask_bits.shape[0]
+    with _Bracket("mha", 1 if nbytes <= 16 else 2):
+        rc = lib().univs_mha_tc_forward_f32(
+            _stream(), _chk(q, "q"), _chk(k, "k"), _chk(v, "v"),
+            None if mask_bits is None else _chk(mask_bits, "mask_bits", torch.int32),
+            None if row_open is None else _chk(row_open, "row_open", torch.int32),
+            mb, B, Lq, Lk, Cc, ws.data_ptr(), out.data_ptr())
+    check(rc, "mha_tc_forward")
+    return out
+
+
 def mha_core(q, k, v, mask_bits=None, row_open=None, precision=None):
     """q [B,Lq,C], k,v [B,Lk,C] (projected, q unscaled); mask_bits int32 [Bm,Lq,ceil(Lk/32)] (bit set = blocked)."""
     B, Lq, Cc = q.shape
     Lk = k.shape[1]
+    if (_mha_tc and Lq <= 256 and Lk >= MHA_TC_MIN_KEYS
+            and (_default_precision if precision is None else precision) == PREC_TF32X3):
+        return mha_core_tc(q, k, v, mask_bits, row_open)
     out = torch.empty_like(q)
     nbytes = lib().univs_mha_workspace_bytes(B, Lq, Lk, Cc)
     ws = _workspace(nbytes, q.device)
