@@ -134,11 +134,12 @@ int univs_mha_forward_f32(void* stream, const float* q, const float* k, const fl
 /* Same operator, strict precision, on the tcgen05 tensor cores for the decoder's cross-attention shape: len_q <= 256
  * queries against a long key sequence (mha_tc.cu: S and the per-block O in TMEM, softmax on rows read back with
  * tcgen05.ld, running output in registers).  Same arguments, mask semantics and split-K partial format; the workspace
- * size comes from univs_mha_tc_workspace_bytes (its key-split plan differs: one CTA per SM). */
+ * size comes from univs_mha_tc_workspace_bytes (its key-split plan differs: one CTA per SM).  flags bit 0 (diagnostic):
+ * stage V transposed and read it through the K-major B descriptor instead of the MN-major one. */
 int64_t univs_mha_tc_workspace_bytes(int batch, int len_q, int len_k, int channels);
 int univs_mha_tc_forward_f32(void* stream, const float* q, const float* k, const float* v, const uint32_t* mask_bits,
                              const int32_t* row_open, int mask_batch, int batch, int len_q, int len_k, int channels,
-                             void* workspace, float* out);
+                             int flags, void* workspace, float* out);
 
 /* ---- ProCA attention core (a14): every (prompt p, frame t) query attends to its own token and its L
  * prompt-memory tokens.  q,k_self,v_self [P,T,C]; k_mem,v_mem [P,Tm,L,C], Tm in {1,T}; out [P,T,C]. */

@@ -30,7 +30,7 @@ def _store_row(sm, th, tl, row, vals):
         sm.st(tl + off, lo)
 
 
-def _cta(rng, q, k, v, bits, row_open, kb_begin, kb_end):
+def _cta(rng, q, k, v, bits, row_open, kb_begin, kb_end, vt=False):
     """One CTA of mha_tc_kernel for one (batch, head): returns (o [Lq,32] unnormalised, m [Lq], l [Lq])."""
     Lq, Lk = q.shape[0], k.shape[0]
     words = (Lk + 31) // 32
@@ -46,7 +46,15 @@ def _cta(rng, q, k, v, bits, row_open, kb_begin, kb_end):
         for r in range(BLK):
             key = kb * BLK + r
             _store_row(sm, st, st + TILE, r, k[key] if key < Lk else np.zeros(32, np.float32))
-            _store_row(sm, st + 2 * TILE, st + 3 * TILE, r, v[key] if key < Lk else np.zeros(32, np.float32))
+            vrow = v[key] if key < Lk else np.zeros(32, np.float32)
+            if not vt:
+                _store_row(sm, st + 2 * TILE, st + 3 * TILE, r, vrow)
+            else:       # store_row_vt: row = dim, 32-key atoms of 32 rows x 64 B
+                for d in range(32):
+                    o = (r >> 5) * 2048 + _swz_off(d, (r & 31) >> 3) + (r & 7) * 2
+                    hi, lo = _split16(vrow[d])
+                    sm.st(st + 2 * TILE + o, hi)
+                    sm.st(st + 3 * TILE + o, lo)
         for tile in range(2):
             for kk in range(2):
                 _umma(sm, tmem, 0, OFF_QL + tile * TILE + 32 * kk, st + 32 * kk, BLK, False, kk > 0)
@@ -97,10 +105,10 @@ def _cta(rng, q, k, v, bits, row_open, kb_begin, kb_end):
                         sm.st(OFF_PL + off + 2 * x, lo)
             for ks in range(8):
                 aoff = (ks >> 1) * TILE + (ks & 1) * 32
-                boff = ks * 16 * ROW
-                _umma(sm, tmem, 128, OFF_PL + aoff, st + 2 * TILE + boff, 32, True, ks > 0)
-                _umma(sm, tmem, 128, OFF_PH + aoff, st + 3 * TILE + boff, 32, True, True)
-                _umma(sm, tmem, 128, OFF_PH + aoff, st + 2 * TILE + boff, 32, True, True)
+                boff = (ks >> 1) * 2048 + (ks & 1) * 32 if vt else ks * 16 * ROW
+                _umma(sm, tmem, 128, OFF_PL + aoff, st + 2 * TILE + boff, 32, not vt, ks > 0)
+                _umma(sm, tmem, 128, OFF_PH + aoff, st + 3 * TILE + boff, 32, not vt, True)
+                _umma(sm, tmem, 128, OFF_PH + aoff, st + 2 * TILE + boff, 32, not vt, True)
             for trow in range(128):
                 for half in range(2):
                     st_ = run[(tile, trow, half)]
@@ -116,8 +124,8 @@ def _cta(rng, q, k, v, bits, row_open, kb_begin, kb_end):
     return o, m, l
 
 
-@pytest.mark.parametrize("nsplit", [1, 2])
-def test_dataflow_model_one_head(nsplit):
+@pytest.mark.parametrize("nsplit,vt", [(1, False), (2, False), (1, True)])
+def test_dataflow_model_one_head(nsplit, vt):
     rng = np.random.default_rng(5)
     Lq, Lk = 150, 300                      # two row tiles (second partly empty), three key blocks (last: 44 keys)
     q = rng.standard_normal((Lq, 32)).astype(np.float32)
@@ -132,7 +140,7 @@ def test_dataflow_model_one_head(nsplit):
     row_open = (~mask.all(1)).astype(np.int32)
     nkb = (Lk + BLK - 1) // BLK
     bps = (nkb + nsplit - 1) // nsplit
-    parts = [_cta(rng, q, k, v, bits, row_open, s * bps, min(nkb, (s + 1) * bps)) for s in range(nsplit)]
+    parts = [_cta(rng, q, k, v, bits, row_open, s * bps, min(nkb, (s + 1) * bps), vt) for s in range(nsplit)]
     # combine (mha_combine_kernel)
     M = np.max([p[1] for p in parts], 0)
     acc, l = np.zeros((Lq, 32)), np.zeros(Lq)
@@ -159,11 +167,12 @@ def _rel(a, b):
 
 @pytest.mark.gpu
 @_gpu_mhatc
+@pytest.mark.parametrize("flags", [0, 1])       # 1: transposed-V diagnostic variant
 @pytest.mark.parametrize("B,Lq,Lk,C,masked", [
     (1, 20, 96, 64, False), (1, 7, 128, 32, True), (2, 200, 920, 256, True), (3, 256, 130, 256, True),
     (5, 200, 3680, 256, True), (1, 232, 14720, 256, True), (5, 200, 14720, 256, False), (40, 100, 777, 256, True),
 ])
-def test_mha_tc(B, Lq, Lk, C, masked):
+def test_mha_tc(B, Lq, Lk, C, masked, flags):
     from univs_b200 import ops
     torch.manual_seed(B * 1000 + Lq)
     q, k, v = torch.randn(B, Lq, C), torch.randn(B, Lk, C), torch.randn(B, Lk, C)
@@ -177,7 +186,7 @@ def test_mha_tc(B, Lq, Lk, C, masked):
         bits = ops.pack_mask_bits(mask).cuda()
         row_open = (~mask.all(-1)).to(torch.int32).cuda()
     want = ops_ref.mha_core(q, k, v, C // 32, None if mask is None else mask.to(torch.uint8), unmask_full_rows=masked)
-    got = ops.mha_core_tc(q.cuda(), k.cuda(), v.cuda(), bits, row_open)
+    got = ops.mha_core_tc(q.cuda(), k.cuda(), v.cuda(), bits, row_open, flags=flags)
     torch.cuda.synchronize()
     assert _rel(got, want) < 2e-5
     ref = ops.mha_core(q.cuda(), k.cuda(), v.cuda(), bits, row_open, precision=0)

@@ -77,6 +77,25 @@ __device__ __forceinline__ void store_row(unsigned char* tile_h, unsigned char* 
   sts_v2(smem_u32(tile_l) + off, l0, l1);
 }
 
+// transposed V (diagnostic variant: K-major B operand instead of the MN-major one): row = dim, 32-key atoms of 32 rows x 64 B
+__device__ __forceinline__ void store_row_vt(unsigned char* tile_h, unsigned char* tile_l, int key, int lane8, float4 x) {
+  uint32_t h0, h1, l0, l1;
+  split_h2(x.x, x.y, h0, l0);
+  split_h2(x.z, x.w, h1, l1);
+  const uint32_t hv[2] = {h0, h1}, lv[2] = {l0, l1};
+  __half* vh = reinterpret_cast<__half*>(tile_h);
+  __half* vl = reinterpret_cast<__half*>(tile_l);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int d = lane8 * 4 + e;
+    const uint32_t o = (uint32_t)(key >> 5) * 2048u + swz_off<kRow>(d, (key & 31) >> 3) + (uint32_t)(key & 7) * 2u;
+    const uint32_t hw = hv[e >> 1], lw = lv[e >> 1];
+    vh[o >> 1] = __ushort_as_half((unsigned short)((e & 1) ? (hw >> 16) : (hw & 0xffffu)));
+    vl[o >> 1] = __ushort_as_half((unsigned short)((e & 1) ? (lw >> 16) : (lw & 0xffffu)));
+  }
+}
+
+template <bool VT>
 __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const Args& a, int b, int h, int kb_begin, int kb_end) {
   const int lt = threadIdx.x - kLoaderWarp0 * 32;
   const int lane8 = lt & 7, slot = lt >> 3;       // 16 rows per pass
@@ -117,18 +136,20 @@ __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const Args& a, 
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
       store_row(st, st + kTile, p * 16 + slot, lane8, kk[p]);
-      store_row(st + 2 * kTile, st + 3 * kTile, p * 16 + slot, lane8, vv[p]);
+      if (VT) store_row_vt(st + 2 * kTile, st + 3 * kTile, p * 16 + slot, lane8, vv[p]);
+      else store_row(st + 2 * kTile, st + 3 * kTile, p * 16 + slot, lane8, vv[p]);
     }
     fence_proxy_async_smem();
     mbar_arrive(&bars[KV_FULL + s]);
   }
 }
 
+template <bool VT>
 __device__ void mma_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_base, int nblocks) {
   const uint32_t base = smem_u32(smem);
   const int count = 2 * nblocks;                  // units: (block, row tile)
   constexpr uint32_t idesc_s = make_idesc_f16(128, kBlk, false, false);
-  constexpr uint32_t idesc_pv = make_idesc_f16(128, 32, false, true);
+  constexpr uint32_t idesc_pv = make_idesc_f16(128, 32, false, !VT);
   mbar_wait(&bars[Q_FULL], 0, Q_FULL);
   for (int n = -1; n < count; ++n) {
     if (n + 1 < count) {          // S of unit n+1
@@ -161,7 +182,7 @@ __device__ void mma_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_base
 #pragma unroll
         for (int ks = 0; ks < kBlk / 16; ++ks) {
           const uint32_t aoff = (uint32_t)(ks >> 1) * kTile + (uint32_t)(ks & 1) * 32u;
-          const uint32_t boff = (uint32_t)ks * 16u * kRow;
+          const uint32_t boff = VT ? (uint32_t)(ks >> 1) * 2048u + (uint32_t)(ks & 1) * 32u : (uint32_t)ks * 16u * kRow;
           const uint64_t ah = make_desc<kRow>(base + kOffPh + aoff), al = make_desc<kRow>(base + kOffPl + aoff);
           const uint64_t bh = make_desc<kRow>(st + 2 * kTile + boff), bl = make_desc<kRow>(st + 3 * kTile + boff);
           umma_f16(tmem_base + kColO, al, bh, idesc_pv, ks ? 1u : 0u);
@@ -361,6 +382,7 @@ __device__ void softmax_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_
   }
 }
 
+template <bool VT>
 __global__ void __launch_bounds__(kThreads, 1) mha_tc_kernel(const Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -394,9 +416,9 @@ __global__ void __launch_bounds__(kThreads, 1) mha_tc_kernel(const Args a) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= kLoaderWarp0) {
-    loader_loop(smem, bars, a, b, h, kb_begin, kb_end);
+    loader_loop<VT>(smem, bars, a, b, h, kb_begin, kb_end);
   } else if (warp == kMmaWarp) {
-    mma_loop(smem, bars, tmem_base, kb_end - kb_begin);
+    mma_loop<VT>(smem, bars, tmem_base, kb_end - kb_begin);
   } else if (warp < 8) {
     softmax_loop(smem, bars, tmem_base, a, b, h, split, kb_begin, kb_end);
   }
@@ -445,9 +467,20 @@ extern "C" int64_t univs_mha_tc_workspace_bytes(int batch, int len_q, int len_k,
   return (int64_t)ns * batch * (channels / 32) * len_q * (32 + 2) * (int64_t)sizeof(float);
 }
 
+template <bool VT>
+static int launch_mha_tc(cudaStream_t st, const mhatc::Args& a) {
+  cudaError_t e = cudaFuncSetAttribute(mhatc::mha_tc_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mhatc::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("mha_tc_forward: cudaFuncSetAttribute(%d): %s", mhatc::kSmemBytes, cudaGetErrorString(e));
+    return UNIVS_E_LAUNCH;
+  }
+  mhatc::mha_tc_kernel<VT><<<dim3((unsigned)(a.B * a.heads), (unsigned)a.nsplit), mhatc::kThreads, mhatc::kSmemBytes, st>>>(a);
+  return check_launch("mha_tc_forward");
+}
+
 extern "C" int univs_mha_tc_forward_f32(void* stream, const float* q, const float* k, const float* v,
                                         const uint32_t* mask_bits, const int32_t* row_open, int mask_batch, int batch,
-                                        int len_q, int len_k, int channels, void* workspace, float* out) {
+                                        int len_q, int len_k, int channels, int flags, void* workspace, float* out) {
   UNIVS_REQUIRE(q && k && v && out, "mha_tc_forward: null pointer");
   UNIVS_REQUIRE(batch >= 0 && len_q >= 0 && len_k > 0, "mha_tc_forward: bad sizes (len_k must be > 0)");
   UNIVS_REQUIRE(len_q <= mhatc::kMaxLq, "mha_tc_forward: at most %d queries per batch element (got %d); use univs_mha_forward_f32",
@@ -466,14 +499,9 @@ extern "C" int univs_mha_tc_forward_f32(void* stream, const float* q, const floa
   a.out = out;
   a.part_o = reinterpret_cast<float*>(workspace);
   a.part_ml = a.part_o ? a.part_o + (size_t)a.nsplit * batch * heads * len_q * 32 : nullptr;
+  UNIVS_REQUIRE((flags & ~1) == 0, "mha_tc_forward: unknown flags %d", flags);
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaFuncSetAttribute(mhatc::mha_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mhatc::kSmemBytes);
-  if (e != cudaSuccess) {
-    set_error("mha_tc_forward: cudaFuncSetAttribute(%d): %s", mhatc::kSmemBytes, cudaGetErrorString(e));
-    return UNIVS_E_LAUNCH;
-  }
-  mhatc::mha_tc_kernel<<<dim3((unsigned)(batch * heads), (unsigned)a.nsplit), mhatc::kThreads, mhatc::kSmemBytes, st>>>(a);
-  int rc = check_launch("mha_tc_forward");
+  const int rc = (flags & 1) ? launch_mha_tc<true>(st, a) : launch_mha_tc<false>(st, a);
   if (rc || a.nsplit == 1) return rc;
   return launch_mha_combine(st, a.part_o, a.part_ml, batch, heads, len_q, channels, a.nsplit, out);
 }

@@ -297,11 +297,12 @@ def _workspace(nbytes, device):
     return ws
 
 
-_mha_tc = int(os.environ.get("UNIVS_MHA_TC", "0"))   # opt-in: tcgen05 kernel for the cross-attention shape (Lq <= 256)
+_mha_tc = int(os.environ.get("UNIVS_MHA_TC", "0"))   # opt-in: 1 = tcgen05 kernel for the cross-attention shape (Lq <= 256),
+                                                      # 3 = the same with the transposed-V (K-major) diagnostic variant
 MHA_TC_MIN_KEYS = 512
 
 
-def mha_core_tc(q, k, v, mask_bits=None, row_open=None):
+def mha_core_tc(q, k, v, mask_bits=None, row_open=None, flags=None):
     """Strict-precision attention core on the tcgen05 tensor cores (univs_mha_tc_forward_f32): Lq <= 256."""
     B, Lq, Cc = q.shape
     Lk = k.shape[1]
@@ -314,7 +315,7 @@ def mha_core_tc(q, k, v, mask_bits=None, row_open=None):
             _stream(), _chk(q, "q"), _chk(k, "k"), _chk(v, "v"),
             None if mask_bits is None else _chk(mask_bits, "mask_bits", torch.int32),
             None if row_open is None else _chk(row_open, "row_open", torch.int32),
-            mb, B, Lq, Lk, Cc, ws.data_ptr(), out.data_ptr())
+            mb, B, Lq, Lk, Cc, (_mha_tc >> 1) if flags is None else flags, ws.data_ptr(), out.data_ptr())
     check(rc, "mha_tc_forward")
     return out
 
