@@ -18,14 +18,16 @@ run default_gpu_tests 900 python -m pytest tests -m gpu -q -x
 UNIVS_GPU_WINTC=1 run wintc_tests 600 python -m pytest tests/test_window_attn_tc.py -m gpu -q
 run wintc_check 600 python tools/win_tc_check.py --time
 UNIVS_GPU_MHATC=1 run mhatc_tests 600 python -m pytest tests/test_mha_tc.py -m gpu -q
+UNIVS_GPU_ROWWISE_V2=1 run rowwise_v2_tests 600 python -m pytest tests/test_rowwise_v2.py -m gpu -q
 UNIVS_GPU_GLUE=1 run glue_tests 900 python -m pytest tests/test_fused_glue.py -m gpu -q
 UNIVS_GPU_HEADS=1 run heads_tests 900 python -m pytest tests/test_heads_golden.py -m gpu -q
 # 2. measurements: default, then each opt-in on top of it (a path that failed above still runs: its number is void)
 run bench_default 900 python bench.py --steps 10 --warmup 3
 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 run bench_glue 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_WIN_TC=1 run bench_wintc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+UNIVS_ROWWISE_V2=1 run bench_rowwise_v2 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_MHA_TC=1 run bench_mhatc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
-UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 run bench_all 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 run bench_all 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 # 3. end-to-end parity of the opt-in paths at the north-star geometry (T=2): same tool and thresholds as round 1
-PARITY_MODES=fp16x3 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 run parity_at_scale 1200 python tools/parity_at_scale.py
+PARITY_MODES=fp16x3 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 run parity_at_scale 1200 python tools/parity_at_scale.py
 cat "$out/summary.txt"
