@@ -33,3 +33,32 @@ def test_clip_stream_equals_per_clip_recompute():
         assert got[s].shape == want[s].shape
         err = (got[s] - want[s]).abs().max().item() / want[s].abs().max().item()
         assert err < 1e-4, (s, err)
+
+
+def test_frame_groups_equal_whole_clip():
+    """UniVS_Prompt(frame_streams=g): backbone + pixel decoder per contiguous frame group (one CUDA stream per group on the
+    GPU, sequential on CPU), decoder once -- must equal the ungrouped forward (frames are independent up to the decoder)."""
+    from univs_b200 import nn_ops
+    T, Q = 5, 6
+    bb, pix, dec = mf.build_product_model(mf.TINY_SWIN, num_queries=Q, num_frames=T, clip_emb=mf.make_clip_emb(),
+                                          enc_layers=1, dec_layers=2)
+    mf.load_keyed((bb, pix, dec))
+    shapes = {f"res{i + 2}": ShapeSpec(channels=32 * 2 ** i, stride=4 * 2 ** i) for i in range(4)}
+    head = MaskFormerHead(shapes, num_classes=133, pixel_decoder=pix, transformer_predictor=dec)
+    kw = dict(backbone=bb, sem_seg_head=head, pixel_mean=[123.675, 116.28, 103.53], pixel_std=[58.395, 57.12, 57.375])
+    g = torch.Generator().manual_seed(5)
+    frames = (torch.rand(T, 3, 60, 90, generator=g) * 255).round()
+    tg = lambda: [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual", "frame_indices": torch.arange(T)}]
+    for fused in (False, True):
+        nn_ops.set_fused_glue(fused)
+        try:
+            with oracle_ops("tf32x3" if fused else "fp32"):
+                want = UniVS_Prompt(**kw).clip_forward(frames, tg())
+                for groups in (2, 3, 8):
+                    got = UniVS_Prompt(frame_streams=groups, **kw).clip_forward(frames, tg())
+                    for k in ("pred_masks", "pred_logits", "pred_embds"):
+                        assert got[k].shape == want[k].shape
+                        err = (got[k] - want[k]).abs().max().item() / want[k].abs().max().item()
+                        assert err < 1e-4, (fused, groups, k, err)
+        finally:
+            nn_ops.set_fused_glue(False)

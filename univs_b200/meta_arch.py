@@ -27,7 +27,7 @@ from .sharding import FrameSharder, TokenExchange
 @META_ARCH_REGISTRY.register()
 class UniVS_Prompt(nn.Module):
     def __init__(self, cfg=None, *, backbone=None, sem_seg_head=None, pixel_mean=None, pixel_std=None,
-                 size_divisibility=32, num_frames=5, process_group=None, shard_decoder=None):
+                 size_divisibility=32, num_frames=5, process_group=None, shard_decoder=None, frame_streams=None):
         super().__init__()
         if cfg is not None:
             backbone = build_backbone(cfg)
@@ -46,6 +46,10 @@ class UniVS_Prompt(nn.Module):
         self.sharder = FrameSharder(process_group)
         # frame-sharded decoder with per-layer token exchange instead of the feature all-gather (opt-in)
         self.shard_decoder = (os.environ.get("UNIVS_SHARD_DECODER", "0") == "1") if shard_decoder is None else shard_decoder
+        # single GPU: backbone + pixel decoder of g frame groups on g CUDA streams, so that the memory-bound passes of one
+        # group can run under the tensor-core GEMMs of another (frames are independent up to the decoder); opt-in
+        self.frame_streams = int(os.environ.get("UNIVS_FRAME_STREAMS", "1")) if frame_streams is None else int(frame_streams)
+        self._streams = []
         self.eval()
 
     @property
@@ -104,6 +108,8 @@ class UniVS_Prompt(nn.Module):
         if "frame_indices" in targets[0]:
             targets[0]["frame_indices"] = targets[0]["frame_indices"].to(self.device)
         if self.sharder.world_size == 1:
+            if self.frame_streams > 1 and T > 1:
+                return self._grouped_forward(frames if fused else x, fused, T, targets)
             features = self.backbone_from_frames(frames) if fused else self.backbone(x)
             return self.sem_seg_head(features, targets=targets)
         pd = self.sem_seg_head.pixel_decoder
@@ -130,6 +136,43 @@ class UniVS_Prompt(nn.Module):
         gathered = self.sharder.all_gather_frames(parts, T)
         gathered = [t.permute(0, 3, 1, 2) for t in gathered]
         mask_features, multi_scale = gathered[0], gathered[1:]
+        return self.sem_seg_head.predictor(multi_scale, mask_features, mask_features, None, targets)
+
+    def _grouped_forward(self, whole, fused, T, targets):
+        """Backbone + pixel decoder per contiguous frame group, each group on its own CUDA stream (sequentially on CPU
+        tensors); the per-group outputs are concatenated in frame order and the decoder runs once on the current stream.
+        Frame independence of this part of the path is the property frame sharding relies on (sharding.py)."""
+        n = min(self.frame_streams, T)
+        bounds = [(T * g) // n for g in range(n + 1)]
+        pd = self.sem_seg_head.pixel_decoder
+        on_gpu = self.device.type == "cuda"
+        outs = []
+        if on_gpu:
+            cur = torch.cuda.current_stream()
+            while len(self._streams) < n:
+                self._streams.append(torch.cuda.Stream(device=self.device))
+        for g in range(n):
+            part = whole[bounds[g]:bounds[g + 1]]
+
+            def run():
+                feats = self.backbone_from_frames(part) if fused else self.backbone(part)
+                mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(feats)
+                return mask_features, list(multi_scale)
+
+            if on_gpu:
+                st = self._streams[g]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    outs.append(run())
+            else:
+                outs.append(run())
+        if on_gpu:
+            for g in range(n):
+                cur.wait_stream(self._streams[g])
+        cat = lambda ts: torch.cat([t.permute(0, 2, 3, 1) for t in ts], 0).permute(0, 3, 1, 2)   # keep channel-last storage
+        mask_features = cat([o[0] for o in outs])
+        multi_scale = [cat([o[1][l] for o in outs]) for l in range(len(outs[0][1]))]
+        # mask_features_bfe_conv is not read by the inference decoder (only viewed, ..._univs.py:313): as in the sharded path
         return self.sem_seg_head.predictor(multi_scale, mask_features, mask_features, None, targets)
 
     def forward(self, batched_inputs):

@@ -437,10 +437,11 @@ _gn_ws = {}
 
 
 def _gn_workspace(device, nbytes):
-    buf = _gn_ws.get(device)
+    key = (device, torch.cuda.current_stream().cuda_stream)      # per stream: frame groups may run concurrently
+    buf = _gn_ws.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 16), device=device, dtype=torch.uint8)
-        _gn_ws[device] = buf
+        _gn_ws[key] = buf
     return buf
 
 
