@@ -131,6 +131,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ns", choices=list(WORKLOADS))
+    ap.add_argument("--video-frames", type=int, default=0,
+                    help="> 0: secondary benchmark (SURVEY 8f rank 1) -- the VIS sliding-window head over a synthetic video of this "
+                         "many frames of the workload's geometry (stride-1 clips of T frames), with per-frame feature reuse "
+                         "(ClipStream) and with the reference's schedule; one step = one video; N=1 only")
     ap.add_argument("--precision", default=os.environ.get("UNIVS_PRECISION", "fp16x3"), choices=["fp16x3", "tf32x3", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the clip eagerly instead of replaying a CUDA graph")
@@ -179,6 +183,37 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.video_frames > 0:
+        if world > 1:
+            raise SystemExit("--video-frames is a single-GPU benchmark")
+        from univs_b200.inference import InferenceVideoVISFast
+        V = max(args.video_frames, T)
+        video = [f for f in (torch.rand(V, 3, H, W, generator=g) * 255).to(torch.uint8).pin_memory()]
+        res = {}
+        for reuse in (True, False):
+            head = InferenceVideoVISFast(num_queries=Q, num_frames=T, num_frames_window_test=T, reuse_features=reuse)
+            run = lambda: head.eval(model, [{"image": video, "height": H, "width": W, "dataset_name": "ytvis21"}])
+            run()                                                       # warm-up (weight caches, allocator)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()                                    # host wall clock: the head has host control flow
+            for _ in range(steps):                                      # (Hungarian matching, result lists); sync'd both sides
+                out_v = run()
+            torch.cuda.synchronize()
+            res[reuse] = (time.perf_counter() - t0) / steps
+        print(json.dumps({
+            "metric": "video frames/sec (VIS fast head: stride-1 clips, MinVIS tracker, masks at output size)",
+            "value": V / res[True], "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": 1,
+            "ms_per_step": res[True] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"{args.workload}_video: Swin-{variant} V={V} frames {H}x{W}, T={T}, Q={Q}, "
+                                   f"{V - T + 1} clips, frames from pinned host memory, results (bool masks) to the host",
+                       "precision": args.precision, "execution": "eager"},
+            "reference_schedule": {"value": V / res[False], "unit": "frames/s", "ms_per_step": res[False] * 1e3,
+                                   "what": "same head with reuse_features=False: pixel decoder re-run for every clip, as "
+                                           "inference_video_vis_fast.py:223-236 does"},
+            "instances": len(out_v["pred_scores"])}))
+        return
 
     def timed(fn, n):
         barrier()
