@@ -120,6 +120,16 @@ int univs_mask_einsum_mma_f32(void* stream, const float* mask_embed, const float
 int univs_attn_mask_bits_f32(void* stream, const float* logits, int queries, int frames, int height, int width,
                              int tgt_h, int tgt_w, uint32_t* bits, int32_t* row_open);
 
+/* Pooled-feature variant of the same step (decoder_glue.cu): the resize is linear, so resize(E . F) = E . resize(F).
+ * univs_mask_feature_pool_f32 pools the channel-last mask features [T,H,W,C] once per clip to a memory size (even integer
+ * ratios: mean of the centre 2x2 block of each cell, the bilinear weights of align_corners=False) into [T, h*w, C] plain
+ * f32 (split 0) or the fp16 [hi|lo] einsum operand (split UNIVS_SPLIT_F16U); the mask einsum on it yields the logits at
+ * the memory resolution and univs_attn_mask_bits_direct_f32 turns those ([Q,T,S]) into the bits / row flags above. */
+int univs_mask_feature_pool_f32(void* stream, const float* feats_cl, int frames, int height, int width, int channels,
+                                int tgt_h, int tgt_w, void* out, int split);
+int univs_attn_mask_bits_direct_f32(void* stream, const float* logits, int queries, int frames, int keys, uint32_t* bits,
+                                    int32_t* row_open);
+
 /* ---- Multi-head attention core (a12 masked cross-attention, a13 spatio-temporal self-attention).
  * q [B,Lq,C], k,v [B,Lk,C] f32, already in-projected (q unscaled), head_dim 32, heads = C/32.
  * mask_bits (nullable) [Bm,Lq,ceil(Lk/32)] u32, Bm in {1,B}, bit set = blocked;

@@ -36,7 +36,7 @@ def _msda_fwd(value, shapes, starts, loc, w):
     return ops_ref.ms_deform_attn(value, sh, st, loc, w)
 
 
-def _einsum(mask_embed, feats_cl, out=None, mode=None):
+def _einsum(mask_embed, feats_cl, out=None, mode=None, tag=None):
     r = ops_ref.mask_einsum(mask_embed, feats_cl.transpose(1, 2))
     if out is not None:
         out.copy_(r)
@@ -46,6 +46,11 @@ def _einsum(mask_embed, feats_cl, out=None, mode=None):
 
 def _bits(mask_logits, hw, target_hw):
     m = ops_ref.attn_mask_from_logits(mask_logits, hw, target_hw)          # [T,Q,S] uint8
+    return ops.pack_mask_bits(m.bool()), (~m.bool().all(-1)).to(torch.int32)
+
+
+def _bits_direct(mask_logits):
+    m = ops_ref.attn_mask_direct(mask_logits)
     return ops.pack_mask_bits(m.bool()), (~m.bool().all(-1)).to(torch.int32)
 
 
@@ -143,7 +148,8 @@ _PATCH = {"layernorm": _layernorm,
           "split_tf32": _split,
           "split_operand": lambda x, split="tf32": _maybe_split(x, split),
           "swin_window_attention": _swin, "ms_deform_attn_encoder": _msda_enc, "ms_deform_attn_forward": _msda_fwd,
-          "mask_einsum": _einsum, "attn_mask_bits": _bits, "mha_core": _mha, "proca_core": _proca,
+          "mask_einsum": _einsum, "attn_mask_bits": _bits, "attn_mask_bits_direct": _bits_direct,
+          "mask_feature_pool": lambda f, hw, thw, mode=None: ops_ref.mask_feature_pool(f, hw, thw), "mha_core": _mha, "proca_core": _proca,
           "round_tf32": lambda x, out=None: x, "prepare_mask_features": lambda x, mode=None: x}
 
 

@@ -157,6 +157,21 @@ def attn_mask_from_logits(mask_logits, hw, target_hw):
     return (m.sigmoid() < 0.5).to(torch.uint8)
 
 
+def mask_feature_pool(feats_cl, hw, target_hw):
+    """Pooled-feature variant (csrc/decoder_glue.cu): the bilinear resize of ..._univs.py:555-560 applied to the mask
+    features [T, H*W, C] instead of the logits (resize and einsum are both linear).  Returns [T, h*w, C]."""
+    T, _, C = feats_cl.shape
+    H, W = hw
+    x = feats_cl.view(T, H, W, C).permute(0, 3, 1, 2)
+    y = F.interpolate(x, size=target_hw, mode="bilinear", align_corners=False)
+    return y.permute(0, 2, 3, 1).reshape(T, -1, C).contiguous()
+
+
+def attn_mask_direct(mask_logits):
+    """[Q,T,S] logits already at the memory resolution -> uint8 [T,Q,S], 1 = blocked (sigmoid < 0.5, ..._univs.py:561)"""
+    return (mask_logits.permute(1, 0, 2).sigmoid() < 0.5).to(torch.uint8)
+
+
 # ---------------------------------------------------------------------------
 # a12/a13: multi-head attention core of nn.MultiheadAttention (post in-projection,
 # pre out-projection): torch.nn.functional.multi_head_attention_forward, called from

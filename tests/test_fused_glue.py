@@ -250,3 +250,77 @@ def test_layernorm_multi_cuda(C, fmt):
     y2, op2, opp2 = ops.layernorm_multi(x.to(d), gamma.to(d), beta.to(d), want_f32=False, split=fmt)
     assert y2 is None and opp2 is None
     assert _rel(_unsplit(op2, fmt, C).cpu(), torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5)) < tol
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pooled-feature attention masks (csrc/decoder_glue.cu, UNIVS_POOLED_MASKS=1)
+# ---------------------------------------------------------------------------------------------------------------
+def test_pooled_feature_masks_equal_resized_logits_cpu():
+    """resize(E.F) == E.resize(F): the oracle's pooled features reproduce the reference's resized-logit decisions, and the
+    2x2-centre mean the CUDA kernel computes is torch's bilinear resize for even ratios."""
+    torch.manual_seed(2)
+    T, Q, C, H, W = 2, 9, 32, 16, 24
+    E, Fm = torch.randn(T, Q, C), torch.randn(T, H * W, C)
+    logits = ops_ref.mask_einsum(E, Fm.transpose(1, 2))                       # [Q,T,HW]
+    for tgt in ((8, 12), (4, 6), (2, 3)):
+        want = ops_ref.attn_mask_from_logits(logits, (H, W), tgt)             # reference order: einsum -> resize -> threshold
+        pooled = ops_ref.mask_feature_pool(Fm, (H, W), tgt)
+        small = ops_ref.mask_einsum(E, pooled.transpose(1, 2))
+        got = ops_ref.attn_mask_direct(small)
+        resized = torch.nn.functional.interpolate(logits.view(Q, T, H, W), size=tgt, mode="bilinear", align_corners=False)
+        near_zero = (resized.permute(1, 0, 2, 3).reshape(T, Q, -1).abs() < 1e-5)
+        assert ((got != want) & ~near_zero).sum() == 0
+        # closed form used by mask_feature_pool_kernel
+        ry, rx = H // tgt[0], W // tgt[1]
+        x = Fm.view(T, H, W, C)
+        a, b = ry // 2 - 1, rx // 2 - 1
+        mean = 0.5 * (0.5 * x[:, a::ry, b::rx] + 0.5 * x[:, a::ry, b + 1::rx]) + 0.5 * (0.5 * x[:, a + 1::ry, b::rx] + 0.5 * x[:, a + 1::ry, b + 1::rx])
+        assert _rel(mean.reshape(T, -1, C), pooled) < 1e-6
+
+
+def test_pooled_masks_decoder_path_equals_default_cpu():
+    T = 2
+    model = _model(T)
+    dec = model.sem_seg_head.predictor
+    g = torch.Generator().manual_seed(9)
+    frames = (torch.rand(T, 3, 64, 96, generator=g) * 255).round()
+    for tg in (lambda: [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual"}],
+               lambda: [{"task": "detection", "dataset_name": "bdd_track", "prompt_type": "text"}]):
+        outs = {}
+        for pooled in (False, True):
+            dec.pooled_masks = pooled
+            seen = []
+            dec.attn_mask_hook = lambda i, bits, ro: (seen.append((bits.clone(), ro.clone())), (bits, ro))[1]
+            try:
+                with oracle_ops():
+                    outs[pooled] = (model.clip_forward(frames, tg()), seen)
+            finally:
+                dec.pooled_masks = False
+                dec.attn_mask_hook = None
+        (o0, s0), (o1, s1) = outs[False], outs[True]
+        assert len(s0) == len(s1) > 0
+        for (b0, r0), (b1, r1) in zip(s0, s1):                 # identical decisions in every intermediate head
+            assert torch.equal(b0, b1) and torch.equal(r0, r1)
+        for k in ("pred_masks", "pred_logits", "pred_embds"):
+            assert o1[k].shape == o0[k].shape and _rel(o1[k], o0[k]) < 1e-5, k
+
+
+@pytest.mark.gpu
+@_gpu_glue
+@pytest.mark.parametrize("mode", ["f16x3", "mma3x"])
+def test_pooled_mask_kernels_gpu(mode):
+    from univs_b200 import ops
+    torch.manual_seed(4)
+    T, Q, C, H, W = 2, 37, 256, 48, 80
+    E, Fm = torch.randn(T, Q, C), torch.randn(T, H * W, C)
+    for tgt in ((24, 40), (12, 20), (6, 10)):
+        want = ops_ref.mask_feature_pool(Fm, (H, W), tgt)
+        got = ops.mask_feature_pool(Fm.cuda(), (H, W), tgt, mode=mode)
+        if mode == "f16x3":
+            got = got[..., :C].float() + got[..., C:].float()
+        assert _rel(got, want) < 2e-6
+        small = ops_ref.mask_einsum(E, want.transpose(1, 2))
+        bits, ro = ops.attn_mask_bits_direct(small.cuda())
+        m = ops_ref.attn_mask_direct(small).bool()
+        assert torch.equal(bits.cpu(), ops.pack_mask_bits(m))
+        assert torch.equal(ro.cpu(), (~m.all(-1)).to(torch.int32))

@@ -24,6 +24,8 @@ SIGNATURES = {
     "univs_mask_einsum_f16x3": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "univs_mask_einsum_mma_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "univs_attn_mask_bits_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "univs_mask_feature_pool_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i]),
+    "univs_attn_mask_bits_direct_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "univs_mha_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "univs_mha_forward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "univs_mha_tc_workspace_bytes": (_i64, [_i, _i, _i, _i]),

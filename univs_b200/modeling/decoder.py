@@ -19,6 +19,8 @@ out of scope and raise.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -225,6 +227,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         # diagnostic hook (tools/parity_at_scale.py): fn(call_index, bits, row_open) -> (bits, row_open); lets a parity
         # run record the attention-mask decisions or replay another run's decisions.  None in normal operation.
         self.attn_mask_hook = None
+        # intermediate heads from pooled mask features (csrc/decoder_glue.cu): resize(E.F) = E.resize(F); opt-in
+        self.pooled_masks = os.environ.get("UNIVS_POOLED_MASKS", "0") == "1"
         self._head_calls = 0
         self._clip_norm_cache = None
         self.eval()
@@ -319,7 +323,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         y = nn_ops.layernorm(tok, layer.norm, residual=o, for_gemm=False, residual_bias=mha.out_proj.bias)[1]   # [P,T,C]
         return torch.cat([x[:, :nq], y.transpose(0, 1)], 1)
 
-    def _heads(self, x, feats_cl, hw, next_hw, task, targets, t, need_class, need_attn, out_buf=None, exchange=None):
+    def _heads(self, x, feats_cl, hw, next_hw, task, targets, t, need_class, need_attn, out_buf=None, exchange=None,
+               pooled_feats=None):
         """forward_prediction_heads (:498-567).  x [T,Q,C] -> (class logits | None, mask logits [Q,T,HW], bits, row_open, reid)"""
         dec, dec_g = nn_ops.layernorm(x, self.decoder_norm, want_sum=False, for_gemm=False)[1], None
         dec_g = nn_ops.prep(dec)                                            # GEMM operand of decoder_norm(x)
@@ -338,6 +343,15 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
                 exp = torch.stack([tg["exp_sentence_feats"][:, 0] for tg in targets]).to(oc)      # [1,P,640]
                 cls = nn_ops.linear(oc.mean(0, keepdim=True), exp[0].contiguous(), cache=False)
         emb = self.mask_embed(dec_g, prepped=True)                          # [T,Q,C]
+        if pooled_feats is not None:
+            # intermediate head: its mask logits only feed the next layer's attention mask, and the bilinear resize to the
+            # memory size commutes with the einsum -- run it on the pooled features, at the memory resolution
+            small = ops.mask_einsum(emb.contiguous(), pooled_feats, tag="mask_einsum_pooled")      # [Q,T,S_next]
+            bits, row_open = ops.attn_mask_bits_direct(small)
+            if self.attn_mask_hook is not None:
+                bits, row_open = self.attn_mask_hook(self._head_calls, bits, row_open)
+            self._head_calls += 1
+            return cls, None, bits, row_open, reid
         logits = ops.mask_einsum(emb.contiguous(), feats_cl, out=out_buf)   # [Q,T,HW]
         if task == "grounding" and self.prompt_as_queries:
             # learnable-for-prompt mask fusion (:537-547)
@@ -456,7 +470,8 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         feats_cl = mask_features.permute(0, 2, 3, 1)                        # [T,H,W,C]
         if not feats_cl.is_contiguous():
             feats_cl = feats_cl.contiguous()
-        feats_cl = ops.prepare_mask_features(feats_cl.view(t, h_m * w_m, c_m))
+        feats_raw = feats_cl.view(t, h_m * w_m, c_m)
+        feats_cl = ops.prepare_mask_features(feats_raw)
         if "frame_indices" in targets[0]:
             frame_indices = targets[0]["frame_indices"]
         else:
@@ -492,8 +507,14 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
 
         hw = (h_m, w_m)
         self._head_calls = 0
+        pooled = {}
+        if (self.pooled_masks and not want_aux and not (task == "grounding" and self.prompt_as_queries)
+                and all(h_m % h == 0 and w_m % w == 0 and (h_m // h) % 2 == 0 and (w_m // w) % 2 == 0 for h, w in size_list)):
+            for size in size_list:         # once per clip: the mask features at the three memory resolutions
+                if size not in pooled:
+                    pooled[size] = ops.mask_feature_pool(feats_raw, hw, size)
         cls, logits, bits, row_open, reid = self._heads(out, feats_cl, hw, size_list[0], task, targets, t, want_aux, True,
-                                                        exchange=exchange)
+                                                        exchange=exchange, pooled_feats=pooled.get(size_list[0]))
         if want_aux:
             record(cls, logits, reid, out)
         sa_bits = self._self_attn_mask_bits(t_all, n_lp, device, task)
@@ -516,7 +537,7 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
             last = i == self.num_layers - 1
             cls, logits, bits, row_open, reid = self._heads(
                 out, feats_cl, hw, size_list[(i + 1) % 3], task, targets, t, want_aux or last, not last, out_buf=logits,
-                exchange=exchange)
+                exchange=exchange, pooled_feats=None if last else pooled.get(size_list[(i + 1) % 3]))
             if want_aux and not last:
                 record(cls, logits, reid, out)
         embds = nn_ops.layernorm(out.transpose(0, 1), self.decoder_norm, for_gemm=False)[1][None]   # [1,Q,T,C]

@@ -225,8 +225,9 @@ def prepare_mask_features(mask_features_cl, mode=None):
     return mask_features_cl
 
 
-def mask_einsum(mask_embed, mask_features_prepared, out=None, mode=None):
-    """mask_embed [T,Q,C] fp32, mask_features_prepared from prepare_mask_features (channel-last) -> [Q,T,HW] fp32."""
+def mask_einsum(mask_embed, mask_features_prepared, out=None, mode=None, tag="mask_einsum"):
+    """mask_embed [T,Q,C] fp32, mask_features_prepared from prepare_mask_features (channel-last) -> [Q,T,HW] fp32.
+    `tag` names the launch in the per-kernel event brackets (bench.py)."""
     mode = _einsum_mode if mode is None else mode
     T, Q, Cc = mask_embed.shape
     HW = mask_features_prepared.shape[1]
@@ -234,21 +235,21 @@ def mask_einsum(mask_embed, mask_features_prepared, out=None, mode=None):
         out = torch.empty((Q, T, HW), device=mask_embed.device, dtype=torch.float32)
     if Q > 256:      # one launch covers <= 256 queries (TMEM columns); large prompt vocabularies run in query chunks
         for q0 in range(0, Q, 256):
-            mask_einsum(mask_embed[:, q0:q0 + 256].contiguous(), mask_features_prepared, out=out[q0:q0 + 256], mode=mode)
+            mask_einsum(mask_embed[:, q0:q0 + 256].contiguous(), mask_features_prepared, out=out[q0:q0 + 256], mode=mode, tag=tag)
         return out
     if mode == "f16x3":
         e = split_operand(mask_embed if mask_embed.is_contiguous() else mask_embed.contiguous(), "f16u")
-        with _Bracket("mask_einsum", 1):
+        with _Bracket(tag, 1):
             rc = lib().univs_mask_einsum_f16x3(_stream(), _chk(e, "mask_embed", torch.float16),
                                                _chk(mask_features_prepared, "mask_features", torch.float16),
                                                T, Q, Cc, HW, _chk(out, "out"))
     elif mode == "tf32":
         e = round_tf32(mask_embed)
-        with _Bracket("mask_einsum", 1):
+        with _Bracket(tag, 1):
             rc = lib().univs_mask_einsum_f32(_stream(), _chk(e, "mask_embed"), _chk(mask_features_prepared, "mask_features"),
                                              T, Q, Cc, HW, _chk(out, "out"))
     else:
-        with _Bracket("mask_einsum", 1):
+        with _Bracket(tag, 1):
             rc = lib().univs_mask_einsum_mma_f32(_stream(), _chk(mask_embed, "mask_embed"),
                                                  _chk(mask_features_prepared, "mask_features"), T, Q, Cc, HW, PREC_TF32X3,
                                                  _chk(out, "out"))
@@ -282,6 +283,33 @@ def attn_mask_bits(mask_logits, hw, target_hw):
         rc = lib().univs_attn_mask_bits_f32(_stream(), _chk(mask_logits, "mask_logits"), Q, T, H, W, h, w,
                                         bits.data_ptr(), row_open.data_ptr())
     check(rc, "attn_mask_bits")
+    return bits, row_open
+
+
+def mask_feature_pool(feats_cl, hw, target_hw, mode=None):
+    """Mask features [T, H*W, C] fp32 (channel-last) pooled to `target_hw` in the operand format of the einsum mode
+    (see prepare_mask_features): [T, h*w, C or 2C]."""
+    mode = _einsum_mode if mode is None else mode
+    T, _, C = feats_cl.shape
+    (H, W), (h, w) = hw, target_hw
+    f16 = mode == "f16x3"
+    out = torch.empty((T, h * w, 2 * C if f16 else C), device=feats_cl.device, dtype=torch.float16 if f16 else torch.float32)
+    with _Bracket("mask_feature_pool", 1):
+        rc = lib().univs_mask_feature_pool_f32(_stream(), _chk(feats_cl, "mask_features"), T, H, W, C, h, w, out.data_ptr(),
+                                               -2 if f16 else 0)
+    check(rc, "mask_feature_pool")
+    return round_tf32(out) if mode == "tf32" else out
+
+
+def attn_mask_bits_direct(mask_logits):
+    """mask_logits [Q,T,S] at the memory resolution -> (bits [T,Q,words], row_open [T,Q])"""
+    Q, T, S = mask_logits.shape
+    bits = torch.empty((T, Q, (S + 31) // 32), device=mask_logits.device, dtype=torch.int32)
+    row_open = torch.empty((T, Q), device=mask_logits.device, dtype=torch.int32)
+    with _Bracket("attn_mask_bits", 1):
+        rc = lib().univs_attn_mask_bits_direct_f32(_stream(), _chk(mask_logits, "mask_logits"), Q, T, S, bits.data_ptr(),
+                                                   row_open.data_ptr())
+    check(rc, "attn_mask_bits_direct")
     return bits, row_open
 
 
