@@ -156,7 +156,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from univs_b200 import ops
+    from univs_b200 import ops, switches
     from univs_b200.build import build_model, make_cfg
     from univs_b200.precision import set_precision
 
@@ -341,6 +341,7 @@ def main():
                                                                   if model.shard_decoder else ", feature all-gather"))
                        if world > 1 else "single",
                        "execution": "CUDA graph replay" if use_graph else "eager",
+                       "switches": switches.active(),      # opt-in paths that were on ({} = the round-1 default path)
                        "l2": "per-step working set (multi-GB activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": T / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

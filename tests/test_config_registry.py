@@ -86,3 +86,16 @@ def test_training_mode_is_rejected():
     m.train()
     with pytest.raises(NotImplementedError):
         m([{"image": [torch.zeros(3, 32, 32)] * 2}])
+
+
+def test_switch_defaults_are_the_round1_path(monkeypatch):
+    """every opt-in path is off unless asked for (environment > univs_b200/tuned.json > built-in default)"""
+    import importlib
+    from univs_b200 import switches
+    for k in switches.DEFAULTS:
+        monkeypatch.delenv("UNIVS_" + k, raising=False)
+    importlib.reload(switches)
+    assert switches.active() == {k: v for k, v in switches._TUNED.items() if v != switches.DEFAULTS[k]}
+    monkeypatch.setenv("UNIVS_WIN_TC", "1")
+    monkeypatch.setenv("UNIVS_FRAME_STREAMS", "2")
+    assert switches.get("win_tc") == 1 and switches.active()["FRAME_STREAMS"] == 2

@@ -62,6 +62,8 @@ def lib():
             raise UnivsB200Error(
                 f"{LIB_PATH} not found: build it with `bash univs_b200/csrc/build.sh` "
                 "(there is no CPU / PyTorch fallback for the hot-path kernels)")
+        from . import switches
+        switches.export_native()
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)

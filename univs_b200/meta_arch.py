@@ -17,9 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-import os
-
-from . import nn_ops
+from . import nn_ops, switches
 from .registry import META_ARCH_REGISTRY, build_backbone, build_sem_seg_head
 from .sharding import FrameSharder, TokenExchange
 
@@ -45,10 +43,10 @@ class UniVS_Prompt(nn.Module):
         self.register_buffer("pixel_std", torch.tensor(pixel_std, dtype=torch.float32).view(-1, 1, 1), False)
         self.sharder = FrameSharder(process_group)
         # frame-sharded decoder with per-layer token exchange instead of the feature all-gather (opt-in)
-        self.shard_decoder = (os.environ.get("UNIVS_SHARD_DECODER", "0") == "1") if shard_decoder is None else shard_decoder
+        self.shard_decoder = (switches.get("SHARD_DECODER") == 1) if shard_decoder is None else shard_decoder
         # single GPU: backbone + pixel decoder of g frame groups on g CUDA streams, so that the memory-bound passes of one
         # group can run under the tensor-core GEMMs of another (frames are independent up to the decoder); opt-in
-        self.frame_streams = int(os.environ.get("UNIVS_FRAME_STREAMS", "1")) if frame_streams is None else int(frame_streams)
+        self.frame_streams = switches.get("FRAME_STREAMS") if frame_streams is None else int(frame_streams)
         self._streams = []
         self.eval()
 

@@ -19,13 +19,11 @@ out of scope and raise.
 """
 from __future__ import annotations
 
-import os
-
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import nn_ops, ops
+from .. import nn_ops, ops, switches
 from ..registry import TRANSFORMER_DECODER_REGISTRY, is_cfg
 from . import position
 from .prompt_sampler import VisualPromptSampler
@@ -228,7 +226,7 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         # run record the attention-mask decisions or replay another run's decisions.  None in normal operation.
         self.attn_mask_hook = None
         # intermediate heads from pooled mask features (csrc/decoder_glue.cu): resize(E.F) = E.resize(F); opt-in
-        self.pooled_masks = os.environ.get("UNIVS_POOLED_MASKS", "0") == "1"
+        self.pooled_masks = switches.get("POOLED_MASKS") == 1
         self._head_calls = 0
         self._clip_norm_cache = None
         self.eval()

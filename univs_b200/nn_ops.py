@@ -14,14 +14,14 @@ import os
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, switches
 
 _policy = "fp32"
 _wcache = {}
 # Fused glue kernels (channel-last GroupNorm + FPN add / ReLU / operand emission, PatchMerging gather-LayerNorm, fused
 # frame ingest; csrc/groupnorm.cu, csrc/swin_glue.cu).  Written at the end of round 1 without GPU time left to validate
 # them, hence opt-in (UNIVS_FUSED_GLUE=1 or set_fused_glue(True)); the default path is the one measured in round 1.
-_fused_glue = os.environ.get("UNIVS_FUSED_GLUE", "0") == "1"
+_fused_glue = switches.get("FUSED_GLUE") == 1
 
 
 def set_fused_glue(on: bool):

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, switches
 from ._cabi import check, lib
 
 PREC_TF32X3 = 0
@@ -117,7 +117,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 # Work distribution of the encoder MSDeformAttn kernel: 0 = 4 consecutive queries x 8 heads per CTA (validated in round 1),
 # w in {1,..,32} = w x (32/w) query tiles of one head per CTA (bit-identical results, better L1 reuse; opt-in until it
 # has been run on a B200).
-_msda_tile = int(os.environ.get("UNIVS_MSDA_TILE", "0"))
+_msda_tile = switches.get("MSDA_TILE")
 
 
 def set_msda_tile(width: int):
@@ -155,7 +155,7 @@ def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits
     return out
 
 
-_win_tc = int(os.environ.get("UNIVS_WIN_TC", "0"))   # opt-in: 1 = tcgen05 kernel for 12x12 windows
+_win_tc = switches.get("WIN_TC")   # opt-in: 1 = tcgen05 kernel for 12x12 windows
 
 
 def swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, want_f32=True, want_operand=False,
@@ -325,7 +325,7 @@ def _workspace(nbytes, device):
     return ws
 
 
-_mha_tc = int(os.environ.get("UNIVS_MHA_TC", "0"))   # opt-in: 1 = tcgen05 kernel for the cross-attention shape (Lq <= 256),
+_mha_tc = switches.get("MHA_TC")   # opt-in: 1 = tcgen05 kernel for the cross-attention shape (Lq <= 256),
                                                       # 3 = the same with the transposed-V (K-major) diagnostic variant
 MHA_TC_MIN_KEYS = 512
 
