@@ -2,18 +2,20 @@
 # First GPU call of round 2: validates everything that was written without GPU time at the end of round 1 and measures
 # it, in ONE box session.  Every step runs under its own `timeout` (a hung kernel must not hang the box) and logs to
 # gpurun_out/r2_open/; a failing step does not stop the next one.
-#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_round2_open.sh'
+#   /usr/local/graft/bin/gpurun --timeout 3300 -- 'bash tools/gpu_round2_open.sh'      (≈ 40 min of box time)
+# STEPS=a,b,c restricts the run to the named steps (names as in the `run` lines below).
 set -u
 out=gpurun_out/r2_open
 mkdir -p "$out"
 run() {  # name, seconds, command...
   local name=$1 secs=$2; shift 2
+  if [ -n "${STEPS:-}" ] && [[ ",$STEPS," != *",$name,"* ]]; then return 0; fi
   echo "=== $name: $*" | tee -a "$out/summary.txt"
   ( time timeout "$secs" "$@" ) > "$out/$name.log" 2>&1
   echo "    exit $? ($(tail -n 4 "$out/$name.log" | tr '\n' ' ' | cut -c1-300))" | tee -a "$out/summary.txt"
 }
 # 0. the validated default path still green on this box
-run default_gpu_tests 900 python -m pytest tests -m gpu -q -x
+run default_gpu_tests 1500 python -m pytest tests -m gpu -q -x
 # 1. opt-in kernels, one family per step so that a trapped launch (sticky CUDA error) only spoils its own process
 UNIVS_GPU_WINTC=1 run wintc_tests 600 python -m pytest tests/test_window_attn_tc.py -m gpu -q
 run wintc_check 600 python tools/win_tc_check.py --time
