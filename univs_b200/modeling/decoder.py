@@ -517,14 +517,17 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
             record(cls, logits, reid, out)
         sa_bits = self._self_attn_mask_bits(t_all, n_lp, device, task)
         qpos_all = exchange.gather(qpos) if exchange is not None else None   # constant over the layers
+        kv_operands = {}
         for i in range(self.num_layers):
             if self.prompt_as_queries and 0 < i < self.prompt_self_attn_layers:
                 out = self._proca(i, out, qpos, mem, mem_pe)
             lvl = i % 3
             ca = self.transformer_cross_attention_layers[i].multihead_attn
             wk, bk = ca.wk(); wv, bv = ca.wv()
-            k = nn_ops.linear(src[lvl] + pos[lvl], wk, None)      # biases handled in _cross_attention
-            v = nn_ops.linear(src[lvl], wv, None)
+            if lvl not in kv_operands:      # every level feeds three layers: its GEMM operands are prepared once
+                kv_operands[lvl] = (nn_ops.prep(src[lvl] + pos[lvl]), nn_ops.prep(src[lvl]))
+            k = nn_ops.linear_prepped(kv_operands[lvl][0], wk, None)      # biases handled in _cross_attention
+            v = nn_ops.linear_prepped(kv_operands[lvl][1], wv, None)
             out = self._cross_attention(self.transformer_cross_attention_layers[i], out, qpos, k, v, bits, row_open)
             if exchange is None:
                 out = self._self_attention(self.transformer_self_attention_layers[i], out, qpos, sa_bits)
