@@ -20,6 +20,7 @@ run default_gpu_tests 1500 python -m pytest tests -m gpu -q -x
 UNIVS_GPU_WINTC=1 run wintc_tests 600 python -m pytest tests/test_window_attn_tc.py -m gpu -q
 run wintc_check 600 python tools/win_tc_check.py --time
 UNIVS_GPU_MHATC=1 run mhatc_tests 600 python -m pytest tests/test_mha_tc.py -m gpu -q
+run mhatc_check 600 python tools/mha_tc_check.py --time
 UNIVS_GPU_ROWWISE_V2=1 run rowwise_v2_tests 600 python -m pytest tests/test_rowwise_v2.py -m gpu -q
 UNIVS_GPU_GLUE=1 run glue_tests 900 python -m pytest tests/test_fused_glue.py -m gpu -q
 UNIVS_GPU_HEADS=1 run heads_tests 900 python -m pytest tests/test_heads_golden.py -m gpu -q
