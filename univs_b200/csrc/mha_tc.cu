@@ -23,6 +23,8 @@
 // Pipelining: softmax warps run softmax(n+1) -> merge(n), the MMA lane S(n+1) -> PV(n); consecutive units alternate
 // between the two row tiles, so the running state touched by softmax(n+1) and merge(n) is disjoint.
 // HBM-bound by design: K and V are read once per (frame, head) = 2 * S * 128 B; everything else is on chip.
+#include <stdlib.h>
+
 #include "tc05.cuh"
 
 namespace univs {
@@ -443,6 +445,12 @@ static void plan(int B, int heads, int Lk, int& nsplit, int& bps) {
   const int nkb = (Lk + kBlk - 1) / kBlk;
   const long long pairs = (long long)B * heads;
   int want = (int)(num_sms / pairs);      // one wave: at most one CTA per SM
+  static int forced = -1;                 // tuning aid: UNIVS_MHA_TC_SPLITS overrides the number of key splits
+  if (forced < 0) {
+    const char* e = getenv("UNIVS_MHA_TC_SPLITS");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) want = forced;
   if (want < 1) want = 1;
   if (want > nkb) want = nkb;
   bps = (nkb + want - 1) / want;
