@@ -191,8 +191,9 @@ def main():
         V = max(args.video_frames, T)
         video = [f for f in (torch.rand(V, 3, H, W, generator=g) * 255).to(torch.uint8).pin_memory()]
         res = {}
-        for reuse in (True, False):
-            head = InferenceVideoVISFast(num_queries=Q, num_frames=T, num_frames_window_test=T, reuse_features=reuse)
+        for reuse in (True, False, "rle"):     # "rle": feature reuse + COCO RLE results (run scan on the device)
+            head = InferenceVideoVISFast(num_queries=Q, num_frames=T, num_frames_window_test=T, reuse_features=bool(reuse),
+                                         rle_output=reuse == "rle")
             run = lambda: head.eval(model, [{"image": video, "height": H, "width": W, "dataset_name": "ytvis21"}])
             run()                                                       # warm-up (weight caches, allocator)
             torch.cuda.synchronize()
@@ -212,6 +213,9 @@ def main():
             "reference_schedule": {"value": V / res[False], "unit": "frames/s", "ms_per_step": res[False] * 1e3,
                                    "what": "same head with reuse_features=False: pixel decoder re-run for every clip, as "
                                            "inference_video_vis_fast.py:223-236 does"},
+            "rle_results": {"value": V / res["rle"], "unit": "frames/s", "ms_per_step": res["rle"] * 1e3,
+                            "what": "feature reuse + results as COCO RLE built from device-side run boundaries instead of "
+                                    "dense bool masks copied to the host"},
             "instances": len(out_v["pred_scores"])}))
         return
 

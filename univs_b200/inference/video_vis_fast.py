@@ -19,13 +19,15 @@ from torch import nn
 from ..modeling.decoder import COMBINED_DATASETS_CATEGORY_INFO
 from ..registry import is_cfg
 from ..streaming import ClipStream
+from . import rle
 from .comm import TemporalMaskMean, calculate_mask_quality_scores, match_from_learnable_embds
 
 
 class InferenceVideoVISFast(nn.Module):
     def __init__(self, cfg=None, *, num_queries=200, num_frames=5, size_divisibility=32, stability_score_thresh=0.0,
                  test_topk_per_image=100, zero_shot_inference=False, tracker_type="minvis", merge_on_cpu=False,
-                 num_frames_window_test=5, lsj_aug_enable_test=False, lsj_aug_image_size=1024, reuse_features=True):
+                 num_frames_window_test=5, lsj_aug_enable_test=False, lsj_aug_image_size=1024, reuse_features=True,
+                 rle_output=False):
         super().__init__()
         if cfg is not None and is_cfg(cfg):
             mf, bv = cfg.MODEL.MASK_FORMER, cfg.MODEL.BoxVIS.TEST
@@ -52,6 +54,9 @@ class InferenceVideoVISFast(nn.Module):
         self.LSJ_aug_enable_test = lsj_aug_enable_test
         self.LSJ_aug_image_size = lsj_aug_image_size
         self.reuse_features = reuse_features
+        # True: return COCO RLE per (instance, frame) -- what the reference's writers build on the host from the dense masks
+        # (inference_video_vis.py:526-531) -- with the run scan on the device, instead of the dense masks themselves
+        self.rle_output = rle_output
 
     # ------------------------------------------------------------------ entry point (reference :185-218)
     @torch.no_grad()
@@ -165,12 +170,18 @@ class InferenceVideoVISFast(nn.Module):
         quality = calculate_mask_quality_scores(mask_pred[:, ::step]).clamp(min=0.1)
         scores_per_video = scores_per_video * quality.to(scores_per_video.device)
 
-        masks_per_video = []
+        masks_per_video, rles_per_video = [], []
         for m in mask_pred:        # one object at a time: bounded memory for long videos (:330-338)
             m = F.interpolate(m.unsqueeze(0), size=out_size, mode="bilinear", align_corners=False).squeeze(0) > 0.0
-            masks_per_video.append(m.cpu())
-        return {"image_size": out_size, "pred_scores": scores_per_video.tolist(),
-                "pred_labels": labels_per_video.tolist(), "pred_masks": masks_per_video}
+            if self.rle_output:
+                rles_per_video.append(rle.encode(m))           # [V] dicts; only the run boundaries leave the device
+            else:
+                masks_per_video.append(m.cpu())
+        out = {"image_size": out_size, "pred_scores": scores_per_video.tolist(),
+               "pred_labels": labels_per_video.tolist(), "pred_masks": masks_per_video}
+        if self.rle_output:
+            out["segmentations"] = rles_per_video
+        return out
 
 
 class _Images:
