@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import nn_ops, switches
+from . import nn_ops, ops, switches
 from .registry import META_ARCH_REGISTRY, build_backbone, build_sem_seg_head
 from .sharding import FrameSharder, TokenExchange
 
@@ -157,13 +157,17 @@ class UniVS_Prompt(nn.Module):
                 mask_features, mf_bfe, _enc, multi_scale = pd.forward_features(feats)
                 return mask_features, list(multi_scale)
 
-            if on_gpu:
-                st = self._streams[g]
-                st.wait_stream(cur)
-                with torch.cuda.stream(st):
+            ops.scratch_slot = g                 # persistent scratch buffers are per group (groups run concurrently)
+            try:
+                if on_gpu:
+                    st = self._streams[g]
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        outs.append(run())
+                else:
                     outs.append(run())
-            else:
-                outs.append(run())
+            finally:
+                ops.scratch_slot = 0
         if on_gpu:
             for g in range(n):
                 cur.wait_stream(self._streams[g])

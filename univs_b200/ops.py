@@ -464,8 +464,15 @@ def split_operand(x, split="tf32"):
 _gn_ws = {}
 
 
+# Scratch buffers that persist between calls (GroupNorm partial sums here, the zero-bordered operand buffers in nn_ops) are
+# keyed by this slot: meta_arch._grouped_forward issues frame group g with scratch_slot = g, so concurrently running groups
+# never share one.  (Not keyed by the stream id: under CUDA-graph capture the stream differs from the warm-up stream and a
+# fresh buffer -- with its zero fill -- would be captured into the graph.)
+scratch_slot = 0
+
+
 def _gn_workspace(device, nbytes):
-    key = (device, torch.cuda.current_stream().cuda_stream)      # per stream: frame groups may run concurrently
+    key = (device, scratch_slot)
     buf = _gn_ws.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 16), device=device, dtype=torch.uint8)
