@@ -387,7 +387,9 @@ def load_inference_heads():
     _mod("univs.inference.visualization", visualization_query_embds=lambda **kw: None)
     _mod("univs.utils.visualizer", VisualizerFrame=object)
     vos = imp("univs.inference.inference_video_vos")
-    _HEADS = types.SimpleNamespace(comm=comm, utils_comm=ucomm, vis_fast=vis_fast, vos=vos,
+    vps = imp("univs.inference.inference_video_vps")
+    _HEADS = types.SimpleNamespace(comm=comm, utils_comm=ucomm, vis_fast=vis_fast, vos=vos, vps=vps,
+                                   InferenceVideoVPS=vps.InferenceVideoVPS,
                                    InferenceVideoVISFast=vis_fast.InferenceVideoVISFast,
                                    InferenceVideoVOS=vos.InferenceVideoVOS,
                                    RefModel=_RefModel, ImageList=_ImageList, Instances=_Instances,

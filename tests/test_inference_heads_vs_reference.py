@@ -357,3 +357,46 @@ def test_heads_build_from_cfg_and_pad_square():
         out = head.eval(model, [{"image": frames, "dataset_name": "ovis", "height": 60, "width": 90}])
     assert out["image_size"] == (60, 90) and out["pred_masks"][0].shape == (V, 60, 90)
     assert model.sem_seg_head.predictor is not None and len(out["pred_scores"]) == len(out["pred_labels"]) >= 5
+
+
+def test_vps_online_head():
+    """InferenceVideoVPS (inference_video_vps.py): clip loop + tracker + panoptic assembly against the reference head."""
+    import types
+    from univs_b200.inference import InferenceVideoVPS
+    heads = ref_shim.load_inference_heads()
+    T, Q, V, H, W = 2, 12, 4, 60, 90
+    ref, model = _pair(T, Q, enc_layers=1, dec_layers=3)
+    g = torch.Generator().manual_seed(11)
+    frames = [(torch.rand(3, H, W, generator=g) * 255).round() for _ in range(V)]
+    inputs = [{"image": frames, "height": 75, "width": 120, "dataset_name": "vipseg", "task": "detection",
+               "video_len": V, "file_names": [f"{i}.jpg" for i in range(V)]}]
+    things = {c for c in range(1, 125) if c % 3 == 0}            # synthetic thing / stuff split of the 124 VIPSeg classes
+    meta = types.SimpleNamespace(thing_dataset_id_to_contiguous_id={c: i for i, c in enumerate(sorted(things))})
+    kw = dict(hidden_dim=256, num_queries=Q, object_mask_threshold=0.0, overlap_threshold=0.3, overlap_threshold_entity=0.5,
+              stability_score_thresh=0.0, metadata=meta, size_divisibility=32, LSJ_aug_image_size=1024,
+              LSJ_aug_enable_test=False, sem_seg_postprocess_before_inference=False, pixel_mean=MEAN, pixel_std=STD,
+              num_frames=T, data_name="vipseg_val", prompt_as_queries=True, zero_shot_inference=False, semantic_on=False,
+              instance_on=False, panoptic_on=True, test_topk_per_image=8, tracker_type="minvis", window_inference=False,
+              is_multi_cls=True, apply_cls_thres=0.05, merge_on_cpu=False, num_max_inst_test=50, num_frames_window_test=T,
+              clip_stride=1)
+    import inspect
+    accepted = set(inspect.signature(heads.InferenceVideoVPS.__init__).parameters)
+    rhead = heads.InferenceVideoVPS(**{k: v for k, v in kw.items() if k in accepted})
+    xs = torch.stack([(f - rhead.pixel_mean) / rhead.pixel_std for f in frames])
+    xs = torch.nn.functional.pad(xs, (0, 96 - W, 0, 64 - H))
+    rimages = heads.ImageList(xs, [(H, W)] * V)
+    tg = [{"task": "detection", "dataset_name": "vipseg", "prompt_type": "visual"}]
+    with torch.no_grad():
+        want = rhead.inference_video_vps_online(heads.RefModel(*ref), inputs, rimages, tg)
+
+    for reuse in (True, False):
+        phead = InferenceVideoVPS(num_queries=Q, num_frames=T, object_mask_threshold=0.0, overlap_threshold=0.3,
+                                  test_topk_per_image=8, num_frames_window_test=T, thing_ids=things, reuse_features=reuse)
+        with oracle_ops():
+            got = phead.eval(model, inputs)
+        assert got["image_size"] == want["image_size"] == (720, 1152) and got["task"] == "vps"
+        assert got["segments_infos"] == want["segments_infos"] and len(got["segments_infos"]) > 0
+        assert [int(i) for i in got["pred_ids"]] == [int(i) for i in want["pred_ids"]]
+        assert got["pred_masks"].shape == want["pred_masks"].shape == (V, 720, 1152)
+        diff = (got["pred_masks"] != want["pred_masks"]).float().mean().item()
+        assert diff <= 1e-4, diff

@@ -4,7 +4,8 @@ from .comm import (TemporalMaskMean, calculate_mask_quality_scores, check_consis
                    generate_temporal_weights, match_from_learnable_embds, pair_mask_iou, video_box_iou)
 from .video_vis_fast import InferenceVideoVISFast
 from .video_vos import FrameAnnotations, InferenceVideoVOS
+from .video_vps import InferenceVideoVPS
 
-__all__ = ["InferenceVideoVISFast", "InferenceVideoVOS", "FrameAnnotations", "match_from_learnable_embds",
+__all__ = ["InferenceVideoVISFast", "InferenceVideoVOS", "InferenceVideoVPS", "FrameAnnotations", "match_from_learnable_embds",
            "check_consistency_with_prev_frames", "generate_temporal_weights", "calculate_mask_quality_scores",
            "video_box_iou", "pair_mask_iou", "TemporalMaskMean"]
