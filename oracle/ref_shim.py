@@ -365,7 +365,15 @@ def load_inference_heads():
     load()
     R = REF_ROOT
     _mod("kornia", color=types.SimpleNamespace())
-    mu = _mod("pycocotools.mask")
+    def _encode(arr):
+        """pycocotools.mask.encode for an [h, w, n] uint8 array (restated codec, oracle/rle_ref.py); counts as bytes"""
+        from . import rle_ref
+        out = []
+        for k in range(arr.shape[2]):
+            r = rle_ref.encode(arr[:, :, k])
+            out.append({"size": r["size"], "counts": r["counts"].encode("ascii")})
+        return out
+    mu = _mod("pycocotools.mask", encode=_encode)
     _mod("pycocotools", mask=mu)
     _mod("detectron2.data", MetadataCatalog=types.SimpleNamespace(get=lambda name: types.SimpleNamespace()))
     _mod("detectron2.modeling.postprocessing", sem_seg_postprocess=None)
@@ -388,7 +396,11 @@ def load_inference_heads():
     _mod("univs.utils.visualizer", VisualizerFrame=object)
     vos = imp("univs.inference.inference_video_vos")
     vps = imp("univs.inference.inference_video_vps")
+    _mod("univs.data", datasets=None)
+    _mod("univs.data.datasets", _get_vspw_vss_metadata=None, _get_vipseg_panoptic_metadata_val=None)
+    entity = imp("univs.inference.inference_video_entity")
     _HEADS = types.SimpleNamespace(comm=comm, utils_comm=ucomm, vis_fast=vis_fast, vos=vos, vps=vps,
+                                   entity=entity, InferenceVideoEntity=entity.InferenceVideoEntity,
                                    InferenceVideoVPS=vps.InferenceVideoVPS,
                                    InferenceVideoVISFast=vis_fast.InferenceVideoVISFast,
                                    InferenceVideoVOS=vos.InferenceVideoVOS,

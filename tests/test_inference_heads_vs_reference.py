@@ -400,3 +400,238 @@ def test_vps_online_head():
         assert got["pred_masks"].shape == want["pred_masks"].shape == (V, 720, 1152)
         diff = (got["pred_masks"] != want["pred_masks"]).float().mean().item()
         assert diff <= 1e-4, diff
+
+
+def _entity_pair(T, Q, V, H, W, seed, dataset, **over):
+    """Reference entity head + its inputs, and the keyword arguments of the product head for the same setting."""
+    import inspect
+    import types
+    heads = ref_shim.load_inference_heads()
+    g = torch.Generator().manual_seed(seed)
+    frames = [(torch.rand(3, H, W, generator=g) * 255).round() for _ in range(V)]
+    inputs = [{"image": frames, "height": 75, "width": 120, "dataset_name": dataset, "task": "detection",
+               "video_len": V, "video_id": 7, "file_names": [f"{i}.jpg" for i in range(V)]}]
+    things = {c for c in range(1, 125) if c % 3 == 0}
+    meta = types.SimpleNamespace(thing_dataset_id_to_contiguous_id={c: i for i, c in enumerate(sorted(things))})
+    kw = dict(hidden_dim=256, num_queries=Q, overlap_threshold=0.3, overlap_threshold_entity=0.2,
+              stability_score_thresh=0.0, metadata=meta, size_divisibility=32, LSJ_aug_image_size=1024,
+              LSJ_aug_enable_test=False, sem_seg_postprocess_before_inference=False, pixel_mean=MEAN, pixel_std=STD,
+              num_frames=T, num_classes=133, data_name="ytvis_2021_val", prompt_as_queries=True, zero_shot_inference=False,
+              semantic_on=False, instance_on=True, panoptic_on=False, test_topk_per_image=8, tracker_type="minvis",
+              window_inference=False, is_multi_cls=True, apply_cls_thres=0.02, merge_on_cpu=False, box_nms_thresh=0.75,
+              num_max_inst_test=50, num_frames_window_test=T, clip_stride=1, output_dir="/tmp/univs_entity_test",
+              num_prev_frames_memory=1, video_unified_inference_entities="", temporal_consistency_threshold=0.05,
+              detect_newly_object_threshold=0.02, detect_newly_interval_frames=1, custom_videos_enable=False)
+    kw.update(over)
+    accepted = set(inspect.signature(heads.InferenceVideoEntity.__init__).parameters)
+    rhead = heads.InferenceVideoEntity(**{k: v for k, v in kw.items() if k in accepted})
+    xs = torch.stack([(f - rhead.pixel_mean) / rhead.pixel_std for f in frames])
+    xs = torch.nn.functional.pad(xs, (0, 96 - W, 0, 64 - H))
+    rimages = heads.ImageList(xs, [(H, W)] * V)
+    pkw = dict(num_queries=Q, num_frames=T, overlap_threshold=kw["overlap_threshold"],
+               overlap_threshold_entity=kw["overlap_threshold_entity"], stability_score_thresh=kw["stability_score_thresh"],
+               test_topk_per_image=kw["test_topk_per_image"], apply_cls_thres=kw["apply_cls_thres"],
+               box_nms_thresh=kw["box_nms_thresh"], num_frames_window_test=T, clip_stride=kw["clip_stride"],
+               num_prev_frames_memory=kw["num_prev_frames_memory"],
+               video_unified_inference_entities=kw["video_unified_inference_entities"],
+               temporal_consistency_threshold=kw["temporal_consistency_threshold"],
+               detect_newly_object_threshold=kw["detect_newly_object_threshold"],
+               detect_newly_interval_frames=kw["detect_newly_interval_frames"], thing_ids=things)
+    return heads, rhead, rimages, inputs, pkw
+
+
+def _ref_entity_run(heads, rhead, ref, inputs, rimages, dataset, sub_task):
+    import contextlib
+    import io
+    tg = [{"task": "detection", "dataset_name": dataset, "prompt_type": "visual", "video_len": inputs[0]["video_len"],
+           "sub_task": sub_task}]
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):     # the reference prints pool shapes per clip
+        rmodel = ref[0] if len(ref) == 1 else heads.RefModel(*ref)      # a scripted stand-in, or (backbone, pixdec, decoder)
+        want = rhead.inference_video(rmodel, inputs, rimages, tg)
+    return want, tg
+
+
+class _ScriptedScene:
+    """Stand-in for `model` with a scripted decoder: three objects in separate image regions (the third one enters at
+    frame 5), learnable queries that find them (with duplicates), prompt queries that follow the pooled entities.  Both
+    heads see identical clip outputs, so every pool update / result must agree exactly."""
+
+    def __init__(self, Q, class_start, classes=(3, 7, 11), enter=(0, 0, 5), C=256):
+        self.Q, self.class_start, self.classes, self.enter = Q, class_start, classes, enter
+        g = torch.Generator().manual_seed(1)
+        self.embds = torch.nn.functional.normalize(torch.randn(len(classes), C, generator=g), dim=-1) * 4
+        self.noise = torch.randn(64, C, generator=g) * 0.05
+        self.sem_seg_head = self._head
+        self.pixel_mean = torch.tensor(MEAN).view(-1, 1, 1)
+        self.pixel_std = torch.tensor(STD).view(-1, 1, 1)
+        self.device = torch.device("cpu")
+
+    def preprocess(self, frames):
+        x = (torch.stack(list(frames)).float() - self.pixel_mean) / self.pixel_std
+        H, W = x.shape[-2:]
+        return torch.nn.functional.pad(x, (0, (W + 31) // 32 * 32 - W, 0, (H + 31) // 32 * 32 - H)), (H, W)
+
+    def backbone(self, x):
+        return {"res2": x[:, :1, ::4, ::4]}
+
+    def _rect(self, k, f, h, w):
+        m = torch.full((h, w), -5.0)
+        if f >= self.enter[k]:
+            x0 = 1 + k * (w // 3) + (f % 3)
+            m[2 + (f % 2):h - 3, x0:x0 + w // 3 - 3] = 5.0
+        return m
+
+    def _head(self, features, targets=None):
+        tg = targets[0]
+        fi = [int(f) for f in tg["frame_indices"]]
+        n, (h, w) = len(fi), features["res2"].shape[-2:]
+        assert features["res2"].shape[0] == n
+        rows = []
+        for j in range(self.Q):                       # learnable queries: query j looks at object j % 3
+            rows.append((j % 3, 1.0 - 0.1 * (j // 3), j))
+        if "masks" in tg and tg["masks"].nelement():  # prompt queries: one per pooled entity, following "its" object
+            seen = tg["mask_logits"].gt(0).any(1).float()[:, ::4, ::4]                         # [N, h, w]
+            regions = torch.stack([torch.stack([self._rect(k, f, h, w) for f in range(12)]).gt(0).any(0).float()
+                                   for k in range(3)])                                          # [3, h, w]
+            owner = torch.einsum("nhw,khw->nk", seen[:, :h, :w], regions).argmax(1)
+            for e, k in enumerate(owner.tolist()):
+                rows.append((k, 1.0, 32 + e))
+        logits = torch.full((1, len(rows), 3938), -4.0)
+        masks = torch.empty((1, len(rows), n, h, w))
+        embds = torch.empty((1, len(rows), n, self.embds.shape[1]))
+        for r, (k, conf, tag) in enumerate(rows):
+            visible = any(f >= self.enter[k] for f in fi)
+            logits[0, r, self.class_start + self.classes[k]] = (3.0 * conf) if visible else -4.0
+            for t, f in enumerate(fi):
+                masks[0, r, t] = self._rect(k, f, h, w) * conf
+                embds[0, r, t] = self.embds[k] + self.noise[(tag + f) % 64]
+        return {"pred_logits": logits, "pred_masks": masks, "pred_embds": embds, "pred_reid_logits": [None],
+                "aux_outputs": []}
+
+
+@pytest.mark.parametrize("sub_task,dataset,stride", [("vis", "ytvis21", 1), ("entity_vis_coco", "ytvis21", 2)])
+def test_entity_head_vis_scripted(sub_task, dataset, stride):
+    """InferenceVideoEntity, instance sub-tasks, on a scripted scene: NMS of duplicate queries, pool updates from prompt
+    and learnable queries, an entity entering mid-video, windowed result output -> COCO-video json, exactly."""
+    from univs_b200.inference import InferenceVideoEntity
+    from univs_b200.modeling.decoder import COMBINED_DATASETS_CATEGORY_INFO as INFO
+    T, Q, V, H, W = 2, 6, 14, 60, 90
+    heads, rhead, rimages, inputs, pkw = _entity_pair(
+        T, Q, V, H, W, 21, dataset, clip_stride=stride, apply_cls_thres=0.05, detect_newly_object_threshold=0.05,
+        video_unified_inference_entities=sub_task if sub_task.startswith("entity") else "")
+    scene = _ScriptedScene(Q, INFO["coco" if sub_task == "entity_vis_coco" else dataset][1])
+    want, rtg = _ref_entity_run(heads, rhead, (scene,), inputs, rimages, dataset, sub_task)
+    assert rtg[0]["ids"].tolist() == [0, 1, 2] and rtg[0]["first_appear_frame_idxs"].tolist()[:2] == [0, 0]
+    assert rtg[0]["first_appear_frame_idxs"][2] >= 4               # the third object enters later
+    got = InferenceVideoEntity(reuse_features=False, **pkw).eval(scene, inputs)
+    key = lambda r: (r["category_id"], round(r["score"], 5))
+    want_s, got_s = sorted(want, key=key), sorted(got, key=key)
+    assert len(got_s) == len(want_s) >= 3
+    for rw, rg in zip(want_s, got_s):
+        assert rg["category_id"] == rw["category_id"] and rg["video_id"] == rw["video_id"] == 7
+        assert abs(rg["score"] - rw["score"]) <= 1e-6
+        assert rg["segmentations"] == rw["segmentations"]          # same RLE strings, frame by frame
+
+
+def test_entity_head_vps_vss_scripted():
+    """Panoptic (things tracked per entity, stuff merged per class) and semantic sub-tasks on the scripted scene."""
+    from univs_b200.inference import InferenceVideoEntity
+    from univs_b200.modeling.decoder import COMBINED_DATASETS_CATEGORY_INFO as INFO
+    T, Q, V, H, W = 2, 6, 14, 60, 90
+    heads, rhead, rimages, inputs, pkw = _entity_pair(T, Q, V, H, W, 22, "vipseg", apply_cls_thres=0.05,
+                                                      detect_newly_object_threshold=0.05)
+    scene = _ScriptedScene(Q, INFO["vipseg"][1], classes=(2, 7, 10))     # dataset ids 3 (thing), 8 (stuff), 11 (stuff)
+    want, rtg = _ref_entity_run(heads, rhead, (scene,), inputs, rimages, "vipseg", "vps")
+    assert len(want["segments_infos"]) == 3 and sorted(i["isthing"] for i in want["segments_infos"]) == [False, False, True]
+    got = InferenceVideoEntity(reuse_features=False, **pkw).eval(scene, inputs)
+    assert got["task"] == "vps" and got["image_size"] == want["image_size"] == (75, 120)
+    assert got["segments_infos"] == want["segments_infos"]
+    assert got["pred_masks"].dtype == torch.int32 and torch.equal(got["pred_masks"], want["pred_masks"])
+    assert got["pred_masks"].shape == (V, 75, 120) and got["pred_masks"].unique().numel() == 4
+
+    heads, rhead, rimages, inputs, pkw = _entity_pair(T, Q, 5, H, W, 23, "vspw")
+    scene = _ScriptedScene(Q, INFO["vspw"][1])
+    want, _ = _ref_entity_run(heads, rhead, (scene,), inputs, rimages, "vspw", "vss")
+    got = InferenceVideoEntity(reuse_features=False, **pkw).eval(scene, inputs)
+    assert got["task"] == "vss" and torch.equal(got["pred_masks"], want["pred_masks"])
+    assert got["pred_masks"].shape == (5, 75, 120) and got["pred_masks"].unique().tolist() == [3, 7]
+
+
+def test_entity_head_vis_full_model():
+    """The entity head over the real decoder + visual-prompt sampler (tiny model): entities of the first clip come back as
+    prompt queries in every later clip; product (feature reuse on / off) against the reference head."""
+    from univs_b200.inference import InferenceVideoEntity
+    from oracle import rle_ref
+    T, Q, V, H, W = 2, 12, 7, 60, 90
+    ref, model = _pair(T, Q, enc_layers=1, dec_layers=3)
+    heads, rhead, rimages, inputs, pkw = _entity_pair(T, Q, V, H, W, 21, "ytvis21", box_nms_thresh=1.01,
+                                                      apply_cls_thres=0.45, detect_newly_object_threshold=0.05)
+    torch.manual_seed(3)              # the visual-prompt sampler draws its points from the global generator
+    want, rtg = _ref_entity_run(heads, rhead, ref, inputs, rimages, "ytvis21", "vis")
+    assert len(want) >= 3 and rtg[0]["ids"].numel() >= 3 and "prompt_feats" in rtg[0]
+    for reuse in (True, False):
+        phead = InferenceVideoEntity(reuse_features=reuse, **pkw)
+        torch.manual_seed(3)
+        with oracle_ops():
+            got = phead.eval(model, inputs)
+        ptg = phead._last_targets[0]
+        assert ptg["ids"].tolist() == rtg[0]["ids"].tolist()
+        torch.testing.assert_close(ptg["logits"], rtg[0]["logits"], rtol=1e-3, atol=1e-5)
+        torch.testing.assert_close(ptg["occurrence"], rtg[0]["occurrence"])
+        key = lambda r: (r["category_id"], round(r["score"], 4))
+        want_s, got_s = sorted(want, key=key), sorted(got, key=key)
+        assert [r["category_id"] for r in got_s] == [r["category_id"] for r in want_s]
+        np.testing.assert_allclose([r["score"] for r in got_s], [r["score"] for r in want_s], rtol=1e-3, atol=1e-6)
+        flips = total = 0
+        for rw, rg in zip(want_s, got_s):
+            assert len(rg["segmentations"]) == V
+            for sw, sg in zip(rw["segmentations"], rg["segmentations"]):
+                flips += int((rle_ref.decode(sw) != rle_ref.decode(sg)).sum())
+                total += 75 * 120
+        assert flips <= 1e-4 * total, (flips, total)
+
+
+def test_forward_inference_dispatch():
+    """UniVS_Prompt.forward with task heads attached routes whole videos like univs_prompt.py:416-452."""
+    from univs_b200.modeling.decoder import COMBINED_DATASETS_CATEGORY_INFO as INFO
+    T, Q = 2, 6
+    _, model = _pair(T, Q, enc_layers=1, dec_layers=2)
+    kw = dict(num_queries=Q, num_frames=T, num_frames_window_test=T, reuse_features=False)
+    g = torch.Generator().manual_seed(2)
+    frames = [(torch.rand(3, 60, 90, generator=g) * 255).round() for _ in range(3)]
+    video = {"image": frames, "height": 60, "width": 90, "task": "detection", "video_len": 3, "video_id": 1}
+    calls = []
+
+    class Spy:
+        def __init__(self, name):
+            self.name = name
+
+        def eval(self, m, inputs):
+            calls.append(self.name)
+            return self.name
+
+    with pytest.raises(RuntimeError):
+        model.forward_inference([dict(video, dataset_name="ytvis21")])
+    model.attach_task_heads(thing_ids={3}, **kw)
+    assert model.task_heads["entity"].thing_ids == {3} and model.task_heads["vps"].num_frames == T
+    for k in ("vis_fast", "vos", "vps", "entity"):
+        model.task_heads[k] = Spy(k)
+    assert model([dict(video, dataset_name="ytvis21")]) == "vis_fast"
+    assert model([dict(video, dataset_name="vipseg_val")]) == "vps"
+    assert model([dict(video, dataset_name="davis17", task="sot")]) == "vos"
+    assert model([dict(video, dataset_name="refytvos", task="grounding")]) == "vos"
+    with pytest.raises(ValueError):
+        model([dict(video, dataset_name="bdd_track")])
+    with pytest.raises(NotImplementedError):
+        model([dict(video, dataset_name="coco_panoptic")])
+    model.task_heads["unified"] = True
+    assert model([dict(video, dataset_name="ovis")]) == "entity"
+    assert model([dict(video, dataset_name="vspw")]) == "entity"
+    model.task_heads["unified"], model.task_heads["tracker_type"] = False, "mdqe"
+    with pytest.raises(NotImplementedError):
+        model([dict(video, dataset_name="ytvis21")])
+    # and one real head end to end through forward()
+    model.attach_task_heads(**kw)
+    with oracle_ops():
+        out = model([dict(video, dataset_name="ytvis21")])
+    assert out["image_size"] == (60, 90) and len(out["pred_scores"]) == len(out["pred_labels"])

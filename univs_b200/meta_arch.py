@@ -5,8 +5,9 @@ Registered under the reference's name so `MODEL.META_ARCHITECTURE: UniVS_Prompt`
 non-persistent `pixel_mean` / `pixel_std` buffers (:169-170).  `forward(batched_inputs)` keeps the input contract
 (list of one dict with "image": list of T [3,H,W] tensors, "height", "width", "task", "dataset_name", ...) and runs
 ONE clip through normalise -> pad to a multiple of 32 (ImageList.from_tensors semantics) -> backbone -> sem_seg_head.
-The sliding-window task heads, trackers and result writers of univs/inference/* are callers of this path and out of
-scope this round; `forward` therefore returns the per-clip decoder output dict.
+Without task heads `forward` returns the per-clip decoder output dict.  With task heads (`attach_task_heads`, or a cfg
+that carries MODEL.UniVS.TEST / MODEL.BoxVIS.TEST) `forward` = `forward_inference`: the reference's dispatch over whole
+videos (univs_prompt.py:416-452) to the sliding-window heads of `univs_b200/inference/`.
 
 Frame sharding (new capability): with a process group of n ranks, rank r runs backbone + pixel decoder
 on frames {f : f mod n == r}; one all-gather reassembles the three multi-scale maps and mask_features; the decoder
@@ -48,6 +49,8 @@ class UniVS_Prompt(nn.Module):
         # group can run under the tensor-core GEMMs of another (frames are independent up to the decoder); opt-in
         self.frame_streams = switches.get("FRAME_STREAMS") if frame_streams is None else int(frame_streams)
         self._streams = []
+        self._cfg = cfg
+        self.task_heads = None                 # see attach_task_heads
         self.eval()
 
     @property
@@ -177,9 +180,63 @@ class UniVS_Prompt(nn.Module):
         # mask_features_bfe_conv is not read by the inference decoder (only viewed, ..._univs.py:313): as in the sharded path
         return self.sem_seg_head.predictor(multi_scale, mask_features, mask_features, None, targets)
 
+    # ---- whole-video inference: the reference's dispatch to the task heads (univs_prompt.py:416-452)
+    def attach_task_heads(self, cfg=None, *, thing_ids=(), metadata=None, video_unified_inference_enable=None,
+                          tracker_type=None, custom_videos_enable=None, custom_videos_text=None, **head_kwargs):
+        """Builds the sliding-window heads this build has (VIS with the MinVIS tracker, VOS / RefVOS, VPS, unified entity
+        head) from `cfg` (default: the cfg the model was built from) and makes `forward` dispatch to them.
+        `thing_ids` / `metadata` stand in for detectron2's MetadataCatalog entry of the test dataset; `head_kwargs` are
+        passed to every head that accepts them (e.g. reuse_features=False)."""
+        import inspect
+        from .inference import InferenceVideoEntity, InferenceVideoVISFast, InferenceVideoVOS, InferenceVideoVPS
+        cfg = self._cfg if cfg is None else cfg
+        uv = cfg.MODEL.UniVS.TEST if cfg is not None else {}
+        bv = cfg.MODEL.BoxVIS.TEST if cfg is not None else {}
+        pick = lambda given, node, key, default: given if given is not None else (node.get(key, default) if node else default)
+
+        def make(cls, **extra):
+            accepted = set(inspect.signature(cls.__init__).parameters)
+            return cls(cfg, **{k: v for k, v in {**head_kwargs, **extra}.items() if k in accepted})
+
+        self.task_heads = {
+            "vis_fast": make(InferenceVideoVISFast),
+            "vos": make(InferenceVideoVOS, metadata=metadata),
+            "vps": make(InferenceVideoVPS, thing_ids=thing_ids),
+            "entity": make(InferenceVideoEntity, thing_ids=thing_ids),
+            "unified": bool(pick(video_unified_inference_enable, uv, "VIDEO_UNIFIED_INFERENCE_ENABLE", False)),
+            "custom_videos": bool(pick(custom_videos_enable, uv, "CUSTOM_VIDEOS_ENABLE", False)),
+            "custom_videos_text": list(pick(custom_videos_text, uv, "CUSTOM_VIDEOS_TEXT", [])),
+            "tracker_type": pick(tracker_type, bv, "TRACKER_TYPE", "minvis"),
+        }
+        return self
+
+    @torch.no_grad()
+    def forward_inference(self, batched_inputs):
+        h = self.task_heads
+        if h is None:
+            raise RuntimeError("forward_inference needs task heads: call attach_task_heads() first")
+        name = batched_inputs[0]["dataset_name"]
+        if name.startswith("coco") or name.startswith("ade20k"):
+            raise NotImplementedError("the image heads (inference_image_generic_seg.py) are not part of this build")
+        if batched_inputs[0].get("task") in ("grounding", "sot") or len(h["custom_videos_text"]):
+            return h["vos"].eval(self, batched_inputs)                  # prompt-specified tasks
+        if h["unified"] or h["custom_videos"]:                          # category-specified tasks, unified entity inference
+            if name.startswith(("ytvis", "ovis", "vipseg", "vspw")) or h["custom_videos"]:
+                return h["entity"].eval(self, batched_inputs)
+            raise ValueError(f"Not support to eval the dataset {name} yet")
+        if name.startswith(("ytvis", "ovis")):
+            if h["tracker_type"] == "mdqe":
+                raise NotImplementedError("the clip-level MDQE tracker head (inference_video_vis.py) is not part of this build")
+            return h["vis_fast"].eval(self, batched_inputs)
+        if name.startswith(("vipseg", "vpsw")):
+            return h["vps"].eval(self, batched_inputs)
+        raise ValueError(f"Not support to eval the dataset {name} yet")
+
     def forward(self, batched_inputs):
         if self.training:
             raise NotImplementedError("training is out of scope for the B200 hot-path build")
+        if self.task_heads is not None:
+            return self.forward_inference(batched_inputs)
         assert len(batched_inputs) == 1, "inference processes one video at a time (univs_prompt.py:421)"
         inp = batched_inputs[0]
         frames = inp["image"]
