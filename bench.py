@@ -95,7 +95,7 @@ def run_cpu_reference(args, workload, steps, warmup, as_line):
     cfg = make_cfg(variant, Q, 1, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
     model = build_model(cfg)
     frames = torch.rand(1, 3, H, W, generator=g) * 255
-    times = []
+    times, budget_s, t_begin = [], float(os.environ.get("UNIVS_CPU_BUDGET_S", "240")), time.perf_counter()
     with oracle_ops():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
@@ -104,9 +104,13 @@ def run_cpu_reference(args, workload, steps, warmup, as_line):
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-            if i == 0 and dt * (warmup + steps) > 900:
-                raise SystemExit(f"cpu reference too slow for the requested step count ({dt:.1f}s/step)")
+            # the whole run has to end within a few minutes on any host: stop early once one timed step exists
+            if times and time.perf_counter() - t_begin + dt > budget_s:
+                break
+            if not times and time.perf_counter() - t_begin + 2 * dt > budget_s:
+                warmup = i + 1                       # slow host: the next step is the (first) timed one
     mean = sum(times) / len(times)
+    steps = len(times)
     sample = f"1 clip of T=1 frame ({variant} {H}x{W}, Q={Q}) per step; full workload has T={T} frames/clip"
     base = {"value": 1.0 / mean, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
     if not as_line:
