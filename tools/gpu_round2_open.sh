@@ -37,4 +37,8 @@ UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE
 run bench_video 900 python bench.py --steps 2 --video-frames 12
 # 3. end-to-end parity of the opt-in paths at the north-star geometry (T=2): same tool and thresholds as round 1
 PARITY_MODES=fp16x3 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 UNIVS_POOLED_MASKS=1 run parity_at_scale 1200 python tools/parity_at_scale.py
+# 4. the prompt configurations of BASELINE.json at full geometry (default path): C3 sot memory over 3 clips, C4 grounding, C5 1080p
+PARITY_CONFIG=c3 run parity_c3 900 python tools/parity_configs.py
+PARITY_CONFIG=c4 run parity_c4 900 python tools/parity_configs.py
+PARITY_CONFIG=c5 run parity_c5 900 python tools/parity_configs.py
 cat "$out/summary.txt"
