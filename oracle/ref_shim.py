@@ -376,7 +376,11 @@ def load_inference_heads():
     mu = _mod("pycocotools.mask", encode=_encode)
     _mod("pycocotools", mask=mu)
     _mod("detectron2.data", MetadataCatalog=types.SimpleNamespace(get=lambda name: types.SimpleNamespace()))
-    _mod("detectron2.modeling.postprocessing", sem_seg_postprocess=None)
+    def _sem_seg_postprocess(result, img_size, output_height, output_width):
+        """detectron2/modeling/postprocessing.py: crop to the unpadded size, bilinear resize to the output size"""
+        result = result[:, : img_size[0], : img_size[1]].expand(1, -1, -1, -1)
+        return F.interpolate(result, size=(output_height, output_width), mode="bilinear", align_corners=False)[0]
+    _mod("detectron2.modeling.postprocessing", sem_seg_postprocess=_sem_seg_postprocess)
     _mod("detectron2.structures", Boxes=_TensorBox, ImageList=_ImageList, Instances=_Instances, BitMasks=_TensorBox)
     _mod("detectron2.utils.memory", retry_if_cuda_oom=lambda f: f)
     _pkg("mask2former.utils", f"{R}/mask2former/utils")
@@ -392,15 +396,17 @@ def load_inference_heads():
     ucomm = imp("univs.utils.comm")
     vis_fast = imp("univs.inference.inference_video_vis_fast")
     _mod("matplotlib"); _mod("matplotlib.pyplot")
-    _mod("univs.inference.visualization", visualization_query_embds=lambda **kw: None)
+    _mod("univs.inference.visualization", visualization_query_embds=lambda **kw: None, display_instance_masks=None)
     _mod("univs.utils.visualizer", VisualizerFrame=object)
     vos = imp("univs.inference.inference_video_vos")
     vps = imp("univs.inference.inference_video_vps")
     _mod("univs.data", datasets=None)
     _mod("univs.data.datasets", _get_vspw_vss_metadata=None, _get_vipseg_panoptic_metadata_val=None)
     entity = imp("univs.inference.inference_video_entity")
+    image = imp("univs.inference.inference_image_generic_seg")
     _HEADS = types.SimpleNamespace(comm=comm, utils_comm=ucomm, vis_fast=vis_fast, vos=vos, vps=vps,
                                    entity=entity, InferenceVideoEntity=entity.InferenceVideoEntity,
+                                   image=image, InferenceImageGenericSeg=image.InferenceImageGenericSegmentation,
                                    InferenceVideoVPS=vps.InferenceVideoVPS,
                                    InferenceVideoVISFast=vis_fast.InferenceVideoVISFast,
                                    InferenceVideoVOS=vos.InferenceVideoVOS,

@@ -614,7 +614,7 @@ def test_forward_inference_dispatch():
         model.forward_inference([dict(video, dataset_name="ytvis21")])
     model.attach_task_heads(thing_ids={3}, **kw)
     assert model.task_heads["entity"].thing_ids == {3} and model.task_heads["vps"].num_frames == T
-    for k in ("vis_fast", "vos", "vps", "entity"):
+    for k in ("vis_fast", "vos", "vps", "entity", "image"):
         model.task_heads[k] = Spy(k)
     assert model([dict(video, dataset_name="ytvis21")]) == "vis_fast"
     assert model([dict(video, dataset_name="vipseg_val")]) == "vps"
@@ -622,8 +622,8 @@ def test_forward_inference_dispatch():
     assert model([dict(video, dataset_name="refytvos", task="grounding")]) == "vos"
     with pytest.raises(ValueError):
         model([dict(video, dataset_name="bdd_track")])
-    with pytest.raises(NotImplementedError):
-        model([dict(video, dataset_name="coco_panoptic")])
+    assert model([dict(video, dataset_name="coco_panoptic")]) == "image"
+    assert model([dict(video, dataset_name="ade20k_sem_seg")]) == "image"
     model.task_heads["unified"] = True
     assert model([dict(video, dataset_name="ovis")]) == "entity"
     assert model([dict(video, dataset_name="vspw")]) == "entity"
@@ -635,3 +635,98 @@ def test_forward_inference_dispatch():
     with oracle_ops():
         out = model([dict(video, dataset_name="ytvis21")])
     assert out["image_size"] == (60, 90) and len(out["pred_scores"]) == len(out["pred_labels"])
+    # demo form (demo/predictor.py:117): no dataset_name / task -> the keys run_on_video reads (:49-52)
+    with oracle_ops():
+        demo = model([{"image": frames, "height": 60, "width": 90}])
+    assert set(demo) >= {"image_size", "pred_scores", "pred_labels", "pred_masks"}
+    assert len(demo["pred_masks"]) == len(out["pred_masks"]) and demo["pred_scores"] == out["pred_scores"]
+
+
+class _ScriptedImage(_ScriptedScene):
+    """One image: 220 learnable + K category-prompt queries with blob masks of varied extent and noisy class scores."""
+
+    def __init__(self, Q, class_start, K):
+        super().__init__(Q, class_start)
+        self.K = K
+
+    def _head(self, features, targets=None):
+        h, w = features["res2"].shape[-2:]
+        g = torch.Generator().manual_seed(4)
+        n = self.Q + self.K
+        logits = torch.full((1, n, 3938), -6.0)
+        logits[0, :, self.class_start:self.class_start + self.K] = torch.randn(n, self.K, generator=g) * 1.5 - 3.0
+        masks = torch.full((1, n, 1, h, w), -4.0)
+        for r in range(n):
+            y0, x0 = int(torch.randint(0, h - 4, (1,), generator=g)), int(torch.randint(0, w - 6, (1,), generator=g))
+            hh, ww = int(torch.randint(2, 7, (1,), generator=g)), int(torch.randint(3, 10, (1,), generator=g))
+            masks[0, r, 0, y0:y0 + hh, x0:x0 + ww] = 3.0 + torch.rand(1, generator=g).item()
+            logits[0, r, self.class_start + r % self.K] += 4.0 * torch.rand(1, generator=g).item()
+        masks += torch.randn(masks.shape, generator=g) * 0.3
+        for r in range(0, n, 7):                     # duplicates of the previous query: class-wise NMS must drop them
+            if r:
+                masks[0, r] = masks[0, r - 1] + 0.01
+                logits[0, r] = logits[0, r - 1] - 0.05
+        return {"pred_logits": logits, "pred_masks": masks, "pred_embds": torch.zeros(1, n, 1, 256),
+                "pred_reid_logits": [None], "aux_outputs": []}
+
+
+@pytest.mark.parametrize("before", [False, True])
+def test_image_generic_seg_head_scripted(before):
+    """InferenceImageGenericSeg (inference_image_generic_seg.py): semantic / panoptic / instance post-processing and the
+    class-wise box NMS against the reference head (torchvision batched_nms) on scripted decoder outputs."""
+    import inspect
+    import types
+    from univs_b200.inference import InferenceImageGenericSeg
+    from univs_b200.modeling.decoder import COMBINED_DATASETS_CATEGORY_INFO as INFO
+    heads = ref_shim.load_inference_heads()
+    Q, H, W = 220, 60, 90
+    K, start = INFO["coco_panoptic"]
+    things = list(range(80))                                               # contiguous ids of the thing classes
+    meta = types.SimpleNamespace(thing_dataset_id_to_contiguous_id={i + 1: i for i in things})
+    kw = dict(hidden_dim=256, num_queries=Q, object_mask_threshold=0.02, overlap_threshold=0.5, stability_score_thresh=0.0,
+              metadata=meta, size_divisibility=32, LSJ_aug_image_size=1024, LSJ_aug_enable_test=False,
+              sem_seg_postprocess_before_inference=before, pixel_mean=MEAN, pixel_std=STD, num_frames=1,
+              data_name="coco_2017_val_panoptic", prompt_as_queries=True, zero_shot_inference=False, semantic_on=True,
+              instance_on=True, panoptic_on=True, disable_semantic_queries=False, test_topk_per_image=20,
+              tracker_type="minvis", window_inference=False, is_multi_cls=True, apply_cls_thres=0.05, merge_on_cpu=False,
+              num_max_inst_test=50, num_frames_window_test=1, clip_stride=1)
+    accepted = set(inspect.signature(heads.InferenceImageGenericSeg.__init__).parameters)
+    rhead = heads.InferenceImageGenericSeg(**{k: v for k, v in kw.items() if k in accepted})
+    scene = _ScriptedImage(Q, start, K)
+    g = torch.Generator().manual_seed(8)
+    image = (torch.rand(3, H, W, generator=g) * 255).round()
+    inputs = [{"image": [image], "height": 75, "width": 120, "dataset_name": "coco_panoptic", "task": "detection"}]
+    x, image_size = scene.preprocess([image])
+    with torch.no_grad():
+        want = rhead.inference_image(scene, inputs, heads.ImageList(x, [image_size]),
+                                     [{"task": "detection", "dataset_name": "coco_panoptic", "frame_indices": torch.arange(1)}])[0]
+    phead = InferenceImageGenericSeg(num_queries=Q, object_mask_threshold=0.02, overlap_threshold=0.5, semantic_on=True,
+                                     instance_on=True, panoptic_on=True, test_topk_per_image=20,
+                                     sem_seg_postprocess_before_inference=before, thing_contiguous_ids=things)
+    got = phead.eval(scene, inputs)[0]
+    torch.testing.assert_close(got["sem_seg"], want["sem_seg"], rtol=1e-5, atol=1e-6)
+    assert got["sem_seg"].shape == (K, 75, 120)
+    assert torch.equal(got["panoptic_seg"][0], want["panoptic_seg"][0]) and got["panoptic_seg"][1] == want["panoptic_seg"][1]
+    assert got["panoptic_seg"][0].shape == (75, 120) and len(got["panoptic_seg"][1]) >= 3
+    wi, gi = want["instances"], got["instances"]
+    order_w, order_g = wi.scores.sort(descending=True)[1], gi["scores"].sort(descending=True)[1]
+    assert len(order_g) == len(order_w) == 20 and gi["image_size"] == wi.image_size == (75, 120)
+    torch.testing.assert_close(gi["scores"][order_g], wi.scores[order_w])
+    assert torch.equal(gi["pred_classes"][order_g], wi.pred_classes[order_w])
+    assert torch.equal(gi["pred_masks"][order_g], wi.pred_masks[order_w])
+    assert torch.equal(gi["pred_boxes"][order_g].float(), wi.pred_boxes.tensor[order_w].float())
+
+
+def test_classwise_box_nms_matches_torchvision():
+    from torchvision.ops.boxes import batched_nms
+    from univs_b200.inference import classwise_box_nms
+    g = torch.Generator().manual_seed(0)
+    for n in (0, 1, 7, 150):
+        xy = torch.randint(0, 40, (n, 2), generator=g).float()
+        wh = torch.randint(0, 25, (n, 2), generator=g).float()               # zero-area boxes included
+        boxes = torch.cat([xy, xy + wh], 1)
+        if n > 4:
+            boxes[3] = boxes[2]                                               # exact duplicate
+        scores, labels = torch.rand(n, generator=g), torch.randint(0, 4, (n,), generator=g)
+        for thr in (0.3, 0.85):
+            assert classwise_box_nms(boxes, scores, labels, thr).tolist() == batched_nms(boxes, scores, labels, thr).tolist()

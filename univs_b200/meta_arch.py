@@ -181,14 +181,16 @@ class UniVS_Prompt(nn.Module):
         return self.sem_seg_head.predictor(multi_scale, mask_features, mask_features, None, targets)
 
     # ---- whole-video inference: the reference's dispatch to the task heads (univs_prompt.py:416-452)
-    def attach_task_heads(self, cfg=None, *, thing_ids=(), metadata=None, video_unified_inference_enable=None,
+    def attach_task_heads(self, cfg=None, *, thing_ids=(), thing_contiguous_ids=(), metadata=None,
+                          video_unified_inference_enable=None,
                           tracker_type=None, custom_videos_enable=None, custom_videos_text=None, **head_kwargs):
-        """Builds the sliding-window heads this build has (VIS with the MinVIS tracker, VOS / RefVOS, VPS, unified entity
+        """Builds the task heads this build has (VIS with the MinVIS tracker, VOS / RefVOS, VPS, unified entity head, image
         head) from `cfg` (default: the cfg the model was built from) and makes `forward` dispatch to them.
-        `thing_ids` / `metadata` stand in for detectron2's MetadataCatalog entry of the test dataset; `head_kwargs` are
+        `thing_ids` (1-based dataset ids) / `thing_contiguous_ids` (0-based class indices) / `metadata` stand in for detectron2's MetadataCatalog entry of the test dataset; `head_kwargs` are
         passed to every head that accepts them (e.g. reuse_features=False)."""
         import inspect
-        from .inference import InferenceVideoEntity, InferenceVideoVISFast, InferenceVideoVOS, InferenceVideoVPS
+        from .inference import (InferenceImageGenericSeg, InferenceVideoEntity, InferenceVideoVISFast, InferenceVideoVOS,
+                                InferenceVideoVPS)
         cfg = self._cfg if cfg is None else cfg
         uv = cfg.MODEL.UniVS.TEST if cfg is not None else {}
         bv = cfg.MODEL.BoxVIS.TEST if cfg is not None else {}
@@ -203,6 +205,7 @@ class UniVS_Prompt(nn.Module):
             "vos": make(InferenceVideoVOS, metadata=metadata),
             "vps": make(InferenceVideoVPS, thing_ids=thing_ids),
             "entity": make(InferenceVideoEntity, thing_ids=thing_ids),
+            "image": make(InferenceImageGenericSeg, thing_contiguous_ids=thing_contiguous_ids),
             "unified": bool(pick(video_unified_inference_enable, uv, "VIDEO_UNIFIED_INFERENCE_ENABLE", False)),
             "custom_videos": bool(pick(custom_videos_enable, uv, "CUSTOM_VIDEOS_ENABLE", False)),
             "custom_videos_text": list(pick(custom_videos_text, uv, "CUSTOM_VIDEOS_TEXT", [])),
@@ -215,9 +218,15 @@ class UniVS_Prompt(nn.Module):
         h = self.task_heads
         if h is None:
             raise RuntimeError("forward_inference needs task heads: call attach_task_heads() first")
+        if "dataset_name" not in batched_inputs[0]:
+            # demo form (demo/predictor.py:106-118: {"image", "height", "width"} only; the reference's dispatch raises a
+            # KeyError on it): category-specified detection over the default video vocabulary
+            batched_inputs = [dict(batched_inputs[0], dataset_name=h.get("demo_dataset", "ytvis21"),
+                                   task=batched_inputs[0].get("task", "detection"))]
+            batched_inputs[0].setdefault("video_len", len(batched_inputs[0]["image"]))
         name = batched_inputs[0]["dataset_name"]
         if name.startswith("coco") or name.startswith("ade20k"):
-            raise NotImplementedError("the image heads (inference_image_generic_seg.py) are not part of this build")
+            return h["image"].eval(self, batched_inputs)                # image vocabularies
         if batched_inputs[0].get("task") in ("grounding", "sot") or len(h["custom_videos_text"]):
             return h["vos"].eval(self, batched_inputs)                  # prompt-specified tasks
         if h["unified"] or h["custom_videos"]:                          # category-specified tasks, unified entity inference
