@@ -1,4 +1,4 @@
-"""Parity + timing of the tcgen05 cross-attention kernel (run on the B200 box):  python tools/mha_tc_check.py [--time]
+"""Parity + timing of the tcgen05 cross-attention kernel (run on the B200 box):  python tests/tools/mha_tc_check.py [--time]
 Parity against the CPU oracle and the validated mma.sync kernel for both V staging variants (flags 0: MN-major B
 descriptor, flags 1: transposed V, K-major); --time adds CUDA-event timings at the three north-star memory sizes
 (T=5 frames, Q=200, 8 heads) next to the mma.sync kernel, with the achieved K/V streaming bandwidth."""
@@ -8,7 +8,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ops_ref          # noqa: E402  (diagnostic tool: the oracle is the checker)
 from univs_b200 import ops          # noqa: E402
 

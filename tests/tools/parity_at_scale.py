@@ -7,7 +7,7 @@ far more than any arithmetic error.  So two numbers are reported per policy:
   free-running  : the CUDA path on its own decisions (max-norm error, relative L2, #queries beyond 1e-3, #bits flipped)
   same-decisions: the CUDA path replaying the oracle's attention-mask bits (isolates the arithmetic error)."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle.cpu_backend import oracle_ops
 from univs_b200.build import build_model, make_cfg

@@ -9,17 +9,17 @@
   c5  Swin-L, 1080x1920, Q=200, detection, T frames (default 1; BASELINE: 8 frames sharded over 8 GPUs -- the sharded
       run itself is `torchrun ... bench.py`; here the single-GPU result at that geometry is checked)
 
-  PARITY_CONFIG=c3 python tools/parity_configs.py        -> gpurun_out/parity_config_c3.json
+  PARITY_CONFIG=c3 python tests/tools/parity_configs.py        -> gpurun_out/parity_config_c3.json
 
 Per clip: max|a-b|/max|b| of pred_masks / pred_logits / pred_embds (tolerance 1e-3, BASELINE.json north_star), and for
-c3 the prompt memory written into `targets` (prompt_feats, prompt_attn_masks).  Same caveat as tools/parity_at_scale.py:
+c3 the prompt memory written into `targets` (prompt_feats, prompt_attn_masks).  Same caveat as tests/tools/parity_at_scale.py:
 an attention-mask bit is the sign of a logit, so the count of queries beyond 1e-3 is reported next to the maximum."""
 import json
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 from oracle.cpu_backend import oracle_ops

@@ -2,7 +2,7 @@
 (Swin-L, 720x1280, Q=200, bench initialisation, one frame): product host model with the CPU oracle operators, default path
 vs pooled path; counts the attention-mask bits that differ in every intermediate head and compares the outputs."""
 import json, os, sys, time, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.cpu_backend import oracle_ops
 from univs_b200.build import build_model, make_cfg
 torch.set_num_threads(8)

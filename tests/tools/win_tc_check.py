@@ -1,5 +1,5 @@
 """Staged diagnostics + timing of the tcgen05 window-attention kernel (run on the B200 box):
-  python tools/win_tc_check.py [--time]
+  python tests/tools/win_tc_check.py [--time]
 Stage 1 compares the biased, masked scores (QK^T path: loader, swizzled operand tiles, K-major descriptors),
 stage 2 the attention output (softmax, P tile, PV path with the MN-major V descriptor), stage 3 the GEMM-operand output,
 each against the CPU oracle and the validated mma.sync kernel; --time adds CUDA-event timings at the four
@@ -10,7 +10,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ops_ref          # noqa: E402  (diagnostic tool: the oracle is the checker)
 from univs_b200 import ops          # noqa: E402
 

@@ -18,9 +18,9 @@ run() {  # name, seconds, command...
 run default_gpu_tests 1500 python -m pytest tests -m gpu -q -x
 # 1. opt-in kernels, one family per step so that a trapped launch (sticky CUDA error) only spoils its own process
 UNIVS_GPU_WINTC=1 run wintc_tests 600 python -m pytest tests/test_window_attn_tc.py -m gpu -q
-run wintc_check 600 python tools/win_tc_check.py --time
+run wintc_check 600 python tests/tools/win_tc_check.py --time
 UNIVS_GPU_MHATC=1 run mhatc_tests 600 python -m pytest tests/test_mha_tc.py -m gpu -q
-run mhatc_check 600 python tools/mha_tc_check.py --time
+run mhatc_check 600 python tests/tools/mha_tc_check.py --time
 UNIVS_GPU_ROWWISE_V2=1 run rowwise_v2_tests 600 python -m pytest tests/test_rowwise_v2.py -m gpu -q
 UNIVS_GPU_GLUE=1 run glue_tests 900 python -m pytest tests/test_fused_glue.py -m gpu -q
 UNIVS_GPU_HEADS=1 run heads_tests 900 python -m pytest tests/test_heads_golden.py -m gpu -q
@@ -36,9 +36,9 @@ UNIVS_MHA_TC=1 run bench_mhatc 900 python bench.py --steps 10 --warmup 3 --no-cp
 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 UNIVS_POOLED_MASKS=1 run bench_all 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run bench_video 900 python bench.py --steps 2 --video-frames 12
 # 3. end-to-end parity of the opt-in paths at the north-star geometry (T=2): same tool and thresholds as round 1
-PARITY_MODES=fp16x3 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 UNIVS_POOLED_MASKS=1 run parity_at_scale 1200 python tools/parity_at_scale.py
+PARITY_MODES=fp16x3 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 UNIVS_POOLED_MASKS=1 run parity_at_scale 1200 python tests/tools/parity_at_scale.py
 # 4. the prompt configurations of BASELINE.json at full geometry (default path): C3 sot memory over 3 clips, C4 grounding, C5 1080p
-PARITY_CONFIG=c3 run parity_c3 900 python tools/parity_configs.py
-PARITY_CONFIG=c4 run parity_c4 900 python tools/parity_configs.py
-PARITY_CONFIG=c5 run parity_c5 900 python tools/parity_configs.py
+PARITY_CONFIG=c3 run parity_c3 900 python tests/tools/parity_configs.py
+PARITY_CONFIG=c4 run parity_c4 900 python tests/tools/parity_configs.py
+PARITY_CONFIG=c5 run parity_c5 900 python tests/tools/parity_configs.py
 cat "$out/summary.txt"

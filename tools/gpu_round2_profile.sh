@@ -20,8 +20,8 @@ cap() {  # name, kernel regex, command...
     grep -E 'Kernel Name|gpu__time_duration.sum|dram__bytes_(read|write)\.sum|gpu__dram_throughput|sm__pipe_tensor.*cycles_active|sm__throughput|l1tex__t_sector_hit_rate|lts__t_sector_hit_rate|launch__registers_per_thread|sm__warps_active' \
     > "$out/$name.summary.csv"
 }
-cap wintc 'swin_window_attn_tc12' python tools/win_tc_check.py --time
-cap winmma 'swin_window_attn_f16x3' python tools/win_tc_check.py --time
+cap wintc 'swin_window_attn_tc12' python tests/tools/win_tc_check.py --time
+cap winmma 'swin_window_attn_f16x3' python tests/tools/win_tc_check.py --time
 cap einsum 'mask_einsum_tc' python tools/einsum_tc_check.py
 cap mhatc 'mha_tc_kernel' python bench.py --ncu-step --no-cpu-baseline
 cap msda 'msda_encoder' python bench.py --ncu-step --no-cpu-baseline

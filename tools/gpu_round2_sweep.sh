@@ -6,7 +6,7 @@ out=gpurun_out/r2_sweep
 mkdir -p "$out"
 timeout 600 python tools/msda_tile_sweep.py > "$out/msda_tiles.log" 2>&1
 for s in 1 2 3 4 7; do
-  UNIVS_MHA_TC_SPLITS=$s timeout 300 python tools/mha_tc_check.py --time > "$out/mha_tc_splits_$s.log" 2>&1
+  UNIVS_MHA_TC_SPLITS=$s timeout 300 python tests/tools/mha_tc_check.py --time > "$out/mha_tc_splits_$s.log" 2>&1
 done
 for g in 2 3 5; do
   UNIVS_FRAME_STREAMS=$g timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$out/bench_streams_$g.log" 2>&1

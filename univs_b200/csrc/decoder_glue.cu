@@ -10,7 +10,7 @@
 // full-resolution logits (235 MB per head at the north-star size); only the last head, whose logits are the output, runs
 // at full resolution.  Same mathematics; the fp32 rounding differs (the mean is taken before instead of after the dot
 // product), so a logit within rounding distance of zero may flip its mask bit -- the class of deviation DESIGN.md 2
-// quantifies with tools/parity_at_scale.py.
+// quantifies with tests/tools/parity_at_scale.py.
 //   mask_feature_pool : F [T,H,W,C] channel-last fp32 -> [T, h*w, C] pooled (plain fp32 or einsum operand format)
 //   mask_bits_direct  : logits [Q,T,S] at the memory resolution -> bits [T,Q,ceil(S/32)] (bit set = blocked) + row flag
 #include "rowwise.cuh"

@@ -222,7 +222,7 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         self.enabled_prev_visual_prompts_for_grounding = enabled_prev_visual_prompts_for_grounding
         self.semantic_extraction_enable = semantic_extraction_enable
         self.return_aux_outputs = False
-        # diagnostic hook (tools/parity_at_scale.py): fn(call_index, bits, row_open) -> (bits, row_open); lets a parity
+        # diagnostic hook (tests/tools/parity_at_scale.py): fn(call_index, bits, row_open) -> (bits, row_open); lets a parity
         # run record the attention-mask decisions or replay another run's decisions.  None in normal operation.
         self.attn_mask_hook = None
         # intermediate heads from pooled mask features (csrc/decoder_glue.cu): resize(E.F) = E.resize(F); opt-in
