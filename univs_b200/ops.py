@@ -317,7 +317,7 @@ _ws_cache = {}
 
 
 def _workspace(nbytes, device):
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    key = (device.index, _stream())
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
