@@ -404,9 +404,11 @@ def load_inference_heads():
     _mod("univs.data.datasets", _get_vspw_vss_metadata=None, _get_vipseg_panoptic_metadata_val=None)
     entity = imp("univs.inference.inference_video_entity")
     image = imp("univs.inference.inference_image_generic_seg")
+    semx = imp("univs.inference.inference_video_semantic_extraction")
     _HEADS = types.SimpleNamespace(comm=comm, utils_comm=ucomm, vis_fast=vis_fast, vos=vos, vps=vps,
                                    entity=entity, InferenceVideoEntity=entity.InferenceVideoEntity,
                                    image=image, InferenceImageGenericSeg=image.InferenceImageGenericSegmentation,
+                                   semx=semx,
                                    InferenceVideoVPS=vps.InferenceVideoVPS,
                                    InferenceVideoVISFast=vis_fast.InferenceVideoVISFast,
                                    InferenceVideoVOS=vos.InferenceVideoVOS,

@@ -614,8 +614,11 @@ def test_forward_inference_dispatch():
         model.forward_inference([dict(video, dataset_name="ytvis21")])
     model.attach_task_heads(thing_ids={3}, **kw)
     assert model.task_heads["entity"].thing_ids == {3} and model.task_heads["vps"].num_frames == T
-    for k in ("vis_fast", "vos", "vps", "entity", "image"):
+    for k in ("vis_fast", "vos", "vps", "entity", "image", "semantic_extraction"):
         model.task_heads[k] = Spy(k)
+    model.sem_seg_head.predictor.semantic_extraction_enable = True
+    assert model([dict(video, dataset_name="ytvis21")]) == "semantic_extraction"
+    model.sem_seg_head.predictor.semantic_extraction_enable = False
     assert model([dict(video, dataset_name="ytvis21")]) == "vis_fast"
     assert model([dict(video, dataset_name="vipseg_val")]) == "vps"
     assert model([dict(video, dataset_name="davis17", task="sot")]) == "vos"
@@ -730,3 +733,46 @@ def test_classwise_box_nms_matches_torchvision():
         scores, labels = torch.rand(n, generator=g), torch.randint(0, 4, (n,), generator=g)
         for thr in (0.3, 0.85):
             assert classwise_box_nms(boxes, scores, labels, thr).tolist() == batched_nms(boxes, scores, labels, thr).tolist()
+
+
+def test_semantic_extraction_head(tmp_path):
+    """InferenceVideoSemanticExtraction: object tokens + compressed mask features of non-overlapping clips (last clip
+    shorter), against the files the reference head writes."""
+    import inspect
+    from univs_b200.inference import InferenceVideoSemanticExtraction
+    heads = ref_shim.load_inference_heads()
+    T, Q, V, H, W = 2, 8, 5, 60, 90
+    ref, model = _pair(T, Q, enc_layers=1, dec_layers=2)
+    ref[2].semantic_extraction_enable = True
+    model.sem_seg_head.predictor.semantic_extraction_enable = True
+    g = torch.Generator().manual_seed(9)
+    frames = [(torch.rand(3, H, W, generator=g) * 255).round() for _ in range(V)]
+    inputs = [{"image": frames, "height": 64, "width": 96, "dataset_name": "ytvis21", "task": "detection", "video_len": V,
+               "video_id": "vid0", "file_names": [f"raw/vid0/{i}.jpg" for i in range(V)]}]
+    kw = dict(hidden_dim=256, num_queries=Q, overlap_threshold=0.8, overlap_threshold_entity=0.5, stability_score_thresh=0.0,
+              metadata=None, size_divisibility=32, LSJ_aug_image_size=1024, LSJ_aug_enable_test=False,
+              sem_seg_postprocess_before_inference=False, pixel_mean=MEAN, pixel_std=STD, num_frames=T, num_classes=133,
+              semantic_extraction_enable=True, semantic_extraction_compression_ratio=8,
+              semantic_extraction_compression_ratio_temporal=2, semantic_extraction_output_dir=str(tmp_path / "ref"))
+    accepted = set(inspect.signature(heads.semx.InferenceVideoSemanticExtraction.__init__).parameters)
+    rhead = heads.semx.InferenceVideoSemanticExtraction(**{k: v for k, v in kw.items() if k in accepted})
+    xs = torch.stack([(f - rhead.pixel_mean) / rhead.pixel_std for f in frames])
+    xs = torch.nn.functional.pad(xs, (0, 96 - W, 0, 64 - H))
+    tg = [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual", "file_names": inputs[0]["file_names"]}]
+    with torch.no_grad():
+        rhead.inference_video(heads.RefModel(*ref), inputs, heads.ImageList(xs, [(H, W)] * V), tg)
+    want_tok = torch.load(tmp_path / "ref" / "vid0._obj_tokens_8_2.pt")
+    want_mf = torch.load(tmp_path / "ref" / "vid0._compression_mask_features_8_2.pt")
+
+    phead = InferenceVideoSemanticExtraction(num_frames=T, compression_ratio=8, compression_ratio_temporal=2,
+                                             output_dir=str(tmp_path / "prod"))
+    with oracle_ops():
+        got = phead.eval(model, inputs)
+    assert got["obj_tokens"].shape == want_tok.shape == (3, 256, Q)
+    assert got["compression_mask_features"].shape == want_mf.shape == (3, 256, 8, 12)
+    torch.testing.assert_close(got["obj_tokens"], want_tok, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(got["compression_mask_features"], want_mf, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(torch.load(tmp_path / "prod" / "vid0._obj_tokens_8_2.pt"), got["obj_tokens"])
+    model.sem_seg_head.predictor.semantic_extraction_enable = False
+    with pytest.raises(RuntimeError):
+        phead.eval(model, inputs)

@@ -189,8 +189,8 @@ class UniVS_Prompt(nn.Module):
         `thing_ids` (1-based dataset ids) / `thing_contiguous_ids` (0-based class indices) / `metadata` stand in for detectron2's MetadataCatalog entry of the test dataset; `head_kwargs` are
         passed to every head that accepts them (e.g. reuse_features=False)."""
         import inspect
-        from .inference import (InferenceImageGenericSeg, InferenceVideoEntity, InferenceVideoVISFast, InferenceVideoVOS,
-                                InferenceVideoVPS)
+        from .inference import (InferenceImageGenericSeg, InferenceVideoEntity, InferenceVideoSemanticExtraction,
+                                InferenceVideoVISFast, InferenceVideoVOS, InferenceVideoVPS)
         cfg = self._cfg if cfg is None else cfg
         uv = cfg.MODEL.UniVS.TEST if cfg is not None else {}
         bv = cfg.MODEL.BoxVIS.TEST if cfg is not None else {}
@@ -206,6 +206,7 @@ class UniVS_Prompt(nn.Module):
             "vps": make(InferenceVideoVPS, thing_ids=thing_ids),
             "entity": make(InferenceVideoEntity, thing_ids=thing_ids),
             "image": make(InferenceImageGenericSeg, thing_contiguous_ids=thing_contiguous_ids),
+            "semantic_extraction": make(InferenceVideoSemanticExtraction),
             "unified": bool(pick(video_unified_inference_enable, uv, "VIDEO_UNIFIED_INFERENCE_ENABLE", False)),
             "custom_videos": bool(pick(custom_videos_enable, uv, "CUSTOM_VIDEOS_ENABLE", False)),
             "custom_videos_text": list(pick(custom_videos_text, uv, "CUSTOM_VIDEOS_TEXT", [])),
@@ -218,6 +219,8 @@ class UniVS_Prompt(nn.Module):
         h = self.task_heads
         if h is None:
             raise RuntimeError("forward_inference needs task heads: call attach_task_heads() first")
+        if getattr(self.sem_seg_head.predictor, "semantic_extraction_enable", False):
+            return h["semantic_extraction"].eval(self, batched_inputs)
         if "dataset_name" not in batched_inputs[0]:
             # demo form (demo/predictor.py:106-118: {"image", "height", "width"} only; the reference's dispatch raises a
             # KeyError on it): category-specified detection over the default video vocabulary
