@@ -72,6 +72,65 @@ def _common(T, Q):
                 window_inference=False, num_frames_window_test=T, clip_stride=1)
 
 
+ENTITY = dict(T=2, Q=12, V=7, H=60, W=90, out=(75, 120), model=dict(enc_layers=1, dec_layers=3), seed=21, rng=3,
+              head=dict(overlap_threshold=0.3, overlap_threshold_entity=0.2, test_topk_per_image=8, apply_cls_thres=0.45,
+                        box_nms_thresh=1.01, clip_stride=1, num_prev_frames_memory=1, temporal_consistency_threshold=0.05,
+                        detect_newly_object_threshold=0.05, detect_newly_interval_frames=1))
+VPS = dict(T=2, Q=12, V=4, H=60, W=90, out=(75, 120), model=dict(enc_layers=1, dec_layers=3), seed=11,
+           things=[c for c in range(1, 125) if c % 3 == 0],
+           head=dict(object_mask_threshold=0.0, overlap_threshold=0.3, test_topk_per_image=8))
+
+
+def main_entity_vps():
+    """Fixtures of the unified entity head (VIS sub-task) and the online VPS head."""
+    import contextlib
+    import inspect
+    import io
+    import types
+    heads = ref_shim.load_inference_heads()
+    s = ENTITY
+    frames = video(s)
+    xs, _ = _padded(frames, s["H"], s["W"])
+    kw = dict(_common(s["T"], s["Q"]), is_multi_cls=True, merge_on_cpu=False, num_max_inst_test=50, output_dir="/tmp",
+              video_unified_inference_entities="", custom_videos_enable=False, **s["head"])
+    accepted = set(inspect.signature(heads.InferenceVideoEntity.__init__).parameters)
+    head = heads.InferenceVideoEntity(**{k: v for k, v in kw.items() if k in accepted})
+    inputs = [{"image": frames, "height": s["out"][0], "width": s["out"][1], "dataset_name": "ytvis21",
+               "task": "detection", "video_len": s["V"], "video_id": 7}]
+    tg = [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual", "video_len": s["V"], "sub_task": "vis"}]
+    model = heads.RefModel(*_reference(s))
+    torch.manual_seed(s["rng"])              # after the model is built: the sampler draws from the global generator
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        res = head.inference_video(model, inputs, heads.ImageList(xs, [(s["H"], s["W"])] * s["V"]), tg)
+    res = sorted(res, key=lambda r: (r["category_id"], round(r["score"], 4)))
+    torch.save({"category_ids": [r["category_id"] for r in res], "scores": torch.tensor([r["score"] for r in res]),
+                "segmentations": [[seg["counts"] for seg in r["segmentations"]] for r in res],
+                "ids": tg[0]["ids"], "first_appear": tg[0]["first_appear_frame_idxs"], "logits": tg[0]["logits"],
+                "occurrence": tg[0]["occurrence"]}, os.path.join(HERE, "head_entity_vis.pt"))
+    print("head_entity_vis", len(res), "entries,", int(tg[0]["ids"].numel()), "entities")
+
+    s = VPS
+    frames = video(s)
+    xs, _ = _padded(frames, s["H"], s["W"])
+    meta = types.SimpleNamespace(thing_dataset_id_to_contiguous_id={c: i for i, c in enumerate(s["things"])})
+    kw = dict(_common(s["T"], s["Q"]), overlap_threshold_entity=0.5, is_multi_cls=True, apply_cls_thres=0.05,
+              merge_on_cpu=False, num_max_inst_test=50)
+    kw.update(s["head"], metadata=meta, data_name="vipseg_val", panoptic_on=True, instance_on=False)
+    accepted = set(inspect.signature(heads.InferenceVideoVPS.__init__).parameters)
+    head = heads.InferenceVideoVPS(**{k: v for k, v in kw.items() if k in accepted})
+    head.change_to_720p = False              # results at the requested output size: keeps the fixture small
+    inputs = [{"image": frames, "height": s["out"][0], "width": s["out"][1], "dataset_name": "vipseg", "task": "detection",
+               "video_len": s["V"]}]
+    with torch.no_grad():
+        res = head.inference_video_vps_online(heads.RefModel(*_reference(s)), inputs,
+                                              heads.ImageList(xs, [(s["H"], s["W"])] * s["V"]),
+                                              [{"task": "detection", "dataset_name": "vipseg", "prompt_type": "visual"}])
+    torch.save({"pred_masks": res["pred_masks"].to(torch.int16), "segments_infos": res["segments_infos"],
+                "pred_ids": [int(i) for i in res["pred_ids"]], "image_size": res["image_size"]},
+               os.path.join(HERE, "head_vps.pt"))
+    print("head_vps", len(res["segments_infos"]), "segments", tuple(res["pred_masks"].shape))
+
+
 def main():
     heads = ref_shim.load_inference_heads()
     # ---- VIS, MinVIS tracker
@@ -120,4 +179,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "entity_vps" in sys.argv[1:]:        # added later in round 1: leaves the first fixtures untouched
+        main_entity_vps()
+    else:
+        main()

@@ -11,8 +11,9 @@ import torch
 
 from oracle.cpu_backend import oracle_ops
 from tests import model_factory as mf
-from tests.golden.make_golden_heads import MEAN, SOT, STD, VIS, sot_annotations, video
-from univs_b200.inference import FrameAnnotations, InferenceVideoVISFast, InferenceVideoVOS
+from tests.golden.make_golden_heads import ENTITY, MEAN, SOT, STD, VIS, VPS, sot_annotations, video
+from univs_b200.inference import (FrameAnnotations, InferenceVideoEntity, InferenceVideoVISFast, InferenceVideoVOS,
+                                  InferenceVideoVPS)
 from univs_b200.meta_arch import UniVS_Prompt
 from univs_b200.modeling.head import MaskFormerHead
 from univs_b200.registry import ShapeSpec
@@ -65,6 +66,54 @@ def _sot(device):
         assert err < (2e-2 if k == "boxes" else 1e-3), (k, err)      # boxes are integer pixel edges / size
 
 
+def _entity(device):
+    from oracle import rle_ref
+    s = ENTITY
+    gold = torch.load(os.path.join(HERE, "head_entity_vis.pt"))
+    head = InferenceVideoEntity(num_queries=s["Q"], num_frames=s["T"], num_frames_window_test=s["T"], **s["head"])
+    model = _model(s, device)
+    torch.manual_seed(s["rng"])              # the prompt sampler draws its points from the global CPU generator
+    got = head.eval(model, [{"image": video(s), "height": s["out"][0], "width": s["out"][1],
+                             "dataset_name": "ytvis21", "task": "detection", "video_len": s["V"], "video_id": 7}])
+    tg = head._last_targets[0]
+    assert tg["ids"].tolist() == gold["ids"].tolist() and tg["first_appear_frame_idxs"].tolist() == gold["first_appear"].tolist()
+    torch.testing.assert_close(tg["logits"].cpu(), gold["logits"], rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(tg["occurrence"].cpu(), gold["occurrence"])
+    got = sorted(got, key=lambda r: (r["category_id"], round(r["score"], 4)))
+    assert [r["category_id"] for r in got] == gold["category_ids"]
+    np.testing.assert_allclose([r["score"] for r in got], gold["scores"].numpy(), rtol=1e-3, atol=1e-6)
+    flips = total = 0
+    size = list(s["out"])
+    for r, counts in zip(got, gold["segmentations"]):
+        assert len(r["segmentations"]) == s["V"]
+        for seg, c in zip(r["segmentations"], counts):
+            flips += int((rle_ref.decode(seg) != rle_ref.decode({"size": size, "counts": c})).sum())
+            total += size[0] * size[1]
+    assert flips <= 1e-3 * total, (flips, total)
+
+
+def _vps(device):
+    s = VPS
+    gold = torch.load(os.path.join(HERE, "head_vps.pt"))
+    head = InferenceVideoVPS(num_queries=s["Q"], num_frames=s["T"], num_frames_window_test=s["T"], thing_ids=s["things"],
+                             change_to_720p=False, **s["head"])
+    got = head.eval(_model(s, device), [{"image": video(s), "height": s["out"][0], "width": s["out"][1],
+                                         "dataset_name": "vipseg", "task": "detection", "video_len": s["V"]}])
+    assert got["image_size"] == tuple(gold["image_size"]) and got["segments_infos"] == gold["segments_infos"]
+    assert [int(i) for i in got["pred_ids"]] == gold["pred_ids"]
+    assert (got["pred_masks"] != gold["pred_masks"].to(torch.int32)).float().mean().item() <= 1e-3
+
+
+def test_entity_head_with_oracle_ops_matches_golden():
+    with oracle_ops():
+        _entity("cpu")
+
+
+def test_vps_head_with_oracle_ops_matches_golden():
+    with oracle_ops():
+        _vps("cpu")
+
+
 def test_vis_fast_head_with_oracle_ops_matches_golden():
     with oracle_ops():
         _vis("cpu")
@@ -99,5 +148,17 @@ def test_vos_sot_head_cuda_matches_golden(policy):
     precision.set_precision(policy)
     try:
         _sot("cuda")
+    finally:
+        precision.set_precision("fp32")
+
+
+@pytest.mark.gpu
+@_gpu_heads
+@pytest.mark.parametrize("which", ["entity", "vps"])
+def test_entity_and_vps_heads_cuda_match_golden(which):
+    from univs_b200 import precision
+    precision.set_precision("fp16x3")
+    try:
+        (_entity if which == "entity" else _vps)("cuda")
     finally:
         precision.set_precision("fp32")
