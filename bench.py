@@ -75,6 +75,43 @@ class ClockSampler:
                 "samples": len(clocks)}
 
 
+def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, dec_layers=9, enc_layers=6):
+    """Algorithmic HBM bytes per clip (SURVEY.md 8(d) formulas, fp32 element size) of the four kernels BASELINE.json names,
+    divided by their CUDA-event time per clip.  Pure arithmetic on the per-kernel brackets; returns
+    {name: {"bytes_per_step", "ms_per_step", "achieved" (GB/s), "frac"}}."""
+    from univs_b200.config import SWIN_VARIANTS
+    sw = SWIN_VARIANTS[variant]
+    Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+    e, C = 4, 256
+    out = {}
+
+    def put(name, key, nbytes):
+        if key in kernel_ms and kernel_ms[key] > 0:
+            ms = kernel_ms[key] * kernel_calls.get(key, 1)
+            ach = nbytes / (ms * 1e-3) / 1e9
+            out[name] = {"bytes_per_step": nbytes, "ms_per_step": ms, "achieved": ach, "frac": ach / peak}
+
+    # mask einsum: e*(Q*C + C*HW + Q*HW) per frame per call, dec_layers + 1 calls
+    HW = (Hp // 4) * (Wp // 4)
+    put("mask_einsum", "mask_einsum", float(e * T * (Q * C + C * HW + Q * HW) * (dec_layers + 1)))
+    # MSDeformAttn core: e*(2*Len*256 + 3*Len*M*L*P) per frame per layer, M*L*P = 96
+    Len = sum((Hp // s) * (Wp // s) for s in (8, 16, 32))
+    put("ms_deform_attn", "ms_deform_attn_encoder", float(e * T * (2 * Len * C + 3 * Len * 96) * enc_layers))
+    # Swin window attention: e*4*nW*N*C per block per frame (q, k, v in, out), windows padded to the window size
+    ws, total = sw["WINDOW_SIZE"], 0
+    for s, depth in enumerate(sw["DEPTHS"]):
+        hs, wsz = Hp // (4 << s), Wp // (4 << s)
+        tokens = (-(-hs // ws) * ws) * (-(-wsz // ws) * ws)
+        total += depth * e * 4 * tokens * (sw["EMBED_DIM"] << s)
+    put("swin_window_attention", "swin_window_attention", float(total * T))
+    # decoder attention: cross-attention e*(2*S_l*256 + 2*Q*256) per frame per layer (level l = layer % 3, 1/32 first)
+    # + the Q*T self-attention e*4*Q*T*256 per layer
+    S = [(Hp // s) * (Wp // s) for s in (32, 16, 8)]
+    mha = sum(e * T * (2 * S[i % 3] * C + 2 * Q * C) + e * 4 * Q * T * C for i in range(dec_layers))
+    put("decoder_attention", "mha", float(mha))
+    return out
+
+
 def make_targets(T, device):
     return [{"task": "detection", "dataset_name": "ytvis21", "prompt_type": "visual",
              "frame_indices": torch.arange(T, device=device)}]
@@ -330,6 +367,14 @@ def main():
                 "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "launch_ms": kernel_ms["mask_einsum"],
                 "algorithmic_bytes_per_launch": alg_bytes}
 
+    named = None
+    try:    # per-kernel roofline fractions of the four named kernels (metric (iii) of SURVEY.md 8d); never blocks the line
+        named = named_kernel_rooflines(variant, T, H, W, n_lp, kernel_ms, kernel_calls, peak,
+                                       dec_layers=cfg.MODEL.MASK_FORMER.DEC_LAYERS - 1,
+                                       enc_layers=cfg.MODEL.SEM_SEG_HEAD.TRANSFORMER_ENC_LAYERS)
+    except Exception as exc:  # noqa: BLE001
+        sys.stderr.write(f"[bench] named-kernel rooflines unavailable: {exc}\n")
+
     line = None
     if rank == 0:
         cpu = None
@@ -356,6 +401,7 @@ def main():
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches,
             "roofline": roof,
+            "named_kernel_rooflines": named,        # algorithmic bytes per clip / event time per clip, vs the same HBM peak
             "kernels": {k: {"ms_per_launch": kernel_ms[k], "launches_per_step": kernel_calls[k]} for k in sorted(kernel_ms)},
             "cpu_baseline": cpu,
         }

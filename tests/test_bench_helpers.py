@@ -1,0 +1,46 @@
+"""bench.py arithmetic that can be checked without a GPU: the algorithmic-byte formulas of the four named kernels
+(SURVEY.md 8d figures at the north-star shape) and the JSON contract of the reference arm."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_named_kernel_algorithmic_bytes_match_survey_figures():
+    ms = {"mask_einsum": 1.0, "ms_deform_attn_encoder": 1.0, "swin_window_attention": 1.0, "mha": 1.0}
+    calls = {k: 1 for k in ms}
+    r = bench.named_kernel_rooflines("large", 1, 720, 1280, 200, ms, calls, 1000.0, dec_layers=0, enc_layers=1)
+    assert abs(r["mask_einsum"]["bytes_per_step"] / 1e6 - 107.6) < 0.1          # per frame per call
+    assert abs(r["ms_deform_attn"]["bytes_per_step"] / 1e6 - 61.8) < 0.1        # per frame per layer
+    r = bench.named_kernel_rooflines("large", 5, 720, 1280, 200, ms, calls, 1000.0)
+    assert abs(r["mask_einsum"]["bytes_per_step"] / 1e9 - 5.38) < 0.01          # x10 calls x T=5
+    # stage 1 of Swin-L at 736x1280: 184x320 tokens padded to 192x324, C = 192 -> 191 MB per block per frame
+    stage1 = 4 * 4 * 192 * 324 * 192
+    assert abs(stage1 / 1e6 - 191) < 0.5
+    assert r["swin_window_attention"]["bytes_per_step"] > 2 * 5 * stage1
+    # achieved = bytes / time, frac = achieved / peak
+    one = r["ms_deform_attn"]
+    assert abs(one["achieved"] - one["bytes_per_step"] / 1e-3 / 1e9) < 1e-6 and abs(one["frac"] - one["achieved"] / 1000.0) < 1e-12
+    # a kernel that was not bracketed is simply absent
+    assert "decoder_attention" not in bench.named_kernel_rooflines("tiny", 5, 480, 864, 100, {"mask_einsum": 1.0}, {}, 1.0)
+
+
+def test_committed_round1_line_reproduces_the_documented_fractions():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_ns_fp16x3_1gpu.json")))
+    km = {k: v["ms_per_launch"] for k, v in d["kernels"].items()}
+    kc = {k: v["launches_per_step"] for k, v in d["kernels"].items()}
+    r = bench.named_kernel_rooflines("large", 5, 720, 1280, 200, km, kc, d["roofline"]["peak"])
+    assert abs(r["mask_einsum"]["frac"] - d["roofline"]["frac"]) < 1e-6
+    assert 0.10 < r["ms_deform_attn"]["frac"] < 0.12 and 0.17 < r["swin_window_attention"]["frac"] < 0.21
+
+
+def test_reference_arm_contract_on_non_zero_ranks():
+    """Under torchrun only rank 0 runs the CPU reference; the other ranks exit 0 without output."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == ""
