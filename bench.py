@@ -201,8 +201,12 @@ def main():
     from univs_b200.build import build_model, make_cfg
     from univs_b200.precision import set_precision
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    # UNIVS_BENCH_DEVICE exists for tests/test_bench_dryrun.py (control-flow check of this script on a CPU with the oracle
+    # operator backend patched in by the test); the operators themselves have no CPU path, so a plain run on "cpu" fails
+    dev_type = os.environ.get("UNIVS_BENCH_DEVICE", "cuda")
+    if dev_type == "cuda":
+        torch.cuda.set_device(local_rank)
+    dev = torch.device(dev_type, local_rank)
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -1,0 +1,102 @@
+"""Control-flow check of bench.py without a GPU: `bench.main()` runs on the CPU with the oracle operator backend patched
+in and the CUDA timing primitives faked, at a tiny geometry.  The numbers mean nothing; what is checked is that every
+code path of the default run, of the eager run and of the video benchmark executes and prints a line that carries every
+key of the bench contract (a NameError in this script at round end would cost the round's measurement)."""
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from oracle.cpu_backend import oracle_ops  # noqa: E402
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        self.t = None
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+    def synchronize(self):
+        pass
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+
+@contextlib.contextmanager
+def _fake_cuda(monkeypatch):
+    monkeypatch.setenv("UNIVS_BENCH_DEVICE", "cpu")
+    monkeypatch.setenv("UNIVS_CPU_THREADS", "4")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setitem(bench.WORKLOADS, "dry", ("tiny", 2, 64, 96, 8))
+    with oracle_ops():
+        yield
+
+
+def _run(monkeypatch, argv):
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    buf = io.StringIO()
+    with _fake_cuda(monkeypatch), contextlib.redirect_stdout(buf):
+        bench.main()
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, buf.getvalue()
+    return json.loads(lines[0])
+
+
+CONTRACT = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline")
+
+
+def test_default_run_control_flow(monkeypatch):
+    # --no-graph: CUDA-graph capture is the one part that cannot be imitated on a CPU (runtime.GraphedClip)
+    line = _run(monkeypatch, ["--workload", "dry", "--steps", "1", "--warmup", "1", "--no-graph", "--precision", "fp32"])
+    for k in CONTRACT:
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 3       # W >= 3 is enforced
+    assert line["value"] > 0 and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["config"]["workload"].startswith("dry:") and line["config"]["switches"] == {}
+    assert line["config"]["execution"] == "eager" and "l2" in line["config"]
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 2 * 3 * 64 * 96 and e2e["d2h_bytes_per_step"] > 0
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] > 0 and "sample" in cpu
+    assert line["named_kernel_rooflines"] == {}         # no CUDA brackets on this backend: absent, not wrong
+
+
+def test_video_benchmark_control_flow(monkeypatch):
+    line = _run(monkeypatch, ["--workload", "dry", "--steps", "1", "--video-frames", "3", "--no-graph", "--precision", "fp32"])
+    assert line["metric"].startswith("video frames/sec") and line["value"] > 0
+    assert line["reference_schedule"]["value"] > 0 and line["rle_results"]["value"] > 0
+
+
+def test_plain_cpu_run_fails_loudly(monkeypatch):
+    """without the oracle patch the same invocation must die in the first operator: there is no CPU path"""
+    from univs_b200._cabi import UnivsB200Error
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "dry", "--steps", "1", "--no-graph"])
+    monkeypatch.setenv("UNIVS_BENCH_DEVICE", "cpu")
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setitem(bench.WORKLOADS, "dry", ("tiny", 2, 64, 96, 8))
+    with pytest.raises(UnivsB200Error):
+        bench.main()
