@@ -75,7 +75,7 @@ class ClockSampler:
                 "samples": len(clocks)}
 
 
-def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, dec_layers=9, enc_layers=6):
+def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, dec_layers=9, enc_layers=6, sm_mhz=1965.0):
     """Algorithmic HBM bytes per clip (SURVEY.md 8(d) formulas, fp32 element size) of the four kernels BASELINE.json names,
     divided by their CUDA-event time per clip.  Pure arithmetic on the per-kernel brackets; returns
     {name: {"bytes_per_step", "ms_per_step", "achieved" (GB/s), "frac"}}."""
@@ -97,6 +97,13 @@ def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, d
     # MSDeformAttn core: e*(2*Len*256 + 3*Len*M*L*P) per frame per layer, M*L*P = 96
     Len = sum((Hp // s) * (Wp // s) for s in (8, 16, 32))
     put("ms_deform_attn", "ms_deform_attn_encoder", float(e * T * (2 * Len * C + 3 * Len * 96) * enc_layers))
+    if "ms_deform_attn" in out:
+        # the gather is bound by L1 request throughput long before HBM: every (query, head) fetches L*P*4 = 48 corners of
+        # 32 fp32 channels = 48 requests of one 128-byte line, and an SM's L1 serves one 128-byte wavefront per clock
+        wavefronts = float(T * Len * 8 * 48 * enc_layers)
+        floor_ms = wavefronts / (148 * sm_mhz * 1e6) * 1e3
+        out["ms_deform_attn"].update({"l1_wavefronts_per_step": wavefronts, "l1_floor_ms_per_step": floor_ms,
+                                      "frac_of_l1_floor": floor_ms / out["ms_deform_attn"]["ms_per_step"]})
     # Swin window attention: e*4*nW*N*C per block per frame (q, k, v in, out), windows padded to the window size
     ws, total = sw["WINDOW_SIZE"], 0
     for s, depth in enumerate(sw["DEPTHS"]):
@@ -375,7 +382,8 @@ def main():
     try:    # per-kernel roofline fractions of the four named kernels (metric (iii) of SURVEY.md 8d); never blocks the line
         named = named_kernel_rooflines(variant, T, H, W, n_lp, kernel_ms, kernel_calls, peak,
                                        dec_layers=cfg.MODEL.MASK_FORMER.DEC_LAYERS - 1,
-                                       enc_layers=cfg.MODEL.SEM_SEG_HEAD.TRANSFORMER_ENC_LAYERS)
+                                       enc_layers=cfg.MODEL.SEM_SEG_HEAD.TRANSFORMER_ENC_LAYERS,
+                                       sm_mhz=float((clocks or {}).get("sm_mhz") or 1965.0))
     except Exception as exc:  # noqa: BLE001
         sys.stderr.write(f"[bench] named-kernel rooflines unavailable: {exc}\n")
 
