@@ -106,6 +106,13 @@ int univs_mask_einsum_f32(void* stream, const float* mask_embed, const float* ma
 int univs_mask_einsum_f16x3(void* stream, const void* mask_embed16, const void* mask_features16, int frames, int queries,
                             int channels, int pixels, float* out);
 
+/* Cluster variant of univs_mask_einsum_f16x3 (csrc/mask_einsum_mc.cu; same operands, same result up to the fp32
+ * accumulation order, which is identical per output element): two CTAs of a cluster split the queries, each keeps its half
+ * of mask_embed16 resident in shared memory for a whole frame, mask_features16 tiles reach both through TMA multicast.
+ * 16 < Q <= 256, C % 32 == 0 and C <= 256.  Opt-in (never run on hardware in round 1). */
+int univs_mask_einsum_f16x3_cluster(void* stream, const void* mask_embed16, const void* mask_features16, int frames,
+                                    int queries, int channels, int pixels, float* out);
+
 /* Same contraction with register operands (mma.sync): precision UNIVS_PREC_TF32 rounds operands to nearest TF32
  * in-kernel (bit-identical to the tcgen05 kernel on pre-rounded operands); UNIVS_PREC_TF32X3 uses the 3xTF32 split
  * (fp32-equivalent products) -- the strict-parity policy and the on-device cross-check of the tcgen05 kernel. */

@@ -23,7 +23,18 @@ E = ops.round_tf32(torch.randn(T, Q, C, device="cuda")); F = ops.round_tf32(torc
 out = torch.empty(Q, T, HW, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 F16 = ops.prepare_mask_features(F, "f16x3")
-for name, fn in (("tc_tf32", lambda e, f, out: ops.mask_einsum(e, f, out=out, mode="tf32")), ("tc_f16x3", lambda e, f, out: ops.mask_einsum(e, F16, out=out, mode="f16x3")), ("mma", lambda e, f, out: ops.mask_einsum_mma(e, f, ops.PREC_TF32, out=out)), ("mma3x", lambda e, f, out: ops.mask_einsum_mma(e, f, ops.PREC_TF32X3, out=out))):
+def _cluster(e, f, out):
+    ops._einsum_mc = 1
+    try:
+        return ops.mask_einsum(e, F16, out=out, mode="f16x3")
+    finally:
+        ops._einsum_mc = 0
+
+
+variants = [("tc_tf32", lambda e, f, out: ops.mask_einsum(e, f, out=out, mode="tf32")), ("tc_f16x3", lambda e, f, out: ops.mask_einsum(e, F16, out=out, mode="f16x3")), ("mma", lambda e, f, out: ops.mask_einsum_mma(e, f, ops.PREC_TF32, out=out)), ("mma3x", lambda e, f, out: ops.mask_einsum_mma(e, f, ops.PREC_TF32X3, out=out))]
+if os.environ.get("EINSUM_MC") == "1":          # opt-in: the cluster / multicast kernel (csrc/mask_einsum_mc.cu)
+    variants.insert(2, ("tc_f16x3_cluster", _cluster))
+for name, fn in variants:
     for _ in range(3): fn(E, F, out=out)
     ts = []
     for _ in range(10):

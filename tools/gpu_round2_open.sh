@@ -21,6 +21,8 @@ UNIVS_GPU_WINTC=1 run wintc_tests 600 python -m pytest tests/test_window_attn_tc
 run wintc_check 600 python tests/tools/win_tc_check.py --time
 UNIVS_GPU_MHATC=1 run mhatc_tests 600 python -m pytest tests/test_mha_tc.py -m gpu -q
 run mhatc_check 600 python tests/tools/mha_tc_check.py --time
+UNIVS_GPU_EINSUM_MC=1 run einsum_mc_tests 600 python -m pytest tests/test_einsum_mc.py -m gpu -q
+EINSUM_MC=1 run einsum_mc_check 600 python tools/einsum_tc_check.py
 UNIVS_GPU_ROWWISE_V2=1 run rowwise_v2_tests 600 python -m pytest tests/test_rowwise_v2.py -m gpu -q
 UNIVS_GPU_GLUE=1 run glue_tests 900 python -m pytest tests/test_fused_glue.py -m gpu -q
 UNIVS_GPU_HEADS=1 run heads_tests 900 python -m pytest tests/test_heads_golden.py -m gpu -q
@@ -32,6 +34,7 @@ UNIVS_ROWWISE_V2=1 run bench_rowwise_v2 900 python bench.py --steps 10 --warmup 
 UNIVS_FRAME_STREAMS=2 run bench_streams2 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_FRAME_STREAMS=5 run bench_streams5 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_POOLED_MASKS=1 run bench_pooled_masks 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+UNIVS_EINSUM_MC=1 run bench_einsum_mc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_MHA_TC=1 run bench_mhatc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 UNIVS_POOLED_MASKS=1 run bench_all 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run bench_video 900 python bench.py --steps 2 --video-frames 12

@@ -22,6 +22,7 @@ SIGNATURES = {
     "univs_swin_window_attention_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "univs_mask_einsum_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "univs_mask_einsum_f16x3": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "univs_mask_einsum_f16x3_cluster": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "univs_mask_einsum_mma_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "univs_attn_mask_bits_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "univs_mask_feature_pool_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i]),

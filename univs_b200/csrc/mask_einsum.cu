@@ -130,6 +130,7 @@ mask_einsum_kernel(const float* __restrict__ E, const float* __restrict__ F, int
 namespace univs {
 int launch_mask_einsum_tc(cudaStream_t st, const float* E, const float* F, int T, int Q, int C, int HW, float* out);
 int launch_mask_einsum_tc_f16(cudaStream_t st, const void* E16, const void* F16, int T, int Q, int C, int HW, float* out);
+int launch_mask_einsum_mc_f16(cudaStream_t st, const void* E16, const void* F16, int T, int Q, int C, int HW, float* out);
 }
 using namespace univs;
 
@@ -161,6 +162,18 @@ extern "C" int univs_mask_einsum_f16x3(void* stream, const void* mask_embed16, c
   UNIVS_REQUIRE(((uintptr_t)mask_embed16 & 15) == 0 && ((uintptr_t)mask_features16 & 15) == 0,
                 "mask_einsum_f16x3: operands must be 16-byte aligned (TMA)");
   return launch_mask_einsum_tc_f16((cudaStream_t)stream, mask_embed16, mask_features16, frames, queries, channels, pixels, out);
+}
+
+extern "C" int univs_mask_einsum_f16x3_cluster(void* stream, const void* mask_embed16, const void* mask_features16, int frames,
+                                               int queries, int channels, int pixels, float* out) {
+  int rc = check_einsum_args("mask_einsum_f16x3_cluster", (const float*)mask_embed16, (const float*)mask_features16, out,
+                             frames, queries, channels, pixels);
+  if (rc) return rc < 0 ? rc : UNIVS_OK;
+  UNIVS_REQUIRE(channels % 32 == 0, "mask_einsum_f16x3_cluster: channels must be a multiple of 32");
+  UNIVS_REQUIRE(queries > 16, "mask_einsum_f16x3_cluster: the query split needs more than 16 queries");
+  UNIVS_REQUIRE(((uintptr_t)mask_embed16 & 15) == 0 && ((uintptr_t)mask_features16 & 15) == 0,
+                "mask_einsum_f16x3_cluster: operands must be 16-byte aligned (TMA)");
+  return launch_mask_einsum_mc_f16((cudaStream_t)stream, mask_embed16, mask_features16, frames, queries, channels, pixels, out);
 }
 
 extern "C" int univs_mask_einsum_mma_f32(void* stream, const float* mask_embed, const float* mask_features_cl,

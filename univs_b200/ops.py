@@ -225,6 +225,9 @@ def prepare_mask_features(mask_features_cl, mode=None):
     return mask_features_cl
 
 
+_einsum_mc = switches.get("EINSUM_MC")   # opt-in: 1 = cluster / multicast kernel for the f16x3 mode
+
+
 def mask_einsum(mask_embed, mask_features_prepared, out=None, mode=None, tag="mask_einsum"):
     """mask_embed [T,Q,C] fp32, mask_features_prepared from prepare_mask_features (channel-last) -> [Q,T,HW] fp32.
     `tag` names the launch in the per-kernel event brackets (bench.py)."""
@@ -239,10 +242,10 @@ def mask_einsum(mask_embed, mask_features_prepared, out=None, mode=None, tag="ma
         return out
     if mode == "f16x3":
         e = split_operand(mask_embed if mask_embed.is_contiguous() else mask_embed.contiguous(), "f16u")
+        entry = lib().univs_mask_einsum_f16x3_cluster if (_einsum_mc and Q > 16 and Cc <= 256) else lib().univs_mask_einsum_f16x3
         with _Bracket(tag, 1):
-            rc = lib().univs_mask_einsum_f16x3(_stream(), _chk(e, "mask_embed", torch.float16),
-                                               _chk(mask_features_prepared, "mask_features", torch.float16),
-                                               T, Q, Cc, HW, _chk(out, "out"))
+            rc = entry(_stream(), _chk(e, "mask_embed", torch.float16),
+                       _chk(mask_features_prepared, "mask_features", torch.float16), T, Q, Cc, HW, _chk(out, "out"))
     elif mode == "tf32":
         e = round_tf32(mask_embed)
         with _Bracket(tag, 1):

@@ -15,6 +15,7 @@ DEFAULTS = {
     "WIN_TC": 0,            # ops: tcgen05 window attention for 12x12 windows
     "MHA_TC": 0,            # ops: tcgen05 cross-attention (1; 3 = transposed-V diagnostic variant)
     "ROWWISE_V2": 0,        # csrc/elementwise.cu: 8-wide GELU / ReLU / operand split
+    "EINSUM_MC": 0,         # ops: cluster / TMA-multicast mask einsum (E resident per CTA pair)
     "POOLED_MASKS": 0,      # decoder: intermediate heads from pooled mask features
     "SHARD_DECODER": 0,     # meta_arch: frame-sharded decoder with token exchange (N > 1)
     "FRAME_STREAMS": 1,     # meta_arch: frame groups on CUDA streams (N == 1)
