@@ -111,3 +111,23 @@ def test_reference_function_runs_on_the_compat_module(monkeypatch):
     (value, shapes, lsi, loc, w), dims = _inputs()
     out = func.MSDeformAttnFunction.apply(value, shapes, lsi, loc, w, 128)        # ms_deform_attn.py:120
     assert out.shape == (2, 5, 256) and len(rec.calls) == 1 and rec.calls[0][6:13] == dims
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("UNIVS_GPU_COMPAT") != "1",
+                    reason="compat module on CUDA: opt-in until run on a B200 (UNIVS_GPU_COMPAT=1)")
+def test_compat_module_on_cuda_matches_the_oracle():
+    from oracle import ops_ref
+    mod = _load_compat()
+    torch.manual_seed(3)                                         # shapes / seed of the reference's ops/test.py:24-33
+    N, M, D, Lq, L, P = 1, 2, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = torch.rand(N, S, M, D) * 0.01
+    loc = torch.rand(N, Lq, M, L, P, 2)
+    w = torch.rand(N, Lq, M, L, P) + 1e-5
+    w = w / w.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    got = mod.ms_deform_attn_forward(value.cuda(), shapes.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 2)
+    want = ops_ref.ms_deform_attn(value, shapes.tolist(), lsi.tolist(), loc, w)
+    assert (got.cpu() - want).abs().max().item() <= 1e-5 * max(want.abs().max().item(), 1e-6) + 1e-9

@@ -25,6 +25,7 @@ UNIVS_GPU_EINSUM_MC=1 run einsum_mc_tests 600 python -m pytest tests/test_einsum
 EINSUM_MC=1 run einsum_mc_check 600 python tools/einsum_tc_check.py
 UNIVS_GPU_ROWWISE_V2=1 run rowwise_v2_tests 600 python -m pytest tests/test_rowwise_v2.py -m gpu -q
 UNIVS_GPU_GLUE=1 run glue_tests 900 python -m pytest tests/test_fused_glue.py -m gpu -q
+UNIVS_GPU_COMPAT=1 run compat_tests 300 python -m pytest tests/test_compat_msda_module.py -m gpu -q
 UNIVS_GPU_HEADS=1 run heads_tests 900 python -m pytest tests/test_heads_golden.py -m gpu -q
 # 2. measurements: default, then each opt-in on top of it (a path that failed above still runs: its number is void)
 run bench_default 900 python bench.py --steps 10 --warmup 3
