@@ -776,3 +776,28 @@ def test_semantic_extraction_head(tmp_path):
     model.sem_seg_head.predictor.semantic_extraction_enable = False
     with pytest.raises(RuntimeError):
         phead.eval(model, inputs)
+
+
+def test_entity_head_vss_full_model_uses_category_prompts():
+    """VSPW (a semantic dataset): PrepareTargets gives detection clips prompt_type "text" (prepare_targets.py:58-64), so the
+    124 category prompts join the learnable queries in the decoder; semantic result of the entity head vs the reference."""
+    from univs_b200.inference import InferenceVideoEntity, process_inference
+    T, Q, V, H, W = 2, 12, 4, 60, 90
+    ref, model = _pair(T, Q, enc_layers=1, dec_layers=3)
+    heads, rhead, rimages, inputs, pkw = _entity_pair(T, Q, V, H, W, 31, "vspw")
+    tg = [{"task": "detection", "dataset_name": "vspw", "prompt_type": "text", "video_len": V, "sub_task": "vss"}]
+    seen = []
+    rmodel = heads.RefModel(*ref)
+    orig = rmodel.sem_seg_head
+    rmodel.sem_seg_head = lambda feats, targets=None: (lambda o: (seen.append(o["pred_masks"].shape[1]), o)[1])(orig(feats, targets=targets))
+    with torch.no_grad():
+        want = rhead.inference_video(rmodel, inputs, rimages, tg)
+    assert seen and all(n == Q + 124 for n in seen)             # the category prompts were in the decoder
+    assert process_inference(inputs[0], (64, 96), (H, W), T)[0]["prompt_type"] == "text"
+    assert process_inference(dict(inputs[0], dataset_name="ytvis21"), (64, 96), (H, W), T)[0]["prompt_type"] == "visual"
+    assert process_inference(dict(inputs[0], dataset_name="ytvis21"), (64, 96), (H, W), T, semantic_on=True)[0]["prompt_type"] == "text"
+    for reuse in (True, False):
+        with oracle_ops():
+            got = InferenceVideoEntity(reuse_features=reuse, **pkw).eval(model, inputs)
+        assert got["task"] == "vss" and got["pred_masks"].shape == want["pred_masks"].shape == (V, 75, 120)
+        assert (got["pred_masks"] != want["pred_masks"]).float().mean().item() <= 1e-3

@@ -118,3 +118,42 @@ def pair_mask_iou(masks1, masks2):
     """IoU of corresponding binary masks [..., H, W] -> [...] (univs/utils/comm.py:213-227)."""
     a, b = masks1.flatten(-2) > 0.5, masks2.flatten(-2) > 0.5
     return (a & b).sum(-1) / (a | b).sum(-1).clamp(min=1)
+
+
+def is_semseg_dataset(dataset_name: str) -> bool:
+    """univs/prepare_targets.py:13-17"""
+    return dataset_name.startswith("vspw")
+
+
+def process_inference(video: dict, inter_image_size, image_size, num_frames: int, semantic_on: bool = False,
+                      custom_videos_text=()):
+    """PrepareTargets.process_inference (univs/prepare_targets.py:46-95) for the one video of an inference batch: the
+    `targets` list the decoder and the prompt sampler read and mutate.  prompt_type: "text" for grounding and for
+    category-prompt detection on semantic datasets (or SEMANTIC_ON), "visual" otherwise (:58-64).  The CLIP text tower is
+    not part of this build: expression features (`exp_word_feats`, `exp_sentence_feats`, `exp_word_len`) are taken from
+    the input dict where the reference computes them here (:90-93, :260-330)."""
+    video_in = video
+    if len(custom_videos_text) > 0:
+        video = dict(video, task="grounding", expressions=list(custom_videos_text[0]),
+                     exp_obj_ids=list(range(len(custom_videos_text[0]))))
+    task = video.get("task", "detection")
+    name = video["dataset_name"]
+    if task == "grounding":
+        prompt_type = "text"
+    elif task == "detection":
+        prompt_type = "text" if (is_semseg_dataset(name) or semantic_on) else "visual"
+    else:
+        prompt_type = "visual"
+    V = len(video["image"])
+    tg = {"video_len": int(video.get("video_len", V)), "dataset_name": name, "task": task, "num_frames": num_frames,
+          "inter_image_size": tuple(inter_image_size), "image_size": tuple(image_size),
+          "file_names": video.get("file_names", [""] * V), "prompt_type": prompt_type}
+    if "video_id" in video:
+        tg["video_id"] = video["video_id"]
+    for key in ("mask_palette", "expressions", "exp_obj_ids", "exp_word_feats", "exp_sentence_feats", "exp_word_len"):
+        if key in video:
+            tg[key] = video[key]
+    if task == "sot" and "instances" in video:
+        tg["instances"] = video["instances"]
+    video_in["prompt_type"] = prompt_type          # the reference writes it back into the input dict as well (:81)
+    return [tg]

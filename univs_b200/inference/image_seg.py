@@ -19,7 +19,7 @@ from torch import nn
 from ..modeling.decoder import COMBINED_DATASETS_CATEGORY_INFO
 from ..modeling.visual_prompts import mask_to_box
 from ..registry import is_cfg
-from .comm import calculate_mask_quality_scores
+from .comm import calculate_mask_quality_scores, process_inference
 
 
 def classwise_box_nms(boxes, scores, labels, iou_threshold):
@@ -103,9 +103,8 @@ class InferenceImageGenericSeg(nn.Module):
             x = F.pad(x, (0, S - x.shape[-1], 0, S - x.shape[-2]), value=0.0)
         targets = inp.get("targets")
         if targets is None:
-            targets = [{"task": inp.get("task", "detection"), "dataset_name": name, "prompt_type": "visual",
-                        "video_len": 1, "num_frames": 1, "inter_image_size": tuple(x.shape[-2:]), "image_size": image_size,
-                        "frame_indices": torch.arange(1)}]
+            targets = process_inference(inp, tuple(x.shape[-2:]), image_size, 1, semantic_on=self.semantic_on)
+            targets[0]["frame_indices"] = torch.arange(1)
         return self.inference_image(model, batched_inputs, x, image_size, targets)
 
     # ------------------------------------------------------------------ reference :211-289

@@ -33,7 +33,7 @@ from ..modeling.visual_prompts import mask_to_box
 from ..registry import is_cfg
 from ..streaming import ClipStream
 from . import rle
-from .comm import calculate_mask_quality_scores, check_consistency_with_prev_frames, video_box_iou
+from .comm import calculate_mask_quality_scores, check_consistency_with_prev_frames, process_inference, video_box_iou
 
 _ENTITY_DATASETS = {"entity_vss_entityseg": "entityseg_panoptic", "entity_vps_entityseg": "entityseg_panoptic",
                     "entity_vss_vipseg": "vipseg", "entity_vps_vipseg": "vipseg",
@@ -120,10 +120,11 @@ class InferenceVideoEntity(nn.Module):
                  apply_cls_thres=0.05, box_nms_thresh=0.75, num_frames_window_test=5, clip_stride=1,
                  num_prev_frames_memory=5, video_unified_inference_entities="", temporal_consistency_threshold=0.05,
                  detect_newly_object_threshold=0.05, detect_newly_interval_frames=1, custom_videos_enable=False,
-                 thing_ids=(), lsj_aug_enable_test=False, lsj_aug_image_size=1024, reuse_features=True):
+                 thing_ids=(), lsj_aug_enable_test=False, lsj_aug_image_size=1024, reuse_features=True, semantic_on=False):
         super().__init__()
         if cfg is not None and is_cfg(cfg):
             mf, bv, uv = cfg.MODEL.MASK_FORMER, cfg.MODEL.BoxVIS.TEST, cfg.MODEL.UniVS.TEST
+            semantic_on = mf.TEST.get("SEMANTIC_ON", False)
             hidden_dim = mf.HIDDEN_DIM
             num_queries = mf.NUM_OBJECT_QUERIES
             num_frames = cfg.INPUT.SAMPLING_FRAME_NUM
@@ -170,6 +171,7 @@ class InferenceVideoEntity(nn.Module):
         self.thing_ids = set(int(i) for i in thing_ids)       # 1-based dataset ids of the thing classes (metadata, :674)
         self.LSJ_aug_enable_test, self.LSJ_aug_image_size = lsj_aug_enable_test, lsj_aug_image_size
         self.reuse_features = reuse_features
+        self.semantic_on = semantic_on           # PrepareTargets: category prompts ("text") for detection clips
         self._device = torch.device("cpu")
         self._last_targets = None
 
@@ -187,10 +189,7 @@ class InferenceVideoEntity(nn.Module):
         V = x.shape[0]
         targets = video.get("targets")
         if targets is None:
-            targets = [{"task": video.get("task", "detection"), "dataset_name": video["dataset_name"],
-                        "prompt_type": "visual", "video_len": int(video.get("video_len", V)), "num_frames": self.num_frames,
-                        "inter_image_size": tuple(x.shape[-2:]), "image_size": image_size,
-                        "file_names": video.get("file_names", [""] * V)}]
+            targets = process_inference(video, tuple(x.shape[-2:]), image_size, self.num_frames, semantic_on=self.semantic_on)
         if self.video_unified_inference_entities:
             targets[0]["sub_task"] = self.video_unified_inference_entities
         else:

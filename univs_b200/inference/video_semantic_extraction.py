@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..registry import is_cfg
+from .comm import process_inference
 
 
 class InferenceVideoSemanticExtraction(nn.Module):
@@ -57,10 +58,7 @@ class InferenceVideoSemanticExtraction(nn.Module):
         V = x.shape[0]
         targets = video.get("targets")
         if targets is None:
-            targets = [{"task": video.get("task", "detection"), "dataset_name": video["dataset_name"],
-                        "prompt_type": "visual", "video_len": int(video.get("video_len", V)), "num_frames": self.num_frames,
-                        "inter_image_size": tuple(x.shape[-2:]), "image_size": image_size,
-                        "file_names": video.get("file_names", [""] * V)}]
+            targets = process_inference(video, tuple(x.shape[-2:]), image_size, self.num_frames)
         return self.inference_video(model, batched_inputs, x, image_size, targets)
 
     @torch.no_grad()

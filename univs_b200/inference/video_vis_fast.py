@@ -20,7 +20,7 @@ from ..modeling.decoder import COMBINED_DATASETS_CATEGORY_INFO
 from ..registry import is_cfg
 from ..streaming import ClipStream
 from . import rle
-from .comm import TemporalMaskMean, calculate_mask_quality_scores, match_from_learnable_embds
+from .comm import TemporalMaskMean, calculate_mask_quality_scores, match_from_learnable_embds, process_inference
 
 
 class InferenceVideoVISFast(nn.Module):
@@ -78,10 +78,7 @@ class InferenceVideoVISFast(nn.Module):
         if targets is None:
             # detection on a VIS dataset: visual prompt type without masks => learnable queries only
             # (prepare_targets.py:58-64, prompt_encoder.py:809-810)
-            targets = [{"task": video.get("task", "detection"), "dataset_name": dataset_name, "prompt_type": "visual",
-                        "video_len": len(video["image"]), "num_frames": self.num_frames,
-                        "inter_image_size": tuple(x.shape[-2:]), "image_size": image_size,
-                        "file_names": video.get("file_names", [""] * len(video["image"]))}]
+            targets = process_inference(video, tuple(x.shape[-2:]), image_size, self.num_frames)
         images = _Images(x, [image_size] * x.shape[0])
         return self.inference_video_vis_minvis(model, batched_inputs, images, targets)
 

@@ -15,7 +15,7 @@ from torch import nn
 from ..modeling.decoder import COMBINED_DATASETS_CATEGORY_INFO
 from ..registry import is_cfg
 from ..streaming import ClipStream
-from .comm import TemporalMaskMean, calculate_mask_quality_scores
+from .comm import TemporalMaskMean, calculate_mask_quality_scores, process_inference
 
 
 def match_from_embds(tgt_embds, cur_embds):
@@ -76,10 +76,7 @@ class InferenceVideoVPS(nn.Module):
             x = F.pad(x, (0, S - x.shape[-1], 0, S - x.shape[-2]), value=0.0)
         targets = video.get("targets")
         if targets is None:
-            targets = [{"task": video.get("task", "detection"), "dataset_name": dataset_name, "prompt_type": "visual",
-                        "video_len": len(video["image"]), "num_frames": self.num_frames,
-                        "inter_image_size": tuple(x.shape[-2:]), "image_size": image_size,
-                        "file_names": video.get("file_names", [""] * len(video["image"]))}]
+            targets = process_inference(video, tuple(x.shape[-2:]), image_size, self.num_frames)
         return self.inference_video_vps_online(model, batched_inputs, x, image_size, targets)
 
     # ------------------------------------------------------------------ clip loop + tracker (reference :209-293)
