@@ -18,6 +18,14 @@ import bench  # noqa: E402
 from oracle.cpu_backend import oracle_ops  # noqa: E402
 
 
+@pytest.fixture(autouse=True)
+def _restore_policy():
+    """bench.main() sets the process-wide arithmetic policy; put the library default back for the tests that follow"""
+    yield
+    from univs_b200.precision import set_precision
+    set_precision("fp32")
+
+
 class _Event:
     def __init__(self, enable_timing=False):
         self.t = None
