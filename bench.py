@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the UniVS per-clip forward hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ns|c2] [--precision fp32|tf32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ns|c2|c5] [--precision fp32|tf32]
 
 One step = one per-clip forward (normalise+pad -> Swin backbone -> MSDeformAttn pixel decoder -> UniVS decoder ->
 mask logits) over one synthetic clip.  Default workload = the configuration BASELINE.json's metric is quoted on:
@@ -26,6 +26,7 @@ WORKLOADS = {
     # name: (swin variant, T, H, W, Q)
     "ns": ("large", 5, 720, 1280, 200),      # north-star / metric configuration
     "c2": ("tiny", 5, 480, 864, 100),        # BASELINE.json configs[1]
+    "c5": ("large", 8, 1080, 1920, 200),     # BASELINE.json configs[4]: meant for --gpus 8 (one frame per GPU); fits one GPU too
 }
 
 
