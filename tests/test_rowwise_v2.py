@@ -1,5 +1,6 @@
-"""8-wide GELU / ReLU / operand-split kernel (csrc/elementwise.cu gelu_split8_kernel, opt-in UNIVS_ROWWISE_V2=1): must be
-BIT-identical to the validated gelu_split_kernel (same erff, same conversions).  The switch is read once per process, so
+"""8-wide GELU / ReLU / operand-split kernel (csrc/elementwise.cu gelu_split8_kernel, UNIVS_ROWWISE_V2 bit 0) and the
+wide-store LayerNorm (layernorm_wide_kernel, bit 1): must be BIT-identical to the validated gelu_split_kernel /
+layernorm_kernel (same erff, same reductions, same conversions).  The switch is read once per process, so
 the two variants run in two child processes and their outputs are compared byte for byte.
 Opt-in until it has run on a B200: UNIVS_GPU_ROWWISE_V2=1."""
 import os
@@ -26,6 +27,12 @@ for rows, C in [(1, 8), (37, 48), (1000, 192), (4600, 768), (333, 6144), (7, 204
         out[f"gelu_{rows}_{C}_{fmt}"] = ops.gelu(x, split=fmt, bias=b).cpu()
         out[f"relu_{rows}_{C}_{fmt}"] = ops.relu(x, split=fmt, bias=None).cpu()
         out[f"split_{rows}_{C}_{fmt}"] = ops.split_operand(x, fmt).cpu()
+        if C <= 4096:                                       # LayerNorm (+ residual + deferred bias), fp32 sum and operand
+            w, bb, r = torch.randn(C, device="cuda"), torch.randn(C, device="cuda"), torch.randn(rows, C, device="cuda")
+            ssum, y = ops.layernorm(x, w, bb, 1e-5, r, True, fmt, b)
+            out[f"ln_{rows}_{C}_{fmt}"] = y.cpu()
+            out[f"lnsum_{rows}_{C}_{fmt}"] = ssum.cpu()
+            out[f"ln_plain_{rows}_{C}_{fmt}"] = ops.layernorm(x, w, bb, 1e-5, None, False, fmt, None)[1].cpu()
 torch.cuda.synchronize()
 torch.save(out, sys.argv[1])
 """
@@ -36,11 +43,13 @@ torch.save(out, sys.argv[1])
 def test_rowwise_v2_bit_identical():
     with tempfile.TemporaryDirectory() as d:
         res = {}
-        for v2 in ("0", "1"):
+        for v2 in ("0", "3"):          # 3 = bit 0 (GELU / ReLU / split) + bit 1 (wide-store LayerNorm)
             path = os.path.join(d, f"v{v2}.pt")
             env = dict(os.environ, UNIVS_ROWWISE_V2=v2)
             subprocess.run([sys.executable, "-c", _CHILD, path, ROOT], check=True, env=env, timeout=600)
             res[v2] = torch.load(path)
-    assert res["0"].keys() == res["1"].keys() and len(res["0"]) == 36
+    assert res["0"].keys() == res["3"].keys() and len(res["0"]) == 36 + 30
     for k in res["0"]:
-        assert torch.equal(res["0"][k].view(torch.int16), res["1"][k].view(torch.int16)), k
+        a, b = res["0"][k], res["3"][k]
+        assert a.dtype == b.dtype and a.shape == b.shape, k
+        assert torch.equal(a.contiguous().view(torch.int16), b.contiguous().view(torch.int16)), k

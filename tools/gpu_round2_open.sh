@@ -31,16 +31,16 @@ UNIVS_GPU_HEADS=1 run heads_tests 900 python -m pytest tests/test_heads_golden.p
 run bench_default 900 python bench.py --steps 10 --warmup 3
 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 run bench_glue 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_WIN_TC=1 run bench_wintc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
-UNIVS_ROWWISE_V2=1 run bench_rowwise_v2 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+UNIVS_ROWWISE_V2=3 run bench_rowwise_v2 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_FRAME_STREAMS=2 run bench_streams2 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_FRAME_STREAMS=5 run bench_streams5 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_POOLED_MASKS=1 run bench_pooled_masks 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_EINSUM_MC=1 run bench_einsum_mc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_MHA_TC=1 run bench_mhatc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
-UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 UNIVS_POOLED_MASKS=1 run bench_all 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=3 UNIVS_EINSUM_MC=1 UNIVS_POOLED_MASKS=1 run bench_all 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run bench_video 900 python bench.py --steps 2 --video-frames 12
 # 3. end-to-end parity of the opt-in paths at the north-star geometry (T=2): same tool and thresholds as round 1
-PARITY_MODES=fp16x3 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=1 UNIVS_POOLED_MASKS=1 run parity_at_scale 1200 python tests/tools/parity_at_scale.py
+PARITY_MODES=fp16x3 UNIVS_FUSED_GLUE=1 UNIVS_MSDA_TILE=8 UNIVS_WIN_TC=1 UNIVS_MHA_TC=1 UNIVS_ROWWISE_V2=3 UNIVS_EINSUM_MC=1 UNIVS_POOLED_MASKS=1 run parity_at_scale 1200 python tests/tools/parity_at_scale.py
 # 4. the prompt configurations of BASELINE.json at full geometry (default path): C3 sot memory over 3 clips, C4 grounding, C5 1080p
 PARITY_CONFIG=c3 run parity_c3 900 python tests/tools/parity_configs.py
 PARITY_CONFIG=c4 run parity_c4 900 python tests/tools/parity_configs.py

@@ -14,7 +14,7 @@ DEFAULTS = {
     "MSDA_TILE": 0,         # ops: tiled MSDeformAttn encoder kernel (tile width, 0 = untiled)
     "WIN_TC": 0,            # ops: tcgen05 window attention for 12x12 windows
     "MHA_TC": 0,            # ops: tcgen05 cross-attention (1; 3 = transposed-V diagnostic variant)
-    "ROWWISE_V2": 0,        # csrc/elementwise.cu: 8-wide GELU / ReLU / operand split
+    "ROWWISE_V2": 0,        # csrc/elementwise.cu: bit 0 = 8-wide GELU / ReLU / operand split, bit 1 = wide-store LayerNorm
     "EINSUM_MC": 0,         # ops: cluster / TMA-multicast mask einsum (E resident per CTA pair)
     "POOLED_MASKS": 0,      # decoder: intermediate heads from pooled mask features
     "SHARD_DECODER": 0,     # meta_arch: frame-sharded decoder with token exchange (N > 1)
@@ -44,4 +44,4 @@ def active() -> dict:
 def export_native():
     """the C side reads UNIVS_ROWWISE_V2 with getenv at its first launch: make tuned.json visible to it"""
     if get("ROWWISE_V2") and os.environ.get("UNIVS_ROWWISE_V2") is None:
-        os.environ["UNIVS_ROWWISE_V2"] = "1"
+        os.environ["UNIVS_ROWWISE_V2"] = str(get("ROWWISE_V2"))
