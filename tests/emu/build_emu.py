@@ -1,0 +1,102 @@
+"""Builds tests/emu/_build/libunivs_emu.so: the plain CUDA kernels of univs_b200/csrc compiled by g++ for CPU execution
+(tests/emu/cuda_emu.h).  The only source transformation is the launch syntax:
+    kernel<<<grid, block, smem, stream>>>(args);   ->   ::emu::launch(dim3(grid), dim3(block), [=]() { kernel(args); });
+Everything else -- kernels, argument validation, the extern "C" entry points -- is compiled as written."""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "univs_b200", "csrc")
+BUILD = os.path.join(HERE, "_build")
+SOURCES = ["common.cu", "groupnorm.cu", "swin_glue.cu", "decoder_glue.cu", "elementwise.cu", "msda.cu"]
+HEADERS = ["common.cuh", "rowwise.cuh"]
+CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
+
+
+def _matching(text, start, open_ch, close_ch):
+    """index just past the bracket that closes the one at text[start]"""
+    depth = 0
+    for i in range(start, len(text)):
+        if text[i] == open_ch:
+            depth += 1
+        elif text[i] == close_ch:
+            depth -= 1
+            if depth == 0:
+                return i + 1
+    raise ValueError("unbalanced brackets")
+
+
+def _split_top(s):
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{<" and not (ch == "<" and depth == 0 and False):
+            depth += ch in "([{"
+        if ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+def rewrite_launches(text):
+    out, pos = "", 0
+    while True:
+        i = text.find("<<<", pos)
+        if i < 0:
+            return out + text[pos:]
+        # kernel expression: identifier, optionally with template arguments, right before <<<
+        j = i
+        if text[j - 1] == ">":                     # name<...>
+            depth = 0
+            while True:
+                j -= 1
+                if text[j] == ">":
+                    depth += 1
+                elif text[j] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+        while j > 0 and (text[j - 1].isalnum() or text[j - 1] in "_:"):
+            j -= 1
+        kernel = text[j:i]
+        k = text.find(">>>", i)
+        cfg = _split_top(text[i + 3:k])
+        a0 = text.index("(", k)
+        a1 = _matching(text, a0, "(", ")")
+        args = text[a0 + 1:a1 - 1]
+        out += text[pos:j] + f"::emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), [=]() {{ {kernel}({args}); }})"
+        pos = a1
+
+
+def build(force=False):
+    os.makedirs(BUILD, exist_ok=True)
+    lib = os.path.join(BUILD, "libunivs_emu.so")
+    inputs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "build_emu.py")]
+    if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(p) for p in inputs):
+        return lib
+    gen = []
+    for f in HEADERS:       # headers are used as they are (UNIVS_CPU_EMU selects host versions of the two PTX helpers)
+        with open(os.path.join(CSRC, f)) as src, open(os.path.join(BUILD, f), "w") as dst:
+            dst.write(src.read().replace('#include "../../include/univs_b200.h"', f'#include "{ROOT}/include/univs_b200.h"'))
+    for f in SOURCES:
+        with open(os.path.join(CSRC, f)) as src:
+            text = rewrite_launches(src.read())
+        path = os.path.join(BUILD, f.replace(".cu", "_emu.cpp"))
+        with open(path, "w") as dst:
+            dst.write(text)
+        gen.append(path)
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-DUNIVS_CPU_EMU", f"-I{CUDA_INCLUDE}", f"-I{BUILD}",
+           f"-I{HERE}", "-include", os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_emu.cpp"), *gen, "-o", lib]
+    subprocess.run(cmd, check=True)
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

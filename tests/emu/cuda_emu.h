@@ -1,0 +1,143 @@
+// CPU execution of the plain CUDA kernels of univs_b200/csrc (TEST INFRASTRUCTURE, tests/test_kernels_cpu_emulation.py).
+// The kernel SOURCES are compiled unchanged by g++ (tests/emu/build_emu.py rewrites only the <<<...>>> launch syntax):
+// every CUDA thread of a block is a host thread, __syncthreads / warp shuffles / ballots are barriers over them, shared
+// memory is a function-local static (blocks run one after the other), atomics take a lock.  What this checks is the
+// kernels' index arithmetic, predication, reductions and output formats against the oracle -- not performance and not
+// the hardware.  Kernels built on tcgen05 / TMA / mma.sync / cp.async are outside its reach.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __launch_bounds__(...)
+#undef __shared__
+#define __shared__ static
+
+namespace emu {
+
+struct Barrier {          // reusable barrier whose participants may leave (a CUDA thread that returned no longer takes part)
+  std::mutex m;
+  std::condition_variable cv;
+  int expected = 0, arrived = 0;
+  unsigned long long gen = 0;
+  void wait() {
+    std::unique_lock<std::mutex> l(m);
+    const unsigned long long g = gen;
+    if (++arrived >= expected) {
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+    } else {
+      cv.wait(l, [&] { return gen != g; });
+    }
+  }
+  void drop() {
+    std::unique_lock<std::mutex> l(m);
+    --expected;
+    if (expected > 0 && arrived >= expected) {
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+    }
+  }
+};
+struct Warp {
+  Barrier bar;
+  uint32_t slot[32];
+};
+struct Ctx {
+  uint3 tid, bid;
+  dim3 bdim, gdim;
+  Barrier* block_bar;
+  Warp* warp;
+  int lane;
+};
+extern thread_local Ctx ctx;
+extern std::mutex atomic_lock;
+
+void launch(dim3 grid, dim3 block, const std::function<void()>& body);
+
+inline uint32_t exchange(uint32_t v, int src_lane) {
+  Warp* w = ctx.warp;
+  w->slot[ctx.lane] = v;
+  w->bar.wait();
+  const uint32_t r = (src_lane >= 0 && src_lane < 32) ? w->slot[src_lane] : v;
+  w->bar.wait();
+  return r;
+}
+template <typename T>
+inline T shfl(T v, int src_lane) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  u = exchange(u, src_lane);
+  std::memcpy(&v, &u, 4);
+  return v;
+}
+
+}  // namespace emu
+
+#define threadIdx (::emu::ctx.tid)
+#define blockIdx (::emu::ctx.bid)
+#define blockDim (::emu::ctx.bdim)
+#define gridDim (::emu::ctx.gdim)
+
+inline void __syncthreads() { ::emu::ctx.block_bar->wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { ::emu::ctx.warp->bar.wait(); }
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return ::emu::shfl(v, ::emu::ctx.lane ^ lane_mask); }
+template <typename T>
+inline T __shfl_down_sync(unsigned, T v, int delta) {
+  const int src = ::emu::ctx.lane + delta;
+  return ::emu::shfl(v, src < 32 ? src : ::emu::ctx.lane);
+}
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src) { return ::emu::shfl(v, src & 31); }
+inline unsigned __ballot_sync(unsigned, int pred) {
+  ::emu::Warp* w = ::emu::ctx.warp;
+  w->slot[::emu::ctx.lane] = pred ? 1u : 0u;
+  w->bar.wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= (w->slot[i] & 1u) << i;
+  w->bar.wait();
+  return r;
+}
+template <typename T>
+inline T atomicAdd(T* p, T v) {
+  std::lock_guard<std::mutex> l(::emu::atomic_lock);
+  const T old = *p;
+  *p = old + v;
+  return old;
+}
+inline int atomicOr(int* p, int v) {
+  std::lock_guard<std::mutex> l(::emu::atomic_lock);
+  const int old = *p;
+  *p = old | v;
+  return old;
+}
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+template <typename T>
+inline void __stcs(T* p, T v) { *p = v; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+inline float __expf(float x) { return std::exp(x); }
+inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
+template <typename T>
+inline T min(T a, T b) { return a < b ? a : b; }
+template <typename T>
+inline T max(T a, T b) { return a > b ? a : b; }
+inline long long min(long long a, int b) { return a < b ? a : b; }
+inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }

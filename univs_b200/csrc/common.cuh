@@ -21,9 +21,14 @@ int check_launch(const char* what);
 
 // ---- TF32 helpers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t f2tf32(float x) {
+#ifdef UNIVS_CPU_EMU      // tests/emu: round to nearest, ties away from zero, to 10 explicit significand bits
+  const uint32_t u = __float_as_uint(x);
+  return ((u & 0x7f800000u) == 0x7f800000u) ? u : ((u + 0x1000u) & 0xffffe000u);
+#else
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
+#endif
 }
 // big/small split: x ~= big + small, both exactly representable in TF32
 __device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& small) {
