@@ -11,8 +11,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "univs_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
-SOURCES = ["common.cu", "groupnorm.cu", "swin_glue.cu", "decoder_glue.cu", "elementwise.cu", "msda.cu"]
-HEADERS = ["common.cuh", "rowwise.cuh"]
+SOURCES = ["common.cu", "groupnorm.cu", "swin_glue.cu", "decoder_glue.cu", "elementwise.cu", "msda.cu",
+           "swin_window_attn_tc.cu", "mha_tc.cu", "mha_combine_emu.cu"]
+HEADERS = ["common.cuh", "rowwise.cuh", "tc05_math.cuh"]      # tc05.cuh itself is replaced by tests/emu/tc05.cuh
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 
 
@@ -78,7 +79,7 @@ def rewrite_launches(text):
 def build(force=False):
     os.makedirs(BUILD, exist_ok=True)
     lib = os.path.join(BUILD, "libunivs_emu.so")
-    inputs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "build_emu.py")]
+    inputs = [os.path.join(CSRC, "mha.cu" if f == "mha_combine_emu.cu" else f) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc05.cuh", "build_emu.py")]
     if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(p) for p in inputs):
         return lib
     gen = []
@@ -86,14 +87,26 @@ def build(force=False):
         with open(os.path.join(CSRC, f)) as src, open(os.path.join(BUILD, f), "w") as dst:
             dst.write(src.read().replace('#include "../../include/univs_b200.h"', f'#include "{ROOT}/include/univs_b200.h"'))
     for f in SOURCES:
-        with open(os.path.join(CSRC, f)) as src:
-            text = rewrite_launches(src.read())
+        if f == "mha_combine_emu.cu":
+            # mha.cu as a whole is out of reach (mma.sync / cp.async kernels); the tcgen05 cross-attention needs only its
+            # split-K merge: the combine kernel and its launcher, cut out of the file as they are written
+            whole = open(os.path.join(CSRC, "mha.cu")).read()
+            k0 = whole.index("// merge split-K partials")
+            k1 = whole.index("// ---- ProCA")
+            l0 = whole.index("// split-K merge for the tensor-core kernel")
+            l1 = whole.index("}  // namespace univs", l0)
+            raw = '#include <math.h>\n#include "common.cuh"\nnamespace univs {\n' + whole[k0:k1] + whole[l0:l1] + "}  // namespace univs\n"
+        else:
+            raw = open(os.path.join(CSRC, f)).read()
+        if True:
+            text = rewrite_launches(raw)
+            # dynamic shared memory: one emulated buffer per CTA
+            text = re.sub(r"extern __shared__ __align__\(\d+\) unsigned char (\w+)\[\];", r"unsigned char* \1 = ::emu::dyn_smem();", text)
         path = os.path.join(BUILD, f.replace(".cu", "_emu.cpp"))
         with open(path, "w") as dst:
             dst.write(text)
         gen.append(path)
-    cmd = ["g++", "-std=c++20", "-O1", "-w", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-DUNIVS_CPU_EMU", f"-I{CUDA_INCLUDE}", f"-I{BUILD}",
-           f"-I{HERE}", "-include", os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_emu.cpp"), *gen, "-o", lib]
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-DUNIVS_CPU_EMU", f"-I{CUDA_INCLUDE}", f"-I{HERE}", f"-I{BUILD}", "-include", os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_emu.cpp"), *gen, "-o", lib]
     subprocess.run(cmd, check=True)
     return lib
 

@@ -141,3 +141,6 @@ template <typename T>
 inline T max(T a, T b) { return a > b ? a : b; }
 inline long long min(long long a, int b) { return a < b ? a : b; }
 inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
+// kernel attributes are meaningless here (nvcc offers this overload for __global__ functions)
+template <typename R, typename... A>
+inline cudaError_t cudaFuncSetAttribute(R (*)(A...), cudaFuncAttribute, int) { return cudaSuccess; }

@@ -1,0 +1,122 @@
+"""The tcgen05 attention kernels (csrc/swin_window_attn_tc.cu, csrc/mha_tc.cu -- written after the round's GPU budget was
+spent, never run on hardware) EXECUTED ON THE CPU: their sources are compiled unchanged by g++ against a CPU implementation
+of csrc/tc05.cuh (tests/emu/tc05.cuh: mbarriers with phases and transaction counts, tcgen05.mma reading emulated shared
+memory through the matrix descriptors -- start address, stride byte offset, swizzle on the absolute address, K-major and
+MN-major operands --, TMEM with the 32-lanes-per-warp access rule, named barriers) and driven through the real
+`univs_b200.ops` wrappers, against the oracle.  512 / 448 host threads play the CUDA threads of a CTA, so the kernels'
+own warp specialisation, pipelining and barrier protocol run as written (shared memory and TMEM start NaN-filled: using
+anything that was not produced first is visible).
+
+This checks the kernels' logic under the modelled hardware semantics (the ones the kernels were written against, taken from
+the PTX ISA tables restated in CuTe) -- loader addressing, operand tiles and descriptors, accumulator placement, softmax,
+tail-tile handling, split-K partials, the barrier protocol -- not the hardware itself and not performance."""
+import os
+import shutil
+
+import pytest
+import torch
+
+from oracle import cpu_backend, ops_ref
+from tests.emu import build_emu
+from tests.test_kernels_cpu_emulation import _load, dev, plain
+from univs_b200 import _cabi, ops
+
+if shutil.which("g++") is None or not os.path.exists(os.path.join(build_emu.CUDA_INCLUDE, "cuda_runtime.h")):
+    pytest.skip("needs g++ and the CUDA headers", allow_module_level=True)
+
+
+@pytest.fixture(scope="module")
+def emu_lib_path():
+    return build_emu.build()
+
+
+def _use(monkeypatch, path, sms, tmp_path):
+    """a private copy of the emulated library whose launchers see `sms` SMs (they cache the count): few SMs make the
+    persistent CTAs walk many work units each"""
+    copy = str(tmp_path / f"libunivs_emu_{sms}.so")
+    shutil.copy(path, copy)
+    monkeypatch.setenv("UNIVS_EMU_SMS", str(sms))
+    monkeypatch.setattr(_cabi, "_lib", _load(copy))
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops, "_ws_cache", {})
+
+
+def _rel(a, b):
+    a, b = plain(a).float(), plain(b).float()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
+
+
+@pytest.mark.parametrize("B,H,W,nH,shift,sms", [
+    (1, 24, 24, 2, 0, 148),      # 8 units, one per CTA
+    (2, 24, 36, 2, 6, 3),        # 24 units over 3 persistent CTAs: ring reuse, barrier phases beyond the first wrap
+    (1, 20, 30, 1, 6, 2),        # padded grid (20x30 -> 24x36): pad tokens carry the bias only; shifted + masked windows
+    (1, 12, 12, 3, 0, 1),        # a single window, three heads on one CTA
+])
+def test_window_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, B, H, W, nH, shift, sms):
+    _use(monkeypatch, emu_lib_path, sms, tmp_path)
+    g = torch.Generator().manual_seed(B * 1000 + H + shift)
+    C = nH * 32
+    qkv = torch.randn(B, H, W, 3 * C, generator=g)
+    bias = torch.randn(3 * C, generator=g) * 0.2
+    table = torch.randn(23 * 23, nH, generator=g) * 0.5
+    out, op = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, shift, want_f32=True, want_operand=True)
+    want = ops_ref.swin_window_attention(qkv, bias, table, nH, 12, shift)
+    assert _rel(out, want) < 5e-6
+    # the fp16x3 operand of the projection GEMM [lo * 2^11 | hi * 2^-11 | hi]
+    op = plain(op).float()
+    rec = op[..., 2 * C:] + op[..., :C] / 2048.0
+    assert _rel(rec, want) < 5e-6
+    assert torch.equal(plain(out).half().float(), op[..., 2 * C:])
+    # operand-only and fp32-only calls produce the same values
+    only16 = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, shift, want_f32=False, want_operand=True)[1]
+    assert torch.equal(plain(only16).float(), op)
+
+
+def test_window_attention_tc_score_dump(monkeypatch, emu_lib_path, tmp_path):
+    """the staged diagnostic of tests/tools/win_tc_check.py: the debug dump holds the raw scores q.k * scale per unit"""
+    _use(monkeypatch, emu_lib_path, 2, tmp_path)
+    g = torch.Generator().manual_seed(3)
+    nH, C = 1, 32
+    qkv, bias, table = torch.randn(1, 12, 24, 3 * C, generator=g), torch.randn(3 * C, generator=g) * 0.2, torch.randn(529, nH, generator=g)
+    out, _, dbg = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, 0, debug_scores=True)
+    want, scores = ops_ref.swin_window_attention(qkv, bias, table, nH, 12, 0, return_scores=True)
+    assert _rel(out, want) < 5e-6
+    assert plain(dbg).shape == (2, 144, 144)
+    assert _rel(plain(dbg).reshape(scores.shape), scores) < 5e-6
+
+
+def _mask_case(g, B, Lq, Lk):
+    mask = torch.rand(B, Lq, Lk, generator=g) < 0.4
+    mask[0, 1] = True                                   # fully blocked row: ignores its mask (row_open = 0)
+    mask[0, 2, :-1] = True                              # only the last key open
+    words = (Lk + 31) // 32
+    padded = torch.zeros(B, Lq, words * 32, dtype=torch.int64)
+    padded[..., :Lk] = mask.long()
+    bits = (padded.view(B, Lq, words, 32) << torch.arange(32)).sum(-1)
+    bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+    row_open = (~mask.all(-1)).to(torch.int32)
+    return mask, bits, row_open
+
+
+@pytest.mark.parametrize("B,Lq,Lk,heads,sms,masked", [
+    (1, 40, 300, 2, 148, True),      # one row tile in use, 3 key blocks (the last partial), split over many CTAs + combine
+    (2, 200, 520, 1, 2, True),       # both row tiles, 5 key blocks on one CTA each: the 3-stage ring wraps
+    (1, 256, 128, 2, 1, False),      # Lq at the limit, one key block, no mask
+    (1, 7, 1100, 1, 4, True),        # few queries, 9 key blocks, split-K with uneven splits
+])
+@pytest.mark.parametrize("flags", [0, 1])        # 1 = transposed-V (K-major) diagnostic variant
+def test_cross_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, B, Lq, Lk, heads, sms, masked, flags):
+    _use(monkeypatch, emu_lib_path, sms, tmp_path)
+    g = torch.Generator().manual_seed(Lq + Lk)
+    C = heads * 32
+    q, k, v = (torch.randn(B, L, C, generator=g) for L in (Lq, Lk, Lk))
+    k = k * 1.5
+    mask = bits = row_open = None
+    if masked:
+        mask, bits, row_open = _mask_case(g, B, Lq, Lk)
+    got = ops.mha_core_tc(dev(q), dev(k), dev(v), dev(bits), dev(row_open), flags=flags)
+    want = ops_ref.mha_core(q, k, v, heads, mask, unmask_full_rows=masked)
+    assert _rel(got, want) < 5e-6
+    if masked:      # the two special rows, exactly as the reference's rule (..._univs.py:390) treats them
+        full = ops_ref.mha_core(q[:1, 1:2], k[:1], v[:1], heads)
+        assert _rel(plain(got)[:1, 1:2], full) < 5e-6
