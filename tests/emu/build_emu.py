@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "univs_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 SOURCES = ["common.cu", "groupnorm.cu", "swin_glue.cu", "decoder_glue.cu", "elementwise.cu", "msda.cu",
-           "swin_window_attn_tc.cu", "mha_tc.cu", "mha_combine_emu.cu"]
+           "swin_window_attn_tc.cu", "mha_tc.cu", "mha_combine_emu.cu", "mask_einsum_mc.cu", "mask_einsum_tc.cu", "einsum_entry_emu.cu"]
 HEADERS = ["common.cuh", "rowwise.cuh", "tc05_math.cuh"]      # tc05.cuh itself is replaced by tests/emu/tc05.cuh
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 
@@ -76,10 +76,26 @@ def rewrite_launches(text):
         pos = a1
 
 
+def rewrite_launch_ex(text):
+    """cudaLaunchKernelEx(&cfg, kernel, args...)  ->  ::emu::launch_ex(cfg, [=]() { kernel(args...); })"""
+    out, pos = "", 0
+    while True:
+        i = text.find("cudaLaunchKernelEx(", pos)
+        if i < 0:
+            return out + text[pos:]
+        a0 = text.index("(", i)
+        a1 = _matching(text, a0, "(", ")")
+        parts = _split_top(text[a0 + 1:a1 - 1])
+        cfg, kernel, args = parts[0].lstrip("&"), parts[1], ", ".join(parts[2:])
+        out += text[pos:i] + f"::emu::launch_ex({cfg}, [=]() {{ {kernel}({args}); }})"
+        pos = a1
+
+
 def build(force=False):
     os.makedirs(BUILD, exist_ok=True)
     lib = os.path.join(BUILD, "libunivs_emu.so")
-    inputs = [os.path.join(CSRC, "mha.cu" if f == "mha_combine_emu.cu" else f) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc05.cuh", "build_emu.py")]
+    alias = {"mha_combine_emu.cu": "mha.cu", "einsum_entry_emu.cu": "mask_einsum.cu"}
+    inputs = [os.path.join(CSRC, alias.get(f, f)) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc05.cuh", "build_emu.py")]
     if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(p) for p in inputs):
         return lib
     gen = []
@@ -96,10 +112,50 @@ def build(force=False):
             l0 = whole.index("// split-K merge for the tensor-core kernel")
             l1 = whole.index("}  // namespace univs", l0)
             raw = '#include <math.h>\n#include "common.cuh"\nnamespace univs {\n' + whole[k0:k1] + whole[l0:l1] + "}  // namespace univs\n"
+        elif f == "mask_einsum_tc.cu":
+            # the kernel that IS validated on the B200 keeps private copies of its PTX wrappers; for the emulator they are
+            # swapped for tests/emu/tc05.cuh (same names, two of them with another spelling) -- the calibration case of the
+            # emulated TMA / descriptor / TMEM semantics.  Any pattern that no longer matches fails the build.
+            whole = open(os.path.join(CSRC, f)).read()
+            w0 = whole.index("__device__ __forceinline__ uint32_t smem_u32(const void* p)")
+            w1 = whole.index("// F16X3 == false: fp32 operands consumed as TF32")
+            shim = ("using namespace tc;\n"
+                    "__device__ __forceinline__ void tc_fence_before() {}\n__device__ __forceinline__ void tc_fence_after() {}\n"
+                    "__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {\n"
+                    "  tc::tma_load_3d(smem_u32(dst), map, bar, c0, c1, c2);\n}\n"
+                    "#define TMEM_LD_32x32b_X32(taddr, r) UNIVS_TMEM_LD_X32(taddr, r)\n")
+            raw = whole[:w0] + shim + whole[w1:]
+            raw = raw.replace('#include "common.cuh"', '#include "tc05.cuh"', 1)
+            for old, new in [
+                ('asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");', "mbar_init_fence();"),
+                ('asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));',
+                 "tmem_alloc(tmem_slot, 512);"),
+                ('asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");', ""),
+                ('asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");', "tmem_wait_ld();"),
+                ('asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));', "tmem_dealloc(tmem_base, 512);"),
+            ]:
+                assert raw.count(old) == 1, old
+                raw = raw.replace(old, new)
+            assert "asm" not in raw.replace("namespace", ""), "unexpected inline assembly left in mask_einsum_tc.cu"
+        elif f == "einsum_entry_emu.cu":
+            # mask_einsum.cu holds the mma.sync kernel (out of reach); the cluster kernel needs only its argument check and
+            # its extern "C" entry point, cut out of the file as they are written
+            whole = open(os.path.join(CSRC, "mask_einsum.cu")).read()
+            c0 = whole.index("static int check_einsum_args(")
+            c1 = whole.index("\n}\n", c0) + 3
+            entries = ""
+            for name in ("univs_mask_einsum_f32", "univs_mask_einsum_f16x3", "univs_mask_einsum_f16x3_cluster"):
+                e0 = whole.index(f'extern "C" int {name}(')
+                entries += whole[e0:whole.index("\n}\n", e0) + 3]
+            raw = ('#include "common.cuh"\nnamespace univs {\n'
+                   'int launch_mask_einsum_tc(cudaStream_t st, const float* E, const float* F, int T, int Q, int C, int HW, float* out);\n'
+                   'int launch_mask_einsum_tc_f16(cudaStream_t st, const void* E16, const void* F16, int T, int Q, int C, int HW, float* out);\n'
+                   'int launch_mask_einsum_mc_f16(cudaStream_t st, const void* E16, const void* F16, int T, int Q, int C, int HW, float* out);\n'
+                   '}\nusing namespace univs;\n' + whole[c0:c1] + entries)
         else:
             raw = open(os.path.join(CSRC, f)).read()
         if True:
-            text = rewrite_launches(raw)
+            text = rewrite_launch_ex(rewrite_launches(raw))
             # dynamic shared memory: one emulated buffer per CTA
             text = re.sub(r"extern __shared__ __align__\(\d+\) unsigned char (\w+)\[\];", r"unsigned char* \1 = ::emu::dyn_smem();", text)
         path = os.path.join(BUILD, f.replace(".cu", "_emu.cpp"))

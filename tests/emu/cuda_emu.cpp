@@ -15,21 +15,33 @@ namespace emu {
 thread_local Ctx ctx;
 std::mutex atomic_lock;
 
-// ---- per-CTA state of the tensor-core emulation (blocks run one after the other) ---------------------------------------
+// ---- per-CTA state of the tensor-core emulation (the CTAs of one cluster run concurrently, clusters one after the other)
 static constexpr size_t kSmemBytes = 232448;                       // 227 KB
-alignas(1024) static unsigned char g_smem[kSmemBytes + 1024];
-static float g_tmem[128 * 512];
-static std::map<const void*, MBar> g_mbars;
+static constexpr int kMaxCluster = 2;
+struct CtaState {
+  alignas(1024) unsigned char smem[kSmemBytes + 1024];
+  float tmem[128 * 512];
+  std::map<const void*, MBar> mbars;
+  std::map<int, std::unique_ptr<Barrier>> named;
+};
+static CtaState g_cta[kMaxCluster];
 static std::mutex g_mbar_lock, g_named_lock;
-static std::map<int, std::unique_ptr<Barrier>> g_named;
+static int g_wait_id[kMaxCluster][1024], g_wait_parity[kMaxCluster][1024];
 
-unsigned char* dyn_smem() { return g_smem; }
-float* tmem() { return g_tmem; }
-MBar& mbar_of(const void* p) { return g_mbars[p]; }
+unsigned char* dyn_smem() { return g_cta[ctx.cta].smem; }
+unsigned char* dyn_smem_of(int cta) { return g_cta[cta].smem; }
+float* tmem() { return g_cta[ctx.cta].tmem; }
+MBar& mbar_of(const void* p) {                                     // the barrier lives in the CTA whose shared memory holds it
+  for (int c = 0; c < kMaxCluster; ++c) {
+    const unsigned char* b = g_cta[c].smem;
+    if (p >= (const void*)b && p < (const void*)(b + sizeof(g_cta[c].smem))) return g_cta[c].mbars[p];
+  }
+  fail("mbarrier outside shared memory");
+}
 std::mutex& mbar_lock() { return g_mbar_lock; }
 Barrier& named_barrier(int id, int threads) {
   std::lock_guard<std::mutex> l(g_named_lock);
-  auto& b = g_named[id];
+  auto& b = g_cta[ctx.cta].named[id];
   if (!b) {
     b.reset(new Barrier());
     b->expected = threads;
@@ -37,11 +49,10 @@ Barrier& named_barrier(int id, int threads) {
   if (b->expected != threads) fail("bar.sync: the same barrier id used with two thread counts");
   return *b;
 }
-static int g_wait_id[1024], g_wait_parity[1024];
 void note_wait(int thread, int id, int parity) {
   if (thread >= 0 && thread < 1024) {
-    g_wait_id[thread] = id;
-    g_wait_parity[thread] = parity;
+    g_wait_id[ctx.cta][thread] = id;
+    g_wait_parity[ctx.cta][thread] = parity;
   }
 }
 void dump_waits() {
@@ -50,20 +61,23 @@ void dump_waits() {
   std::lock_guard<std::mutex> l(once);
   if (done) return;
   done = true;
-  std::string out = "emu: threads waiting on mbarriers (id/parity: threads):";
-  std::map<std::pair<int, int>, std::string> groups;
-  for (int t = 0; t < 1024; ++t)
-    if (g_wait_id[t] >= 0) groups[{g_wait_id[t], g_wait_parity[t]}] += " " + std::to_string(t);
-  for (auto& kv : groups) out += "\n  " + std::to_string(kv.first.first) + "/" + std::to_string(kv.first.second) + ":" + kv.second;
-  out += "\nemu: mbarrier states (index: count pending tx phase):";
-  {
+  std::string out;
+  for (int c = 0; c < kMaxCluster; ++c) {
+    std::map<std::pair<int, int>, std::string> groups;
+    for (int t = 0; t < 1024; ++t)
+      if (g_wait_id[c][t] >= 0) groups[{g_wait_id[c][t], g_wait_parity[c][t]}] += " " + std::to_string(t);
+    if (groups.empty() && g_cta[c].mbars.empty()) continue;
+    out += "emu: CTA " + std::to_string(c) + ": threads waiting on mbarriers (id/parity: threads):";
+    for (auto& kv : groups) out += "\n  " + std::to_string(kv.first.first) + "/" + std::to_string(kv.first.second) + ":" + kv.second;
+    out += "\nemu: CTA " + std::to_string(c) + ": mbarrier states (index: count pending tx phase):";
     std::lock_guard<std::mutex> l2(g_mbar_lock);
     int i = 0;
-    for (auto& kv : g_mbars)
+    for (auto& kv : g_cta[c].mbars)
       out += " [" + std::to_string(i++) + "] " + std::to_string(kv.second.count) + "/" + std::to_string(kv.second.pending) + "/" +
              std::to_string(kv.second.tx) + "/" + std::to_string(kv.second.phase);
+    out += "\n";
   }
-  std::fprintf(stderr, "%s\n", out.c_str());
+  std::fprintf(stderr, "%s", out.c_str());
   std::fflush(stderr);
 }
 void fail(const char* what) {
@@ -71,45 +85,85 @@ void fail(const char* what) {
   std::fflush(stderr);
   std::abort();
 }
-static void reset_cta_state() {
-  std::memset(g_smem, 0xFF, sizeof(g_smem));                       // fp16 / fp32 NaN patterns: unwritten data is visible
-  std::memset(g_tmem, 0xFF, sizeof(g_tmem));
-  g_mbars.clear();
-  g_named.clear();
-  for (int t = 0; t < 1024; ++t) g_wait_id[t] = -1;
+CUresult encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                      CUtensorMapSwizzle swizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  if (rank != 3 || il != CU_TENSOR_MAP_INTERLEAVE_NONE || estr[0] != 1 || estr[1] != 1 || estr[2] != 1) return CUDA_ERROR_INVALID_VALUE;
+  TensorMap t;
+  std::memset(&t, 0, sizeof(t));
+  t.magic = 0x554e495653ull;
+  t.base = static_cast<const unsigned char*>(base);
+  t.esize = dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT16 ? 2 : (dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 4 : 0);
+  t.swizzle_bits = swizzle == CU_TENSOR_MAP_SWIZZLE_128B ? 3 : (swizzle == CU_TENSOR_MAP_SWIZZLE_64B ? 2 : (swizzle == CU_TENSOR_MAP_SWIZZLE_32B ? 1 : 0));
+  if (t.esize == 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return CUDA_ERROR_INVALID_VALUE;
+  for (int i = 0; i < 3; ++i) {
+    t.dims[i] = dims[i];
+    t.box[i] = box[i];
+    if (box[i] == 0 || box[i] > 256) return CUDA_ERROR_INVALID_VALUE;
+  }
+  for (int i = 0; i < 2; ++i) {
+    t.strides[i] = strides[i];
+    if (strides[i] % 16) return CUDA_ERROR_INVALID_VALUE;          // global strides must be multiples of 16 bytes
+  }
+  t.rank = 3;
+  std::memset(m, 0, sizeof(*m));
+  std::memcpy(m, &t, sizeof(t));
+  return CUDA_SUCCESS;
+}
+int emulated_sm_count() {
+  const char* e = std::getenv("UNIVS_EMU_SMS");      // few "SMs": persistent kernels walk many work units per CTA
+  return (e != nullptr && std::atoi(e) > 0) ? std::atoi(e) : 148;
+}
+static void reset_cta_state(int c) {
+  std::memset(g_cta[c].smem, 0xFF, sizeof(g_cta[c].smem));         // fp16 / fp32 NaN patterns: unwritten data is visible
+  std::memset(g_cta[c].tmem, 0xFF, sizeof(g_cta[c].tmem));
+  g_cta[c].mbars.clear();
+  g_cta[c].named.clear();
+  for (int t = 0; t < 1024; ++t) g_wait_id[c][t] = -1;
 }
 
-void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+void launch(dim3 grid, dim3 block, const std::function<void()>& body, int cluster) {
   const int nthreads = (int)(block.x * block.y * block.z);
   const int nwarps = (nthreads + 31) / 32;
+  if (cluster < 1 || cluster > kMaxCluster || grid.x % cluster) fail("launch: unsupported cluster shape");
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        reset_cta_state();
-        Barrier block_bar;
-        block_bar.expected = nthreads;
-        std::vector<Warp> warps(nwarps);
-        for (int w = 0; w < nwarps; ++w) {
-          warps[w].bar.expected = std::min(32, nthreads - 32 * w);
-          std::memset(warps[w].slot, 0, sizeof(warps[w].slot));
+      for (unsigned bx0 = 0; bx0 < grid.x; bx0 += cluster) {
+        Barrier cluster_bar;
+        cluster_bar.expected = nthreads * cluster;
+        std::vector<Barrier> block_bars(cluster);
+        std::vector<std::vector<Warp>> warps(cluster);
+        for (int c = 0; c < cluster; ++c) {
+          reset_cta_state(c);
+          block_bars[c].expected = nthreads;
+          warps[c] = std::vector<Warp>(nwarps);
+          for (int w = 0; w < nwarps; ++w) {
+            warps[c][w].bar.expected = std::min(32, nthreads - 32 * w);
+            std::memset(warps[c][w].slot, 0, sizeof(warps[c][w].slot));
+          }
         }
         std::vector<std::thread> threads;
-        threads.reserve(nthreads);
-        for (int t = 0; t < nthreads; ++t) {
-          threads.emplace_back([&, t] {
-            Ctx& c = ctx;
-            c.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-            c.bid = make_uint3(bx, by, bz);
-            c.bdim = block;
-            c.gdim = grid;
-            c.block_bar = &block_bar;
-            c.warp = &warps[t >> 5];
-            c.lane = t & 31;
-            body();
-            c.warp->bar.drop();      // a returned thread no longer takes part in barriers / collectives
-            block_bar.drop();
-          });
-        }
+        threads.reserve((size_t)nthreads * cluster);
+        for (int c = 0; c < cluster; ++c)
+          for (int t = 0; t < nthreads; ++t) {
+            threads.emplace_back([&, c, t] {
+              Ctx& x = ctx;
+              x.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+              x.bid = make_uint3(bx0 + c, by, bz);
+              x.bdim = block;
+              x.gdim = grid;
+              x.block_bar = &block_bars[c];
+              x.cluster_bar = &cluster_bar;
+              x.warp = &warps[c][t >> 5];
+              x.lane = t & 31;
+              x.cta = c;
+              x.cluster_size = cluster;
+              body();
+              x.warp->bar.drop();      // a returned thread no longer takes part in barriers / collectives
+              x.block_bar->drop();
+              x.cluster_bar->drop();
+            });
+          }
         for (auto& th : threads) th.join();
       }
 }
@@ -138,9 +192,17 @@ cudaError_t cudaGetDevice(int* d) {
   return cudaSuccess;
 }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
-  const char* e = std::getenv("UNIVS_EMU_SMS");      // few "SMs": persistent kernels walk many work units per CTA
-  *v = (e != nullptr && std::atoi(e) > 0) ? std::atoi(e) : 148;
+  *v = emu::emulated_sm_count();
   return cudaSuccess;
+}
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* status) {
+  if (std::strcmp(symbol, "cuTensorMapEncodeTiled") == 0) {
+    *fn = reinterpret_cast<void*>(&emu::encode_tiled);
+    if (status) *status = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+  }
+  if (status) *status = cudaDriverEntryPointSymbolNotFound;
+  return cudaErrorSymbolNotFound;
 }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {

@@ -19,6 +19,7 @@
 #include <vector>
 
 #define __launch_bounds__(...)
+#define __grid_constant__
 #undef __shared__
 #define __shared__ static
 
@@ -58,13 +59,17 @@ struct Ctx {
   uint3 tid, bid;
   dim3 bdim, gdim;
   Barrier* block_bar;
+  Barrier* cluster_bar;
   Warp* warp;
   int lane;
+  int cta;          // rank of this CTA inside its cluster (0 without clusters): selects the emulated shared memory / TMEM
+  int cluster_size;
 };
 extern thread_local Ctx ctx;
 extern std::mutex atomic_lock;
 
-void launch(dim3 grid, dim3 block, const std::function<void()>& body);
+void launch(dim3 grid, dim3 block, const std::function<void()>& body, int cluster = 1);
+int emulated_sm_count();
 
 inline uint32_t exchange(uint32_t v, int src_lane) {
   Warp* w = ctx.warp;
@@ -86,10 +91,24 @@ inline T shfl(T v, int src_lane) {
 
 }  // namespace emu
 
-#define threadIdx (::emu::ctx.tid)
-#define blockIdx (::emu::ctx.bid)
-#define blockDim (::emu::ctx.bdim)
-#define gridDim (::emu::ctx.gdim)
+// threadIdx / blockIdx / blockDim / gridDim: objects whose .x / .y / .z read the calling host thread's coordinates (not
+// macros: cudaLaunchConfig_t has members called gridDim and blockDim)
+namespace emu {
+struct Axis {
+  int vec, axis;
+  operator unsigned() const {
+    const Ctx& c = ctx;
+    const unsigned v[4][3] = {{c.tid.x, c.tid.y, c.tid.z}, {c.bid.x, c.bid.y, c.bid.z}, {c.bdim.x, c.bdim.y, c.bdim.z},
+                              {c.gdim.x, c.gdim.y, c.gdim.z}};
+    return v[vec][axis];
+  }
+};
+struct Vec3 {
+  Axis x, y, z;
+};
+}  // namespace emu
+static const ::emu::Vec3 threadIdx{{0, 0}, {0, 1}, {0, 2}}, blockIdx{{1, 0}, {1, 1}, {1, 2}}, blockDim{{2, 0}, {2, 1}, {2, 2}},
+    gridDim{{3, 0}, {3, 1}, {3, 2}};
 
 inline void __syncthreads() { ::emu::ctx.block_bar->wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { ::emu::ctx.warp->bar.wait(); }
@@ -144,3 +163,19 @@ inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<
 // kernel attributes are meaningless here (nvcc offers this overload for __global__ functions)
 template <typename R, typename... A>
 inline cudaError_t cudaFuncSetAttribute(R (*)(A...), cudaFuncAttribute, int) { return cudaSuccess; }
+
+// cluster launches: build_emu.py rewrites  cudaLaunchKernelEx(&cfg, kernel, args...)  into  ::emu::launch_ex(cfg, [=]{ kernel(args...); })
+namespace emu {
+inline cudaError_t launch_ex(const cudaLaunchConfig_t& cfg, const std::function<void()>& body) {
+  int cluster = 1;
+  for (unsigned i = 0; i < cfg.numAttrs; ++i)
+    if (cfg.attrs[i].id == cudaLaunchAttributeClusterDimension) cluster = (int)cfg.attrs[i].val.clusterDim.x;
+  launch(cfg.gridDim, cfg.blockDim, body, cluster);
+  return cudaSuccess;
+}
+}  // namespace emu
+template <typename R, typename... A>
+inline cudaError_t cudaOccupancyMaxActiveClusters(int* n, R (*)(A...), const cudaLaunchConfig_t*) {
+  *n = ::emu::emulated_sm_count() / 2;
+  return cudaSuccess;
+}

@@ -15,6 +15,7 @@
 //   * bar.sync id, n: a barrier per id over n threads; elect.sync: lane 0.
 // Shared memory is a NaN-filled 232 KB buffer per CTA; `smem_u32` is the offset into it.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <chrono>
@@ -28,6 +29,18 @@
 
 namespace emu {
 unsigned char* dyn_smem();                       // base of the CTA's dynamic shared memory (1024-byte aligned)
+unsigned char* dyn_smem_of(int cta);             // the same of another CTA of the cluster
+CUresult encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave,
+                      CUtensorMapSwizzle swizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TensorMap {                               // what the emulated cuTensorMapEncodeTiled stores in the opaque CUtensorMap
+  unsigned long long magic;
+  const unsigned char* base;
+  unsigned long long dims[3], strides[2];        // elements / bytes
+  unsigned box[3];
+  int esize, swizzle_bits, rank;
+};
+static_assert(sizeof(TensorMap) <= sizeof(CUtensorMap), "fits the opaque descriptor");
 float* tmem();                                   // [128][512]
 struct MBar {
   int count = 0, pending = 0;
@@ -110,7 +123,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int id
     } else {
       std::this_thread::sleep_for(std::chrono::microseconds(50));
       if ((spin & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) {
-        std::fprintf(stderr, "emu: mbarrier wait timed out (id %d, parity %u, thread %u)\n", id, parity, threadIdx.x);
+        std::fprintf(stderr, "emu: mbarrier wait timed out (id %d, parity %u, thread %u)\n", id, parity, (unsigned)threadIdx.x);
         ::emu::dump_waits();
         ::emu::fail("mbarrier wait timed out: protocol deadlock");
       }
@@ -121,6 +134,48 @@ __device__ __forceinline__ void fence_before() {}
 __device__ __forceinline__ void fence_after() {}
 __device__ __forceinline__ void fence_proxy_async_smem() {}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) { mbar_arrive(bar); }     // MMAs run synchronously at issue
+
+// ---- thread-block clusters and TMA ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() { return (uint32_t)::emu::ctx.cta; }
+__device__ __forceinline__ void cluster_sync_all() { ::emu::ctx.cluster_bar->wait(); }
+inline uint64_t* peer_bar(uint64_t* bar, int cta) {          // the barrier at the same shared-memory offset in CTA `cta`
+  return reinterpret_cast<uint64_t*>(::emu::dyn_smem_of(cta) + (reinterpret_cast<unsigned char*>(bar) - ::emu::dyn_smem()));
+}
+// cp.async.bulk.tensor.3d: box [box0 elements][box1 rows][1] at (c0, c1, c2); elements outside the tensor read as zero; the
+// box lands row by row (box0 * esize bytes per row) with the map's swizzle applied to the absolute shared-memory address;
+// the full box size is credited to the barrier.  Executed synchronously (a legal schedule of the asynchronous copy).
+inline void tma_copy(int cta, uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  const ::emu::TensorMap& m = *reinterpret_cast<const ::emu::TensorMap*>(map);
+  if (m.magic != 0x554e495653ull || m.rank != 3) ::emu::fail("TMA: not a tensor map of the emulated encoder");
+  const unsigned row_bytes = m.box[0] * (unsigned)m.esize;
+  if (dst % 1024u) ::emu::fail("TMA: swizzled destination must be 1024-byte aligned");
+  if (row_bytes != (16u << m.swizzle_bits)) ::emu::fail("TMA: box row must be one swizzle span");
+  unsigned char* smem = ::emu::dyn_smem_of(cta);
+  for (unsigned r = 0; r < m.box[1]; ++r)
+    for (unsigned e = 0; e < m.box[0]; ++e) {
+      const long long x = (long long)c0 + e, y = (long long)c1 + r, z = c2;
+      unsigned char v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (x >= 0 && y >= 0 && z >= 0 && (unsigned long long)x < m.dims[0] && (unsigned long long)y < m.dims[1] && (unsigned long long)z < m.dims[2])
+        std::memcpy(v, m.base + (size_t)z * m.strides[1] + (size_t)y * m.strides[0] + (size_t)x * m.esize, m.esize);
+      const uint32_t addr = dst + r * row_bytes + e * (unsigned)m.esize;
+      const uint32_t sw = addr ^ (((addr >> 7) & ((1u << m.swizzle_bits) - 1u)) << 4);
+      if (sw + m.esize > 232448u) ::emu::fail("TMA: box beyond shared memory");
+      std::memcpy(smem + sw, v, m.esize);
+    }
+  mbar_complete_tx(peer_bar(bar, cta), (long long)row_bytes * m.box[1]);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  tma_copy(::emu::ctx.cta, dst, map, bar, c0, c1, c2);
+}
+__device__ __forceinline__ void tma_load_3d_multicast(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                      int c2, uint16_t mask) {
+  for (int c = 0; c < ::emu::ctx.cluster_size; ++c)
+    if (mask & (1u << c)) tma_copy(c, dst, map, bar, c0, c1, c2);
+}
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  for (int c = 0; c < ::emu::ctx.cluster_size; ++c)
+    if (mask & (1u << c)) mbar_arrive(peer_bar(bar, c));
+}
 
 // ---- operand access through the shared-memory matrix descriptor ------------------------------------------------------
 struct Desc {
@@ -141,40 +196,56 @@ inline Desc decode_desc(uint64_t d) {
 inline uint32_t swizzled(uint32_t addr, int bits) {      // Swizzle<bits,4,3> on the absolute shared-memory address
   return addr ^ (((addr >> 7) & ((1u << bits) - 1u)) << 4);
 }
-// element (r = M/N index, k = K index, k < 16) of an fp16 operand
-inline float operand_elem(const Desc& d, bool mn_major, int r, int k) {
+// element (r = M/N index, k = K index inside one MMA) of an operand whose elements are `esize` bytes (2: fp16, 4: tf32)
+inline float operand_elem(const Desc& d, bool mn_major, int r, int k, int esize) {
   const int span = 16 << d.swizzle_bits;          // bytes of one swizzle row (32 / 64 / 128)
+  const int per16 = 16 / esize;                   // elements per 16-byte unit (the "T" of the canonical layouts)
   uint32_t off;
   if (!mn_major) {                                // K-major: rows of `span` bytes, 8-row groups SBO apart, K contiguous
-    off = (uint32_t)(r >> 3) * d.sbo + (uint32_t)(r & 7) * span + (uint32_t)k * 2u;
-  } else {                                        // MN-major: K rows of `span` bytes (span/2 MN elements), 8-row groups SBO apart
-    const int per_row = span / 2;
-    off = (uint32_t)(r / per_row) * d.lbo + (uint32_t)(r % per_row) * 2u + (uint32_t)(k >> 3) * d.sbo + (uint32_t)(k & 7) * span;
+    off = (uint32_t)(r >> 3) * d.sbo + (uint32_t)(r & 7) * span + (uint32_t)k * esize;
+  } else {                                        // MN-major: K rows of `span` bytes (span/esize MN elements), 8-row groups SBO apart
+    const int per_row = span / esize;
+    off = (uint32_t)(r / per_row) * d.lbo + (uint32_t)(r % per_row) * esize + (uint32_t)(k >> 3) * d.sbo + (uint32_t)(k & 7) * span;
   }
+  (void)per16;
   const uint32_t addr = swizzled(d.start + off, d.swizzle_bits);
-  if (addr + 2 > 232448u) ::emu::fail("tcgen05.mma operand read beyond shared memory");
-  return __half2float(*reinterpret_cast<const __half*>(::emu::dyn_smem() + addr));
+  if (addr + esize > 232448u) ::emu::fail("tcgen05.mma operand read beyond shared memory");
+  const unsigned char* p = ::emu::dyn_smem() + addr;
+  if (esize == 2) return __half2float(*reinterpret_cast<const __half*>(p));
+  uint32_t u;
+  std::memcpy(&u, p, 4);
+  u &= 0xFFFFE000u;                               // kind::tf32 consumes the upper 19 bits of each fp32 operand
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+inline void umma_emulated(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum, int fmt, int esize, int K) {
   const int M = (int)((idesc >> 24) & 0x1F) << 4, N = (int)((idesc >> 17) & 0x3F) << 3;
   const bool a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
   if (M != 128 || N < 16 || N > 256 || (N & 15)) ::emu::fail("tcgen05.mma: unsupported shape (M = 128, 16 <= N <= 256, N % 16 == 0)");
-  if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 0 || ((idesc >> 10) & 7) != 0) ::emu::fail("tcgen05.mma: expected f16 x f16 -> f32");
+  if (((idesc >> 4) & 3) != 1 || (int)((idesc >> 7) & 7) != fmt || (int)((idesc >> 10) & 7) != fmt)
+    ::emu::fail("tcgen05.mma: instruction descriptor formats do not match the instruction kind (f32 accumulate)");
   const Desc a = decode_desc(adesc), b = decode_desc(bdesc);
   const int lane0 = (int)(tmem_d >> 16), col0 = (int)(tmem_d & 0xFFFF);
   if (lane0 != 0 || col0 + N > 512) ::emu::fail("tcgen05.mma: accumulator outside TMEM");
   float* T = ::emu::tmem();
   static thread_local float A[128][16], B[256][16];
   for (int m = 0; m < M; ++m)
-    for (int k = 0; k < 16; ++k) A[m][k] = operand_elem(a, a_mn, m, k);
+    for (int k = 0; k < K; ++k) A[m][k] = operand_elem(a, a_mn, m, k, esize);
   for (int n = 0; n < N; ++n)
-    for (int k = 0; k < 16; ++k) B[n][k] = operand_elem(b, b_mn, n, k);
+    for (int k = 0; k < K; ++k) B[n][k] = operand_elem(b, b_mn, n, k, esize);
   for (int m = 0; m < M; ++m)
     for (int n = 0; n < N; ++n) {
       float acc = accum ? T[m * 512 + col0 + n] : 0.f;
-      for (int k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
+      for (int k = 0; k < K; ++k) acc += A[m][k] * B[n][k];
       T[m * 512 + col0 + n] = acc;
     }
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  umma_emulated(tmem_d, adesc, bdesc, idesc, accum, /*fmt f16*/ 0, 2, 16);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  umma_emulated(tmem_d, adesc, bdesc, idesc, accum, /*fmt tf32*/ 2, 4, 8);
 }
 __device__ __forceinline__ bool elect_one() { return ::emu::ctx.lane == 0; }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { ::emu::named_barrier(id, threads).wait(); }

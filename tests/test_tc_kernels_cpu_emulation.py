@@ -120,3 +120,56 @@ def test_cross_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, B, Lq, L
     if masked:      # the two special rows, exactly as the reference's rule (..._univs.py:390) treats them
         full = ops_ref.mha_core(q[:1, 1:2], k[:1], v[:1], heads)
         assert _rel(plain(got)[:1, 1:2], full) < 5e-6
+
+
+@pytest.mark.parametrize("T,Q,C,HW,sms", [
+    (1, 20, 64, 300, 4),         # 3 tiles over 2 clusters; queries split 16 / 16 (4 of the second half exist)
+    (2, 200, 256, 700, 4),       # north-star query / channel counts: split 112 / 96, E reloaded at the frame boundary
+    (3, 40, 128, 129, 2),        # one cluster walks all 6 tiles: every other tile has a single valid pixel, 3 frames
+    (1, 256, 64, 128, 148),      # Q at the limit (128 / 128), exactly one tile
+    (2, 17, 64, 1000, 148),      # the smallest query count the split accepts (16 + 1), one cluster per tile
+])
+def test_cluster_einsum_kernel(monkeypatch, emu_lib_path, tmp_path, T, Q, C, HW, sms):
+    """csrc/mask_einsum_mc.cu on the emulator: two CTAs of a cluster run concurrently, E halves resident per frame, F stages
+    delivered to both CTAs by (emulated) TMA multicast, stage release by multicast commits, contiguous tile ranges"""
+    _use(monkeypatch, emu_lib_path, sms, tmp_path)
+    chk = ops._chk
+    monkeypatch.setattr(ops, "_chk", lambda t, name, dtype=torch.float32: chk(dev(t), name, dtype))
+    monkeypatch.setattr(ops, "_einsum_mc", 1)
+    g = torch.Generator().manual_seed(T * 100 + Q)
+    E, F = torch.randn(T, Q, C, generator=g), torch.randn(T, HW, C, generator=g)
+    F16 = cpu_backend._split16(F, False)                    # fp16 [hi | lo], what prepare_mask_features("f16x3") makes
+    guard = torch.full((Q + 2, T, HW), 7.0)
+    got = ops.mask_einsum(dev(E), dev(F16), out=guard[1:Q + 1], mode="f16x3")
+    want = ops_ref.mask_einsum(E.double(), F.transpose(1, 2).double()).float()
+    assert not torch.isnan(plain(got)).any()
+    assert _rel(got, want) < 5e-6
+    assert bool((guard[0] == 7.0).all()) and bool((guard[Q + 1] == 7.0).all())       # nothing written outside [Q, T, HW]
+
+
+@pytest.mark.parametrize("T,Q,C,HW", [(1, 20, 256, 300), (2, 200, 256, 400), (1, 232, 64, 130), (2, 7, 64, 66)])
+def test_calibration_the_hardware_validated_einsum_kernel_runs_on_the_emulator(monkeypatch, emu_lib_path, tmp_path, T, Q, C, HW):
+    """csrc/mask_einsum_tc.cu is the tcgen05 kernel that HAS run on the B200 (bit-identical there to the mma.sync kernel, 0.73
+    of the HBM roofline): on the emulator it must give the same answers.  This pins the emulated semantics the never-run
+    kernels rely on -- TMA boxes with SWIZZLE_64B / SWIZZLE_128B, K-major matrix descriptors with the 32-byte k-step
+    advance, kind::f16 and kind::tf32 instruction descriptors, TMEM lane = M row / column = N, 32x32b loads, the mbarrier
+    pipeline -- to code whose behaviour on the hardware is known."""
+    _use(monkeypatch, emu_lib_path, 3, tmp_path)
+    chk = ops._chk
+    monkeypatch.setattr(ops, "_chk", lambda t, name, dtype=torch.float32: chk(dev(t), name, dtype))
+    monkeypatch.setattr(ops, "_einsum_mc", 0)
+    g = torch.Generator().manual_seed(T * 100 + Q)
+    E, F = torch.randn(T, Q, C, generator=g), torch.randn(T, HW, C, generator=g)
+    want = ops_ref.mask_einsum(E.double(), F.transpose(1, 2).double()).float()
+    # fp16 hi|lo operands, three kind::f16 MMAs per k-step, SWIZZLE_64B
+    got = ops.mask_einsum(dev(E), dev(cpu_backend._split16(F, False)), mode="f16x3")
+    assert not torch.isnan(plain(got)).any() and _rel(got, want) < 5e-6
+    # fp32 operands consumed as TF32 (pre-rounded to nearest, as the decoder does), SWIZZLE_128B
+    rnd = lambda x: cpu_backend._split(x)[..., :x.shape[-1]].contiguous()
+    Er, Fr = rnd(E), rnd(F)
+    out = torch.empty(Q, T, HW)
+    rc = _cabi.lib().univs_mask_einsum_f32(0, Er.data_ptr(), Fr.data_ptr(), T, Q, C, HW, out.data_ptr())
+    assert rc == 0
+    exact = ops_ref.mask_einsum(Er.double(), Fr.transpose(1, 2).double()).float()
+    assert _rel(out, exact) < 5e-6                           # exact products of the rounded operands, fp32 accumulation
+    assert 1e-5 < _rel(out, want) < 2e-3                     # and it IS the one-pass TF32 result, not fp32
