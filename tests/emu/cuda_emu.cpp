@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
 #include <map>
 #include <memory>
 #include <string>
@@ -25,6 +26,56 @@ struct CtaState {
   std::map<int, std::unique_ptr<Barrier>> named;
 };
 static CtaState g_cta[kMaxCluster];
+
+// the tensor pipe of a CTA: tcgen05.mma / tcgen05.commit are ASYNCHRONOUS -- issued work is queued and executed in order by a
+// worker thread (with random delays under UNIVS_EMU_CHAOS), so an operand tile that is overwritten before "its" MMA has
+// actually run, or an accumulator read before the commit retired, shows up as a wrong result
+struct Pipe {
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<std::function<void()>> q;
+  bool stop = false;
+  std::thread worker;
+};
+static Pipe g_pipe[kMaxCluster];
+void pipe_push(std::function<void()> fn) {
+  Pipe& p = g_pipe[ctx.cta];
+  {
+    std::lock_guard<std::mutex> l(p.m);
+    p.q.push_back(std::move(fn));
+  }
+  p.cv.notify_one();
+}
+static void pipe_start(int c) {
+  Pipe& p = g_pipe[c];
+  p.stop = false;
+  p.worker = std::thread([c] {
+    ctx.cta = c;
+    ctx.cluster_size = kMaxCluster;
+    ctx.lane = 0;
+    Pipe& p = g_pipe[c];
+    for (;;) {
+      std::function<void()> fn;
+      {
+        std::unique_lock<std::mutex> l(p.m);
+        p.cv.wait(l, [&] { return p.stop || !p.q.empty(); });
+        if (p.q.empty()) return;
+        fn = std::move(p.q.front());
+        p.q.pop_front();
+      }
+      fn();
+    }
+  });
+}
+static void pipe_finish(int c) {
+  Pipe& p = g_pipe[c];
+  {
+    std::lock_guard<std::mutex> l(p.m);
+    p.stop = true;
+  }
+  p.cv.notify_one();
+  p.worker.join();
+}
 static std::mutex g_mbar_lock, g_named_lock;
 static int g_wait_id[kMaxCluster][1024], g_wait_parity[kMaxCluster][1024];
 
@@ -142,6 +193,7 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body, int cluste
             std::memset(warps[c][w].slot, 0, sizeof(warps[c][w].slot));
           }
         }
+        for (int c = 0; c < cluster; ++c) pipe_start(c);
         std::vector<std::thread> threads;
         threads.reserve((size_t)nthreads * cluster);
         for (int c = 0; c < cluster; ++c)
@@ -165,6 +217,7 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body, int cluste
             });
           }
         for (auto& th : threads) th.join();
+        for (int c = 0; c < cluster; ++c) pipe_finish(c);
       }
 }
 

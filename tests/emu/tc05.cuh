@@ -8,7 +8,8 @@
 //     (emulated) shared memory through the matrix descriptors -- start address, stride byte offset between 8-row groups,
 //     swizzle mode applied to the ABSOLUTE shared-memory address (XOR of address bits 4.. with bits 7..), K-major or
 //     MN-major as the instruction descriptor says -- multiplied in fp32 and accumulated into TMEM (lane = M row,
-//     column = N index); executed synchronously at issue, so tcgen05.commit arrives at once;
+//     column = N index); issued work goes to an in-order tensor pipe that executes it LATER on its own thread, and
+//     tcgen05.commit arrives when the pipe reaches it (operands overwritten too early give wrong results);
 //   * TMEM: 128 lanes x 512 fp32 columns per CTA, NaN-filled at launch (reading what no MMA wrote is visible);
 //   * tcgen05.ld 32x32b: thread i of a warp reads lane (warp % 4) * 32 + i; the address' lane field must name that
 //     quarter (the hardware restriction is checked);
@@ -19,6 +20,7 @@
 #include <cuda_fp16.h>
 
 #include <chrono>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -52,12 +54,24 @@ MBar& mbar_of(const void* p);                    // state of the mbarrier stored
 std::mutex& mbar_lock();
 Barrier& named_barrier(int id, int threads);
 [[noreturn]] void fail(const char* what);
+void pipe_push(std::function<void()> fn);        // enqueue work on this CTA's (asynchronous, in-order) tensor pipe
 void note_wait(int thread, int id, int parity);  // diagnostics: what every thread of the CTA is waiting for (-1: nothing)
 void dump_waits();
 }  // namespace emu
 
 namespace univs {
 namespace tc {
+
+// UNIVS_EMU_CHAOS=<max microseconds>: every barrier operation, MMA issue, TMEM load and TMA copy is preceded by a random
+// delay of the calling thread, so that roles overtake each other in ways the natural scheduling rarely produces
+inline void chaos() {
+  static const int max_us = [] { const char* e = std::getenv("UNIVS_EMU_CHAOS"); return e ? std::atoi(e) : 0; }();
+  if (max_us <= 0) return;
+  static thread_local unsigned state = 0x9E3779B9u ^ (unsigned)(size_t)&state;
+  state = state * 1664525u + 1013904223u;
+  const unsigned r = state >> 8;
+  if ((r & 3u) == 0) std::this_thread::sleep_for(std::chrono::microseconds((r >> 2) % (unsigned)max_us));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)(reinterpret_cast<const unsigned char*>(p) - ::emu::dyn_smem());
@@ -77,6 +91,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_init_fence() {}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  chaos();
   std::lock_guard<std::mutex> l(::emu::mbar_lock());
   ::emu::MBar& b = ::emu::mbar_of(bar);
   if (b.pending <= 0) ::emu::fail("mbarrier: more arrivals than its count in one phase");
@@ -85,6 +100,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   mbar_complete(b);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  chaos();
   std::lock_guard<std::mutex> l(::emu::mbar_lock());
   ::emu::MBar& b = ::emu::mbar_of(bar);
   if (b.pending <= 0) ::emu::fail("mbarrier: more arrivals than its count in one phase");
@@ -105,6 +121,7 @@ inline void mbar_complete_tx(uint64_t* bar, long long bytes) {
 // the business of tests/test_tc_protocol_sim.py / test_einsum_mc_protocol.py, at the granularity of roles.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int id = 0) {
   static thread_local std::map<const void*, unsigned long long> seen;      // completions at this thread's last pass
+  chaos();
   const auto t0 = std::chrono::steady_clock::now();
   ::emu::note_wait((int)threadIdx.x, id, (int)parity);
   for (unsigned spin = 0;; ++spin) {
@@ -133,7 +150,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int id
 __device__ __forceinline__ void fence_before() {}
 __device__ __forceinline__ void fence_after() {}
 __device__ __forceinline__ void fence_proxy_async_smem() {}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) { mbar_arrive(bar); }     // MMAs run synchronously at issue
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {      // arrives when everything issued before it has executed
+  ::emu::pipe_push([bar] { mbar_arrive(bar); });
+}
 
 // ---- thread-block clusters and TMA ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_rank() { return (uint32_t)::emu::ctx.cta; }
@@ -145,6 +164,7 @@ inline uint64_t* peer_bar(uint64_t* bar, int cta) {          // the barrier at t
 // box lands row by row (box0 * esize bytes per row) with the map's swizzle applied to the absolute shared-memory address;
 // the full box size is credited to the barrier.  Executed synchronously (a legal schedule of the asynchronous copy).
 inline void tma_copy(int cta, uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  chaos();
   const ::emu::TensorMap& m = *reinterpret_cast<const ::emu::TensorMap*>(map);
   if (m.magic != 0x554e495653ull || m.rank != 3) ::emu::fail("TMA: not a tensor map of the emulated encoder");
   const unsigned row_bytes = m.box[0] * (unsigned)m.esize;
@@ -174,7 +194,10 @@ __device__ __forceinline__ void tma_load_3d_multicast(uint32_t dst, const CUtens
 }
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
   for (int c = 0; c < ::emu::ctx.cluster_size; ++c)
-    if (mask & (1u << c)) mbar_arrive(peer_bar(bar, c));
+    if (mask & (1u << c)) {
+      uint64_t* target = peer_bar(bar, c);
+      ::emu::pipe_push([target] { mbar_arrive(target); });
+    }
 }
 
 // ---- operand access through the shared-memory matrix descriptor ------------------------------------------------------
@@ -220,6 +243,7 @@ inline float operand_elem(const Desc& d, bool mn_major, int r, int k, int esize)
   return f;
 }
 inline void umma_emulated(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum, int fmt, int esize, int K) {
+  chaos();
   const int M = (int)((idesc >> 24) & 0x1F) << 4, N = (int)((idesc >> 17) & 0x3F) << 3;
   const bool a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
   if (M != 128 || N < 16 || N > 256 || (N & 15)) ::emu::fail("tcgen05.mma: unsupported shape (M = 128, 16 <= N <= 256, N % 16 == 0)");
@@ -242,10 +266,10 @@ inline void umma_emulated(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
     }
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  umma_emulated(tmem_d, adesc, bdesc, idesc, accum, /*fmt f16*/ 0, 2, 16);
+  ::emu::pipe_push([=] { umma_emulated(tmem_d, adesc, bdesc, idesc, accum, /*fmt f16*/ 0, 2, 16); });
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  umma_emulated(tmem_d, adesc, bdesc, idesc, accum, /*fmt tf32*/ 2, 4, 8);
+  ::emu::pipe_push([=] { umma_emulated(tmem_d, adesc, bdesc, idesc, accum, /*fmt tf32*/ 2, 4, 8); });
 }
 __device__ __forceinline__ bool elect_one() { return ::emu::ctx.lane == 0; }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { ::emu::named_barrier(id, threads).wait(); }
@@ -257,6 +281,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t, uint32_t) {}
 __device__ __forceinline__ void tmem_wait_ld() {}
 
 inline void tmem_ld(uint32_t taddr, uint32_t* r, int n) {
+  chaos();
   const int lane_field = (int)(taddr >> 16), col = (int)(taddr & 0xFFFF);
   const int warp = (int)(threadIdx.x >> 5);
   if (lane_field != (warp & 3) * 32) ::emu::fail("tcgen05.ld 32x32b: a warp may only access TMEM lanes 32 * (warp % 4) ..+31");

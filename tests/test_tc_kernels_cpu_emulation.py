@@ -173,3 +173,18 @@ def test_calibration_the_hardware_validated_einsum_kernel_runs_on_the_emulator(m
     exact = ops_ref.mask_einsum(Er.double(), Fr.transpose(1, 2).double()).float()
     assert _rel(out, exact) < 5e-6                           # exact products of the rounded operands, fp32 accumulation
     assert 1e-5 < _rel(out, want) < 2e-3                     # and it IS the one-pass TF32 result, not fp32
+
+
+@pytest.mark.parametrize("kernel", ["window", "cross_attention", "cluster_einsum", "einsum"])
+def test_tc_kernels_under_randomised_scheduling(monkeypatch, emu_lib_path, tmp_path, kernel):
+    """UNIVS_EMU_CHAOS: random delays before every barrier operation / MMA issue / TMEM load / TMA copy of every thread, so
+    producers, the MMA lane, softmax and epilogue warps overtake each other in unusual orders; results must not change"""
+    monkeypatch.setenv("UNIVS_EMU_CHAOS", "300")
+    if kernel == "window":
+        test_window_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, 1, 24, 36, 1, 6, 1)
+    elif kernel == "cross_attention":
+        test_cross_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, 1, 150, 700, 1, 1, True, 0)
+    elif kernel == "cluster_einsum":
+        test_cluster_einsum_kernel(monkeypatch, emu_lib_path, tmp_path, 2, 40, 128, 520, 2)
+    else:
+        test_calibration_the_hardware_validated_einsum_kernel_runs_on_the_emulator(monkeypatch, emu_lib_path, tmp_path, 2, 40, 64, 520)
