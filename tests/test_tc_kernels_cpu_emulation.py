@@ -188,3 +188,31 @@ def test_tc_kernels_under_randomised_scheduling(monkeypatch, emu_lib_path, tmp_p
         test_cluster_einsum_kernel(monkeypatch, emu_lib_path, tmp_path, 2, 40, 128, 520, 2)
     else:
         test_calibration_the_hardware_validated_einsum_kernel_runs_on_the_emulator(monkeypatch, emu_lib_path, tmp_path, 2, 40, 64, 520)
+
+
+def test_cross_attention_tc_kernel_edge_cases(monkeypatch, emu_lib_path, tmp_path):
+    """single query / single key / a mask shared by the batch / key counts around the 128-key block and 32-bit word sizes"""
+    _use(monkeypatch, emu_lib_path, 2, tmp_path)
+    g = torch.Generator().manual_seed(77)
+    for B, Lq, Lk, shared in [(1, 1, 1, False), (2, 3, 31, True), (1, 129, 128, False), (2, 5, 129, True), (1, 2, 257, False)]:
+        C = 32
+        q, k, v = (torch.randn(B, L, C, generator=g) for L in (Lq, Lk, Lk))
+        mask, bits, row_open = _mask_case(g, B, max(Lq, 3), Lk)
+        mask, bits, row_open = mask[:, :Lq], bits[:, :Lq].contiguous(), row_open[:, :Lq].contiguous()
+        if shared:                                   # one mask for every batch element (mask_batch = 1)
+            mask, bits, row_open = mask[:1], bits[:1].contiguous(), row_open[:1].contiguous()
+        got = ops.mha_core_tc(dev(q), dev(k), dev(v), dev(bits), dev(row_open), flags=0)
+        want = ops_ref.mha_core(q, k, v, 1, mask.expand(B, -1, -1), unmask_full_rows=True)
+        assert not torch.isnan(plain(got)).any(), (B, Lq, Lk)
+        assert _rel(got, want) < 5e-6, (B, Lq, Lk, shared)
+
+
+def test_window_attention_tc_kernel_stage1_heads(monkeypatch, emu_lib_path, tmp_path):
+    """Swin-L stage 1 head count (6 heads, C = 192), one shifted window row with padding in x"""
+    _use(monkeypatch, emu_lib_path, 3, tmp_path)
+    g = torch.Generator().manual_seed(5)
+    nH, C = 6, 192
+    qkv = torch.randn(1, 12, 20, 3 * C, generator=g)
+    bias, table = torch.randn(3 * C, generator=g) * 0.2, torch.randn(529, nH, generator=g) * 0.5
+    out, _ = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, 6)
+    assert _rel(out, ops_ref.swin_window_attention(qkv, bias, table, nH, 12, 6)) < 5e-6
