@@ -216,3 +216,15 @@ def test_window_attention_tc_kernel_stage1_heads(monkeypatch, emu_lib_path, tmp_
     bias, table = torch.randn(3 * C, generator=g) * 0.2, torch.randn(529, nH, generator=g) * 0.5
     out, _ = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, 6)
     assert _rel(out, ops_ref.swin_window_attention(qkv, bias, table, nH, 12, 6)) < 5e-6
+
+
+def test_cross_attention_tc_kernel_north_star_level(monkeypatch, emu_lib_path, tmp_path):
+    """the decoder's cross-attention at the north-star size, coarsest level: 200 queries x 920 keys (23 x 40), 8 heads,
+    per-frame mask bits shared by the heads"""
+    _use(monkeypatch, emu_lib_path, 16, tmp_path)
+    g = torch.Generator().manual_seed(920)
+    B, Lq, Lk, heads = 1, 200, 920, 8
+    q, k, v = (torch.randn(B, L, heads * 32, generator=g) for L in (Lq, Lk, Lk))
+    mask, bits, row_open = _mask_case(g, B, Lq, Lk)
+    got = ops.mha_core_tc(dev(q), dev(k), dev(v), dev(bits), dev(row_open), flags=0)
+    assert _rel(got, ops_ref.mha_core(q, k, v, heads, mask, unmask_full_rows=True)) < 5e-6
