@@ -87,26 +87,26 @@ def test_clip_forward_with_all_switches_on_the_emulator(monkeypatch, tmp_path):
         return call
 
     dec = model.sem_seg_head.predictor
+    chk = ops._chk
+    monkeypatch.setattr(_cabi, "_lib", _load(lib_path))
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops, "_chk", lambda t, name, dtype=torch.float32: chk(_as_dev(t), name, dtype))
+    monkeypatch.setattr(ops, "_chk_t", lambda t, name, dtype=torch.float32: (chk(_as_dev(t), name, dtype), _as_dev(t))[1])
+    monkeypatch.setattr(ops, "_ws_cache", {})
+    monkeypatch.setattr(ops, "_gn_ws", {})
+    monkeypatch.setattr(nn_ops, "_pad_cache", {})
+    monkeypatch.setattr(ops, "_win_tc", 1)                # tcgen05 window attention
+    monkeypatch.setattr(ops, "_mha_tc", 1)                # tcgen05 attention core ...
+    monkeypatch.setattr(ops, "MHA_TC_MIN_KEYS", 1)        # ... for the small key counts of this geometry too
+    monkeypatch.setattr(ops, "_msda_tile", 8)             # tiled MSDeformAttn
+    monkeypatch.setattr(ops, "_einsum_mc", 1)             # cluster einsum
+    monkeypatch.setattr(ops, "_einsum_mode", "f16x3")
+    monkeypatch.setattr(dec, "pooled_masks", True)        # intermediate heads from pooled mask features
     nn_ops.set_fused_glue(True)
     try:
         with oracle_ops("tf32x3"):
-            chk = ops._chk
-            monkeypatch.setattr(_cabi, "_lib", _load(lib_path))
-            monkeypatch.setattr(ops, "_stream", lambda: 0)
-            monkeypatch.setattr(ops, "_chk", lambda t, name, dtype=torch.float32: chk(_as_dev(t), name, dtype))
-            monkeypatch.setattr(ops, "_chk_t", lambda t, name, dtype=torch.float32: (chk(_as_dev(t), name, dtype), _as_dev(t))[1])
-            monkeypatch.setattr(ops, "_ws_cache", {})
-            monkeypatch.setattr(ops, "_gn_ws", {})
-            monkeypatch.setattr(nn_ops, "_pad_cache", {})
-            for name in EMULATED:
-                monkeypatch.setattr(ops, name, bound(name))
-            monkeypatch.setattr(ops, "_win_tc", 1)                # tcgen05 window attention
-            monkeypatch.setattr(ops, "_mha_tc", 1)                # tcgen05 attention core ...
-            monkeypatch.setattr(ops, "MHA_TC_MIN_KEYS", 1)        # ... for the small key counts of this geometry too
-            monkeypatch.setattr(ops, "_msda_tile", 8)             # tiled MSDeformAttn
-            monkeypatch.setattr(ops, "_einsum_mc", 1)             # cluster einsum
-            monkeypatch.setattr(ops, "_einsum_mode", "f16x3")
-            monkeypatch.setattr(dec, "pooled_masks", True)        # intermediate heads from pooled mask features
+            for name in EMULATED:         # inside the context (which restores every operator on exit): not via monkeypatch,
+                setattr(ops, name, bound(name))       # whose teardown would put the oracle functions back for good
             got = model.clip_forward(frames, tg())
     finally:
         nn_ops.set_fused_glue(False)
