@@ -62,3 +62,28 @@ def test_frame_groups_equal_whole_clip():
                         assert err < 1e-4, (fused, groups, k, err)
         finally:
             nn_ops.set_fused_glue(False)
+
+
+def test_l2_chunked_mlp_equals_the_whole_tensor_schedule():
+    """UNIVS_MLP_CHUNK_MB: the Swin MLP in row chunks (fc1 -> GELU -> fc2 per chunk) is the same function of its input"""
+    import torch.nn as nn
+    from oracle.cpu_backend import oracle_ops
+    from univs_b200 import nn_ops
+    g = torch.Generator().manual_seed(0)
+    fc1, fc2 = nn.Linear(48, 192), nn.Linear(192, 48)
+    x = torch.randn(2, 37, 29, 48, generator=g)
+    for policy in ("fp32", "tf32x3"):
+        with oracle_ops(policy):
+            h = nn_ops.prep(x)
+            want = nn_ops.mlp(h, fc1, fc2)
+            nn_ops.set_mlp_chunk_mb(1)
+            try:
+                rows = 2 * 37 * 29
+                assert nn_ops.mlp_rows_per_chunk(rows, 192) == 256 * ((1 << 20) // (192 * (4 + (8 if policy == "tf32x3" else 4))) // 256) < rows
+                got = nn_ops.mlp(h, fc1, fc2)
+            finally:
+                nn_ops.set_mlp_chunk_mb(0)
+        assert got.shape == want.shape == (2, 37, 29, 48)
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(want, fc2(torch.nn.functional.gelu(fc1(x))) - fc2.bias, rtol=1e-4, atol=1e-5)
+    assert nn_ops.mlp_rows_per_chunk(1000, 768) == 1000          # switched off: one chunk

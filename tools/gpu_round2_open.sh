@@ -34,6 +34,7 @@ UNIVS_WIN_TC=1 run bench_wintc 900 python bench.py --steps 10 --warmup 3 --no-cp
 UNIVS_ROWWISE_V2=3 run bench_rowwise_v2 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_FRAME_STREAMS=2 run bench_streams2 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_FRAME_STREAMS=5 run bench_streams5 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+UNIVS_MLP_CHUNK_MB=96 run bench_mlp_chunk 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_POOLED_MASKS=1 run bench_pooled_masks 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_EINSUM_MC=1 run bench_einsum_mc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 UNIVS_MHA_TC=1 run bench_mhatc 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline

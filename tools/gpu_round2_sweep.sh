@@ -11,4 +11,8 @@ done
 for g in 2 3 5; do
   UNIVS_FRAME_STREAMS=$g timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$out/bench_streams_$g.log" 2>&1
 done
+# L2-resident MLP schedule (validated kernels, another order): working-set sizes around the 126 MB L2
+for mb in 32 64 96 160; do
+  UNIVS_MLP_CHUNK_MB=$mb timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$out/bench_mlp_chunk_$mb.log" 2>&1
+done
 tail -n 12 "$out"/*.log

@@ -72,8 +72,7 @@ class _Block(nn.Module):
             y = ops.swin_window_attention(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift)
             y = nn_ops.linear(y, a.proj.weight, None)
         x, h = nn_ops.layernorm(x, self.norm2, residual=y, want_sum=True, residual_bias=a.proj.bias)
-        f = nn_ops.linear_prepped(h, self.mlp.fc1.weight, None)
-        z = nn_ops.linear_prepped(nn_ops.gelu(f, bias=self.mlp.fc1.bias), self.mlp.fc2.weight, None)
+        z = nn_ops.mlp(h, self.mlp.fc1, self.mlp.fc2)      # fc1 -> GELU (+ deferred fc1 bias) -> fc2 (optionally in L2-sized row chunks)
         return x, z, self.mlp.fc2.bias
 
 

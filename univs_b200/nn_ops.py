@@ -208,6 +208,49 @@ def linear(x, weight, bias=None, cache=True):
     return linear_prepped(prep(x), weight, bias, cache)
 
 
+# L2-resident MLP (opt-in: UNIVS_MLP_CHUNK_MB = working set in MB, e.g. 96).  fc1 -> GELU -> fc2 over the whole token matrix
+# streams the 4C-wide hidden activation through HBM twice as fp32 and twice as operand (4.5 GB per Swin-L stage-1 block at
+# the north-star size).  The three steps are row-independent, so they can run chunk by chunk over the rows with the chunk
+# sized so that its fp32 hidden + operand fit in the 126 MB L2: the GELU pass then reads what the GEMM just wrote from L2,
+# fc2 reads its operand from L2, and because the allocator hands every chunk the same two scratch blocks the dirty lines
+# are overwritten in L2 instead of being written back.  Same kernels, same arithmetic per row; only the schedule changes
+# (the library may pick another tile shape for the smaller M: ~1e-7 differences).  The price is GEMM wave quantisation on
+# small chunks -- to be swept on the GPU (tools/gpu_round2_sweep.sh).
+_mlp_chunk_mb = switches.get("MLP_CHUNK_MB")
+
+
+def set_mlp_chunk_mb(mb: int):
+    global _mlp_chunk_mb
+    _mlp_chunk_mb = int(mb)
+
+
+def mlp_rows_per_chunk(rows: int, hidden: int) -> int:
+    """rows per chunk such that fp32 hidden + GEMM operand of the chunk take about _mlp_chunk_mb MB (multiple of 256);
+    `rows` when chunking is off or would not split"""
+    if _mlp_chunk_mb <= 0:
+        return rows
+    operand_bytes = {"fp16x3": 6, "tf32x3": 8}.get(_policy, 4)
+    per_row = hidden * (4 + operand_bytes)
+    chunk = max(256, (_mlp_chunk_mb << 20) // per_row // 256 * 256)
+    return rows if chunk >= rows else chunk
+
+
+def mlp(h, fc1, fc2):
+    """fc2(GELU(fc1(h) + b1)) without b2 (deferred into the consumer, like everywhere on this path); h is the operand of fc1."""
+    width = h.shape[-1]
+    rows = h.numel() // width
+    chunk = mlp_rows_per_chunk(rows, fc1.out_features)
+    if chunk >= rows:
+        return linear_prepped(gelu(linear_prepped(h, fc1.weight, None), bias=fc1.bias), fc2.weight, None)
+    h2 = h.reshape(rows, width)
+    out = torch.empty((rows, fc2.out_features), device=h.device, dtype=torch.float32)
+    for r0 in range(0, rows, chunk):
+        f = linear_prepped(h2[r0:r0 + chunk], fc1.weight, None)
+        out[r0:r0 + chunk] = linear_prepped(gelu(f, bias=fc1.bias), fc2.weight, None)
+        del f
+    return out.view(*h.shape[:-1], fc2.out_features)
+
+
 _pad_cache = {}
 
 

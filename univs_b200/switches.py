@@ -16,6 +16,7 @@ DEFAULTS = {
     "MHA_TC": 0,            # ops: tcgen05 cross-attention (1; 3 = transposed-V diagnostic variant)
     "ROWWISE_V2": 0,        # csrc/elementwise.cu: bit 0 = 8-wide GELU / ReLU / operand split, bit 1 = wide-store LayerNorm
     "EINSUM_MC": 0,         # ops: cluster / TMA-multicast mask einsum (E resident per CTA pair)
+    "MLP_CHUNK_MB": 0,      # backbone: Swin MLP in row chunks whose fp32 hidden + operand stay in L2 (0 = whole tensor)
     "POOLED_MASKS": 0,      # decoder: intermediate heads from pooled mask features
     "SHARD_DECODER": 0,     # meta_arch: frame-sharded decoder with token exchange (N > 1)
     "FRAME_STREAMS": 1,     # meta_arch: frame groups on CUDA streams (N == 1)
