@@ -33,8 +33,8 @@ if shutil.which("g++") is None or not os.path.exists(os.path.join(build_emu.CUDA
 
 MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
 EMULATED = ("ms_deform_attn_encoder", "groupnorm_cl", "layernorm_multi", "layernorm_merge2x2", "patchify_normalize",
-            "mask_feature_pool", "attn_mask_bits_direct", "swin_window_attention", "mha_core", "mask_einsum",
-            "prepare_mask_features")
+            "mask_feature_pool", "attn_mask_bits_direct", "swin_window_attention", "swin_window_attention_operand", "mha_core",
+            "mask_einsum", "prepare_mask_features")
 
 
 def _as_dev(x):
@@ -55,7 +55,32 @@ def _rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-def test_clip_forward_with_all_switches_on_the_emulator(monkeypatch, tmp_path):
+def _cpu_fp16_gemm(monkeypatch):
+    """torch.addmm(..., out_dtype=float32) on fp16 operands is a CUDA-only library entry; the fp16x3 policy needs it.
+    CPU stand-in for this test: products of fp16 values are exact in fp32, accumulation in fp32 -- what the tensor core does
+    up to the order of the sum."""
+    real = torch.addmm
+
+    def addmm(inp, a, b, *, beta=1, alpha=1, out_dtype=None, out=None):
+        if out_dtype is None:
+            return real(inp, a, b, beta=beta, alpha=alpha) if out is None else real(inp, a, b, beta=beta, alpha=alpha, out=out)
+        r = alpha * (plain(a).float() @ plain(b).float())
+        if beta != 0:
+            r = r + beta * plain(inp).float()
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+    monkeypatch.setattr(torch, "addmm", addmm)
+
+
+@pytest.mark.parametrize("policy", ["tf32x3", "fp16x3"])
+def test_clip_forward_with_all_switches_on_the_emulator(monkeypatch, tmp_path, policy):
+    """fp16x3 is the production default: fp16 operand formats everywhere (window attention writes the projection GEMM's
+    operand itself, GroupNorm writes the padded fp16 operand of the 3x3 taps, the MSDeformAttn kernel the output_proj one)"""
+    if policy == "fp16x3":
+        _cpu_fp16_gemm(monkeypatch)
+        monkeypatch.setattr(nn_ops, "_inplace16", [None])
     lib_path = str(tmp_path / "libunivs_emu_model.so")
     shutil.copy(build_emu.build(), lib_path)
     monkeypatch.setenv("UNIVS_EMU_SMS", "4")
@@ -104,7 +129,7 @@ def test_clip_forward_with_all_switches_on_the_emulator(monkeypatch, tmp_path):
     monkeypatch.setattr(dec, "pooled_masks", True)        # intermediate heads from pooled mask features
     nn_ops.set_fused_glue(True)
     try:
-        with oracle_ops("tf32x3"):
+        with oracle_ops(policy):
             for name in EMULATED:         # inside the context (which restores every operator on exit): not via monkeypatch,
                 setattr(ops, name, bound(name))       # whose teardown would put the oracle functions back for good
             got = model.clip_forward(frames, tg())
@@ -112,7 +137,8 @@ def test_clip_forward_with_all_switches_on_the_emulator(monkeypatch, tmp_path):
         nn_ops.set_fused_glue(False)
 
     print("emulated operators: calls", calls, "seconds", {k: round(v, 1) for k, v in seconds.items()})
-    for name in ("swin_window_attention", "mha_core", "mask_einsum", "ms_deform_attn_encoder", "groupnorm_cl", "layernorm_multi",
+    assert calls["swin_window_attention_operand" if policy == "fp16x3" else "swin_window_attention"] > 0
+    for name in ("mha_core", "mask_einsum", "ms_deform_attn_encoder", "groupnorm_cl", "layernorm_multi",
                  "layernorm_merge2x2", "patchify_normalize", "mask_feature_pool", "attn_mask_bits_direct"):
         assert calls[name] > 0, f"{name} was not exercised"
     assert plain(got["pred_masks"]).shape == want["pred_masks"].shape == (1, Q, T, 16, 24)
