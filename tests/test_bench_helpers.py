@@ -54,15 +54,15 @@ def test_round2_report_promotes_only_green_and_faster_switches(tmp_path):
     spec.loader.exec_module(rep)
     d = tmp_path
     (d / "summary.txt").write_text(
-        "=== default_gpu_tests: python -m pytest\\n    exit 0 (98 passed)\\n=== wintc_tests: x\\n    exit 0 (ok)\\n=== wintc_check: x\\n    exit 0 (ok)\\n"
-        "=== mhatc_tests: x\\n    exit 1 (boom)\\n=== mhatc_check: x\\n    exit 0 (ok)\\n=== glue_tests: x\\n    exit 0 (ok)\\n"
-        "=== rowwise_v2_tests: x\\n    exit 0 (ok)\\n=== parity_at_scale: x\\n    exit 0 (ok)\\n")
+        "=== default_gpu_tests: python -m pytest\n    exit 0 (98 passed)\n=== wintc_tests: x\n    exit 0 (ok)\n=== wintc_check: x\n    exit 0 (ok)\n"
+        "=== mhatc_tests: x\n    exit 1 (boom)\n=== mhatc_check: x\n    exit 0 (ok)\n=== glue_tests: x\n    exit 0 (ok)\n"
+        "=== rowwise_v2_tests: x\n    exit 0 (ok)\n=== parity_at_scale: x\n    exit 0 (ok)\n")
     line = lambda ms, reasons=(): json.dumps({"ms_per_step": ms, "value": 5e3 / ms, "unit": "frames/s", "clocks": {"reasons": list(reasons)}})
-    (d / "bench_default.log").write_text("noise\\n" + line(52.9) + "\\n")
-    (d / "bench_wintc.log").write_text(line(49.5) + "\\n")                 # green + faster
-    (d / "bench_mhatc.log").write_text(line(51.0) + "\\n")                 # faster but its tests failed
-    (d / "bench_glue.log").write_text(line(47.0, ["hw_thermal_slowdown"]) + "\\n")     # throttled run: void
-    (d / "bench_rowwise_v2.log").write_text(line(52.85) + "\\n")           # green but no real gain
+    (d / "bench_default.log").write_text("noise\n" + line(52.9) + "\n")
+    (d / "bench_wintc.log").write_text(line(49.5) + "\n")                 # green + faster
+    (d / "bench_mhatc.log").write_text(line(51.0) + "\n")                 # faster but its tests failed
+    (d / "bench_glue.log").write_text(line(47.0, ["hw_thermal_slowdown"]) + "\n")     # throttled run: void
+    (d / "bench_rowwise_v2.log").write_text(line(52.85) + "\n")           # green but no real gain
     codes, base, rows, promote = rep.report(str(d), 0.3)
     assert base["ms_per_step"] == 52.9 and codes["mhatc_tests"] == 1
     assert promote == {"WIN_TC": 1}
