@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "univs_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 SOURCES = ["common.cu", "groupnorm.cu", "swin_glue.cu", "decoder_glue.cu", "elementwise.cu", "msda.cu",
-           "swin_window_attn_tc.cu", "mha_tc.cu", "mha_combine_emu.cu", "mask_einsum_mc.cu", "mask_einsum_tc.cu", "einsum_entry_emu.cu"]
+           "swin_window_attn_tc.cu", "mha_tc.cu", "mask_einsum_mc.cu", "mask_einsum_tc.cu",
+           "swin_window_attn.cu", "mha.cu", "mask_einsum.cu"]          # the last three: mma.sync / cp.async kernels
 HEADERS = ["common.cuh", "rowwise.cuh", "tc05_math.cuh"]      # tc05.cuh itself is replaced by tests/emu/tc05.cuh
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 
@@ -94,8 +95,7 @@ def rewrite_launch_ex(text):
 def build(force=False):
     os.makedirs(BUILD, exist_ok=True)
     lib = os.path.join(BUILD, "libunivs_emu.so")
-    alias = {"mha_combine_emu.cu": "mha.cu", "einsum_entry_emu.cu": "mask_einsum.cu"}
-    inputs = [os.path.join(CSRC, alias.get(f, f)) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc05.cuh", "build_emu.py")]
+    inputs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc05.cuh", "build_emu.py")]
     if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(p) for p in inputs):
         return lib
     gen = []
@@ -103,15 +103,8 @@ def build(force=False):
         with open(os.path.join(CSRC, f)) as src, open(os.path.join(BUILD, f), "w") as dst:
             dst.write(src.read().replace('#include "../../include/univs_b200.h"', f'#include "{ROOT}/include/univs_b200.h"'))
     for f in SOURCES:
-        if f == "mha_combine_emu.cu":
-            # mha.cu as a whole is out of reach (mma.sync / cp.async kernels); the tcgen05 cross-attention needs only its
-            # split-K merge: the combine kernel and its launcher, cut out of the file as they are written
-            whole = open(os.path.join(CSRC, "mha.cu")).read()
-            k0 = whole.index("// merge split-K partials")
-            k1 = whole.index("// ---- ProCA")
-            l0 = whole.index("// split-K merge for the tensor-core kernel")
-            l1 = whole.index("}  // namespace univs", l0)
-            raw = '#include <math.h>\n#include "common.cuh"\nnamespace univs {\n' + whole[k0:k1] + whole[l0:l1] + "}  // namespace univs\n"
+        if False:
+            pass
         elif f == "mask_einsum_tc.cu":
             # the kernel that IS validated on the B200 keeps private copies of its PTX wrappers; for the emulator they are
             # swapped for tests/emu/tc05.cuh (same names, two of them with another spelling) -- the calibration case of the
@@ -137,27 +130,17 @@ def build(force=False):
                 assert raw.count(old) == 1, old
                 raw = raw.replace(old, new)
             assert "asm" not in raw.replace("namespace", ""), "unexpected inline assembly left in mask_einsum_tc.cu"
-        elif f == "einsum_entry_emu.cu":
-            # mask_einsum.cu holds the mma.sync kernel (out of reach); the cluster kernel needs only its argument check and
-            # its extern "C" entry point, cut out of the file as they are written
-            whole = open(os.path.join(CSRC, "mask_einsum.cu")).read()
-            c0 = whole.index("static int check_einsum_args(")
-            c1 = whole.index("\n}\n", c0) + 3
-            entries = ""
-            for name in ("univs_mask_einsum_f32", "univs_mask_einsum_f16x3", "univs_mask_einsum_f16x3_cluster"):
-                e0 = whole.index(f'extern "C" int {name}(')
-                entries += whole[e0:whole.index("\n}\n", e0) + 3]
-            raw = ('#include "common.cuh"\nnamespace univs {\n'
-                   'int launch_mask_einsum_tc(cudaStream_t st, const float* E, const float* F, int T, int Q, int C, int HW, float* out);\n'
-                   'int launch_mask_einsum_tc_f16(cudaStream_t st, const void* E16, const void* F16, int T, int Q, int C, int HW, float* out);\n'
-                   'int launch_mask_einsum_mc_f16(cudaStream_t st, const void* E16, const void* F16, int T, int Q, int C, int HW, float* out);\n'
-                   '}\nusing namespace univs;\n' + whole[c0:c1] + entries)
         else:
             raw = open(os.path.join(CSRC, f)).read()
+            # the two private m16n8k16 wrappers (inline PTX) -> the emulated warp MMA
+            raw = re.sub(r'(void (?:mma_f16|mha_mma_f16)\(float \(&c\)\[4\], const uint32_t \(&a\)\[4\], uint32_t b0, uint32_t b1\) \{)\s*asm volatile\(.*?\);\s*\}',
+                         r'\1 ::emu::mma_m16n8k16_f16(c, a, b0, b1); }', raw, flags=re.S)
+            assert not re.search(r'asm(?: volatile)?\(\s*"[^"]', raw), f"inline assembly left in {f}"
         if True:
             text = rewrite_launch_ex(rewrite_launches(raw))
             # dynamic shared memory: one emulated buffer per CTA
-            text = re.sub(r"extern __shared__ __align__\(\d+\) unsigned char (\w+)\[\];", r"unsigned char* \1 = ::emu::dyn_smem();", text)
+            text = re.sub(r"extern __shared__ __align__\(\d+\) (unsigned char|float) (\w+)\[\];",
+                          r"\1* \2 = reinterpret_cast<\1*>(::emu::dyn_smem());", text)
         path = os.path.join(BUILD, f.replace(".cu", "_emu.cpp"))
         with open(path, "w") as dst:
             dst.write(text)

@@ -54,6 +54,7 @@ struct Barrier {          // reusable barrier whose participants may leave (a CU
 struct Warp {
   Barrier bar;
   uint32_t slot[32];
+  uint32_t frag_a[32][4], frag_b[32][2];      // mma.sync operand fragments of the 32 lanes
 };
 struct Ctx {
   uint3 tid, bid;
@@ -69,6 +70,7 @@ extern thread_local Ctx ctx;
 extern std::mutex atomic_lock;
 
 void launch(dim3 grid, dim3 block, const std::function<void()>& body, int cluster = 1);
+unsigned char* dyn_smem();                       // the CTA's dynamic shared memory
 int emulated_sm_count();
 
 inline uint32_t exchange(uint32_t v, int src_lane) {
@@ -87,6 +89,58 @@ inline T shfl(T v, int src_lane) {
   u = exchange(u, src_lane);
   std::memcpy(&v, &u, 4);
   return v;
+}
+
+// mma.sync.aligned.m16n8k8 (tf32) / m16n8k16 (f16), fp32 accumulate: every lane deposits its operand fragments, then
+// computes its own four accumulator elements from the fragments of the lanes that hold the row / column it needs
+// (fragment layouts of the PTX ISA: g = lane >> 2, t = lane & 3; A rows g, g+8; C columns 2t, 2t+1)
+inline float half_of(uint32_t reg, int which) {
+  const unsigned short h = (unsigned short)(which ? (reg >> 16) : (reg & 0xffffu));
+  __half v;
+  std::memcpy(&v, &h, 2);
+  return __half2float(v);
+}
+inline float tf32_of(uint32_t reg) {
+  reg &= 0xFFFFE000u;
+  float f;
+  std::memcpy(&f, &reg, 4);
+  return f;
+}
+inline void mma_exchange(const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  Warp* w = ctx.warp;
+  for (int i = 0; i < 4; ++i) w->frag_a[ctx.lane][i] = a[i];
+  w->frag_b[ctx.lane][0] = b0;
+  w->frag_b[ctx.lane][1] = b1;
+  w->bar.wait();
+}
+inline void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  mma_exchange(a, b0, b1);
+  Warp* w = ctx.warp;
+  const int g = ctx.lane >> 2, t = ctx.lane & 3;
+  for (int i = 0; i < 4; ++i) {
+    const int row = g + 8 * (i >> 1), col = 2 * t + (i & 1);
+    float acc = c[i];
+    for (int k = 0; k < 8; ++k)
+      acc += tf32_of(w->frag_a[(row & 7) * 4 + (k & 3)][(row >> 3) + 2 * (k >> 2)]) * tf32_of(w->frag_b[col * 4 + (k & 3)][k >> 2]);
+    c[i] = acc;
+  }
+  w->bar.wait();
+}
+inline void mma_m16n8k16_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  mma_exchange(a, b0, b1);
+  Warp* w = ctx.warp;
+  const int g = ctx.lane >> 2, t = ctx.lane & 3;
+  for (int i = 0; i < 4; ++i) {
+    const int row = g + 8 * (i >> 1), col = 2 * t + (i & 1);
+    float acc = c[i];
+    for (int k = 0; k < 16; ++k) {
+      const int kk = k & 7;
+      acc += half_of(w->frag_a[(row & 7) * 4 + (kk >> 1)][(row >> 3) + 2 * (k >> 3)], kk & 1) *
+             half_of(w->frag_b[col * 4 + (kk >> 1)][k >> 3], kk & 1);
+    }
+    c[i] = acc;
+  }
+  w->bar.wait();
 }
 
 }  // namespace emu

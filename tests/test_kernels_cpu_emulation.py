@@ -59,6 +59,9 @@ def emu(monkeypatch, emu_lib_path):
     monkeypatch.setattr(_cabi, "_lib", _load(emu_lib_path))
     monkeypatch.setattr(ops, "_stream", lambda: 0)
     monkeypatch.setattr(ops, "_gn_ws", {})
+    monkeypatch.setattr(ops, "_ws_cache", {})
+    chk = ops._chk            # tensors the wrappers allocate themselves are plain CPU tensors: let them through as well
+    monkeypatch.setattr(ops, "_chk", lambda t, name, dtype=torch.float32: chk(torch.Tensor._make_subclass(_Dev, t), name, dtype))
     yield ops
 
 
@@ -281,3 +284,54 @@ def test_rowwise_v2_kernels_are_bit_identical_on_the_emulator(emu_lib_path, monk
     for a, b in zip(base, v2):
         assert a.dtype == b.dtype and a.shape == b.shape
         assert torch.equal(a.contiguous().view(torch.int16), b.contiguous().view(torch.int16))
+
+
+# ------------------------------------------------------------------ the mma.sync / cp.async kernels (validated on the B200)
+# Their warp-level MMAs run on the emulator too (fragments exchanged between the 32 host threads of a warp, PTX fragment
+# layouts): a CPU regression harness for the default path, and the second calibration of the emulator against code whose
+# behaviour on the hardware is known.
+@pytest.mark.parametrize("window,H,W,nH,shift", [(7, 14, 21, 2, 3), (7, 10, 9, 1, 0), (12, 24, 20, 1, 6), (4, 8, 8, 3, 2)])
+@pytest.mark.parametrize("precision", [ops.PREC_TF32X3, ops.PREC_TF32])
+def test_default_window_attention_kernels_on_the_emulator(emu, window, H, W, nH, shift, precision):
+    g = torch.Generator().manual_seed(window * 100 + H)
+    C = nH * 32
+    qkv = torch.randn(1, H, W, 3 * C, generator=g)
+    bias, table = torch.randn(3 * C, generator=g) * 0.2, torch.randn((2 * window - 1) ** 2, nH, generator=g) * 0.5
+    want = ops_ref.swin_window_attention(qkv, bias, table, nH, window, shift)
+    got = emu.swin_window_attention(dev(qkv), dev(bias), dev(table), nH, window, shift, precision)
+    _close(got, want, 2e-5 if precision == ops.PREC_TF32X3 else 4e-3)
+    if precision == ops.PREC_TF32X3:
+        op = plain(emu.swin_window_attention_operand(dev(qkv), dev(bias), dev(table), nH, window, shift)).float()
+        _close(op[..., 2 * C:] + op[..., :C] / 2048.0, want, 2e-5)
+
+
+@pytest.mark.parametrize("precision", [ops.PREC_TF32X3, ops.PREC_TF32])
+def test_default_attention_core_and_einsum_kernels_on_the_emulator(emu, precision):
+    from tests.test_tc_kernels_cpu_emulation import _mask_case
+    g = torch.Generator().manual_seed(31)
+    B, Lq, Lk, heads = 2, 37, 150, 2
+    q, k, v = (torch.randn(B, L, heads * 32, generator=g) for L in (Lq, Lk, Lk))
+    mask, bits, row_open = _mask_case(g, B, Lq, Lk)
+    got = emu.mha_core(dev(q), dev(k), dev(v), dev(bits), dev(row_open), precision)
+    want = ops_ref.mha_core(q, k, v, heads, mask, unmask_full_rows=True)
+    _close(got, want, 2e-5 if precision == ops.PREC_TF32X3 else 4e-3)
+    E, F = torch.randn(2, 20, 64, generator=g), torch.randn(2, 130, 64, generator=g)
+    got = emu.mask_einsum_mma(dev(E), dev(F), precision)
+    _close(got, ops_ref.mask_einsum(E, F.transpose(1, 2)), 5e-6 if precision == ops.PREC_TF32X3 else 2e-3)
+
+
+def test_default_decoder_glue_kernels_on_the_emulator(emu):
+    g = torch.Generator().manual_seed(32)
+    Q, T, H, W = 5, 2, 8, 12
+    logits = torch.randn(Q, T, H * W, generator=g)
+    logits[1, 0] = -2.0
+    bits, row_open = emu.attn_mask_bits(dev(logits), (H, W), (4, 6))
+    want = ops_ref.attn_mask_from_logits(logits, (H, W), (4, 6)).bool()
+    assert torch.equal(cpu_backend.unpack_bits(plain(bits), 24).bool(), want)
+    assert torch.equal(plain(row_open) != 0, ~want.all(-1))
+    P, L, C = 3, 5, 64
+    qq, ks, vs = (torch.randn(P, T, C, generator=g) for _ in range(3))
+    km, vm = torch.randn(P, T, L, C, generator=g), torch.randn(P, T, L, C, generator=g)
+    _close(emu.proca_core(dev(qq), dev(ks), dev(vs), dev(km), dev(vm)), ops_ref.proca_core(qq, ks, vs, km, vm, 2), 2e-5)
+    x = torch.randn(7, 33, generator=g)
+    assert torch.equal(plain(emu.round_tf32(dev(x))), cpu_backend._split(x)[..., :33].contiguous())

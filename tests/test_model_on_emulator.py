@@ -33,8 +33,8 @@ if shutil.which("g++") is None or not os.path.exists(os.path.join(build_emu.CUDA
 
 MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
 EMULATED = ("ms_deform_attn_encoder", "groupnorm_cl", "layernorm_multi", "layernorm_merge2x2", "patchify_normalize",
-            "mask_feature_pool", "attn_mask_bits_direct", "swin_window_attention", "swin_window_attention_operand", "mha_core",
-            "mask_einsum", "prepare_mask_features")
+            "mask_feature_pool", "attn_mask_bits_direct", "attn_mask_bits", "swin_window_attention",
+            "swin_window_attention_operand", "mha_core", "mask_einsum", "prepare_mask_features")
 
 
 def _as_dev(x):

@@ -41,6 +41,10 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& sma
 //   a0:(g,t) a1:(g+8,t) a2:(g,t+4) a3:(g+8,t+4);  b0:(k=t,n=g) b1:(k=t+4,n=g);
 //   c0:(g,2t) c1:(g,2t+1) c2:(g+8,2t) c3:(g+8,2t+1)
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#ifdef UNIVS_CPU_EMU
+  ::emu::mma_m16n8k8_tf32(c, a, b0, b1);
+  return;
+#endif
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -55,6 +59,12 @@ __device__ __forceinline__ void mma_tf32x3(float (&c)[4], const uint32_t (&ab)[4
   mma_tf32(c, ab, bb0, bb1);
 }
 
+#ifdef UNIVS_CPU_EMU      // tests/emu: the copy happens at once (a legal schedule of the asynchronous one)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
@@ -64,6 +74,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
+#endif
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
