@@ -335,3 +335,17 @@ def test_default_decoder_glue_kernels_on_the_emulator(emu):
     _close(emu.proca_core(dev(qq), dev(ks), dev(vs), dev(km), dev(vm)), ops_ref.proca_core(qq, ks, vs, km, vm, 2), 2e-5)
     x = torch.randn(7, 33, generator=g)
     assert torch.equal(plain(emu.round_tf32(dev(x))), cpu_backend._split(x)[..., :33].contiguous())
+
+
+def test_query_chunking_beyond_256_queries_on_the_emulator(emu):
+    """the body of tests/test_ops_gpu.py::test_mask_einsum_more_than_256_queries (added after the last GPU run of round 1),
+    on the emulator: 600 queries run as 256 + 256 + 88, tcgen05 and register kernels"""
+    torch.manual_seed(14)
+    T, Q, C, HW = 1, 600, 64, 260
+    E, F = torch.randn(T, Q, C), torch.randn(T, HW, C)
+    want = ops_ref.mask_einsum(E.double(), F.transpose(1, 2).double()).float()
+    for mode in ("f16x3", "mma3x"):
+        feats = emu.prepare_mask_features(dev(F), mode)
+        got = emu.mask_einsum(dev(E), dev(feats), mode=mode)
+        assert plain(got).shape == (Q, T, HW)
+        _close(got, want, 5e-6)
