@@ -145,3 +145,59 @@ def test_clip_forward_with_all_switches_on_the_emulator(monkeypatch, tmp_path, p
     for k in ("pred_masks", "pred_logits", "pred_embds"):
         assert not torch.isnan(plain(got[k])).any()
         assert _rel(got[k], want[k]) < 1e-3, (k, _rel(got[k], want[k]))
+
+
+DEFAULT_PATH = ("layernorm", "gelu", "relu", "split_operand", "split_tf32", "round_tf32", "ms_deform_attn_encoder", "swin_window_attention",
+                "swin_window_attention_operand", "mha_core", "mask_einsum", "prepare_mask_features", "attn_mask_bits", "proca_core")
+
+
+def test_default_path_clip_forward_on_the_emulator(monkeypatch, tmp_path):
+    """The DEFAULT path (no switch on) under the production fp16x3 policy with EVERY operator running from its kernel source
+    on the emulator -- the host code that changed after the last GPU run of round 1 (K/V operands prepared once per level,
+    the MLP helper, encoder layers returning carries, scratch slots) driving the real wrappers and the real kernels.
+    Category prompts (ProCA) included."""
+    _cpu_fp16_gemm(monkeypatch)
+    monkeypatch.setattr(nn_ops, "_inplace16", [None])
+    lib_path = str(tmp_path / "libunivs_emu_default.so")
+    shutil.copy(build_emu.build(), lib_path)
+    T, Q = 2, 6
+    swin = dict(embed_dim=32, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8], window_size=4)
+    parts = mf.build_product_model(swin, num_queries=Q, num_frames=T, clip_emb=mf.make_clip_emb(), enc_layers=1, dec_layers=2)
+    mf.load_keyed(parts)
+    shapes = {f"res{i + 2}": ShapeSpec(channels=32 * 2 ** i, stride=4 * 2 ** i) for i in range(4)}
+    head = MaskFormerHead(shapes, num_classes=133, pixel_decoder=parts[1], transformer_predictor=parts[2])
+    model = UniVS_Prompt(backbone=parts[0], sem_seg_head=head, pixel_mean=MEAN, pixel_std=STD)
+    g = torch.Generator().manual_seed(13)
+    frames = (torch.rand(T, 3, 32, 64, generator=g) * 255).round()
+    tg = lambda: [{"task": "detection", "dataset_name": "bdd_track", "prompt_type": "text"}]        # 8 category prompts -> ProCA
+    with oracle_ops("fp32"):
+        want = model.clip_forward(frames, tg())
+    real = {k: getattr(ops, k) for k in DEFAULT_PATH}
+    calls = {k: 0 for k in DEFAULT_PATH}
+
+    def bound(name):
+        fn = real[name]
+
+        def call(*a, **k):
+            calls[name] += 1
+            return fn(*[_as_dev(x) for x in a], **{kk: _as_dev(v) for kk, v in k.items()})
+        return call
+
+    chk = ops._chk
+    monkeypatch.setattr(_cabi, "_lib", _load(lib_path))
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops, "_chk", lambda t, name, dtype=torch.float32: chk(_as_dev(t), name, dtype))
+    monkeypatch.setattr(ops, "_ws_cache", {})
+    monkeypatch.setattr(ops, "_einsum_mode", "f16x3")
+    monkeypatch.setattr(nn_ops, "_wcache", {})
+    with oracle_ops("fp16x3"):
+        for name in DEFAULT_PATH:
+            setattr(ops, name, bound(name))
+        got = model.clip_forward(frames, tg())
+    for name in ("layernorm", "gelu", "split_operand", "ms_deform_attn_encoder", "swin_window_attention_operand", "mha_core",
+                 "mask_einsum", "attn_mask_bits", "proca_core"):
+        assert calls[name] > 0, f"{name} was not exercised"
+    assert plain(got["pred_masks"]).shape == want["pred_masks"].shape == (1, Q + 8, T, 8, 16)
+    for k in ("pred_masks", "pred_logits", "pred_embds"):
+        assert not torch.isnan(plain(got[k])).any()
+        assert _rel(got[k], want[k]) < 1e-3, (k, _rel(got[k], want[k]))
