@@ -218,7 +218,10 @@ def main():
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        if dev_type == "cuda":
+            dist.init_process_group("nccl", device_id=dev)
+        else:                                   # tests/test_bench_dryrun.py: the same control flow over gloo on the CPU
+            dist.init_process_group("gloo")
         group = dist.group.WORLD
     set_precision(args.precision)
 

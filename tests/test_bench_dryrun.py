@@ -108,3 +108,44 @@ def test_plain_cpu_run_fails_loudly(monkeypatch):
     monkeypatch.setitem(bench.WORKLOADS, "dry", ("tiny", 2, 64, 96, 8))
     with pytest.raises(UnivsB200Error):
         bench.main()
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    """one rank of `torchrun ... bench.py --gpus 2` on the CPU: gloo, oracle operators, faked CUDA timers"""
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), UNIVS_BENCH_DEVICE="cpu", UNIVS_CPU_THREADS="2")
+    torch.set_num_threads(2)
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.Event = _Event
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+    bench.WORKLOADS["dry"] = ("tiny", 3, 64, 96, 8)               # T = 3 over 2 ranks: ragged frame shards
+    sys.argv = ["bench.py", "--gpus", str(world), "--workload", "dry", "--steps", "1", "--warmup", "1", "--no-graph",
+                "--precision", "fp32"]
+    buf = io.StringIO()
+    with oracle_ops(), contextlib.redirect_stdout(buf):
+        bench.main()
+    with open(os.path.join(out_dir, f"rank{rank}.out"), "w") as f:
+        f.write(buf.getvalue())
+
+
+def test_frame_sharded_run_control_flow_over_gloo(tmp_path):
+    """the multi-GPU bench (driver: torchrun, one rank per GPU, NCCL) with two CPU processes over gloo: barrier + max-over-
+    ranks timing, frame sharding + all-gather inside the step, only rank 0 prints, n_gpus / parallelism fields"""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    out0, out1 = (open(tmp_path / f"rank{r}.out").read() for r in (0, 1))
+    assert out1.strip() == ""
+    lines = [l for l in out0.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for k in CONTRACT:
+        assert k in line, k
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["value"] > 0
+    assert line["config"]["parallelism"].startswith("frame-shard x2") and line["config"]["execution"] == "eager"
+    assert line["cpu_baseline"] is None                    # measured at N = 1 only
+    assert line["e2e"]["value"] > 0
