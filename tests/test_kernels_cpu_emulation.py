@@ -349,3 +349,16 @@ def test_query_chunking_beyond_256_queries_on_the_emulator(emu):
         got = emu.mask_einsum(dev(E), dev(feats), mode=mode)
         assert plain(got).shape == (Q, T, HW)
         _close(got, want, 5e-6)
+
+
+def test_graft_entry_smoke_runs_on_the_emulator(emu, monkeypatch):
+    """__graft_entry__.smoke() -- what the driver runs on cuda:0 before the bench -- with `.cuda()` handing out emulator-backed
+    tensors: the tcgen05 einsum, mask bits, the masked attention core, window attention and MSDeformAttn, each against the
+    oracle inside smoke() itself"""
+    import __graft_entry__ as entry
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: dev(self))
+    monkeypatch.setattr(torch.Tensor, "cpu", lambda self, *a, **k: plain(self))
+    entry.smoke()
