@@ -13,8 +13,42 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the read-only reference tree at /root/reference")
 
 
+def _emulate_gpu():
+    """UNIVS_EMULATE=1: run `-m gpu` tests WITHOUT a GPU on the CPU emulator of tests/emu (the kernels' sources compiled by
+    g++): `.cuda()` hands out emulator-backed tensors, the C ABI is the emulated library.  For checking the gated GPU tests
+    themselves (shapes, calls, tolerances) before they get GPU time; big cases are only feasible on the hardware."""
+    import torch
+    from tests.emu import build_emu
+    from tests.test_kernels_cpu_emulation import _Dev, _load, plain
+    from univs_b200 import _cabi, ops
+    as_dev = lambda t: t if isinstance(t, _Dev) else torch.Tensor._make_subclass(_Dev, t)
+    _cabi._lib = _load(build_emu.build())
+    ops._stream = lambda: 0
+    chk = ops._chk
+    ops._chk = lambda t, name, dtype=torch.float32: chk(as_dev(t), name, dtype)
+    ops._chk_t = lambda t, name, dtype=torch.float32: (chk(as_dev(t), name, dtype), as_dev(t))[1]
+    torch.cuda.is_available = lambda: True
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.Tensor.cuda = lambda self, *a, **k: as_dev(self)
+    real_to = torch.Tensor.to
+    is_cuda = lambda d: (isinstance(d, str) and d.startswith("cuda")) or (isinstance(d, torch.device) and d.type == "cuda")
+
+    def to(self, *a, **k):
+        rest = [x for x in a if not is_cuda(x)]
+        kw = {kk: v for kk, v in k.items() if not (kk == "device" and is_cuda(v))}
+        wanted = len(rest) != len(a) or len(kw) != len(k)
+        r = real_to(self, *rest, **kw) if (rest or kw) else self
+        return as_dev(r) if wanted else r
+    torch.Tensor.to = to
+    torch.Tensor.cpu = lambda self, *a, **k: plain(self)
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
+    if os.environ.get("UNIVS_EMULATE") == "1" and not torch.cuda.is_available():
+        _emulate_gpu()
     has_gpu = torch.cuda.is_available()
     from oracle import ref_shim
     has_ref = ref_shim.available()
