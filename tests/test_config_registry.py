@@ -99,3 +99,18 @@ def test_switch_defaults_are_the_round1_path(monkeypatch):
     monkeypatch.setenv("UNIVS_WIN_TC", "1")
     monkeypatch.setenv("UNIVS_FRAME_STREAMS", "2")
     assert switches.get("win_tc") == 1 and switches.active()["FRAME_STREAMS"] == 2
+
+
+def test_task_heads_build_from_the_model_cfg():
+    """attach_task_heads() reads the keys the reference heads' from_config read (defaults where a config omits them)"""
+    cfg = make_cfg("tiny", 10, 2, clip_emb=torch.randn(3938, 640))
+    model = build_model(cfg)
+    assert model.task_heads is None
+    model.attach_task_heads(thing_ids={1, 2}, thing_contiguous_ids=[0, 1])
+    h = model.task_heads
+    assert {"vis_fast", "vos", "vps", "entity", "image", "semantic_extraction"} <= set(h)
+    assert h["entity"].num_frames == 2 and h["entity"].num_queries == 10 and h["entity"].num_frames_window_output == 10
+    assert h["vps"].thing_ids == {1, 2} and h["image"].thing_contiguous_ids == [0, 1]
+    assert h["unified"] is False and h["tracker_type"] == "minvis"
+    cfg.MODEL.UniVS.TEST["VIDEO_UNIFIED_INFERENCE_ENABLE"] = True
+    assert build_model(cfg).attach_task_heads().task_heads["unified"] is True
