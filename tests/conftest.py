@@ -43,6 +43,7 @@ def _emulate_gpu():
     torch.Tensor.to = to
     torch.Tensor.cpu = lambda self, *a, **k: plain(self)
     torch.nn.Module.cuda = lambda self, *a, **k: self
+    torch.Tensor.is_cuda = property(lambda self: True)       # intermediates of a model forward are plain CPU tensors
     real_addmm = torch.addmm
 
     def addmm(inp, a, b, *, beta=1, alpha=1, out_dtype=None, out=None):
