@@ -35,11 +35,10 @@ def _emulate_gpu():
     is_cuda = lambda d: (isinstance(d, str) and d.startswith("cuda")) or (isinstance(d, torch.device) and d.type == "cuda")
 
     def to(self, *a, **k):
-        rest = [x for x in a if not is_cuda(x)]
-        kw = {kk: v for kk, v in k.items() if not (kk == "device" and is_cuda(v))}
-        wanted = len(rest) != len(a) or len(kw) != len(k)
-        r = real_to(self, *rest, **kw) if (rest or kw) else self
-        return as_dev(r) if wanted else r
+        if not (any(is_cuda(x) for x in a) or is_cuda(k.get("device"))):
+            return real_to(self, *a, **k)
+        dtype = next((x for x in a if isinstance(x, torch.dtype)), k.get("dtype"))      # .to("cuda", dtype, non_blocking)
+        return as_dev(real_to(self, dtype) if dtype is not None else self)
     torch.Tensor.to = to
     torch.Tensor.cpu = lambda self, *a, **k: plain(self)
     torch.nn.Module.cuda = lambda self, *a, **k: self
