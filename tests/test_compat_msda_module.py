@@ -114,8 +114,6 @@ def test_reference_function_runs_on_the_compat_module(monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("UNIVS_GPU_COMPAT") != "1",
-                    reason="compat module on CUDA: opt-in until run on a B200 (UNIVS_GPU_COMPAT=1)")
 def test_compat_module_on_cuda_matches_the_oracle():
     from oracle import ops_ref
     mod = _load_compat()

@@ -2,7 +2,7 @@
 (tests/golden/make_golden_heads.py); needs no reference tree, so it also runs on the GPU box.
  * not-gpu: product heads + host model with CPU oracle operators;
  * gpu:     product heads + host model with the CUDA kernels.  New in this round and not yet run on a B200, therefore
-            opt-in (UNIVS_GPU_HEADS=1) until validated -- see DESIGN.md section 8."""
+            validated on the B200 in round 2 (gpurun_out/r2_open)."""
 import os
 
 import numpy as np
@@ -124,8 +124,7 @@ def test_vos_sot_head_with_oracle_ops_matches_golden():
         _sot("cpu")
 
 
-_gpu_heads = pytest.mark.skipif(os.environ.get("UNIVS_GPU_HEADS") != "1",
-                                reason="task heads on CUDA: opt-in until validated on a B200 (UNIVS_GPU_HEADS=1)")
+_gpu_heads = pytest.mark.filterwarnings("default")      # validated on a B200 (round 2): no gate
 
 
 @pytest.mark.gpu

@@ -156,8 +156,7 @@ def test_dataflow_model_one_head(nsplit, vt):
 
 
 # ---- GPU parity ----------------------------------------------------------------------------------------------------
-_gpu_mhatc = pytest.mark.skipif(os.environ.get("UNIVS_GPU_MHATC") != "1",
-                                reason="opt-in (UNIVS_GPU_MHATC=1): tcgen05 cross-attention not yet validated on a B200")
+_gpu_mhatc = pytest.mark.filterwarnings("default")      # validated on a B200 (round 2): no gate
 
 
 def _rel(a, b):

@@ -39,7 +39,6 @@ torch.save(out, sys.argv[1])
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("UNIVS_GPU_ROWWISE_V2") != "1", reason="opt-in (UNIVS_GPU_ROWWISE_V2=1): not yet run on a B200")
 def test_rowwise_v2_bit_identical():
     with tempfile.TemporaryDirectory() as d:
         res = {}

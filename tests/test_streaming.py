@@ -35,6 +35,37 @@ def test_clip_stream_equals_per_clip_recompute():
         assert err < 1e-4, (s, err)
 
 
+def test_clip_stream_window_larger_than_its_capacity():
+    """Heads push NUM_FRAMES_WINDOW_TEST frames at a time; reference configs have W > 2T (T=2 / W=5, T=3 / W=5): frames a
+    clip still needs must survive the push (video_vis_fast.py:97)."""
+    class _Dec(torch.nn.Module):
+        def forward(self, ms, mf, bfe, mask, targets):
+            return {"frames": mf[:, 0, 0, 0].clone()}
+
+    class _Pix:
+        @staticmethod
+        def forward_features(feats):
+            x = feats["x"]
+            return x, x, x, [x, x, x]
+
+    class _Model:
+        sem_seg_head = type("H", (), {"pixel_decoder": _Pix(), "predictor": _Dec()})()
+        backbone = staticmethod(lambda x: {"x": x})
+
+    for T, Wn, V in ((2, 5, 11), (3, 5, 9), (2, 7, 8)):
+        stream = ClipStream(_Model(), T)                     # default capacity 2T < W
+        video = torch.arange(V, dtype=torch.float32).view(V, 1, 1, 1).expand(V, 4, 2, 2).contiguous()
+        pushed = 0
+        for i in range(V - T + 1):
+            while pushed < i + T:
+                k = min(Wn, V - pushed)
+                stream.push_preprocessed(pushed, video[pushed:pushed + k])
+                pushed += k
+            out = stream.clip(i, [{}])
+            assert out["frames"].tolist() == list(range(i, i + T))
+            assert len(stream._cache) <= max(stream.capacity, Wn + T)
+
+
 def test_frame_groups_equal_whole_clip():
     """UniVS_Prompt(frame_streams=g): backbone + pixel decoder per contiguous frame group (one CUDA stream per group on the
     GPU, sequential on CPU), decoder once -- must equal the ungrouped forward (frames are independent up to the decoder)."""

@@ -94,7 +94,8 @@ class InferenceVideoVISFast(nn.Module):
             raise KeyError(dataset_name)
         num_classes, first_class = COMBINED_DATASETS_CATEGORY_INFO[dataset_name]
 
-        stream = ClipStream(model, T) if self.reuse_features else None
+        stream = ClipStream(model, T, max_cached_frames=2 * max(T, self.num_frames_window_test)) \
+            if self.reuse_features else None
         pushed, window = 0, (0, 0, None)
         logit_sum, masks, memory, n_clips = None, None, [], 0
         for i in range(V - T + 1):

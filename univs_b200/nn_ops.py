@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import contextlib
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -64,6 +65,22 @@ def g1_chunk(K: int) -> int:
     return K
 
 
+def _owner(w: torch.Tensor) -> torch.Tensor:
+    """the tensor whose lifetime bounds the validity of a cache entry made from `w`: the base of a view (in_proj slices are
+    fresh view objects on every call), else `w` itself"""
+    return w._base if w._base is not None else w
+
+
+def _owner_ref(w):
+    return weakref.ref(_owner(w))
+
+
+def _same_owner(ref, w) -> bool:
+    """A cache hit needs the SAME live tensor object, not just the same address: the allocator hands a freed model's
+    addresses to the next model of the same architecture (same shape, same _version), whose weights differ."""
+    return ref() is _owner(w)
+
+
 def _split_weight(w: torch.Tensor, cache=True):
     """2-D weight [N,K] -> policy-specific B operands, cached per parameter version.
     tf32x3: (Wh [N,K], Wlh [N,2K] = [Wl | Wh]).
@@ -72,13 +89,13 @@ def _split_weight(w: torch.Tensor, cache=True):
     key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()))        # views of packed parameters (in_proj slices) hit too
     sig = (w.data_ptr(), w._version, tuple(w.shape), _policy)
     ent = _wcache.get(key) if cache else None
-    if ent is None or ent[0] != sig:
+    if ent is None or ent[0] != sig or not _same_owner(ent[3], w):
         w2d = w.detach().float().reshape(w.shape[0], -1).contiguous()
         N, K = w2d.shape
         if _policy == "tf32x3":
             hl = ops.split_operand(w2d, "tf32")                              # [N,2K] = [hi | lo]
             hi, lo = hl[:, :K], hl[:, K:]
-            ent = (sig, hi.contiguous(), torch.cat([lo, hi], 1).contiguous())
+            ent = (sig, hi.contiguous(), torch.cat([lo, hi], 1).contiguous(), _owner_ref(w))
         else:
             amax = float(w2d.abs().max())
             s = 0 if amax == 0.0 else max(-24, min(24, int(torch.floor(torch.log2(torch.tensor(8192.0 / amax))))))
@@ -86,7 +103,7 @@ def _split_weight(w: torch.Tensor, cache=True):
             kc = ops.f16_chunk(K)
             v = a3.view(N, K // kc, 3, kc)
             b3 = torch.stack([v[:, :, 1], v[:, :, 0], v[:, :, 2]], 2).reshape(N, 3 * K).contiguous()   # [hi_s | lo' | hi]
-            ent = (sig, b3, 2.0 ** -s)
+            ent = (sig, b3, 2.0 ** -s, _owner_ref(w))
         if cache:
             _wcache[key] = ent
     return ent[1], ent[2]
@@ -310,9 +327,9 @@ def _conv_weight_taps(weight):
     key = ("conv", weight.data_ptr(), tuple(weight.shape))
     sig = (weight.data_ptr(), weight._version)
     ent = _wcache.get(key)
-    if ent is None or ent[0] != sig:
+    if ent is None or ent[0] != sig or not _same_owner(ent[2], weight):
         taps = [_split_weight(weight.detach()[:, :, dy, dx].contiguous(), cache=False) for dy in range(kh) for dx in range(kw)]
-        ent = (sig, taps)
+        ent = (sig, taps, _owner_ref(weight))
         _wcache[key] = ent
     return ent[1]
 

@@ -25,6 +25,7 @@ class ClipStream:
         self._cache = OrderedDict()          # frame index -> (mask_features [1,C,h,w], [ms_1/32, ms_1/16, ms_1/8])
         self.image_size = None
         self.frames_encoded = 0
+        self._floor = 0                      # first frame a future clip may still need (clips move forward)
 
     @torch.no_grad()
     def push(self, first_index: int, frames):
@@ -50,7 +51,9 @@ class ClipStream:
         for j in range(mf.shape[0]):
             self._cache[first_index + j] = (mf[j:j + 1], [m[j:j + 1] for m in ms])
             self.frames_encoded += 1
-        while len(self._cache) > self.capacity:
+        # `capacity` is a soft bound: a frame at or after the start of the oldest clip still to come is never evicted
+        # (callers push NUM_FRAMES_WINDOW_TEST frames at a time, which may exceed 2*T: reference configs T=3 / W=5)
+        while len(self._cache) > self.capacity and next(iter(self._cache)) < self._floor:
             self._cache.popitem(last=False)
 
     @torch.no_grad()
@@ -66,6 +69,9 @@ class ClipStream:
         ms = [torch.cat([self._cache[i][1][l] for i in idx], 0) for l in range(3)]
         # keep the channel-last storage the decoder consumes without a copy
         mf = mf.contiguous(memory_format=torch.channels_last)
+        self._floor = max(self._floor, start)
+        while len(self._cache) > self.capacity and next(iter(self._cache)) < self._floor:
+            self._cache.popitem(last=False)
         tg = targets[0]
         tg["frame_indices"] = torch.arange(start, start + n, device=mf.device)
         tg.setdefault("num_frames", self.T)
