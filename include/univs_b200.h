@@ -158,6 +158,22 @@ int univs_mha_tc_forward_f32(void* stream, const float* q, const float* k, const
                              const int32_t* row_open, int mask_batch, int batch, int len_q, int len_k, int channels,
                              int flags, void* workspace, float* out);
 
+/* ---- Dense layer with fused epilogue on the tcgen05 tensor cores (gemm_tc.cu).  Replaces nn.Linear +
+ * the activation / residual behind it (swin.py:35-41, 138-169, 292-293; ms_deform_attn.py:98-120; transformer_layers.py):
+ *   y[t, n] = act(alpha * sum_k x[t, k] * w[n, k] + bias[n]) + addend[t, n]
+ * Operands are fp16 pairs, value = hi + lo' * 2^-11 (lo' = the residual scaled by 2^11): x16 rows [tokens, ldx] halfs with the
+ * hi block at column x_hi_off and the lo' block at x_lo_off (k columns each); w16 rows [channels, ldw] likewise (weights
+ * pre-scaled by a power of two that `alpha` undoes).  Both the [lo' | hi*2^-11 | hi] K-chunk container of the row-wise kernels
+ * (split = -Kc; offsets 2*Kc and 0) and the compact [hi | lo'] container written by this function fit.  k % 8 == 0; one
+ * call accumulates at most one K-chunk (callers slice k > 1536 and pass the partial result as `addend`).
+ * Outputs (each nullable, at least one): out f32 [tokens, ldo]; out16 = y as the next layer's operand, fp16 [tokens, ld16] with
+ * hi at column n and lo' at column out16_lo_off + n.  addend f32 [tokens, ldadd] may alias out.
+ * activation: 0 none, 1 GELU (erf), 2 ReLU.  bias f32 [channels] nullable. */
+int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, int64_t x_hi_off, int64_t x_lo_off, const void* w16,
+                        int64_t ldw, int64_t w_hi_off, int64_t w_lo_off, int64_t tokens, int channels, int k, float alpha,
+                        const float* bias, const float* addend, int64_t ldadd, float* out, int64_t ldo, void* out16,
+                        int64_t ld16, int64_t out16_lo_off, int activation);
+
 /* ---- ProCA attention core (a14): every (prompt p, frame t) query attends to its own token and its L
  * prompt-memory tokens.  q,k_self,v_self [P,T,C]; k_mem,v_mem [P,Tm,L,C], Tm in {1,T}; out [P,T,C]. */
 int univs_proca_forward_f32(void* stream, const float* q, const float* k_self, const float* v_self,

@@ -135,7 +135,17 @@ def _layernorm_multi(x, weight, bias, eps=1e-5, residual=None, residual_bias=Non
     return (y if want_f32 else None), op, op_pos
 
 
+def _gemm_tc(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None, out=None, want_f32=True, want_operand=False,
+             act=0):
+    y, y16 = ops_ref.gemm_f16x3(x16, x_offs, w16, w_offs, k, alpha, bias, addend, act)
+    if out is not None:
+        out.copy_(y)
+        y = out
+    return (y if (want_f32 or out is not None) else None), (y16 if want_operand else None)
+
+
 _PATCH = {"layernorm": _layernorm,
+          "gemm_f16x3_tc": _gemm_tc,
           "layernorm_multi": _layernorm_multi,
           "groupnorm_cl": _groupnorm_cl,
           "patchify_normalize": lambda f, m, s, padded, patch=4, split=None: _maybe_split(

@@ -312,3 +312,24 @@ def layernorm_merge2x2(x_cl, weight, bias, eps=1e-5):
     x = torch.nn.functional.pad(x_cl, (0, 0, 0, W % 2, 0, H % 2))
     x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
     return torch.nn.functional.layer_norm(x, (4 * C,), weight, bias, eps)
+
+
+def gemm_f16x3(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None, act=0):
+    """CPU restatement of univs_gemm_f16x3_tc (csrc/gemm_tc.cu): the dense layer the reference computes with nn.Linear + the
+    activation / residual behind it (swin.py:35-41 Mlp, :138-169 qkv / proj; ms_deform_attn.py:98-120;
+    transformer_layers.py).  Operands are fp16 pairs, value = hi + lo' * 2^-11.  Returns (y fp32, y as the compact operand
+    [hi | lo' ] fp16)."""
+    def value(t, offs):
+        return t[:, offs[0]: offs[0] + k].double() + t[:, offs[1]: offs[1] + k].double() * 2.0 ** -11
+    y = (value(x16, x_offs) @ value(w16, w_offs).t() * alpha).float()
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = torch.nn.functional.gelu(y)
+    elif act == 2:
+        y = torch.relu(y)
+    if addend is not None:
+        y = y + addend
+    hi = y.clamp(-65504.0, 65504.0).half()
+    lo = ((y - hi.float()) * 2048.0).clamp(-65504.0, 65504.0).half()
+    return y, torch.cat([hi, lo], 1)

@@ -319,7 +319,7 @@ def test_pooled_mask_kernels_gpu(mode):
             got = got[..., :C].float() + got[..., C:].float()
         assert _rel(got.cpu(), want) < 2e-6
         small = ops_ref.mask_einsum(E, want.transpose(1, 2))
-        bits, ro = ops.attn_mask_bits_direct(small.cuda())
+        bits, ro = ops.attn_mask_bits_direct(small.contiguous().cuda())
         m = ops_ref.attn_mask_direct(small).bool()
         assert torch.equal(bits.cpu(), ops.pack_mask_bits(m))
         assert torch.equal(ro.cpu(), (~m.all(-1)).to(torch.int32))

@@ -1,0 +1,109 @@
+"""csrc/gemm_tc.cu (tcgen05 dense layer with fused epilogue) EXECUTED ON THE CPU emulator of tests/emu (the kernel source
+compiled by g++ against the CPU implementation of tc05.cuh: TMA boxes with zero fill and SWIZZLE_128B, K-major descriptors,
+in-order asynchronous tensor pipe, TMEM, mbarrier protocol), driven through the real ops wrapper, against the oracle
+restatement (oracle/ops_ref.py::gemm_f16x3) and against the fp64 product of the original fp32 values."""
+import os
+import shutil
+
+import pytest
+import torch
+
+from oracle import cpu_backend, ops_ref
+from tests.emu import build_emu
+from tests.test_kernels_cpu_emulation import _Dev, _load, dev, plain
+from univs_b200 import _cabi, ops
+
+if shutil.which("g++") is None or not os.path.exists(os.path.join(build_emu.CUDA_INCLUDE, "cuda_runtime.h")):
+    pytest.skip("needs g++ and the CUDA headers", allow_module_level=True)
+
+
+@pytest.fixture(scope="module")
+def emu_lib_path():
+    return build_emu.build()
+
+
+def _use(monkeypatch, path, sms, tmp_path):
+    copy = str(tmp_path / f"libunivs_emu_{sms}.so")
+    shutil.copy(path, copy)
+    monkeypatch.setenv("UNIVS_EMU_SMS", str(sms))
+    monkeypatch.setattr(_cabi, "_lib", _load(copy))
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+
+
+def _view(t):
+    return torch.Tensor._make_subclass(_Dev, t)        # keeps the strides (row views of wider containers)
+
+
+def _rel(a, b):
+    a, b = plain(a).double(), plain(b).double()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
+
+
+def _chunk3(x):
+    """the [lo*2^11 | hi*2^-11 | hi] K-chunk container the row-wise kernels write (split = "f16")"""
+    return cpu_backend._maybe_split(x, "f16")
+
+
+@pytest.mark.parametrize("M,N,K,sms,act", [
+    (200, 192, 128, 148, 0),      # 2 token tiles x 2 channel tiles (second one half empty), one CTA per tile
+    (130, 72, 96, 148, 1),        # channel tile mostly empty, K tail (96 = 64 + 32: zero-filled half box), GELU
+    (300, 260, 192, 2, 2),        # 9 tiles on 2 persistent CTAs: ring wrap-around, both accumulator stages, ReLU
+    (128, 128, 64, 1, 0),         # exactly one full tile, one k-block
+])
+def test_gemm_tc_kernel_chunk3_operands(monkeypatch, emu_lib_path, tmp_path, M, N, K, sms, act):
+    _use(monkeypatch, emu_lib_path, sms, tmp_path)
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    s = 8                                                    # weight scale 2^s, undone by alpha
+    x3, w3 = _chunk3(x), _chunk3(w * 2.0 ** s)
+    kc = ops.f16_chunk(K)
+    assert kc == K
+    offs = (2 * K, 0)
+    y, y16 = ops.gemm_f16x3_tc(dev(x3), offs, dev(w3), offs, K, 2.0 ** -s, dev(bias), dev(add), want_f32=True,
+                               want_operand=True, act=act)
+    wy, wy16 = ops_ref.gemm_f16x3(x3, offs, w3, offs, K, 2.0 ** -s, bias, add, act)
+    assert _rel(y, wy) < 2e-6
+    # against the exact product of the original values: the two-term split carries ~22 bits
+    ref = x.double() @ w.double().t() + bias.double()
+    ref = torch.nn.functional.gelu(ref) if act == 1 else (torch.relu(ref) if act == 2 else ref)
+    assert _rel(y, ref + add.double()) < 5e-6
+    # operand output: compact [hi | lo*2^11]; the value it carries equals the fp32 output to ~2^-22
+    y16 = plain(y16).float()
+    assert y16.shape == (M, 2 * N)
+    assert _rel(y16[:, :N] + y16[:, N:] / 2048.0, y) < 1e-6
+    assert torch.equal(y16[:, :N], plain(y).half().float())
+
+
+def test_gemm_tc_compact_operand_k_slices_and_row_views(monkeypatch, emu_lib_path, tmp_path):
+    """fc1 -> GELU -> operand, then fc2 over the compact container in two K slices accumulated in place, on row views"""
+    _use(monkeypatch, emu_lib_path, 3, tmp_path)
+    g = torch.Generator().manual_seed(7)
+    M, C, Hd = 150, 64, 256
+    x, w1, w2 = torch.randn(M + 20, C, generator=g), torch.randn(Hd, C, generator=g) * 0.1, torch.randn(C, Hd, generator=g) * 0.1
+    b1 = torch.randn(Hd, generator=g) * 0.1
+    x3, w13, w23 = _chunk3(x), _chunk3(w1 * 16.0), _chunk3(w2 * 16.0)
+    xv = x3[20:]                                             # a row view (the 3x3 convolution taps address rows like this)
+    _, h16 = ops.gemm_f16x3_tc(_view(xv), (2 * C, 0), dev(w13), (2 * C, 0), C, 1 / 16.0, dev(b1), None, want_f32=False,
+                               want_operand=True, act=ops.ACT_GELU)
+    hid = torch.nn.functional.gelu(x[20:].double() @ w1.double().t() + b1.double())
+    h16p = plain(h16).float()
+    assert _rel(h16p[:, :Hd] + h16p[:, Hd:] / 2048.0, hid) < 5e-6
+    out = torch.zeros(M, C)
+    half = Hd // 2
+    for i, k0 in enumerate((0, half)):                       # weights: chunk3 container of the full K, sliced by offsets
+        ops.gemm_f16x3_tc(_view(h16), (k0, Hd + k0), dev(w23), (2 * Hd + k0, k0), half, 1 / 16.0, None, dev(out) if i else None,
+                          out=dev(out), want_f32=True)
+    want = hid @ w2.double().t()
+    assert _rel(out, want) < 5e-6
+
+
+def test_gemm_tc_argument_validation(monkeypatch, emu_lib_path, tmp_path):
+    _use(monkeypatch, emu_lib_path, 1, tmp_path)
+    x3, w3 = torch.zeros(8, 3 * 64, dtype=torch.float16), torch.zeros(8, 3 * 64, dtype=torch.float16)
+    with pytest.raises(_cabi.UnivsB200Error, match="exceed the row pitch"):
+        ops.gemm_f16x3_tc(dev(x3), (160, 0), dev(w3), (128, 0), 64)
+    with pytest.raises(_cabi.UnivsB200Error, match="multiples of 8"):
+        ops.gemm_f16x3_tc(dev(x3), (4, 0), dev(w3), (128, 0), 64)
+    y, _ = ops.gemm_f16x3_tc(dev(x3[:0]), (128, 0), dev(w3), (128, 0), 64)      # empty token matrix
+    assert y.shape == (0, 8)

@@ -1,0 +1,306 @@
+// Dense layers of the path on the 5th-gen tensor cores with fused epilogues: the fp32-equivalent
+// fp16 hi|lo product of the strict policy as ONE kernel -- TMA -> shared memory -> tcgen05.mma -> TMEM -> tcgen05.ld ->
+// bias / GELU / ReLU / residual / operand emission -> coalesced global stores.
+// Replaces, on the reference side, nn.Linear + the activation / residual that follows it:
+//   swin.py:35-41 (Mlp fc1 -> GELU -> fc2), :138-169 (qkv / proj), :292-293 (residual), ms_deform_attn.py:98-120
+//   (value / offset / output projections), transformer_layers.py (decoder linears, FFN).
+//
+//   Y[t, n] = act( alpha * sum_k X[t, k] * W[n, k] + bias[n] ) + addend[t, n]
+//
+// Operands are fp16 pairs: x = hi + lo' * 2^-11 with hi = fp16(x), lo' = fp16((x - hi) * 2^11) (the scale keeps lo out of
+// fp16's subnormal range); the weight tensor is pre-scaled by a per-tensor power of two (alpha undoes it).  hi*hi products
+// are exact in fp32, two correction products restore ~22 bits:
+//   main = Wh Xh^T          corr = Wh Xl'^T + Wl' Xh^T          Y = alpha * (main + corr * 2^-11)
+// with main and corr in SEPARATE TMEM accumulators: the tensor core accumulates with truncation (tools/accum_probe.py), and
+// the correction terms must not be added to an accumulator 2^11 times their size.  Three kind::f16 MMAs per 16-wide k-step
+// read four operand tiles (the single-GEMM formulation of round 1 read six: [lo'|hi_s|hi] x [hi_s|lo'|hi]).
+//
+// Mapping onto UMMA (D = A * B^T, both operands K-major, 128-byte rows = 64 halfs, SWIZZLE_128B):
+//   A (M side, 128 rows) = weight tile: 128 output channels   -> TMEM lane   = output channel n
+//   B (N side, 128 rows) = activation tile: 128 tokens        -> TMEM column = token
+// so that a 32x32b TMEM load gives the 32 lanes of a warp 32 CONSECUTIVE channels of one token: every global store of the
+// epilogue is one full 128-byte line of the row-major [tokens, N] output (or 64 bytes of the fp16 operand output), and
+// bias[n] is a per-thread scalar.
+//
+// Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer (3-stage ring of {Wh, Wl', Xh, Xl'} = 64 KB),
+// warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-11 = epilogue (two per TMEM lane quarter, 64
+// token columns each).  Two TMEM stages of {main, corr} (4 x 128 columns): the epilogue of tile i -- which for the GELU
+// variant is as long as the main loop -- overlaps the MMAs of tile i+1.  Tiles are ordered channel-tile fastest, so
+// concurrently running CTAs share activation tiles in L2; weights stay L2-resident.
+//
+// The operand tensors are addressed through four 2-D tensor maps (rows x K window with an arbitrary row pitch), which makes
+// the kernel independent of the operand container: the round-1 [lo' | hi_s | hi] K-chunk format (hi_s simply is not read)
+// and the compact [hi | lo'] format this kernel's own operand epilogue writes.  K beyond 1536 is sliced on the host
+// (one launch per slice, `addend` = the partial result): bounds the main accumulation chain to 96 MMA steps.
+#include "rowwise.cuh"
+#include "tc05.cuh"
+
+namespace univs {
+namespace gemmtc {
+
+using namespace tc;
+
+constexpr int kBM = 128;                 // channels per tile (UMMA M)
+constexpr int kBT = 128;                 // tokens per tile (UMMA N)
+constexpr int kBK = 64;                  // halfs per operand row in shared memory (one SWIZZLE_128B span)
+constexpr int kStages = 3;
+constexpr int kTileBytes = 128 * 128;    // one operand tile: 128 rows x 128 bytes
+constexpr int kStageBytes = 4 * kTileBytes;
+constexpr int kThreads = 384;            // 4 control warps + 8 epilogue warps
+constexpr int kOffBars = kStages * kStageBytes;
+constexpr int kNumBars = 2 * kStages + 4;
+constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
+constexpr uint32_t kColsPerStage = 2 * kBT;   // main [0,128) corr [128,256)
+
+struct Args {
+  int M, N, K;                 // tokens, output channels, reduction length
+  float alpha;
+  const float* bias;           // [N] or null
+  const float* addend;         // fp32 [M, ldadd] or null (may alias out)
+  long long ldadd;
+  float* out;                  // fp32 [M, ldo] or null
+  long long ldo;
+  __half* out16;               // fp16 operand output or null: hi at column n, lo*2^11 at column lo_off16 + n
+  long long ld16, lo_off16;
+  int act;                     // 0 none, 1 GELU (erf), 2 ReLU
+};
+
+__device__ __forceinline__ float activate(float v, int act) {
+  if (act == 1) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (act == 2) return fmaxf(v, 0.f);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                     const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const Args a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ct = (a.N + kBM - 1) / kBM;
+  const int n_tt = (a.M + kBT - 1) / kBT;
+  const int num_tiles = n_ct * n_tt;
+  const int kblocks = (a.K + kBK - 1) / kBK;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);   // one arrive per epilogue warp
+    }
+    mbar_init_fence();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tt = tile / n_ct, ct = tile - tt * n_ct;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 10 + stage);
+          const uint32_t s0 = smem_u32(smem + (size_t)stage * kStageBytes);
+          mbar_expect_tx(&full[stage], (uint32_t)kStageBytes);     // a box always counts in full (out-of-range parts are zero-filled)
+          tma_load_3d(s0, &map_wh, &full[stage], kb * kBK, ct * kBM, 0);
+          tma_load_3d(s0 + kTileBytes, &map_wl, &full[stage], kb * kBK, ct * kBM, 0);
+          tma_load_3d(s0 + 2 * kTileBytes, &map_xh, &full[stage], kb * kBK, tt * kBT, 0);
+          tma_load_3d(s0 + 3 * kTileBytes, &map_xl, &full[stage], kb * kBK, tt * kBT, 0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_f16(kBM, kBT, false, false);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1, 20 + acc);
+      fence_after();
+      const uint32_t d_main = tmem_base + (uint32_t)acc * kColsPerStage;
+      const uint32_t d_corr = d_main + (uint32_t)kBT;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase, 30 + stage);
+        fence_after();
+        if (elect_one()) {
+          const uint32_t s0 = smem_u32(smem + (size_t)stage * kStageBytes);
+          const uint64_t wh = make_desc<128>(s0), wl = make_desc<128>(s0 + kTileBytes);
+          const uint64_t xh = make_desc<128>(s0 + 2 * kTileBytes), xl = make_desc<128>(s0 + 3 * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {   // one k-step = 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            umma_f16(d_corr, wh + (uint64_t)(2 * k), xl + (uint64_t)(2 * k), idesc, first);   // Wh  * Xl'
+            umma_f16(d_corr, wl + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc, 1u);      // Wl' * Xh
+            umma_f16(d_main, wh + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc, first);   // Wh  * Xh
+          }
+          umma_commit(&empty[stage]);                       // frees the stage when these MMAs retire
+          if (kb == kblocks - 1) umma_commit(&tfull[acc]);  // both accumulators complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global.  8 warps: two per TMEM lane quarter, 64 token columns each =====
+    const int ew = warp - 4;
+    const int wq = ew & 3;       // TMEM lane quarter this warp may access (== warp % 4)
+    const int half = ew >> 2;    // token columns [64 * half, 64 * half + 64)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tt = tile / n_ct, ct = tile - tt * n_ct;
+      const int n = ct * kBM + wq * 32 + lane;              // this thread's output channel
+      const bool n_ok = n < a.N;
+      const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
+      mbar_wait(&tfull[acc], acc_phase, 40 + acc);
+      fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * kColsPerStage + (uint32_t)(half * 64);
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t rm[32], rc[32];
+        UNIVS_TMEM_LD_X32(taddr + (uint32_t)(cb * 32), rm);
+        UNIVS_TMEM_LD_X32(taddr + (uint32_t)(kBT + cb * 32), rc);
+        tmem_wait_ld();
+        if (cb == 1) {            // both chunks are in registers: the MMA lane may overwrite this accumulator stage
+          fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        const int t0 = tt * kBT + half * 64 + cb * 32;      // first token of this chunk
+        const int nt = a.M - t0 < 32 ? a.M - t0 : 32;       // valid tokens (<= 0: none)
+        if (n_ok && nt > 0) {
+        const float* ap = a.addend != nullptr ? a.addend + (size_t)t0 * a.ldadd + n : nullptr;
+        float* op = a.out != nullptr ? a.out + (size_t)t0 * a.ldo + n : nullptr;
+        __half* hp = a.out16 != nullptr ? a.out16 + (size_t)t0 * a.ld16 + n : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < nt) {
+            float v = fmaf(__uint_as_float(rc[j]), 1.f / 2048.f, __uint_as_float(rm[j]));
+            v = activate(fmaf(v, a.alpha, bias), a.act);
+            if (ap != nullptr) v += __ldg(ap + (size_t)j * a.ldadd);
+            if (op != nullptr) op[(size_t)j * a.ldo] = v;
+            if (hp != nullptr) {
+              const __half h = sat_half(v);
+              hp[(size_t)j * a.ld16] = h;
+              hp[(size_t)j * a.ld16 + a.lo_off16] = sat_half((v - __half2float(h)) * 2048.f);
+            }
+          }
+        }
+        }
+        __syncwarp();           // the TMEM loads of the next chunk / tile are warp-collective
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 window [rows][K] of a row-major tensor with `pitch` halfs per row; box [64 halfs][128 rows], SWIZZLE_128B; rows and
+// columns beyond the window read as zeros
+static int make_map(CUtensorMap* m, const __half* base, long long rows, int K, long long pitch) {
+  EncodeTiledFn enc = encoder();
+  if (!enc) { set_error("gemm_f16x3_tc: cuTensorMapEncodeTiled entry point unavailable"); return UNIVS_E_LAUNCH; }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_f16x3_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return UNIVS_E_LAUNCH; }
+  return 0;
+}
+
+}  // namespace gemmtc
+}  // namespace univs
+
+using namespace univs;
+
+extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, int64_t x_hi_off, int64_t x_lo_off,
+                                   const void* w16, int64_t ldw, int64_t w_hi_off, int64_t w_lo_off, int64_t tokens,
+                                   int channels, int k, float alpha, const float* bias, const float* addend, int64_t ldadd,
+                                   float* out, int64_t ldo, void* out16, int64_t ld16, int64_t out16_lo_off, int activation) {
+  using namespace gemmtc;
+  UNIVS_REQUIRE(x16 && w16 && (out || out16), "gemm_f16x3_tc: null pointer");
+  UNIVS_REQUIRE(tokens >= 0 && tokens < (1ll << 31) - 256 && channels > 0 && k > 0, "gemm_f16x3_tc: bad sizes");
+  UNIVS_REQUIRE(k % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && x_hi_off % 8 == 0 && x_lo_off % 8 == 0 && w_hi_off % 8 == 0 &&
+                    w_lo_off % 8 == 0,
+                "gemm_f16x3_tc: K, row pitches and block offsets must be multiples of 8 halfs (16-byte TMA alignment)");
+  UNIVS_REQUIRE(((uintptr_t)x16 | (uintptr_t)w16) % 16 == 0, "gemm_f16x3_tc: operands must be 16-byte aligned");
+  UNIVS_REQUIRE(x_hi_off + k <= ldx && x_lo_off + k <= ldx && w_hi_off + k <= ldw && w_lo_off + k <= ldw,
+                "gemm_f16x3_tc: operand blocks exceed the row pitch");
+  UNIVS_REQUIRE(activation >= 0 && activation <= 2, "gemm_f16x3_tc: activation must be 0 (none), 1 (GELU) or 2 (ReLU)");
+  UNIVS_REQUIRE(out == nullptr || ldo >= channels, "gemm_f16x3_tc: ldo < channels");
+  UNIVS_REQUIRE(addend == nullptr || ldadd >= channels, "gemm_f16x3_tc: ldadd < channels");
+  UNIVS_REQUIRE(out16 == nullptr || (ld16 >= channels && out16_lo_off >= 0 && out16_lo_off + channels <= ld16),
+                "gemm_f16x3_tc: operand output blocks exceed its row pitch");
+  if (tokens == 0) return UNIVS_OK;
+  const __half* x = reinterpret_cast<const __half*>(x16);
+  const __half* w = reinterpret_cast<const __half*>(w16);
+  CUtensorMap mwh, mwl, mxh, mxl;
+  int rc;
+  if ((rc = make_map(&mwh, w + w_hi_off, channels, k, ldw))) return rc;
+  if ((rc = make_map(&mwl, w + w_lo_off, channels, k, ldw))) return rc;
+  if ((rc = make_map(&mxh, x + x_hi_off, tokens, k, ldx))) return rc;
+  if ((rc = make_map(&mxl, x + x_lo_off, tokens, k, ldx))) return rc;
+  Args a;
+  a.M = (int)tokens; a.N = channels; a.K = k; a.alpha = alpha; a.bias = bias; a.addend = addend; a.ldadd = ldadd;
+  a.out = out; a.ldo = ldo; a.out16 = reinterpret_cast<__half*>(out16); a.ld16 = ld16; a.lo_off16 = out16_lo_off;
+  a.act = activation;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_error("gemm_f16x3_tc: cudaFuncSetAttribute(%d): %s", kSmemBytes, cudaGetErrorString(e)); return UNIVS_E_LAUNCH; }
+    attr_set = true;
+  }
+  const long long tiles = (long long)((channels + kBM - 1) / kBM) * ((tokens + kBT - 1) / kBT);
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  gemm_f16x3_tc_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mwh, mwl, mxh, mxl, a);
+  return check_launch("gemm_f16x3_tc");
+}

@@ -25,6 +25,38 @@ _wcache = {}
 _fused_glue = switches.get("FUSED_GLUE") == 1
 
 
+# Dense layers on the own tcgen05 GEMM (csrc/gemm_tc.cu) instead of the library GEMM: fp16x3 policy only.  Reads four operand
+# tiles per k-step instead of six, keeps the correction terms in their own accumulator, and fuses bias / GELU / ReLU /
+# K-slice accumulation / operand emission into the epilogue (the Swin MLP never materialises its fp32 hidden activation).
+_gemm_tc = switches.get("GEMM_TC") == 1
+
+
+def set_gemm_tc(on: bool):
+    global _gemm_tc
+    _gemm_tc = bool(on)
+
+
+def gemm_tc() -> bool:
+    return _gemm_tc and _policy == "fp16x3"
+
+
+def _tc_linear(h3, K, b3, alpha, bias, act=0, want_f32=True, want_operand=False, compact=False):
+    """y = act(x W^T + bias) through ops.gemm_f16x3_tc.  h3: activation operand [rows, 3K] in the K-chunk container
+    [lo' | hi_s | hi] of the row-wise kernels, or (compact) [rows, 2K] = [hi | lo'] as written by the GEMM's own operand
+    epilogue; b3: weight operand [N, 3K] chunks [hi_s | lo' | hi] (_split_weight).  K-chunks beyond the first accumulate
+    into the fp32 result in place."""
+    kc = ops.f16_chunk(K)
+    n = K // kc
+    assert n == 1 or (act == 0 and not want_operand), "activation / operand epilogues need a single K-chunk"
+    y = y16 = None
+    for c in range(n):
+        x_offs = (c * kc, K + c * kc) if compact else (c * 3 * kc + 2 * kc, c * 3 * kc)
+        w_offs = (c * 3 * kc + 2 * kc, c * 3 * kc + kc)
+        y, y16 = ops.gemm_f16x3_tc(h3, x_offs, b3, w_offs, kc, alpha, bias if c == 0 else None, y, out=y, want_f32=want_f32,
+                                   want_operand=want_operand, act=act)
+    return y, y16
+
+
 def set_fused_glue(on: bool):
     global _fused_glue
     _fused_glue = bool(on)
@@ -198,6 +230,8 @@ def linear_prepped(h, weight, bias=None, cache=True):
         for k0 in range(kc, K, kc):
             y.addmm_(h2[:, k0:k0 + kc], wh[:, k0:k0 + kc].t())
         y.addmm_(h2, wlh.t())
+    elif gemm_tc() and K % 8 == 0:
+        y = _tc_linear(h.reshape(-1, 3 * K), K, wh, wlh, None if bias is None else bias.float().contiguous())[0]
     else:  # fp16x3: ONE fp16 GEMM per K-chunk over [Xl' | Xh_s | Xh] x [Wh_s | Wl' | Wh], fp32 accumulate and output
         f32 = torch.float32
         b3, alpha = wh, wlh
@@ -256,6 +290,14 @@ def mlp(h, fc1, fc2):
     """fc2(GELU(fc1(h) + b1)) without b2 (deferred into the consumer, like everywhere on this path); h is the operand of fc1."""
     width = h.shape[-1]
     rows = h.numel() // width
+    if gemm_tc() and fc1.in_features % 8 == 0 and fc1.in_features <= 1536:
+        # fc1 + bias + GELU + operand emission in ONE kernel: the fp32 hidden activation never exists
+        b31, a1 = _split_weight(fc1.weight)
+        b32, a2 = _split_weight(fc2.weight)
+        hid16 = _tc_linear(h.reshape(rows, width), fc1.in_features, b31, a1, fc1.bias, act=ops.ACT_GELU, want_f32=False,
+                           want_operand=True)[1]
+        y = _tc_linear(hid16, fc1.out_features, b32, a2, None, compact=True)[0]
+        return y.view(*h.shape[:-1], fc2.out_features)
     chunk = mlp_rows_per_chunk(rows, fc1.out_features)
     if chunk >= rows:
         return linear_prepped(gelu(linear_prepped(h, fc1.weight, None), bias=fc1.bias), fc2.weight, None)
@@ -346,6 +388,10 @@ def _conv_taps(xs, H, W, weight, bias, taps):
     for t, (wh, wlh) in enumerate(taps):
         off = (t // kw) * Wp + (t % kw)
         a = x2[off: off + R]
+        if gemm_tc() and Cin % 8 == 0 and Cin <= 1536:
+            ops.gemm_f16x3_tc(a, (2 * Cin, 0), wh, (2 * Cin, Cin), Cin, wlh, bias.float() if (bias is not None and t == 0) else None,
+                              yr if t else None, out=yr)
+            continue
         if _policy == "tf32x3":
             if t == 0:
                 torch.addmm(bias if bias is not None else y.new_zeros(Cout), a[:, :Cin], wh.t(), out=yr)

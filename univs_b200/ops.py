@@ -384,6 +384,48 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
     return out
 
 
+def _chk_rows16(t: torch.Tensor, name: str):
+    """fp16 CUDA matrix whose rows are contiguous (a row pitch is allowed: views of wider operand containers)"""
+    if not t.is_cuda:
+        raise _cabi.UnivsB200Error(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != torch.float16 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise _cabi.UnivsB200Error(f"{name}: expected an fp16 matrix with contiguous rows")
+    return t.data_ptr()
+
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+def gemm_f16x3_tc(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None, out=None, want_f32=True,
+                  want_operand=False, act=ACT_NONE):
+    """Dense layer on the tcgen05 tensor cores with fused epilogue (univs_gemm_f16x3_tc, csrc/gemm_tc.cu):
+        y = act(alpha * x w^T + bias) + addend
+    x16 [tokens, ldx] / w16 [channels, ldw]: fp16 operand containers (row views allowed); `x_offs` / `w_offs` = (column of
+    the hi block, column of the lo*2^11 block), `k` columns each.  addend fp32 [tokens, channels] (rows may be strided; may
+    be `out`).  Returns (y fp32 [tokens, channels] or None, y as compact operand fp16 [tokens, 2*channels] = [hi | lo*2^11]
+    or None)."""
+    M, N = x16.shape[0], w16.shape[0]
+    xp, wp = _chk_rows16(x16, "x16"), _chk_rows16(w16, "w16")
+    if out is not None and (out.dtype != torch.float32 or not out.is_cuda or out.shape != (M, N) or out.stride(1) != 1):
+        raise _cabi.UnivsB200Error("gemm_f16x3_tc: out must be an fp32 CUDA [tokens, channels] matrix with contiguous rows")
+    if want_f32 and out is None:
+        out = torch.empty((M, N), device=x16.device, dtype=torch.float32)
+    if addend is not None and (addend.dtype != torch.float32 or not addend.is_cuda or addend.shape != (M, N) or addend.stride(1) != 1):
+        raise _cabi.UnivsB200Error("gemm_f16x3_tc: addend must be an fp32 CUDA [tokens, channels] matrix with contiguous rows")
+    out16 = torch.empty((M, 2 * N), device=x16.device, dtype=torch.float16) if want_operand else None
+    if M == 0:
+        return out, out16
+    with _Bracket("gemm_f16x3_tc", 1):
+        rc = lib().univs_gemm_f16x3_tc(
+            _stream(), xp, x16.stride(0), int(x_offs[0]), int(x_offs[1]), wp, w16.stride(0), int(w_offs[0]), int(w_offs[1]),
+            M, N, int(k), float(alpha), None if bias is None else _chk(bias, "bias"),
+            None if addend is None else addend.data_ptr(), 0 if addend is None else addend.stride(0),
+            None if out is None else out.data_ptr(), 0 if out is None else out.stride(0),
+            None if out16 is None else out16.data_ptr(), 2 * N, N, int(act))
+    check(rc, "gemm_f16x3_tc")
+    return out, out16
+
+
 def f16_chunk(K: int) -> int:
     """K-chunk of the fp16x3 operand layout: the largest divisor of K that is <= 1536 and a multiple of 32 (bounds the
     main-term accumulation chain of one GEMM to 96 MMA steps; chunks are summed by fp32 GEMM epilogues)."""
