@@ -76,10 +76,15 @@ class ClockSampler:
                 "samples": len(clocks)}
 
 
-def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, dec_layers=9, enc_layers=6, sm_mhz=1965.0):
-    """Algorithmic HBM bytes per clip (SURVEY.md 8(d) formulas, fp32 element size) of the four kernels BASELINE.json names,
-    divided by their CUDA-event time per clip.  Pure arithmetic on the per-kernel brackets; returns
+def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, dec_layers=9, enc_layers=6, sm_mhz=1965.0,
+                           T_local=None, T_dec=None):
+    """Algorithmic HBM bytes (SURVEY.md 8(d) formulas, fp32 element size) of the four kernels BASELINE.json names that THIS
+    RANK's launches move, divided by their CUDA-event time on this rank.  `T_local` = frames this rank runs through
+    backbone + pixel decoder (frame sharding: ceil(T / world) on rank 0), `T_dec` = frames its decoder kernels see (T when
+    the decoder is replicated, T_local when it is frame-sharded).  Pure arithmetic on the per-kernel brackets; returns
     {name: {"bytes_per_step", "ms_per_step", "achieved" (GB/s), "frac"}}."""
+    T_local = T if T_local is None else T_local
+    T_dec = T if T_dec is None else T_dec
     from univs_b200.config import SWIN_VARIANTS
     sw = SWIN_VARIANTS[variant]
     Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
@@ -94,14 +99,14 @@ def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, d
 
     # mask einsum: e*(Q*C + C*HW + Q*HW) per frame per call, dec_layers + 1 calls
     HW = (Hp // 4) * (Wp // 4)
-    put("mask_einsum", "mask_einsum", float(e * T * (Q * C + C * HW + Q * HW) * (dec_layers + 1)))
+    put("mask_einsum", "mask_einsum", float(e * T_dec * (Q * C + C * HW + Q * HW) * (dec_layers + 1)))
     # MSDeformAttn core: e*(2*Len*256 + 3*Len*M*L*P) per frame per layer, M*L*P = 96
     Len = sum((Hp // s) * (Wp // s) for s in (8, 16, 32))
-    put("ms_deform_attn", "ms_deform_attn_encoder", float(e * T * (2 * Len * C + 3 * Len * 96) * enc_layers))
+    put("ms_deform_attn", "ms_deform_attn_encoder", float(e * T_local * (2 * Len * C + 3 * Len * 96) * enc_layers))
     if "ms_deform_attn" in out:
         # the gather is bound by L1 request throughput long before HBM: every (query, head) fetches L*P*4 = 48 corners of
         # 32 fp32 channels = 48 requests of one 128-byte line, and an SM's L1 serves one 128-byte wavefront per clock
-        wavefronts = float(T * Len * 8 * 48 * enc_layers)
+        wavefronts = float(T_local * Len * 8 * 48 * enc_layers)
         floor_ms = wavefronts / (148 * sm_mhz * 1e6) * 1e3
         out["ms_deform_attn"].update({"l1_wavefronts_per_step": wavefronts, "l1_floor_ms_per_step": floor_ms,
                                       "frac_of_l1_floor": floor_ms / out["ms_deform_attn"]["ms_per_step"]})
@@ -111,11 +116,11 @@ def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, d
         hs, wsz = Hp // (4 << s), Wp // (4 << s)
         tokens = (-(-hs // ws) * ws) * (-(-wsz // ws) * ws)
         total += depth * e * 4 * tokens * (sw["EMBED_DIM"] << s)
-    put("swin_window_attention", "swin_window_attention", float(total * T))
+    put("swin_window_attention", "swin_window_attention", float(total * T_local))
     # decoder attention: cross-attention e*(2*S_l*256 + 2*Q*256) per frame per layer (level l = layer % 3, 1/32 first)
     # + the Q*T self-attention e*4*Q*T*256 per layer
     S = [(Hp // s) * (Wp // s) for s in (32, 16, 8)]
-    mha = sum(e * T * (2 * S[i % 3] * C + 2 * Q * C) + e * 4 * Q * T * C for i in range(dec_layers))
+    mha = sum(e * T_dec * (2 * S[i % 3] * C + 2 * Q * C) + e * 4 * Q * T * C for i in range(dec_layers))
     put("decoder_attention", "mha", float(mha))
     return out
 
@@ -128,7 +133,9 @@ def make_targets(T, device):
 def run_cpu_reference(args, workload, steps, warmup, as_line):
     """The reference algorithm on the host cores: product host logic with every operator replaced by its CPU oracle
     (oracle/ops_ref.py; the reference tree itself does not travel to the GPU box), fp32, all host threads.
-    Bounded sample: a clip of ONE frame of the workload (the full clip has T frames)."""
+    Sample: ONE full clip of the workload (all T frames, the same configuration as the GPU arm) per step; the number of
+    timed steps is bounded by a wall-clock budget (UNIVS_CPU_BUDGET_S, default 240 s: the CPU needs ~18 s per north-star
+    clip), and at least one timed step always runs."""
     from oracle.cpu_backend import oracle_ops
     from univs_b200.build import build_model, make_cfg
     variant, T, H, W, Q = WORKLOADS[workload]
@@ -137,14 +144,15 @@ def run_cpu_reference(args, workload, steps, warmup, as_line):
     cores = min(os.cpu_count() or 1, int(os.environ.get("UNIVS_CPU_THREADS", "32")))
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
-    cfg = make_cfg(variant, Q, 1, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
+    Ts = int(os.environ.get("UNIVS_CPU_SAMPLE_FRAMES", T))              # frames per sampled clip (default: the whole clip)
+    cfg = make_cfg(variant, Q, Ts, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
     model = build_model(cfg)
-    frames = torch.rand(1, 3, H, W, generator=g) * 255
+    frames = torch.rand(Ts, 3, H, W, generator=g) * 255
     times, budget_s, t_begin = [], float(os.environ.get("UNIVS_CPU_BUDGET_S", "240")), time.perf_counter()
     with oracle_ops():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            out = model.clip_forward(frames, make_targets(1, "cpu"))
+            out = model.clip_forward(frames, make_targets(Ts, "cpu"))
             float(out["pred_masks"].sum())
             dt = time.perf_counter() - t0
             if i >= warmup:
@@ -156,20 +164,22 @@ def run_cpu_reference(args, workload, steps, warmup, as_line):
                 warmup = i + 1                       # slow host: the next step is the (first) timed one
     mean = sum(times) / len(times)
     steps = len(times)
-    sample = f"1 clip of T=1 frame ({variant} {H}x{W}, Q={Q}) per step; full workload has T={T} frames/clip"
-    base = {"value": 1.0 / mean, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+    sample = (f"{steps} timed step(s) of 1 clip of T={Ts} frames ({variant} {H}x{W}, Q={Q}); the workload's clip has T={T} frames"
+              + ("" if Ts == T else " (reduced sample)"))
+    base = {"value": Ts / mean, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+            "same_config": Ts == T}
     if not as_line:
         return base
     return {
         "impl": "reference",
         "metric": "frames/sec (Swin-L 720p T=5 Q=200)" if workload == "ns" else "frames/sec (per-clip forward)",
-        "value": 1.0 / mean, "unit": "frames/s",
+        "value": Ts / mean, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init",
                    "precision": "fp32 (CPU)", "sample": sample},
         "cpu_baseline": base,
-        "e2e": {"value": 1.0 / mean, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": Ts / mean, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
 
 
@@ -302,9 +312,10 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    # frame-sharded runs replay a graph only when asked to (UNIVS_GRAPH_MULTI=1): capturing the NCCL all-gather is
-    # supported by torch but has been validated here on fewer configurations than the eager path
-    use_graph = not args.no_graph and (world == 1 or os.environ.get("UNIVS_GRAPH_MULTI", "0") == "1")
+    # frame-sharded runs replay a graph too (the NCCL all-gather is captured with the rest of the step; round 1 ran them
+    # eagerly and was host-launch-bound: ~900 launches of 16-20 us each per 20 ms step at N=8).  UNIVS_GRAPH_MULTI=0 opts
+    # out; a failed capture on any rank sends every rank down the eager path.
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("UNIVS_GRAPH_MULTI", "1") == "1")
     graphed = None
     if use_graph:
         from univs_b200.runtime import GraphedClip
@@ -372,22 +383,25 @@ def main():
     roof = None
     if "mask_einsum" in kernel_ms:
         ach = alg_bytes / (kernel_ms["mask_einsum"] * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_source = None, None
         tpath = os.path.join(ROOT, "profiles", "r1_einsum_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("workload") == args.workload and tj.get("precision") == args.precision:
                 traffic = tj.get("dram_bytes_per_launch")     # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full
+                traffic_source = "static: ncu --set full capture of this kernel at this shape, profiles/r1_einsum_traffic.json (not re-measured by this run)"
         roof = {"kernel": "mask_einsum", "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "launch_ms": kernel_ms["mask_einsum"],
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_source, "launch_ms": kernel_ms["mask_einsum"],
                 "algorithmic_bytes_per_launch": alg_bytes}
 
     named = None
     try:    # per-kernel roofline fractions of the four named kernels (metric (iii) of SURVEY.md 8d); never blocks the line
+        t_local = len(range(rank, T, world))                  # frames of this rank (frame_plan: round robin)
         named = named_kernel_rooflines(variant, T, H, W, n_lp, kernel_ms, kernel_calls, peak,
                                        dec_layers=cfg.MODEL.MASK_FORMER.DEC_LAYERS - 1,
                                        enc_layers=cfg.MODEL.SEM_SEG_HEAD.TRANSFORMER_ENC_LAYERS,
-                                       sm_mhz=float((clocks or {}).get("sm_mhz") or 1965.0))
+                                       sm_mhz=float((clocks or {}).get("sm_mhz") or 1965.0), T_local=t_local,
+                                       T_dec=t_local if (world > 1 and model.shard_decoder) else T)
     except Exception as exc:  # noqa: BLE001
         sys.stderr.write(f"[bench] named-kernel rooflines unavailable: {exc}\n")
 
@@ -411,6 +425,8 @@ def main():
                        if world > 1 else "single",
                        "execution": "CUDA graph replay" if use_graph else "eager",
                        "switches": switches.active(),      # opt-in paths that were on ({} = the round-1 default path)
+                       "e2e_result": "pred_logits + pred_embds + BINARISED pred_masks (pred_masks > 0, 1 byte/pixel) copied to pinned host memory "
+                                     "every step -- what the task heads move to the host; the fp32 mask logits stay on the device",
                        "l2": "per-step working set (multi-GB activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": T / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

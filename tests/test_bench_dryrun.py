@@ -84,7 +84,8 @@ def test_default_run_control_flow(monkeypatch):
         assert k in line, k
     assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 3       # W >= 3 is enforced
     assert line["value"] > 0 and line["unit"] == "frames/s" and line["higher_is_better"] is True
-    assert line["config"]["workload"].startswith("dry:") and line["config"]["switches"] == {}
+    from univs_b200 import switches
+    assert line["config"]["workload"].startswith("dry:") and line["config"]["switches"] == switches.active()
     assert line["config"]["execution"] == "eager" and "l2" in line["config"]
     e2e = line["e2e"]
     assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 2 * 3 * 64 * 96 and e2e["d2h_bytes_per_step"] > 0

@@ -49,6 +49,7 @@ def _chunk3(x):
     (130, 72, 96, 148, 1),        # channel tile mostly empty, K tail (96 = 64 + 32: zero-filled half box), GELU
     (300, 260, 192, 2, 2),        # 9 tiles on 2 persistent CTAs: ring wrap-around, both accumulator stages, ReLU
     (128, 128, 64, 1, 0),         # exactly one full tile, one k-block
+    (70, 71, 64, 1, 1),           # odd channel count: the last channel of the operand output is stored alone
 ])
 def test_gemm_tc_kernel_chunk3_operands(monkeypatch, emu_lib_path, tmp_path, M, N, K, sms, act):
     _use(monkeypatch, emu_lib_path, sms, tmp_path)

@@ -65,12 +65,77 @@ struct Args {
   int act;                     // 0 none, 1 GELU (erf), 2 ReLU
 };
 
-__device__ __forceinline__ float activate(float v, int act) {
-  if (act == 1) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-  if (act == 2) return fmaxf(v, 0.f);
+template <int ACT>
+__device__ __forceinline__ float activate(float v) {
+  if (ACT == 1) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (ACT == 2) return fmaxf(v, 0.f);
   return v;
 }
 
+__device__ __forceinline__ uint32_t pack_sat_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// One 32-token chunk of the epilogue for this thread's channel n: v[j] = act(alpha * (main + corr * 2^-11) + bias) (+ addend),
+// written as fp32 (one 128-byte line per token and warp) and / or as the fp16 [hi | lo'] operand.  The variant is fixed at
+// compile time: the first version took `act` and the nullable pointers at run time, and its per-element branches and
+// argument reloads made the epilogue several times longer than the main loop (ncu: instruction-fetch and dependency stalls).
+// FULL = all 32 tokens valid and every lane's channel valid: no predicates at all.
+template <int ACT, bool OUT32, bool OUT16, bool ADD, bool FULL>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const uint32_t (&rc)[32], const Args& a, float bias, int n,
+                                               bool n_ok, int t0, int nt, int lane) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float s = fmaf(__uint_as_float(rc[j]), 1.f / 2048.f, __uint_as_float(rm[j]));
+    v[j] = activate<ACT>(fmaf(s, a.alpha, bias));
+  }
+  if (ADD) {
+    const float* ap = a.addend + (size_t)t0 * a.ldadd + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (FULL || (n_ok && j < nt)) v[j] += __ldg(ap);
+      ap += a.ldadd;
+    }
+  }
+  if (OUT32) {
+    float* op = a.out + (size_t)t0 * a.ldo + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (FULL || (n_ok && j < nt)) *op = v[j];
+      op += a.ldo;
+    }
+  }
+  if (OUT16) {
+    // lane pairs exchange so that a lane holds TWO adjacent channels of one token (even lane: token j, odd lane: token
+    // j + 1) and stores them as one half2: half as many store instructions as 2-byte stores per element
+    const bool odd = lane & 1;
+    const int ne = n & ~1;                                   // first channel of the pair
+    __half* hp = a.out16 + (size_t)(t0 + (odd ? 1 : 0)) * a.ld16 + ne;
+    const bool pair_ok = ne + 1 < a.N;                       // both channels valid (N even in practice)
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float mine = odd ? v[j + 1] : v[j];              // my channel, my token
+      const float other = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);   // partner's channel, my token
+      const float c0 = odd ? other : mine, c1 = odd ? mine : other;   // channels ne, ne + 1
+      const __half2 h = __floats2half2_rn(fminf(fmaxf(c0, -65504.f), 65504.f), fminf(fmaxf(c1, -65504.f), 65504.f));
+      const float2 hf = __half22float2(h);
+      const uint32_t lo = pack_sat_half2((c0 - hf.x) * 2048.f, (c1 - hf.y) * 2048.f);
+      const int tok = j + (odd ? 1 : 0);
+      if (FULL || (tok < nt && pair_ok)) {
+        *reinterpret_cast<__half2*>(hp) = h;
+        *reinterpret_cast<uint32_t*>(hp + a.lo_off16) = lo;
+      } else if (tok < nt && ne < a.N) {                     // odd channel count: the last channel alone
+        hp[0] = __low2half(h);
+        hp[a.lo_off16] = __ushort_as_half((unsigned short)(lo & 0xffffu));
+      }
+      hp += 2 * a.ld16;
+    }
+  }
+}
+
+template <int ACT, bool OUT32, bool OUT16, bool ADD>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                      const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const Args a) {
@@ -170,6 +235,7 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
       const int tt = tile / n_ct, ct = tile - tt * n_ct;
       const int n = ct * kBM + wq * 32 + lane;              // this thread's output channel
       const bool n_ok = n < a.N;
+      const bool tile_full = (ct + 1) * kBM <= a.N;         // every lane of every warp has a valid channel
       const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
       mbar_wait(&tfull[acc], acc_phase, 40 + acc);
       fence_after();
@@ -187,24 +253,10 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
         }
         const int t0 = tt * kBT + half * 64 + cb * 32;      // first token of this chunk
         const int nt = a.M - t0 < 32 ? a.M - t0 : 32;       // valid tokens (<= 0: none)
-        if (n_ok && nt > 0) {
-        const float* ap = a.addend != nullptr ? a.addend + (size_t)t0 * a.ldadd + n : nullptr;
-        float* op = a.out != nullptr ? a.out + (size_t)t0 * a.ldo + n : nullptr;
-        __half* hp = a.out16 != nullptr ? a.out16 + (size_t)t0 * a.ld16 + n : nullptr;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nt) {
-            float v = fmaf(__uint_as_float(rc[j]), 1.f / 2048.f, __uint_as_float(rm[j]));
-            v = activate(fmaf(v, a.alpha, bias), a.act);
-            if (ap != nullptr) v += __ldg(ap + (size_t)j * a.ldadd);
-            if (op != nullptr) op[(size_t)j * a.ldo] = v;
-            if (hp != nullptr) {
-              const __half h = sat_half(v);
-              hp[(size_t)j * a.ld16] = h;
-              hp[(size_t)j * a.ld16 + a.lo_off16] = sat_half((v - __half2float(h)) * 2048.f);
-            }
-          }
-        }
+        if (nt == 32 && tile_full) {
+          epilogue_chunk<ACT, OUT32, OUT16, ADD, true>(rm, rc, a, bias, n, true, t0, 32, lane);
+        } else if (nt > 0) {
+          epilogue_chunk<ACT, OUT32, OUT16, ADD, false>(rm, rc, a, bias, n, n_ok, t0, nt, lane);
         }
         __syncwarp();           // the TMEM loads of the next chunk / tile are warp-collective
       }
@@ -293,14 +345,38 @@ extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) { set_error("gemm_f16x3_tc: cudaFuncSetAttribute(%d): %s", kSmemBytes, cudaGetErrorString(e)); return UNIVS_E_LAUNCH; }
-    attr_set = true;
-  }
   const long long tiles = (long long)((channels + kBM - 1) / kBM) * ((tokens + kBT - 1) / kBT);
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  gemm_f16x3_tc_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mwh, mwl, mxh, mxl, a);
-  return check_launch("gemm_f16x3_tc");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool o32 = out != nullptr, o16 = out16 != nullptr, add = addend != nullptr;
+  // the epilogue variants the path uses are compiled; anything else is a caller error
+#define UNIVS_GEMM_CASE(ACT, O32, O16, ADDF)                                                                                   \
+  if (activation == ACT && o32 == O32 && o16 == O16 && add == ADDF) {                                                          \
+    static bool attr_set = false;                                                                                              \
+    if (!attr_set) {                                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           kSmemBytes);                                                                        \
+      if (e != cudaSuccess) { set_error("gemm_f16x3_tc: cudaFuncSetAttribute(%d): %s", kSmemBytes, cudaGetErrorString(e)); return UNIVS_E_LAUNCH; } \
+      attr_set = true;                                                                                                         \
+    }                                                                                                                          \
+    gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF><<<grid, kThreads, kSmemBytes, st>>>(mwh, mwl, mxh, mxl, a);                         \
+    return check_launch("gemm_f16x3_tc");                                                                                      \
+  }
+  UNIVS_GEMM_CASE(0, true, false, false)      // plain dense layer
+  UNIVS_GEMM_CASE(0, true, false, true)       // + residual / previous K-slice
+  UNIVS_GEMM_CASE(1, false, true, false)      // GELU -> next operand (Swin MLP fc1)
+  UNIVS_GEMM_CASE(2, false, true, false)      // ReLU -> next operand (FFN linear1)
+  UNIVS_GEMM_CASE(0, false, true, false)      // operand only
+  UNIVS_GEMM_CASE(0, true, true, false)       // fp32 + operand
+  UNIVS_GEMM_CASE(0, true, true, true)
+  UNIVS_GEMM_CASE(1, true, true, false)
+  UNIVS_GEMM_CASE(1, true, true, true)
+  UNIVS_GEMM_CASE(2, true, true, false)
+  UNIVS_GEMM_CASE(2, true, true, true)
+  UNIVS_GEMM_CASE(1, true, false, false)
+  UNIVS_GEMM_CASE(2, true, false, false)
+#undef UNIVS_GEMM_CASE
+  set_error("gemm_f16x3_tc: epilogue variant (activation %d, f32 %d, operand %d, addend %d) is not instantiated", activation,
+            (int)o32, (int)o16, (int)add);
+  return UNIVS_E_BADARG;
 }

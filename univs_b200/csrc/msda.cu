@@ -70,11 +70,25 @@ __device__ __forceinline__ float sample1(const float* __restrict__ base, int pix
   return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
 }
 
+// Level tables of the reference ABI are DEVICE int64 tensors (ms_deform_attn_cuda.cu:25-32): when the caller hands device
+// pointers the kernels read them here, so the entry point stays stream-ordered with no host synchronisation (and can be
+// captured in a CUDA graph); host tables arrive by value in `lt`.
+__device__ __forceinline__ void device_levels(LevelTable& lt, const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi, int L) {
+  if (shapes == nullptr) return;
+  for (int l = 0; l < L; ++l) {
+    lt.H[l] = (int)__ldg(shapes + 2 * l);
+    lt.W[l] = (int)__ldg(shapes + 2 * l + 1);
+    lt.start[l] = (int)__ldg(lsi + l);
+  }
+}
+
 // ---- reference-ABI kernel: explicit sampling_loc / attn_weight tensors, any L, P; D % 4 == 0 ------------
 __global__ void __launch_bounds__(256)
-msda_generic_vec4_kernel(const float* __restrict__ value, LevelTable lt, const float* __restrict__ loc,
+msda_generic_vec4_kernel(const float* __restrict__ value, LevelTable lt, const int64_t* __restrict__ dev_shapes,
+                         const int64_t* __restrict__ dev_lsi, const float* __restrict__ loc,
                          const float* __restrict__ aw, int N, int S, int M, int D, int L, int Lq, int P,
                          float* __restrict__ out) {
+  device_levels(lt, dev_shapes, dev_lsi, L);
   const int groups = D >> 2;
   const long long total = (long long)N * Lq * M * groups;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -101,9 +115,11 @@ msda_generic_vec4_kernel(const float* __restrict__ value, LevelTable lt, const f
 }
 
 __global__ void __launch_bounds__(256)
-msda_generic_scalar_kernel(const float* __restrict__ value, LevelTable lt, const float* __restrict__ loc,
+msda_generic_scalar_kernel(const float* __restrict__ value, LevelTable lt, const int64_t* __restrict__ dev_shapes,
+                           const int64_t* __restrict__ dev_lsi, const float* __restrict__ loc,
                            const float* __restrict__ aw, int N, int S, int M, int D, int L, int Lq, int P,
                            float* __restrict__ out) {
+  device_levels(lt, dev_shapes, dev_lsi, L);
   const long long total = (long long)N * Lq * M * D;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -349,10 +365,17 @@ static int fill_levels(LevelTable& lt, const int64_t* shapes_h, const int64_t* l
 
 using namespace univs;
 
-// spatial_shapes / level_start_index are DEVICE pointers in the reference ABI (ms_deform_attn_cuda.cu:25-32
-// receives CUDA tensors).  They are tiny (L <= 8 rows); to stay stream-ordered without a device->host sync
-// we accept either kind of pointer and resolve it with cudaPointerGetAttributes: host memory is read
-// directly, device memory is copied with a blocking 64-byte cudaMemcpy only when it is not host-accessible.
+static bool is_device_pointer(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice;
+}
+
+// Host-side read of a small level table (the encoder entry points of this library take host tables; a device pointer is
+// still accepted there through a blocking 64-byte copy -- the reference-ABI entry below never takes this path).
 static int load_small_i64(const int64_t* p, int n, int64_t* dst) {
   cudaPointerAttributes attr;
   cudaError_t e = cudaPointerGetAttributes(&attr, p);
@@ -385,30 +408,35 @@ extern "C" int univs_ms_deform_attn_forward_f32(void* stream, const float* value
   UNIVS_REQUIRE(num_heads > 0 && channels > 0 && num_point > 0, "ms_deform_attn_forward: bad head/channel/point");
   UNIVS_REQUIRE(num_levels > 0 && num_levels <= kMaxLevels, "ms_deform_attn_forward: num_levels must be 1..%d",
                 kMaxLevels);
-  if (batch == 0 || num_query == 0) return UNIVS_OK;
-  int64_t sh[2 * kMaxLevels], ls[kMaxLevels];
-  int rc = load_small_i64(spatial_shapes, 2 * num_levels, sh);
-  if (rc) return rc;
-  rc = load_small_i64(level_start_index, num_levels, ls);
-  if (rc) return rc;
-  LevelTable lt;
-  fill_levels(lt, sh, ls, num_levels);
-  long long tot = 0;
-  for (int l = 0; l < num_levels; ++l) {
-    UNIVS_REQUIRE(lt.H[l] > 0 && lt.W[l] > 0, "ms_deform_attn_forward: empty level %d", l);
-    tot += (long long)lt.H[l] * lt.W[l];
+  // spatial_shapes / level_start_index: DEVICE int64 tensors in the reference ABI (ms_deform_attn_cuda.cu:25-32).  Device
+  // tables are read by the kernel itself -- stream-ordered, no device->host copy, capturable -- and, like in the reference,
+  // not validated; host tables (this library's own callers) are validated here and passed by value.
+  LevelTable lt = {};
+  const int64_t *dev_shapes = nullptr, *dev_lsi = nullptr;
+  if (is_device_pointer(spatial_shapes) || is_device_pointer(level_start_index)) {
+    UNIVS_REQUIRE(is_device_pointer(spatial_shapes) && is_device_pointer(level_start_index),
+                  "ms_deform_attn_forward: spatial_shapes and level_start_index must live in the same memory space");
+    dev_shapes = spatial_shapes;
+    dev_lsi = level_start_index;
+  } else {
+    fill_levels(lt, spatial_shapes, level_start_index, num_levels);
+    long long tot = 0;
+    for (int l = 0; l < num_levels; ++l) {
+      UNIVS_REQUIRE(lt.H[l] > 0 && lt.W[l] > 0, "ms_deform_attn_forward: empty level %d", l);
+      tot += (long long)lt.H[l] * lt.W[l];
+    }
+    UNIVS_REQUIRE(tot == spatial_size, "ms_deform_attn_forward: sum(H*W)=%lld != spatial_size=%d", tot, spatial_size);
   }
-  UNIVS_REQUIRE(tot == spatial_size, "ms_deform_attn_forward: sum(H*W)=%lld != spatial_size=%d", tot, spatial_size);
   cudaStream_t st = (cudaStream_t)stream;
   if (channels % 4 == 0) {
     const long long total = (long long)batch * num_query * num_heads * (channels / 4);
     const int grid = (int)min((total + 255) / 256, (long long)148 * 64);
-    msda_generic_vec4_kernel<<<grid, 256, 0, st>>>(value, lt, sampling_loc, attn_weight, batch, spatial_size,
+    msda_generic_vec4_kernel<<<grid, 256, 0, st>>>(value, lt, dev_shapes, dev_lsi, sampling_loc, attn_weight, batch, spatial_size,
                                                    num_heads, channels, num_levels, num_query, num_point, out);
   } else {
     const long long total = (long long)batch * num_query * num_heads * channels;
     const int grid = (int)min((total + 255) / 256, (long long)148 * 64);
-    msda_generic_scalar_kernel<<<grid, 256, 0, st>>>(value, lt, sampling_loc, attn_weight, batch, spatial_size,
+    msda_generic_scalar_kernel<<<grid, 256, 0, st>>>(value, lt, dev_shapes, dev_lsi, sampling_loc, attn_weight, batch, spatial_size,
                                                      num_heads, channels, num_levels, num_query, num_point, out);
   }
   return check_launch("ms_deform_attn_forward");

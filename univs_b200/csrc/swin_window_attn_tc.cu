@@ -7,9 +7,13 @@
 //
 // Work unit = (frame, window, head): 144 tokens x 32 dims of q, k, v.  Persistent CTAs (one per SM, 512 threads),
 // warp-specialised, units round-robin over CTAs:
-//   warps 12-15  loaders : gather q/k/v rows through the roll/pad addressing (128-bit loads, 9 in flight per thread), add
-//                          the qkv bias, scale q, split fp32 -> fp16 hi + lo once, store K-major SWIZZLE_64B operand
-//                          tiles (64-byte rows = 32 dims) + the head's relative-position table; 2-stage ring
+//   warps 10-15  loaders : gather q/k/v rows through the roll/pad addressing (128-bit loads, all 18 of a thread's unit share
+//                          in flight at once: one memory latency per unit), add the qkv bias, scale q, split fp32 -> fp16
+//                          hi + lo once, store K-major SWIZZLE_64B operand tiles (64-byte rows = 32 dims); 2-stage ring.
+//                          The grid is a multiple of the head count, so a CTA only ever sees ONE head: its
+//                          relative-position table and qkv bias are fetched once per CTA, not per unit (ncu, round 2: the
+//                          per-unit table gather was 17 % of the loader's time, the three dependent load batches most of
+//                          the rest, and the softmax warps spent 43 % of theirs waiting for scores)
 //   warp 9       MMA     : one elected lane issues  S = Ql Kh^T + Qh Kl^T + Qh Kh^T  and  O = Pl Vh + Ph Vl + Ph Vh;
 //                          V is consumed as stored ([key][dim] rows) through the MN-major B descriptor
 //   warps 0-7    softmax of row tile 0 (query rows 0-127; M=128, N=144): warp = (TMEM lane quarter, column half); a thread
@@ -22,7 +26,7 @@
 //                          keys 0-63 of the 16 rows, lanes 16-31 with keys 64-143 of the same rows, both in columns
 //                          0-79.  Each lane writes its part of its P row and zeros elsewhere, the PV MMA leaves two
 //                          partial sums per row and the epilogue adds them with one shuffle.
-//   warp 10      TMEM allocator; warp 11 idle.
+//   warp 9 also allocates TMEM.
 // Softmax warps run  softmax(n+1) -> epilogue(n), the MMA lane  S(n+1) -> PV(n), so the tensor pipe works on the next
 // unit's scores while the softmax of the current one is in flight, and no softmax warp waits for a PV it just enabled.
 // TMEM columns: S tile0 [0,144)  S tail [160,240)  O tile0 [320,352)  O tail [352,384).
@@ -40,9 +44,10 @@ constexpr int kWS = 12;
 constexpr int kN = 144;
 constexpr int kThreads = 512;
 constexpr int kMmaWarp = 9;
-constexpr int kAllocWarp = 10;
-constexpr int kLoaderWarp0 = 12;
-constexpr int kLoaderThreads = 128;
+constexpr int kAllocWarp = 9;
+constexpr int kLoaderWarp0 = 10;
+constexpr int kLoaderThreads = 192;
+constexpr int kItemsPerLoader = kN * 8 / kLoaderThreads;   // (token, 4-dim group) items per loader thread and unit: 6
 constexpr int kTable = 23 * 23;
 constexpr int kTailKeys0 = 64;                 // keys of the tail rows handled by TMEM lanes 0-15 (lanes 16-31: the other 80)
 
@@ -62,7 +67,7 @@ constexpr int kP1Bytes = 5 * kP1Atom;          // 10240 (the MMA reads up to 6 K
 constexpr int kP0Bytes = 5 * kP0Atom;          // 40960
 constexpr int kOffP1h = 2 * kStageBytes, kOffP1l = kOffP1h + kP1Bytes;
 constexpr int kOffP0h = kOffP1l + kP1Bytes, kOffP0l = kOffP0h + kP0Bytes;
-constexpr int kOffBias = kOffP0l + kP0Bytes;   // 2 x 544 floats
+constexpr int kOffBias = kOffP0l + kP0Bytes;   // 544 floats (+ 544 unused)
 constexpr int kBiasStride = 544;
 constexpr int kOffXch = kOffBias + 2 * kBiasStride * 4;   // max[2 parity][2 half][128] + sum[2][2][128] floats
 constexpr int kOffKidx = kOffXch + 2 * 2 * 2 * 128 * 4;   // int[144]: key -> ky * 23 + kx
@@ -137,40 +142,44 @@ __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const float* __
                (uint32_t)chunk * 16u,
            0u, 0u, 0u, 0u);
   }
+  // one head per CTA (gridDim.x % nH == 0): relative-position table, key LUT and qkv bias once
+  const int head = (int)(blockIdx.x % (unsigned)g.nH);
+  {
+    float* sb = reinterpret_cast<float*>(smem + kOffBias);
+    for (int i = lt; i < kTable; i += kLoaderThreads) sb[i] = __ldg(table + (size_t)i * g.nH + head);
+    int* kidx = reinterpret_cast<int*>(smem + kOffKidx);
+    for (int k = lt; k < kN; k += kLoaderThreads) kidx[k] = (k / kWS) * 23 + (k % kWS);
+  }
+  const int c = head * 32 + lane8 * 4;
   int it = 0;
   for (long long u = blockIdx.x; u < units; u += gridDim.x, ++it) {
     const int s = it & 1;
-    if (it >= 2) mbar_wait(&bars[QKV_EMPTY + s], (uint32_t)(((it >> 1) - 1) & 1), QKV_EMPTY + s);
     const Unit un = decode(u, g);
     unsigned char* st = smem + (size_t)s * kStageBytes;
-    float* sb = reinterpret_cast<float*>(smem + kOffBias) + s * kBiasStride;
-    for (int i = lt; i < kTable; i += kLoaderThreads) sb[i] = __ldg(table + (size_t)i * g.nH + un.head);
-    const int c = un.head * 32 + lane8 * 4;
+    float4 q[kItemsPerLoader], k[kItemsPerLoader], v[kItemsPerLoader];
+#pragma unroll
+    for (int p = 0; p < kItemsPerLoader; ++p) {      // the loads do not depend on the stage being free: issue them first
+      const int i = p * (kLoaderThreads / 8) + slot;
+      const int src = source_token(g, un, i);
+      q[p] = k[p] = v[p] = make_float4(0.f, 0.f, 0.f, 0.f);   // pad token: qkv == bias (swin.py:247-255)
+      if (src >= 0) {
+        const float* ptr = qkv + (size_t)src * (3 * C) + c;
+        q[p] = ldg_f4(ptr);
+        k[p] = ldg_f4(ptr + C);
+        v[p] = ldg_f4(ptr + 2 * C);
+      }
+    }
+    if (it >= 2) mbar_wait(&bars[QKV_EMPTY + s], (uint32_t)(((it >> 1) - 1) & 1), QKV_EMPTY + s);
+    // the head's qkv bias: L1-resident after the first unit (kept out of the registers the 18 loads in flight need)
     const float4 bq = ldg_f4(qkv_bias + c), bk = ldg_f4(qkv_bias + C + c), bv = ldg_f4(qkv_bias + 2 * C + c);
 #pragma unroll
-    for (int grp = 0; grp < 3; ++grp) {
-      float4 q[3], k[3], v[3];
-#pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        const int i = (grp * 3 + p) * 16 + slot;
-        const int src = source_token(g, un, i);
-        q[p] = k[p] = v[p] = make_float4(0.f, 0.f, 0.f, 0.f);   // pad token: qkv == bias (swin.py:247-255)
-        if (src >= 0) {
-          const float* ptr = qkv + (size_t)src * (3 * C) + c;
-          q[p] = ldg_f4(ptr);
-          k[p] = ldg_f4(ptr + C);
-          v[p] = ldg_f4(ptr + 2 * C);
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        const int i = (grp * 3 + p) * 16 + slot;
-        float4 qq = q[p], kk = k[p], vv = v[p];
-        qq.x = (qq.x + bq.x) * scale; qq.y = (qq.y + bq.y) * scale; qq.z = (qq.z + bq.z) * scale; qq.w = (qq.w + bq.w) * scale;
-        kk.x += bk.x; kk.y += bk.y; kk.z += bk.z; kk.w += bk.w;
-        vv.x += bv.x; vv.y += bv.y; vv.z += bv.z; vv.w += bv.w;
-        store_token(st, i, lane8, qq, kk, vv);
-      }
+    for (int p = 0; p < kItemsPerLoader; ++p) {
+      const int i = p * (kLoaderThreads / 8) + slot;
+      float4 qq = q[p], kk = k[p], vv = v[p];
+      qq.x = (qq.x + bq.x) * scale; qq.y = (qq.y + bq.y) * scale; qq.z = (qq.z + bq.z) * scale; qq.w = (qq.w + bq.w) * scale;
+      kk.x += bk.x; kk.y += bk.y; kk.z += bk.z; kk.w += bk.w;
+      vv.x += bv.x; vv.y += bv.y; vv.z += bv.z; vv.w += bv.w;
+      store_token(st, i, lane8, qq, kk, vv);
     }
     fence_proxy_async_smem();
     mbar_arrive(&bars[QKV_FULL + s]);
@@ -296,7 +305,7 @@ __device__ __forceinline__ float softmax_unit(unsigned char* smem, uint64_t* bar
 
   // relative-position bias (swin.py:108-121: index = (qy-ky+11)*23 + (qx-kx+11)) and the shift mask
   const int qy = rc.row / kWS, qx = rc.row - qy * kWS;
-  const float* sbias = reinterpret_cast<const float*>(smem + kOffBias) + (n & 1) * kBiasStride + (qy + 11) * 23 + (qx + 11);
+  const float* sbias = reinterpret_cast<const float*>(smem + kOffBias) + (qy + 11) * 23 + (qx + 11);
   const int* kidx = reinterpret_cast<const int*>(smem + kOffKidx);
   const int key0 = TAIL ? rc.half * kTailKeys0 : rc.half * 72;
   float sc[NCOL];
@@ -522,11 +531,10 @@ swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restr
     mbar_init(&bars[O_FREE + 0], 8);
     mbar_init(&bars[O_FREE + 1], 1);
     mbar_init_fence();
-  } else if (warp == kAllocWarp) {
+  }
+  if (warp == kAllocWarp) {
+    __syncwarp();
     tmem_alloc(tmem_slot, 512);
-  } else if (warp == kAllocWarp + 1) {
-    int* kidx = reinterpret_cast<int*>(smem + kOffKidx);
-    for (int k = lane; k < kN; k += 32) kidx[k] = (k / kWS) * 23 + (k % kWS);
   }
   fence_before();
   __syncthreads();
@@ -577,7 +585,10 @@ static int launch(cudaStream_t st, const float* qkv, const float* bias, const fl
     set_error("swin_window_attention_tc: cudaFuncSetAttribute(%d): %s", kSmemBytes, cudaGetErrorString(e));
     return UNIVS_E_LAUNCH;
   }
-  const int grid = (int)(units < num_sms ? units : num_sms);
+  // one head per CTA: the grid is a multiple of the head count (units = windows * nH is one too), unit u has head u % nH
+  long long grid_ll = g.nH <= num_sms ? (long long)(num_sms / g.nH) * g.nH : g.nH;
+  if (grid_ll > units) grid_ll = units;
+  const int grid = (int)grid_ll;
   const float scale = 0.17677669529663687f;   // 32^-0.5 (swin.py:96)
   swin_window_attn_tc12_kernel<<<grid, kThreads, kSmemBytes, st>>>(qkv, bias, table, g, units, scale, out, out16, dbg);
   return check_launch("swin_window_attention_tc");
