@@ -323,7 +323,9 @@ def main():
             graphed = GraphedClip(model, frames_dev, lambda: make_targets(T, dev))
             ok = torch.ones(1, device=dev)
         except Exception as e:  # noqa: BLE001  (e.g. a collective that refuses stream capture)
-            sys.stderr.write(f"[bench] CUDA-graph capture failed on rank {rank}: {e}\n")
+            import traceback
+            sys.stderr.write(f"[bench] CUDA-graph capture failed on rank {rank}: {e}\n"
+                             + "".join(traceback.format_exc().splitlines(True)[-14:]))
             graphed, ok = None, torch.zeros(1, device=dev)
         if world > 1:                                   # all ranks must take the same path
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)

@@ -194,6 +194,7 @@ int univs_proca_forward_f32(void* stream, const float* q, const float* k_self, c
  *   e.g. swin.py:246,292).  channels % 4 == 0, <= 4096.
  * gelu: exact erf GELU (nn.GELU default, swin.py:24-41). */
 #define UNIVS_SPLIT_F16U (-2)  /* fp16 [rows,2C] = [hi | lo]  (operands of the fp16 mask einsum)                            */
+#define UNIVS_SPLIT_F16C (-3)  /* fp16 [rows,2C] = [hi | lo*2^11]  (compact operand of univs_gemm_f16x3_tc: 4 bytes / element) */
 /* split = -Kc (Kc >= 4, Kc | C): fp16 [rows,3C] in K-chunks [lo*2^11 | hi*2^-11 | hi]  (A operand of the fp16x3 GEMM) */
 int univs_layernorm_f32(void* stream, const float* x, const float* residual, const float* residual_bias,
                         const float* gamma, const float* beta, int64_t rows, int channels, float eps, float* sum_out,

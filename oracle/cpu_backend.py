@@ -97,6 +97,10 @@ def _maybe_split(y, split):
         return y
     if split in ("f16", "f16u"):
         return _split16(y, split == "f16")
+    if split == "f16c":                       # compact [hi | lo*2^11] (UNIVS_SPLIT_F16C)
+        hi = y.clamp(-65504, 65504).half()
+        lo = ((y - hi.float()) * 2048.0).clamp(-65504, 65504).half()
+        return torch.cat([hi, lo], -1)
     return _split(y)
 
 

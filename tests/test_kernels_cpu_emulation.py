@@ -80,6 +80,9 @@ def _same_operand(a, b, fmt):
     if fmt == "f16u":
         C = a.shape[-1] // 2
         _close(a[..., :C].float() + a[..., C:].float(), b[..., :C].float() + b[..., C:].float(), 4e-6)
+    elif fmt == "f16c":                                 # compact [hi | lo * 2^11]
+        C = a.shape[-1] // 2
+        _close(a[..., :C].float() + a[..., C:].float() / 2048.0, b[..., :C].float() + b[..., C:].float() / 2048.0, 4e-6)
     elif fmt == "f16":
         C = a.shape[-1] // 3
         kc = ops.f16_chunk(C)
@@ -97,7 +100,7 @@ def _same_operand(a, b, fmt):
 
 # ------------------------------------------------------------------ validated kernels: a check of the emulator itself
 @pytest.mark.parametrize("rows,C", [(37, 192), (5, 48), (9, 1024)])
-@pytest.mark.parametrize("fmt", [None, "tf32", "f16", "f16u"])
+@pytest.mark.parametrize("fmt", [None, "tf32", "f16", "f16u", "f16c"])
 def test_validated_rowwise_kernels_on_the_emulator(emu, rows, C, fmt):
     g = torch.Generator().manual_seed(rows + C)
     x, r = torch.randn(rows, C, generator=g) * 2, torch.randn(rows, C, generator=g)
@@ -266,7 +269,7 @@ def test_rowwise_v2_kernels_are_bit_identical_on_the_emulator(emu_lib_path, monk
     def run():
         out = []
         for x, b, w, bb, r in cases:
-            for fmt in ("f16", "f16u"):
+            for fmt in ("f16", "f16u", "f16c"):
                 out.append(plain(ops.gelu(dev(x), split=fmt, bias=dev(b))))
                 out.append(plain(ops.relu(dev(x), split=fmt)))
                 out.append(plain(ops.split_operand(dev(x), fmt)))
@@ -280,7 +283,7 @@ def test_rowwise_v2_kernels_are_bit_identical_on_the_emulator(emu_lib_path, monk
     monkeypatch.setenv("UNIVS_ROWWISE_V2", "3")
     monkeypatch.setattr(_cabi, "_lib", _load(v2_path))
     v2 = run()
-    assert len(base) == len(v2) == 60
+    assert len(base) == len(v2) == 90
     for a, b in zip(base, v2):
         assert a.dtype == b.dtype and a.shape == b.shape
         assert torch.equal(a.contiguous().view(torch.int16), b.contiguous().view(torch.int16))

@@ -23,7 +23,7 @@ for rows, C in [(1, 8), (37, 48), (1000, 192), (4600, 768), (333, 6144), (7, 204
     x = (torch.randn(rows, C, device="cuda") * 3).contiguous()
     x[0, 0] = 70000.0          # saturates the fp16 hi part
     b = torch.randn(C, device="cuda")
-    for fmt in ("f16", "f16u"):
+    for fmt in ("f16", "f16u", "f16c"):
         out[f"gelu_{rows}_{C}_{fmt}"] = ops.gelu(x, split=fmt, bias=b).cpu()
         out[f"relu_{rows}_{C}_{fmt}"] = ops.relu(x, split=fmt, bias=None).cpu()
         out[f"split_{rows}_{C}_{fmt}"] = ops.split_operand(x, fmt).cpu()
@@ -47,7 +47,7 @@ def test_rowwise_v2_bit_identical():
             env = dict(os.environ, UNIVS_ROWWISE_V2=v2)
             subprocess.run([sys.executable, "-c", _CHILD, path, ROOT], check=True, env=env, timeout=600)
             res[v2] = torch.load(path)
-    assert res["0"].keys() == res["3"].keys() and len(res["0"]) == 36 + 30
+    assert res["0"].keys() == res["3"].keys() and len(res["0"]) == 54 + 45
     for k in res["0"]:
         a, b = res["0"][k], res["3"][k]
         assert a.dtype == b.dtype and a.shape == b.shape, k

@@ -139,7 +139,7 @@ gelu_split8_kernel(const float* __restrict__ x, const float* __restrict__ bias, 
       const __half2 s2 = __floats2half2_rn(hf.x * (1.f / 2048.f), hf.y * (1.f / 2048.f));
       hs[e] = *reinterpret_cast<const uint32_t*>(&s2);
     }
-    if (split == -2) {          // [hi | lo]
+    if (split == -2 || split == -3) {          // [hi | lo] / [hi | lo*2^11]
       __half* o = out + (size_t)row * (2 * (size_t)C) + col;
       *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(o + C) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -241,7 +241,7 @@ layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ res
     const uint32_t ns0 = __shfl_down_sync(0xffffffffu, hs[0], 1), ns1 = __shfl_down_sync(0xffffffffu, hs[1], 1);
     if (has && (lane & 1) == 0) {
       const int col = idx * 4;                       // multiple of 8
-      if (split == -2) {                             // [hi | lo]
+      if (split == -2 || split == -3) {              // [hi | lo] / [hi | lo*2^11]
         __half* o16 = out + (size_t)row * (2 * (size_t)C) + col;
         *reinterpret_cast<uint4*>(o16) = make_uint4(hi[0], hi[1], nh0, nh1);
         *reinterpret_cast<uint4*>(o16 + C) = make_uint4(lo[0], lo[1], nl0, nl1);
@@ -259,7 +259,7 @@ layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ res
 // returns true when the v2 kernel took the launch
 static bool launch_split8(cudaStream_t st, const float* x, const float* bias, int64_t rows, int C, float* out, int mode, int split) {
   if (!rowwise_v2_enabled() || split >= 0 || C % 8 != 0) return false;
-  if (split != -2 && ((-split) % 8 != 0)) return false;
+  if (split != -2 && split != -3 && ((-split) % 8 != 0)) return false;
   const int64_t total8 = rows * (C / 8);
   if (total8 >= (1ll << 31) - (1ll << 24)) return false;
   if (((uintptr_t)x | (uintptr_t)out) & 15) return false;
@@ -284,12 +284,12 @@ extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* re
   UNIVS_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
   UNIVS_REQUIRE(residual_bias == nullptr || residual != nullptr, "layernorm: residual_bias needs a residual");
   UNIVS_REQUIRE(channels % 4 == 0 && channels <= 4096, "layernorm: channels must be a multiple of 4 and <= 4096 (got %d)", channels);
-  UNIVS_REQUIRE(split == 0 || split == -2 || (split != -1 && split != -3 && (split > 0 ? split : -split) % 4 == 0 &&
+  UNIVS_REQUIRE(split == 0 || split == -2 || split == -3 || (split != -1 && (split > 0 ? split : -split) % 4 == 0 &&
                                                channels % (split > 0 ? split : -split) == 0),
                 "layernorm: split chunk must divide channels");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rowwise_v2_bits() & 2) && split < 0 && channels % 8 == 0 && (split == -2 || (-split) % 8 == 0) &&
+  if ((rowwise_v2_bits() & 2) && split < 0 && channels % 8 == 0 && (split == -2 || split == -3 || (-split) % 8 == 0) &&
       (((uintptr_t)x | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)sum_out) & 15) == 0) {
     __half* o16 = reinterpret_cast<__half*>(out);
 #define LNW_LAUNCH(MV) layernorm_wide_kernel<MV><<<grid, 256, 0, st>>>(x, residual, residual_bias, gamma, beta, rows, channels, eps, sum_out, o16, split)
@@ -337,7 +337,7 @@ extern "C" int univs_relu_f32(void* stream, const float* x, const float* bias, i
 
 extern "C" int univs_split_tf32_f32(void* stream, const float* x, int64_t rows, int channels, int chunk, float* out) {
   UNIVS_REQUIRE(rows >= 0 && channels > 0 && channels % 4 == 0, "split_tf32: bad sizes (channels %% 4 == 0)");
-  UNIVS_REQUIRE(chunk == -2 || (chunk != 0 && chunk != -1 && chunk != -3 && (chunk > 0 ? chunk : -chunk) % 4 == 0 &&
+  UNIVS_REQUIRE(chunk == -2 || chunk == -3 || (chunk != 0 && chunk != -1 && (chunk > 0 ? chunk : -chunk) % 4 == 0 &&
                                channels % (chunk > 0 ? chunk : -chunk) == 0),
                 "split_tf32: |chunk| must divide channels and be a multiple of 4 (or -2 for the fp16 [hi|lo] format)");
   if (rows == 0) return UNIVS_OK;

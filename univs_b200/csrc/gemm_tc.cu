@@ -113,7 +113,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const u
     const bool odd = lane & 1;
     const int ne = n & ~1;                                   // first channel of the pair
     __half* hp = a.out16 + (size_t)(t0 + (odd ? 1 : 0)) * a.ld16 + ne;
-    const bool pair_ok = ne + 1 < a.N;                       // both channels valid (N even in practice)
+    // 4-byte stores need an even channel count, lo offset and row pitch (true for every layer of the path); otherwise the
+    // two channels are stored one by one
+    const bool even = ((a.N | a.lo_off16 | a.ld16) & 1) == 0;
+    const bool pair_ok = even && ne + 1 < a.N;
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       const float mine = odd ? v[j + 1] : v[j];              // my channel, my token
@@ -126,9 +129,15 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const u
       if (FULL || (tok < nt && pair_ok)) {
         *reinterpret_cast<__half2*>(hp) = h;
         *reinterpret_cast<uint32_t*>(hp + a.lo_off16) = lo;
-      } else if (tok < nt && ne < a.N) {                     // odd channel count: the last channel alone
-        hp[0] = __low2half(h);
-        hp[a.lo_off16] = __ushort_as_half((unsigned short)(lo & 0xffffu));
+      } else if (tok < nt) {
+        if (ne < a.N) {
+          hp[0] = __low2half(h);
+          hp[a.lo_off16] = __ushort_as_half((unsigned short)(lo & 0xffffu));
+        }
+        if (ne + 1 < a.N) {
+          hp[1] = __high2half(h);
+          hp[a.lo_off16 + 1] = __ushort_as_half((unsigned short)(lo >> 16));
+        }
       }
       hp += 2 * a.ld16;
     }
@@ -235,7 +244,8 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
       const int tt = tile / n_ct, ct = tile - tt * n_ct;
       const int n = ct * kBM + wq * 32 + lane;              // this thread's output channel
       const bool n_ok = n < a.N;
-      const bool tile_full = (ct + 1) * kBM <= a.N;         // every lane of every warp has a valid channel
+      // every lane of every warp has a valid channel (and the packed operand stores are aligned)
+      const bool tile_full = (ct + 1) * kBM <= a.N && (!OUT16 || ((a.N | a.lo_off16 | a.ld16) & 1) == 0);
       const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
       mbar_wait(&tfull[acc], acc_phase, 40 + acc);
       fence_after();

@@ -190,8 +190,8 @@ extern "C" int univs_groupnorm_apply_f32(void* stream, const float* x, int frame
   UNIVS_REQUIRE(lowres == nullptr || (low_height > 0 && low_width > 0 && lowres_img_stride % 4 == 0 &&
                                       lowres_img_stride >= (int64_t)low_height * low_width * channels),
                 "groupnorm_apply: bad low-resolution size / stride");
-  UNIVS_REQUIRE(out_split == nullptr || split == UNIVS_SPLIT_F16U ||
-                    (split != 0 && split != -1 && split != -3 && (split > 0 ? split : -split) % 4 == 0 &&
+  UNIVS_REQUIRE(out_split == nullptr || split == UNIVS_SPLIT_F16U || split == UNIVS_SPLIT_F16C ||
+                    (split != 0 && split != -1 && (split > 0 ? split : -split) % 4 == 0 &&
                      channels % (split > 0 ? split : -split) == 0),
                 "groupnorm_apply: split chunk must divide channels");
   UNIVS_REQUIRE(row_stride % 4 == 0 && img_stride % 4 == 0, "groupnorm_apply: strides must keep 16-byte alignment");

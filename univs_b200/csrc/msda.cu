@@ -517,8 +517,8 @@ extern "C" int univs_ms_deform_attn_encoder_tiled_f32(void* stream, const float*
                                                                                  num_heads, log2w, out, nullptr, nullptr, 0);
   } else {
     const int C = num_heads * 32;
-    UNIVS_REQUIRE(split == 0 || split == UNIVS_SPLIT_F16U ||
-                      (split != -1 && split != -3 && (split > 0 ? split : -split) % 4 == 0 && C % (split > 0 ? split : -split) == 0),
+    UNIVS_REQUIRE(split == 0 || split == UNIVS_SPLIT_F16U || split == UNIVS_SPLIT_F16C ||
+                      (split != -1 && (split > 0 ? split : -split) % 4 == 0 && C % (split > 0 ? split : -split) == 0),
                   "ms_deform_attn_encoder_tiled: split chunk must divide heads*32");
     msda_encoder_tiled_kernel<3, 4, true><<<grid, 256, 0, (cudaStream_t)stream>>>(value, lt, tt, offs_logits, spatial_size,
                                                                                 num_heads, log2w, out, value_bias,

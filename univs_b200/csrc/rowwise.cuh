@@ -18,6 +18,8 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(f2tf3
 //   0          plain fp32 [rows, C]
 //   Kc > 0     fp32 [rows, 2C] in K-chunks of Kc columns, chunk c = [hi_c | lo_c], hi = rna_tf32(x), lo = x - hi
 //   -2         fp16 [rows, 2C] = [hi | lo], hi = fp16(x) (round-to-nearest, saturating), lo = x - hi   (einsum operands)
+//   -3         fp16 [rows, 2C] = [hi | lo * 2^11]: the compact operand of the tcgen05 GEMM (gemm_tc.cu), which keeps the
+//              correction terms in their own accumulator and therefore needs no hi * 2^-11 copy: 4 bytes per element
 //   -Kc <= -4  fp16 [rows, 3C] in K-chunks of Kc columns, chunk c = [lo_c * 2^11 | hi_c * 2^-11 | hi_c]: the A operand of
 //              the single-GEMM fp16x3 product  X W^T = [Xl' | Xh_s | Xh] [Wh_s | Wl' | Wh]^T  (correction terms first, so
 //              the tensor core's truncating accumulator is still small while they are added; main term last).
@@ -47,7 +49,7 @@ __device__ __forceinline__ void store_maybe_split(float* __restrict__ out, size_
       l[i] = sat_half((vv[i] - hf) * sc);
       hs[i] = __float2half_rn(hf * (1.f / 2048.f));
     }
-    if (split == -2) {
+    if (split == -2 || split == -3) {
       const size_t o = row * (2 * (size_t)C) + col;
       *reinterpret_cast<__half2*>(o16 + o) = __halves2half2(h[0], h[1]);
       *reinterpret_cast<__half2*>(o16 + o + 2) = __halves2half2(h[2], h[3]);

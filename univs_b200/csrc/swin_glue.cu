@@ -185,9 +185,9 @@ layernorm_multi_kernel(const float* __restrict__ x, const float* __restrict__ re
 using namespace univs;
 
 static bool split_ok(int split, int channels) {
-  if (split == 0 || split == UNIVS_SPLIT_F16U) return true;
+  if (split == 0 || split == UNIVS_SPLIT_F16U || split == UNIVS_SPLIT_F16C) return true;
   const int a = split > 0 ? split : -split;
-  return split != -1 && split != -3 && a % 4 == 0 && channels % a == 0;
+  return split != -1 && a % 4 == 0 && channels % a == 0;
 }
 
 extern "C" int univs_patchify_normalize(void* stream, const void* frames, int is_uint8, int num_frames, int height, int width,

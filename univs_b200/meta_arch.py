@@ -86,8 +86,14 @@ class UniVS_Prompt(nn.Module):
         if frames.dtype not in (torch.uint8, torch.float32):
             frames = frames.float()
         H, W = frames.shape[-2:]
-        return self.backbone.forward_frames(frames.contiguous(), self.pixel_mean.flatten().tolist(),
-                                            self.pixel_std.flatten().tolist(), self._padded_size(H, W))
+        # host copies of the normalisation constants, read back ONCE per buffer version: a device->host read in every step
+        # cannot be captured in a CUDA graph (round 2: this silently sent the fused-glue step down the eager path)
+        key = (self.pixel_mean.data_ptr(), self.pixel_mean._version, self.pixel_std.data_ptr(), self.pixel_std._version)
+        cached = self.__dict__.get("_mean_std_host")
+        if cached is None or cached[0] != key:
+            cached = (key, self.pixel_mean.flatten().tolist(), self.pixel_std.flatten().tolist())
+            self.__dict__["_mean_std_host"] = cached
+        return self.backbone.forward_frames(frames.contiguous(), cached[1], cached[2], self._padded_size(H, W))
 
     @torch.no_grad()
     def clip_forward(self, frames, targets):
@@ -117,7 +123,12 @@ class UniVS_Prompt(nn.Module):
         dec = self.sem_seg_head.predictor
         if self.shard_decoder and dec.supports_exchange(targets):
             # frames stay on their rank through the decoder; only query tokens are exchanged (sharding.TokenExchange)
-            ex = TokenExchange(self.sharder, T)
+            # one exchange object per clip length: its device-resident frame-index tensors are created once (a host->device
+            # copy inside the step would break CUDA-graph capture)
+            cache = self.__dict__.setdefault("_exchange_cache", {})
+            ex = cache.get(T)
+            if ex is None:
+                ex = cache[T] = TokenExchange(self.sharder, T)
             whole = frames if fused else x
             local = whole.index_select(0, ex.frames_tensor(whole.device))
             features = self.backbone_from_frames(local) if fused else self.backbone(local)

@@ -61,6 +61,8 @@ class _Block(nn.Module):
         that consume them (LayerNorm, GELU, window attention); LayerNorm / GELU outputs are emitted directly in the GEMM
         operand format of the active policy (nn_ops)."""
         a = self.attn
+        if nn_ops.gemm_tc() and a.qkv.weight.shape[1] <= 1536 and x.is_contiguous():
+            return self._forward_fused_residual(x, pending, pending_bias)
         x, h = nn_ops.layernorm(x, self.norm1, residual=pending, want_sum=True, residual_bias=pending_bias)
         qkv = nn_ops.linear_prepped(h, a.qkv.weight, None)                  # bias added inside the attention kernel
         bias = a.qkv.bias if a.qkv.bias is not None else x.new_zeros(qkv.shape[-1])
@@ -74,6 +76,23 @@ class _Block(nn.Module):
         x, h = nn_ops.layernorm(x, self.norm2, residual=y, want_sum=True, residual_bias=a.proj.bias)
         z = nn_ops.mlp(h, self.mlp.fc1, self.mlp.fc2)      # fc1 -> GELU (+ deferred fc1 bias) -> fc2 (optionally in L2-sized row chunks)
         return x, z, self.mlp.fc2.bias
+
+
+    def _forward_fused_residual(self, x, pending, pending_bias):
+        """Own-GEMM variant: both residual adds (and the proj / fc2 biases) ride in the GEMM epilogues, which update the
+        residual stream in place; the LayerNorms read one tensor and write only the next operand."""
+        a = self.attn
+        if pending is not None:                    # first block after a library-path producer
+            x, h = nn_ops.layernorm(x, self.norm1, residual=pending, want_sum=True, residual_bias=pending_bias)
+        else:
+            h = nn_ops.layernorm(x, self.norm1)[1]
+        qkv = nn_ops.linear_prepped(h, a.qkv.weight, None)
+        bias = a.qkv.bias if a.qkv.bias is not None else x.new_zeros(qkv.shape[-1])
+        ys = ops.swin_window_attention_operand(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift)
+        x = nn_ops.linear_residual(ys, a.proj.weight, a.proj.bias, x)
+        h = nn_ops.layernorm(x, self.norm2)[1]
+        x = nn_ops.mlp(h, self.mlp.fc1, self.mlp.fc2, residual=x)
+        return x, None, None
 
 
 class _PatchMerging(nn.Module):
@@ -108,9 +127,11 @@ class _Stage(nn.Module):
         for blk in self.blocks:
             x, pending, pbias = blk(x, pending, pbias)
         y = None
-        if out_norm is not None:
+        if out_norm is not None and pending is None:        # residuals already folded in (own-GEMM epilogues)
+            y = nn_ops.layernorm(x, out_norm, for_gemm=False)[1]
+        elif out_norm is not None:
             x, y = nn_ops.layernorm(x, out_norm, residual=pending, want_sum=True, for_gemm=False, residual_bias=pbias)
-        else:
+        elif pending is not None:
             x = x + pending + pbias
         return y, (self.downsample(x) if self.downsample is not None else x)
 

@@ -40,19 +40,23 @@ def gemm_tc() -> bool:
     return _gemm_tc and _policy == "fp16x3"
 
 
-def _tc_linear(h3, K, b3, alpha, bias, act=0, want_f32=True, want_operand=False, compact=False):
-    """y = act(x W^T + bias) through ops.gemm_f16x3_tc.  h3: activation operand [rows, 3K] in the K-chunk container
-    [lo' | hi_s | hi] of the row-wise kernels, or (compact) [rows, 2K] = [hi | lo'] as written by the GEMM's own operand
-    epilogue; b3: weight operand [N, 3K] chunks [hi_s | lo' | hi] (_split_weight).  K-chunks beyond the first accumulate
-    into the fp32 result in place."""
+def _tc_linear(h3, K, b3, alpha, bias, act=0, want_f32=True, want_operand=False, addend=None, inplace=False):
+    """y = act(x W^T + bias) (+ addend) through ops.gemm_f16x3_tc.  h3: activation operand, either [rows, 3K] in the K-chunk
+    container [lo' | hi_s | hi] (attention / MSDeformAttn epilogues, split "f16") or the compact [rows, 2K] = [hi | lo']
+    (row-wise kernels with split "f16c", the GEMM's own operand epilogue) -- told apart by the width; b3: weight operand
+    [N, 3K] chunks [hi_s | lo' | hi] (_split_weight).  K-chunks beyond the first accumulate into the fp32 result in place.
+    `addend` [rows, N] fp32 is added by the epilogue (residual); with `inplace` the result overwrites it."""
+    compact = h3.shape[-1] == 2 * K
+    assert compact or h3.shape[-1] == 3 * K, (tuple(h3.shape), K)
     kc = ops.f16_chunk(K)
     n = K // kc
     assert n == 1 or (act == 0 and not want_operand), "activation / operand epilogues need a single K-chunk"
-    y = y16 = None
+    y, y16 = addend, None
     for c in range(n):
         x_offs = (c * kc, K + c * kc) if compact else (c * 3 * kc + 2 * kc, c * 3 * kc)
         w_offs = (c * 3 * kc + 2 * kc, c * 3 * kc + kc)
-        y, y16 = ops.gemm_f16x3_tc(h3, x_offs, b3, w_offs, kc, alpha, bias if c == 0 else None, y, out=y, want_f32=want_f32,
+        y, y16 = ops.gemm_f16x3_tc(h3, x_offs, b3, w_offs, kc, alpha, bias if c == 0 else None, y,
+                                   out=y if (c > 0 or addend is None or inplace) else None, want_f32=want_f32,
                                    want_operand=want_operand, act=act)
     return y, y16
 
@@ -82,7 +86,10 @@ def splitting() -> bool:
 
 
 def _fmt():
-    """operand format produced by the fused kernels for the active policy"""
+    """operand format produced by the fused kernels for the active policy: with the own tcgen05 GEMM the compact
+    [hi | lo*2^11] container (4 bytes per element; the library-GEMM formulation needs the 6-byte [lo' | hi_s | hi] one)"""
+    if _policy == "fp16x3" and _gemm_tc:
+        return "f16c"
     return {"tf32x3": "tf32", "fp16x3": "f16"}.get(_policy)
 
 
@@ -231,7 +238,13 @@ def linear_prepped(h, weight, bias=None, cache=True):
             y.addmm_(h2[:, k0:k0 + kc], wh[:, k0:k0 + kc].t())
         y.addmm_(h2, wlh.t())
     elif gemm_tc() and K % 8 == 0:
-        y = _tc_linear(h.reshape(-1, 3 * K), K, wh, wlh, None if bias is None else bias.float().contiguous())[0]
+        y = _tc_linear(h.reshape(-1, h.shape[-1]), K, wh, wlh, None if bias is None else bias.float().contiguous())[0]
+    elif gemm_tc():      # K % 8 != 0: tiny prompt-side products; rebuild the fp32 value (hi + lo' * 2^-11, exact) -> IEEE GEMM
+        h2 = h.reshape(-1, h.shape[-1]).float()
+        x = (h2[:, :K] + h2[:, K:] * 2.0 ** -11) if h2.shape[-1] == 2 * K else \
+            (h2.view(-1, 1, 3, K)[:, :, 2] + h2.view(-1, 1, 3, K)[:, :, 0] * 2.0 ** -11).reshape(-1, K)
+        with ieee_fp32():
+            y = F.linear(x, weight.float(), bias)
     else:  # fp16x3: ONE fp16 GEMM per K-chunk over [Xl' | Xh_s | Xh] x [Wh_s | Wl' | Wh], fp32 accumulate and output
         f32 = torch.float32
         b3, alpha = wh, wlh
@@ -286,17 +299,37 @@ def mlp_rows_per_chunk(rows: int, hidden: int) -> int:
     return rows if chunk >= rows else chunk
 
 
-def mlp(h, fc1, fc2):
-    """fc2(GELU(fc1(h) + b1)) without b2 (deferred into the consumer, like everywhere on this path); h is the operand of fc1."""
+def linear_residual(h, weight, bias, residual):
+    """residual + h W^T + bias, written over `residual` (own GEMM only: the residual add and the bias ride in the epilogue,
+    the consumer LayerNorm then reads one tensor instead of two and writes no sum).  h: operand of the layer."""
+    assert gemm_tc()
+    N, K = weight.shape
+    b3, alpha = _split_weight(weight)
+    r2 = residual.view(-1, N)
+    _tc_linear(h.reshape(-1, h.shape[-1]), K, b3, alpha, None if bias is None else bias, addend=r2, inplace=True)
+    return residual
+
+
+def mlp(h, fc1, fc2, residual=None):
+    """fc2(GELU(fc1(h) + b1)) without b2 (deferred into the consumer, like everywhere on this path); h is the operand of fc1.
+    With `residual` (own GEMM only): residual + fc2(...) + b2, written over `residual`."""
     width = h.shape[-1]
     rows = h.numel() // width
+    if residual is not None:
+        assert gemm_tc() and fc1.in_features % 8 == 0 and fc1.in_features <= 1536
+        b31, a1 = _split_weight(fc1.weight)
+        b32, a2 = _split_weight(fc2.weight)
+        hid16 = _tc_linear(h.reshape(rows, width), fc1.in_features, b31, a1, fc1.bias, act=ops.ACT_GELU, want_f32=False,
+                           want_operand=True)[1]
+        _tc_linear(hid16, fc1.out_features, b32, a2, fc2.bias, addend=residual.view(rows, fc2.out_features), inplace=True)
+        return residual
     if gemm_tc() and fc1.in_features % 8 == 0 and fc1.in_features <= 1536:
         # fc1 + bias + GELU + operand emission in ONE kernel: the fp32 hidden activation never exists
         b31, a1 = _split_weight(fc1.weight)
         b32, a2 = _split_weight(fc2.weight)
         hid16 = _tc_linear(h.reshape(rows, width), fc1.in_features, b31, a1, fc1.bias, act=ops.ACT_GELU, want_f32=False,
                            want_operand=True)[1]
-        y = _tc_linear(hid16, fc1.out_features, b32, a2, None, compact=True)[0]
+        y = _tc_linear(hid16, fc1.out_features, b32, a2, None)[0]
         return y.view(*h.shape[:-1], fc2.out_features)
     chunk = mlp_rows_per_chunk(rows, fc1.out_features)
     if chunk >= rows:
@@ -389,7 +422,8 @@ def _conv_taps(xs, H, W, weight, bias, taps):
         off = (t // kw) * Wp + (t % kw)
         a = x2[off: off + R]
         if gemm_tc() and Cin % 8 == 0 and Cin <= 1536:
-            ops.gemm_f16x3_tc(a, (2 * Cin, 0), wh, (2 * Cin, Cin), Cin, wlh, bias.float() if (bias is not None and t == 0) else None,
+            x_offs = (0, Cin) if a.shape[-1] == 2 * Cin else (2 * Cin, 0)       # compact / K-chunk container
+            ops.gemm_f16x3_tc(a, x_offs, wh, (2 * Cin, Cin), Cin, wlh, bias.float() if (bias is not None and t == 0) else None,
                               yr if t else None, out=yr)
             continue
         if _policy == "tf32x3":

@@ -447,6 +447,8 @@ def _split_code(split, C):
         return -f16_chunk(C), 3, torch.float16
     if split == "f16u":
         return -2, 2, torch.float16
+    if split == "f16c":
+        return -3, 2, torch.float16
     raise ValueError(split)
 
 

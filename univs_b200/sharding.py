@@ -28,10 +28,10 @@ class FrameSharder:
         self._order = {}
 
     def local_frames(self, x):
-        idx = frame_plan(x.shape[0], self.world_size)[self.rank]
-        if not idx:                      # an idle rank still takes part in the collective with a padding frame
+        if self.rank >= x.shape[0]:     # an idle rank still takes part in the collective with a padding frame
             return x[:0]
-        return x[idx]
+        # round robin = a strided slice: no index tensor, hence no host->device copy (the step is captured in a CUDA graph)
+        return x[self.rank::self.world_size].contiguous()
 
     def all_gather_frames(self, tensors, num_frames):
         """tensors: list of [T_local, ...] (same trailing shapes on every rank).  Returns the list of [T, ...]
