@@ -28,6 +28,12 @@ WORKLOADS = {
     "c2": ("tiny", 5, 480, 864, 100),        # BASELINE.json configs[1]
     "c5": ("large", 8, 1080, 1920, 200),     # BASELINE.json configs[4]: meant for --gpus 8 (one frame per GPU); fits one GPU too
 }
+# prompt configurations (BASELINE.json configs[2], configs[3]): eager execution (data-dependent host logic), N=1
+PROMPT_WORKLOADS = {
+    # name: (swin variant, T, H, W, Q, task, clips that grow the prompt memory before the timed clip)
+    "c3": ("base", 5, 720, 1280, 200, "sot", 2),          # P=10 visual prompts, R=128 points, memory of 2 earlier clips
+    "c4": ("large", 10, 720, 1280, 200, "grounding", 0),  # P=32 text prompts + lang->vision
+}
 
 
 def peaks():
@@ -183,13 +189,104 @@ def run_cpu_reference(args, workload, steps, warmup, as_line):
     }
 
 
+def run_prompt_workload(args, dev):
+    """BASELINE configs[2] / configs[3]: one step = the per-clip forward of a clip WITH prompts (ProCA path).  sot: the
+    visual-prompt memory has been grown by the preceding stride-1 clips (kv length 1 + R * (1 + frames in the pool)); every
+    step starts from a copy of that state.  Runs eagerly (the prompt sampler has data-dependent host control flow)."""
+    from univs_b200 import ops, switches
+    from univs_b200.build import build_model, make_cfg
+    from univs_b200.synthetic import ClipSource, clone_targets, univs_overrides
+    variant, T, H, W, Q, task, grow = PROMPT_WORKLOADS[args.workload]
+    src = ClipSource(task, T, T + grow, H, W)
+    cfg = make_cfg(variant, Q, T, clip_emb=src.clip_emb, **univs_overrides(task))
+    model = build_model(cfg).to(dev)
+    tg = src.targets(dev)
+    for c in range(grow):                                       # earlier clips of the video: fill the prompt memory pool
+        torch.manual_seed(100 + c)
+        model.clip_forward(src.clip_inputs(tg, c, dev), tg)
+    frames_dev = src.clip_inputs(tg, grow, dev).to(torch.uint8)
+    frames_host = frames_dev.cpu().pin_memory()
+    state = clone_targets(tg)
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    def step(frames):
+        torch.manual_seed(7)
+        return model.clip_forward(frames, clone_targets(state))
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(warmup):
+        out = step(frames_dev)
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timed(lambda: step(frames_dev), steps)
+    clocks = sampler.stop()
+    sink = ops.profile_events(True)
+    l0 = ops.launch_count
+    timed(lambda: step(frames_dev), steps)
+    launches = (ops.launch_count - l0) // steps
+    torch.cuda.synchronize()
+    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in sink.items()}
+    kernel_calls = {k: len(v) // steps for k, v in sink.items()}
+    ops.profile_events(False)
+    pinned = {}
+
+    def step_e2e():
+        o = step(frames_host)
+        for k, v in (("pred_logits", o["pred_logits"]), ("pred_embds", o["pred_embds"]), ("pred_masks_bin", o["pred_masks"] > 0)):
+            if k not in pinned:
+                pinned[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+            pinned[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, steps)
+    peak, peak_kind = peaks()
+    n_lp = out["pred_masks"].shape[1]
+    P = n_lp - Q
+    roof = None
+    if "proca" in kernel_ms:
+        # ProCA (SURVEY 8d): per layer e*2*Q_p*(1+L)*256 (T-invariant memory, read once) + e*2*Q_p*T*256; L from the pool
+        pool = state[0].get("prompt_feats")
+        L = int(pool.shape[1] * min(pool.shape[2], 1 + cfg.MODEL.UniVS.TEST.NUM_PREV_FRAMES_MEMORY)) if pool is not None else 78
+        nbytes = 4.0 * (2 * P * (1 + L) * 256 + 2 * P * T * 256)
+        ach = nbytes / (kernel_ms["proca"] * 1e-3) / 1e9
+        roof = {"kernel": "proca", "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "launch_ms": kernel_ms["proca"], "algorithmic_bytes_per_launch": nbytes,
+                "prompts": P, "memory_tokens_per_prompt": L,
+                "note": "latency-bound by size: a few MB per launch; the K/V in-projection of the memory tokens (library "
+                        "/ own GEMM) dominates the ProCA layer"}
+    print(json.dumps({
+        "metric": "frames/sec (per-clip forward with prompts)", "value": T / (ms / 1e3), "unit": "frames/s", "n_gpus": 1,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} task={task} P={P} prompts"
+                               + (f", prompt memory grown over {grow} earlier clips" if grow else ", lang->vision on"),
+                   "precision": args.precision, "execution": "eager", "switches": switches.active(),
+                   "l2": "per-step working set (multi-GB activations) exceeds the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": T / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": frames_host.numel(),
+                "d2h_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()), "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "roofline": roof,
+        "kernels": {k: {"ms_per_launch": kernel_ms[k], "launches_per_step": kernel_calls[k]} for k in sorted(kernel_ms)},
+        "cpu_baseline": None}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ns", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="ns", choices=list(WORKLOADS) + list(PROMPT_WORKLOADS))
     ap.add_argument("--video-frames", type=int, default=0,
                     help="> 0: secondary benchmark (SURVEY 8f rank 1) -- the VIS sliding-window head over a synthetic video of this "
                          "many frames of the workload's geometry (stride-1 clips of T frames), with per-frame feature reuse "
@@ -234,6 +331,10 @@ def main():
             dist.init_process_group("gloo")
         group = dist.group.WORLD
     set_precision(args.precision)
+    if args.workload in PROMPT_WORKLOADS:
+        if world > 1:
+            raise SystemExit("the prompt workloads are single-GPU benchmarks")
+        return run_prompt_workload(args, dev)
 
     variant, T, H, W, Q = WORKLOADS[args.workload]
     g = torch.Generator().manual_seed(0)

@@ -50,27 +50,7 @@ def _popcount32(x):
     return (x * 0x01010101 >> 24) & 0xFF
 
 
-def rectangle_masks(P, frames, H, W, seed=1):
-    """P axis-aligned rectangles of 2-20 % of the frame, drifting a few pixels per frame: masks [P, frames, H, W] float,
-    boxes [P, frames, 4] XYXY normalised (what PrepareTargets hands to the sampler, prepare_targets.py:327)."""
-    g = torch.Generator().manual_seed(seed)
-    masks, boxes = torch.zeros(P, frames, H, W), torch.zeros(P, frames, 4)
-    for p in range(P):
-        area = (0.02 + 0.18 * torch.rand(1, generator=g).item()) * H * W
-        aspect = 0.5 + 1.5 * torch.rand(1, generator=g).item()
-        h = int(min(H - 8, max(8, (area / aspect) ** 0.5)))
-        w = int(min(W - 8, max(8, area / h)))
-        y0 = int(torch.randint(0, H - h - 4, (1,), generator=g))
-        x0 = int(torch.randint(0, W - w - 4, (1,), generator=g))
-        for f in range(frames):
-            y, x = min(y0 + f, H - h), min(x0 + 2 * f, W - w)
-            masks[p, f, y:y + h, x:x + w] = 1
-            boxes[p, f] = torch.tensor([x / W, y / H, (x + w) / W, (y + h) / H])
-    return masks, boxes
-
-
-def _clone_targets(tg):
-    return [{k: (v.clone() if torch.is_tensor(v) else copy.deepcopy(v)) for k, v in t.items()} for t in tg]
+from univs_b200.synthetic import ClipSource, clone_targets as _clone_targets, rectangle_masks, univs_overrides  # noqa: E402,F401
 
 
 def run_config(name, T=None, clips=None, precision="fp16x3", variant=None, hw=None, points=128, threads=None):
@@ -82,12 +62,9 @@ def run_config(name, T=None, clips=None, precision="fp16x3", variant=None, hw=No
     if hw is not None:
         H, W = hw
     dry = not torch.cuda.is_available()        # no GPU: oracle side only (checks the target construction)
-    g = torch.Generator().manual_seed(0)
-    clip_emb = torch.randn(3938, 640, generator=g)
-    over = {"sot": dict(VISUAL_PROMPT_PIXELS_PER_IMAGE=points),
-            "grounding": dict(MASKDEC_SELF_ATTN_MASK_TYPE="sep-blocked", TEXT_PROMPT_TO_IMAGE_ENABLE=True),
-            "detection": dict(TEXT_PROMPT_TO_IMAGE_ENABLE=False)}[task]
-    cfg = make_cfg(variant, Q, T, clip_emb=clip_emb, **over)
+    V = T + clips - 1
+    src = ClipSource(task, T, V, H, W)
+    cfg = make_cfg(variant, Q, T, clip_emb=src.clip_emb, **univs_overrides(task, points))
     cpu_model = build_model(cfg)
     gpu_model = None
     if not dry:
@@ -95,37 +72,8 @@ def run_config(name, T=None, clips=None, precision="fp16x3", variant=None, hw=No
         gpu_model.load_state_dict(cpu_model.state_dict())
     old_threads = torch.get_num_threads()
     torch.set_num_threads(threads or min(32, os.cpu_count() or 1))
-    V = T + clips - 1
-    frames = torch.rand(V, 3, H, W, generator=g) * 255
-    Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
-    P = {"sot": 10, "grounding": 32, "detection": 0}[task]
-
-    def targets(dev):
-        tg = {"task": task, "dataset_name": {"sot": "davis", "grounding": "refytvos", "detection": "ytvis21"}[task],
-              "prompt_type": "text" if task == "grounding" else "visual"}
-        if task == "sot":
-            tg["ids"] = torch.arange(P, device=dev)
-            tg["first_appear_frame_idxs"] = torch.zeros(P, dtype=torch.long, device=dev)
-        if task == "grounding":
-            gg = torch.Generator().manual_seed(2)
-            tg["exp_word_feats"] = torch.randn(P, 77, T, 640, generator=gg).to(dev)
-            tg["exp_sentence_feats"] = torch.randn(P, T, 640, generator=gg).to(dev)
-            tg["exp_word_len"] = torch.full((P,), 12, dtype=torch.long, device=dev)
-        return [tg]
-
-    masks = boxes = None
-    if task == "sot":
-        masks, boxes = rectangle_masks(P, V, Hp, Wp)
-        masks[:, 1:] = 0                 # only the first frame is annotated; the memory carries the objects afterwards
-        boxes[:, 1:] = 0
-
-    def clip_inputs(tg, c, dev):
-        tg[0]["first_frame_idx"] = c
-        tg[0]["frame_indices"] = torch.arange(c, c + T, device=dev)
-        if task == "sot":
-            tg[0]["masks"] = masks[:, : c + T].clone().to(dev)
-            tg[0]["boxes"] = boxes[:, : c + T].clone().to(dev)
-        return frames[c: c + T].to(dev)
+    P = src.P
+    targets, clip_inputs = src.targets, src.clip_inputs
 
     res = {"config": name, "geometry": f"Swin-{variant} T={T} {H}x{W} Q={Q} P={P} task={task} clips={clips}",
            "precision": precision, "tolerance": TOL, "tolerance_metric": "max|a-b|/max|b| per tensor", "clips": []}

@@ -59,6 +59,8 @@ def _fake_cuda(monkeypatch):
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     monkeypatch.setitem(bench.WORKLOADS, "dry", ("tiny", 2, 64, 96, 8))
+    monkeypatch.setitem(bench.PROMPT_WORKLOADS, "dry_sot", ("tiny", 2, 64, 96, 8, "sot", 1))
+    monkeypatch.setitem(bench.PROMPT_WORKLOADS, "dry_grounding", ("tiny", 2, 64, 96, 8, "grounding", 0))
     with oracle_ops():
         yield
 
@@ -107,6 +109,8 @@ def test_plain_cpu_run_fails_loudly(monkeypatch):
     monkeypatch.setenv("UNIVS_BENCH_DEVICE", "cpu")
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     monkeypatch.setitem(bench.WORKLOADS, "dry", ("tiny", 2, 64, 96, 8))
+    monkeypatch.setitem(bench.PROMPT_WORKLOADS, "dry_sot", ("tiny", 2, 64, 96, 8, "sot", 1))
+    monkeypatch.setitem(bench.PROMPT_WORKLOADS, "dry_grounding", ("tiny", 2, 64, 96, 8, "grounding", 0))
     with pytest.raises(UnivsB200Error):
         bench.main()
 
@@ -150,3 +154,16 @@ def test_frame_sharded_run_control_flow_over_gloo(tmp_path):
     assert line["config"]["parallelism"].startswith("frame-shard x2") and line["config"]["execution"] == "eager"
     assert line["cpu_baseline"] is None                    # measured at N = 1 only
     assert line["e2e"]["value"] > 0
+
+
+@pytest.mark.parametrize("workload", ["dry_sot", "dry_grounding"])
+def test_prompt_workload_control_flow(monkeypatch, workload):
+    """BASELINE configs[2] / configs[3] (visual prompts with a grown memory pool, text prompts + lang->vision)"""
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", workload, "--steps", "1", "--warmup", "1", "--precision", "fp32"])
+    # the parser's choices were fixed at import: let it see the dry workloads
+    line = _run(monkeypatch, ["--workload", workload, "--steps", "1", "--warmup", "1", "--precision", "fp32"])
+    for k in CONTRACT:
+        assert k in line, k
+    assert line["value"] > 0 and line["config"]["execution"] == "eager" and workload in line["config"]["workload"]
+    assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 2 * 3 * 64 * 96
+    assert ("P=10" if workload == "dry_sot" else "P=32") in line["config"]["workload"]

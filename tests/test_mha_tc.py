@@ -190,3 +190,29 @@ def test_mha_tc(B, Lq, Lk, C, masked, flags):
     assert _rel(got, want) < 2e-5
     ref = ops.mha_core(q.cuda(), k.cuda(), v.cuda(), bits, row_open, precision=0)
     assert _rel(got, ref) < 2e-5
+
+
+@_gpu_mhatc
+@pytest.mark.parametrize("Lq,masked", [(1000, False), (1000, True), (1160, True), (300, True)])
+def test_self_attention_shape_through_query_chunks(Lq, masked, monkeypatch):
+    """the decoder's Q*T self-attention (one batch element, Lq = Q*T query tokens = keys, transformer_layers.py:34-44) on
+    the tcgen05 kernel: ops.mha_core cuts the queries into <= 256-row chunks that become its batch dimension"""
+    from univs_b200 import ops
+    monkeypatch.setattr(ops, "_mha_tc", 1)
+    torch.manual_seed(Lq)
+    C = 256
+    q, k, v = torch.randn(1, Lq, C), torch.randn(1, Lq, C), torch.randn(1, Lq, C)
+    mask = bits = row_open = None
+    if masked:
+        mask = torch.rand(1, Lq, Lq) < 0.6
+        mask[:, 3] = True
+        bits = ops.pack_mask_bits(mask).cuda()
+        row_open = (~mask.all(-1)).to(torch.int32).cuda()
+    want = ops_ref.mha_core(q, k, v, 8, None if mask is None else mask.to(torch.uint8), unmask_full_rows=masked)
+    calls = []
+    real = ops.mha_core_tc
+    monkeypatch.setattr(ops, "mha_core_tc", lambda *a, **kw: (calls.append(a[0].shape), real(*a, **kw))[1])
+    got = ops.mha_core(q.cuda(), k.cuda(), v.cuda(), bits, row_open)
+    torch.cuda.synchronize()
+    assert len(calls) == 1 and calls[0][1] <= 256 and calls[0][0] * calls[0][1] >= Lq
+    assert _rel(got, want) < 2e-5

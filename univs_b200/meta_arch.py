@@ -19,6 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import nn_ops, ops, switches
+from . import precision  # noqa: F401  (applies the documented default policy at import)
 from .registry import META_ARCH_REGISTRY, build_backbone, build_sem_seg_head
 from .sharding import FrameSharder, TokenExchange
 
@@ -241,7 +242,18 @@ class UniVS_Prompt(nn.Module):
         name = batched_inputs[0]["dataset_name"]
         if name.startswith("coco") or name.startswith("ade20k"):
             return h["image"].eval(self, batched_inputs)                # image vocabularies
-        if batched_inputs[0].get("task") in ("grounding", "sot") or len(h["custom_videos_text"]):
+        if len(h["custom_videos_text"]) and batched_inputs[0].get("task") not in ("grounding", "sot"):
+            # custom-text route (univs_prompt.py:431-433 + prepare_targets.py:66-71): the video becomes a grounding video whose
+            # expressions are the configured texts.  The reference encodes them with its CLIP text tower at this point; that
+            # tower is outside this build, so the caller supplies the features.
+            texts = list(h["custom_videos_text"][0])
+            missing = [k for k in ("exp_word_feats", "exp_sentence_feats", "exp_word_len") if k not in batched_inputs[0]]
+            if missing:
+                raise NotImplementedError(
+                    "CUSTOM_VIDEOS_TEXT: the expressions must come with their CLIP text features "
+                    f"({', '.join(missing)} missing from the input dict): the CLIP text tower is not part of this build")
+            batched_inputs = [dict(batched_inputs[0], task="grounding", expressions=texts, exp_obj_ids=list(range(len(texts))))]
+        if batched_inputs[0].get("task") in ("grounding", "sot"):
             return h["vos"].eval(self, batched_inputs)                  # prompt-specified tasks
         if h["unified"] or h["custom_videos"]:                          # category-specified tasks, unified entity inference
             if name.startswith(("ytvis", "ovis", "vipseg", "vspw")) or h["custom_videos"]:

@@ -240,12 +240,18 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
 
     # ------------------------------------------------------------------ helpers
     def _clip_normalized(self, device):
-        c = self._clip_norm_cache
-        if c is None or c.device != device:
+        # keyed on the table's identity and version: `clip_cls_text_emb` is a plain attribute that callers may replace
+        # (another vocabulary file) or edit in place after the first forward
+        if self.clip_cls_text_emb.device != device:
             self.clip_cls_text_emb = self.clip_cls_text_emb.to(device)
-            c = F.normalize(self.clip_cls_text_emb.float(), p=2, dim=-1)
+        t = self.clip_cls_text_emb
+        key = (t.data_ptr(), t._version, tuple(t.shape), str(device))
+        c = self._clip_norm_cache
+        if c is None or c[0] != key or c[2]() is not t:
+            import weakref
+            c = (key, F.normalize(t.float(), p=2, dim=-1), weakref.ref(t))
             self._clip_norm_cache = c
-        return c
+        return c[1]
 
     def _self_attn_mask_bits(self, t, n_lp, device, task):
         """generate_self_attn_mask (:824-848) over tokens ordered (q*T + t); returns packed bits or None when

@@ -350,7 +350,7 @@ def padded_operand_buffer(N, H, W, C, pad, device):
     """Zeroed [N, H+2p, W+2p, width] buffer in the operand format of the active policy, cached per shape: producers
     only ever write its interior, so the zero border survives from call to call (and across CUDA-graph replays)."""
     _code, mult, dt = ops._split_code(_fmt(), C)
-    key = (N, H, W, C, pad, str(device), dt, ops.scratch_slot)   # per frame group: groups may run concurrently
+    key = (N, H, W, C, pad, mult, str(device), dt, ops.scratch_slot)   # per frame group: groups may run concurrently
     buf = _pad_cache.get(key)
     if buf is None:
         buf = torch.zeros((N, H + 2 * pad, W + 2 * pad, mult * C), device=device, dtype=dt)

@@ -358,6 +358,22 @@ def mha_core(q, k, v, mask_bits=None, row_open=None, precision=None):
     if (_mha_tc and Lq <= 256 and Lk >= MHA_TC_MIN_KEYS
             and (_default_precision if precision is None else precision) == PREC_TF32X3):
         return mha_core_tc(q, k, v, mask_bits, row_open)
+    if (_mha_tc and B == 1 and Lq > 256 and Lk >= MHA_TC_MIN_KEYS and (mask_bits is None or mask_bits.shape[0] == 1)
+            and (_default_precision if precision is None else precision) == PREC_TF32X3):
+        # the Q*T self-attention of the decoder (one batch element, ~1000 query tokens, transformer_layers.py:34-44): the
+        # tcgen05 kernel takes <= 256 query rows per batch element, so the queries are cut into equal chunks that become the
+        # batch dimension (keys / values repeated: ~1 MB each); padding rows attend everywhere and are dropped
+        n = -(-Lq // 256)
+        chunk = -(-Lq // n)
+        pad = n * chunk - Lq
+        qq = (torch.nn.functional.pad(q, (0, 0, 0, pad)) if pad else q).reshape(n, chunk, Cc)
+        kk, vv = k.expand(n, Lk, Cc).contiguous(), v.expand(n, Lk, Cc).contiguous()
+        mb = ro = None
+        if mask_bits is not None:
+            mb = (torch.nn.functional.pad(mask_bits, (0, 0, 0, pad)) if pad else mask_bits).reshape(n, chunk, -1).contiguous()
+            if row_open is not None:
+                ro = (torch.nn.functional.pad(row_open, (0, pad), value=1) if pad else row_open).reshape(n, chunk).contiguous()
+        return mha_core_tc(qq.contiguous(), kk, vv, mb, ro).reshape(1, n * chunk, Cc)[:, :Lq].contiguous()
     out = torch.empty_like(q)
     nbytes = lib().univs_mha_workspace_bytes(B, Lq, Lk, Cc)
     ws = _workspace(nbytes, q.device)
