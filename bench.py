@@ -197,7 +197,7 @@ def run_prompt_workload(args, dev):
     from univs_b200.build import build_model, make_cfg
     from univs_b200.synthetic import ClipSource, clone_targets, univs_overrides
     variant, T, H, W, Q, task, grow = PROMPT_WORKLOADS[args.workload]
-    src = ClipSource(task, T, T + grow, H, W)
+    src = ClipSource(task, T, T + grow, H, W, annotate_all=True)    # later frames: masks fed back by the task head
     cfg = make_cfg(variant, Q, T, clip_emb=src.clip_emb, **univs_overrides(task))
     model = build_model(cfg).to(dev)
     tg = src.targets(dev)

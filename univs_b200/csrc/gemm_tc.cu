@@ -65,9 +65,31 @@ struct Args {
   int act;                     // 0 none, 1 GELU (erf), 2 ReLU
 };
 
+// erf(z) in one branch-free form:  erf(|z|) = 1 - exp(-|z| * q(|z|)),  q = degree-7 polynomial fitted to -ln(erfc(t)) / t on
+// [0, 4] (weighted for the absolute error of erf; beyond 4 erf rounds to 1).  Max absolute error 1.3e-7 (2 ulp of 1, the
+// same class as erff) at about a third of erff's instruction count -- erff evaluates two polynomial branches and merges them
+// with selects, ~35 instructions per element in an epilogue whose issue slots bound the kernel (ncu, round 2).  The result
+// for negative z is built as 1 + erf = exp(...) directly, so GELU keeps its relative accuracy in the negative tail.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float t = fminf(fabsf(z), 4.0f);
+  float q = 3.1440224120160565e-05f;
+  q = fmaf(q, t, -0.00030880147824063897f);
+  q = fmaf(q, t, 0.001032395986840129f);
+  q = fmaf(q, t, 0.0005369476275518537f);
+  q = fmaf(q, t, -0.01958397589623928f);
+  q = fmaf(q, t, 0.10291962325572968f);
+  q = fmaf(q, t, 0.636597752571106f);
+  q = fmaf(q, t, 1.128380298614502f);
+  const float e = ex2_approx(q * t * -1.4426950408889634f);      // exp(-t q(t)) = erfc(t)
+  // 1 + erf(z):  z >= 0 -> 2 - e ;  z < 0 -> e
+  const float one_plus_erf = z >= 0.f ? 2.f - e : e;
+  return 0.5f * x * one_plus_erf;
+}
+
 template <int ACT>
 __device__ __forceinline__ float activate(float v) {
-  if (ACT == 1) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (ACT == 1) return gelu_erf(v);
   if (ACT == 2) return fmaxf(v, 0.f);
   return v;
 }
@@ -81,7 +103,9 @@ __device__ __forceinline__ uint32_t pack_sat_half2(float a, float b) {
 // written as fp32 (one 128-byte line per token and warp) and / or as the fp16 [hi | lo'] operand.  The variant is fixed at
 // compile time: the first version took `act` and the nullable pointers at run time, and its per-element branches and
 // argument reloads made the epilogue several times longer than the main loop (ncu: instruction-fetch and dependency stalls).
-// FULL = all 32 tokens valid and every lane's channel valid: no predicates at all.
+// FULL = all 32 tokens of the chunk valid (every chunk but those of the last token tile): the only predicate left is the
+// per-lane channel validity `n_ok`, one branch around each load / store loop.  (Per-element predicates -- the first form
+// of the partial-channel-tile path -- cost 5x: N = 192 and 576 have a partial last channel tile in EVERY token tile.)
 template <int ACT, bool OUT32, bool OUT16, bool ADD, bool FULL>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const uint32_t (&rc)[32], const Args& a, float bias, int n,
                                                bool n_ok, int t0, int nt, int lane) {
@@ -91,19 +115,19 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const u
     const float s = fmaf(__uint_as_float(rc[j]), 1.f / 2048.f, __uint_as_float(rm[j]));
     v[j] = activate<ACT>(fmaf(s, a.alpha, bias));
   }
-  if (ADD) {
+  if (ADD && n_ok) {
     const float* ap = a.addend + (size_t)t0 * a.ldadd + n;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      if (FULL || (n_ok && j < nt)) v[j] += __ldg(ap);
+      if (FULL || j < nt) v[j] += __ldg(ap);
       ap += a.ldadd;
     }
   }
-  if (OUT32) {
+  if (OUT32 && n_ok) {
     float* op = a.out + (size_t)t0 * a.ldo + n;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      if (FULL || (n_ok && j < nt)) *op = v[j];
+      if (FULL || j < nt) *op = v[j];
       op += a.ldo;
     }
   }
@@ -126,7 +150,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const u
       const float2 hf = __half22float2(h);
       const uint32_t lo = pack_sat_half2((c0 - hf.x) * 2048.f, (c1 - hf.y) * 2048.f);
       const int tok = j + (odd ? 1 : 0);
-      if (FULL || (tok < nt && pair_ok)) {
+      if (pair_ok && (FULL || tok < nt)) {
         *reinterpret_cast<__half2*>(hp) = h;
         *reinterpret_cast<uint32_t*>(hp + a.lo_off16) = lo;
       } else if (tok < nt) {
@@ -244,8 +268,6 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
       const int tt = tile / n_ct, ct = tile - tt * n_ct;
       const int n = ct * kBM + wq * 32 + lane;              // this thread's output channel
       const bool n_ok = n < a.N;
-      // every lane of every warp has a valid channel (and the packed operand stores are aligned)
-      const bool tile_full = (ct + 1) * kBM <= a.N && (!OUT16 || ((a.N | a.lo_off16 | a.ld16) & 1) == 0);
       const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
       mbar_wait(&tfull[acc], acc_phase, 40 + acc);
       fence_after();
@@ -263,8 +285,8 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
         }
         const int t0 = tt * kBT + half * 64 + cb * 32;      // first token of this chunk
         const int nt = a.M - t0 < 32 ? a.M - t0 : 32;       // valid tokens (<= 0: none)
-        if (nt == 32 && tile_full) {
-          epilogue_chunk<ACT, OUT32, OUT16, ADD, true>(rm, rc, a, bias, n, true, t0, 32, lane);
+        if (nt == 32) {
+          epilogue_chunk<ACT, OUT32, OUT16, ADD, true>(rm, rc, a, bias, n, n_ok, t0, 32, lane);
         } else if (nt > 0) {
           epilogue_chunk<ACT, OUT32, OUT16, ADD, false>(rm, rc, a, bias, n, n_ok, t0, nt, lane);
         }

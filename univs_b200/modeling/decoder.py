@@ -100,8 +100,7 @@ class _FFNLayer(nn.Module):               # transformer_layers.py:151-191 (post-
         nn.init.xavier_uniform_(self.linear2.weight)
 
     def forward(self, x):
-        f = nn_ops.linear(x, self.linear1.weight, None)
-        z = nn_ops.linear_prepped(nn_ops.relu(f, bias=self.linear1.bias), self.linear2.weight, None)
+        z = nn_ops.linear_prepped(nn_ops.linear_act_operand(nn_ops.prep(x), self.linear1), self.linear2.weight, None)
         return nn_ops.layernorm(x, self.norm, residual=z, for_gemm=False, residual_bias=self.linear2.bias)[1]
 
 
@@ -114,10 +113,10 @@ class _MLP(nn.Module):                    # transformer_layers.py:205-217
     def forward(self, x, prepped=False):
         h = x if prepped else nn_ops.prep(x)
         for i, l in enumerate(self.layers):
-            last = i == len(self.layers) - 1
-            y = nn_ops.linear_prepped(h, l.weight, l.bias if last else None)
-            if not last:
-                h = nn_ops.relu(y, bias=l.bias)
+            if i < len(self.layers) - 1:
+                h = nn_ops.linear_act_operand(h, l)
+            else:
+                y = nn_ops.linear_prepped(h, l.weight, l.bias)
         return y
 
 

@@ -85,8 +85,7 @@ class _EncoderLayer(nn.Module):
                                            split=nn_ops._fmt() if nn_ops.splitting() else None)
             o = nn_ops.linear_prepped(y, a.output_proj.weight, None)
             src, h1, _ = nn_ops.layernorm_multi(src, self.norm1, residual=o, residual_bias=a.output_proj.bias)
-            f = nn_ops.linear_prepped(h1, self.linear1.weight, None)
-            z = nn_ops.linear_prepped(nn_ops.relu(f, bias=self.linear1.bias), self.linear2.weight, None)
+            z = nn_ops.linear_prepped(nn_ops.linear_act_operand(h1, self.linear1), self.linear2.weight, None)
             src, h2, hq2 = nn_ops.layernorm_multi(src, self.norm2, residual=z, residual_bias=self.linear2.bias,
                                                   pos=pos if emit_next else None, want_operand=emit_next)
             return src, ((h2, hq2) if emit_next else None)
@@ -95,8 +94,7 @@ class _EncoderLayer(nn.Module):
         y = ops.ms_deform_attn_encoder(value, shapes, starts, offs_logits, a.n_levels, a.n_points)
         o = nn_ops.linear(y, a.output_proj.weight, None)
         src = nn_ops.layernorm(src, self.norm1, residual=o, for_gemm=False, residual_bias=a.output_proj.bias)[1]
-        f = nn_ops.linear(src, self.linear1.weight, None)
-        z = nn_ops.linear_prepped(nn_ops.relu(f, bias=self.linear1.bias), self.linear2.weight, None)
+        z = nn_ops.linear_prepped(nn_ops.linear_act_operand(nn_ops.prep(src), self.linear1), self.linear2.weight, None)
         return nn_ops.layernorm(src, self.norm2, residual=z, for_gemm=False, residual_bias=self.linear2.bias)[1], None
 
 

@@ -47,68 +47,86 @@ def box_to_mask(boxes: torch.Tensor, h: int, w: int) -> torch.Tensor:
     return (gx > x1[:, None, None]) & (gx <= x2[:, None, None]) & (gy > y1[:, None, None]) & (gy <= y2[:, None, None])
 
 
-def _select_points(masks, boxes, mask_thresh=0.75):
-    """one point per instance, preferring the centre quarter of the box inside the mask (:361-442, inference)."""
+_coords_cache = {}
+
+
+def _pixel_centres(h, w, dev):
+    """normalised (x, y) pixel centres [h*w, 2], cached per size and device"""
+    key = (h, w, str(dev))
+    c = _coords_cache.get(key)
+    if c is None:
+        ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        c = ((torch.stack([xs, ys], -1) + 0.5) / torch.as_tensor([w, h]).view(1, 1, -1)).flatten(0, 1).to(dev)
+        _coords_cache[key] = c
+    return c
+
+
+def _kth_true(sel, ranks):
+    """index of the ranks[i, j]-th (0-based, row-major) True of row i of `sel` [Q, n] -- what `nonzero(sel[i])[rank]` picks"""
+    cs = sel.to(torch.int32).cumsum(1)
+    return torch.searchsorted(cs, (ranks + 1).to(torch.int32), right=False).clamp(max=sel.shape[1] - 1)
+
+
+def _point_candidates(masks, boxes, mask_thresh=0.75):
+    """select_points_from_box_mask, inference branch (:361-442), device part: per instance the candidate pixels -- the
+    centre quarter of the box inside the mask, or (none there) the pixels at >= min(0.95, max) of the mask."""
     Q, h, w = masks.shape
-    dev = masks.device
-    masks = masks.float()
-    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
-    coords = ((torch.stack([xs, ys], -1) + 0.5) / torch.as_tensor([w, h]).view(1, 1, -1)).flatten(0, 1).to(dev)
+    mf = masks.float().flatten(1)
+    coords = _pixel_centres(h, w, masks.device)
     cxcy = 0.5 * (boxes[:, :2] + boxes[:, 2:])
     wh = boxes[:, 2:] - boxes[:, :2]
-    thr = masks.flatten(1).max(1)[0].clamp(max=mask_thresh).reshape(-1, 1)
-    binary = masks.flatten(1) >= thr
+    mmax = mf.max(1)[0]
+    binary = mf >= mmax.clamp(max=mask_thresh).reshape(-1, 1)
     in_ctr = ((coords[None] - cxcy[:, None]).abs() < 0.25 * wh[:, None]).all(-1) & binary
-    pts = []
-    for i in range(Q):
-        sel = in_ctr[i]
-        if not bool(sel.any()):
-            sel = masks[i].flatten() >= min(0.95, float(masks[i].max()))
-        idx = torch.randperm(int(sel.sum()))[:1]            # CPU generator, as in the reference
-        pts.append(coords[sel][idx.to(dev)])
-    pts = torch.stack(pts)[:, 0]                              # [Q,2]
-    assert bool((pts <= 1).all()), "Point coordinates should be smaller than 1"
-    return pts
+    fallback = mf >= mmax.clamp(max=0.95).reshape(-1, 1)
+    sel = torch.where(in_ctr.any(1, keepdim=True), in_ctr, fallback)
+    return sel, coords
 
 
 def _mask_prompt(sampler, feat, pe, masks, boxes, key_fid, key_fid_original, T, h, w):
-    """get_mask_prompt (:167-263) for one key frame.  feat/pe: [hw, C] tokens of the 1/8 level."""
+    """get_mask_prompt (:167-263) for one key frame.  feat/pe: [hw, C] tokens of the 1/8 level.
+
+    The reference walks the instances in Python (select_points_from_box_mask :361-442, get_dense_features :444-497): a
+    `.any()` / `.max()` / `nonzero` host synchronisation and a handful of small device ops per instance.  Here the device
+    side is vectorised over the instances and ONE device->host read per key frame brings back the candidate counts; the
+    random picks stay `torch.randperm(n)` on the CPU generator, per instance and in the reference's order (points first,
+    then dense features), so a seeded run reproduces the reference's choices; the picks go back as one index tensor."""
     dev = feat.device
     R, s = sampler.num_dense_points, sampler.img_feats_scale
     Q, hm, wm = masks.shape
     if (h * s, w * s) != (hm, wm):
         raise AssertionError(f"Input images must have same size with masks: {(hm, wm), (h * s, w * s)}")
     valid = masks.gt(0.5).flatten(1).sum(-1) > 0
-    pts = _select_points(masks, boxes)
+    sel, coords = _point_candidates(masks, boxes)
+    fm = F.interpolate(masks.float().unsqueeze(1), (h, w), mode="nearest").squeeze(1)          # [Q,h,w]
+    fm_bin = fm >= fm.max().clamp(max=0.5)
+    fmb = fm_bin.flatten(1)
+    counts = torch.stack([sel.sum(1), fmb.sum(1)]).cpu()                                       # the one host sync
+    n_sel, n_dense = counts[0].tolist(), counts[1].tolist()
+    pick = torch.tensor([int(torch.randperm(n)[:1]) for n in n_sel], dtype=torch.long)          # CPU generator (:420-425)
+    ranks = torch.zeros((Q, R), dtype=torch.long)
+    for i, n in enumerate(n_dense):                                                             # get_dense_features (:470-492)
+        if n == 0:
+            continue
+        ranks[i] = torch.arange(R) % n if n < R else torch.randperm(n)[:R]
+    pts = coords[_kth_true(sel, pick.to(dev).view(-1, 1))[:, 0]]                                # [Q,2]
     t_idx = torch.as_tensor(key_fid_original, device=dev).reshape(-1)[:1].repeat(T)
     q_pe = position.sine_3d_points(pts, t_idx, dev, feat.shape[-1] // 2).transpose(0, 1)        # [Q,T,C]
-    fm = F.interpolate(masks.float().unsqueeze(1), (h, w), mode="nearest").squeeze(1)          # [Q,h,w]
-    fm_bin = fm >= min(0.5, float(fm.max()))
     wgt = (fm * fm_bin).flatten(1)
     with nn_ops.ieee_fp32():
         key_feat = (wgt @ feat) / wgt.sum(-1).clamp(min=0.5)[:, None]                           # [Q,C]
     q_feat = key_feat[:, None].repeat(1, T, 1)
     attn = torch.zeros((T, 1, Q, h * w), dtype=torch.bool, device=dev)
     attn[key_fid, 0] = ~box_to_mask(boxes, h, w).flatten(-2)
-    dense_f, dense_p = [], []
-    for i in range(Q):                                          # get_dense_features (:444-497)
-        idx = torch.nonzero(fm_bin[i].flatten()).reshape(-1)
-        if len(idx) == 0:
-            dense_f.append(q_feat[i, 0].reshape(1, -1).repeat(R, 1))
-            dense_p.append(q_pe[i, 0].reshape(1, -1).repeat(R, 1))
-            continue
-        if len(idx) < R:
-            idx = idx.repeat(int(R / len(idx)) + 1)[:R]
-        else:
-            idx = idx[torch.randperm(len(idx))[:R].to(dev)]
-        dense_f.append(feat[idx])
-        dense_p.append(pe[idx])
-    dense_f = torch.stack(dense_f)[:, :, None].repeat(1, 1, T, 1)                              # [Q,R,T,C]
-    dense_p = torch.stack(dense_p)[:, :, None].repeat(1, 1, T, 1)
-    if bool((~valid).any()):
-        v = valid.view(-1, 1, 1, 1).float()
-        dense_p, dense_f = dense_p * v, dense_f * v
-        attn[:, :, ~valid] = False
+    idx = _kth_true(fmb, ranks.to(dev))                                                         # [Q,R] token indices
+    empty = (torch.tensor(n_dense) == 0).to(dev).view(-1, 1, 1)
+    dense_f = torch.where(empty, q_feat[:, :1].expand(-1, R, -1), feat[idx])                    # no mask pixel: the query itself
+    dense_p = torch.where(empty, q_pe[:, :1].expand(-1, R, -1), pe[idx])
+    dense_f = dense_f[:, :, None].repeat(1, 1, T, 1)                                            # [Q,R,T,C]
+    dense_p = dense_p[:, :, None].repeat(1, 1, T, 1)
+    v = valid.view(-1, 1, 1, 1)                                                                 # blank instances: zero prompt,
+    dense_p, dense_f = dense_p * v.to(dense_p.dtype), dense_f * v.to(dense_f.dtype)             # nothing blocked (:255-262)
+    attn = attn & valid.view(1, 1, -1, 1)
     return dense_p, dense_f, attn
 
 

@@ -310,6 +310,19 @@ def linear_residual(h, weight, bias, residual):
     return residual
 
 
+def linear_act_operand(h, lin, act="relu"):
+    """act(lin(h)) emitted as the next layer's GEMM operand.  Own GEMM: one kernel (bias + activation + operand emission in the
+    epilogue, no fp32 intermediate); otherwise the library GEMM followed by the row-wise activation kernel."""
+    K = lin.in_features
+    if gemm_tc() and K % 8 == 0 and K <= 1536:
+        b3, alpha = _split_weight(lin.weight)
+        y16 = _tc_linear(h.reshape(-1, h.shape[-1]), K, b3, alpha, lin.bias, act=ops.ACT_GELU if act == "gelu" else ops.ACT_RELU,
+                         want_f32=False, want_operand=True)[1]
+        return y16.view(*h.shape[:-1], y16.shape[-1])
+    f = linear_prepped(h, lin.weight, None)
+    return gelu(f, bias=lin.bias) if act == "gelu" else relu(f, bias=lin.bias)
+
+
 def mlp(h, fc1, fc2, residual=None):
     """fc2(GELU(fc1(h) + b1)) without b2 (deferred into the consumer, like everywhere on this path); h is the operand of fc1.
     With `residual` (own GEMM only): residual + fc2(...) + b2, written over `residual`."""

@@ -36,7 +36,9 @@ def rectangle_masks(P, frames, H, W, seed=1):
 class ClipSource:
     """Frames, targets and per-clip annotations of one synthetic video of `task` at padded size (Hp, Wp)."""
 
-    def __init__(self, task, T, V, H, W, seed_frames=0):
+    def __init__(self, task, T, V, H, W, seed_frames=0, annotate_all=False):
+        """annotate_all (sot): every frame carries the (drifting) object masks, as when a task head feeds the previous
+        clip's predictions back as pseudo annotations; default: only frame 0 is annotated and the memory carries the objects"""
         self.task, self.T, self.V, self.H, self.W = task, T, V, H, W
         self.Hp, self.Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
         self.P = PROMPTS[task]
@@ -46,8 +48,9 @@ class ClipSource:
         self.masks = self.boxes = None
         if task == "sot":
             self.masks, self.boxes = rectangle_masks(self.P, V, self.Hp, self.Wp)
-            self.masks[:, 1:] = 0            # only the first frame is annotated; the memory carries the objects afterwards
-            self.boxes[:, 1:] = 0
+            if not annotate_all:
+                self.masks[:, 1:] = 0        # only the first frame is annotated; the memory carries the objects afterwards
+                self.boxes[:, 1:] = 0
 
     def targets(self, dev):
         task, P, T = self.task, self.P, self.T
