@@ -1,0 +1,16 @@
+#!/usr/bin/env bash
+set -u
+out=gpurun_out/r2_call9
+mkdir -p "$out"
+run() { local name=$1 secs=$2; shift 2
+  echo "=== $name: $*" | tee -a "$out/summary.txt"
+  ( time timeout "$secs" "$@" ) > "$out/$name.log" 2>&1
+  echo "    exit $? ($(grep -o '"ms_per_step": [0-9.]*' "$out/$name.log" | head -2 | tr '\n' ' ') $(tail -n 3 "$out/$name.log" | tr '\n' ' ' | cut -c1-200))" | tee -a "$out/summary.txt"; }
+run shapes 600 python tools/gemm_tc_shapes.py
+run gemm_tests 600 python -m pytest tests/test_gemm_tc_gpu.py -m gpu -q
+run bench_ns 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+NCU="ncu --clock-control none"
+timeout 900 $NCU --metrics gpu__time_duration.sum --profile-from-start off --csv --log-file "$out/launches.csv" \
+    python bench.py --ncu-step --no-cpu-baseline > "$out/launches.log" 2>&1
+python tools/summarize_launches.py "$out/launches.csv" 30 > "$out/launches_summary.txt" 2>&1
+cat "$out/summary.txt"

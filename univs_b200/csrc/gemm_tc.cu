@@ -23,7 +23,7 @@
 // bias[n] is a per-thread scalar.
 //
 // Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer (3-stage ring of {Wh, Wl', Xh, Xl'} = 64 KB),
-// warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-11 = epilogue (two per TMEM lane quarter, 64
+// warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-19 = epilogue (four per TMEM lane quarter, 32
 // token columns each).  Two TMEM stages of {main, corr} (4 x 128 columns): the epilogue of tile i -- which for the GELU
 // variant is as long as the main loop -- overlaps the MMAs of tile i+1.  Tiles are ordered channel-tile fastest, so
 // concurrently running CTAs share activation tiles in L2; weights stay L2-resident.
@@ -46,7 +46,9 @@ constexpr int kBK = 64;                  // halfs per operand row in shared memo
 constexpr int kStages = 3;
 constexpr int kTileBytes = 128 * 128;    // one operand tile: 128 rows x 128 bytes
 constexpr int kStageBytes = 4 * kTileBytes;
-constexpr int kThreads = 384;            // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 16;            // four per TMEM lane quarter, 32 token columns each
+constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 control warps + the epilogue warps
+constexpr int kCh = 16;                  // token columns per epilogue chunk (registers: 2 x 16 accumulator values + 16 results)
 constexpr int kOffBars = kStages * kStageBytes;
 constexpr int kNumBars = 2 * kStages + 4;
 constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
@@ -107,18 +109,18 @@ __device__ __forceinline__ uint32_t pack_sat_half2(float a, float b) {
 // per-lane channel validity `n_ok`, one branch around each load / store loop.  (Per-element predicates -- the first form
 // of the partial-channel-tile path -- cost 5x: N = 192 and 576 have a partial last channel tile in EVERY token tile.)
 template <int ACT, bool OUT32, bool OUT16, bool ADD, bool FULL>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const uint32_t (&rc)[32], const Args& a, float bias, int n,
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[kCh], const uint32_t (&rc)[kCh], const Args& a, float bias, int n,
                                                bool n_ok, int t0, int nt, int lane) {
-  float v[32];
+  float v[kCh];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < kCh; ++j) {
     const float s = fmaf(__uint_as_float(rc[j]), 1.f / 2048.f, __uint_as_float(rm[j]));
     v[j] = activate<ACT>(fmaf(s, a.alpha, bias));
   }
   if (ADD && n_ok) {
     const float* ap = a.addend + (size_t)t0 * a.ldadd + n;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < kCh; ++j) {
       if (FULL || j < nt) v[j] += __ldg(ap);
       ap += a.ldadd;
     }
@@ -126,7 +128,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const u
   if (OUT32 && n_ok) {
     float* op = a.out + (size_t)t0 * a.ldo + n;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < kCh; ++j) {
       if (FULL || j < nt) *op = v[j];
       op += a.ldo;
     }
@@ -138,11 +140,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const u
     const int ne = n & ~1;                                   // first channel of the pair
     __half* hp = a.out16 + (size_t)(t0 + (odd ? 1 : 0)) * a.ld16 + ne;
     // 4-byte stores need an even channel count, lo offset and row pitch (true for every layer of the path); otherwise the
-    // two channels are stored one by one
+    // two channels are stored one by one.  With an even N a pair is valid or invalid as a whole.
     const bool even = ((a.N | a.lo_off16 | a.ld16) & 1) == 0;
-    const bool pair_ok = even && ne + 1 < a.N;
+    const bool pair_ok = ne + 1 < a.N;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+    for (int j = 0; j < kCh; j += 2) {
       const float mine = odd ? v[j + 1] : v[j];              // my channel, my token
       const float other = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);   // partner's channel, my token
       const float c0 = odd ? other : mine, c1 = odd ? mine : other;   // channels ne, ne + 1
@@ -150,10 +152,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[32], const u
       const float2 hf = __half22float2(h);
       const uint32_t lo = pack_sat_half2((c0 - hf.x) * 2048.f, (c1 - hf.y) * 2048.f);
       const int tok = j + (odd ? 1 : 0);
-      if (pair_ok && (FULL || tok < nt)) {
-        *reinterpret_cast<__half2*>(hp) = h;
-        *reinterpret_cast<uint32_t*>(hp + a.lo_off16) = lo;
-      } else if (tok < nt) {
+      if (even) {
+        if (pair_ok && (FULL || tok < nt)) {
+          *reinterpret_cast<__half2*>(hp) = h;
+          *reinterpret_cast<uint32_t*>(hp + a.lo_off16) = lo;
+        }
+      } else if (FULL || tok < nt) {
         if (ne < a.N) {
           hp[0] = __low2half(h);
           hp[a.lo_off16] = __ushort_as_half((unsigned short)(lo & 0xffffu));
@@ -193,7 +197,7 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);   // one arrive per epilogue warp
+      mbar_init(&tempty[i], kEpiWarps);   // one arrive per epilogue warp
     }
     mbar_init_fence();
   } else if (warp == 2) {
@@ -258,10 +262,12 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> global.  8 warps: two per TMEM lane quarter, 64 token columns each =====
+    // ===== epilogue: TMEM -> registers -> global.  16 warps: four per TMEM lane quarter, 32 token columns each, in two
+    // chunks of 16.  (Eight warps with 64 columns each left the epilogue latency-bound: two warps per scheduler walking
+    // dependent convert / shuffle / store chains; for K = 192 layers the epilogue, not the main loop, set the tile time.) =====
     const int ew = warp - 4;
     const int wq = ew & 3;       // TMEM lane quarter this warp may access (== warp % 4)
-    const int half = ew >> 2;    // token columns [64 * half, 64 * half + 64)
+    const int part = ew >> 2;    // token columns [32 * part, 32 * part + 32)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -271,26 +277,26 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
       const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
       mbar_wait(&tfull[acc], acc_phase, 40 + acc);
       fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * kColsPerStage + (uint32_t)(half * 64);
-#pragma unroll 1
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * kColsPerStage + (uint32_t)(part * 32);
+      uint32_t rm[2][kCh], rc[2][kCh];
+      UNIVS_TMEM_LD_X16(taddr, rm[0]);
+      UNIVS_TMEM_LD_X16(taddr + (uint32_t)kBT, rc[0]);
+      UNIVS_TMEM_LD_X16(taddr + (uint32_t)kCh, rm[1]);
+      UNIVS_TMEM_LD_X16(taddr + (uint32_t)(kBT + kCh), rc[1]);
+      tmem_wait_ld();
+      fence_before();             // this warp's share of the accumulator stage is in registers: release it to the MMA lane
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+#pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
-        uint32_t rm[32], rc[32];
-        UNIVS_TMEM_LD_X32(taddr + (uint32_t)(cb * 32), rm);
-        UNIVS_TMEM_LD_X32(taddr + (uint32_t)(kBT + cb * 32), rc);
-        tmem_wait_ld();
-        if (cb == 1) {            // both chunks are in registers: the MMA lane may overwrite this accumulator stage
-          fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
-        const int t0 = tt * kBT + half * 64 + cb * 32;      // first token of this chunk
-        const int nt = a.M - t0 < 32 ? a.M - t0 : 32;       // valid tokens (<= 0: none)
-        if (nt == 32) {
-          epilogue_chunk<ACT, OUT32, OUT16, ADD, true>(rm, rc, a, bias, n, n_ok, t0, 32, lane);
+        const int t0 = tt * kBT + part * 32 + cb * kCh;     // first token of this chunk
+        const int nt = a.M - t0 < kCh ? a.M - t0 : kCh;     // valid tokens (<= 0: none)
+        if (nt == kCh) {
+          epilogue_chunk<ACT, OUT32, OUT16, ADD, true>(rm[cb], rc[cb], a, bias, n, n_ok, t0, kCh, lane);
         } else if (nt > 0) {
-          epilogue_chunk<ACT, OUT32, OUT16, ADD, false>(rm, rc, a, bias, n, n_ok, t0, nt, lane);
+          epilogue_chunk<ACT, OUT32, OUT16, ADD, false>(rm[cb], rc[cb], a, bias, n, n_ok, t0, nt, lane);
         }
-        __syncwarp();           // the TMEM loads of the next chunk / tile are warp-collective
+        __syncwarp();           // the shuffles / TMEM loads that follow are warp-collective
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
