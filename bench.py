@@ -223,7 +223,9 @@ def run_torch_eager_gpu(args):
                 "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init",
                            "execution": "eager, torch library kernels (port of the reference algorithm)"}}
     except Exception as e:  # noqa: BLE001
-        return {"impl": "torch-eager", "unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+        import traceback
+        where = " <- ".join(f"{fr.filename.split('/')[-1]}:{fr.lineno}" for fr in traceback.extract_tb(e.__traceback__)[-4:])
+        return {"impl": "torch-eager", "unavailable": f"{type(e).__name__}: {str(e)[:300]} [{where}]"}
 
 
 def run_prompt_workload(args, dev):

@@ -289,6 +289,7 @@ inline void tmem_ld(uint32_t taddr, uint32_t* r, int n) {
   const float* T = ::emu::tmem() + (size_t)(lane_field + ::emu::ctx.lane) * 512 + col;
   std::memcpy(r, T, sizeof(float) * n);
 }
+#define UNIVS_TMEM_LD_X4(taddr, r) ::univs::tc::tmem_ld(taddr, r, 4)
 #define UNIVS_TMEM_LD_X8(taddr, r) ::univs::tc::tmem_ld(taddr, r, 8)
 #define UNIVS_TMEM_LD_X16(taddr, r) ::univs::tc::tmem_ld(taddr, r, 16)
 #define UNIVS_TMEM_LD_X32(taddr, r) ::univs::tc::tmem_ld(taddr, r, 32)

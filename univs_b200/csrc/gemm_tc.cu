@@ -11,6 +11,7 @@
 // fp16's subnormal range); the weight tensor is pre-scaled by a per-tensor power of two (alpha undoes it).  hi*hi products
 // are exact in fp32, two correction products restore ~22 bits:
 //   main = Wh Xh^T          corr = Wh Xl'^T + Wl' Xh^T          Y = alpha * (main + corr * 2^-11)
+// (issued as two MMAs per k-step: Wh * [Xh ; Xl']^T with N = 256 into the adjacent {main, corr} columns, then Wl' * Xh^T)
 // with main and corr in SEPARATE TMEM accumulators: the tensor core accumulates with truncation (tools/accum_probe.py), and
 // the correction terms must not be added to an accumulator 2^11 times their size.  Three kind::f16 MMAs per 16-wide k-step
 // read four operand tiles (the single-GEMM formulation of round 1 read six: [lo'|hi_s|hi] x [hi_s|lo'|hi]).
@@ -229,7 +230,13 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // Two MMA instructions per k-step carry the three products: the Xh and Xl' tiles are adjacent in shared memory (256 rows of
+    // one K-major operand), and {main, corr} are adjacent in TMEM, so ONE N = 256 MMA computes Wh * [Xh ; Xl']^T -- the main
+    // term and the first correction term -- reading the Wh tile once; the N = 128 MMA adds Wl' * Xh^T to corr.  Same products
+    // and accumulation order as three N = 128 MMAs, with 20 KB instead of 24 KB of shared-memory operand reads per k-step
+    // (the one-CTA 128 x 128 tile is bound by shared-memory bandwidth, not by the tensor pipe).
     constexpr uint32_t idesc = make_idesc_f16(kBM, kBT, false, false);
+    constexpr uint32_t idesc2 = make_idesc_f16(kBM, 2 * kBT, false, false);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -245,13 +252,12 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
         if (elect_one()) {
           const uint32_t s0 = smem_u32(smem + (size_t)stage * kStageBytes);
           const uint64_t wh = make_desc<128>(s0), wl = make_desc<128>(s0 + kTileBytes);
-          const uint64_t xh = make_desc<128>(s0 + 2 * kTileBytes), xl = make_desc<128>(s0 + 3 * kTileBytes);
+          const uint64_t xh = make_desc<128>(s0 + 2 * kTileBytes);     // rows 0-127: Xh tile, rows 128-255: the Xl' tile behind it
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {   // one k-step = 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
             const uint32_t first = (kb | k) != 0 ? 1u : 0u;
-            umma_f16(d_corr, wh + (uint64_t)(2 * k), xl + (uint64_t)(2 * k), idesc, first);   // Wh  * Xl'
-            umma_f16(d_corr, wl + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc, 1u);      // Wl' * Xh
-            umma_f16(d_main, wh + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc, first);   // Wh  * Xh
+            umma_f16(d_main, wh + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc2, first);  // [main | corr] (+)= Wh * [Xh ; Xl']^T
+            umma_f16(d_corr, wl + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc, 1u);      // corr += Wl' * Xh^T
           }
           umma_commit(&empty[stage]);                       // frees the stage when these MMAs retire
           if (kb == kblocks - 1) umma_commit(&tfull[acc]);  // both accumulators complete -> epilogue

@@ -136,6 +136,10 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
 }
 
 
+#define UNIVS_TMEM_LD_X4(taddr, r)                                                              \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"                     \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])                                 \
+               : "r"(taddr))
 #define UNIVS_TMEM_LD_X8(taddr, r)                                                                              \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                        \
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
