@@ -34,8 +34,8 @@ def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_loc, attn_
     shapes = [(int(h), int(w)) for h, w in spatial_shapes]
     starts = [int(s) for s in level_start_index]
     out = value.new_zeros(N, Lq, M, D)
-    n_idx = torch.arange(N).view(N, 1, 1, 1)
-    m_idx = torch.arange(M).view(1, 1, M, 1)
+    n_idx = torch.arange(N, device=value.device).view(N, 1, 1, 1)
+    m_idx = torch.arange(M, device=value.device).view(1, 1, M, 1)
     for l, (H, W) in enumerate(shapes):
         v = value[:, starts[l]:starts[l] + H * W]                  # [N,HW,M,D]
         x = sampling_loc[:, :, :, l, :, 0] * W - 0.5                # [N,Lq,M,P]
@@ -79,7 +79,7 @@ def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offs_logits, 
     logit = offs_logits[..., n_off:].reshape(N, Len, M, L * P)
     w = torch.softmax(logit, -1).reshape(N, Len, M, L, P)
     ref = encoder_reference_points(spatial_shapes).to(value)            # [Len,2]
-    norm = torch.tensor([[int(w_), int(h_)] for h_, w_ in spatial_shapes], dtype=value.dtype)
+    norm = torch.tensor([[int(w_), int(h_)] for h_, w_ in spatial_shapes], dtype=value.dtype, device=value.device)
     loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
     return ms_deform_attn(value, spatial_shapes, level_start_index, loc, w)
 
@@ -111,14 +111,14 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     q, k, v = win[0] * (d ** -0.5), win[1], win[2]
     attn = q @ k.transpose(-2, -1)                                    # [B,nW,nH,N,N]
     # relative position bias (swin.py:108-121, 148-156)
-    ar = torch.arange(ws)
+    ar = torch.arange(ws, device=qkv.device)
     cy, cx = torch.meshgrid(ar, ar, indexing="ij")
     cy = cy.reshape(-1); cx = cx.reshape(-1)
     idx = (cy[:, None] - cy[None, :] + ws - 1) * (2 * ws - 1) + (cx[:, None] - cx[None, :] + ws - 1)
     bias = rel_bias_table[idx.reshape(-1)].view(ws * ws, ws * ws, num_heads).permute(2, 0, 1)
     attn = attn + bias[None, None]
     if shift > 0:
-        lab = torch.zeros(Hp, Wp)
+        lab = torch.zeros(Hp, Wp, device=qkv.device)
         cnt = 0
         for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
             for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
@@ -295,8 +295,8 @@ def patchify_normalize(frames, pixel_mean, pixel_std, padded_size, patch=4):
     """(x - mean) / std (univs_prompt.py:165-168), zero pad right / bottom (ImageList.from_tensors), then the im2col of
     the stride-`patch` PatchEmbed convolution (swin.py:456-495): [N,3,H,W] -> [N, Hp/p, Wp/p, 3*p*p], column order
     (c, ky, kx) = proj.weight.view(E, -1)."""
-    mean = torch.as_tensor(pixel_mean, dtype=torch.float32).view(1, 3, 1, 1)
-    std = torch.as_tensor(pixel_std, dtype=torch.float32).view(1, 3, 1, 1)
+    mean = torch.as_tensor(pixel_mean, dtype=torch.float32, device=frames.device).view(1, 3, 1, 1)
+    std = torch.as_tensor(pixel_std, dtype=torch.float32, device=frames.device).view(1, 3, 1, 1)
     x = (frames.float() - mean) / std
     N, _, H, W = x.shape
     Hp, Wp = padded_size

@@ -27,6 +27,7 @@ def _emulate_gpu():
     chk = ops._chk
     ops._chk = lambda t, name, dtype=torch.float32: chk(as_dev(t), name, dtype)
     ops._chk_t = lambda t, name, dtype=torch.float32: (chk(as_dev(t), name, dtype), as_dev(t))[1]
+    ops._on_device = lambda t: True
     torch.cuda.is_available = lambda: True
     torch.cuda.synchronize = lambda *a, **k: None
     torch.cuda.set_device = lambda *a, **k: None

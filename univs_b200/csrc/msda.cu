@@ -352,6 +352,126 @@ msda_encoder_tiled_kernel(const float* __restrict__ value, LevelTable lt, TileTa
   msda_encoder_pair<L, P, FUSED>(value, lt, ol, n, lt.start[l] + qy * lt.W[l] + qx, m, lane8, S, M, out, value_bias, ol_bias, split);
 }
 
+// Staged variant of the fused tiled kernel (round 2).  ncu of msda_encoder_tiled_kernel<3,4,true>: issue-bound (SM 69 %), 1890
+// instructions per lane and (query, head) -- of which the gather itself (48 x {address, 128-bit load, 4 FMA}) is ~350: every
+// one of the 8 lanes of a (query, head) group recomputed the whole set-up (36 bias loads, 12 expf, 24 IEEE divisions, 12
+// floor / weight / address computations).  Here the 8 lanes SHARE it: lane j prepares sample points j and j + 8 (softmax
+// normaliser by two 8-lane shuffle reductions), writes each point's four corner offsets and four weights (attention weight
+// folded in) to shared memory, and after a __syncwarp every lane walks the 12 points with two broadcast 128-bit shared loads
+// per point.  The value bias enters once per (query, head): sum_p aw_p * (w1 + w2 + w3 + w4)_p * b, reduced over the 8 lanes.
+// Same mathematics as sample4_biased (reference: ms_deform_im2col_cuda.cuh:38-89, 242-304; ms_deform_attn.py:101-108);
+// the attention weight multiplies the corner weights before instead of after the corner sum (1 ulp-level differences).
+template <int L, int P>
+__global__ void __launch_bounds__(256)
+msda_encoder_staged_kernel(const float* __restrict__ value, LevelTable lt, TileTable tt, const float* __restrict__ ol,
+                           int S, int M, int tile_w_log2, float* __restrict__ out, const float* __restrict__ value_bias,
+                           const float* __restrict__ ol_bias, int split) {
+  constexpr int LP = L * P;
+  static_assert(LP <= 16, "two sample points per lane");
+  __shared__ int4 s_off[32][LP];
+  __shared__ float4 s_w[32][LP];
+  const int lane8 = threadIdx.x & 7;
+  const int tq = threadIdx.x >> 3;                 // query inside the tile = (query, head) unit of this CTA
+  const int tile = blockIdx.x, m = blockIdx.y, n = blockIdx.z;
+  int lq = 0;
+#pragma unroll
+  for (int i = 1; i < L; ++i)
+    if (tile >= tt.first[i]) lq = i;
+  const int t = tile - tt.first[lq];
+  const int ty = t / tt.tiles_x[lq], tx = t - ty * tt.tiles_x[lq];
+  const int tile_w = 1 << tile_w_log2, tile_h = 32 >> tile_w_log2;
+  const int qx0 = tx * tile_w + (tq & (tile_w - 1));
+  const int qy0 = ty * tile_h + (tq >> tile_w_log2);
+  const bool valid = qx0 < lt.W[lq] && qy0 < lt.H[lq];
+  // out-of-tile units run on a clamped query (the shuffles below need every lane) and skip the store
+  const int qx = min(qx0, lt.W[lq] - 1), qy = min(qy0, lt.H[lq] - 1);
+  const int q = lt.start[lq] + qy * lt.W[lq] + qx;
+  const long long nq = (long long)n * S + q;
+  const float refx = ((float)qx + 0.5f) / (float)lt.W[lq];
+  const float refy = ((float)qy + 0.5f) / (float)lt.H[lq];
+  const float* row = ol + nq * (long long)(M * LP * 3);
+  const int pix_stride = M * 32;
+
+  // ---- phase 1: lane j prepares points j and j + 8 -------------------------------------------------------------------
+  float lg[2], ox[2], oy[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int pp = lane8 + 8 * k;
+    lg[k] = -INFINITY;
+    ox[k] = oy[k] = 0.f;
+    if (pp < LP) {
+      const float2 o2 = __ldg(reinterpret_cast<const float2*>(row + m * (LP * 2) + pp * 2));
+      ox[k] = o2.x;
+      oy[k] = o2.y;
+      lg[k] = __ldg(row + M * LP * 2 + m * LP + pp);
+      if (ol_bias != nullptr) {
+        ox[k] += __ldg(ol_bias + m * (LP * 2) + pp * 2);
+        oy[k] += __ldg(ol_bias + m * (LP * 2) + pp * 2 + 1);
+        lg[k] += __ldg(ol_bias + M * LP * 2 + m * LP + pp);
+      }
+    }
+  }
+  float mx = fmaxf(lg[0], lg[1]);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float e[2];
+  e[0] = expf(lg[0] - mx);                          // expf(-inf) = 0 for the unused slot
+  e[1] = expf(lg[1] - mx);
+  float sum = e[0] + e[1];
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  float bpart = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int pp = lane8 + 8 * k;
+    if (pp < LP) {
+      const int l = pp / P;
+      const int H = lt.H[l], W = lt.W[l];
+      const float locx = refx + ox[k] / (float)W;
+      const float locy = refy + oy[k] / (float)H;
+      const float x = locx * (float)W - 0.5f, y = locy * (float)H - 0.5f;
+      const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+      const float xf = floorf(x), yf = floorf(y);
+      const int x0 = (int)xf, y0 = (int)yf;
+      const float lx = x - xf, ly = y - yf;
+      const float hx = 1.f - lx, hy = 1.f - ly;
+      const bool x0ok = x0 >= 0, x1ok = x0 + 1 <= W - 1, y0ok = y0 >= 0, y1ok = y0 + 1 <= H - 1;
+      const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+      const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+      const float w1 = (inside && y0ok && x0ok) ? hy * hx : 0.f;
+      const float w2 = (inside && y0ok && x1ok) ? hy * lx : 0.f;
+      const float w3 = (inside && y1ok && x0ok) ? ly * hx : 0.f;
+      const float w4 = (inside && y1ok && x1ok) ? ly * lx : 0.f;
+      const float aw = e[k] * inv;
+      const int lbase = lt.start[l];
+      s_off[tq][pp] = make_int4((lbase + yc0 * W + xc0) * pix_stride, (lbase + yc0 * W + xc1) * pix_stride,
+                                (lbase + yc1 * W + xc0) * pix_stride, (lbase + yc1 * W + xc1) * pix_stride);
+      s_w[tq][pp] = make_float4(aw * w1, aw * w2, aw * w3, aw * w4);
+      bpart = fmaf(aw, (w1 + w2) + (w3 + w4), bpart);
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) bpart += __shfl_xor_sync(0xffffffffu, bpart, o);
+  __syncwarp();                                     // the 8 lanes of a unit sit in one warp
+
+  // ---- phase 2: every lane gathers its 4 channels over the 12 points -------------------------------------------------
+  const float* base = value + (size_t)n * S * pix_stride + m * 32 + lane8 * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int pp = 0; pp < LP; ++pp) {
+    const int4 o = s_off[tq][pp];
+    const float4 w = s_w[tq][pp];
+    const float4 v1 = ldg_f4(base + o.x), v2 = ldg_f4(base + o.y), v3 = ldg_f4(base + o.z), v4 = ldg_f4(base + o.w);
+    fma4(acc, w.x, v1);
+    fma4(acc, w.y, v2);
+    fma4(acc, w.z, v3);
+    fma4(acc, w.w, v4);
+  }
+  if (value_bias != nullptr) fma4(acc, bpart, ldg_f4(value_bias + m * 32 + lane8 * 4));
+  if (valid) store_maybe_split(out, (size_t)nq, M * 32, m * 32 + lane8 * 4, acc, split);
+}
+
 static int fill_levels(LevelTable& lt, const int64_t* shapes_h, const int64_t* lsi_h, int L) {
   for (int l = 0; l < L; ++l) {
     lt.H[l] = (int)shapes_h[2 * l];
@@ -520,7 +640,7 @@ extern "C" int univs_ms_deform_attn_encoder_tiled_f32(void* stream, const float*
     UNIVS_REQUIRE(split == 0 || split == UNIVS_SPLIT_F16U || split == UNIVS_SPLIT_F16C ||
                       (split != -1 && (split > 0 ? split : -split) % 4 == 0 && C % (split > 0 ? split : -split) == 0),
                   "ms_deform_attn_encoder_tiled: split chunk must divide heads*32");
-    msda_encoder_tiled_kernel<3, 4, true><<<grid, 256, 0, (cudaStream_t)stream>>>(value, lt, tt, offs_logits, spatial_size,
+    msda_encoder_staged_kernel<3, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(value, lt, tt, offs_logits, spatial_size,
                                                                                 num_heads, log2w, out, value_bias,
                                                                                 offs_logits_bias, split);
   }

@@ -7,29 +7,26 @@
 //
 // Work unit = (frame, window, head): 144 tokens x 32 dims of q, k, v.  Persistent CTAs (one per SM, 512 threads),
 // warp-specialised, units round-robin over CTAs:
-//   9 loader warps      : gather q/k/v rows through the roll/pad addressing (128-bit loads, all 12 of a thread's unit share
+//   warps 10-15  loaders : gather q/k/v rows through the roll/pad addressing (128-bit loads, all 18 of a thread's unit share
 //                          in flight at once: one memory latency per unit), add the qkv bias, scale q, split fp32 -> fp16
 //                          hi + lo once, store K-major SWIZZLE_64B operand tiles (64-byte rows = 32 dims); 2-stage ring.
 //                          The grid is a multiple of the head count, so a CTA only ever sees ONE head: its
 //                          relative-position table and qkv bias are fetched once per CTA, not per unit (ncu, round 2: the
 //                          per-unit table gather was 17 % of the loader's time, the three dependent load batches most of
 //                          the rest, and the softmax warps spent 43 % of theirs waiting for scores)
-//   warp 17      MMA     : one elected lane issues  S = Ql Kh^T + Qh Kl^T + Qh Kh^T  and  O = Pl Vh + Ph Vl + Ph Vh;
-//                          V is consumed as stored ([key][dim] rows) through the MN-major B descriptor; also allocates TMEM
-//   warps 0-15   softmax of row tile 0 (query rows 0-127; M=128, N=144): warp = (TMEM lane quarter, column part); a thread
-//                          owns 36 scores (three key rows) of one row; the four parts exchange max / sum through shared
-//                          memory.  (Round 2, ncu: with 8 warps x 72 columns the softmax warps were busy 76 % of the time at
-//                          IPC 0.1 -- dependent convert / exp / split chains with two warps per scheduler; twice the warps
-//                          with half the columns each hide that latency.)
-//   warps 16, 20 softmax of the tail tile (query rows 128-143), 40 of its 80 columns each.  tcgen05.ld addresses are
-//                          warp-uniform, so the two lane halves cannot read different columns; instead the MMA puts
-//                          different KEYS under the same columns: the 16 tail rows of Q sit between two blocks of 16 zero
-//                          rows ("Z Q Z"), the A tile starting at Z (rows = [0 | Q]) multiplies keys 64-143 (N=80,
-//                          overwrite), the A tile starting at Q (rows = [Q | 0]) multiplies keys 0-63 (N=64, accumulate):
-//                          TMEM lanes 0-15 end up with keys 0-63 of the 16 rows, lanes 16-31 with keys 64-143 of the same
-//                          rows, both in columns 0-79.  Each lane writes its part of its P row and zeros elsewhere, the PV
-//                          MMA leaves two partial sums per row and the epilogue adds them with one shuffle.
-//   warps 18-19, 21-27  loaders (see above), 288 threads, four (token, 4-dim group) items each.
+//   warp 9       MMA     : one elected lane issues  S = Ql Kh^T + Qh Kl^T + Qh Kh^T  and  O = Pl Vh + Ph Vl + Ph Vh;
+//                          V is consumed as stored ([key][dim] rows) through the MN-major B descriptor
+//   warps 0-7    softmax of row tile 0 (query rows 0-127; M=128, N=144): warp = (TMEM lane quarter, column half); a thread
+//                          owns 72 scores of one row; the halves exchange max / sum through shared memory
+//   warp 8       softmax of the tail tile (query rows 128-143).  tcgen05.ld addresses are warp-uniform, so the two lane
+//                          halves cannot read different columns; instead the MMA puts different KEYS under the same
+//                          columns: the 16 tail rows of Q sit between two blocks of 16 zero rows ("Z Q Z"), the A tile
+//                          starting at Z (rows = [0 | Q]) multiplies keys 64-143 (N=80, overwrite), the A tile starting
+//                          at Q (rows = [Q | 0]) multiplies keys 0-63 (N=64, accumulate): TMEM lanes 0-15 end up with
+//                          keys 0-63 of the 16 rows, lanes 16-31 with keys 64-143 of the same rows, both in columns
+//                          0-79.  Each lane writes its part of its P row and zeros elsewhere, the PV MMA leaves two
+//                          partial sums per row and the epilogue adds them with one shuffle.
+//   warp 9 also allocates TMEM.
 // Softmax warps run  softmax(n+1) -> epilogue(n), the MMA lane  S(n+1) -> PV(n), so the tensor pipe works on the next
 // unit's scores while the softmax of the current one is in flight, and no softmax warp waits for a PV it just enabled.
 // TMEM columns: S tile0 [0,144)  S tail [160,240)  O tile0 [320,352)  O tail [352,384).
@@ -45,13 +42,11 @@ using namespace tc;
 
 constexpr int kWS = 12;
 constexpr int kN = 144;
-constexpr int kThreads = 896;               // 28 warps: 16 softmax + 2 tail + 1 MMA + 9 loaders (<= 72 registers per thread)
-constexpr int kMmaWarp = 17;
-constexpr int kAllocWarp = 17;
-constexpr int kTailWarpA = 16, kTailWarpB = 20;     // both = 0 mod 4: the tail tile lives in TMEM lanes 0-31
-constexpr int kLoaderThreads = 288;
-constexpr int kPartCols = 36;               // tile 0: score columns per softmax thread (three key rows)
-constexpr int kTailCols = 40;               // tail tile: score columns per thread
+constexpr int kThreads = 512;
+constexpr int kMmaWarp = 9;
+constexpr int kAllocWarp = 9;
+constexpr int kLoaderWarp0 = 10;
+constexpr int kLoaderThreads = 192;
 constexpr int kItemsPerLoader = kN * 8 / kLoaderThreads;   // (token, 4-dim group) items per loader thread and unit: 6
 constexpr int kTable = 23 * 23;
 constexpr int kTailKeys0 = 64;                 // keys of the tail rows handled by TMEM lanes 0-15 (lanes 16-31: the other 80)
@@ -74,11 +69,8 @@ constexpr int kOffP1h = 2 * kStageBytes, kOffP1l = kOffP1h + kP1Bytes;
 constexpr int kOffP0h = kOffP1l + kP1Bytes, kOffP0l = kOffP0h + kP0Bytes;
 constexpr int kOffBias = kOffP0l + kP0Bytes;   // 544 floats (+ 544 unused)
 constexpr int kBiasStride = 544;
-// exchange area (floats): tile 0 max[4 part][128] + sum[2 parity][4][128]; tail max[2 warp][32] + sum[2 parity][2][32]
-constexpr int kXchMax0 = 0, kXchSum0 = 4 * 128, kXchMax1 = kXchSum0 + 2 * 4 * 128, kXchSum1 = kXchMax1 + 2 * 32;
-constexpr int kXchFloats = kXchSum1 + 2 * 2 * 32;
-constexpr int kOffXch = kOffBias + kBiasStride * 4;
-constexpr int kOffKidx = kOffXch + kXchFloats * 4;        // int[144]: key -> ky * 23 + kx
+constexpr int kOffXch = kOffBias + 2 * kBiasStride * 4;   // max[2 parity][2 half][128] + sum[2][2][128] floats
+constexpr int kOffKidx = kOffXch + 2 * 2 * 2 * 128 * 4;   // int[144]: key -> ky * 23 + kx
 constexpr int kOffBars = kOffKidx + kN * 4;
 constexpr int kNumBars = 16;
 constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
@@ -140,9 +132,7 @@ __device__ __forceinline__ void store_token(unsigned char* st, int i, int lane8,
 __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const float* __restrict__ qkv,
                             const float* __restrict__ qkv_bias, const float* __restrict__ table, const Geo g,
                             long long units, float scale) {
-  // loader warps are 18, 19 and 21-27 (warps 16 / 20 are the tail warps, 17 the MMA warp)
-  const int lw = (int)(threadIdx.x >> 5);
-  const int lt = (lw < kTailWarpB ? lw - 18 : lw - 19) * 32 + (int)(threadIdx.x & 31);
+  const int lt = threadIdx.x - kLoaderWarp0 * 32;
   const int lane8 = lt & 7, slot = lt >> 3;
   const int C = g.C;
   // the zero rows of the "Z Q Z" blocks (both stages, hi and lo) are written once; token stores never touch them
@@ -279,75 +269,33 @@ __device__ void mma_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_base
 //   TAIL == true : row = 128 + (lane & 15), half = lane >> 4: keys [0,64) (half 0; columns 64-79 are not its keys) or
 //                  [64,144) (half 1); partner = lane ^ 16
 struct RowCtx {
-  int quarter, part, lane;
+  int quarter, half, lane;
   int row;       // token slot in the window, 0..143
   int prow;      // row inside the P tile
 };
 
-// P = exp(s - max) of 8 consecutive keys as fp16 hi + lo into chunk `gch` (16 bytes = 8 keys) of this thread's P row
-__device__ __forceinline__ float store_p8(const float* sc, float mneg, uint32_t ph, uint32_t pl, uint32_t atom, uint32_t rowoff,
-                                          uint32_t sw, uint32_t gch) {
-  constexpr float kLog2e = 1.4426950408889634f;
-  uint32_t hi[4], lo[4];
-  float sum = 0.f;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float p0 = ex2_approx(fmaf(sc[2 * e], kLog2e, mneg));        // exp2(-inf) = 0 in unowned columns
-    const float p1 = ex2_approx(fmaf(sc[2 * e + 1], kLog2e, mneg));
-    sum += p0 + p1;
-    split_h2(p0, p1, hi[e], lo[e]);
-  }
-  const uint32_t off = (gch >> 2) * atom + rowoff + (((gch & 3u) ^ sw) << 4);
-  sts_v4(ph + off, hi[0], hi[1], hi[2], hi[3]);
-  sts_v4(pl + off, lo[0], lo[1], lo[2], lo[3]);
-  return sum;
-}
-// the same for 4 keys: the lower (upper == false) or upper 8 bytes of chunk `gch`
-__device__ __forceinline__ float store_p4(const float* sc, float mneg, uint32_t ph, uint32_t pl, uint32_t atom, uint32_t rowoff,
-                                          uint32_t sw, uint32_t gch, bool upper) {
-  constexpr float kLog2e = 1.4426950408889634f;
-  uint32_t hi[2], lo[2];
-  float sum = 0.f;
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const float p0 = ex2_approx(fmaf(sc[2 * e], kLog2e, mneg));
-    const float p1 = ex2_approx(fmaf(sc[2 * e + 1], kLog2e, mneg));
-    sum += p0 + p1;
-    split_h2(p0, p1, hi[e], lo[e]);
-  }
-  const uint32_t off = (gch >> 2) * atom + rowoff + (((gch & 3u) ^ sw) << 4) + (upper ? 8u : 0u);
-  sts_v2(ph + off, hi[0], hi[1]);
-  sts_v2(pl + off, lo[0], lo[1]);
-  return sum;
-}
-
-// One thread = NCOL consecutive score columns of one query row.
-//   TAIL == false: row = 32*quarter + lane of tile 0, keys [36*part, 36*part + 36) (three key rows); partners = the same row
-//                  in the warps (quarter, other parts)
-//   TAIL == true : row = 128 + (lane & 15), lane half h = lane >> 4 owns keys [0,64) (h = 0; columns 64-79 are not its
-//                  keys) or [64,144) (h = 1), both under columns 0-79; warp part p takes columns [40p, 40p + 40); partners:
-//                  lane ^ 16 (other key range of the row) and the same lane of the other tail warp
 template <bool TAIL>
 __device__ __forceinline__ float softmax_unit(unsigned char* smem, uint64_t* bars, uint32_t tmem_base, const RowCtx& rc,
                                               const Geo& g, const Unit& un, int n, long long u, float* __restrict__ dbg) {
   constexpr float kLog2e = 1.4426950408889634f;
-  constexpr int NCOL = TAIL ? kTailCols : kPartCols;
+  constexpr int NCOL = TAIL ? (kN - kTailKeys0) : 72;
   constexpr int TB = TAIL ? 1 : 0;
-  float sc[NCOL];
+  uint32_t sr[NCOL];
   mbar_wait(&bars[S_FULL + TB], (uint32_t)(n & 1), S_FULL + TB);
   fence_after();
   {
-    // warp-uniform address: lane quarter and column part are per-warp values
-    const uint32_t taddr = TAIL ? tmem_base + kColS1 + (uint32_t)(rc.part * kTailCols)
-                                : tmem_base + ((uint32_t)(rc.quarter * 32) << 16) + kColS0 + (uint32_t)(rc.part * kPartCols);
-    uint32_t* r0 = reinterpret_cast<uint32_t*>(sc);
+    // warp-uniform address: lane quarter and (tile 0) column half are per-warp values
+    const uint32_t taddr = TAIL ? tmem_base + kColS1
+                                : tmem_base + ((uint32_t)(rc.quarter * 32) << 16) + kColS0 + (uint32_t)rc.half * 72u;
+    uint32_t* r0 = sr;
+    uint32_t* r1 = sr + 32;
+    uint32_t* r2 = sr + 64;
     UNIVS_TMEM_LD_X32(taddr, r0);
+    UNIVS_TMEM_LD_X32(taddr + 32u, r1);
     if (TAIL) {
-      uint32_t* r1 = reinterpret_cast<uint32_t*>(sc) + 32;
-      UNIVS_TMEM_LD_X8(taddr + 32u, r1);
+      UNIVS_TMEM_LD_X16(taddr + 64u, r2);
     } else {
-      uint32_t* r1 = reinterpret_cast<uint32_t*>(sc) + 32;
-      UNIVS_TMEM_LD_X4(taddr + 32u, r1);
+      UNIVS_TMEM_LD_X8(taddr + 64u, r2);
     }
     tmem_wait_ld();
   }
@@ -359,21 +307,19 @@ __device__ __forceinline__ float softmax_unit(unsigned char* smem, uint64_t* bar
   const int qy = rc.row / kWS, qx = rc.row - qy * kWS;
   const float* sbias = reinterpret_cast<const float*>(smem + kOffBias) + (qy + 11) * 23 + (qx + 11);
   const int* kidx = reinterpret_cast<const int*>(smem + kOffKidx);
-  const int lhalf = rc.lane >> 4;                        // tail: which key range this lane owns
-  const int key0 = TAIL ? lhalf * kTailKeys0 + rc.part * kTailCols : rc.part * kPartCols;
+  const int key0 = TAIL ? rc.half * kTailKeys0 : rc.half * 72;
+  float sc[NCOL];
   if (!TAIL) {
-    const float* bp = sbias - rc.part * 3 * 23;          // 36 keys = 3 key rows: the per-column part is a compile-time constant
+    const float* bp = sbias - rc.half * 6 * 23;     // 72 keys = 6 key rows: the per-column part is a compile-time constant
 #pragma unroll
-    for (int j = 0; j < NCOL; ++j) sc[j] += bp[-((j / kWS) * 23 + (j % kWS))];
+    for (int j = 0; j < NCOL; ++j) sc[j] = __uint_as_float(sr[j]) + bp[-((j / kWS) * 23 + (j % kWS))];
   } else {
-    // key -> table offset through the LUT (64 keys are not a whole number of key rows); keys beyond 143 (columns that are
-    // not this lane's) read a clamped entry and are overwritten below
-    // in blocks of 8 columns with a scheduling barrier in between, so that the dependent loads are not all hoisted
-    // (register pressure: 72 registers per thread)
+    // key -> table offset through the LUT (64 keys are not a whole number of key rows); in blocks of 16 columns with a
+    // scheduling barrier in between, so that the 160 dependent loads are not all hoisted (register pressure)
 #pragma unroll
-    for (int jb = 0; jb < NCOL; jb += 8) {
+    for (int jb = 0; jb < NCOL; jb += 16) {
 #pragma unroll
-      for (int j = jb; j < jb + 8; ++j) sc[j] += sbias[-kidx[min(key0 + j, kN - 1)]];
+      for (int j = jb; j < jb + 16; ++j) sc[j] = __uint_as_float(sr[j]) + sbias[-kidx[key0 + j]];
       asm volatile("" ::: "memory");
     }
   }
@@ -386,93 +332,79 @@ __device__ __forceinline__ float softmax_unit(unsigned char* smem, uint64_t* bar
     if (mh) dh = (qy >= thr) ? ((1u << thr) - 1u) : (0xfffu & ~((1u << thr) - 1u));
     if (mw) dw = (qx >= thr) ? ((1u << thr) - 1u) : (0xfffu & ~((1u << thr) - 1u));
     if (!TAIL) {
-      dh >>= rc.part * 3;
+      dh >>= rc.half * 6;
 #pragma unroll
       for (int j = 0; j < NCOL; ++j)
         if (((dh >> (j / kWS)) | (dw >> (j % kWS))) & 1u) sc[j] += -100.f;
     } else {
 #pragma unroll
-      for (int jb = 0; jb < NCOL; jb += 8) {
-#pragma unroll
-        for (int j = jb; j < jb + 8; ++j) {
-          const int c = kidx[min(key0 + j, kN - 1)];
-          const int ky = c / 23, kx = c - ky * 23;
-          if (((dh >> ky) | (dw >> kx)) & 1u) sc[j] += -100.f;
-        }
-        asm volatile("" ::: "memory");
+      for (int j = 0; j < NCOL; ++j) {
+        const int c = kidx[key0 + j];
+        const int ky = c / 23, kx = c - ky * 23;
+        if (((dh >> ky) | (dw >> kx)) & 1u) sc[j] += -100.f;
       }
     }
   }
-  if (TAIL) {      // lanes 0-15 own keys 0-63 only: columns 64-79 hold nothing of theirs
+  if (TAIL) {      // lanes 0-15 own 64 keys only: the other 16 columns hold nothing of theirs
 #pragma unroll
-    for (int j = 0; j < NCOL; ++j)
-      if (lhalf == 0 && rc.part * kTailCols + j >= kTailKeys0) sc[j] = -INFINITY;
+    for (int j = kTailKeys0; j < NCOL; ++j)
+      if (rc.half == 0) sc[j] = -INFINITY;
   }
   if (dbg != nullptr) {
     float* drow = dbg + ((size_t)u * kN + rc.row) * kN + key0;
 #pragma unroll
     for (int j = 0; j < NCOL; ++j)
-      if (!TAIL || lhalf == 1 || rc.part * kTailCols + j < kTailKeys0) drow[j] = sc[j];
+      if (!TAIL || rc.half == 1 || j < kTailKeys0) drow[j] = sc[j];
   }
   float mx = sc[0];
 #pragma unroll
   for (int j = 1; j < NCOL; ++j) mx = fmaxf(mx, sc[j]);
   float* xch = reinterpret_cast<float*>(smem + kOffXch);
   if (!TAIL) {
-    // exchange between the four column parts of the row; the second barrier keeps a fast warp from overwriting its slot
-    // (next unit) before the others have read it
-    float* xmax = xch + kXchMax0;
-    xmax[rc.part * 128 + rc.row] = mx;
-    named_bar_sync(1 + rc.quarter, 128);
-    mx = fmaxf(fmaxf(xmax[rc.row], xmax[128 + rc.row]), fmaxf(xmax[256 + rc.row], xmax[384 + rc.row]));
-    named_bar_sync(5 + rc.quarter, 128);
+    float* xmax = xch + (n & 1) * 256;
+    xmax[rc.half * 128 + rc.row] = mx;
+    named_bar_sync(1 + rc.quarter, 64);
+    mx = fmaxf(mx, xmax[(rc.half ^ 1) * 128 + rc.row]);
   } else {
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-    float* xmax = xch + kXchMax1;
-    xmax[rc.part * 32 + rc.lane] = mx;
-    named_bar_sync(9, 64);
-    mx = fmaxf(xmax[rc.lane], xmax[32 + rc.lane]);
-    named_bar_sync(10, 64);
   }
   const float mneg = -mx * kLog2e;
 
-  // P = exp(s - max) as fp16 hi + lo into the K-major SWIZZLE_64B A tile of the PV MMA (32-key atoms, 16-byte chunks of 8 keys)
+  // P = exp(s - max) as fp16 hi + lo into the K-major SWIZZLE_64B A tile of the PV MMA (32-key atoms)
   if (n > 0) mbar_wait(&bars[P_FREE + TB], (uint32_t)((n - 1) & 1), P_FREE + TB);
   const uint32_t ph = smem_u32(smem + (TAIL ? kOffP1h : kOffP0h)), pl = smem_u32(smem + (TAIL ? kOffP1l : kOffP0l));
   constexpr uint32_t atom = TAIL ? kP1Atom : kP0Atom;
   const uint32_t rowoff = (uint32_t)rc.prow * kRow;
   const uint32_t sw = (uint32_t)(rc.prow >> 1) & 3u;
+  const uint32_t chunk0 = (uint32_t)key0 >> 3;                               // first 16-byte chunk (8 keys) of this thread
   float sum = 0.f;
-  if (!TAIL) {
-    // keys [36 part, 36 part + 36): even parts start on a chunk boundary (4 chunks + the lower half of the next), odd parts
-    // start in the middle of a chunk (its upper half + 4 chunks)
-    if ((rc.part & 1) == 0) {
-      const uint32_t g0 = (uint32_t)(rc.part * kPartCols) >> 3;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) sum += store_p8(sc + 8 * cc, mneg, ph, pl, atom, rowoff, sw, g0 + (uint32_t)cc);
-      sum += store_p4(sc + 32, mneg, ph, pl, atom, rowoff, sw, g0 + 4u, false);
-    } else {
-      const uint32_t g0 = (uint32_t)(rc.part * kPartCols - 4) >> 3;
-      sum += store_p4(sc, mneg, ph, pl, atom, rowoff, sw, g0, true);
+  for (int cc = 0; cc < NCOL / 8; ++cc) {
+    uint32_t hi[4], lo[4];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) sum += store_p8(sc + 4 + 8 * cc, mneg, ph, pl, atom, rowoff, sw, g0 + 1u + (uint32_t)cc);
+    for (int e = 0; e < 4; ++e) {
+      const float p0 = ex2_approx(fmaf(sc[cc * 8 + 2 * e], kLog2e, mneg));        // exp2(-inf) = 0 in the unowned columns
+      const float p1 = ex2_approx(fmaf(sc[cc * 8 + 2 * e + 1], kLog2e, mneg));
+      sum += p0 + p1;
+      split_h2(p0, p1, hi[e], lo[e]);
     }
-    xch[kXchSum0 + (n & 1) * 512 + rc.part * 128 + rc.row] = sum;
-  } else {
-    // this lane's keys sit in chunks [key0 / 8, key0 / 8 + 5) of ITS OWN P row; the rest of that row is zero (those keys
-    // belong to the partner lane's copy of the row): lane half 0 owns chunks 0-9 (8, 9 come out as zeros: -inf columns)
-    // and chunks 10-17 are zero; lane half 1 owns chunks 8-17 and chunks 0-7 are zero.  Each tail warp clears half of them.
-    const uint32_t g0 = (uint32_t)key0 >> 3;
+    const uint32_t gch = chunk0 + (uint32_t)cc;
+    const uint32_t off = (gch >> 2) * atom + rowoff + (((gch & 3u) ^ sw) << 4);
+    sts_v4(ph + off, hi[0], hi[1], hi[2], hi[3]);
+    sts_v4(pl + off, lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (TAIL) {
+    // the rest of this lane's P row is zero (its keys belong to the partner lane's copy of the row):
+    // half 0 wrote chunks 0-9 (8, 9 as zeros) -> zero 10-17;  half 1 wrote chunks 8-17 -> zero 0-7
 #pragma unroll
-    for (int cc = 0; cc < 5; ++cc) sum += store_p8(sc + 8 * cc, mneg, ph, pl, atom, rowoff, sw, g0 + (uint32_t)cc);
-#pragma unroll
-    for (int cz = 0; cz < 4; ++cz) {
-      const uint32_t gz = (lhalf ? 0u : 10u) + (uint32_t)(rc.part * 4 + cz);
+    for (int cz = 0; cz < 8; ++cz) {
+      const uint32_t gz = (rc.half ? 0u : 10u) + (uint32_t)cz;
       const uint32_t offz = (gz >> 2) * atom + rowoff + (((gz & 3u) ^ sw) << 4);
       sts_v4(ph + offz, 0u, 0u, 0u, 0u);
       sts_v4(pl + offz, 0u, 0u, 0u, 0u);
     }
-    xch[kXchSum1 + (n & 1) * 64 + rc.part * 32 + rc.lane] = sum;
+  } else {
+    xch[512 + (n & 1) * 256 + rc.half * 128 + rc.row] = sum;
   }
   fence_proxy_async_smem();
   mbar_arrive(&bars[P_FULL + TB]);
@@ -486,40 +418,29 @@ __device__ __forceinline__ void epilogue_unit(unsigned char* smem, uint64_t* bar
   constexpr int TB = TAIL ? 1 : 0;
   mbar_wait(&bars[O_FULL + TB], (uint32_t)(n & 1), O_FULL + TB);
   fence_after();
-  float o[8];          // this thread's 8 output dims: tile 0: [8 part, 8 part + 8); tail: [16 part + 8 (lane >> 4), + 8)
+  float o[16];
   float total;
-  const float* xch = reinterpret_cast<const float*>(smem + kOffXch);
-  int dim0;
   if (!TAIL) {
-    uint32_t r[8];
-    const uint32_t taddr = tmem_base + ((uint32_t)(rc.quarter * 32) << 16) + kColO0 + (uint32_t)rc.part * 8u;
-    UNIVS_TMEM_LD_X8(taddr, r);
-    tmem_wait_ld();
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[e]);
-    const float* xs = xch + kXchSum0 + (n & 1) * 512 + rc.row;
-    total = (xs[0] + xs[128]) + (xs[256] + xs[384]);
-    dim0 = rc.part * 8;
-  } else {
-    // lanes l and l^16 hold the two key-range partial sums of the same row; tail warp `part` takes dims [16 part, 16 part + 16),
-    // lanes 0-15 store the first 8 of them, lanes 16-31 the other 8
     uint32_t r[16];
-    const uint32_t taddr = tmem_base + kColO1 + (uint32_t)rc.part * 16u;
+    const uint32_t taddr = tmem_base + ((uint32_t)(rc.quarter * 32) << 16) + kColO0 + (uint32_t)rc.half * 16u;
     UNIVS_TMEM_LD_X16(taddr, r);
     tmem_wait_ld();
-    const int lhalf = rc.lane >> 4;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float a = __uint_as_float(r[e]), b = __uint_as_float(r[8 + e]);
+    for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(r[e]);
+    total = sum + reinterpret_cast<const float*>(smem + kOffXch)[512 + (n & 1) * 256 + (rc.half ^ 1) * 128 + rc.row];
+  } else {
+    uint32_t r[32];
+    const uint32_t taddr = tmem_base + kColO1;
+    UNIVS_TMEM_LD_X32(taddr, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {   // lanes l and l^16 hold the two key-range partial sums of the same row
+      const float a = __uint_as_float(r[e]), b = __uint_as_float(r[16 + e]);
       const float a2 = a + __shfl_xor_sync(0xffffffffu, a, 16), b2 = b + __shfl_xor_sync(0xffffffffu, b, 16);
-      o[e] = lhalf ? b2 : a2;
+      o[e] = rc.half ? b2 : a2;      // lanes 0-15 store dims 0-15, lanes 16-31 dims 16-31
     }
-    const float* xs = xch + kXchSum1 + (n & 1) * 64;
-    const float mine = xs[rc.lane] + xs[32 + rc.lane];
-    total = mine + __shfl_xor_sync(0xffffffffu, mine, 16);
-    dim0 = rc.part * 16 + lhalf * 8;
+    total = sum + __shfl_xor_sync(0xffffffffu, sum, 16);
   }
-  (void)sum;
   fence_before();
   __syncwarp();
   if (rc.lane == 0) mbar_arrive(&bars[O_FREE + TB]);
@@ -527,30 +448,36 @@ __device__ __forceinline__ void epilogue_unit(unsigned char* smem, uint64_t* bar
   const int src = source_token(g, un, rc.row);     // window_reverse + roll(+shift) + crop: pad rows are dropped
   if (src < 0) return;
   const float inv = 1.f / total;
-  const int c = un.head * 32 + dim0;
+  const int c = un.head * 32 + rc.half * 16;
   if (out != nullptr) {
     float4* dst = reinterpret_cast<float4*>(out + (size_t)src * g.C + c);
-    dst[0] = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
-    dst[1] = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e] * inv, o[4 * e + 1] * inv, o[4 * e + 2] * inv, o[4 * e + 3] * inv);
   }
   if (out16 != nullptr) {
     // fp16x3 GEMM operand (single K-chunk, C <= 1536): [lo*2^11 (C) | hi*2^-11 (C) | hi (C)]
-    uint32_t lo2[4], hs2[4], hi2[4];
+    uint32_t lo2[8], hs2[8], hi2[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < 8; ++e) {
       const float a = o[2 * e] * inv, b = o[2 * e + 1] * inv;
       const __half2 h = __floats2half2_rn(a, b);
       const float2 f = __half22float2(h);
       const __half2 l = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);
-      const __half2 sc2 = __floats2half2_rn(f.x * (1.f / 2048.f), f.y * (1.f / 2048.f));
+      const __half2 s = __floats2half2_rn(f.x * (1.f / 2048.f), f.y * (1.f / 2048.f));
       hi2[e] = *reinterpret_cast<const uint32_t*>(&h);
       lo2[e] = *reinterpret_cast<const uint32_t*>(&l);
-      hs2[e] = *reinterpret_cast<const uint32_t*>(&sc2);
+      hs2[e] = *reinterpret_cast<const uint32_t*>(&s);
     }
     __half* rowp = out16 + (size_t)src * (3 * (size_t)g.C) + c;
-    *reinterpret_cast<uint4*>(rowp) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
-    *reinterpret_cast<uint4*>(rowp + g.C) = make_uint4(hs2[0], hs2[1], hs2[2], hs2[3]);
-    *reinterpret_cast<uint4*>(rowp + 2 * g.C) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+    uint4* d0 = reinterpret_cast<uint4*>(rowp);
+    uint4* d1 = reinterpret_cast<uint4*>(rowp + g.C);
+    uint4* d2 = reinterpret_cast<uint4*>(rowp + 2 * g.C);
+    d0[0] = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+    d0[1] = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+    d1[0] = make_uint4(hs2[0], hs2[1], hs2[2], hs2[3]);
+    d1[1] = make_uint4(hs2[4], hs2[5], hs2[6], hs2[7]);
+    d2[0] = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+    d2[1] = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);
   }
 }
 
@@ -593,16 +520,16 @@ swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restr
     }
     mbar_init(&bars[S_FULL + 0], 1);
     mbar_init(&bars[S_FULL + 1], 1);
-    mbar_init(&bars[S_FREE + 0], 16);     // one arrive per softmax warp of tile 0
-    mbar_init(&bars[S_FREE + 1], 2);      // the two tail warps
-    mbar_init(&bars[P_FULL + 0], 512);    // every softmax thread arrives after its own P stores + proxy fence
-    mbar_init(&bars[P_FULL + 1], 64);
+    mbar_init(&bars[S_FREE + 0], 8);      // one arrive per softmax warp of tile 0
+    mbar_init(&bars[S_FREE + 1], 1);
+    mbar_init(&bars[P_FULL + 0], 256);    // every softmax thread arrives after its own P stores + proxy fence
+    mbar_init(&bars[P_FULL + 1], 32);
     mbar_init(&bars[P_FREE + 0], 1);
     mbar_init(&bars[P_FREE + 1], 1);
     mbar_init(&bars[O_FULL + 0], 1);
     mbar_init(&bars[O_FULL + 1], 1);
-    mbar_init(&bars[O_FREE + 0], 16);
-    mbar_init(&bars[O_FREE + 1], 2);
+    mbar_init(&bars[O_FREE + 0], 8);
+    mbar_init(&bars[O_FREE + 1], 1);
     mbar_init_fence();
   }
   if (warp == kAllocWarp) {
@@ -614,26 +541,26 @@ swin_window_attn_tc12_kernel(const float* __restrict__ qkv, const float* __restr
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kMmaWarp) {
+  if (warp >= kLoaderWarp0) {
+    loader_loop(smem, bars, qkv, qkv_bias, table, g, units, scale);
+  } else if (warp == kMmaWarp) {
     mma_loop(smem, bars, tmem_base, count);
-  } else if (warp < 16) {
+  } else if (warp < 8) {
     RowCtx rc;
     rc.quarter = warp & 3;
-    rc.part = warp >> 2;
+    rc.half = warp >> 2;
     rc.lane = lane;
     rc.row = rc.quarter * 32 + lane;
     rc.prow = rc.row;
     softmax_loop<false>(smem, bars, tmem_base, rc, g, count, out, out16, dbg);
-  } else if (warp == kTailWarpA || warp == kTailWarpB) {
+  } else if (warp == 8) {
     RowCtx rc;
     rc.quarter = 0;
-    rc.part = warp == kTailWarpB ? 1 : 0;
+    rc.half = lane >> 4;
     rc.lane = lane;
     rc.row = 128 + (lane & 15);
     rc.prow = lane;
     softmax_loop<true>(smem, bars, tmem_base, rc, g, count, out, out16, dbg);
-  } else {
-    loader_loop(smem, bars, qkv, qkv_bias, table, g, units, scale);
   }
   fence_before();
   __syncthreads();

@@ -400,9 +400,13 @@ def proca_core(q, k_self, v_self, k_mem, v_mem):
     return out
 
 
+def _on_device(t: torch.Tensor) -> bool:
+    return t.is_cuda
+
+
 def _chk_rows16(t: torch.Tensor, name: str):
     """fp16 CUDA matrix whose rows are contiguous (a row pitch is allowed: views of wider operand containers)"""
-    if not t.is_cuda:
+    if not _on_device(t):
         raise _cabi.UnivsB200Error(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
     if t.dtype != torch.float16 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
         raise _cabi.UnivsB200Error(f"{name}: expected an fp16 matrix with contiguous rows")
@@ -422,11 +426,11 @@ def gemm_f16x3_tc(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None
     or None)."""
     M, N = x16.shape[0], w16.shape[0]
     xp, wp = _chk_rows16(x16, "x16"), _chk_rows16(w16, "w16")
-    if out is not None and (out.dtype != torch.float32 or not out.is_cuda or out.shape != (M, N) or out.stride(1) != 1):
+    if out is not None and (out.dtype != torch.float32 or not _on_device(out) or out.shape != (M, N) or out.stride(1) != 1):
         raise _cabi.UnivsB200Error("gemm_f16x3_tc: out must be an fp32 CUDA [tokens, channels] matrix with contiguous rows")
     if want_f32 and out is None:
         out = torch.empty((M, N), device=x16.device, dtype=torch.float32)
-    if addend is not None and (addend.dtype != torch.float32 or not addend.is_cuda or addend.shape != (M, N) or addend.stride(1) != 1):
+    if addend is not None and (addend.dtype != torch.float32 or not _on_device(addend) or addend.shape != (M, N) or addend.stride(1) != 1):
         raise _cabi.UnivsB200Error("gemm_f16x3_tc: addend must be an fp32 CUDA [tokens, channels] matrix with contiguous rows")
     out16 = torch.empty((M, 2 * N), device=x16.device, dtype=torch.float16) if want_operand else None
     if M == 0:
