@@ -512,7 +512,9 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
         self._head_calls = 0
         pooled = {}
         if (self.pooled_masks and not want_aux and not (task == "grounding" and self.prompt_as_queries)
-                and all(h_m % h == 0 and w_m % w == 0 and (h_m // h) % 2 == 0 and (w_m // w) % 2 == 0 for h, w in size_list)):
+                and all(h_m % h == 0 and w_m % w == 0 and (h_m // h) % 2 == 0 and (w_m // w) % 2 == 0 for h, w in size_list)
+                # the register (mma.sync) einsum of the non-fp16x3 policies needs an even pixel count per frame
+                and (ops._einsum_mode == "f16x3" or all((h * w) % 2 == 0 for h, w in size_list))):
             for size in size_list:         # once per clip: the mask features at the three memory resolutions
                 if size not in pooled:
                     pooled[size] = ops.mask_feature_pool(feats_raw, hw, size)
