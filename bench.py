@@ -105,7 +105,16 @@ def named_kernel_rooflines(variant, T, H, W, Q, kernel_ms, kernel_calls, peak, d
 
     # mask einsum: e*(Q*C + C*HW + Q*HW) per frame per call, dec_layers + 1 calls
     HW = (Hp // 4) * (Wp // 4)
-    put("mask_einsum", "mask_einsum", float(e * T_dec * (Q * C + C * HW + Q * HW) * (dec_layers + 1)))
+    # full-resolution launches only: with pooled intermediate heads (SURVEY 8a note a11') nine of the ten head calls run on
+    # the pooled features at the memory resolutions (reported separately); the last one writes the full-resolution logits
+    n_full = kernel_calls.get("mask_einsum", dec_layers + 1)
+    put("mask_einsum", "mask_einsum", float(e * T_dec * (Q * C + C * HW + Q * HW) * n_full))
+    if "mask_einsum_pooled" in kernel_ms:
+        Sp = [(Hp // s) * (Wp // s) for s in (32, 16, 8)]
+        calls = kernel_calls.get("mask_einsum_pooled", dec_layers)
+        # head i (0-based, i < dec_layers) feeds layer i, whose memory level is i % 3
+        put("mask_einsum_pooled", "mask_einsum_pooled",
+            float(sum(e * T_dec * (Q * C + C * Sp[i % 3] + Q * Sp[i % 3]) for i in range(calls))))
     # MSDeformAttn core: e*(2*Len*256 + 3*Len*M*L*P) per frame per layer, M*L*P = 96
     Len = sum((Hp // s) * (Wp // s) for s in (8, 16, 32))
     put("ms_deform_attn", "ms_deform_attn_encoder", float(e * T_local * (2 * Len * C + 3 * Len * 96) * enc_layers))

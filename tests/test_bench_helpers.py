@@ -16,8 +16,15 @@ def test_named_kernel_algorithmic_bytes_match_survey_figures():
     r = bench.named_kernel_rooflines("large", 1, 720, 1280, 200, ms, calls, 1000.0, dec_layers=0, enc_layers=1)
     assert abs(r["mask_einsum"]["bytes_per_step"] / 1e6 - 107.6) < 0.1          # per frame per call
     assert abs(r["ms_deform_attn"]["bytes_per_step"] / 1e6 - 61.8) < 0.1        # per frame per layer
-    r = bench.named_kernel_rooflines("large", 5, 720, 1280, 200, ms, calls, 1000.0)
+    r = bench.named_kernel_rooflines("large", 5, 720, 1280, 200, ms, dict(calls, mask_einsum=10), 1000.0)
     assert abs(r["mask_einsum"]["bytes_per_step"] / 1e9 - 5.38) < 0.01          # x10 calls x T=5
+    # pooled intermediate heads: one full-resolution call + nine at the memory resolutions (1/32, 1/16, 1/8 in turn)
+    pooled = bench.named_kernel_rooflines("large", 5, 720, 1280, 200, dict(ms, mask_einsum_pooled=1.0),
+                                          dict(calls, mask_einsum=1, mask_einsum_pooled=9), 1000.0)
+    assert abs(pooled["mask_einsum"]["bytes_per_step"] / 1e9 - 0.538) < 0.001
+    S = [23 * 40, 46 * 80, 92 * 160]
+    want = sum(4 * 5 * (200 * 256 + 256 * S[i % 3] + 200 * S[i % 3]) for i in range(9))
+    assert pooled["mask_einsum_pooled"]["bytes_per_step"] == want
     # stage 1 of Swin-L at 736x1280: 184x320 tokens padded to 192x324, C = 192 -> 191 MB per block per frame
     stage1 = 4 * 4 * 192 * 324 * 192
     assert abs(stage1 / 1e6 - 191) < 0.5

@@ -373,22 +373,31 @@ msda_encoder_staged_kernel(const float* __restrict__ value, LevelTable lt, TileT
   const int lane8 = threadIdx.x & 7;
   const int tq = threadIdx.x >> 3;                 // query inside the tile = (query, head) unit of this CTA
   const int tile = blockIdx.x, m = blockIdx.y, n = blockIdx.z;
-  int lq = 0;
+  // level of this tile and its geometry by explicit selects (run-time indexing of the by-value tables compiles to long
+  // uniform compare / select chains)
+  int Wq = lt.W[0], Hq = lt.H[0], startq = lt.start[0], firstq = tt.first[0], tilesxq = tt.tiles_x[0];
 #pragma unroll
-  for (int i = 1; i < L; ++i)
-    if (tile >= tt.first[i]) lq = i;
-  const int t = tile - tt.first[lq];
-  const int ty = t / tt.tiles_x[lq], tx = t - ty * tt.tiles_x[lq];
+  for (int i = 1; i < L; ++i) {
+    if (tile >= tt.first[i]) {
+      Wq = lt.W[i];
+      Hq = lt.H[i];
+      startq = lt.start[i];
+      firstq = tt.first[i];
+      tilesxq = tt.tiles_x[i];
+    }
+  }
+  const int t = tile - firstq;
+  const int ty = t / tilesxq, tx = t - ty * tilesxq;
   const int tile_w = 1 << tile_w_log2, tile_h = 32 >> tile_w_log2;
   const int qx0 = tx * tile_w + (tq & (tile_w - 1));
   const int qy0 = ty * tile_h + (tq >> tile_w_log2);
-  const bool valid = qx0 < lt.W[lq] && qy0 < lt.H[lq];
+  const bool valid = qx0 < Wq && qy0 < Hq;
   // out-of-tile units run on a clamped query (the shuffles below need every lane) and skip the store
-  const int qx = min(qx0, lt.W[lq] - 1), qy = min(qy0, lt.H[lq] - 1);
-  const int q = lt.start[lq] + qy * lt.W[lq] + qx;
+  const int qx = min(qx0, Wq - 1), qy = min(qy0, Hq - 1);
+  const int q = startq + qy * Wq + qx;
   const long long nq = (long long)n * S + q;
-  const float refx = ((float)qx + 0.5f) / (float)lt.W[lq];
-  const float refy = ((float)qy + 0.5f) / (float)lt.H[lq];
+  const float refx = ((float)qx + 0.5f) / (float)Wq;
+  const float refy = ((float)qy + 0.5f) / (float)Hq;
   const float* row = ol + nq * (long long)(M * LP * 3);
   const int pix_stride = M * 32;
 
@@ -427,7 +436,17 @@ msda_encoder_staged_kernel(const float* __restrict__ value, LevelTable lt, TileT
     const int pp = lane8 + 8 * k;
     if (pp < LP) {
       const int l = pp / P;
-      const int H = lt.H[l], W = lt.W[l];
+      // explicit selects over the L levels: indexing the by-value table with a run-time level compiles to a long
+      // compare / select chain over all kMaxLevels entries (ncu: 264 uniform compares in this kernel)
+      int H = lt.H[0], W = lt.W[0], lbase = lt.start[0];
+#pragma unroll
+      for (int i = 1; i < L; ++i) {
+        if (l == i) {
+          H = lt.H[i];
+          W = lt.W[i];
+          lbase = lt.start[i];
+        }
+      }
       const float locx = refx + ox[k] / (float)W;
       const float locy = refy + oy[k] / (float)H;
       const float x = locx * (float)W - 0.5f, y = locy * (float)H - 0.5f;
@@ -444,7 +463,6 @@ msda_encoder_staged_kernel(const float* __restrict__ value, LevelTable lt, TileT
       const float w3 = (inside && y1ok && x0ok) ? ly * hx : 0.f;
       const float w4 = (inside && y1ok && x1ok) ? ly * lx : 0.f;
       const float aw = e[k] * inv;
-      const int lbase = lt.start[l];
       s_off[tq][pp] = make_int4((lbase + yc0 * W + xc0) * pix_stride, (lbase + yc0 * W + xc1) * pix_stride,
                                 (lbase + yc1 * W + xc0) * pix_stride, (lbase + yc1 * W + xc1) * pix_stride);
       s_w[tq][pp] = make_float4(aw * w1, aw * w2, aw * w3, aw * w4);
