@@ -192,6 +192,7 @@ def test_mha_tc(B, Lq, Lk, C, masked, flags):
     assert _rel(got, ref) < 2e-5
 
 
+@pytest.mark.gpu
 @_gpu_mhatc
 @pytest.mark.parametrize("Lq,masked", [(1000, False), (1000, True), (1160, True), (300, True)])
 def test_self_attention_shape_through_query_chunks(Lq, masked, monkeypatch):

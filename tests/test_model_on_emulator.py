@@ -158,12 +158,15 @@ def test_default_path_clip_forward_on_the_emulator(monkeypatch, tmp_path):
     Category prompts (ProCA) included."""
     _cpu_fp16_gemm(monkeypatch)
     monkeypatch.setattr(nn_ops, "_inplace16", [None])
+    monkeypatch.setattr(nn_ops, "_gemm_tc", False)      # the library-GEMM formulation: row-wise GELU / ReLU / split kernels in use
+    monkeypatch.setattr(nn_ops, "_fused_glue", False)
     lib_path = str(tmp_path / "libunivs_emu_default.so")
     shutil.copy(build_emu.build(), lib_path)
     T, Q = 2, 6
     swin = dict(embed_dim=32, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8], window_size=4)
     parts = mf.build_product_model(swin, num_queries=Q, num_frames=T, clip_emb=mf.make_clip_emb(), enc_layers=1, dec_layers=2)
     mf.load_keyed(parts)
+    parts[2].pooled_masks = False           # this test binds the round-1 operator set only (pooled heads: the test below)
     shapes = {f"res{i + 2}": ShapeSpec(channels=32 * 2 ** i, stride=4 * 2 ** i) for i in range(4)}
     head = MaskFormerHead(shapes, num_classes=133, pixel_decoder=parts[1], transformer_predictor=parts[2])
     model = UniVS_Prompt(backbone=parts[0], sem_seg_head=head, pixel_mean=MEAN, pixel_std=STD)

@@ -31,21 +31,29 @@ def run_boundaries(masks):
 
 
 def counts_to_string(cnts):
-    """maskApi.c rleToString on a sequence of run lengths"""
-    out = bytearray()
-    cnts = [int(c) for c in cnts]
-    for i, x in enumerate(cnts):
-        if i > 2:
-            x -= cnts[i - 2]
-        more = True
-        while more:
-            c = x & 0x1F
-            x >>= 5
-            more = (x != -1) if (c & 0x10) else (x != 0)
-            if more:
-                c |= 0x20
-            out.append(c + 48)
-    return out.decode("ascii")
+    """maskApi.c rleToString on a sequence of run lengths: value i > 2 is coded as the difference to value i - 2; every value
+    as little-endian groups of 5 data bits + a continuation bit, offset 48.  Vectorised over the runs (a noisy mask has
+    hundreds of thousands of them; the per-run Python loop made the RLE output 7x slower than copying dense masks)."""
+    c = np.asarray(cnts, dtype=np.int64).reshape(-1)
+    if c.size == 0:
+        return ""
+    x = c.copy()
+    if c.size > 3:
+        x[3:] -= c[1:-2]
+    chars = np.zeros((c.size, 13), dtype=np.uint8)          # 64-bit values need at most 13 groups
+    used = np.zeros(c.size, dtype=np.int64)
+    alive = np.ones(c.size, dtype=bool)
+    for k in range(13):
+        g = x & 0x1F
+        x = x >> 5                                           # arithmetic shift, like the C code on a signed long
+        more = np.where((g & 0x10) != 0, x != -1, x != 0)
+        ch = (g | np.where(more, 0x20, 0)) + 48
+        chars[alive, k] = ch[alive]
+        used[alive] += 1
+        alive &= more
+        if not alive.any():
+            break
+    return chars[np.arange(13)[None, :] < used[:, None]].tobytes().decode("ascii")
 
 
 def encode(masks):
