@@ -198,45 +198,6 @@ def run_cpu_reference(args, workload, steps, warmup, as_line):
     }
 
 
-def run_torch_eager_gpu(args):
-    """Informative arm (SURVEY.md 8d "GPU-side reference"): the reference algorithm on the SAME B200 through torch's
-    library kernels -- the product host model with every hot-path operator replaced by its torch restatement
-    (oracle/ops_ref.py: F.grid_sample MSDeformAttn, matmul / softmax attention, einsum), eager, fp32 with torch's default
-    TF32 settings.  What "beat torch library dispatch on the same GPU" is measured against; not a parity-checked path."""
-    try:
-        from oracle.cpu_backend import oracle_ops
-        from univs_b200.build import build_model, make_cfg
-        variant, T, H, W, Q = WORKLOADS[args.workload]
-        dev = torch.device("cuda", 0)
-        g = torch.Generator().manual_seed(0)
-        cfg = make_cfg(variant, Q, T, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
-        model = build_model(cfg).to(dev)
-        frames = (torch.rand(T, 3, H, W, generator=g) * 255).to(dev)
-        torch.backends.cudnn.allow_tf32 = True           # torch's shipped defaults
-        torch.backends.cuda.matmul.allow_tf32 = False
-        steps, warmup = max(1, min(args.steps, 5)), 2
-        with oracle_ops():
-            for _ in range(warmup):
-                model.clip_forward(frames, make_targets(T, dev))
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(steps):
-                model.clip_forward(frames, make_targets(T, dev))
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        return {"impl": "torch-eager", "metric": "frames/sec (Swin-L 720p T=5 Q=200)" if args.workload == "ns" else "frames/sec (per-clip forward)",
-                "value": T / (ms / 1e3), "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms,
-                "higher_is_better": True, "dtype": "f32 (torch defaults: IEEE matmul, TF32 cuDNN)", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init",
-                           "execution": "eager, torch library kernels (port of the reference algorithm)"}}
-    except Exception as e:  # noqa: BLE001
-        import traceback
-        where = " <- ".join(f"{fr.filename.split('/')[-1]}:{fr.lineno}" for fr in traceback.extract_tb(e.__traceback__)[-4:])
-        return {"impl": "torch-eager", "unavailable": f"{type(e).__name__}: {str(e)[:300]} [{where}]"}
-
-
 def run_prompt_workload(args, dev):
     """BASELINE configs[2] / configs[3]: one step = the per-clip forward of a clip WITH prompts (ProCA path).  sot: the
     visual-prompt memory has been grown by the preceding stride-1 clips (kv length 1 + R * (1 + frames in the pool)); every
@@ -333,8 +294,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-eager"],
-                    help="reference: the CPU arm; torch-eager (informative): the same port on the GPU's torch LIBRARY kernels")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ns", choices=list(WORKLOADS) + list(PROMPT_WORKLOADS))
     ap.add_argument("--video-frames", type=int, default=0,
                     help="> 0: secondary benchmark (SURVEY 8f rank 1) -- the VIS sliding-window head over a synthetic video of this "
@@ -355,10 +315,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    if args.impl == "torch-eager":
-        if rank == 0:
-            print(json.dumps(run_torch_eager_gpu(args)))
-        return
     if args.impl == "reference":
         if rank == 0:
             print(json.dumps(run_cpu_reference(args, args.workload, max(1, args.steps), max(0, args.warmup), True)))

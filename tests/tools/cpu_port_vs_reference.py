@@ -1,7 +1,7 @@
 """Calibration of bench.py's CPU arm (kind "port": product host logic + oracle/ops_ref.py operators) against the REFERENCE'S
 OWN FILES loaded by path (oracle/ref_shim.py; needs /root/reference, i.e. the development container): same weights, same
 clip, same thread count, fp32.  BASELINE config C2 geometry (Swin-T, 480x864, Q=100) at T frames (default 2).
-  python tools/cpu_port_vs_reference.py [T]        -> one JSON line (recorded in BASELINE.md)"""
+  python tests/tools/cpu_port_vs_reference.py [T]        -> one JSON line (recorded in BASELINE.md)"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ref_shim                      # noqa: E402
 from oracle.cpu_backend import oracle_ops        # noqa: E402
 from tests import model_factory as mf            # noqa: E402

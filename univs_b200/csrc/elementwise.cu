@@ -214,6 +214,7 @@ layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ res
   const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
   const float sc = (split == -2) ? 1.f : 2048.f;
   const int kc = -split;
+  const bool two_blocks = split == -2 || split == -3;      // [hi | lo] containers: no hi * 2^-11 copy to compute or exchange
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + i * 32;
@@ -231,14 +232,20 @@ layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ res
         hi[e] = pack_sat_h2(o[2 * e], o[2 * e + 1]);
         const float2 hf = unpack_h2(hi[e]);
         lo[e] = pack_sat_h2((o[2 * e] - hf.x) * sc, (o[2 * e + 1] - hf.y) * sc);
-        const __half2 s2 = __floats2half2_rn(hf.x * (1.f / 2048.f), hf.y * (1.f / 2048.f));
-        hs[e] = *reinterpret_cast<const uint32_t*>(&s2);
+        if (!two_blocks) {
+          const __half2 s2 = __floats2half2_rn(hf.x * (1.f / 2048.f), hf.y * (1.f / 2048.f));
+          hs[e] = *reinterpret_cast<const uint32_t*>(&s2);
+        }
       }
     }
     // every lane takes part in the exchange; even lanes store their own four halves followed by the odd neighbour's
     const uint32_t nh0 = __shfl_down_sync(0xffffffffu, hi[0], 1), nh1 = __shfl_down_sync(0xffffffffu, hi[1], 1);
     const uint32_t nl0 = __shfl_down_sync(0xffffffffu, lo[0], 1), nl1 = __shfl_down_sync(0xffffffffu, lo[1], 1);
-    const uint32_t ns0 = __shfl_down_sync(0xffffffffu, hs[0], 1), ns1 = __shfl_down_sync(0xffffffffu, hs[1], 1);
+    uint32_t ns0 = 0u, ns1 = 0u;
+    if (!two_blocks) {                               // uniform branch (kernel argument)
+      ns0 = __shfl_down_sync(0xffffffffu, hs[0], 1);
+      ns1 = __shfl_down_sync(0xffffffffu, hs[1], 1);
+    }
     if (has && (lane & 1) == 0) {
       const int col = idx * 4;                       // multiple of 8
       if (split == -2 || split == -3) {              // [hi | lo] / [hi | lo*2^11]
