@@ -76,6 +76,31 @@ def test_gemm_tc_kernel_chunk3_operands(monkeypatch, emu_lib_path, tmp_path, M, 
     assert torch.equal(y16[:, :N], plain(y).half().float())
 
 
+@pytest.mark.parametrize("M,N,K,sms", [
+    (200, 256, 128, 4),       # 2 token tiles x 1 channel pair on 2 clusters
+    (300, 260, 192, 2),       # 3 channel tiles: the second CTA of the last pair repeats tile 2 and stores nothing; one cluster
+    (130, 520, 320, 6),       # 5 channel tiles, K tail, ring wrap-around on 3 clusters
+])
+def test_gemm_tc_cluster_multicast_variant(monkeypatch, emu_lib_path, tmp_path, M, N, K, sms):
+    """UNIVS_GEMM_MC=1: pairs of CTAs share the activation tile by TMA multicast; results equal the one-CTA kernel's bit for bit
+    (same MMA sequence per tile)."""
+    _use(monkeypatch, emu_lib_path, sms, tmp_path)
+    g = torch.Generator().manual_seed(M * N + K)
+    x, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    x3, w3 = _chunk3(x), _chunk3(w * 256.0)
+    offs = (2 * K, 0)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("UNIVS_GEMM_MC", mode)
+        y, y16 = ops.gemm_f16x3_tc(dev(x3), offs, dev(w3), offs, K, 2.0 ** -8, dev(bias), dev(add), want_f32=True,
+                                   want_operand=True, act=1)
+        outs[mode] = (plain(y).clone(), plain(y16).clone())
+    assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
+    wy, _ = ops_ref.gemm_f16x3(x3, offs, w3, offs, K, 2.0 ** -8, bias, add, 1)
+    assert _rel(outs["1"][0], wy) < 2e-6
+
+
 def test_gemm_tc_compact_operand_k_slices_and_row_views(monkeypatch, emu_lib_path, tmp_path):
     """fc1 -> GELU -> operand, then fc2 over the compact container in two K slices accumulated in place, on row views"""
     _use(monkeypatch, emu_lib_path, 3, tmp_path)

@@ -173,7 +173,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[kCh], const 
   }
 }
 
-template <int ACT, bool OUT32, bool OUT16, bool ADD>
+// MC (round 2, compute-bound layers): a cluster of two CTAs works on two CHANNEL tiles of the same token tile.  The 128-token
+// activation tile both need arrives by TMA multicast -- each CTA fetches 64 of its rows (hi and lo') and the boxes land in
+// both CTAs' shared memory -- so a CTA pulls 48 KB instead of 64 KB per k-block out of L2.  (The experiment behind it: the
+// one-CTA kernel runs the K >= 768 layers at 1.15-1.2 PFLOP/s whatever their shape, i.e. 98 flop per L2 byte x ~12 TB/s, which
+// suggested an L2 read bound.  The variant cut L2 reads by a quarter and gained nothing, which rules that out; what remains is
+// the power-capped tensor pipe -- cuBLAS bf16 sustains 1.36 PFLOP/s on the same box, MEASURED_PEAKS.json -- and the per-SM
+// delivery of 64 KB per k-block, which multicast does not reduce.  Kept as a switch, off by default.)  A stage is refilled only after BOTH CTAs consumed it (tcgen05.commit multicast on an `empty`
+// barrier of count 2: the peer's multicast writes into my shared memory); each CTA runs the one-CTA MMA sequence into its own
+// TMEM and its own epilogue.  With an odd number of channel tiles the second CTA of the last pair repeats the last tile and
+// skips the stores.  Protocol as in mask_einsum_mc.cu.
+template <int ACT, bool OUT32, bool OUT16, bool ADD, bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                      const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const Args a) {
@@ -188,13 +198,18 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_ct = (a.N + kBM - 1) / kBM;
   const int n_tt = (a.M + kBT - 1) / kBT;
-  const int num_tiles = n_ct * n_tt;
   const int kblocks = (a.K + kBK - 1) / kBK;
+  // work items: tiles (one CTA) or pairs of channel tiles of one token tile (cluster of two), channel index fastest
+  const int rank = MC ? (int)cluster_rank() : 0;
+  const int n_cu = MC ? (n_ct + 1) / 2 : n_ct;             // channel units per token tile
+  const int num_items = n_cu * n_tt;
+  const int item0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], MC ? 2 : 1);                    // MC: both CTAs' MMAs must have retired (the peer writes my stage too)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -207,6 +222,7 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
   fence_before();
   __syncthreads();
   fence_after();
+  if (MC) cluster_sync_all();           // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -214,16 +230,23 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tt = tile / n_ct, ct = tile - tt * n_ct;
+      for (int item = item0; item < num_items; item += item_step) {
+        const int tt = item / n_cu, cu = item - tt * n_cu;
+        const int ct = MC ? min(2 * cu + rank, n_ct - 1) : cu;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 10 + stage);
           const uint32_t s0 = smem_u32(smem + (size_t)stage * kStageBytes);
           mbar_expect_tx(&full[stage], (uint32_t)kStageBytes);     // a box always counts in full (out-of-range parts are zero-filled)
           tma_load_3d(s0, &map_wh, &full[stage], kb * kBK, ct * kBM, 0);
           tma_load_3d(s0 + kTileBytes, &map_wl, &full[stage], kb * kBK, ct * kBM, 0);
-          tma_load_3d(s0 + 2 * kTileBytes, &map_xh, &full[stage], kb * kBK, tt * kBT, 0);
-          tma_load_3d(s0 + 3 * kTileBytes, &map_xl, &full[stage], kb * kBK, tt * kBT, 0);
+          if (MC) {     // my 64 rows of the activation tile (map_x*: 64-row boxes) into BOTH CTAs; the peer sends the other 64
+            const uint32_t half = (uint32_t)rank * (uint32_t)(kTileBytes / 2);
+            tma_load_3d_multicast(s0 + 2 * kTileBytes + half, &map_xh, &full[stage], kb * kBK, tt * kBT + rank * (kBT / 2), 0, (uint16_t)0x3);
+            tma_load_3d_multicast(s0 + 3 * kTileBytes + half, &map_xl, &full[stage], kb * kBK, tt * kBT + rank * (kBT / 2), 0, (uint16_t)0x3);
+          } else {
+            tma_load_3d(s0 + 2 * kTileBytes, &map_xh, &full[stage], kb * kBK, tt * kBT, 0);
+            tma_load_3d(s0 + 3 * kTileBytes, &map_xl, &full[stage], kb * kBK, tt * kBT, 0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -241,7 +264,7 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = item0; item < num_items; item += item_step) {
       mbar_wait(&tempty[acc], acc_phase ^ 1, 20 + acc);
       fence_after();
       const uint32_t d_main = tmem_base + (uint32_t)acc * kColsPerStage;
@@ -259,7 +282,8 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
             umma_f16(d_main, wh + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc2, first);  // [main | corr] (+)= Wh * [Xh ; Xl']^T
             umma_f16(d_corr, wl + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc, 1u);      // corr += Wl' * Xh^T
           }
-          umma_commit(&empty[stage]);                       // frees the stage when these MMAs retire
+          if (MC) umma_commit_multicast(&empty[stage], (uint16_t)0x3);   // frees the stage in both CTAs when these MMAs retire
+          else umma_commit(&empty[stage]);                  // frees the stage when these MMAs retire
           if (kb == kblocks - 1) umma_commit(&tfull[acc]);  // both accumulators complete -> epilogue
         }
         __syncwarp();
@@ -276,8 +300,9 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
     const int part = ew >> 2;    // token columns [32 * part, 32 * part + 32)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tt = tile / n_ct, ct = tile - tt * n_ct;
+    for (int item = item0; item < num_items; item += item_step) {
+      const int tt = item / n_cu, cu = item - tt * n_cu;
+      const int ct = MC ? 2 * cu + rank : cu;               // MC, odd n_ct: the repeated last tile has ct == n_ct -> n >= N, no stores
       const int n = ct * kBM + wq * 32 + lane;              // this thread's output channel
       const bool n_ok = n < a.N;
       const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
@@ -309,6 +334,7 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
   }
   fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();           // no CTA leaves while the peer may still multicast into it / signal its barriers
   if (warp == 2) {
     fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -333,18 +359,52 @@ static EncodeTiledFn encoder() {
 
 // fp16 window [rows][K] of a row-major tensor with `pitch` halfs per row; box [64 halfs][128 rows], SWIZZLE_128B; rows and
 // columns beyond the window read as zeros
-static int make_map(CUtensorMap* m, const __half* base, long long rows, int K, long long pitch) {
+static int make_map(CUtensorMap* m, const __half* base, long long rows, int K, long long pitch, int box_rows = 128) {
   EncodeTiledFn enc = encoder();
   if (!enc) { set_error("gemm_f16x3_tc: cuTensorMapEncodeTiled entry point unavailable"); return UNIVS_E_LAUNCH; }
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 1};
   cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)kBK, 128, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("gemm_f16x3_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return UNIVS_E_LAUNCH; }
   return 0;
+}
+
+// cluster launch: persistent pairs of CTAs, as many as can be co-resident (a GPC with an odd number of free SMs leaves one out)
+template <typename Kern>
+static int launch_mc(Kern kern, int num_sms, long long pairs, cudaStream_t st, const CUtensorMap& mwh, const CUtensorMap& mwl,
+                     const CUtensorMap& mxh, const CUtensorMap& mxl, const Args& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int resident = 0;       // the same for every epilogue variant: one CTA per SM, same shared memory
+  if (!resident) {
+    cfg.gridDim = dim3((unsigned)(2 * (num_sms / 2)));
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n < 1) {
+      set_error("gemm_f16x3_tc: cudaOccupancyMaxActiveClusters: %s (%d clusters)", cudaGetErrorString(e), n);
+      (void)cudaGetLastError();
+      return UNIVS_E_LAUNCH;
+    }
+    resident = n < num_sms / 2 ? n : num_sms / 2;
+  }
+  const long long clusters = resident < pairs ? resident : pairs;
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mwh, mwl, mxh, mxl, a);
+  if (e != cudaSuccess) { set_error("gemm_f16x3_tc: cluster launch: %s", cudaGetErrorString(e)); return UNIVS_E_LAUNCH; }
+  return check_launch("gemm_f16x3_tc");
 }
 
 }  // namespace gemmtc
@@ -377,8 +437,17 @@ extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, i
   int rc;
   if ((rc = make_map(&mwh, w + w_hi_off, channels, k, ldw))) return rc;
   if ((rc = make_map(&mwl, w + w_lo_off, channels, k, ldw))) return rc;
-  if ((rc = make_map(&mxh, x + x_hi_off, tokens, k, ldx))) return rc;
-  if ((rc = make_map(&mxl, x + x_lo_off, tokens, k, ldx))) return rc;
+  // cluster variant (see the kernel).  Measured on the B200 (tools/gemm_tc_mc.py, profiles/r2_gemm_mc.txt): bit-identical
+  // results, but equal or slower at every Swin-L layer shape (sum over the shapes 1872 us -> 2008 us) -- the operand stream
+  // out of L2 is NOT what holds the one-CTA kernel at 1.15-1.2 PFLOP/s.  UNIVS_GEMM_MC=1 selects it (measurement switch);
+  // mode 2 is the heuristic that was tried (deep K, >= 2 channel tiles, enough pairs to fill the SMs).
+  const char* mc_env = getenv("UNIVS_GEMM_MC");        // read per call: the tests toggle it
+  const int mc_mode = mc_env ? (atoi(mc_env) ? 1 : 0) : 0;      // default off: measured no faster on the B200 (see above)
+  const int n_ct_h = (channels + kBM - 1) / kBM;
+  const long long n_tt_h = (tokens + kBT - 1) / kBT;
+  const bool mc = mc_mode == 1 ? n_ct_h >= 2 : (mc_mode == 2 && k >= 512 && n_ct_h >= 2 && (long long)((n_ct_h + 1) / 2) * n_tt_h >= 74);
+  if ((rc = make_map(&mxh, x + x_hi_off, tokens, k, ldx, mc ? kBT / 2 : kBT))) return rc;
+  if ((rc = make_map(&mxl, x + x_lo_off, tokens, k, ldx, mc ? kBT / 2 : kBT))) return rc;
   Args a;
   a.M = (int)tokens; a.N = channels; a.K = k; a.alpha = alpha; a.bias = bias; a.addend = addend; a.ldadd = ldadd;
   a.out = out; a.ldo = ldo; a.out16 = reinterpret_cast<__half*>(out16); a.ld16 = ld16; a.lo_off16 = out16_lo_off;
@@ -389,8 +458,9 @@ extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const long long tiles = (long long)((channels + kBM - 1) / kBM) * ((tokens + kBT - 1) / kBT);
+  const long long tiles = (long long)n_ct_h * n_tt_h;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  const long long pairs = (long long)((n_ct_h + 1) / 2) * n_tt_h;
   cudaStream_t st = (cudaStream_t)stream;
   const bool o32 = out != nullptr, o16 = out16 != nullptr, add = addend != nullptr;
   // the epilogue variants the path uses are compiled; anything else is a caller error
@@ -398,12 +468,16 @@ extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, i
   if (activation == ACT && o32 == O32 && o16 == O16 && add == ADDF) {                                                          \
     static bool attr_set = false;                                                                                              \
     if (!attr_set) {                                                                                                           \
-      cudaError_t e = cudaFuncSetAttribute(gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           kSmemBytes);                                                                        \
+      cudaError_t e = cudaFuncSetAttribute(gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF, false>,                                   \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);                           \
+      if (e == cudaSuccess)                                                                                                    \
+        e = cudaFuncSetAttribute(gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 kSmemBytes);                                                                                  \
       if (e != cudaSuccess) { set_error("gemm_f16x3_tc: cudaFuncSetAttribute(%d): %s", kSmemBytes, cudaGetErrorString(e)); return UNIVS_E_LAUNCH; } \
       attr_set = true;                                                                                                         \
     }                                                                                                                          \
-    gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF><<<grid, kThreads, kSmemBytes, st>>>(mwh, mwl, mxh, mxl, a);                         \
+    if (mc) return launch_mc(gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF, true>, num_sms, pairs, st, mwh, mwl, mxh, mxl, a);        \
+    gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF, false><<<grid, kThreads, kSmemBytes, st>>>(mwh, mwl, mxh, mxl, a);                  \
     return check_launch("gemm_f16x3_tc");                                                                                      \
   }
   UNIVS_GEMM_CASE(0, true, false, false)      // plain dense layer
