@@ -44,6 +44,33 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def tensor_peak():
+    """Dense tensor denominator for a kernel timed inside a long step: the SUSTAINED cuBLAS bf16 rate (B200_PROFILING.md)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured (cuBLAS bf16, sustained under the power cap)"
+    return 1400.0, "fallback (sustained)"
+
+
+def dense_layer_roofline(kernel_ms, kernel_calls, flops_per_step):
+    """Tensor roofline of the dense-layer kernel (csrc/gemm_tc.cu), the kernel most of the step's time is spent in.
+    `achieved` = ALGORITHMIC flops (2*M*N*K of every launch of a step: the fp32 products the reference computes) over the
+    launches' CUDA-event time; `executed` = the fp16 MMA flops the strict hi|lo policy issues for them (3 products per
+    algorithmic one) -- the number that says how busy the tensor pipe is."""
+    if "gemm_f16x3_tc" not in kernel_ms or not flops_per_step:
+        return None
+    peak, kind = tensor_peak()
+    ms = kernel_ms["gemm_f16x3_tc"] * kernel_calls["gemm_f16x3_tc"]
+    ach = flops_per_step / (ms * 1e-3) / 1e12
+    return {"kernel": "gemm_f16x3_tc", "bound": "tensor", "achieved": ach, "peak": peak, "peak_kind": kind, "unit": "TFLOP/s",
+            "frac": ach / peak, "executed": 3 * ach, "frac_executed": 3 * ach / peak,
+            "note": "strict fp16 hi|lo policy: 3 tensor-core products per fp32-equivalent product (parity bound 1e-3 rules out 1 pass)",
+            "launches_per_step": kernel_calls["gemm_f16x3_tc"], "ms_per_step": ms,
+            "algorithmic_flops_per_step": float(flops_per_step), "traffic": None}
+
+
 class ClockSampler:
     """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
 
@@ -306,6 +333,9 @@ def main():
     ap.add_argument("--shard-decoder", action="store_true",
                     help="N>1: keep the decoder frame-sharded and exchange query tokens per layer instead of all-gathering "
                          "the pixel features (also UNIVS_SHARD_DECODER=1)")
+    ap.add_argument("--frames", type=int, default=0,
+                    help="diagnostic: override the workload's T (e.g. --frames 1 on one GPU = the compute share of one rank of "
+                         "an 8-GPU run, without the exchange); the line's config.workload says so -- not a headline number")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: after warm-up run ONE step between cudaProfilerStart/Stop and exit "
                          "(use with `ncu --profile-from-start off`); prints no bench line")
@@ -346,6 +376,8 @@ def main():
         return run_prompt_workload(args, dev)
 
     variant, T, H, W, Q = WORKLOADS[args.workload]
+    if args.frames > 0:
+        T = args.frames
     g = torch.Generator().manual_seed(0)
     cfg = make_cfg(variant, Q, T, clip_emb=torch.randn(3938, 640, generator=g), TEXT_PROMPT_TO_IMAGE_ENABLE=False)
     model = build_model(cfg, process_group=group).to(dev)
@@ -463,6 +495,7 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in sink.items()}
     kernel_calls = {k: len(v) // steps for k, v in sink.items()}
+    dense = dense_layer_roofline(kernel_ms, kernel_calls, ops.flop_count.get("gemm_f16x3_tc", 0) // steps)
     ops.profile_events(False)
 
     # ---- end-to-end through the public API with host buffers ------------------------------------------------
@@ -527,11 +560,13 @@ def main():
                 cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                        "sample": f"failed: {str(e)[:200]}"}
         line = {
-            "metric": "frames/sec (Swin-L 720p T=5 Q=200)" if args.workload == "ns" else "frames/sec (per-clip forward)",
+            "metric": ("frames/sec (Swin-L 720p T=5 Q=200)" if args.workload == "ns" and not args.frames
+                       else "frames/sec (per-clip forward)"),
             "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"fp16x3": "fp16x3 (2-term fp16 split operands, fp32-equivalent products, fp32 accumulate)", "tf32x3": "tf32x3 (3-pass TF32 split, fp32-equivalent products, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init",
+            "config": {"workload": f"{args.workload}: Swin-{variant} T={T} {H}x{W}->pad32 Q={Q} detection, no prompts, random init"
+                                   + (" [DIAGNOSTIC --frames override of the workload's T]" if args.frames else ""),
                        "precision": args.precision, "parallelism": (f"frame-shard x{world}" + (", frame-sharded decoder (token all-gather per layer)"
                                                                   if model.shard_decoder else ", feature all-gather"))
                        if world > 1 else "single",
@@ -544,7 +579,10 @@ def main():
             "e2e": {"value": T / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches,
-            "roofline": roof,
+            # the DOMINANT kernel of the step (dense layers: ~57 % of the NS step) against the tensor roofline; the mask
+            # einsum -- SURVEY 8(d) metric (ii), the kernel BASELINE.json's north star names -- against the HBM roofline
+            "roofline": dense if dense is not None else roof,
+            "roofline_mask_einsum": roof,
             "named_kernel_rooflines": named,        # algorithmic bytes per clip / event time per clip, vs the same HBM peak
             "kernels": {k: {"ms_per_launch": kernel_ms[k], "launches_per_step": kernel_calls[k]} for k in sorted(kernel_ms)},
             "cpu_baseline": cpu,

@@ -73,3 +73,18 @@ def test_round2_report_promotes_only_green_and_faster_switches(tmp_path):
     codes, base, rows, promote = rep.report(str(d), 0.3)
     assert base["ms_per_step"] == 52.9 and codes["mhatc_tests"] == 1
     assert promote == {"WIN_TC": 1}
+
+
+def test_dense_layer_roofline_is_algorithmic_flops_over_event_time():
+    """bench.py `roofline` (dominant kernel): achieved = sum of 2*M*N*K of a step's dense-layer launches / their CUDA-event time;
+    `executed` counts the three fp16 products the strict policy issues per algorithmic product."""
+    r = bench.dense_layer_roofline({"gemm_f16x3_tc": 0.08}, {"gemm_f16x3_tc": 250}, 7.0e12)
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["kernel"] == "gemm_f16x3_tc"
+    assert abs(r["ms_per_step"] - 20.0) < 1e-9 and abs(r["achieved"] - 350.0) < 1e-6
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and abs(r["executed"] - 3 * r["achieved"]) < 1e-9
+    assert abs(r["frac_executed"] - 3 * r["frac"]) < 1e-12 and r["traffic"] is None
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        assert r["peak"] == json.load(open(peaks_file))["bf16_tflops_sustained"] and r["peak_kind"].startswith("measured")
+    # no dense-layer brackets (library-GEMM policies, CPU dry run): no object
+    assert bench.dense_layer_roofline({"mask_einsum": 0.1}, {"mask_einsum": 1}, 0) is None

@@ -475,19 +475,18 @@ class VideoMultiScaleMaskedTransformerDecoderUniVS(nn.Module):
             feats_cl = feats_cl.contiguous()
         feats_raw = feats_cl.view(t, h_m * w_m, c_m)
         feats_cl = ops.prepare_mask_features(feats_raw)
-        if "frame_indices" in targets[0]:
-            frame_indices = targets[0]["frame_indices"]
-        else:
-            frame_indices = torch.arange(t_all, device=device)
+        # the temporal term of the position encoding is the same for the three levels: once per clip (cached for host-side
+        # or default frame indices)
+        pz = position.temporal_sine(targets[0].get("frame_indices", t_all), device, self.level_embed.weight.shape[1] // 2)
         if exchange is not None:
-            frame_indices = frame_indices.to(device).index_select(0, exchange.frames_tensor(device))
+            pz = pz.index_select(0, exchange.frames_tensor(device))
         src, pos, size_list = [], [], []
         for i in range(3):
             n, c, h, w = x[i].shape
             size_list.append((h, w))
             xi = x[i].permute(0, 2, 3, 1).reshape(n, h * w, c)              # token-major (view when channel-last)
             src.append(xi + self.level_embed.weight[i])
-            pos.append(position.sine_3d_arbitrary_t(frame_indices, h, w, device, c // 2))
+            pos.append(position.sine_3d_arbitrary_t(None, h, w, device, c // 2, pz=pz))
         nq = self.num_queries
         out = self.query_feat.weight[None].expand(t, -1, -1).contiguous()   # [T,Q,C]
         qpos = self.query_embed.weight[None].expand(t, -1, -1).contiguous()

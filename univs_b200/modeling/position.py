@@ -32,13 +32,36 @@ def sine_2d(h, w, device, num_pos_feats=128, temperature=10000.0):
     return _cache[key]
 
 
-def sine_3d_arbitrary_t(frame_indices, h, w, device, num_pos_feats=128, temperature=10000.0, num_max_frames=128):
-    """-> [T, h*w, 2*num_pos_feats]"""
-    base = sine_2d(h, w, device, num_pos_feats, temperature)
+def temporal_sine(frame_indices, device, num_pos_feats=128, temperature=10000.0, num_max_frames=128):
+    """The z (frame) term of the 3-D encoding -> [T, 2*num_pos_feats].  It does not depend on the level: the decoder
+    computes it once per clip and shares it between the three memory levels.  Frame indices that live on the host (or the
+    default 0..T-1, passed as an int) key a cache, so a steady stream of clips launches nothing for it."""
+    key = None
+    if isinstance(frame_indices, int):
+        key = ("z", tuple(range(frame_indices)), str(device), num_pos_feats)
+    elif not frame_indices.is_cuda:
+        key = ("z", tuple(int(v) for v in frame_indices.tolist()), str(device), num_pos_feats)
+    if key is not None and key in _cache:
+        return _cache[key]
+    if isinstance(frame_indices, int):
+        frame_indices = torch.arange(frame_indices)
     z = frame_indices.to(device=device, dtype=torch.float32) / num_max_frames * (2 * math.pi)
     dz = _dim_t(2 * num_pos_feats, temperature, device)
     pz = z[:, None] / dz
     pz = torch.stack((pz[:, 0::2].sin(), pz[:, 1::2].cos()), 2).flatten(1)        # [T, C]
+    if key is not None:
+        if len(_cache) > 256:           # sliding-window heads walk through many index tuples
+            for k in [k for k in _cache if k[0] == "z"]:
+                del _cache[k]
+        _cache[key] = pz
+    return pz
+
+
+def sine_3d_arbitrary_t(frame_indices, h, w, device, num_pos_feats=128, temperature=10000.0, num_max_frames=128, pz=None):
+    """-> [T, h*w, 2*num_pos_feats]; `pz` = temporal_sine(frame_indices, ...) when the caller already has it"""
+    base = sine_2d(h, w, device, num_pos_feats, temperature)
+    if pz is None:
+        pz = temporal_sine(frame_indices, device, num_pos_feats, temperature, num_max_frames)
     return base[None] + pz[:, None, :]
 
 

@@ -19,12 +19,14 @@ _default_precision = PREC_TF32X3
 # ---- optional instrumentation (bench.py): launch counter + per-kernel CUDA-event brackets --------------------
 launch_count = 0          # number of univs_b200 kernels launched through this module
 _event_sink = None        # None, or dict name -> list[(start_event, end_event)]
+flop_count = {}           # while the event brackets are on: name -> algorithmic flops (2*M*N*K per dense-layer launch)
 
 
 def profile_events(enable: bool):
     """When enabled every wrapper brackets its launch(es) with CUDA events on the current stream."""
     global _event_sink
     _event_sink = {} if enable else None
+    flop_count.clear()
     return _event_sink
 
 
@@ -435,6 +437,8 @@ def gemm_f16x3_tc(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None
     out16 = torch.empty((M, 2 * N), device=x16.device, dtype=torch.float16) if want_operand else None
     if M == 0:
         return out, out16
+    if _event_sink is not None:
+        flop_count["gemm_f16x3_tc"] = flop_count.get("gemm_f16x3_tc", 0) + 2 * int(x16.shape[0]) * int(w16.shape[0]) * int(k)
     with _Bracket("gemm_f16x3_tc", 1):
         rc = lib().univs_gemm_f16x3_tc(
             _stream(), xp, x16.stride(0), int(x_offs[0]), int(x_offs[1]), wp, w16.stride(0), int(w_offs[0]), int(w_offs[1]),
