@@ -194,7 +194,7 @@ def test_mha_tc(B, Lq, Lk, C, masked, flags):
 
 @pytest.mark.gpu
 @_gpu_mhatc
-@pytest.mark.parametrize("Lq,masked", [(1000, False), (1000, True), (1160, True), (300, True)])
+@pytest.mark.parametrize("Lq,masked", [(1000, False), (1000, True), (1160, True), (600, True)])
 def test_self_attention_shape_through_query_chunks(Lq, masked, monkeypatch):
     """the decoder's Q*T self-attention (one batch element, Lq = Q*T query tokens = keys, transformer_layers.py:34-44) on
     the tcgen05 kernel: ops.mha_core cuts the queries into <= 256-row chunks that become its batch dimension"""
