@@ -82,6 +82,7 @@ static int g_wait_id[kMaxCluster][1024], g_wait_parity[kMaxCluster][1024];
 unsigned char* dyn_smem() { return g_cta[ctx.cta].smem; }
 unsigned char* dyn_smem_of(int cta) { return g_cta[cta].smem; }
 float* tmem() { return g_cta[ctx.cta].tmem; }
+float* tmem_of(int cta) { return g_cta[cta].tmem; }
 MBar& mbar_of(const void* p) {                                     // the barrier lives in the CTA whose shared memory holds it
   for (int c = 0; c < kMaxCluster; ++c) {
     const unsigned char* b = g_cta[c].smem;

@@ -54,6 +54,7 @@ MBar& mbar_of(const void* p);                    // state of the mbarrier stored
 std::mutex& mbar_lock();
 Barrier& named_barrier(int id, int threads);
 [[noreturn]] void fail(const char* what);
+float* tmem_of(int cta);                       // TMEM of CTA `cta` of the running cluster (cta_group::2 MMAs write both)
 void pipe_push(std::function<void()> fn);        // enqueue work on this CTA's (asynchronous, in-order) tensor pipe
 void note_wait(int thread, int id, int parity);  // diagnostics: what every thread of the CTA is waiting for (-1: nothing)
 void dump_waits();
@@ -163,7 +164,7 @@ inline uint64_t* peer_bar(uint64_t* bar, int cta) {          // the barrier at t
 // cp.async.bulk.tensor.3d: box [box0 elements][box1 rows][1] at (c0, c1, c2); elements outside the tensor read as zero; the
 // box lands row by row (box0 * esize bytes per row) with the map's swizzle applied to the absolute shared-memory address;
 // the full box size is credited to the barrier.  Executed synchronously (a legal schedule of the asynchronous copy).
-inline void tma_copy(int cta, uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+inline void tma_copy(int cta, uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int bar_cta = -1) {
   chaos();
   const ::emu::TensorMap& m = *reinterpret_cast<const ::emu::TensorMap*>(map);
   if (m.magic != 0x554e495653ull || m.rank != 3) ::emu::fail("TMA: not a tensor map of the emulated encoder");
@@ -182,7 +183,7 @@ inline void tma_copy(int cta, uint32_t dst, const CUtensorMap* map, uint64_t* ba
       if (sw + m.esize > 232448u) ::emu::fail("TMA: box beyond shared memory");
       std::memcpy(smem + sw, v, m.esize);
     }
-  mbar_complete_tx(peer_bar(bar, cta), (long long)row_bytes * m.box[1]);
+  mbar_complete_tx(peer_bar(bar, bar_cta < 0 ? cta : bar_cta), (long long)row_bytes * m.box[1]);
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   tma_copy(::emu::ctx.cta, dst, map, bar, c0, c1, c2);
@@ -220,7 +221,7 @@ inline uint32_t swizzled(uint32_t addr, int bits) {      // Swizzle<bits,4,3> on
   return addr ^ (((addr >> 7) & ((1u << bits) - 1u)) << 4);
 }
 // element (r = M/N index, k = K index inside one MMA) of an operand whose elements are `esize` bytes (2: fp16, 4: tf32)
-inline float operand_elem(const Desc& d, bool mn_major, int r, int k, int esize) {
+inline float operand_elem(const Desc& d, bool mn_major, int r, int k, int esize, const unsigned char* smem_base = nullptr) {
   const int span = 16 << d.swizzle_bits;          // bytes of one swizzle row (32 / 64 / 128)
   const int per16 = 16 / esize;                   // elements per 16-byte unit (the "T" of the canonical layouts)
   uint32_t off;
@@ -233,7 +234,7 @@ inline float operand_elem(const Desc& d, bool mn_major, int r, int k, int esize)
   (void)per16;
   const uint32_t addr = swizzled(d.start + off, d.swizzle_bits);
   if (addr + esize > 232448u) ::emu::fail("tcgen05.mma operand read beyond shared memory");
-  const unsigned char* p = ::emu::dyn_smem() + addr;
+  const unsigned char* p = (smem_base ? smem_base : ::emu::dyn_smem()) + addr;
   if (esize == 2) return __half2float(*reinterpret_cast<const __half*>(p));
   uint32_t u;
   std::memcpy(&u, p, 4);
@@ -271,6 +272,45 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   ::emu::pipe_push([=] { umma_emulated(tmem_d, adesc, bdesc, idesc, accum, /*fmt tf32*/ 2, 4, 8); });
 }
+// ---- CTA pairs (cta_group::2) ---------------------------------------------------------------------------------------------
+// One MMA of M = 256 issued by the leader (CTA 0): CTA c contributes rows 128c..128c+127 of A and rows (N/2)c..(N/2)c+N/2-1 of
+// B from ITS shared memory (same descriptors = same offsets in both) and receives rows 128c.. of D in ITS TMEM.
+inline void umma_emulated_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  chaos();
+  const int M = (int)((idesc >> 24) & 0x1F) << 4, N = (int)((idesc >> 17) & 0x3F) << 3;
+  const bool a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
+  if (M != 256 || N < 32 || N > 256 || (N & 31)) ::emu::fail("tcgen05.mma.cta_group::2: unsupported shape (M = 256, 32 <= N <= 256, N % 32 == 0)");
+  if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 0 || ((idesc >> 10) & 7) != 0)
+    ::emu::fail("tcgen05.mma.cta_group::2: instruction descriptor is not f16 x f16 -> f32");
+  if (::emu::ctx.cluster_size != 2) ::emu::fail("tcgen05.mma.cta_group::2 outside a cluster of two CTAs");
+  const Desc a = decode_desc(adesc), b = decode_desc(bdesc);
+  const int lane0 = (int)(tmem_d >> 16), col0 = (int)(tmem_d & 0xFFFF);
+  if (lane0 != 0 || col0 + N > 512) ::emu::fail("tcgen05.mma: accumulator outside TMEM");
+  static thread_local float A[128][16], B[256][16];
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 16; ++k) B[n][k] = operand_elem(b, b_mn, n % (N / 2), k, 2, ::emu::dyn_smem_of(n / (N / 2)));
+  for (int c = 0; c < 2; ++c) {
+    for (int m = 0; m < 128; ++m)
+      for (int k = 0; k < 16; ++k) A[m][k] = operand_elem(a, a_mn, m, k, 2, ::emu::dyn_smem_of(c));
+    float* T = ::emu::tmem_of(c);
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < N; ++n) {
+        float acc = accum ? T[m * 512 + col0 + n] : 0.f;
+        for (int k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
+        T[m * 512 + col0 + n] = acc;
+      }
+  }
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (::emu::ctx.cta != 0) ::emu::fail("tcgen05.mma.cta_group::2 must be issued by the leader CTA");
+  ::emu::pipe_push([=] { umma_emulated_2sm(tmem_d, adesc, bdesc, idesc, accum); });
+}
+__device__ __forceinline__ void umma_commit_multicast_2sm(uint64_t* bar, uint16_t mask) { umma_commit_multicast(bar, mask); }
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  tma_copy(::emu::ctx.cta, dst, map, bar, c0, c1, c2, /*barrier in CTA*/ 0);
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) { mbar_arrive(peer_bar(bar, (int)cta)); }
+
 __device__ __forceinline__ bool elect_one() { return ::emu::ctx.lane == 0; }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { ::emu::named_barrier(id, threads).wait(); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
@@ -278,6 +318,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
   if (::emu::ctx.lane == 0) *slot = 0;
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t, uint32_t) {}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot, uint32_t cols) { tmem_alloc(slot, cols); }
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t, uint32_t) {}
 __device__ __forceinline__ void tmem_wait_ld() {}
 
 inline void tmem_ld(uint32_t taddr, uint32_t* r, int n) {

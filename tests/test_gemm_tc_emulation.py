@@ -81,9 +81,10 @@ def test_gemm_tc_kernel_chunk3_operands(monkeypatch, emu_lib_path, tmp_path, M, 
     (300, 260, 192, 2),       # 3 channel tiles: the second CTA of the last pair repeats tile 2 and stores nothing; one cluster
     (130, 520, 320, 6),       # 5 channel tiles, K tail, ring wrap-around on 3 clusters
 ])
-def test_gemm_tc_cluster_multicast_variant(monkeypatch, emu_lib_path, tmp_path, M, N, K, sms):
-    """UNIVS_GEMM_MC=1: pairs of CTAs share the activation tile by TMA multicast; results equal the one-CTA kernel's bit for bit
-    (same MMA sequence per tile)."""
+def test_gemm_tc_cta_pair_variant(monkeypatch, emu_lib_path, tmp_path, M, N, K, sms):
+    """UNIVS_GEMM_PAIR=1: two CTAs of a cluster run one tcgen05.mma.cta_group::2 (M = 256) per product -- TMA boxes of both CTAs
+    credited to the leader's barrier, multicast commits, remote accumulator release; results equal the one-CTA kernel's bit for
+    bit (same products in the same order per accumulator element)."""
     _use(monkeypatch, emu_lib_path, sms, tmp_path)
     g = torch.Generator().manual_seed(M * N + K)
     x, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
@@ -92,7 +93,7 @@ def test_gemm_tc_cluster_multicast_variant(monkeypatch, emu_lib_path, tmp_path, 
     offs = (2 * K, 0)
     outs = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("UNIVS_GEMM_MC", mode)
+        monkeypatch.setenv("UNIVS_GEMM_PAIR", mode)
         y, y16 = ops.gemm_f16x3_tc(dev(x3), offs, dev(w3), offs, K, 2.0 ** -8, dev(bias), dev(add), want_f32=True,
                                    want_operand=True, act=1)
         outs[mode] = (plain(y).clone(), plain(y16).clone())

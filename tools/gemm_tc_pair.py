@@ -1,6 +1,6 @@
-"""csrc/gemm_tc.cu: one-CTA kernel against the cluster / TMA-multicast variant (UNIVS_GEMM_MC) at the Swin-L layer shapes of
+"""csrc/gemm_tc.cu: one-CTA kernel against the CTA-pair (cta_group::2) variant (UNIVS_GEMM_PAIR) at the Swin-L layer shapes of
 the north-star clip -- bit equality of the results and time per launch (run on the B200 box):
-  python tools/gemm_tc_mc.py"""
+  python tools/gemm_tc_pair.py"""
 import os
 import sys
 
@@ -38,7 +38,7 @@ for (M, N, K) in SHAPES:
     offs = (0, K)
     res, t = {}, {}
     for mode in ("0", "1"):
-        os.environ["UNIVS_GEMM_MC"] = mode
+        os.environ["UNIVS_GEMM_PAIR"] = mode
         res[mode] = ops.gemm_f16x3_tc(x, offs, w, offs, K, 1.0, bias, add, want_f32=True, want_operand=True, act=1)
         torch.cuda.synchronize()
         out = torch.empty(M, N, device="cuda")
@@ -52,6 +52,6 @@ for (M, N, K) in SHAPES:
     print(f"M={M} N={N} K={K}: one-CTA {t['0']:.0f} us ({fl / t['0'] / 1e6:.0f} TF/s)  cluster {t['1']:.0f} us "
           f"({fl / t['1'] / 1e6:.0f} TF/s)  gelu->operand {t['0g']:.0f} / {t['1g']:.0f}  bit-equal {same}", flush=True)
     assert same
-os.environ.pop("UNIVS_GEMM_MC")
+os.environ.pop("UNIVS_GEMM_PAIR")
 print(f"sum one-CTA {tot['0']:.0f} us, cluster {tot['1']:.0f} us")
 print("ok")

@@ -1,0 +1,14 @@
+#!/usr/bin/env bash
+set -u
+out=gpurun_out/r2_call19
+mkdir -p "$out"
+run() { local name=$1 secs=$2; shift 2
+  echo "=== $name: $*" | tee -a "$out/summary.txt"
+  ( time timeout "$secs" "$@" ) > "$out/$name.log" 2>&1
+  echo "    exit $? ($(grep -o '"ms_per_step": [0-9.]*' "$out/$name.log" | head -2 | tr '\n' ' ') $(tail -n 3 "$out/$name.log" | tr '\n' ' ' | cut -c1-220))" | tee -a "$out/summary.txt"; }
+run gemm_tests 600 python -m pytest tests/test_gemm_tc_gpu.py -q -x
+run bench_pair_auto 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+run bench_pair_off 600 env UNIVS_GEMM_PAIR=0 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+run bench_pair_on 600 env UNIVS_GEMM_PAIR=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+run parity_ns 900 python -m pytest tests/test_parity_full_geometry.py -q -x -k "ns or c2"
+cat "$out/summary.txt"

@@ -44,15 +44,22 @@ using namespace tc;
 constexpr int kBM = 128;                 // channels per tile (UMMA M)
 constexpr int kBT = 128;                 // tokens per tile (UMMA N)
 constexpr int kBK = 64;                  // halfs per operand row in shared memory (one SWIZZLE_128B span)
-constexpr int kStages = 3;
 constexpr int kTileBytes = 128 * 128;    // one operand tile: 128 rows x 128 bytes
-constexpr int kStageBytes = 4 * kTileBytes;
+// one CTA per tile: stage = Wh | Wl | Xh | Xl' tiles (64 KB), 3 stages.  CTA pair (cta_group::2): stage = Wh | Wl tiles of this
+// CTA's 128 channels + this CTA's 64-token halves of Xh and Xl' (48 KB), 4 stages.  Both rings are 192 KB.
+template <bool PAIR>
+struct Ring {
+  static constexpr int kStages = PAIR ? 4 : 3;
+  static constexpr int kStageBytes = PAIR ? 3 * kTileBytes : 4 * kTileBytes;
+  static constexpr int kOffBars = kStages * kStageBytes;
+  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
+};
 constexpr int kEpiWarps = 16;            // four per TMEM lane quarter, 32 token columns each
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 control warps + the epilogue warps
 constexpr int kCh = 16;                  // token columns per epilogue chunk (registers: 2 x 16 accumulator values + 16 results)
-constexpr int kOffBars = kStages * kStageBytes;
-constexpr int kNumBars = 2 * kStages + 4;
-constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
+constexpr int kSmemBytes = Ring<true>::kSmemBytes > Ring<false>::kSmemBytes ? Ring<true>::kSmemBytes : Ring<false>::kSmemBytes;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr uint32_t kColsPerStage = 2 * kBT;   // main [0,128) corr [128,256)
 
 struct Args {
@@ -173,22 +180,24 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[kCh], const 
   }
 }
 
-// MC (round 2, compute-bound layers): a cluster of two CTAs works on two CHANNEL tiles of the same token tile.  The 128-token
-// activation tile both need arrives by TMA multicast -- each CTA fetches 64 of its rows (hi and lo') and the boxes land in
-// both CTAs' shared memory -- so a CTA pulls 48 KB instead of 64 KB per k-block out of L2.  (The experiment behind it: the
-// one-CTA kernel runs the K >= 768 layers at 1.15-1.2 PFLOP/s whatever their shape, i.e. 98 flop per L2 byte x ~12 TB/s, which
-// suggested an L2 read bound.  The variant cut L2 reads by a quarter and gained nothing, which rules that out; what remains is
-// the power-capped tensor pipe -- cuBLAS bf16 sustains 1.36 PFLOP/s on the same box, MEASURED_PEAKS.json -- and the per-SM
-// delivery of 64 KB per k-block, which multicast does not reduce.  Kept as a switch, off by default.)  A stage is refilled only after BOTH CTAs consumed it (tcgen05.commit multicast on an `empty`
-// barrier of count 2: the peer's multicast writes into my shared memory); each CTA runs the one-CTA MMA sequence into its own
-// TMEM and its own epilogue.  With an odd number of channel tiles the second CTA of the last pair repeats the last tile and
-// skips the stores.  Protocol as in mask_einsum_mc.cu.
-template <int ACT, bool OUT32, bool OUT16, bool ADD, bool MC>
+// PAIR (round 2): two CTAs of a cluster work as ONE tensor-core unit (tcgen05.mma.cta_group::2, M = 256) on a tile of 256
+// channels x 128 tokens.  Why: the one-CTA kernel runs the K >= 768 layers at 1.15-1.25 PFLOP/s whatever their shape.  A
+// cluster variant that only MULTICAST the shared activation tile (48 instead of 64 KB per k-block out of L2, same shared-memory
+// traffic) gained nothing (profiles/r2_gemm_mc.txt), so L2 is not the limit; shared-memory bandwidth is: per k-block a CTA's
+// MMAs read 80 KB of operands while TMA writes 64 KB, ~187 B/clk at the tensor peak against the ~150 B/clk the SM delivers.
+// In a pair each CTA holds its 128 channels of Wh / Wl and HALF of the token tile (the hardware feeds both tensor cores from
+// both shared memories), so per k-block it reads 72 KB and TMA writes 48 KB, and the ring is 4 stages deep.  Protocol (as in
+// CUTLASS' 2-SM kernels): both CTAs allocate TMEM and load with TMA, crediting the LEADER's `full` barrier; the leader (rank 0)
+// issues the MMAs and multicasts its commits to both CTAs' `empty` / `tfull` barriers; each CTA runs the epilogue of its 128
+// channels from its own TMEM and releases the accumulator stage on the leader's `tempty` barrier.  With an odd number of
+// channel tiles the second CTA of the last pair works on an all-zero (out-of-range) weight tile and stores nothing.
+template <int ACT, bool OUT32, bool OUT16, bool ADD, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                      const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  constexpr int kStages = Ring<PAIR>::kStages, kStageBytes = Ring<PAIR>::kStageBytes, kNumBars = Ring<PAIR>::kNumBars;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ring<PAIR>::kOffBars);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tfull = bars + 2 * kStages;
@@ -200,29 +209,30 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
   const int n_tt = (a.M + kBT - 1) / kBT;
   const int kblocks = (a.K + kBK - 1) / kBK;
   // work items: tiles (one CTA) or pairs of channel tiles of one token tile (cluster of two), channel index fastest
-  const int rank = MC ? (int)cluster_rank() : 0;
-  const int n_cu = MC ? (n_ct + 1) / 2 : n_ct;             // channel units per token tile
+  const int rank = PAIR ? (int)cluster_rank() : 0;
+  const int n_cu = PAIR ? (n_ct + 1) / 2 : n_ct;           // channel units per token tile
   const int num_items = n_cu * n_tt;
-  const int item0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], MC ? 2 : 1);                    // MC: both CTAs' MMAs must have retired (the peer writes my stage too)
+      mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps);   // one arrive per epilogue warp
+      mbar_init(&tempty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);   // one arrive per epilogue warp (pair: of both CTAs, on the leader's)
     }
     mbar_init_fence();
   } else if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+    if (PAIR) tmem_alloc_2sm(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
   }
   fence_before();
   __syncthreads();
   fence_after();
-  if (MC) cluster_sync_all();           // the peer's barriers exist before anything is multicast to them
+  if (PAIR) cluster_sync_all();         // the peer's barriers exist before anything is signalled on them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -232,18 +242,22 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
       uint32_t phase = 0;
       for (int item = item0; item < num_items; item += item_step) {
         const int tt = item / n_cu, cu = item - tt * n_cu;
-        const int ct = MC ? min(2 * cu + rank, n_ct - 1) : cu;
+        const int ct = PAIR ? 2 * cu + rank : cu;          // pair, odd n_ct: ct == n_ct reads an out-of-range (zero-filled) weight tile
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 10 + stage);
           const uint32_t s0 = smem_u32(smem + (size_t)stage * kStageBytes);
-          mbar_expect_tx(&full[stage], (uint32_t)kStageBytes);     // a box always counts in full (out-of-range parts are zero-filled)
-          tma_load_3d(s0, &map_wh, &full[stage], kb * kBK, ct * kBM, 0);
-          tma_load_3d(s0 + kTileBytes, &map_wl, &full[stage], kb * kBK, ct * kBM, 0);
-          if (MC) {     // my 64 rows of the activation tile (map_x*: 64-row boxes) into BOTH CTAs; the peer sends the other 64
-            const uint32_t half = (uint32_t)rank * (uint32_t)(kTileBytes / 2);
-            tma_load_3d_multicast(s0 + 2 * kTileBytes + half, &map_xh, &full[stage], kb * kBK, tt * kBT + rank * (kBT / 2), 0, (uint16_t)0x3);
-            tma_load_3d_multicast(s0 + 3 * kTileBytes + half, &map_xl, &full[stage], kb * kBK, tt * kBT + rank * (kBT / 2), 0, (uint16_t)0x3);
+          // a box always counts in full (out-of-range parts are zero-filled)
+          if (PAIR) {   // both CTAs' boxes are credited to the leader's barrier (the leader issues the MMAs of the pair)
+            if (rank == 0) mbar_expect_tx(&full[stage], (uint32_t)(2 * kStageBytes));
+            tma_load_3d_2sm(s0, &map_wh, &full[stage], kb * kBK, ct * kBM, 0);
+            tma_load_3d_2sm(s0 + kTileBytes, &map_wl, &full[stage], kb * kBK, ct * kBM, 0);
+            // my half of the token tile (map_x*: 64-row boxes): B rows (N/2) * rank .. of every MMA of the pair
+            tma_load_3d_2sm(s0 + 2 * kTileBytes, &map_xh, &full[stage], kb * kBK, tt * kBT + rank * (kBT / 2), 0);
+            tma_load_3d_2sm(s0 + 2 * kTileBytes + kTileBytes / 2, &map_xl, &full[stage], kb * kBK, tt * kBT + rank * (kBT / 2), 0);
           } else {
+            mbar_expect_tx(&full[stage], (uint32_t)kStageBytes);
+            tma_load_3d(s0, &map_wh, &full[stage], kb * kBK, ct * kBM, 0);
+            tma_load_3d(s0 + kTileBytes, &map_wl, &full[stage], kb * kBK, ct * kBM, 0);
             tma_load_3d(s0 + 2 * kTileBytes, &map_xh, &full[stage], kb * kBK, tt * kBT, 0);
             tma_load_3d(s0 + 3 * kTileBytes, &map_xl, &full[stage], kb * kBK, tt * kBT, 0);
           }
@@ -251,8 +265,8 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (pair: the leader CTA only) =====
     // Two MMA instructions per k-step carry the three products: the Xh and Xl' tiles are adjacent in shared memory (256 rows of
     // one K-major operand), and {main, corr} are adjacent in TMEM, so ONE N = 256 MMA computes Wh * [Xh ; Xl']^T -- the main
     // term and the first correction term -- reading the Wh tile once; the N = 128 MMA adds Wl' * Xh^T to corr.  Same products
@@ -260,6 +274,7 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
     // (the one-CTA 128 x 128 tile is bound by shared-memory bandwidth, not by the tensor pipe).
     constexpr uint32_t idesc = make_idesc_f16(kBM, kBT, false, false);
     constexpr uint32_t idesc2 = make_idesc_f16(kBM, 2 * kBT, false, false);
+    constexpr uint32_t idesc_pair = make_idesc_f16(2 * kBM, kBT, false, false);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -276,15 +291,29 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
           const uint32_t s0 = smem_u32(smem + (size_t)stage * kStageBytes);
           const uint64_t wh = make_desc<128>(s0), wl = make_desc<128>(s0 + kTileBytes);
           const uint64_t xh = make_desc<128>(s0 + 2 * kTileBytes);     // rows 0-127: Xh tile, rows 128-255: the Xl' tile behind it
+          if (PAIR) {
+            // M = 256 over the pair, N = 128 tokens (64 rows of B from each CTA): the same three products per k-step in the
+            // same order as the one-CTA kernel -- main (+)= Wh Xh^T; corr (+)= Wh Xl'^T; corr += Wl' Xh^T
+            const uint64_t xl = make_desc<128>(s0 + 2 * kTileBytes + kTileBytes / 2);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {   // one k-step = 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
-            umma_f16(d_main, wh + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc2, first);  // [main | corr] (+)= Wh * [Xh ; Xl']^T
-            umma_f16(d_corr, wl + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc, 1u);      // corr += Wl' * Xh^T
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+              umma_f16_2sm(d_main, wh + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc_pair, first);
+              umma_f16_2sm(d_corr, wh + (uint64_t)(2 * k), xl + (uint64_t)(2 * k), idesc_pair, first);
+              umma_f16_2sm(d_corr, wl + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc_pair, 1u);
+            }
+            umma_commit_multicast_2sm(&empty[stage], (uint16_t)0x3);   // frees the stage in both CTAs when these MMAs retire
+            if (kb == kblocks - 1) umma_commit_multicast_2sm(&tfull[acc], (uint16_t)0x3);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {   // one k-step = 16 halfs = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+              const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+              umma_f16(d_main, wh + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc2, first);  // [main | corr] (+)= Wh * [Xh ; Xl']^T
+              umma_f16(d_corr, wl + (uint64_t)(2 * k), xh + (uint64_t)(2 * k), idesc, 1u);      // corr += Wl' * Xh^T
+            }
+            umma_commit(&empty[stage]);                       // frees the stage when these MMAs retire
+            if (kb == kblocks - 1) umma_commit(&tfull[acc]);  // both accumulators complete -> epilogue
           }
-          if (MC) umma_commit_multicast(&empty[stage], (uint16_t)0x3);   // frees the stage in both CTAs when these MMAs retire
-          else umma_commit(&empty[stage]);                  // frees the stage when these MMAs retire
-          if (kb == kblocks - 1) umma_commit(&tfull[acc]);  // both accumulators complete -> epilogue
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -302,7 +331,7 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
     uint32_t acc_phase = 0;
     for (int item = item0; item < num_items; item += item_step) {
       const int tt = item / n_cu, cu = item - tt * n_cu;
-      const int ct = MC ? 2 * cu + rank : cu;               // MC, odd n_ct: the repeated last tile has ct == n_ct -> n >= N, no stores
+      const int ct = PAIR ? 2 * cu + rank : cu;             // pair, odd n_ct: ct == n_ct -> n >= N, no stores
       const int n = ct * kBM + wq * 32 + lane;              // this thread's output channel
       const bool n_ok = n < a.N;
       const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
@@ -317,7 +346,10 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
       tmem_wait_ld();
       fence_before();             // this warp's share of the accumulator stage is in registers: release it to the MMA lane
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_remote(&tempty[acc], 0u);     // the leader's MMA lane waits for both CTAs' epilogues
+        else mbar_arrive(&tempty[acc]);
+      }
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
         const int t0 = tt * kBT + part * 32 + cb * kCh;     // first token of this chunk
@@ -334,10 +366,11 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
   }
   fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();           // no CTA leaves while the peer may still multicast into it / signal its barriers
+  if (PAIR) cluster_sync_all();         // no CTA leaves (or frees TMEM) while the pair's MMAs / barrier signals may still touch it
   if (warp == 2) {
     fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -373,9 +406,12 @@ static int make_map(CUtensorMap* m, const __half* base, long long rows, int K, l
   return 0;
 }
 
+constexpr int kPairDefault = 2;     // 0: off unless UNIVS_GEMM_PAIR=1; 2: heuristic (see the launcher)
+constexpr int kPairMinK = 768;
+
 // cluster launch: persistent pairs of CTAs, as many as can be co-resident (a GPC with an odd number of free SMs leaves one out)
 template <typename Kern>
-static int launch_mc(Kern kern, int num_sms, long long pairs, cudaStream_t st, const CUtensorMap& mwh, const CUtensorMap& mwl,
+static int launch_pair(Kern kern, int num_sms, long long pairs, cudaStream_t st, const CUtensorMap& mwh, const CUtensorMap& mwl,
                      const CUtensorMap& mxh, const CUtensorMap& mxl, const Args& a) {
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kThreads);
@@ -437,15 +473,17 @@ extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, i
   int rc;
   if ((rc = make_map(&mwh, w + w_hi_off, channels, k, ldw))) return rc;
   if ((rc = make_map(&mwl, w + w_lo_off, channels, k, ldw))) return rc;
-  // cluster variant (see the kernel).  Measured on the B200 (tools/gemm_tc_mc.py, profiles/r2_gemm_mc.txt): bit-identical
-  // results, but equal or slower at every Swin-L layer shape (sum over the shapes 1872 us -> 2008 us) -- the operand stream
-  // out of L2 is NOT what holds the one-CTA kernel at 1.15-1.2 PFLOP/s.  UNIVS_GEMM_MC=1 selects it (measurement switch);
-  // mode 2 is the heuristic that was tried (deep K, >= 2 channel tiles, enough pairs to fill the SMs).
-  const char* mc_env = getenv("UNIVS_GEMM_MC");        // read per call: the tests toggle it
-  const int mc_mode = mc_env ? (atoi(mc_env) ? 1 : 0) : 0;      // default off: measured no faster on the B200 (see above)
+  // CTA-pair variant (see the kernel): UNIVS_GEMM_PAIR = 0 never, 1 whenever there are two channel tiles, unset = where it
+  // pays (deep K, enough pairs to fill the SMs).  Read per call: the tests toggle it.
+  const char* pair_env = getenv("UNIVS_GEMM_PAIR");
+  const int pair_mode = pair_env ? (atoi(pair_env) ? 1 : 0) : kPairDefault;
   const int n_ct_h = (channels + kBM - 1) / kBM;
   const long long n_tt_h = (tokens + kBT - 1) / kBT;
-  const bool mc = mc_mode == 1 ? n_ct_h >= 2 : (mc_mode == 2 && k >= 512 && n_ct_h >= 2 && (long long)((n_ct_h + 1) / 2) * n_tt_h >= 74);
+  // measured (tools/gemm_tc_pair.py, profiles/r2_gemm_pair.txt): the pair wins where the main loop dominates (K >= 768: stage 3 / 4
+  // of Swin-L, 5-15 %) and loses on shallow K and on an odd number of channel tiles (N = 384: a quarter of the pair slots idle)
+  const bool mc = pair_mode == 1 ? n_ct_h >= 2
+                                 : (pair_mode == 2 && k >= kPairMinK && n_ct_h >= 2 && (n_ct_h % 2 == 0 || n_ct_h >= 9) &&
+                                    (long long)((n_ct_h + 1) / 2) * n_tt_h >= 74);
   if ((rc = make_map(&mxh, x + x_hi_off, tokens, k, ldx, mc ? kBT / 2 : kBT))) return rc;
   if ((rc = make_map(&mxl, x + x_lo_off, tokens, k, ldx, mc ? kBT / 2 : kBT))) return rc;
   Args a;
@@ -476,7 +514,7 @@ extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, i
       if (e != cudaSuccess) { set_error("gemm_f16x3_tc: cudaFuncSetAttribute(%d): %s", kSmemBytes, cudaGetErrorString(e)); return UNIVS_E_LAUNCH; } \
       attr_set = true;                                                                                                         \
     }                                                                                                                          \
-    if (mc) return launch_mc(gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF, true>, num_sms, pairs, st, mwh, mwl, mxh, mxl, a);        \
+    if (mc) return launch_pair(gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF, true>, num_sms, pairs, st, mwh, mwl, mxh, mxl, a);        \
     gemm_f16x3_tc_kernel<ACT, O32, O16, ADDF, false><<<grid, kThreads, kSmemBytes, st>>>(mwh, mwl, mxh, mxl, a);                  \
     return check_launch("gemm_f16x3_tc");                                                                                      \
   }

@@ -135,6 +135,54 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
                : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster (ranks 0 / 1, the leader is rank 0) run ONE tcgen05.mma of M = 256.
+// Each CTA holds its 128 rows of A, its N/2 rows of B and its 128 rows of D (same shared-memory / TMEM offsets in both);
+// the leader issues the MMAs and commits, both CTAs load with TMA and both allocate TMEM.  PTX forms as in CUTLASS
+// (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD, cute/arch/mma_sm100_umma.hpp SM100_MMA_F16BF16_2x1SM_SS,
+// cutlass/arch/barrier.h umma_arrive_multicast_2x1SM / ClusterBarrier::arrive).
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot, uint32_t cols) {      // one warp of EACH CTA of the pair, same slot offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t base, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols));
+}
+// box into THIS CTA's shared memory; the bytes are credited to the barrier at the same offset in the pair's leader (even) CTA
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(z)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// arrive on the barrier at this shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 
 #define UNIVS_TMEM_LD_X4(taddr, r)                                                              \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"                     \
