@@ -173,6 +173,18 @@ int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, int64_t x_hi
                         int64_t ldw, int64_t w_hi_off, int64_t w_lo_off, int64_t tokens, int channels, int k, float alpha,
                         const float* bias, const float* addend, int64_t ldadd, float* out, int64_t ldo, void* out16,
                         int64_t ld16, int64_t out16_lo_off, int activation);
+/* The same with shifted-row taps: a k x k "same" convolution over a zero-padded channel-last activation viewed as a token
+ * matrix is sum_t X[m + tap_row_offsets[t], :] * W_t^T (msdeformattn.py:345-360, the 3x3 FPN output convolutions), accumulated in
+ * ONE tensor-core chain instead of k*k GEMMs that re-read and re-write the fp32 result:
+ *   y[m, n] = act(alpha * sum_t sum_kk x[m + tap_row_offsets[t], kk] * w[n, t * k_tap + kk] + bias[n]) + addend[m, n]
+ * x16 has x_rows rows (rows beyond read as zeros); the hi / lo' blocks of w16 are taps * k_tap columns wide, tap-major.
+ * taps <= 9, k_tap % 64 == 0 when taps > 1, taps * k_tap <= 1536 per call (callers group the taps and pass `addend`);
+ * tap_row_offsets is a HOST array.  taps == 1 with offset 0 is univs_gemm_f16x3_tc. */
+int univs_gemm_f16x3_tc_taps(void* stream, const void* x16, int64_t ldx, int64_t x_hi_off, int64_t x_lo_off, int64_t x_rows,
+                             const void* w16, int64_t ldw, int64_t w_hi_off, int64_t w_lo_off, int64_t tokens, int channels,
+                             int k_tap, int taps, const int64_t* tap_row_offsets, float alpha, const float* bias,
+                             const float* addend, int64_t ldadd, float* out, int64_t ldo, void* out16, int64_t ld16,
+                             int64_t out16_lo_off, int activation);
 
 /* ---- ProCA attention core (a14): every (prompt p, frame t) query attends to its own token and its L
  * prompt-memory tokens.  q,k_self,v_self [P,T,C]; k_mem,v_mem [P,Tm,L,C], Tm in {1,T}; out [P,T,C]. */

@@ -140,8 +140,8 @@ def _layernorm_multi(x, weight, bias, eps=1e-5, residual=None, residual_bias=Non
 
 
 def _gemm_tc(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None, out=None, want_f32=True, want_operand=False,
-             act=0):
-    y, y16 = ops_ref.gemm_f16x3(x16, x_offs, w16, w_offs, k, alpha, bias, addend, act)
+             act=0, tap_rows=None, rows=None):
+    y, y16 = ops_ref.gemm_f16x3(x16, x_offs, w16, w_offs, k, alpha, bias, addend, act, tap_rows, rows)
     if out is not None:
         out.copy_(y)
         y = out

@@ -314,14 +314,24 @@ def layernorm_merge2x2(x_cl, weight, bias, eps=1e-5):
     return torch.nn.functional.layer_norm(x, (4 * C,), weight, bias, eps)
 
 
-def gemm_f16x3(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None, act=0):
+def gemm_f16x3(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None, act=0, tap_rows=None, rows=None):
     """CPU restatement of univs_gemm_f16x3_tc (csrc/gemm_tc.cu): the dense layer the reference computes with nn.Linear + the
     activation / residual behind it (swin.py:35-41 Mlp, :138-169 qkv / proj; ms_deform_attn.py:98-120;
     transformer_layers.py).  Operands are fp16 pairs, value = hi + lo' * 2^-11.  Returns (y fp32, y as the compact operand
     [hi | lo' ] fp16)."""
-    def value(t, offs):
-        return t[:, offs[0]: offs[0] + k].double() + t[:, offs[1]: offs[1] + k].double() * 2.0 ** -11
-    y = (value(x16, x_offs) @ value(w16, w_offs).t() * alpha).float()
+    def value(t, offs, width=None, col0=0):
+        width = k if width is None else width
+        return (t[:, offs[0] + col0: offs[0] + col0 + width].double()
+                + t[:, offs[1] + col0: offs[1] + col0 + width].double() * 2.0 ** -11)
+    if tap_rows is None:
+        y = (value(x16, x_offs) @ value(w16, w_offs).t() * alpha).float()
+    else:       # univs_gemm_f16x3_tc_taps: y[m] = sum_t x[m + tap_rows[t]] w_t^T, rows beyond the end of x16 read as zeros
+        xv = value(x16, x_offs)
+        xv = torch.cat([xv, xv.new_zeros(int(rows) + max(tap_rows) - xv.shape[0], k)]) if int(rows) + max(tap_rows) > xv.shape[0] else xv
+        acc = xv.new_zeros(int(rows), w16.shape[0])
+        for t, r0 in enumerate(tap_rows):
+            acc += xv[r0: r0 + int(rows)] @ value(w16, w_offs, k, t * k).t()
+        y = (acc * alpha).float()
     if bias is not None:
         y = y + bias
     if act == 1:

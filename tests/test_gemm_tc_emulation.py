@@ -125,6 +125,35 @@ def test_gemm_tc_compact_operand_k_slices_and_row_views(monkeypatch, emu_lib_pat
     assert _rel(out, want) < 5e-6
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_gemm_tc_shifted_row_taps(monkeypatch, emu_lib_path, tmp_path, pair):
+    """univs_gemm_f16x3_tc_taps: y[m] = sum_t x[m + off_t] w_t^T in one accumulation (the 3x3 convolution over a padded
+    channel-last activation), in two tap groups accumulated through `addend`, one-CTA and CTA-pair kernels"""
+    _use(monkeypatch, emu_lib_path, 4, tmp_path)
+    monkeypatch.setenv("UNIVS_GEMM_PAIR", pair)
+    g = torch.Generator().manual_seed(11)
+    Cin, Cout, Wp, rows_total = 64, 200, 9, 300
+    taps = [(t // 3) * Wp + (t % 3) for t in range(9)]
+    R = rows_total - taps[-1]
+    x = torch.randn(rows_total, Cin, generator=g)
+    w = torch.randn(Cout, 9, Cin, generator=g) * 0.05           # tap-major columns
+    bias = torch.randn(Cout, generator=g)
+    xc = cpu_backend._maybe_split(x, "f16c")                    # compact [hi | lo']
+    wc = cpu_backend._maybe_split(w.reshape(Cout, 9 * Cin) * 64.0, "f16c")
+    out = torch.zeros(R, Cout)
+    for g0, g1 in ((0, 5), (5, 9)):
+        ops.gemm_f16x3_tc(dev(xc), (0, Cin), dev(wc), (g0 * Cin, 9 * Cin + g0 * Cin), Cin, 1 / 64.0, dev(bias) if g0 == 0 else None,
+                          dev(out) if g0 else None, out=dev(out), tap_rows=taps[g0:g1], rows=R)
+    want = sum(x[o:o + R].double() @ w[:, t].double().t() for t, o in enumerate(taps)) + bias.double()
+    assert _rel(out, want) < 5e-6
+    wy = ops_ref.gemm_f16x3(xc, (0, Cin), wc, (0, 9 * Cin), Cin, 1 / 64.0, bias, None, 0, tap_rows=taps, rows=R)[0]
+    assert _rel(out, wy) < 2e-6
+    # rows beyond the end of x16 read as zeros: ask for all rows_total output rows
+    full, _ = ops.gemm_f16x3_tc(dev(xc), (0, Cin), dev(wc), (0, 9 * Cin), Cin, 1 / 64.0, None, None, tap_rows=taps[:4], rows=rows_total)
+    wf = ops_ref.gemm_f16x3(xc, (0, Cin), wc, (0, 9 * Cin), Cin, 1 / 64.0, None, None, 0, tap_rows=taps[:4], rows=rows_total)[0]
+    assert _rel(full, wf) < 2e-6
+
+
 def test_gemm_tc_argument_validation(monkeypatch, emu_lib_path, tmp_path):
     _use(monkeypatch, emu_lib_path, 1, tmp_path)
     x3, w3 = torch.zeros(8, 3 * 64, dtype=torch.float16), torch.zeros(8, 3 * 64, dtype=torch.float16)

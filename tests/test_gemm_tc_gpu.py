@@ -96,3 +96,30 @@ def test_clip_forward_with_gemm_tc_equals_library_gemm_path(glue):
         set_precision(old)
     for k in ("pred_masks", "pred_logits", "pred_embds"):
         assert _rel(got[k], want[k]) < 5e-5, k
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", [(2, 46, 80, 256, 256, 3), (1, 23, 40, 128, 72, 3), (2, 9, 11, 64, 24, 1)])
+def test_fused_conv_taps_on_device(N, H, W, Cin, Cout, k, monkeypatch):
+    """CONV_FUSED (univs_gemm_f16x3_tc_taps): the k x k FPN convolution as one shifted-row accumulation per tap group, against
+    F.conv2d in float64 (msdeformattn.py:345-360) and against the k*k-GEMM path"""
+    from univs_b200.precision import get_precision, set_precision
+    g = torch.Generator().manual_seed(H * W + Cin)
+    conv = torch.nn.Conv2d(Cin, Cout, k, padding=k // 2)
+    x = torch.randn(N, H, W, Cin, generator=g)
+    want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.double(), conv.bias.double(),
+                                      padding=k // 2).permute(0, 2, 3, 1)
+    old, old_tc = get_precision(), nn_ops._gemm_tc
+    set_precision("fp16x3")
+    nn_ops.set_gemm_tc(True)
+    conv = conv.cuda()
+    outs = {}
+    try:
+        for fused in (False, True):
+            monkeypatch.setattr(nn_ops, "_conv_fused", fused)
+            outs[fused] = nn_ops.conv2d_cl(x.cuda(), conv.weight, conv.bias, padding=k // 2).contiguous()
+        torch.cuda.synchronize()
+    finally:
+        nn_ops.set_gemm_tc(old_tc)
+        set_precision(old)
+    assert _rel(outs[True], want) < 5e-6 and _rel(outs[False], want) < 5e-6
+    assert _rel(outs[True], outs[False]) < 2e-6

@@ -58,3 +58,36 @@ def test_k_slices_accumulate_in_place():
             nn_ops.set_gemm_tc(False)
     want = torch.nn.functional.linear(x.double(), lin.weight.double(), lin.bias.double())
     assert float((y - want).abs().max() / want.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("Cin,Cout,k", [(64, 24, 3), (128, 40, 3), (512, 16, 3), (64, 8, 1)])
+def test_fused_conv_taps_equal_conv2d(Cin, Cout, k, monkeypatch):
+    """CONV_FUSED: a k x k "same" convolution as ONE shifted-row accumulation per tap group (K <= 1536 per chain) of
+    ops.gemm_f16x3_tc (univs_gemm_f16x3_tc_taps) -- against F.conv2d (msdeformattn.py:345-360, the FPN output convolutions)."""
+    g = torch.Generator().manual_seed(Cin + Cout)
+    conv = torch.nn.Conv2d(Cin, Cout, k, padding=k // 2)
+    x = torch.randn(2, 5, 7, Cin, generator=g)
+    want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.double(), conv.bias.double(),
+                                      padding=k // 2).permute(0, 2, 3, 1)
+    outs = {}
+    with oracle_ops("fp16x3"):
+        nn_ops.set_gemm_tc(True)
+        try:
+            for fused in (False, True):
+                monkeypatch.setattr(nn_ops, "_conv_fused", fused)
+                calls = []
+                from univs_b200 import ops
+                real = ops.gemm_f16x3_tc
+                monkeypatch.setattr(ops, "gemm_f16x3_tc", lambda *a, **kw: (calls.append(kw.get("tap_rows")), real(*a, **kw))[1])
+                outs[fused] = nn_ops.conv2d_cl(x, conv.weight, conv.bias, padding=k // 2)
+                monkeypatch.setattr(ops, "gemm_f16x3_tc", real)
+                if fused:       # ceil(k*k*Cin / 1536) launches, each with its group of taps
+                    assert len(calls) == -(-k * k * Cin // 1536) and all(c is not None for c in calls)
+                    assert sum(len(c) for c in calls) == k * k
+                else:
+                    assert len(calls) == k * k and all(c is None for c in calls)
+        finally:
+            nn_ops.set_gemm_tc(False)
+    for fused in (False, True):
+        err = float((outs[fused] - want).abs().max() / want.abs().max())
+        assert err < 2e-6, (fused, err)

@@ -33,6 +33,8 @@ SIGNATURES = {
     "univs_mha_tc_forward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "univs_gemm_f16x3_tc": (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i, _i, C.c_float, _vp, _vp, _i64,
                                  _vp, _i64, _vp, _i64, _i64, _i]),
+    "univs_gemm_f16x3_tc_taps": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i, _i, _i, _vp, C.c_float,
+                                      _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i]),
     "univs_proca_forward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "univs_layernorm_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, C.c_float, _vp, _vp, _i]),
     "univs_gelu_f32": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i]),

@@ -57,6 +57,7 @@ struct Ring {
 };
 constexpr int kEpiWarps = 16;            // four per TMEM lane quarter, 32 token columns each
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 control warps + the epilogue warps
+constexpr int kMaxTaps = 9;
 constexpr int kCh = 16;                  // token columns per epilogue chunk (registers: 2 x 16 accumulator values + 16 results)
 constexpr int kSmemBytes = Ring<true>::kSmemBytes > Ring<false>::kSmemBytes ? Ring<true>::kSmemBytes : Ring<false>::kSmemBytes;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -73,6 +74,10 @@ struct Args {
   __half* out16;               // fp16 operand output or null: hi at column n, lo*2^11 at column lo_off16 + n
   long long ld16, lo_off16;
   int act;                     // 0 none, 1 GELU (erf), 2 ReLU
+  // shifted-row taps (kxk convolution as ONE accumulation): K = taps * kpt k-blocks; k-block kb multiplies the weight columns
+  // [64 kb, 64 kb + 64) with the activation rows shifted by tap_off[kb / kpt], columns [64 (kb % kpt), ..).  taps == 1: a plain GEMM.
+  int taps, kpt;
+  int tap_off[kMaxTaps];
 };
 
 // erf(z) in one branch-free form:  erf(|z|) = 1 - exp(-|z| * q(|z|)),  q = degree-7 polynomial fitted to -ln(erfc(t)) / t on
@@ -244,6 +249,9 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
         const int tt = item / n_cu, cu = item - tt * n_cu;
         const int ct = PAIR ? 2 * cu + rank : cu;          // pair, odd n_ct: ct == n_ct reads an out-of-range (zero-filled) weight tile
         for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / a.kpt;
+          const int xk = (kb - tap * a.kpt) * kBK;           // activation column of this k-block
+          const int xr = tt * kBT + a.tap_off[tap];          // first activation row
           mbar_wait(&empty[stage], phase ^ 1, 10 + stage);
           const uint32_t s0 = smem_u32(smem + (size_t)stage * kStageBytes);
           // a box always counts in full (out-of-range parts are zero-filled)
@@ -252,14 +260,14 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
             tma_load_3d_2sm(s0, &map_wh, &full[stage], kb * kBK, ct * kBM, 0);
             tma_load_3d_2sm(s0 + kTileBytes, &map_wl, &full[stage], kb * kBK, ct * kBM, 0);
             // my half of the token tile (map_x*: 64-row boxes): B rows (N/2) * rank .. of every MMA of the pair
-            tma_load_3d_2sm(s0 + 2 * kTileBytes, &map_xh, &full[stage], kb * kBK, tt * kBT + rank * (kBT / 2), 0);
-            tma_load_3d_2sm(s0 + 2 * kTileBytes + kTileBytes / 2, &map_xl, &full[stage], kb * kBK, tt * kBT + rank * (kBT / 2), 0);
+            tma_load_3d_2sm(s0 + 2 * kTileBytes, &map_xh, &full[stage], xk, xr + rank * (kBT / 2), 0);
+            tma_load_3d_2sm(s0 + 2 * kTileBytes + kTileBytes / 2, &map_xl, &full[stage], xk, xr + rank * (kBT / 2), 0);
           } else {
             mbar_expect_tx(&full[stage], (uint32_t)kStageBytes);
             tma_load_3d(s0, &map_wh, &full[stage], kb * kBK, ct * kBM, 0);
             tma_load_3d(s0 + kTileBytes, &map_wl, &full[stage], kb * kBK, ct * kBM, 0);
-            tma_load_3d(s0 + 2 * kTileBytes, &map_xh, &full[stage], kb * kBK, tt * kBT, 0);
-            tma_load_3d(s0 + 3 * kTileBytes, &map_xl, &full[stage], kb * kBK, tt * kBT, 0);
+            tma_load_3d(s0 + 2 * kTileBytes, &map_xh, &full[stage], xk, xr, 0);
+            tma_load_3d(s0 + 3 * kTileBytes, &map_xl, &full[stage], xk, xr, 0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -452,14 +460,30 @@ extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, i
                                    const void* w16, int64_t ldw, int64_t w_hi_off, int64_t w_lo_off, int64_t tokens,
                                    int channels, int k, float alpha, const float* bias, const float* addend, int64_t ldadd,
                                    float* out, int64_t ldo, void* out16, int64_t ld16, int64_t out16_lo_off, int activation) {
+  const int64_t zero = 0;
+  return univs_gemm_f16x3_tc_taps(stream, x16, ldx, x_hi_off, x_lo_off, tokens, w16, ldw, w_hi_off, w_lo_off, tokens, channels, k, 1,
+                                  &zero, alpha, bias, addend, ldadd, out, ldo, out16, ld16, out16_lo_off, activation);
+}
+
+extern "C" int univs_gemm_f16x3_tc_taps(void* stream, const void* x16, int64_t ldx, int64_t x_hi_off, int64_t x_lo_off,
+                                        int64_t x_rows, const void* w16, int64_t ldw, int64_t w_hi_off, int64_t w_lo_off,
+                                        int64_t tokens, int channels, int k_tap, int taps, const int64_t* tap_row_offsets,
+                                        float alpha, const float* bias, const float* addend, int64_t ldadd, float* out,
+                                        int64_t ldo, void* out16, int64_t ld16, int64_t out16_lo_off, int activation) {
   using namespace gemmtc;
   UNIVS_REQUIRE(x16 && w16 && (out || out16), "gemm_f16x3_tc: null pointer");
-  UNIVS_REQUIRE(tokens >= 0 && tokens < (1ll << 31) - 256 && channels > 0 && k > 0, "gemm_f16x3_tc: bad sizes");
+  UNIVS_REQUIRE(tokens >= 0 && tokens < (1ll << 31) - 256 && channels > 0 && k_tap > 0, "gemm_f16x3_tc: bad sizes");
+  UNIVS_REQUIRE(taps >= 1 && taps <= kMaxTaps && tap_row_offsets != nullptr, "gemm_f16x3_tc: taps must be in [1, %d]", kMaxTaps);
+  UNIVS_REQUIRE(taps == 1 || k_tap % kBK == 0, "gemm_f16x3_tc: with taps the per-tap K must be a multiple of %d", kBK);
+  UNIVS_REQUIRE(x_rows >= 0 && x_rows < (1ll << 31) - 256, "gemm_f16x3_tc: bad activation row count");
+  for (int t = 0; t < taps; ++t)
+    UNIVS_REQUIRE(tap_row_offsets[t] >= 0 && tap_row_offsets[t] < (1ll << 31) - 256, "gemm_f16x3_tc: bad tap row offset");
+  const int k = k_tap * taps;                 // accumulation length = weight columns
   UNIVS_REQUIRE(k % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && x_hi_off % 8 == 0 && x_lo_off % 8 == 0 && w_hi_off % 8 == 0 &&
                     w_lo_off % 8 == 0,
                 "gemm_f16x3_tc: K, row pitches and block offsets must be multiples of 8 halfs (16-byte TMA alignment)");
   UNIVS_REQUIRE(((uintptr_t)x16 | (uintptr_t)w16) % 16 == 0, "gemm_f16x3_tc: operands must be 16-byte aligned");
-  UNIVS_REQUIRE(x_hi_off + k <= ldx && x_lo_off + k <= ldx && w_hi_off + k <= ldw && w_lo_off + k <= ldw,
+  UNIVS_REQUIRE(x_hi_off + k_tap <= ldx && x_lo_off + k_tap <= ldx && w_hi_off + k <= ldw && w_lo_off + k <= ldw,
                 "gemm_f16x3_tc: operand blocks exceed the row pitch");
   UNIVS_REQUIRE(activation >= 0 && activation <= 2, "gemm_f16x3_tc: activation must be 0 (none), 1 (GELU) or 2 (ReLU)");
   UNIVS_REQUIRE(out == nullptr || ldo >= channels, "gemm_f16x3_tc: ldo < channels");
@@ -484,12 +508,16 @@ extern "C" int univs_gemm_f16x3_tc(void* stream, const void* x16, int64_t ldx, i
   const bool mc = pair_mode == 1 ? n_ct_h >= 2
                                  : (pair_mode == 2 && k >= kPairMinK && n_ct_h >= 2 && (n_ct_h % 2 == 0 || n_ct_h >= 9) &&
                                     (long long)((n_ct_h + 1) / 2) * n_tt_h >= 74);
-  if ((rc = make_map(&mxh, x + x_hi_off, tokens, k, ldx, mc ? kBT / 2 : kBT))) return rc;
-  if ((rc = make_map(&mxl, x + x_lo_off, tokens, k, ldx, mc ? kBT / 2 : kBT))) return rc;
+  // activation rows beyond x_rows (and columns beyond the per-tap K) read as zeros
+  if ((rc = make_map(&mxh, x + x_hi_off, x_rows, k_tap, ldx, mc ? kBT / 2 : kBT))) return rc;
+  if ((rc = make_map(&mxl, x + x_lo_off, x_rows, k_tap, ldx, mc ? kBT / 2 : kBT))) return rc;
   Args a;
   a.M = (int)tokens; a.N = channels; a.K = k; a.alpha = alpha; a.bias = bias; a.addend = addend; a.ldadd = ldadd;
   a.out = out; a.ldo = ldo; a.out16 = reinterpret_cast<__half*>(out16); a.ld16 = ld16; a.lo_off16 = out16_lo_off;
   a.act = activation;
+  a.taps = taps;
+  a.kpt = (k_tap + kBK - 1) / kBK;
+  for (int t = 0; t < kMaxTaps; ++t) a.tap_off[t] = t < taps ? (int)tap_row_offsets[t] : 0;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

@@ -61,6 +61,9 @@ def _tc_linear(h3, K, b3, alpha, bias, act=0, want_f32=True, want_operand=False,
     return y, y16
 
 
+_conv_fused = switches.get("CONV_FUSED") == 1     # k x k convolutions as one shifted-row accumulation (gemm_tc taps)
+
+
 def set_fused_glue(on: bool):
     global _fused_glue
     _fused_glue = bool(on)
@@ -422,6 +425,23 @@ def _conv_weight_taps(weight):
     return ent[1]
 
 
+def _conv_weight_fused(weight):
+    """k x k convolution weight [Cout,Cin,kh,kw] -> compact fp16 operand [Cout, 2*T*Cin] = [hi | lo*2^11] of W*2^s with the
+    taps side by side (tap-major columns, T = kh*kw) and ONE scale for all taps, alpha = 2^-s: the weight of the fused
+    shifted-row GEMM (ops.gemm_f16x3_tc with tap_rows).  Cached per parameter version."""
+    key = ("convf", weight.data_ptr(), tuple(weight.shape))
+    sig = (weight.data_ptr(), weight._version)
+    ent = _wcache.get(key)
+    if ent is None or ent[0] != sig or not _same_owner(ent[3], weight):
+        Cout, Cin, kh, kw = weight.shape
+        w2d = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin).contiguous()
+        amax = float(w2d.abs().max())
+        s = 0 if amax == 0.0 else max(-24, min(24, int(torch.floor(torch.log2(torch.tensor(8192.0 / amax))))))
+        ent = (sig, ops.split_operand(w2d * (2.0 ** s), "f16c"), 2.0 ** -s, _owner_ref(weight))
+        _wcache[key] = ent
+    return ent[1], ent[2]
+
+
 def _conv_taps(xs, H, W, weight, bias, taps):
     """k*k shifted GEMMs over the padded split activation xs [N,Hp,Wp,width] viewed as one token matrix."""
     Cout, Cin, kh, kw = weight.shape
@@ -431,6 +451,20 @@ def _conv_taps(xs, H, W, weight, bias, taps):
     y = torch.empty((N * Hp * Wp, Cout), device=xs.device, dtype=torch.float32)
     yr = y[:R]
     f32 = torch.float32
+    if gemm_tc() and _conv_fused and Cin % 64 == 0 and Cin <= 1536:
+        # ONE accumulation per group of taps (K <= 1536 per tensor-core chain) instead of k*k GEMMs that re-read and re-write
+        # the fp32 result: the taps are shifted row windows of the same token matrix
+        wf, alpha = _conv_weight_fused(weight)
+        T = kh * kw
+        groups = -(-T * Cin // 1536)
+        per = -(-T // groups)
+        x_offs = (0, Cin) if x2.shape[-1] == 2 * Cin else (2 * Cin, 0)         # compact / K-chunk container
+        for g0 in range(0, T, per):
+            g1 = min(T, g0 + per)
+            ops.gemm_f16x3_tc(x2, x_offs, wf, (g0 * Cin, T * Cin + g0 * Cin), Cin, alpha,
+                              bias.float() if (bias is not None and g0 == 0) else None, yr if g0 else None, out=yr,
+                              tap_rows=[(t // kw) * Wp + (t % kw) for t in range(g0, g1)], rows=R)
+        return y.view(N, Hp, Wp, Cout)[:, :H, :W]
     for t, (wh, wlh) in enumerate(taps):
         off = (t // kw) * Wp + (t % kw)
         a = x2[off: off + R]

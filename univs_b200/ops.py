@@ -3,6 +3,7 @@ allocates the output with torch (device memory plumbing), passes raw pointers an
 through the C ABI and returns immediately (stream-ordered, no synchronisation).  No CPU path exists."""
 from __future__ import annotations
 
+import ctypes
 import os
 
 import numpy as np
@@ -419,14 +420,21 @@ ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
 
 def gemm_f16x3_tc(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None, out=None, want_f32=True,
-                  want_operand=False, act=ACT_NONE):
+                  want_operand=False, act=ACT_NONE, tap_rows=None, rows=None):
     """Dense layer on the tcgen05 tensor cores with fused epilogue (univs_gemm_f16x3_tc, csrc/gemm_tc.cu):
         y = act(alpha * x w^T + bias) + addend
     x16 [tokens, ldx] / w16 [channels, ldw]: fp16 operand containers (row views allowed); `x_offs` / `w_offs` = (column of
     the hi block, column of the lo*2^11 block), `k` columns each.  addend fp32 [tokens, channels] (rows may be strided; may
     be `out`).  Returns (y fp32 [tokens, channels] or None, y as compact operand fp16 [tokens, 2*channels] = [hi | lo*2^11]
-    or None)."""
+    or None).
+    tap_rows (univs_gemm_f16x3_tc_taps): row offsets of shifted-row taps -- y[m] = sum_t x[m + tap_rows[t]] w_t^T with the hi / lo'
+    blocks of w16 `len(tap_rows) * k` columns wide (tap-major) and `rows` output rows (x16 rows beyond its end read as zeros):
+    a k x k convolution over a zero-padded channel-last activation as ONE accumulation."""
     M, N = x16.shape[0], w16.shape[0]
+    taps = 1 if tap_rows is None else len(tap_rows)
+    x_rows = M
+    if tap_rows is not None:
+        M = int(rows)
     xp, wp = _chk_rows16(x16, "x16"), _chk_rows16(w16, "w16")
     if out is not None and (out.dtype != torch.float32 or not _on_device(out) or out.shape != (M, N) or out.stride(1) != 1):
         raise _cabi.UnivsB200Error("gemm_f16x3_tc: out must be an fp32 CUDA [tokens, channels] matrix with contiguous rows")
@@ -438,11 +446,12 @@ def gemm_f16x3_tc(x16, x_offs, w16, w_offs, k, alpha=1.0, bias=None, addend=None
     if M == 0:
         return out, out16
     if _event_sink is not None:
-        flop_count["gemm_f16x3_tc"] = flop_count.get("gemm_f16x3_tc", 0) + 2 * int(x16.shape[0]) * int(w16.shape[0]) * int(k)
+        flop_count["gemm_f16x3_tc"] = flop_count.get("gemm_f16x3_tc", 0) + 2 * M * N * int(k) * taps
+    offs = (ctypes.c_int64 * taps)(*([0] if tap_rows is None else [int(v) for v in tap_rows]))
     with _Bracket("gemm_f16x3_tc", 1):
-        rc = lib().univs_gemm_f16x3_tc(
-            _stream(), xp, x16.stride(0), int(x_offs[0]), int(x_offs[1]), wp, w16.stride(0), int(w_offs[0]), int(w_offs[1]),
-            M, N, int(k), float(alpha), None if bias is None else _chk(bias, "bias"),
+        rc = lib().univs_gemm_f16x3_tc_taps(
+            _stream(), xp, x16.stride(0), int(x_offs[0]), int(x_offs[1]), x_rows, wp, w16.stride(0), int(w_offs[0]), int(w_offs[1]),
+            M, N, int(k), taps, ctypes.cast(offs, ctypes.c_void_p), float(alpha), None if bias is None else _chk(bias, "bias"),
             None if addend is None else addend.data_ptr(), 0 if addend is None else addend.stride(0),
             None if out is None else out.data_ptr(), 0 if out is None else out.stride(0),
             None if out16 is None else out16.data_ptr(), 2 * N, N, int(act))

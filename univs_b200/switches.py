@@ -16,6 +16,7 @@ DEFAULTS = {
     "MHA_TC": 0,            # ops: tcgen05 cross-attention (1; 3 = transposed-V diagnostic variant)
     "ROWWISE_V2": 0,        # csrc/elementwise.cu: bit 0 = 8-wide GELU / ReLU / operand split, bit 1 = wide-store LayerNorm
     "GEMM_TC": 0,           # nn_ops: dense layers on the own tcgen05 GEMM with fused epilogues (csrc/gemm_tc.cu)
+    "CONV_FUSED": 0,        # nn_ops: k x k convolutions as one shifted-row accumulation of the own GEMM (taps) instead of k*k GEMMs
     "EINSUM_MC": 0,         # ops: cluster / TMA-multicast mask einsum (E resident per CTA pair)
     "MLP_CHUNK_MB": 0,      # backbone: Swin MLP in row chunks whose fp32 hidden + operand stay in L2 (0 = whole tensor)
     "POOLED_MASKS": 0,      # decoder: intermediate heads from pooled mask features
