@@ -86,8 +86,11 @@ int univs_swin_window_attention_f16x3out(void* stream, const float* qkv, const f
  * CTA per SM, fp16 hi|lo operand tiles in shared memory, S and O accumulated in TMEM, softmax on rows read back with
  * tcgen05.ld (swin_window_attn_tc.cu).  Strict precision only (same arithmetic contract as UNIVS_PREC_TF32X3 above).
  * out (f32 [B,H,W,C]) and out16 (__half [B,H,W,3C] operand layout as above, channels <= 1536) are both optional, at
- * least one must be given.  flags: reserved, must be 0.  debug_scores: NULL, or f32 [B*windows*heads, 144, 144]
- * receiving the biased, masked scores before the softmax (diagnostics). */
+ * least one must be given.  flags bit 0: the second version of the kernel (swin_window_attn_tc2.cu: the 16 tail rows of
+ * a window as a second row tile served by two warps with the main warps' code, conflict-free bias table, incremental
+ * unit decoding); bit 1 (needs bit 0): out16 is the compact operand __half [B,H,W,2C] = [hi | lo*2^11] that
+ * univs_gemm_f16x3_tc consumes (no hi*2^-11 block; any channel count).  debug_scores: NULL, or f32
+ * [B*windows*heads, 144, 144] receiving the biased, masked scores before the softmax (diagnostics). */
 int univs_swin_window_attention_tc(void* stream, const float* qkv, const float* qkv_bias, const float* rel_bias_table,
                                    int batch, int height, int width, int channels, int num_heads, int window, int shift,
                                    int flags, float* out, void* out16, float* debug_scores);

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "univs_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 SOURCES = ["common.cu", "groupnorm.cu", "swin_glue.cu", "decoder_glue.cu", "elementwise.cu", "msda.cu",
-           "swin_window_attn_tc.cu", "mha_tc.cu", "mask_einsum_mc.cu", "mask_einsum_tc.cu", "gemm_tc.cu",
+           "swin_window_attn_tc.cu", "swin_window_attn_tc2.cu", "mha_tc.cu", "mask_einsum_mc.cu", "mask_einsum_tc.cu", "gemm_tc.cu",
            "swin_window_attn.cu", "mha.cu", "mask_einsum.cu"]          # the last three: mma.sync / cp.async kernels
 HEADERS = ["common.cuh", "rowwise.cuh", "tc05_math.cuh"]      # tc05.cuh itself is replaced by tests/emu/tc05.cuh
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")

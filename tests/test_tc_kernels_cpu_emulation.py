@@ -46,20 +46,22 @@ def _rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
 
 
+@pytest.mark.parametrize("ver", [0, 1])      # flags bit 0: the second version of the kernel (two tail warps)
 @pytest.mark.parametrize("B,H,W,nH,shift,sms", [
     (1, 24, 24, 2, 0, 148),      # 8 units, one per CTA
     (2, 24, 36, 2, 6, 3),        # 24 units over 3 persistent CTAs: ring reuse, barrier phases beyond the first wrap
     (1, 20, 30, 1, 6, 2),        # padded grid (20x30 -> 24x36): pad tokens carry the bias only; shifted + masked windows
     (1, 12, 12, 3, 0, 1),        # a single window, three heads on one CTA
+    (2, 36, 48, 1, 6, 5),        # 24 units over 5 CTAs: a CTA's next window is 5 further (carries into the window row and the frame)
 ])
-def test_window_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, B, H, W, nH, shift, sms):
+def test_window_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, B, H, W, nH, shift, sms, ver):
     _use(monkeypatch, emu_lib_path, sms, tmp_path)
     g = torch.Generator().manual_seed(B * 1000 + H + shift)
     C = nH * 32
     qkv = torch.randn(B, H, W, 3 * C, generator=g)
     bias = torch.randn(3 * C, generator=g) * 0.2
     table = torch.randn(23 * 23, nH, generator=g) * 0.5
-    out, op = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, shift, want_f32=True, want_operand=True)
+    out, op = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, shift, want_f32=True, want_operand=True, flags=ver)
     want = ops_ref.swin_window_attention(qkv, bias, table, nH, 12, shift)
     assert _rel(out, want) < 5e-6
     # the fp16x3 operand of the projection GEMM [lo * 2^11 | hi * 2^-11 | hi]
@@ -68,17 +70,23 @@ def test_window_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, B, H, W
     assert _rel(rec, want) < 5e-6
     assert torch.equal(plain(out).half().float(), op[..., 2 * C:])
     # operand-only and fp32-only calls produce the same values
-    only16 = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, shift, want_f32=False, want_operand=True)[1]
+    only16 = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, shift, want_f32=False, want_operand=True, flags=ver)[1]
     assert torch.equal(plain(only16).float(), op)
+    if ver == 1:     # flags bit 1: the compact operand [hi | lo * 2^11] of the own GEMM
+        c16 = plain(ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, shift, want_f32=False, want_operand=True,
+                                                 flags=1, compact=True)[1]).float()
+        assert c16.shape[-1] == 2 * C
+        assert torch.equal(c16[..., :C], op[..., 2 * C:]) and torch.equal(c16[..., C:], op[..., :C])
 
 
-def test_window_attention_tc_score_dump(monkeypatch, emu_lib_path, tmp_path):
+@pytest.mark.parametrize("ver", [0, 1])
+def test_window_attention_tc_score_dump(monkeypatch, emu_lib_path, tmp_path, ver):
     """the staged diagnostic of tests/tools/win_tc_check.py: the debug dump holds the raw scores q.k * scale per unit"""
     _use(monkeypatch, emu_lib_path, 2, tmp_path)
     g = torch.Generator().manual_seed(3)
     nH, C = 1, 32
     qkv, bias, table = torch.randn(1, 12, 24, 3 * C, generator=g), torch.randn(3 * C, generator=g) * 0.2, torch.randn(529, nH, generator=g)
-    out, _, dbg = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, 0, debug_scores=True)
+    out, _, dbg = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, 0, debug_scores=True, flags=ver)
     want, scores = ops_ref.swin_window_attention(qkv, bias, table, nH, 12, 0, return_scores=True)
     assert _rel(out, want) < 5e-6
     assert plain(dbg).shape == (2, 144, 144)
@@ -175,13 +183,13 @@ def test_calibration_the_hardware_validated_einsum_kernel_runs_on_the_emulator(m
     assert 1e-5 < _rel(out, want) < 2e-3                     # and it IS the one-pass TF32 result, not fp32
 
 
-@pytest.mark.parametrize("kernel", ["window", "cross_attention", "cluster_einsum", "einsum"])
+@pytest.mark.parametrize("kernel", ["window", "window_v2", "cross_attention", "cluster_einsum", "einsum"])
 def test_tc_kernels_under_randomised_scheduling(monkeypatch, emu_lib_path, tmp_path, kernel):
     """UNIVS_EMU_CHAOS: random delays before every barrier operation / MMA issue / TMEM load / TMA copy of every thread, so
     producers, the MMA lane, softmax and epilogue warps overtake each other in unusual orders; results must not change"""
     monkeypatch.setenv("UNIVS_EMU_CHAOS", "300")
-    if kernel == "window":
-        test_window_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, 1, 24, 36, 1, 6, 1)
+    if kernel.startswith("window"):
+        test_window_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, 1, 24, 36, 1, 6, 1, int(kernel == "window_v2"))
     elif kernel == "cross_attention":
         test_cross_attention_tc_kernel(monkeypatch, emu_lib_path, tmp_path, 1, 150, 700, 1, 1, True, 0)
     elif kernel == "cluster_einsum":
@@ -207,14 +215,15 @@ def test_cross_attention_tc_kernel_edge_cases(monkeypatch, emu_lib_path, tmp_pat
         assert _rel(got, want) < 5e-6, (B, Lq, Lk, shared)
 
 
-def test_window_attention_tc_kernel_stage1_heads(monkeypatch, emu_lib_path, tmp_path):
+@pytest.mark.parametrize("ver", [0, 1])
+def test_window_attention_tc_kernel_stage1_heads(monkeypatch, emu_lib_path, tmp_path, ver):
     """Swin-L stage 1 head count (6 heads, C = 192), one shifted window row with padding in x"""
     _use(monkeypatch, emu_lib_path, 3, tmp_path)
     g = torch.Generator().manual_seed(5)
     nH, C = 6, 192
     qkv = torch.randn(1, 12, 20, 3 * C, generator=g)
     bias, table = torch.randn(3 * C, generator=g) * 0.2, torch.randn(529, nH, generator=g) * 0.5
-    out, _ = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, 6)
+    out, _ = ops.swin_window_attention_tc(dev(qkv), dev(bias), dev(table), nH, 6, flags=ver)
     assert _rel(out, ops_ref.swin_window_attention(qkv, bias, table, nH, 12, 6)) < 5e-6
 
 

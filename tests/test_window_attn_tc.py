@@ -108,13 +108,14 @@ def _rel(a, b):
 
 @pytest.mark.gpu
 @_gpu_wintc
+@pytest.mark.parametrize("ver", [0, 1])      # flags bit 0: the second version of the kernel (swin_window_attn_tc2.cu)
 @pytest.mark.parametrize("B,H,W,nH,shift", [
     (1, 12, 12, 1, 0),          # one unit
     (1, 24, 36, 2, 0), (2, 24, 27, 4, 6), (1, 46, 80, 6, 6),
     (3, 23, 40, 24, 6),         # more units than SMs: persistent loop, both ring stages, stage reuse
     (1, 92, 160, 12, 6),
 ])
-def test_window_attention_tc(B, H, W, nH, shift):
+def test_window_attention_tc(B, H, W, nH, shift, ver):
     from univs_b200 import ops
     torch.manual_seed(7)
     C = 32 * nH
@@ -123,7 +124,7 @@ def test_window_attention_tc(B, H, W, nH, shift):
     table = torch.randn(23 * 23, nH) * 0.5
     want, scores = ops_ref.swin_window_attention(qkv, bias, table, nH, 12, shift, return_scores=True)
     out, op, dbg = ops.swin_window_attention_tc(qkv.cuda(), bias.cuda(), table.cuda(), nH, shift, want_f32=True,
-                                                want_operand=True, debug_scores=True)
+                                                want_operand=True, debug_scores=True, flags=ver)
     torch.cuda.synchronize()
     assert _rel(dbg.view(scores.shape), scores) < 2e-5, "QK^T + bias + mask"
     assert _rel(out, want) < 2e-5, "softmax / PV / store"
@@ -134,6 +135,11 @@ def test_window_attention_tc(B, H, W, nH, shift):
     # against the validated mma.sync kernel: same arithmetic contract
     ref = ops.swin_window_attention(qkv.cuda(), bias.cuda(), table.cuda(), nH, 12, shift, precision=0)
     assert _rel(out, ref) < 2e-5
+    if ver == 1:     # flags bit 1: the compact operand [hi | lo * 2^11] the own GEMM reads (production variant of the kernel)
+        c16 = ops.swin_window_attention_tc(qkv.cuda(), bias.cuda(), table.cuda(), nH, shift, want_f32=False, want_operand=True,
+                                           flags=1, compact=True)[1].float()
+        assert c16.shape[-1] == 2 * C
+        assert torch.equal(c16[..., :C], opf[..., 2 * C:]) and torch.equal(c16[..., C:], opf[..., :C])
 
 
 # ---- data-flow model of the kernel (CPU) -----------------------------------------------------------------------------

@@ -20,12 +20,12 @@ def rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-def check(B, H, W, nH, shift):
+def check(B, H, W, nH, shift, ver=0):
     torch.manual_seed(1)
     C = 32 * nH
     qkv, bias, table = torch.randn(B, H, W, 3 * C), torch.randn(3 * C) * 0.3, torch.randn(529, nH) * 0.5
     want, scores = ops_ref.swin_window_attention(qkv, bias, table, nH, 12, shift, return_scores=True)
-    out, op, dbg = ops.swin_window_attention_tc(qkv.cuda(), bias.cuda(), table.cuda(), nH, shift, True, True, 0, True)
+    out, op, dbg = ops.swin_window_attention_tc(qkv.cuda(), bias.cuda(), table.cuda(), nH, shift, True, True, ver, True)
     torch.cuda.synchronize()
     dbg = dbg.view(scores.shape).cpu()
     e_s = rel(dbg, scores)
@@ -58,10 +58,11 @@ def timeit(fn, n=20):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--ver", type=int, default=0, help="kernel version (flags bit 0)")
     a = ap.parse_args()
     ok = True
-    for shp in [(1, 12, 12, 1, 0), (1, 24, 36, 2, 0), (2, 24, 27, 4, 6), (1, 46, 80, 6, 6), (3, 23, 40, 24, 6)]:
-        ok &= check(*shp)
+    for shp in [(1, 12, 12, 1, 0), (1, 24, 36, 2, 0), (2, 24, 27, 4, 6), (1, 46, 80, 6, 6), (3, 23, 40, 24, 6), (2, 36, 48, 1, 6)]:
+        ok &= check(*shp, ver=a.ver)
     print("PARITY", "ok" if ok else "FAILED")
     if a.time:
         for (H, W, nH) in [(184, 320, 6), (92, 160, 12), (46, 80, 24), (23, 40, 48)]:
@@ -69,7 +70,7 @@ if __name__ == "__main__":
             qkv = torch.randn(5, H, W, 3 * C, device="cuda")
             bias, table = torch.randn(3 * C, device="cuda"), torch.randn(529, nH, device="cuda")
             for shift in (0, 6):
-                t_tc = timeit(lambda: ops.swin_window_attention_tc(qkv, bias, table, nH, shift, False, True))
+                t_tc = timeit(lambda: ops.swin_window_attention_tc(qkv, bias, table, nH, shift, False, True, a.ver, compact=bool(a.ver)))
                 t_mma = timeit(lambda: ops.swin_window_attention_operand(qkv, bias, table, nH, 12, shift))
                 gb = qkv.numel() * 4 + qkv.numel() // 3 * 6
                 print(f"stage {H}x{W} heads={nH} shift={shift}: tcgen05 {t_tc:.3f} ms ({gb / t_tc / 1e6:.0f} GB/s)  "

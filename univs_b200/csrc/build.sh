@@ -7,7 +7,7 @@ mkdir -p "$out"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v)
 objs=()
-for f in common msda swin_window_attn swin_window_attn_tc mha mha_tc mask_einsum mask_einsum_tc mask_einsum_mc gemm_tc elementwise groupnorm swin_glue decoder_glue ${UNIVS_EXTRA_SRCS:-}; do
+for f in common msda swin_window_attn swin_window_attn_tc swin_window_attn_tc2 mha mha_tc mask_einsum mask_einsum_tc mask_einsum_mc gemm_tc elementwise groupnorm swin_glue decoder_glue ${UNIVS_EXTRA_SRCS:-}; do
   [ -f "$here/$f.cu" ] || continue
   "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$out/$f.o" 2> "$out/$f.ptxas.log" || { cat "$out/$f.ptxas.log"; exit 1; }
   sed -i '/Compile time = /d' "$out/$f.ptxas.log"      # keep the tracked resource-usage logs stable from build to build

@@ -597,6 +597,13 @@ static int launch(cudaStream_t st, const float* qkv, const float* bias, const fl
 }  // namespace wintc
 }  // namespace univs
 
+namespace univs {
+namespace wintc2 {   // swin_window_attn_tc2.cu: the second version of the kernel (flags bit 0)
+int launch(cudaStream_t st, const float* qkv, const float* bias, const float* table, int batch, int height, int width,
+           int channels, int num_heads, int shift, float* out, __half* out16, float* dbg, int compact);
+}
+}  // namespace univs
+
 using namespace univs;
 
 extern "C" int univs_swin_window_attention_tc(void* stream, const float* qkv, const float* qkv_bias,
@@ -609,9 +616,13 @@ extern "C" int univs_swin_window_attention_tc(void* stream, const float* qkv, co
   UNIVS_REQUIRE(num_heads > 0 && channels == num_heads * 32, "swin_window_attention_tc: head_dim must be 32 (channels=%d heads=%d)",
                 channels, num_heads);
   UNIVS_REQUIRE(shift >= 0 && shift < window, "swin_window_attention_tc: shift must be in [0, window)");
-  UNIVS_REQUIRE(out16 == nullptr || channels <= 1536, "swin_window_attention_tc: the operand output needs channels <= 1536");
-  UNIVS_REQUIRE(flags == 0, "swin_window_attention_tc: no flags are defined yet (got %d)", flags);
+  UNIVS_REQUIRE(out16 == nullptr || channels <= 1536 || (flags & 2), "swin_window_attention_tc: the operand output needs channels <= 1536");
+  UNIVS_REQUIRE((flags & ~3) == 0 && flags != 2,
+                "swin_window_attention_tc: unknown flags %d (bit 0: second kernel version; bit 1, with bit 0: compact operand)", flags);
   if (batch == 0) return UNIVS_OK;
+  if (flags & 1)
+    return wintc2::launch((cudaStream_t)stream, qkv, qkv_bias, rel_bias_table, batch, height, width, channels, num_heads, shift, out,
+                          reinterpret_cast<__half*>(out16), debug_scores, (flags >> 1) & 1);
   wintc::Geo g;
   g.B = batch; g.H = height; g.W = width; g.C = channels; g.nH = num_heads; g.shift = shift;
   g.Hp = (height + window - 1) / window * window;

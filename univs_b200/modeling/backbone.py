@@ -68,7 +68,7 @@ class _Block(nn.Module):
         bias = a.qkv.bias if a.qkv.bias is not None else x.new_zeros(qkv.shape[-1])
         if nn_ops.policy() == "fp16x3" and qkv.shape[-1] <= 3 * 1536:     # attention writes the GEMM operand itself
             ys = ops.swin_window_attention_operand(qkv, bias, a.relative_position_bias_table, self.heads, self.window,
-                                                   self.shift)
+                                                   self.shift, compact=nn_ops.gemm_tc())
             y = nn_ops.linear_prepped(ys, a.proj.weight, None)
         else:
             y = ops.swin_window_attention(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift)
@@ -88,7 +88,8 @@ class _Block(nn.Module):
             h = nn_ops.layernorm(x, self.norm1)[1]
         qkv = nn_ops.linear_prepped(h, a.qkv.weight, None)
         bias = a.qkv.bias if a.qkv.bias is not None else x.new_zeros(qkv.shape[-1])
-        ys = ops.swin_window_attention_operand(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift)
+        ys = ops.swin_window_attention_operand(qkv, bias, a.relative_position_bias_table, self.heads, self.window, self.shift,
+                                               compact=True)
         x = nn_ops.linear_residual(ys, a.proj.weight, a.proj.bias, x)
         h = nn_ops.layernorm(x, self.norm2)[1]
         x = nn_ops.mlp(h, self.mlp.fc1, self.mlp.fc2, residual=x)

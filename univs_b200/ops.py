@@ -158,17 +158,23 @@ def ms_deform_attn_encoder(value, spatial_shapes, level_start_index, offs_logits
     return out
 
 
-_win_tc = switches.get("WIN_TC")   # opt-in: 1 = tcgen05 kernel for 12x12 windows
+_win_tc = switches.get("WIN_TC")   # 1 = tcgen05 kernel for 12x12 windows, 2 = its second version (two tail warps; flags bit 0)
 
 
 def swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, want_f32=True, want_operand=False,
-                             flags=0, debug_scores=False):
+                             flags=None, debug_scores=False, compact=False):
     """12x12-window attention on the tcgen05 tensor cores (univs_swin_window_attention_tc).  Returns
-    (out f32 [B,H,W,C] | None, operand f16 [B,H,W,3C] | None[, scores f32 [units,144,144]])."""
+    (out f32 [B,H,W,C] | None, operand f16 [B,H,W,3C] | None[, scores f32 [units,144,144]]); with `compact` (second
+    kernel version only) the operand is [B,H,W,2C] = [hi | lo*2^11], the format the own GEMM reads."""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
+    if flags is None:
+        flags = 1 if _win_tc >= 2 else 0
+    compact = bool(compact) and bool(flags & 1)
+    if compact:
+        flags |= 2
     out = torch.empty((B, H, W, C), device=qkv.device, dtype=torch.float32) if want_f32 else None
-    op = torch.empty((B, H, W, 3 * C), device=qkv.device, dtype=torch.float16) if want_operand else None
+    op = torch.empty((B, H, W, (2 if compact else 3) * C), device=qkv.device, dtype=torch.float16) if want_operand else None
     dbg = None
     if debug_scores:
         units = B * (-(-H // 12)) * (-(-W // 12)) * num_heads
@@ -188,7 +194,7 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     if _win_tc and window == 12 and (_default_precision if precision is None else precision) == PREC_TF32X3:
-        return swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, flags=0)[0]
+        return swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift)[0]
     out = torch.empty((B, H, W, C), device=qkv.device, dtype=torch.float32)
     with _Bracket("swin_window_attention", 1):
         rc = lib().univs_swin_window_attention_f32(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
@@ -199,14 +205,15 @@ def swin_window_attention(qkv, qkv_bias, rel_bias_table, num_heads, window, shif
     return out
 
 
-def swin_window_attention_operand(qkv, qkv_bias, rel_bias_table, num_heads, window, shift):
+def swin_window_attention_operand(qkv, qkv_bias, rel_bias_table, num_heads, window, shift, compact=False):
     """Strict-precision window attention emitting the fp16x3 GEMM operand directly: fp16 [B,H,W,3C] =
-    [lo*2^11 | hi*2^-11 | hi] (the A operand of the projection GEMM; C <= 1536)."""
+    [lo*2^11 | hi*2^-11 | hi] (the A operand of the projection GEMM; C <= 1536).  `compact` (the consumer is the own
+    GEMM): [B,H,W,2C] = [hi | lo*2^11] where the kernel in use can write it (callers tell the two apart by the width)."""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     if _win_tc and window == 12:
         return swin_window_attention_tc(qkv, qkv_bias, rel_bias_table, num_heads, shift, want_f32=False,
-                                        want_operand=True, flags=0)[1]
+                                        want_operand=True, compact=compact)[1]
     out = torch.empty((B, H, W, 3 * C), device=qkv.device, dtype=torch.float16)
     with _Bracket("swin_window_attention", 1):
         rc = lib().univs_swin_window_attention_f16x3out(_stream(), _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias"),
