@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # window attention v2 (two tail warps): parity + timing against v1
 set -u
-out=gpurun_out/r2_call28
+out=gpurun_out/r2_call30
 mkdir -p "$out"
 run() { local name=$1 secs=$2; shift 2
   echo "=== $name: $*" | tee -a "$out/summary.txt"

@@ -19,7 +19,7 @@ if "win" in what or "winmma" in what:
     bias, table = torch.randn(3 * C, device="cuda"), torch.randn(529, nH, device="cuda")
     for shift in (0, 6):
         if "win" in what:
-            ops.swin_window_attention_tc(qkv, bias, table, nH, shift, False, True)   # version: UNIVS_WIN_TC
+            ops.swin_window_attention_tc(qkv, bias, table, nH, shift, False, True, compact=True)   # version: UNIVS_WIN_TC
         if "winmma" in what:
             ops.swin_window_attention_operand(qkv, bias, table, nH, 12, shift)
 if "mha" in what:

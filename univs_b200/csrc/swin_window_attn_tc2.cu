@@ -135,9 +135,15 @@ __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const float* __
   }
   const int c = head * 32 + lane8 * 4;
   Unit un = first_unit(g);
+  int slot_v = slot;
   for (int it = 0; it < count; ++it, next_unit(un, g)) {
     const int s = it & 1;
     unsigned char* st = smem + (size_t)s * kStageBytes;
+    // the per-pass window coordinates of this thread's tokens are loop invariants the compiler would keep (and, with 96
+    // registers of loads in flight, spill: no L1 is left beside the shared memory, so a spill costs an L2 round trip --
+    // the first build spent 40 % of the loaders' time there); recomputing them per unit is a handful of integer operations
+    asm volatile("" : "+r"(slot_v));
+    const int slot = slot_v;
     float4 q[kLoaderPasses], k[kLoaderPasses], v[kLoaderPasses];
 #pragma unroll
     for (int p = 0; p < kLoaderPasses; ++p) {        // the loads do not depend on the stage being free: issue them first
@@ -428,21 +434,23 @@ __device__ void softmax_loop(unsigned char* smem, uint64_t* bars, uint32_t tmem_
   const int head = (int)(blockIdx.x % (unsigned)g.nH);
   const int G = (int)gridDim.x;
   int u = (int)blockIdx.x;
-  if (u >= units) return;
   Unit un = first_unit(g);
-  float sum_cur = softmax_unit<GENERIC>(smem, bars, tmem_base, rc, g, un, 0, u, dbg);
-  int src_cur = rc.live() ? source_token(g, un, rc.row()) : -1;
-  for (int n = 0; u < units; ++n, u += G) {
-    float sum_nxt = 0.f;
-    int src_nxt = -1;
-    if (u + G < units) {
+  float sum_prev = 0.f;
+  int src_prev = -1;
+  // iteration n: softmax of unit n (if there is one), then the epilogue of unit n-1 -- one inlined copy of each body
+  for (int n = 0;; ++n, u += G) {
+    float sum = 0.f;
+    int src = -1;
+    const bool more = u < units;
+    if (more) {
+      sum = softmax_unit<GENERIC>(smem, bars, tmem_base, rc, g, un, n, u, dbg);
+      src = rc.live() ? source_token(g, un, rc.row()) : -1;
       next_unit(un, g);
-      sum_nxt = softmax_unit<GENERIC>(smem, bars, tmem_base, rc, g, un, n + 1, u + G, dbg);
-      src_nxt = rc.live() ? source_token(g, un, rc.row()) : -1;
     }
-    epilogue_unit<GENERIC>(smem, bars, tmem_base, rc, g, src_cur, head, n, sum_cur, out, out16, compact);
-    src_cur = src_nxt;
-    sum_cur = sum_nxt;
+    if (n > 0) epilogue_unit<GENERIC>(smem, bars, tmem_base, rc, g, src_prev, head, n - 1, sum_prev, out, out16, compact);
+    if (!more) break;
+    src_prev = src;
+    sum_prev = sum;
   }
 }
 
