@@ -8,9 +8,9 @@
 // partials; that mma.sync kernel stays the path for Lq > 256 (the Q*T self-attention) and the cross-check of this one.
 //
 // One CTA = (batch b, head h, key split z); it walks its key blocks of 128 keys.  Work unit n = (key block, query row
-// tile): 128 query rows x 128 keys.  448 threads, warp-specialised like swin_window_attn_tc.cu:
-//   warps 10-13 loaders : Q once (scaled by 32^-0.5, rows >= Lq zero), then K / V blocks (contiguous 128-byte head slices,
-//                         16 x 128-bit loads in flight per thread), split fp32 -> fp16 hi + lo, K-major SWIZZLE_64B tiles,
+// tile): 128 query rows x 128 keys.  384 threads, warp-specialised like swin_window_attn_tc.cu:
+//   warps 9-11 loaders  : Q once (scaled by 32^-0.5, rows >= Lq zero), then K / V blocks (contiguous 128-byte head slices,
+//                         22 x 128-bit loads in flight per thread), split fp32 -> fp16 hi + lo, K-major SWIZZLE_64B tiles,
 //                         3-stage ring (one stage = one key block, used by both row tiles)
 //   warp 8      MMA     : S = Ql Kh^T + Qh Kl^T + Qh Kh^T (M=128, N=128, K=32), O_blk = Pl Vh + Ph Vl + Ph Vh (M=128, N=32,
 //                         K=128, V through the MN-major B descriptor)
@@ -19,7 +19,7 @@
 //                         64-thread named barrier), writes P relative to the NEW running max (so P <= 1) and, one unit
 //                         later, folds the block's O (read back with tcgen05.ld) into its running output in registers:
 //                         o = o * exp(m_old - m_new) + O_blk.  No correction pass over TMEM is needed.
-//   warp 9      TMEM allocator (256 columns: S [0,128), O_blk [128,160)).
+//   warp 8 also allocates TMEM (256 columns: S [0,128), O_blk [128,160)).
 // Pipelining: softmax warps run softmax(n+1) -> merge(n), the MMA lane S(n+1) -> PV(n); consecutive units alternate
 // between the two row tiles, so the running state touched by softmax(n+1) and merge(n) is disjoint.
 // HBM-bound by design: K and V are read once per (frame, head) = 2 * S * 128 B; everything else is on chip.
@@ -32,11 +32,16 @@ namespace mhatc {
 
 using namespace tc;
 
-constexpr int kThreads = 448;
+// 12 warps: warps are allocated in groups of four, so the 14 warps of the first version were budgeted like 16 (128 registers
+// per thread) and the softmax warps' running state (two row tiles x {m, l, alpha, o[16]} beside 64 scores) spilled ~20 values
+// per unit pair -- with 197 KB of shared memory there is no L1 left, so every spill is an L2 round trip.  384 threads get 168.
+constexpr int kThreads = 384;
 constexpr int kMmaWarp = 8;
-constexpr int kAllocWarp = 9;
-constexpr int kLoaderWarp0 = 10;
-constexpr int kLoaderThreads = 128;
+constexpr int kAllocWarp = 8;
+constexpr int kLoaderWarp0 = 9;
+constexpr int kLoaderThreads = 96;
+constexpr int kLoaderRows = kLoaderThreads / 8;                         // rows per pass: 12
+constexpr int kKvPasses = (128 + kLoaderRows - 1) / kLoaderRows;        // 11 (the last one covers 8 rows)
 constexpr int kBlk = 128;                        // keys per block
 constexpr int kStages = 3;
 constexpr int kMaxLq = 256;
@@ -100,20 +105,20 @@ __device__ __forceinline__ void store_row_vt(unsigned char* tile_h, unsigned cha
 template <bool VT>
 __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const Args& a, int b, int h, int kb_begin, int kb_end) {
   const int lt = threadIdx.x - kLoaderWarp0 * 32;
-  const int lane8 = lt & 7, slot = lt >> 3;       // 16 rows per pass
+  const int lane8 = lt & 7, slot = lt >> 3;       // kLoaderRows rows per pass
   const int C = a.C;
   const float scale = 0.17677669529663687f;      // 32^-0.5
   {
     const float* qbase = a.q + (size_t)b * a.Lq * C + h * 32 + lane8 * 4;
 #pragma unroll 4
-    for (int p = 0; p < kMaxLq / 16; ++p) {
-      const int r = p * 16 + slot;
+    for (int p = 0; p < (kMaxLq + kLoaderRows - 1) / kLoaderRows; ++p) {
+      const int r = p * kLoaderRows + slot;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < a.Lq) {
         x = ldg_f4(qbase + (size_t)r * C);
         x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
       }
-      store_row(smem + kOffQh, smem + kOffQl, r, lane8, x);     // rows 128-255 continue into the second tile
+      if (r < kMaxLq) store_row(smem + kOffQh, smem + kOffQl, r, lane8, x);     // rows 128-255 continue into the second tile
     }
     fence_proxy_async_smem();
     mbar_arrive(&bars[Q_FULL]);
@@ -125,21 +130,25 @@ __device__ void loader_loop(unsigned char* smem, uint64_t* bars, const Args& a, 
     const int s = it % kStages, use = it / kStages;
     if (use > 0) mbar_wait(&bars[KV_EMPTY + s], (uint32_t)((use - 1) & 1), KV_EMPTY + s);
     unsigned char* st = smem + kOffKV + (size_t)s * kStageBytes;
-    float4 kk[8], vv[8];
+    float4 kk[kKvPasses], vv[kKvPasses];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int key = kb * kBlk + p * 16 + slot;
+    for (int p = 0; p < kKvPasses; ++p) {
+      const int row = p * kLoaderRows + slot;
+      const int key = kb * kBlk + row;
       kk[p] = vv[p] = make_float4(0.f, 0.f, 0.f, 0.f);       // keys >= Lk: masked in the softmax, V must still be finite
-      if (key < a.Lk) {
+      if (row < kBlk && key < a.Lk) {
         kk[p] = ldg_f4(kbase + (size_t)key * C);
         vv[p] = ldg_f4(vbase + (size_t)key * C);
       }
     }
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      store_row(st, st + kTile, p * 16 + slot, lane8, kk[p]);
-      if (VT) store_row_vt(st + 2 * kTile, st + 3 * kTile, p * 16 + slot, lane8, vv[p]);
-      else store_row(st + 2 * kTile, st + 3 * kTile, p * 16 + slot, lane8, vv[p]);
+    for (int p = 0; p < kKvPasses; ++p) {
+      const int row = p * kLoaderRows + slot;
+      if (row < kBlk) {
+        store_row(st, st + kTile, row, lane8, kk[p]);
+        if (VT) store_row_vt(st + 2 * kTile, st + 3 * kTile, row, lane8, vv[p]);
+        else store_row(st + 2 * kTile, st + 3 * kTile, row, lane8, vv[p]);
+      }
     }
     fence_proxy_async_smem();
     mbar_arrive(&bars[KV_FULL + s]);
@@ -409,7 +418,9 @@ __global__ void __launch_bounds__(kThreads, 1) mha_tc_kernel(const Args a) {
     mbar_init(&bars[O_FULL], 1);
     mbar_init(&bars[O_FREE], 8);
     mbar_init_fence();
-  } else if (warp == kAllocWarp) {
+  }
+  if (warp == kAllocWarp) {
+    __syncwarp();
     tmem_alloc(tmem_slot, 256);
   }
   fence_before();
