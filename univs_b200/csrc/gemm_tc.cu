@@ -199,7 +199,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&rm)[kCh], const 
 template <int ACT, bool OUT32, bool OUT16, bool ADD, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
-                     const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const Args a) {
+                     const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                     const __grid_constant__ Args a) {   // __grid_constant__: tap_off[] is indexed at run time -- from the constant bank, not a local copy
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int kStages = Ring<PAIR>::kStages, kStageBytes = Ring<PAIR>::kStageBytes, kNumBars = Ring<PAIR>::kNumBars;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ring<PAIR>::kOffBars);
@@ -248,10 +249,10 @@ gemm_f16x3_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_co
       for (int item = item0; item < num_items; item += item_step) {
         const int tt = item / n_cu, cu = item - tt * n_cu;
         const int ct = PAIR ? 2 * cu + rank : cu;          // pair, odd n_ct: ct == n_ct reads an out-of-range (zero-filled) weight tile
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int tap = kb / a.kpt;
-          const int xk = (kb - tap * a.kpt) * kBK;           // activation column of this k-block
+        for (int kb = 0, tap = 0, kin = 0; kb < kblocks; ++kb) {      // k-block kb = k-block kin of tap `tap`
+          const int xk = kin * kBK;                          // activation column of this k-block
           const int xr = tt * kBT + a.tap_off[tap];          // first activation row
+          if (++kin == a.kpt) { kin = 0; ++tap; }
           mbar_wait(&empty[stage], phase ^ 1, 10 + stage);
           const uint32_t s0 = smem_u32(smem + (size_t)stage * kStageBytes);
           // a box always counts in full (out-of-range parts are zero-filled)
