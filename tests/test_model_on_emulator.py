@@ -120,7 +120,7 @@ def test_clip_forward_with_all_switches_on_the_emulator(monkeypatch, tmp_path, p
     monkeypatch.setattr(ops, "_ws_cache", {})
     monkeypatch.setattr(ops, "_gn_ws", {})
     monkeypatch.setattr(nn_ops, "_pad_cache", {})
-    monkeypatch.setattr(ops, "_win_tc", 1)                # tcgen05 window attention
+    monkeypatch.setattr(ops, "_win_tc", 2)                # tcgen05 window attention (production version: compact operand)
     monkeypatch.setattr(ops, "_mha_tc", 1)                # tcgen05 attention core ...
     monkeypatch.setattr(ops, "MHA_TC_MIN_KEYS", 1)        # ... for the small key counts of this geometry too
     monkeypatch.setattr(ops, "_msda_tile", 8)             # tiled MSDeformAttn

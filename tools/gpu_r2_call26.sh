@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # ncu source-level capture of window attention v2
 set -u
-out=gpurun_out/r2_call29
+out=gpurun_out/r2_call34
 mkdir -p "$out"
 export UNIVS_WIN_TC=2
 timeout 300 ncu --clock-control none --set full --import-source on -k "regex:swin_window_attn_tc12v2" -s 1 -c 1 -o "$out/wintc2" python tools/prof_targets.py win > "$out/wintc2.log" 2>&1
