@@ -156,7 +156,9 @@ _PATCH = {"layernorm": _layernorm,
               ops_ref.patchify_normalize(f, m, s, padded, patch), split),
           "layernorm_merge2x2": lambda x, w, b, eps=1e-5, split=None: _maybe_split(
               ops_ref.layernorm_merge2x2(x, w, b, eps), split),
-          "swin_window_attention_operand": lambda q, b, t, nh, ws, sh: _split16(_swin(q, b, t, nh, ws, sh), True),
+          # `compact` asks for the [hi | lo'] container where the kernel in use can write it; the consumer tells the two
+          # containers apart by their width, so the oracle keeps the K-chunk one
+          "swin_window_attention_operand": lambda q, b, t, nh, ws, sh, compact=False: _split16(_swin(q, b, t, nh, ws, sh), True),
           "gelu": lambda x, split=None, bias=None: _maybe_split(torch.nn.functional.gelu(x if bias is None else x + bias), split),
           "relu": lambda x, split=None, bias=None: _maybe_split(torch.relu(x if bias is None else x + bias), split),
           "split_tf32": _split,
