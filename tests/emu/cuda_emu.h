@@ -229,6 +229,11 @@ inline cudaError_t launch_ex(const cudaLaunchConfig_t& cfg, const std::function<
 }
 }  // namespace emu
 template <typename R, typename... A>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, R (*)(A...), int, size_t) {
+  *n = 2;
+  return cudaSuccess;
+}
+template <typename R, typename... A>
 inline cudaError_t cudaOccupancyMaxActiveClusters(int* n, R (*)(A...), const cudaLaunchConfig_t*) {
   *n = ::emu::emulated_sm_count() / 2;
   return cudaSuccess;

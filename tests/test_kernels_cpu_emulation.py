@@ -255,13 +255,14 @@ def test_pooled_mask_features_and_direct_bits(emu):
 
 def test_rowwise_v2_kernels_are_bit_identical_on_the_emulator(emu_lib_path, monkeypatch, tmp_path):
     """UNIVS_ROWWISE_V2 is read once per library instance: a second copy of the emulated library runs the v2 kernels
-    (bit 0: 8-wide GELU / ReLU / split, bit 1: wide-store LayerNorm); outputs must equal the validated kernels' bytes"""
+    (bit 0: 8-wide GELU / ReLU / split, bit 1: wide-store LayerNorm, bit 2: streaming LayerNorm of the plain compact-operand
+    case); outputs must equal the validated kernels' bytes"""
     v2_path = str(tmp_path / "libunivs_emu_v2.so")
     shutil.copy(emu_lib_path, v2_path)
     monkeypatch.setattr(ops, "_stream", lambda: 0)
     g = torch.Generator().manual_seed(8)
     cases = []
-    for rows, C in [(1, 8), (37, 48), (19, 192), (6, 768), (3, 2048)]:
+    for rows, C in [(1, 8), (37, 48), (19, 192), (6, 768), (3, 2048), (83, 384)]:      # 83 rows: several rows per warp in the streaming kernel
         x = torch.randn(rows, C, generator=g) * 3
         x[0, 0] = 70000.0                               # saturates the fp16 hi part
         cases.append((x, torch.randn(C, generator=g), torch.randn(C, generator=g), torch.randn(C, generator=g),
@@ -281,13 +282,17 @@ def test_rowwise_v2_kernels_are_bit_identical_on_the_emulator(emu_lib_path, monk
     monkeypatch.setenv("UNIVS_ROWWISE_V2", "0")
     monkeypatch.setattr(_cabi, "_lib", _load(emu_lib_path))
     base = run()
-    monkeypatch.setenv("UNIVS_ROWWISE_V2", "3")
-    monkeypatch.setattr(_cabi, "_lib", _load(v2_path))
-    v2 = run()
-    assert len(base) == len(v2) == 90
-    for a, b in zip(base, v2):
-        assert a.dtype == b.dtype and a.shape == b.shape
-        assert torch.equal(a.contiguous().view(torch.int16), b.contiguous().view(torch.int16))
+    for bits in ("3", "7"):
+        path = str(tmp_path / f"libunivs_emu_v{bits}.so")
+        shutil.copy(emu_lib_path, path)
+        monkeypatch.setenv("UNIVS_ROWWISE_V2", bits)
+        monkeypatch.setenv("UNIVS_EMU_SMS", "2")          # few resident blocks: the streaming kernel's warps walk several rows
+        monkeypatch.setattr(_cabi, "_lib", _load(path))
+        v2 = run()
+        assert len(base) == len(v2) == 108
+        for a, b in zip(base, v2):
+            assert a.dtype == b.dtype and a.shape == b.shape
+            assert torch.equal(a.contiguous().view(torch.int16), b.contiguous().view(torch.int16)), bits
 
 
 # ------------------------------------------------------------------ the mma.sync / cp.async kernels (validated on the B200)

@@ -19,7 +19,7 @@ sys.path.insert(0, sys.argv[2])
 from univs_b200 import ops
 torch.manual_seed(0)
 out = {}
-for rows, C in [(1, 8), (37, 48), (1000, 192), (4600, 768), (333, 6144), (7, 2048)]:
+for rows, C in [(1, 8), (37, 48), (1000, 192), (4600, 768), (333, 6144), (7, 2048), (30001, 384)]:
     x = (torch.randn(rows, C, device="cuda") * 3).contiguous()
     x[0, 0] = 70000.0          # saturates the fp16 hi part
     b = torch.randn(C, device="cuda")
@@ -42,13 +42,14 @@ torch.save(out, sys.argv[1])
 def test_rowwise_v2_bit_identical():
     with tempfile.TemporaryDirectory() as d:
         res = {}
-        for v2 in ("0", "3"):          # 3 = bit 0 (GELU / ReLU / split) + bit 1 (wide-store LayerNorm)
+        for v2 in ("0", "3", "7"):     # 3 = bit 0 (GELU / ReLU / split) + bit 1 (wide-store LayerNorm); 7 = + bit 2 (streaming LayerNorm)
             path = os.path.join(d, f"v{v2}.pt")
             env = dict(os.environ, UNIVS_ROWWISE_V2=v2)
             subprocess.run([sys.executable, "-c", _CHILD, path, ROOT], check=True, env=env, timeout=600)
             res[v2] = torch.load(path)
-    assert res["0"].keys() == res["3"].keys() and len(res["0"]) == 54 + 45
-    for k in res["0"]:
-        a, b = res["0"][k], res["3"][k]
-        assert a.dtype == b.dtype and a.shape == b.shape, k
-        assert torch.equal(a.contiguous().view(torch.int16), b.contiguous().view(torch.int16)), k
+    assert res["0"].keys() == res["3"].keys() == res["7"].keys() and len(res["0"]) == 63 + 54
+    for v2 in ("3", "7"):
+        for k in res["0"]:
+            a, b = res["0"][k], res[v2][k]
+            assert a.dtype == b.dtype and a.shape == b.shape, k
+            assert torch.equal(a.contiguous().view(torch.int16), b.contiguous().view(torch.int16)), (v2, k)

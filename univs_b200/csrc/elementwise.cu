@@ -154,12 +154,13 @@ gelu_split8_kernel(const float* __restrict__ x, const float* __restrict__ bias, 
   }
 }
 
-// UNIVS_ROWWISE_V2: bit 0 = 8-wide GELU / ReLU / split kernel, bit 1 = wide-store LayerNorm ("1", "2" or "3")
+// UNIVS_ROWWISE_V2: bit 0 = 8-wide GELU / ReLU / split kernel, bit 1 = wide-store LayerNorm, bit 2 = streaming LayerNorm for
+// the plain compact-operand case ("0" .. "7")
 static int rowwise_v2_bits() {
   static int bits = -1;
   if (bits < 0) {
     const char* e = getenv("UNIVS_ROWWISE_V2");
-    bits = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+    bits = (e != nullptr && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : 0;
   }
   return bits;
 }
@@ -263,6 +264,84 @@ layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ res
   }
 }
 
+// Streaming LayerNorm (opt-in: UNIVS_ROWWISE_V2 bit 2) for the case the Swin blocks of the default path launch 48 times per
+// clip: no residual, no fp32 sum, compact operand output [hi | lo*2^11].  layernorm_wide_kernel gives every warp ONE row and
+// lets the block retire (36800 blocks at Swin-L stage 1): a warp's life is load -> two dependent warp reductions -> stores, so
+// half of the resident warps are not loading at any time and the launch runs at 3.7 TB/s (ncu launch list, all four stages).
+// Here a warp walks rows with a grid stride and loads its NEXT row before it reduces the current one (two rows in flight per
+// warp, no block turnover).  Per row the arithmetic is layernorm_wide_kernel's, element for element and in the same order:
+// the results are bit-identical.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_stream_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        long long rows, int C, float eps, __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int nv = C >> 2;  // float4 per row (even: C % 8 == 0)
+  const long long stride = (long long)gridDim.x * 8;
+  long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  float4 v[MAXV], vn[MAXV];
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + i * 32;
+      vn[i] = idx < nv ? *reinterpret_cast<const float4*>(x + row * C + idx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  for (; row < rows; row += stride) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      v[i] = vn[i];
+      if (lane + i * 32 < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const long long nxt = row + stride;
+    if (nxt < rows) {
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nv) vn[i] = *reinterpret_cast<const float4*>(x + nxt * C + idx * 4);
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + i * 32 < nv) {
+        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + i * 32;
+      const bool has = idx < nv;                       // the same for both lanes of a pair (nv is even)
+      uint32_t hi[2] = {0u, 0u}, lo[2] = {0u, 0u};
+      if (has) {
+        const float4 gm = ldg_f4(gamma + idx * 4), bt = ldg_f4(beta + idx * 4);
+        float o[4];
+        o[0] = (v[i].x - mean) * rstd * gm.x + bt.x;
+        o[1] = (v[i].y - mean) * rstd * gm.y + bt.y;
+        o[2] = (v[i].z - mean) * rstd * gm.z + bt.z;
+        o[3] = (v[i].w - mean) * rstd * gm.w + bt.w;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          hi[e] = pack_sat_h2(o[2 * e], o[2 * e + 1]);
+          const float2 hf = unpack_h2(hi[e]);
+          lo[e] = pack_sat_h2((o[2 * e] - hf.x) * 2048.f, (o[2 * e + 1] - hf.y) * 2048.f);
+        }
+      }
+      const uint32_t nh0 = __shfl_down_sync(0xffffffffu, hi[0], 1), nh1 = __shfl_down_sync(0xffffffffu, hi[1], 1);
+      const uint32_t nl0 = __shfl_down_sync(0xffffffffu, lo[0], 1), nl1 = __shfl_down_sync(0xffffffffu, lo[1], 1);
+      if (has && (lane & 1) == 0) {
+        __half* o16 = out + (size_t)row * (2 * (size_t)C) + idx * 4;
+        *reinterpret_cast<uint4*>(o16) = make_uint4(hi[0], hi[1], nh0, nh1);
+        *reinterpret_cast<uint4*>(o16 + C) = make_uint4(lo[0], lo[1], nl0, nl1);
+      }
+    }
+  }
+}
+
 // returns true when the v2 kernel took the launch
 static bool launch_split8(cudaStream_t st, const float* x, const float* bias, int64_t rows, int C, float* out, int mode, int split) {
   if (!rowwise_v2_enabled() || split >= 0 || C % 8 != 0) return false;
@@ -296,6 +375,34 @@ extern "C" int univs_layernorm_f32(void* stream, const float* x, const float* re
                 "layernorm: split chunk must divide channels");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rowwise_v2_bits() & 4) && split == -3 && residual == nullptr && sum_out == nullptr && channels % 8 == 0 && channels <= 1024 &&
+      (((uintptr_t)x | (uintptr_t)out) & 15) == 0) {
+    __half* o16 = reinterpret_cast<__half*>(out);
+    // every block resident (occupancy x SMs), so that each warp walks several rows and its prefetch pays
+#define LNS_LAUNCH(MV)                                                                                                  \
+  do {                                                                                                                  \
+    static int resident = 0;                                                                                            \
+    if (!resident) {                                                                                                    \
+      int per_sm = 0, dev = 0, sms = 0;                                                                                 \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_stream_kernel<MV>, 256, 0) != cudaSuccess || \
+          cudaGetDevice(&dev) != cudaSuccess ||                                                                         \
+          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || per_sm <= 0 || sms <= 0) { \
+        cudaGetLastError();                                                                                             \
+        per_sm = 2;                                                                                                     \
+        sms = 148;                                                                                                      \
+      }                                                                                                                 \
+      resident = per_sm * sms;                                                                                          \
+    }                                                                                                                   \
+    const unsigned sgrid = grid < (unsigned)resident ? grid : (unsigned)resident;                                       \
+    layernorm_stream_kernel<MV><<<sgrid, 256, 0, st>>>(x, gamma, beta, rows, channels, eps, o16);                       \
+  } while (0)
+    if (channels <= 128) LNS_LAUNCH(1);
+    else if (channels <= 256) LNS_LAUNCH(2);
+    else if (channels <= 512) LNS_LAUNCH(4);
+    else LNS_LAUNCH(8);
+#undef LNS_LAUNCH
+    return check_launch("layernorm_stream");
+  }
   if ((rowwise_v2_bits() & 2) && split < 0 && channels % 8 == 0 && (split == -2 || split == -3 || (-split) % 8 == 0) &&
       (((uintptr_t)x | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)sum_out) & 15) == 0) {
     __half* o16 = reinterpret_cast<__half*>(out);
