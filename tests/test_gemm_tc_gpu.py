@@ -123,4 +123,4 @@ def test_fused_conv_taps_on_device(N, H, W, Cin, Cout, k, monkeypatch):
         nn_ops.set_gemm_tc(old_tc)
         set_precision(old)
     assert _rel(outs[True], want) < 5e-6 and _rel(outs[False], want) < 5e-6
-    assert _rel(outs[True], outs[False]) < 4e-6      # two fp32 accumulation orders of the same products
+    assert _rel(outs[True], outs[False]) < 6e-6      # two fp32 accumulation orders of the same products (each within 5e-6 of float64)
